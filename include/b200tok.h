@@ -1,0 +1,227 @@
+/*
+ * b200tok.h — C ABI of the B200-native tokenizer hot path (libb200tok.so).
+ *
+ * This is the boundary an OpenVINO-side `ov::Op::evaluate()` (or any other host) binds to.  Each
+ * entry point replaces one reference `evaluate()` body and takes the reference's own decomposed
+ * tensors — `(begins:i32, ends:i32, chars:u8)` strings, with `(ragged_begins:i32[B], ragged_ends:i32[B])`
+ * in front for ragged tensors (reference src/utils.cpp:84-102) — as plain pointers + sizes.
+ *
+ *   b200tok_regexsplit_*   replaces RegexSplit::evaluate          src/regex_split.cpp:124-324
+ *   b200tok_bpe_*          replaces BPETokenizer::evaluate        src/bpe_tokenizer.cpp:47-164
+ *                          (+ BPETokenizerImpl ctor :341-388, tokenize_into :196-339)
+ *   b200tok_wordpiece_*    replaces WordpieceTokenizer::evaluate  src/wordpiece_tokenizer.cpp:49-133
+ *   b200tok_vocabenc_*     replaces VocabEncoder::evaluate_impl   src/vocab_encoder.cpp:56-94
+ *   b200tok_vocabdec_*     replaces VocabDecoder::evaluate        src/vocab_decoder.cpp:23-87
+ *   b200tok_bytefallback_run replaces ByteFallback::evaluate      src/byte_fallback.cpp:16-50
+ *   b200tok_split_bpe_run / b200tok_split_wordpiece_run  fuse RegexSplit(+RegexSplit) -> tokenizer
+ *                          in one kernel (pieces never leave shared memory); same results as the
+ *                          two ops run back to back.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative B200TOK_E_* code; the message is available
+ *     from b200tok_last_error() (thread-local).  Nothing throws across this boundary; the ov::Op
+ *     shim rethrows as ov::Exception (reference error convention: OPENVINO_ASSERT/THROW).
+ *   - `*_create` corresponds to the reference's lazy first-call initialisation (std::call_once in
+ *     evaluate): it reads the Constant inputs once and builds device-resident tables.
+ *   - Handles may be used from several threads; `*_run` calls on one handle are serialised inside.
+ *   - `mem` says where the data pointers of a run live: B200TOK_MEM_HOST (pageable or pinned host
+ *     memory, as ov::Tensor::data() gives; the library stages H2D/D2H itself and returns when the
+ *     outputs are complete) or B200TOK_MEM_DEVICE (device pointers on the handle's GPU; work is
+ *     enqueued on `stream`).
+ *   - Output buffers are caller-allocated at the reference's own worst-case sizes (noted per op) and
+ *     the number of produced elements is returned, mirroring `set_shape(worst) ... set_shape(actual)`.
+ *   - There is no CPU fallback: without a usable sm_100 device `*_create` fails with B200TOK_E_CUDA.
+ */
+#ifndef B200TOK_H_
+#define B200TOK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TOK_API __attribute__((visibility("default")))
+
+#define B200TOK_OK 0
+#define B200TOK_E_INVALID (-1)     /* bad argument / malformed tensors                                 */
+#define B200TOK_E_CUDA (-2)        /* CUDA runtime error or no device                                   */
+#define B200TOK_E_CAPACITY (-3)    /* caller's output buffer is smaller than the result                 */
+#define B200TOK_E_UNSUPPORTED (-4) /* e.g. a split pattern the GPU splitter does not recognise          */
+#define B200TOK_E_VOCAB (-5)       /* merge refers to a token missing from the vocab (ref: vocab.at())  */
+
+#define B200TOK_MEM_HOST 0
+#define B200TOK_MEM_DEVICE 1
+
+typedef struct b200tok_object* b200tok_handle;
+
+/* A decomposed string tensor (host memory; used for Constant inputs at create time). */
+typedef struct {
+    const int32_t* begins;
+    const int32_t* ends;
+    const uint8_t* chars;
+    int64_t n;        /* number of strings  */
+    int64_t n_chars;  /* length of `chars`  */
+} b200tok_strings;
+
+/* A ragged string tensor = inputs [0..4] of RegexSplit / BPETokenizer / WordpieceTokenizer
+ * (+ optional input [5] `skips` of the 7-input RegexSplit form, src/regex_split.cpp:193-199). */
+typedef struct {
+    const int32_t* ragged_begins;  /* [n_rows]  */
+    const int32_t* ragged_ends;    /* [n_rows]  */
+    int64_t n_rows;
+    const int32_t* begins;         /* [n_elems] */
+    const int32_t* ends;           /* [n_elems] */
+    int64_t n_elems;
+    const uint8_t* chars;          /* [n_chars] */
+    int64_t n_chars;
+    const uint8_t* skips;          /* [n_elems] bool, or NULL */
+    int mem;                       /* B200TOK_MEM_*  */
+} b200tok_ragged_strings;
+
+/* Ragged string result (RegexSplit outputs [0..3] and [5]; `chars` is aliased by the op,
+ * src/regex_split.cpp:203).  Worst case n_elems + n_chars elements (src/regex_split.cpp:182). */
+typedef struct {
+    int32_t* ragged_begins;  /* [n_rows]   */
+    int32_t* ragged_ends;    /* [n_rows]   */
+    int32_t* begins;         /* [capacity] */
+    int32_t* ends;           /* [capacity] */
+    uint8_t* skips;          /* [capacity] or NULL */
+    int64_t capacity;
+    int64_t n_elems;         /* out: produced elements */
+    int64_t n_rows;          /* out: rows written (1 for the whole-batch-empty shortcut, src/regex_split.cpp:129-143) */
+    int mem;
+} b200tok_ragged_strings_out;
+
+/* Ragged i32 result (BPETokenizer / WordpieceTokenizer outputs [0..2]).  Worst case n_chars ids
+ * (src/bpe_tokenizer.cpp:135, src/wordpiece_tokenizer.cpp:86). */
+typedef struct {
+    int32_t* begins;    /* [n_rows]   */
+    int32_t* ends;      /* [n_rows]   */
+    int32_t* ids;       /* [capacity] */
+    int64_t capacity;
+    int64_t n_ids;      /* out: produced ids (host value; valid on return unless n_ids_device is used) */
+    int64_t* n_ids_device; /* MEM_DEVICE only, optional: if non-NULL the count is written here on the device
+                              and the call does not synchronise the stream (fully asynchronous)        */
+    int mem;
+} b200tok_ragged_ids;
+
+/* ------------------------------------------------------------------------------------------ */
+B200TOK_API int b200tok_version(void);
+B200TOK_API const char* b200tok_last_error(void);
+B200TOK_API int b200tok_device_count(void);
+B200TOK_API void b200tok_destroy(b200tok_handle h);     /* any handle kind */
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+B200TOK_API int64_t b200tok_launch_count(b200tok_handle h);
+
+/* ---- RegexSplit ----------------------------------------------------------------------------
+ * attributes: behaviour / invert / max_splits (src/regex_split.hpp:42-47); pattern = input [5|6].
+ * The GPU splitter hand-codes the tokenizer patterns the reference converter emits (GPT-2
+ * byte-level, its individual-digits variant, Llama-3/cl100k, BERT whitespace, BERT punctuation,
+ * `\w+|[^\w\s]+`, single-literal metaspace, `.`); any other pattern => B200TOK_E_UNSUPPORTED. */
+typedef struct {
+    const char* pattern;
+    int64_t pattern_len;
+    const char* behaviour;   /* "remove" | "isolate" | "contiguous" | "mergedwithprevious" | "mergedwithnext" */
+    int invert;
+    int max_splits;          /* -1 or > 0 */
+    int device;              /* CUDA device ordinal */
+} b200tok_regexsplit_desc;
+B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* desc, b200tok_handle* out);
+B200TOK_API int b200tok_regexsplit_run(b200tok_handle h, const b200tok_ragged_strings* in,
+                                       b200tok_ragged_strings_out* out, void* cuda_stream);
+
+/* ---- BPETokenizer --------------------------------------------------------------------------
+ * Constant inputs [5..] of the 11/14/15/18-input forms (src/bpe_tokenizer.cpp:18-21,69-114):
+ * merges_right.begins == NULL selects the "L R" string form (11/15 inputs); added.n == 0 means
+ * no added-token inputs.  Attributes as in src/bpe_tokenizer.hpp:220-228. */
+typedef struct {
+    b200tok_strings vocab;
+    b200tok_strings merges_left;
+    b200tok_strings merges_right;
+    b200tok_strings added_tokens;
+    const int32_t* added_ids;
+    const char* unk_token;        int64_t unk_token_len;
+    const char* suffix_indicator; int64_t suffix_indicator_len;   /* stored, unused (as in the reference) */
+    const char* end_suffix;       int64_t end_suffix_len;
+    int fuse_unk;
+    int byte_fallback;
+    int64_t cache_capacity;       /* accepted for IR compatibility; the GPU path has no result cache */
+    int device;
+} b200tok_bpe_desc;
+B200TOK_API int b200tok_bpe_create(const b200tok_bpe_desc* desc, b200tok_handle* out);
+B200TOK_API int b200tok_bpe_run(b200tok_handle h, const b200tok_ragged_strings* in, b200tok_ragged_ids* out,
+                                void* cuda_stream);
+/* Fused RegexSplit -> BPETokenizer (what the converted gpt2 / Llama-3 IRs chain back to back). */
+B200TOK_API int b200tok_split_bpe_run(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
+                                      b200tok_ragged_ids* out, void* cuda_stream);
+
+/* ---- WordpieceTokenizer --------------------------------------------------------------------
+ * inputs [5..7] vocab, [8] unk_token_id; attributes suffix_indicator / max_bytes_per_word
+ * (src/wordpiece_tokenizer.hpp:41-45). */
+typedef struct {
+    b200tok_strings vocab;
+    const char* suffix_indicator; int64_t suffix_indicator_len;
+    int max_bytes_per_word;
+    int device;
+} b200tok_wordpiece_desc;
+B200TOK_API int b200tok_wordpiece_create(const b200tok_wordpiece_desc* desc, b200tok_handle* out);
+B200TOK_API int b200tok_wordpiece_run(b200tok_handle h, const b200tok_ragged_strings* in, int32_t unk_token_id,
+                                      b200tok_ragged_ids* out, void* cuda_stream);
+/* Fused RegexSplit(\s+, remove) -> RegexSplit(punct, isolate) -> WordpieceTokenizer (BERT IR);
+ * `split2` may be NULL for a single splitter. */
+B200TOK_API int b200tok_split_wordpiece_run(b200tok_handle split1, b200tok_handle split2, b200tok_handle wordpiece,
+                                            const b200tok_ragged_strings* in, int32_t unk_token_id,
+                                            b200tok_ragged_ids* out, void* cuda_stream);
+
+/* ---- VocabEncoder --------------------------------------------------------------------------
+ * inputs [3..5] keys, [6] values (i32 or i64), [7] default (src/vocab_encoder.cpp:56-94). */
+typedef struct {
+    b200tok_strings keys;
+    const void* values;     /* int32_t* or int64_t* */
+    int values_are_i64;
+    int device;
+} b200tok_vocabenc_desc;
+B200TOK_API int b200tok_vocabenc_create(const b200tok_vocabenc_desc* desc, b200tok_handle* out);
+/* begins/ends: [n]; out: [n] of the value type. */
+B200TOK_API int b200tok_vocabenc_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n,
+                                     const uint8_t* chars, int64_t n_chars, int64_t default_value,
+                                     void* out_values, int mem, void* cuda_stream);
+
+/* ---- VocabDecoder (+ fused ByteFallback) -----------------------------------------------------
+ * inputs [1..3] vocab; skip tokens come per call (input [4]) or from the attribute
+ * (src/vocab_decoder.cpp:36-41). */
+typedef struct {
+    b200tok_strings vocab;
+    int device;
+} b200tok_vocabdec_desc;
+typedef struct {
+    int32_t* ragged_begins;  /* [batch]              */
+    int32_t* ragged_ends;    /* [batch]              */
+    int32_t* begins;         /* [batch*max(seq,1)]   */
+    int32_t* ends;           /* [batch*max(seq,1)]   */
+    uint8_t* chars;          /* [chars_capacity]     */
+    int64_t chars_capacity;
+    int64_t n_chars;         /* out */
+    int mem;
+} b200tok_decoded;
+B200TOK_API int b200tok_vocabdec_create(const b200tok_vocabdec_desc* desc, b200tok_handle* out);
+/* ids: i32[batch, seq].  byte_fallback != 0 additionally applies ByteFallback to every decoded
+ * token in the same pass (VocabDecoder -> ByteFallback as chained by the detokenizer IR). */
+B200TOK_API int b200tok_vocabdec_run(b200tok_handle h, const int32_t* ids, int64_t batch, int64_t seq,
+                                     const int32_t* skip_tokens, int64_t n_skip, int byte_fallback,
+                                     b200tok_decoded* out, int ids_mem, void* cuda_stream);
+/* Upper bound for chars_capacity for a [batch,seq] call (batch*seq*longest vocab entry). */
+B200TOK_API int64_t b200tok_vocabdec_max_chars(b200tok_handle h, int64_t batch, int64_t seq);
+
+/* ---- ByteFallback (stand-alone op; stateless) -------------------------------------------------
+ * in/out: strings [n]; out_chars worst case n_chars (src/byte_fallback.cpp:25). */
+B200TOK_API int b200tok_bytefallback_run(int device, const int32_t* begins, const int32_t* ends, int64_t n,
+                                         const uint8_t* chars, int64_t n_chars,
+                                         int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                         int64_t* out_n_chars, int mem, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TOK_H_ */

@@ -1,0 +1,247 @@
+"""ctypes wrapper over liboracle.so — TEST INFRASTRUCTURE ONLY (see oracle.cpp header).
+
+All arrays are numpy, laid out exactly as the reference ops see them (decomposed strings:
+``begins:i32, ends:i32, chars:u8``; ragged: ``ragged_begins:i32[B], ragged_ends:i32[B]`` in front,
+reference src/utils.cpp:84-102).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "liboracle.so"
+
+__all__ = [
+    "build", "lib", "pcre2_available", "BpeOracle", "WordpieceOracle", "SplitOracle", "VocabEncoderOracle",
+    "vocab_decoder", "byte_fallback",
+]
+
+
+def build(force: bool = False) -> Path:
+    """Compile liboracle.so with the committed Makefile (gcc only; no reference sources involved)."""
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < (_HERE / "oracle.cpp").stat().st_mtime:
+        subprocess.check_call(["make", "-C", str(_HERE), "-s", "-B", "liboracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            build()
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.orc_bpe_create.restype = C.c_void_p
+        _lib.orc_wp_create.restype = C.c_void_p
+        _lib.orc_split_create.restype = C.c_void_p
+        _lib.orc_venc_create.restype = C.c_void_p
+        for f in ("orc_bpe_run", "orc_wp_run", "orc_split_run", "orc_vdec_run", "orc_bytefallback_run"):
+            getattr(_lib, f).restype = C.c_int64
+    return _lib
+
+
+def _p(a, typ):
+    if a is None:
+        return C.cast(None, typ)
+    return a.ctypes.data_as(typ)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    if isinstance(a, (bytes, bytearray)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def pcre2_available() -> bool:
+    return bool(lib().orc_pcre2_available())
+
+
+class BpeOracle:
+    """BPETokenizer (reference src/bpe_tokenizer.cpp).  ``merges_right=None`` selects the "L R" string form."""
+
+    def __init__(self, vocab, merges_left, merges_right=None, added=None, added_ids=None, *, unk_token=b"",
+                 fuse_unk=False, end_suffix=b"", byte_fallback=False, cache_capacity=20000, use_cache=True):
+        L = lib()
+        vb, ve, vc = (_i32(vocab[0]), _i32(vocab[1]), _u8(vocab[2]))
+        lb, le, lc = (_i32(merges_left[0]), _i32(merges_left[1]), _u8(merges_left[2]))
+        if merges_right is not None:
+            rb, re_, rc = (_i32(merges_right[0]), _i32(merges_right[1]), _u8(merges_right[2]))
+        else:
+            rb = re_ = rc = None
+        if added is not None:
+            ab, ae, ac = (_i32(added[0]), _i32(added[1]), _u8(added[2]))
+            aid = _i32(added_ids)
+            A = len(aid)
+        else:
+            ab = ae = ac = aid = None
+            A = 0
+        unk = _u8(unk_token)
+        es = _u8(end_suffix)
+        self._keep = (vb, ve, vc, lb, le, lc, rb, re_, rc, ab, ae, ac, aid, unk, es)
+        self._h = C.c_void_p(L.orc_bpe_create(
+            _p(vb, _i32p), _p(ve, _i32p), _p(vc, _u8p), C.c_int64(len(vb)),
+            _p(lb, _i32p), _p(le, _i32p), _p(lc, _u8p),
+            _p(rb, _i32p), _p(re_, _i32p), _p(rc, _u8p), C.c_int64(len(lb)),
+            _p(ab, _i32p), _p(ae, _i32p), _p(ac, _u8p), _p(aid, _i32p), C.c_int64(A),
+            _p(unk, _u8p), C.c_int64(len(unk)), C.c_int(int(fuse_unk)),
+            _p(es, _u8p), C.c_int64(len(es)), C.c_int(int(byte_fallback)),
+            C.c_int64(cache_capacity), C.c_int(int(use_cache))))
+        if not self._h:
+            raise ValueError("oracle: BPE table construction failed (merge refers to a missing token)")
+
+    def clear_cache(self):
+        lib().orc_bpe_clear_cache(self._h)
+
+    def __call__(self, rb, re_, begins, ends, chars, threads=1):
+        rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+        B = len(rb)
+        cap = max(int(np.sum(np.maximum(ends - begins, 0))) * 2 + 16, len(chars) + 16)
+        ob, oe = np.empty(B, np.int32), np.empty(B, np.int32)
+        ids = np.empty(cap, np.int32)
+        T = lib().orc_bpe_run(self._h, _p(rb, _i32p), _p(re_, _i32p), C.c_int64(B), _p(begins, _i32p), _p(ends, _i32p),
+                              _p(chars, _u8p), _p(ob, _i32p), _p(oe, _i32p), _p(ids, _i32p), C.c_int64(cap), C.c_int(threads))
+        assert T >= 0
+        return ob, oe, ids[:T].copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_bpe_destroy(self._h)
+            self._h = None
+
+
+class WordpieceOracle:
+    """WordpieceTokenizer (reference src/wordpiece_tokenizer.cpp:49-133)."""
+
+    def __init__(self, vocab, suffix_indicator=b"##", max_bytes_per_word=100):
+        vb, ve, vc = (_i32(vocab[0]), _i32(vocab[1]), _u8(vocab[2]))
+        sfx = _u8(suffix_indicator)
+        self._h = C.c_void_p(lib().orc_wp_create(_p(vb, _i32p), _p(ve, _i32p), _p(vc, _u8p), C.c_int64(len(vb)),
+                                                 _p(sfx, _u8p), C.c_int64(len(sfx)), C.c_int(max_bytes_per_word)))
+
+    def __call__(self, rb, re_, begins, ends, chars, unk_id, threads=1):
+        rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+        B = len(rb)
+        cap = len(chars) + len(begins) + 16
+        ob, oe = np.empty(B, np.int32), np.empty(B, np.int32)
+        ids = np.empty(cap, np.int32)
+        T = lib().orc_wp_run(self._h, _p(rb, _i32p), _p(re_, _i32p), C.c_int64(B), _p(begins, _i32p), _p(ends, _i32p),
+                             _p(chars, _u8p), C.c_int32(unk_id), _p(ob, _i32p), _p(oe, _i32p), _p(ids, _i32p),
+                             C.c_int64(cap), C.c_int(threads))
+        assert T >= 0
+        return ob, oe, ids[:T].copy()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_wp_destroy(self._h)
+            self._h = None
+
+
+class SplitOracle:
+    """RegexSplit (reference src/regex_split.cpp:124-324) on the system PCRE2 (UTF|UCP, JIT)."""
+
+    def __init__(self, pattern, behaviour="remove", invert=False, max_splits=-1, skip_tokens=None):
+        if not pcre2_available():
+            raise RuntimeError("oracle: libpcre2-8.so.0 not found")
+        pat = _u8(pattern.encode() if isinstance(pattern, str) else pattern)
+        if skip_tokens is not None:
+            sb, se, sc = _i32(skip_tokens[0]), _i32(skip_tokens[1]), _u8(skip_tokens[2])
+            ns = len(sb)
+        else:
+            sb = se = sc = None
+            ns = 0
+        self._h = C.c_void_p(lib().orc_split_create(_p(pat, _u8p), C.c_int64(len(pat)), behaviour.lower().encode(),
+                                                    C.c_int(int(invert)), C.c_int(max_splits),
+                                                    _p(sb, _i32p), _p(se, _i32p), _p(sc, _u8p), C.c_int64(ns)))
+        if not self._h:
+            raise ValueError(f"oracle: cannot compile pattern / unknown behaviour {behaviour!r}")
+
+    def __call__(self, rb, re_, begins, ends, chars, skips=None, threads=1):
+        """Returns (rb', re', begins', ends', skips').  chars is passed through by the op (aliased)."""
+        rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+        B = len(rb)
+        if len(chars) == 0:  # regex_split.cpp:129-143
+            z = np.zeros(1, np.int32)
+            return z, z.copy(), begins, ends, (None if skips is None else np.asarray(skips, np.uint8))
+        sk = None if skips is None else _u8(np.asarray(skips, dtype=np.uint8))
+        cap = len(chars) + len(begins) + 16
+        orb, ore = np.empty(B, np.int32), np.empty(B, np.int32)
+        ob, oe, osk = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.uint8)
+        P = lib().orc_split_run(self._h, _p(rb, _i32p), _p(re_, _i32p), C.c_int64(B), _p(begins, _i32p), _p(ends, _i32p),
+                                _p(chars, _u8p), C.c_int64(len(chars)), _p(sk, _u8p),
+                                _p(orb, _i32p), _p(ore, _i32p), _p(ob, _i32p), _p(oe, _i32p), _p(osk, _u8p),
+                                C.c_int64(cap), C.c_int(threads))
+        assert P >= 0
+        return orb, ore, ob[:P].copy(), oe[:P].copy(), osk[:P].copy()
+
+    def fullmatch_cp(self, cp: int) -> bool:
+        return bool(lib().orc_regex_fullmatch_cp(self._h, C.c_uint32(cp)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_split_destroy(self._h)
+            self._h = None
+
+
+class VocabEncoderOracle:
+    """VocabEncoder (reference src/vocab_encoder.cpp:56-94)."""
+
+    def __init__(self, keys, values):
+        vb, ve, vc = _i32(keys[0]), _i32(keys[1]), _u8(keys[2])
+        vals = np.ascontiguousarray(values, dtype=np.int64)
+        self._h = C.c_void_p(lib().orc_venc_create(_p(vb, _i32p), _p(ve, _i32p), _p(vc, _u8p), _p(vals, _i64p),
+                                                   C.c_int64(len(vb))))
+
+    def __call__(self, begins, ends, chars, default_value):
+        begins, ends, chars = _i32(begins), _i32(ends), _u8(chars)
+        out = np.empty(len(begins), np.int64)
+        lib().orc_venc_run(self._h, _p(begins, _i32p), _p(ends, _i32p), _p(chars, _u8p), C.c_int64(len(begins)),
+                           C.c_int64(default_value), _p(out, _i64p))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_venc_destroy(self._h)
+            self._h = None
+
+
+def vocab_decoder(ids, vocab, skip_tokens=()):
+    """VocabDecoder (reference src/vocab_decoder.cpp:23-87).  ids: i32[B,S]."""
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    B, S = ids.shape
+    vb, ve, vc = _i32(vocab[0]), _i32(vocab[1]), _u8(vocab[2])
+    skip = _i32(np.asarray(list(skip_tokens), dtype=np.int32))
+    n = B * max(S, 1)
+    maxlen = int((ve - vb).max()) if len(vb) else 0
+    cap = n * maxlen + 16
+    rb, re_ = np.empty(B, np.int32), np.empty(B, np.int32)
+    ob, oe = np.empty(n, np.int32), np.empty(n, np.int32)
+    oc = np.empty(cap, np.uint8)
+    N = lib().orc_vdec_run(_p(ids, _i32p), C.c_int64(B), C.c_int64(S), _p(vb, _i32p), _p(ve, _i32p), _p(vc, _u8p),
+                           C.c_int64(len(vb)), _p(skip, _i32p), C.c_int64(len(skip)),
+                           _p(rb, _i32p), _p(re_, _i32p), _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p), C.c_int64(cap))
+    assert N >= 0
+    return rb, re_, ob, oe, oc[:N].copy()
+
+
+def byte_fallback(begins, ends, chars):
+    """ByteFallback (reference src/byte_fallback.cpp:16-50)."""
+    begins, ends, chars = _i32(begins), _i32(ends), _u8(chars)
+    ob, oe = np.empty(len(begins), np.int32), np.empty(len(begins), np.int32)
+    oc = np.empty(len(chars) + 16, np.uint8)
+    N = lib().orc_bytefallback_run(_p(begins, _i32p), _p(ends, _i32p), _p(chars, _u8p), C.c_int64(len(begins)),
+                                   _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p))
+    return ob, oe, oc[:N].copy()
