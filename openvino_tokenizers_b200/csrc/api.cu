@@ -1,0 +1,748 @@
+// api.cu — the C ABI declared in include/b200tok.h: handle lifecycle, device tables, workspaces,
+// kernel launches, host<->device staging.  No CPU compute path exists in this library.
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200tok.h"
+#include "kernels.cuh"
+#include "kernels_misc.cuh"
+#include "tables.hpp"
+
+using namespace b200tok;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x)                                                                                              \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) return fail(B200TOK_E_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t n) {   // grow-only; contents are not preserved
+        if (n <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = std::max<size_t>(n + n / 8 + 64, 256);
+        return cudaMalloc(&p, cap * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& v, cudaStream_t s = 0) {
+        cudaError_t e = ensure(std::max<size_t>(v.size(), 1));
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+struct DevTrie {
+    DBuf<int32_t> first, value, edge_child, root_child;
+    DBuf<uint8_t> edge_byte;
+    cudaError_t upload(const HostTrie& h) {
+        cudaError_t e;
+        if ((e = first.upload(h.first))) return e;
+        if ((e = value.upload(h.value))) return e;
+        if ((e = edge_child.upload(h.edge_child))) return e;
+        if ((e = root_child.upload(h.root_child))) return e;
+        return edge_byte.upload(h.edge_byte);
+    }
+    FlatTrie view() const { return FlatTrie{first.p, value.p, edge_byte.p, edge_child.p, root_child.p}; }
+};
+
+struct DevClassTables {
+    DBuf<uint8_t> ascii, stage2;
+    DBuf<uint16_t> stage1;
+    cudaError_t upload() {
+        const HostClassTables& h = host_class_tables();
+        cudaError_t e;
+        if ((e = ascii.upload(h.ascii))) return e;
+        if ((e = stage1.upload(h.stage1))) return e;
+        return stage2.upload(h.stage2);
+    }
+    ClassTables view() const { return ClassTables{ascii.p, stage1.p, stage2.p}; }
+};
+
+// Scratch shared by the row kernels of one handle (grow-only, reused across calls).
+struct RowWorkspace {
+    DBuf<int32_t> rb, re, begins, ends;
+    DBuf<uint8_t> chars, skips;
+    DBuf<int32_t> row_cap, row_base, row_ext, row_cnt, out_begins, out_ends;
+    DBuf<uint8_t> row_flag;
+    DBuf<int32_t> tmp_a, tmp_b, out_a, out_b;
+    DBuf<uint8_t> tmp_c, out_c;
+    DBuf<GiantItem> giants;
+    DBuf<uint8_t> pool, cub_tmp;
+    DBuf<int32_t> status;
+    DBuf<unsigned long long> pool_used;
+    DBuf<int64_t> total;
+    int32_t* h_status = nullptr;   // pinned
+    cudaStream_t stream = nullptr;
+    size_t giants_cap = 4096;
+    size_t pool_bytes = 8u << 20;
+    ~RowWorkspace() {
+        if (h_status) cudaFreeHost(h_status);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+enum Kind { K_SPLIT = 1, K_BPE, K_WORDPIECE, K_VOCABENC, K_VOCABDEC };
+
+}  // namespace
+
+struct b200tok_object {
+    int kind = 0;
+    int device = 0;
+    int sm_count = 148;
+    std::mutex mu;
+    int64_t launches = 0;
+    DevClassTables cls;
+    RowWorkspace ws;
+    virtual ~b200tok_object() {}
+};
+
+namespace {
+
+struct SplitObj : b200tok_object { HostSplit h; };
+struct BpeObj : b200tok_object {
+    HostBpe h;
+    DBuf<int32_t> byte_sym, byte_miss;
+    DevTrie trie;
+    DBuf<MergeSlot> slots;
+    DBuf<uint8_t> suffix;
+    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, trie.view(), MergeTable{slots.p, h.mask}}; }
+};
+struct WordpieceObj : b200tok_object {
+    HostWordpiece h;
+    DevTrie root, sub;
+    WordpieceTables view() const { return WordpieceTables{root.view(), sub.view(), h.max_bytes}; }
+};
+struct VocabEncObj : b200tok_object {
+    HostVocabEnc h;
+    bool i64 = false;
+    DBuf<VocabEncSlot> slots;
+    DBuf<uint8_t> key_bytes;
+    DBuf<int32_t> begins, ends;
+    DBuf<uint8_t> chars, out;
+};
+struct VocabDecObj : b200tok_object {
+    int64_t V = 0;
+    int32_t max_len = 0;
+    DBuf<int32_t> vb, ve;
+    DBuf<uint8_t> vc;
+    DBuf<int16_t> bf_byte;
+    DBuf<int32_t> ids, skip, len, begins, ends, rb, re, status;
+    DBuf<uint8_t> chars, cub_tmp;
+    DBuf<int64_t> total;
+};
+
+int init_object(b200tok_object* o, int kind, int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(B200TOK_E_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= n) return fail(B200TOK_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    o->kind = kind;
+    o->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    o->sm_count = prop.multiProcessorCount;
+    return B200TOK_OK;
+}
+
+int ensure_ws(b200tok_object* o) {
+    RowWorkspace& w = o->ws;
+    if (!w.stream) CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    if (!w.h_status) CU(cudaMallocHost(&w.h_status, 64));
+    CU(w.status.ensure(ST_WORDS));
+    CU(w.pool_used.ensure(1));
+    CU(w.total.ensure(1));
+    return B200TOK_OK;
+}
+
+struct RowCall {
+    int op;                       // OP_*
+    const SplitObj* split = nullptr;   // may be null (PAT_NONE)
+    const SplitObj* split2 = nullptr;
+    BpeObj* bpe = nullptr;
+    WordpieceObj* wp = nullptr;
+    int32_t unk_id = 0;
+};
+
+int validate_in(const b200tok_ragged_strings* in) {
+    if (!in) return fail(B200TOK_E_INVALID, "null input");
+    if (in->n_rows < 0 || in->n_elems < 0 || in->n_chars < 0) return fail(B200TOK_E_INVALID, "negative sizes");
+    if (in->n_rows > 0 && (!in->ragged_begins || !in->ragged_ends)) return fail(B200TOK_E_INVALID, "missing ragged offsets");
+    if (in->n_elems > 0 && (!in->begins || !in->ends)) return fail(B200TOK_E_INVALID, "missing string offsets");
+    if (in->n_chars > 0 && !in->chars) return fail(B200TOK_E_INVALID, "missing chars");
+    if (in->n_chars >= (1ll << 31) - (1 << 20) || in->n_elems >= (1ll << 31) - (1 << 20)) return fail(B200TOK_E_INVALID, "int32 offsets: batch too large");
+    if (in->mem != B200TOK_MEM_HOST && in->mem != B200TOK_MEM_DEVICE) return fail(B200TOK_E_INVALID, "bad mem kind");
+    return B200TOK_OK;
+}
+
+// The shared driver of the row kernels.  `owner` provides workspace / class tables / launch counter.
+// Token ops write (begins, ends, ids); the split op writes (rb', re', begins', ends', skips').
+int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_strings* in,
+             b200tok_ragged_ids* out_ids, b200tok_ragged_strings_out* out_split, void* user_stream) {
+    int rc = validate_in(in);
+    if (rc) return rc;
+    DeviceGuard guard(owner->device);
+    std::lock_guard<std::mutex> lock(owner->mu);
+    if ((rc = ensure_ws(owner))) return rc;
+    RowWorkspace& w = owner->ws;
+    const bool host = in->mem == B200TOK_MEM_HOST;
+    const int out_mem = out_ids ? out_ids->mem : out_split->mem;
+    if (out_mem != in->mem) return fail(B200TOK_E_INVALID, "input and output must live in the same memory kind");
+    cudaStream_t st = user_stream ? (cudaStream_t)user_stream : w.stream;
+    const int64_t B = in->n_rows, E = in->n_elems, N = in->n_chars;
+    const bool is_split = call.op == OP_SPLIT;
+
+    if (B == 0) {
+        if (out_ids) { out_ids->n_ids = 0; if (out_ids->n_ids_device) CU(cudaMemsetAsync(out_ids->n_ids_device, 0, 8, st)); }
+        if (out_split) { out_split->n_elems = 0; out_split->n_rows = 0; }
+        return B200TOK_OK;
+    }
+
+    // ---- inputs on the device ----
+    const int32_t *d_rb, *d_re, *d_b, *d_e;
+    const uint8_t *d_c, *d_sk = nullptr;
+    if (host) {
+        CU(w.rb.ensure(B)); CU(w.re.ensure(B)); CU(w.begins.ensure(E + 1)); CU(w.ends.ensure(E + 1)); CU(w.chars.ensure(N + 64));
+        CU(cudaMemcpyAsync(w.rb.p, in->ragged_begins, B * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(w.re.p, in->ragged_ends, B * 4, cudaMemcpyHostToDevice, st));
+        if (E) CU(cudaMemcpyAsync(w.begins.p, in->begins, E * 4, cudaMemcpyHostToDevice, st));
+        if (E) CU(cudaMemcpyAsync(w.ends.p, in->ends, E * 4, cudaMemcpyHostToDevice, st));
+        if (N) CU(cudaMemcpyAsync(w.chars.p, in->chars, N, cudaMemcpyHostToDevice, st));
+        if (in->skips && E) { CU(w.skips.ensure(E)); CU(cudaMemcpyAsync(w.skips.p, in->skips, E, cudaMemcpyHostToDevice, st)); d_sk = w.skips.p; }
+        d_rb = w.rb.p; d_re = w.re.p; d_b = w.begins.p; d_e = w.ends.p; d_c = w.chars.p;
+    } else {
+        d_rb = in->ragged_begins; d_re = in->ragged_ends; d_b = in->begins; d_e = in->ends; d_c = in->chars; d_sk = in->skips;
+    }
+
+    // ---- parameters ----
+    RowParams P{};
+    P.rb = d_rb; P.re = d_re; P.n_rows = (int32_t)B; P.begins = d_b; P.ends = d_e; P.chars = d_c; P.n_chars = (int32_t)N; P.skips = d_sk;
+    P.spec = SplitSpec{}; P.spec.pat = PAT_NONE; P.mode = SPLIT_ISOLATED; P.invert = 0; P.max_splits = -1; P.repeat = 0;
+    if (call.split) {
+        const HostSplit& hs = call.split->h;
+        P.spec = hs.spec; P.mode = hs.mode; P.invert = hs.invert; P.max_splits = hs.max_splits; P.repeat = hs.repeat;
+        if (call.split2) {
+            const HostSplit& h2 = call.split2->h;
+            const bool bert = hs.spec.pat == PAT_WS && hs.mode == SPLIT_REMOVED && !hs.invert && hs.max_splits == -1 &&
+                              h2.spec.pat == PAT_BERT_PUNCT && h2.mode == SPLIT_ISOLATED && h2.max_splits == -1;
+            if (!bert) return fail(B200TOK_E_UNSUPPORTED, "fused two-splitter path supports RegexSplit(\\s+, remove) -> RegexSplit(bert punctuation, isolate) only");
+            P.spec.pat = PAT_BERT_FUSED;
+        }
+        if (!is_split && (hs.mode >= SPLIT_MERGED_PREV || hs.max_splits != -1))
+            return fail(B200TOK_E_UNSUPPORTED, "fused split+tokenize supports remove/isolate behaviours without max_splits; run the two ops separately");
+    }
+    P.cls = owner->cls.view();
+    int per_elem_extra = 1;
+    if (call.op == OP_BPE) {
+        P.bpe = call.bpe->view();
+        P.suffix_len = (int32_t)call.bpe->h.end_suffix.size();
+        per_elem_extra = P.suffix_len;
+    } else if (call.op == OP_WORDPIECE) {
+        P.wp = call.wp->view();
+        P.unk_id = call.unk_id;
+    }
+    const int64_t tmp_cap = N + E * per_elem_extra + 1;
+    if (tmp_cap >= (1ll << 31)) return fail(B200TOK_E_INVALID, "batch too large for int32 offsets");
+
+    CU(w.row_cap.ensure(B)); CU(w.row_base.ensure(B)); CU(w.row_ext.ensure(B)); CU(w.row_cnt.ensure(B)); CU(w.row_flag.ensure(B));
+    CU(w.tmp_a.ensure(tmp_cap));
+    if (is_split) { CU(w.tmp_b.ensure(tmp_cap)); CU(w.tmp_c.ensure(tmp_cap)); }
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)B, st);
+    CU(w.cub_tmp.ensure(cub_bytes + 256));
+
+    // ---- outputs on the device ----
+    int32_t *d_ob, *d_oe, *d_oa, *d_obb = nullptr;
+    uint8_t* d_oc = nullptr;
+    int64_t out_cap;
+    if (out_ids) {
+        out_cap = out_ids->capacity;
+        if (host) {
+            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap));
+            d_ob = w.out_begins.p; d_oe = w.out_ends.p; d_oa = w.out_a.p;
+            out_cap = std::min<int64_t>(out_cap, tmp_cap);
+        } else { d_ob = out_ids->begins; d_oe = out_ids->ends; d_oa = out_ids->ids; }
+    } else {
+        out_cap = out_split->capacity;
+        if (host) {
+            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap)); CU(w.out_b.ensure(tmp_cap)); CU(w.out_c.ensure(tmp_cap));
+            d_ob = w.out_begins.p; d_oe = w.out_ends.p; d_oa = w.out_a.p; d_obb = w.out_b.p; d_oc = out_split->skips ? w.out_c.p : nullptr;
+            out_cap = std::min<int64_t>(out_cap, tmp_cap);
+        } else { d_ob = out_split->ragged_begins; d_oe = out_split->ragged_ends; d_oa = out_split->begins; d_obb = out_split->ends; d_oc = out_split->skips; }
+    }
+    if (!d_ob || !d_oe || (!d_oa && out_cap > 0)) return fail(B200TOK_E_INVALID, "missing output buffers");
+
+    const size_t smem = 128 + 1024 + WARPS_PER_BLOCK * sizeof(WarpSmem);
+    static bool attr_set[3][64] = {};
+    const int nthreads = 256;
+    const int rows_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * 3);
+    const bool async = out_ids && !host && out_ids->n_ids_device;
+
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CU(cudaMemsetAsync(w.status.p, 0, ST_WORDS * 4, st));
+        CU(cudaMemsetAsync(w.pool_used.p, 0, 8, st));
+        row_capacity_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(d_rb, d_re, d_b, d_e, (int32_t)B, per_elem_extra, w.row_cap.p);
+        cub::DeviceScan::ExclusiveSum(w.cub_tmp.p, cub_bytes, w.row_cap.p, w.row_base.p, (int)B, st);
+        P.row_base = w.row_base.p; P.row_ext = w.row_ext.p; P.row_cnt = w.row_cnt.p; P.row_flag = w.row_flag.p;
+        P.tmp_a = w.tmp_a.p; P.tmp_b = w.tmp_b.p; P.tmp_c = w.tmp_c.p; P.tmp_cap = tmp_cap;
+        P.status = w.status.p;
+        if (call.op == OP_BPE) { CU(w.giants.ensure(w.giants_cap)); P.giants = w.giants.p; P.giants_cap = (int32_t)w.giants_cap; }
+        if (!attr_set[call.op][owner->device]) {
+            if (call.op == OP_BPE) CU(cudaFuncSetAttribute(rows_kernel<OP_BPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else if (call.op == OP_WORDPIECE) CU(cudaFuncSetAttribute(rows_kernel<OP_WORDPIECE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CU(cudaFuncSetAttribute(rows_kernel<OP_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[call.op][owner->device] = true;
+        }
+        if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
+        else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
+        else rows_kernel<OP_SPLIT><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
+        owner->launches += 2;
+        if (call.op == OP_BPE) {
+            CU(w.pool.ensure(w.pool_bytes));
+            GiantParams G{w.giants.p, w.status.p, (int32_t)w.giants_cap, d_c, call.bpe->view(), call.bpe->suffix.p, P.suffix_len,
+                          w.row_base.p, w.row_cnt.p, w.tmp_a.p, w.pool.p, (unsigned long long)w.pool_bytes, w.pool_used.p, w.status.p};
+            giant_bpe_kernel<<<std::max(1, owner->sm_count), 64, 0, st>>>(G);
+            ++owner->launches;
+        }
+        cub::DeviceScan::ExclusiveSum(w.cub_tmp.p, cub_bytes, w.row_cnt.p, d_ob, (int)B, st);
+        finish_offsets_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(d_ob, w.row_cnt.p, (int32_t)B, d_oe, w.status.p,
+                                                                                            async ? out_ids->n_ids_device : w.total.p);
+        compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(w.tmp_a.p, is_split ? w.tmp_b.p : nullptr, (is_split && d_oc) ? w.tmp_c.p : nullptr,
+                                                                  w.row_base.p, w.row_ext.p, w.row_flag.p, d_ob, (int32_t)B, d_oa, d_obb, d_oc,
+                                                                  out_cap, w.status.p);
+        owner->launches += 2;
+        CU(cudaGetLastError());
+        if (async) return B200TOK_OK;
+
+        CU(cudaMemcpyAsync(w.h_status, w.status.p, ST_WORDS * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(w.h_status + ST_WORDS, w.pool_used.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int err = w.h_status[ST_ERROR];
+        const int64_t total = w.h_status[ST_TOTAL];
+        if (err & (ERR_GIANT_LIST | ERR_GIANT_POOL)) {   // grow the giant-piece resources and run again
+            unsigned long long used;
+            std::memcpy(&used, w.h_status + ST_WORDS, 8);
+            if (err & ERR_GIANT_LIST) w.giants_cap = (size_t)w.h_status[ST_NGIANT] + 1024;
+            if (err & ERR_GIANT_POOL) w.pool_bytes = (size_t)used + (1u << 20);
+            if (err & ERR_GIANT_LIST) w.pool_bytes = std::max<size_t>(w.pool_bytes, 80ull * (size_t)tmp_cap + (1u << 20));
+            continue;
+        }
+        if (err & ERR_TMP_OVERFLOW) {
+            if (total > out_cap) return fail(B200TOK_E_CAPACITY, "output capacity %lld is smaller than the result (%lld elements)", (long long)out_cap, (long long)total);
+            return fail(B200TOK_E_INVALID, "row slots overflowed: overlapping or unordered input elements are not supported");
+        }
+        if (total > out_cap) return fail(B200TOK_E_CAPACITY, "output capacity %lld is smaller than the result (%lld elements)", (long long)out_cap, (long long)total);
+        if (out_ids) {
+            out_ids->n_ids = total;
+            if (host) {
+                CU(cudaMemcpyAsync(out_ids->begins, d_ob, B * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(out_ids->ends, d_oe, B * 4, cudaMemcpyDeviceToHost, st));
+                if (total) CU(cudaMemcpyAsync(out_ids->ids, d_oa, total * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            }
+        } else {
+            out_split->n_elems = total;
+            out_split->n_rows = B;
+            if (host) {
+                CU(cudaMemcpyAsync(out_split->ragged_begins, d_ob, B * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(out_split->ragged_ends, d_oe, B * 4, cudaMemcpyDeviceToHost, st));
+                if (total) {
+                    CU(cudaMemcpyAsync(out_split->begins, d_oa, total * 4, cudaMemcpyDeviceToHost, st));
+                    CU(cudaMemcpyAsync(out_split->ends, d_obb, total * 4, cudaMemcpyDeviceToHost, st));
+                    if (out_split->skips) CU(cudaMemcpyAsync(out_split->skips, d_oc, total, cudaMemcpyDeviceToHost, st));
+                }
+                CU(cudaStreamSynchronize(st));
+            }
+        }
+        return B200TOK_OK;
+    }
+    return fail(B200TOK_E_CUDA, "giant-piece resources could not be sized after 4 attempts");
+}
+
+template <class T>
+T* as(b200tok_handle h, int kind) {
+    if (!h || h->kind != kind) return nullptr;
+    return static_cast<T*>(h);
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+B200TOK_API int b200tok_version(void) { return 100; }
+B200TOK_API const char* b200tok_last_error(void) { return g_err.c_str(); }
+B200TOK_API int b200tok_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+B200TOK_API void b200tok_destroy(b200tok_handle h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    delete h;
+}
+B200TOK_API int64_t b200tok_launch_count(b200tok_handle h) { return h ? h->launches : 0; }
+
+// ---- RegexSplit ----
+B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* d, b200tok_handle* out) {
+    if (!d || !out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<SplitObj>();
+    std::string err;
+    int rc = parse_split(*d, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if ((rc = init_object(o.get(), K_SPLIT, d->device))) return rc;
+    DeviceGuard g(d->device);
+    CU(o->cls.upload());
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_regexsplit_run(b200tok_handle h, const b200tok_ragged_strings* in, b200tok_ragged_strings_out* out, void* stream) {
+    SplitObj* s = as<SplitObj>(h, K_SPLIT);
+    if (!s || !out) return fail(B200TOK_E_INVALID, "not a RegexSplit handle");
+    int rc = validate_in(in);
+    if (rc) return rc;
+    if (in->n_chars == 0) {   // src/regex_split.cpp:129-143: shape-[1] zeros, everything else passed through
+        DeviceGuard g(s->device);
+        const cudaMemcpyKind kind = in->mem == B200TOK_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToDevice;
+        const int32_t zero = 0;
+        if (in->mem == B200TOK_MEM_HOST) { out->ragged_begins[0] = 0; out->ragged_ends[0] = 0; }
+        else { CU(cudaMemcpy(out->ragged_begins, &zero, 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(out->ragged_ends, &zero, 4, cudaMemcpyHostToDevice)); }
+        if (in->n_elems > out->capacity) return fail(B200TOK_E_CAPACITY, "output capacity too small");
+        if (in->n_elems) {
+            CU(cudaMemcpy(out->begins, in->begins, in->n_elems * 4, kind));
+            CU(cudaMemcpy(out->ends, in->ends, in->n_elems * 4, kind));
+            if (out->skips && in->skips) CU(cudaMemcpy(out->skips, in->skips, in->n_elems, kind));
+        }
+        out->n_rows = 1;
+        out->n_elems = in->n_elems;
+        return B200TOK_OK;
+    }
+    RowCall call;
+    call.op = OP_SPLIT;
+    call.split = s;
+    return run_rows(s, call, in, nullptr, out, stream);
+}
+
+// ---- BPE ----
+B200TOK_API int b200tok_bpe_create(const b200tok_bpe_desc* d, b200tok_handle* out) {
+    if (!d || !out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<BpeObj>();
+    std::string err;
+    int rc = build_bpe(*d, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if ((rc = init_object(o.get(), K_BPE, d->device))) return rc;
+    DeviceGuard g(d->device);
+    CU(o->cls.upload());
+    CU(o->byte_sym.upload(o->h.byte_sym));
+    CU(o->byte_miss.upload(o->h.byte_miss));
+    CU(o->trie.upload(o->h.trie));
+    CU(o->slots.upload(o->h.slots));
+    std::vector<uint8_t> sfx(o->h.end_suffix.begin(), o->h.end_suffix.end());
+    if (sfx.empty()) sfx.push_back(0);
+    CU(o->suffix.upload(sfx));
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_bpe_run(b200tok_handle h, const b200tok_ragged_strings* in, b200tok_ragged_ids* out, void* stream) {
+    BpeObj* b = as<BpeObj>(h, K_BPE);
+    if (!b || !out) return fail(B200TOK_E_INVALID, "not a BPETokenizer handle");
+    RowCall call;
+    call.op = OP_BPE;
+    call.bpe = b;
+    return run_rows(b, call, in, out, nullptr, stream);
+}
+
+B200TOK_API int b200tok_split_bpe_run(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
+                                      b200tok_ragged_ids* out, void* stream) {
+    SplitObj* s = as<SplitObj>(split, K_SPLIT);
+    BpeObj* b = as<BpeObj>(bpe, K_BPE);
+    if (!s || !b || !out) return fail(B200TOK_E_INVALID, "expected (RegexSplit, BPETokenizer) handles");
+    if (s->device != b->device) return fail(B200TOK_E_INVALID, "handles live on different devices");
+    RowCall call;
+    call.op = OP_BPE;
+    call.split = s;
+    call.bpe = b;
+    return run_rows(b, call, in, out, nullptr, stream);
+}
+
+// ---- WordPiece ----
+B200TOK_API int b200tok_wordpiece_create(const b200tok_wordpiece_desc* d, b200tok_handle* out) {
+    if (!d || !out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<WordpieceObj>();
+    std::string err;
+    int rc = build_wordpiece(*d, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if ((rc = init_object(o.get(), K_WORDPIECE, d->device))) return rc;
+    DeviceGuard g(d->device);
+    CU(o->cls.upload());
+    CU(o->root.upload(o->h.root));
+    CU(o->sub.upload(o->h.sub));
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_wordpiece_run(b200tok_handle h, const b200tok_ragged_strings* in, int32_t unk_token_id,
+                                      b200tok_ragged_ids* out, void* stream) {
+    WordpieceObj* wp = as<WordpieceObj>(h, K_WORDPIECE);
+    if (!wp || !out) return fail(B200TOK_E_INVALID, "not a WordpieceTokenizer handle");
+    RowCall call;
+    call.op = OP_WORDPIECE;
+    call.wp = wp;
+    call.unk_id = unk_token_id;
+    return run_rows(wp, call, in, out, nullptr, stream);
+}
+
+B200TOK_API int b200tok_split_wordpiece_run(b200tok_handle split1, b200tok_handle split2, b200tok_handle wordpiece,
+                                            const b200tok_ragged_strings* in, int32_t unk_token_id,
+                                            b200tok_ragged_ids* out, void* stream) {
+    SplitObj* s1 = as<SplitObj>(split1, K_SPLIT);
+    SplitObj* s2 = split2 ? as<SplitObj>(split2, K_SPLIT) : nullptr;
+    WordpieceObj* wp = as<WordpieceObj>(wordpiece, K_WORDPIECE);
+    if (!s1 || (split2 && !s2) || !wp || !out) return fail(B200TOK_E_INVALID, "expected (RegexSplit[, RegexSplit], WordpieceTokenizer) handles");
+    RowCall call;
+    call.op = OP_WORDPIECE;
+    call.split = s1;
+    call.split2 = s2;
+    call.wp = wp;
+    call.unk_id = unk_token_id;
+    return run_rows(wp, call, in, out, nullptr, stream);
+}
+
+// ---- VocabEncoder ----
+B200TOK_API int b200tok_vocabenc_create(const b200tok_vocabenc_desc* d, b200tok_handle* out) {
+    if (!d || !out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<VocabEncObj>();
+    std::string err;
+    int rc = build_vocabenc(*d, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if ((rc = init_object(o.get(), K_VOCABENC, d->device))) return rc;
+    o->i64 = d->values_are_i64 != 0;
+    DeviceGuard g(d->device);
+    CU(o->slots.upload(o->h.slots));
+    CU(o->key_bytes.upload(o->h.key_bytes));
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_vocabenc_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n,
+                                     const uint8_t* chars, int64_t n_chars, int64_t default_value,
+                                     void* out_values, int mem, void* stream) {
+    VocabEncObj* o = as<VocabEncObj>(h, K_VOCABENC);
+    if (!o) return fail(B200TOK_E_INVALID, "not a VocabEncoder handle");
+    if (n < 0 || n_chars < 0 || (n > 0 && (!begins || !ends || !out_values))) return fail(B200TOK_E_INVALID, "bad arguments");
+    if (n == 0) return B200TOK_OK;
+    DeviceGuard g(o->device);
+    std::lock_guard<std::mutex> lock(o->mu);
+    int rc = ensure_ws(o);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : o->ws.stream;
+    const size_t vsz = o->i64 ? 8 : 4;
+    const int32_t *d_b = begins, *d_e = ends;
+    const uint8_t* d_c = chars;
+    void* d_out = out_values;
+    if (mem == B200TOK_MEM_HOST) {
+        CU(o->begins.ensure(n)); CU(o->ends.ensure(n)); CU(o->chars.ensure(n_chars + 16)); CU(o->out.ensure(n * vsz));
+        CU(cudaMemcpyAsync(o->begins.p, begins, n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(o->ends.p, ends, n * 4, cudaMemcpyHostToDevice, st));
+        if (n_chars) CU(cudaMemcpyAsync(o->chars.p, chars, n_chars, cudaMemcpyHostToDevice, st));
+        d_b = o->begins.p; d_e = o->ends.p; d_c = o->chars.p; d_out = o->out.p;
+    }
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (o->i64) vocab_lookup_kernel<int64_t><<<blocks, 256, 0, st>>>(d_b, d_e, d_c, n, o->slots.p, o->h.mask, o->key_bytes.p, default_value, (int64_t*)d_out);
+    else vocab_lookup_kernel<int32_t><<<blocks, 256, 0, st>>>(d_b, d_e, d_c, n, o->slots.p, o->h.mask, o->key_bytes.p, default_value, (int32_t*)d_out);
+    ++o->launches;
+    CU(cudaGetLastError());
+    if (mem == B200TOK_MEM_HOST) {
+        CU(cudaMemcpyAsync(out_values, d_out, n * vsz, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+// ---- VocabDecoder (+ ByteFallback) ----
+B200TOK_API int b200tok_vocabdec_create(const b200tok_vocabdec_desc* d, b200tok_handle* out) {
+    if (!d || !out) return fail(B200TOK_E_INVALID, "null argument");
+    const b200tok_strings& v = d->vocab;
+    if (v.n < 0 || (v.n > 0 && (!v.begins || !v.ends))) return fail(B200TOK_E_INVALID, "bad vocab tensor");
+    auto o = std::make_unique<VocabDecObj>();
+    int rc = init_object(o.get(), K_VOCABDEC, d->device);
+    if (rc) return rc;
+    o->V = v.n;
+    std::vector<int32_t> vb(v.begins, v.begins + v.n), ve(v.ends, v.ends + v.n);
+    std::vector<uint8_t> vc(v.chars, v.chars + v.n_chars);
+    std::vector<int16_t> bf((size_t)v.n);
+    for (int64_t i = 0; i < v.n; ++i) {
+        if (vb[i] < 0 || ve[i] < vb[i] || ve[i] > v.n_chars) return fail(B200TOK_E_INVALID, "vocab offsets out of range");
+        o->max_len = std::max(o->max_len, ve[i] - vb[i]);
+        bf[i] = (int16_t)byte_fallback_value(vc.data() + vb[i], ve[i] - vb[i]);
+    }
+    if (vc.empty()) vc.push_back(0);
+    DeviceGuard g(d->device);
+    CU(o->vb.upload(vb)); CU(o->ve.upload(ve)); CU(o->vc.upload(vc)); CU(o->bf_byte.upload(bf));
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int64_t b200tok_vocabdec_max_chars(b200tok_handle h, int64_t batch, int64_t seq) {
+    VocabDecObj* o = as<VocabDecObj>(h, K_VOCABDEC);
+    if (!o) return -1;
+    return batch * seq * (int64_t)o->max_len;
+}
+
+B200TOK_API int b200tok_vocabdec_run(b200tok_handle h, const int32_t* ids, int64_t batch, int64_t seq,
+                                     const int32_t* skip_tokens, int64_t n_skip, int byte_fallback,
+                                     b200tok_decoded* out, int ids_mem, void* stream) {
+    VocabDecObj* o = as<VocabDecObj>(h, K_VOCABDEC);
+    if (!o || !out) return fail(B200TOK_E_INVALID, "not a VocabDecoder handle");
+    if (batch < 0 || seq < 0 || n_skip < 0 || (batch * seq > 0 && !ids)) return fail(B200TOK_E_INVALID, "bad arguments");
+    if (out->mem != ids_mem) return fail(B200TOK_E_INVALID, "input and output must live in the same memory kind");
+    const bool host = ids_mem == B200TOK_MEM_HOST;
+    const int64_t width = seq > 0 ? seq : 1, n = batch * seq, n_out = batch * width;
+    if (n >= (1ll << 31)) return fail(B200TOK_E_INVALID, "batch too large for int32 offsets");
+    out->n_chars = 0;
+    if (batch == 0) return B200TOK_OK;
+    DeviceGuard g(o->device);
+    std::lock_guard<std::mutex> lock(o->mu);
+    int rc = ensure_ws(o);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : o->ws.stream;
+    int32_t *d_rb = out->ragged_begins, *d_re = out->ragged_ends, *d_b = out->begins, *d_e = out->ends;
+    uint8_t* d_c = out->chars;
+    const int32_t* d_ids = ids;
+    int64_t cap = out->chars_capacity;
+    if (host) {
+        CU(o->rb.ensure(batch)); CU(o->re.ensure(batch)); CU(o->begins.ensure(n_out)); CU(o->ends.ensure(n_out));
+        cap = std::min<int64_t>(cap, n * (int64_t)o->max_len);
+        CU(o->chars.ensure(cap + 16)); CU(o->ids.ensure(n + 1));
+        if (n) CU(cudaMemcpyAsync(o->ids.p, ids, n * 4, cudaMemcpyHostToDevice, st));
+        d_rb = o->rb.p; d_re = o->re.p; d_b = o->begins.p; d_e = o->ends.p; d_c = o->chars.p; d_ids = o->ids.p;
+    }
+    CU(o->skip.ensure(n_skip + 1));
+    if (n_skip) CU(cudaMemcpyAsync(o->skip.p, skip_tokens, n_skip * 4, host ? cudaMemcpyHostToDevice : cudaMemcpyDefault, st));
+    CU(o->len.ensure(n_out)); CU(o->status.ensure(4)); CU(o->total.ensure(1));
+    CU(cudaMemsetAsync(o->status.p, 0, 16, st));
+    CU(cudaMemsetAsync(o->total.p, 0, 8, st));
+    decode_ragged_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(batch, width, d_rb, d_re);
+    ++o->launches;
+    if (seq == 0) {   // src/vocab_decoder.cpp:61-65: one empty string per row
+        CU(cudaMemsetAsync(d_b, 0, batch * 4, st));
+        CU(cudaMemsetAsync(d_e, 0, batch * 4, st));
+    } else {
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        decode_len_kernel<<<blocks, 256, 0, st>>>(d_ids, n, o->vb.p, o->ve.p, o->V, o->skip.p, (int32_t)n_skip,
+                                                 byte_fallback ? o->bf_byte.p : nullptr, o->len.p);
+        size_t cub_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, o->len.p, d_b, (int)n, st);
+        CU(o->cub_tmp.ensure(cub_bytes + 256));
+        cub::DeviceScan::ExclusiveSum(o->cub_tmp.p, cub_bytes, o->len.p, d_b, (int)n, st);
+        decode_copy_kernel<<<blocks, 256, 0, st>>>(d_ids, n, o->vb.p, o->vc.p, byte_fallback ? o->bf_byte.p : nullptr, o->len.p, d_b, d_e,
+                                                  d_c, cap, o->status.p, o->total.p);
+        o->launches += 2;
+    }
+    CU(cudaGetLastError());
+    int32_t* hs = o->ws.h_status;
+    CU(cudaMemcpyAsync(hs, o->status.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hs + 2, o->total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int64_t total;
+    std::memcpy(&total, hs + 2, 8);
+    out->n_chars = total;
+    if (hs[0] || total > out->chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)out->chars_capacity, (long long)total);
+    if (host) {
+        CU(cudaMemcpyAsync(out->ragged_begins, d_rb, batch * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->ragged_ends, d_re, batch * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->begins, d_b, n_out * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out->ends, d_e, n_out * 4, cudaMemcpyDeviceToHost, st));
+        if (total) CU(cudaMemcpyAsync(out->chars, d_c, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+// ---- ByteFallback (stateless) ----
+B200TOK_API int b200tok_bytefallback_run(int device, const int32_t* begins, const int32_t* ends, int64_t n,
+                                         const uint8_t* chars, int64_t n_chars,
+                                         int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                         int64_t* out_n_chars, int mem, void* stream) {
+    if (n < 0 || n_chars < 0 || !out_n_chars || (n > 0 && (!begins || !ends || !out_begins || !out_ends))) return fail(B200TOK_E_INVALID, "bad arguments");
+    *out_n_chars = 0;
+    if (n == 0) return B200TOK_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B200TOK_E_CUDA, "no such CUDA device %d (there is no CPU fallback)", device);
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = mem == B200TOK_MEM_HOST;
+    DBuf<int32_t> b, e, ob, oe, len;
+    DBuf<uint8_t> c, oc, cub_tmp;
+    DBuf<int64_t> total;
+    const int32_t *d_b = begins, *d_e = ends;
+    const uint8_t* d_c = chars;
+    int32_t *d_ob = out_begins, *d_oe = out_ends;
+    uint8_t* d_oc = out_chars;
+    if (host) {
+        CU(b.ensure(n)); CU(e.ensure(n)); CU(c.ensure(n_chars + 16)); CU(ob.ensure(n)); CU(oe.ensure(n)); CU(oc.ensure(n_chars + 16));
+        CU(cudaMemcpyAsync(b.p, begins, n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(e.p, ends, n * 4, cudaMemcpyHostToDevice, st));
+        if (n_chars) CU(cudaMemcpyAsync(c.p, chars, n_chars, cudaMemcpyHostToDevice, st));
+        d_b = b.p; d_e = e.p; d_c = c.p; d_ob = ob.p; d_oe = oe.p; d_oc = oc.p;
+    }
+    CU(len.ensure(n)); CU(total.ensure(1));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    bytefallback_len_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, n, len.p);
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, len.p, d_ob, (int)n, st);
+    CU(cub_tmp.ensure(cub_bytes + 256));
+    cub::DeviceScan::ExclusiveSum(cub_tmp.p, cub_bytes, len.p, d_ob, (int)n, st);
+    bytefallback_copy_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, n, d_ob, d_oe, d_oc, total.p);
+    CU(cudaGetLastError());
+    int64_t t = 0;
+    CU(cudaMemcpyAsync(&t, total.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_n_chars = t;
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
+        if (t) CU(cudaMemcpyAsync(out_chars, d_oc, t, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+}  // extern "C"

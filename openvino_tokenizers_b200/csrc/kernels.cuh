@@ -1,0 +1,590 @@
+// kernels.cuh — sm_100a kernels of the tokenizer hot path.
+//
+// Work decomposition: one warp per row (input string); the row's bytes are staged
+// through shared memory in 512-byte windows; the split pattern is evaluated for all byte positions
+// of a window in parallel ("what would match if a match started here"), the reference's sequential
+// match loop (src/regex_split.cpp:287-309) is then resolved as a pointer chain; the resulting
+// pieces are handed round-robin to the 32 lanes, each running the BPE merge loop / WordPiece trie
+// walk for its piece with all state in shared memory and the merge-rank hash / tries read through
+// the read-only path from L2-resident HBM tables.  Token ids go to a row-local slot of a worst-case
+// buffer and are compacted by a scan + copy pass.  Integer/byte work only: no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tok_core.cuh"
+
+namespace b200tok {
+
+constexpr int WIN = 512;            // fresh bytes per window
+constexpr int LA = 16;              // look-ahead bytes staged beyond the window
+constexpr int WBYTES = WIN + LA + 16;
+constexpr int NWORDS = (WIN + LA + 31) / 32 + 1;
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
+
+constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK = 0x03FF;
+
+enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2 };
+
+// status words (device int32 array)
+enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_POOL_NEED_LO = 4, ST_POOL_NEED_HI = 5, ST_WORDS = 8 };
+enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
+
+struct GiantItem { int32_t row, begin, end, slot; };
+
+struct RowParams {
+    // input ragged strings (device)
+    const int32_t* rb; const int32_t* re; int32_t n_rows;
+    const int32_t* begins; const int32_t* ends;
+    const uint8_t* chars; int32_t n_chars;
+    const uint8_t* skips;
+    // splitter
+    SplitSpec spec; int repeat; int mode; int invert; int max_splits;
+    ClassTables cls;
+    // tokenizer tables
+    BpeTables bpe; int32_t suffix_len;
+    WordpieceTables wp; int32_t unk_id;
+    // row-local worst-case output slots
+    const int32_t* row_base;   // [n_rows] exclusive scan of row capacities
+    int32_t* row_ext;          // [n_rows] slots used (tokens incl. reserved holes / pieces)
+    int32_t* row_cnt;          // [n_rows] true count
+    uint8_t* row_flag;         // [n_rows] 1 = slot range contains holes (-1)
+    int32_t* tmp_a;            // tokens, or piece begins
+    int32_t* tmp_b;            // piece ends
+    uint8_t* tmp_c;            // piece skip flags
+    int64_t tmp_cap;
+    // giants
+    GiantItem* giants; int32_t giants_cap;
+    int32_t* status;
+};
+
+struct __align__(16) WarpSmem {
+    uint8_t bytes[WBYTES];
+    uint16_t seg[WIN + 4];
+    uint16_t cnt[WIN + 4];
+    union {
+        struct {
+            uint8_t cls[WBYTES];
+            uint32_t bnd[NWORDS], cs[NWORDS], nl[NWORDS], mm[NWORDS], chain[NWORDS];
+            uint16_t entry[32];
+            uint16_t nxt[WIN + LA + 8];
+            uint16_t exitp[WIN + LA + 8];
+        } sp;
+        struct {
+            int32_t ids[WIN];
+            uint32_t key[WIN];
+            int32_t newid[WIN];
+        } bp;
+    } u;
+};
+
+__device__ __forceinline__ int next_bit(const uint32_t* words, int i, int limit) {
+    int wd = (i + 1) >> 5;
+    if (wd >= NWORDS) return limit;
+    uint32_t m = words[wd] & (0xFFFFFFFFu << ((i + 1) & 31));
+    while (!m) {
+        if (++wd >= NWORDS) return limit;
+        m = words[wd];
+    }
+    const int r = wd * 32 + __ffs(m) - 1;
+    return r < limit ? r : limit;
+}
+// highest set bit in [lo, e), or -1
+__device__ __forceinline__ int prev_bit(const uint32_t* words, int e, int lo) {
+    int j = e - 1;
+    if (j < lo) return -1;
+    int wd = j >> 5;
+    uint32_t m = words[wd] & (0xFFFFFFFFu >> (31 - (j & 31)));
+    while (!m) {
+        if (--wd < 0) return -1;
+        m = words[wd];
+    }
+    const int r = wd * 32 + 31 - __clz(m);
+    return r >= lo ? r : -1;
+}
+
+// Window context: same interface as ScanCtx (tok_core.cuh), answers from precomputed bitmasks.
+struct WinCtx {
+    const uint8_t* b; const uint8_t* k;
+    const uint32_t* bnd; const uint32_t* cs; const uint32_t* nl;
+    int hi;   // known end (window-relative)
+    int lm;   // readable limit
+    __device__ __forceinline__ int known() const { return hi; }
+    __device__ __forceinline__ int lim() const { return lm; }
+    __device__ __forceinline__ uint8_t byte(int i) const { return b[i]; }
+    __device__ __forceinline__ uint8_t cls(int i) const { return k[i]; }
+    __device__ __forceinline__ int next(int i) const { return next_bit(cs, i, lm); }
+    __device__ __forceinline__ int run_end(int i) const { return next_bit(bnd, i, hi); }
+    __device__ __forceinline__ int last_nl(int i) const { return prev_bit(nl, run_end(i), i); }
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ bool seg_kept(uint16_t sg, int pat, int mode, int invert) {
+    if (pat == PAT_BERT_FUSED) return !(sg & F_DROP);
+    if (mode == SPLIT_ISOLATED) return true;
+    const bool flag = (sg & F_MATCH) ? !invert : (invert != 0);   // the `invert` argument of add_split
+    return !flag;                                                  // REMOVED drops flagged splits
+}
+
+// ------------------------------------------------------------------------------------------
+// Split phase for one window: fills S.seg[0..ns) (+ sentinel seg[ns]) with the complete segments
+// of bytes [0, wlen) and returns ns; `advance` = how far the window position moves (0 => the first
+// segment does not fit: "giant").  end_rel = element end relative to the window start.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int split_window(WarpSmem& S, const RowParams& P, const uint8_t* ascii_smem, int lane,
+                                            int wlen, int end_rel, int nload, int& advance) {
+    auto& sp = S.u.sp;
+    ClassTables T = P.cls;
+    T.ascii = ascii_smem;
+    // pass A: class per byte (continuation bytes copy their owner's class, plus C_CONT)
+    for (int w = lane; w < nload; w += 32) {
+        const uint8_t b = S.bytes[w];
+        uint8_t k;
+        if (b < 0x80) k = ascii_smem[b];
+        else if (is_cont_byte(b) && w > 0) {   // (index 0 is always treated as a character start)
+            int j = w - 1;
+            while (j >= 0 && j > w - 4 && is_cont_byte(S.bytes[j])) --j;
+            k = C_CONT;
+            if (j >= 0 && j > w - 4 && S.bytes[j] >= 0xC0) k |= char_class(S.bytes, j, end_rel, T);
+        } else k = char_class(S.bytes, w, end_rel, T);
+        sp.cls[w] = k;
+    }
+    __syncwarp();
+    // pass B: run-boundary / char-start / newline bitmasks
+    for (int it = 0; it < NWORDS; ++it) {
+        const int w = it * 32 + lane;
+        const bool valid = w < nload;
+        const uint8_t k = valid ? sp.cls[w] : 0;
+        const bool start = valid && !(k & C_CONT);
+        bool bnd = false;
+        if (start) bnd = (w == 0) || kind_of(k, P.spec.pat, P.spec.class_mask) != kind_of(sp.cls[w - 1], P.spec.pat, P.spec.class_mask);
+        const uint32_t mb = __ballot_sync(0xFFFFFFFFu, bnd);
+        const uint32_t mc = __ballot_sync(0xFFFFFFFFu, start);
+        const uint32_t mn = __ballot_sync(0xFFFFFFFFu, valid && (k & C_NL) && !(k & C_CONT));
+        if (lane == 0) { sp.bnd[it] = mb; sp.cs[it] = mc; sp.nl[it] = mn; }
+    }
+    __syncwarp();
+    // pass C: the match that would start at every character position
+    WinCtx ctx{S.bytes, sp.cls, sp.bnd, sp.cs, sp.nl, wlen, nload};
+    const bool hi_is_end = (wlen == end_rel);
+    for (int it = 0; it * 32 < wlen; ++it) {
+        const int w = it * 32 + lane;
+        bool is_m = false;
+        if (w < wlen && !(sp.cls[w] & C_CONT)) {
+            const Match m = match_rep(ctx, P.spec, P.repeat != 0, w, end_rel);
+            const bool unc = !hi_is_end && m.peek > wlen;
+            int step = m.len > 0 ? w + m.len : ctx.next(w);
+            if (step > wlen + LA) step = wlen + LA;
+            is_m = m.len > 0;
+            sp.nxt[w] = (uint16_t)(step | (is_m ? F_MATCH : 0) | (m.drop ? F_DROP : 0) | (unc ? F_UNC : 0));
+        }
+        const uint32_t mmask = __ballot_sync(0xFFFFFFFFu, is_m);
+        if (lane == 0) sp.mm[it] = mmask;
+    }
+    for (int it = (wlen + 31) / 32 + lane; it < NWORDS; it += 32) sp.mm[it] = 0;
+    __syncwarp();
+    // pass D1: per 16-byte block, where does a chain entering at q leave the block
+    {
+        const int b0 = lane * 16, b1 = b0 + 16;
+        for (int q = 15; q >= 0; --q) {
+            const int w = b0 + q;
+            if (w < wlen && ((sp.cs[w >> 5] >> (w & 31)) & 1u)) {
+                const uint16_t v = sp.nxt[w];
+                const int tgt = v & POS_MASK;
+                uint16_t ex;
+                if (v & F_UNC) ex = (uint16_t)(w | F_UNC);
+                else if (tgt >= b1 || tgt >= wlen) ex = (uint16_t)tgt;
+                else ex = sp.exitp[tgt];
+                sp.exitp[w] = ex;
+            }
+        }
+        sp.entry[lane] = 0xFFFF;
+        reinterpret_cast<uint16_t*>(sp.chain)[lane] = 0;
+        if (lane < 2 * NWORDS - 32) reinterpret_cast<uint16_t*>(sp.chain)[32 + lane] = 0;
+    }
+    __syncwarp();
+    // pass D2: lane 0 hops block to block
+    int stop = 0, unc = 0;
+    if (lane == 0) {
+        int cur = 0;
+        while (cur < wlen) {
+            sp.entry[cur >> 4] = (uint16_t)cur;
+            const uint16_t ex = sp.exitp[cur];
+            if (ex & F_UNC) { unc = 1; cur = ex & POS_MASK; break; }
+            cur = ex;
+        }
+        stop = cur;
+    }
+    stop = __shfl_sync(0xFFFFFFFFu, stop, 0);
+    unc = __shfl_sync(0xFFFFFFFFu, unc, 0);
+    __syncwarp();
+    // pass D3: every lane marks the chain positions inside its block
+    {
+        const int b0 = lane * 16, b1 = b0 + 16;
+        uint32_t bits = 0;
+        int cur = sp.entry[lane];
+        if (cur != 0xFFFF) {
+            while (cur < b1 && cur < stop) {
+                bits |= 1u << (cur - b0);
+                const uint16_t v = sp.nxt[cur];
+                if (v & F_UNC) break;
+                cur = v & POS_MASK;
+            }
+        }
+        reinterpret_cast<uint16_t*>(sp.chain)[lane] = (uint16_t)bits;
+    }
+    __syncwarp();
+    // pass E: segment starts = matches, and gap characters not preceded by a gap character
+    int ns = 0;
+    for (int it = 0; it * 32 < wlen; ++it) {
+        const int w = it * 32 + lane;
+        bool st = false;
+        uint16_t sg = 0;
+        if (w < wlen && w < stop && ((sp.chain[w >> 5] >> (w & 31)) & 1u)) {
+            const bool is_m = (sp.mm[w >> 5] >> (w & 31)) & 1u;
+            if (is_m || w == 0) st = true;
+            else {
+                const int pw = prev_bit(sp.cs, w, 0);
+                const bool prev_gap = pw >= 0 && ((sp.chain[pw >> 5] >> (pw & 31)) & 1u) && !((sp.mm[pw >> 5] >> (pw & 31)) & 1u);
+                st = !prev_gap;
+            }
+            sg = (uint16_t)(w | (sp.nxt[w] & (F_MATCH | F_DROP)));
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
+        if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = sg;
+        ns += __popc(m);
+    }
+    __syncwarp();
+    // completeness
+    if (hi_is_end && !unc) {
+        advance = wlen;
+        if (lane == 0) S.seg[ns] = (uint16_t)wlen;
+    } else {
+        int adv = stop;
+        if (ns > 0) {
+            const uint16_t last = S.seg[ns - 1];
+            if (!(last & F_MATCH)) { --ns; adv = last & POS_MASK; }   // trailing gap may continue: redo from its start
+        }
+        advance = adv;
+        if (lane == 0) S.seg[ns] = (uint16_t)adv;
+    }
+    __syncwarp();
+    return ns;
+}
+
+// Sequentially (lane 0) find the extent of the segment starting at chars[pos] when it does not fit
+// a window.  Returns its length; is_match/drop describe it.
+__device__ __noinline__ int giant_segment(const RowParams& P, int pos, int end_rel, int& is_match, int& drop) {
+    ScanCtx sc{P.chars + pos, end_rel, P.cls, P.spec.pat, P.spec.class_mask};
+    const Match m = match_rep(sc, P.spec, P.repeat != 0, 0, end_rel);
+    if (m.len > 0) { is_match = 1; drop = m.drop; return m.len; }
+    is_match = 0; drop = 0;
+    int q = sc.next(0);
+    while (q < end_rel && match_rep(sc, P.spec, P.repeat != 0, q, end_rel).len == 0) q = sc.next(q);
+    return q;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams P) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* ascii_smem = smem_raw;                                   // [128]
+    int32_t* bytesym_smem = reinterpret_cast<int32_t*>(smem_raw + 128);   // [256]
+    WarpSmem* warps = reinterpret_cast<WarpSmem*>(smem_raw + 128 + 1024);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpSmem& S = warps[wib];
+    if (threadIdx.x < 128) ascii_smem[threadIdx.x] = P.cls.ascii[threadIdx.x];
+    if (OP == OP_BPE) bytesym_smem[threadIdx.x] = P.bpe.byte_sym[threadIdx.x];
+    __syncthreads();
+    BpeTables BT = P.bpe;
+    BT.byte_sym = bytesym_smem;
+
+    for (;;) {
+        int row = 0;
+        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+        row = __shfl_sync(0xFFFFFFFFu, row, 0);
+        if (row >= P.n_rows) break;
+        const int64_t base = P.row_base[row];
+        int emitted = 0;       // slots used in this row's range
+        int holes = 0;         // reserved-but-unfilled slots (giant BPE pieces)
+        const int p0 = P.rb[row], p1 = P.re[row];
+        for (int p = p0; p < p1; ++p) {
+            const int eb = P.begins[p], ee = P.ends[p];
+            const bool skip = P.skips && P.skips[p];
+            if (OP == OP_SPLIT && skip) {   // src/regex_split.cpp:231-234
+                if (lane == 0) {
+                    const int64_t o = base + emitted;
+                    if (o < P.tmp_cap) { P.tmp_a[o] = eb; P.tmp_b[o] = ee; P.tmp_c[o] = 1; }
+                    else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                }
+                ++emitted;
+                continue;
+            }
+            const bool whole = skip || P.spec.pat == PAT_NONE;   // the element is one piece
+            SplitEmitter em;
+            int last_was_match = 1;
+            const bool stateful = OP == OP_SPLIT && (P.mode >= SPLIT_MERGED_PREV || P.max_splits != -1);
+            if (OP == OP_SPLIT) em.reset(P.mode, P.invert != 0, P.max_splits, ee - eb);
+            if (OP == OP_WORDPIECE && whole && ee <= eb) {   // zero-length word -> [unk] (see tok_core.cuh)
+                if (lane == 0) { const int64_t o = base + emitted; if (o < P.tmp_cap) P.tmp_a[o] = P.unk_id; else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW); }
+                ++emitted;
+                continue;
+            }
+            int pos = eb;
+            while (pos < ee) {
+                const int end_rel = ee - pos;
+                const int wlen = end_rel < WIN ? end_rel : WIN;
+                int ns = 0, advance = 0;
+                const bool fits = !(whole && end_rel > WIN) && !(OP == OP_BPE && P.suffix_len > 0);
+                if (fits) {
+                    const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
+                    for (int w = lane; w < nload + 4; w += 32) S.bytes[w] = (w < nload) ? __ldg(P.chars + pos + w) : 0;
+                    __syncwarp();
+                    if (whole) {
+                        if (lane == 0) { S.seg[0] = F_MATCH; S.seg[1] = (uint16_t)wlen; }
+                        ns = 1; advance = wlen;
+                        __syncwarp();
+                    } else {
+                        ns = split_window(S, P, ascii_smem, lane, wlen, end_rel, nload, advance);
+                    }
+                }
+                if (advance == 0) {
+                    // ---- giant: a segment that does not fit the window (or BPE with end_suffix) ----
+                    int glen = end_rel, is_m = 1, drop = 0;
+                    if (!whole) {
+                        if (lane == 0) glen = giant_segment(P, pos, end_rel, is_m, drop);
+                        glen = __shfl_sync(0xFFFFFFFFu, glen, 0);
+                        is_m = __shfl_sync(0xFFFFFFFFu, is_m, 0);
+                        drop = __shfl_sync(0xFFFFFFFFu, drop, 0);
+                    }
+                    const uint16_t sg = (uint16_t)((is_m ? F_MATCH : 0) | (drop ? F_DROP : 0));
+                    const bool kept = whole || seg_kept(sg, P.spec.pat, P.mode, P.invert);
+                    if (OP == OP_SPLIT) {
+                        if (lane == 0) {
+                            int ob, oe;
+                            const bool out = stateful || whole ? em.add(pos - eb, pos + glen - eb, is_m ? !em.invert : em.invert, ob, oe) : kept;
+                            if (!(stateful || whole)) { ob = pos - eb; oe = pos + glen - eb; }
+                            if (out) {
+                                const int64_t o = base + emitted;
+                                if (o < P.tmp_cap) { P.tmp_a[o] = eb + ob; P.tmp_b[o] = eb + oe; P.tmp_c[o] = 0; }
+                                else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                            }
+                            emitted += out ? 1 : 0;
+                        }
+                        emitted = __shfl_sync(0xFFFFFFFFu, emitted, 0);
+                        last_was_match = is_m;
+                    } else if (kept) {
+                        if (OP == OP_WORDPIECE) {
+                            if (lane == 0) {
+                                const int64_t o = base + emitted;
+                                int c = 0;
+                                if (o + glen <= P.tmp_cap) c = wordpiece_word(P.wp, P.chars, pos, pos + glen, P.unk_id, P.tmp_a + o);
+                                else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                                emitted += c;
+                            }
+                            emitted = __shfl_sync(0xFFFFFFFFu, emitted, 0);
+                        } else {
+                            const int reserve = glen + P.suffix_len;
+                            const int64_t o = base + emitted;
+                            if (o + reserve <= P.tmp_cap) {
+                                for (int t = lane; t < reserve; t += 32) P.tmp_a[o + t] = -1;
+                                if (lane == 0) {
+                                    const int gi = atomicAdd(&P.status[ST_NGIANT], 1);
+                                    if (gi < P.giants_cap) P.giants[gi] = GiantItem{row, pos, pos + glen, emitted};
+                                    else atomicOr(&P.status[ST_ERROR], ERR_GIANT_LIST);
+                                }
+                            } else if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                            emitted += reserve;
+                            holes += reserve;
+                        }
+                    }
+                    pos += glen;
+                    continue;
+                }
+                // ---- regular window: ns complete segments, S.seg[ns] is the end sentinel ----
+                if (OP == OP_SPLIT) {
+                    if (stateful) {
+                        if (lane == 0) {
+                            for (int j = 0; j < ns; ++j) {
+                                const uint16_t sg = S.seg[j];
+                                const int s = (pos - eb) + (sg & POS_MASK), e = (pos - eb) + (S.seg[j + 1] & POS_MASK);
+                                int ob, oe;
+                                if (em.add(s, e, (sg & F_MATCH) ? !em.invert : em.invert, ob, oe)) {
+                                    const int64_t o = base + emitted;
+                                    if (o < P.tmp_cap) { P.tmp_a[o] = eb + ob; P.tmp_b[o] = eb + oe; P.tmp_c[o] = 0; }
+                                    else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                                    ++emitted;
+                                }
+                                last_was_match = (sg & F_MATCH) ? 1 : 0;
+                            }
+                        }
+                        emitted = __shfl_sync(0xFFFFFFFFu, emitted, 0);
+                        last_was_match = __shfl_sync(0xFFFFFFFFu, last_was_match, 0);
+                    } else {
+                        for (int j0 = 0; j0 < ns; j0 += 32) {
+                            const int j = j0 + lane;
+                            bool k = false;
+                            uint16_t sg = 0;
+                            if (j < ns) { sg = S.seg[j]; k = seg_kept(sg, P.spec.pat, P.mode, P.invert); }
+                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, k);
+                            if (k) {
+                                const int64_t o = base + emitted + __popc(m & ((1u << lane) - 1u));
+                                if (o < P.tmp_cap) { P.tmp_a[o] = pos + (sg & POS_MASK); P.tmp_b[o] = pos + (S.seg[j + 1] & POS_MASK); P.tmp_c[o] = 0; }
+                                else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                            }
+                            emitted += __popc(m);
+                        }
+                    }
+                } else {
+                    // piece phase: lanes take segments round-robin
+                    for (int j = lane; j < ns; j += 32) {
+                        const uint16_t sg = S.seg[j];
+                        int c = 0;
+                        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
+                            const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
+                            if (OP == OP_BPE) {
+                                const int n = bpe_symbolize(BT, S.bytes, s, e, S.u.bp.ids + s);
+                                c = bpe_merge_packed(BT.merges, S.u.bp.ids + s, S.u.bp.key + s, S.u.bp.newid + s, n);
+                            } else {
+                                c = wordpiece_word(P.wp, S.bytes, s, e, P.unk_id, S.u.bp.ids + s);
+                            }
+                        }
+                        S.cnt[j] = (uint16_t)c;
+                    }
+                    __syncwarp();
+                    // output phase: scan the counts, copy tokens to the row slot
+                    for (int j0 = 0; j0 < ns; j0 += 32) {
+                        const int j = j0 + lane;
+                        const int c = j < ns ? S.cnt[j] : 0;
+                        const int incl = warp_incl_scan(c, lane);
+                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        if (c) {
+                            const int s = S.seg[j] & POS_MASK;
+                            const int64_t o = base + emitted + incl - c;
+                            if (o + c <= P.tmp_cap) { for (int t = 0; t < c; ++t) P.tmp_a[o + t] = S.u.bp.ids[s + t]; }
+                            else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                        }
+                        emitted += total;
+                    }
+                    __syncwarp();
+                }
+                pos += advance;
+            }
+            if (OP == OP_SPLIT && stateful) {   // src/regex_split.cpp:305-309
+                if (lane == 0 && last_was_match) {
+                    int ob, oe;
+                    if (em.finish(ee - eb, ob, oe)) {
+                        const int64_t o = base + emitted;
+                        if (o < P.tmp_cap) { P.tmp_a[o] = eb + ob; P.tmp_b[o] = eb + oe; P.tmp_c[o] = 0; }
+                        else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                        ++emitted;
+                    }
+                }
+                emitted = __shfl_sync(0xFFFFFFFFu, emitted, 0);
+            }
+        }
+        if (lane == 0) {
+            P.row_ext[row] = emitted;
+            P.row_cnt[row] = emitted - holes;
+            P.row_flag[row] = holes ? 1 : 0;
+        }
+    }
+}
+
+// Row capacities: tokens (or pieces) a row can produce at most.
+//   BPE: sum(len + suffix_len); WordPiece / split: sum(len + 1)
+__global__ void row_capacity_kernel(const int32_t* rb, const int32_t* re, const int32_t* begins, const int32_t* ends,
+                                    int32_t n_rows, int32_t per_elem_extra, int32_t* cap) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    int64_t c = 0;
+    for (int p = rb[r]; p < re[r]; ++p) { const int l = ends[p] - begins[p]; c += (l > 0 ? l : 0) + per_elem_extra; }
+    cap[r] = (int32_t)(c > 0x7FFFFFFF ? 0x7FFFFFFF : c);
+}
+
+// Very long BPE pieces (and every piece when an end_suffix is configured): one thread per piece,
+// heap-ordered merge loop with all state in a global scratch pool.
+struct GiantParams {
+    const GiantItem* items; const int32_t* status_in; int32_t giants_cap;
+    const uint8_t* chars; BpeTables bpe; const uint8_t* suffix; int32_t suffix_len;
+    const int32_t* row_base; int32_t* row_cnt; int32_t* tmp; uint8_t* pool; unsigned long long pool_cap;
+    unsigned long long* pool_used; int32_t* status;
+};
+__global__ void giant_bpe_kernel(const GiantParams G) {
+    int n_items = G.status_in[ST_NGIANT];
+    if (n_items > G.giants_cap) n_items = G.giants_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+        const GiantItem it = G.items[i];
+        const int len = it.end - it.begin, n = len + G.suffix_len;
+        // layout: heap [3n x 16 B] | sym_id, sym_prev, sym_next [2n x 4 B each] | bytes [n]; 16-byte granules
+        const unsigned long long need = (48ull * n + 24ull * n + (unsigned long long)n + 15ull) & ~15ull;
+        const unsigned long long off = atomicAdd(G.pool_used, need);
+        if (off + need > G.pool_cap) { atomicOr(&G.status[ST_ERROR], ERR_GIANT_POOL); continue; }
+        uint8_t* mem = G.pool + off;
+        HeapEntry* heap = reinterpret_cast<HeapEntry*>(mem);
+        int32_t* sym_id = reinterpret_cast<int32_t*>(mem + 48ull * n);
+        int32_t* sym_prev = sym_id + 2 * n;
+        int32_t* sym_next = sym_prev + 2 * n;
+        uint8_t* bytes = reinterpret_cast<uint8_t*>(sym_next + 2 * n);
+        for (int k = 0; k < len; ++k) bytes[k] = G.chars[it.begin + k];
+        for (int k = 0; k < G.suffix_len; ++k) bytes[len + k] = G.suffix[k];
+        const int m = bpe_symbolize(G.bpe, bytes, 0, n, sym_id);
+        int32_t* out = G.tmp + G.row_base[it.row] + it.slot;
+        const int cnt = bpe_merge_heap(G.bpe.merges, m, sym_id, sym_prev, sym_next, heap, out);
+        for (int k = cnt; k < n; ++k) out[k] = -1;
+        atomicAdd(&G.row_cnt[it.row], cnt);
+    }
+}
+
+// out_begins = exclusive scan(row_cnt) is done with cub; this finishes ends + total.
+__global__ void finish_offsets_kernel(const int32_t* begins, const int32_t* cnt, int32_t n_rows, int32_t* ends,
+                                      int32_t* status, int64_t* total_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int e = begins[r] + cnt[r];
+    ends[r] = e;
+    if (r == n_rows - 1) { status[ST_TOTAL] = e; if (total_out) *total_out = e; }
+}
+
+// Copy every row's slots to their final place (warp per row); rows with holes are filtered.
+__global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, const uint8_t* tmp_c,
+                                    const int32_t* row_base, const int32_t* row_ext, const uint8_t* row_flag,
+                                    const int32_t* out_begin, int32_t n_rows,
+                                    int32_t* out_a, int32_t* out_b, uint8_t* out_c, int64_t out_cap, int32_t* status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_rows; r += nwarps) {
+        const int64_t src = row_base[r];
+        const int ext = row_ext[r];
+        int64_t dst = out_begin[r];
+        if (!row_flag[r]) {
+            if (dst + ext > out_cap) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
+            for (int t = lane; t < ext; t += 32) {
+                out_a[dst + t] = tmp_a[src + t];
+                if (out_b) out_b[dst + t] = tmp_b[src + t];
+                if (out_c) out_c[dst + t] = tmp_c[src + t];
+            }
+        } else {
+            for (int t0 = 0; t0 < ext; t0 += 32) {
+                const int t = t0 + lane;
+                const int v = t < ext ? tmp_a[src + t] : -1;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, v >= 0);
+                if (v >= 0) {
+                    const int64_t o = dst + __popc(m & ((1u << lane) - 1u));
+                    if (o < out_cap) out_a[o] = v;
+                }
+                dst += __popc(m);
+            }
+        }
+    }
+}
+
+}  // namespace b200tok

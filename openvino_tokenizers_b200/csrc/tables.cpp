@@ -1,0 +1,311 @@
+// tables.cpp — see tables.hpp.
+#include "tables.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+namespace b200tok {
+
+// ------------------------------------------------------------------------------------------
+// Unicode class tables (two-stage), from the PCRE2-derived run list.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Run { uint32_t cp; uint8_t flags; };
+const Run kRuns[] = {
+#include "unicode_ranges.inc"
+};
+
+bool in_bert_punct_or_cjk(uint32_t cp, uint8_t f) {
+    if ((cp >= 0x21 && cp <= 0x2F) || (cp >= 0x3A && cp <= 0x40) || (cp >= 0x5B && cp <= 0x60) || (cp >= 0x7B && cp <= 0x7E))
+        return true;
+    if (f & C_P) return true;
+    static const uint32_t cjk[][2] = {{0x4E00, 0x9FFF}, {0x3400, 0x4DBF}, {0x20000, 0x2A6DF}, {0x2A700, 0x2B73F},
+                                      {0x2B740, 0x2B81F}, {0x2B820, 0x2CEAF}, {0xF900, 0xFAFF}, {0x2F800, 0x2FA1F}};
+    for (auto& r : cjk)
+        if (cp >= r[0] && cp <= r[1]) return true;
+    return false;
+}
+}  // namespace
+
+const HostClassTables& host_class_tables() {
+    static const HostClassTables tables = [] {
+        HostClassTables t;
+        std::vector<uint8_t> flat(0x110000);
+        const size_t n = sizeof(kRuns) / sizeof(kRuns[0]);
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t a = kRuns[i].cp, b = (i + 1 < n) ? kRuns[i + 1].cp : 0x110000u;
+            for (uint32_t cp = a; cp < b; ++cp) {
+                uint8_t f = kRuns[i].flags;
+                if (in_bert_punct_or_cjk(cp, f)) f |= C_BP;
+                if (cp == '\r' || cp == '\n') f |= C_NL;
+                flat[cp] = f;
+            }
+        }
+        t.ascii.assign(flat.begin(), flat.begin() + 128);
+        t.stage1.resize(0x1100);
+        std::map<std::vector<uint8_t>, uint16_t> seen;
+        for (uint32_t blk = 0; blk < 0x1100; ++blk) {
+            std::vector<uint8_t> v(flat.begin() + blk * 256, flat.begin() + blk * 256 + 256);
+            auto it = seen.find(v);
+            if (it == seen.end()) {
+                const uint16_t idx = (uint16_t)seen.size();
+                it = seen.emplace(v, idx).first;
+                t.stage2.insert(t.stage2.end(), v.begin(), v.end());
+            }
+            t.stage1[blk] = it->second;
+        }
+        return t;
+    }();
+    return tables;
+}
+
+// ------------------------------------------------------------------------------------------
+// Flattened trie.
+// ------------------------------------------------------------------------------------------
+void HostTrie::build(const std::vector<std::pair<std::string, int32_t>>& entries) {
+    struct Node { std::map<uint8_t, int32_t> kids; int32_t value = -1; };
+    std::vector<Node> nodes(1);
+    for (const auto& [key, id] : entries) {
+        if (key.empty()) continue;   // the root's value is never consulted (utils.cpp:524-535)
+        int32_t cur = 0;
+        for (unsigned char c : key) {
+            auto it = nodes[cur].kids.find(c);
+            if (it == nodes[cur].kids.end()) {
+                const int32_t nn = (int32_t)nodes.size();
+                nodes[cur].kids.emplace(c, nn);
+                nodes.emplace_back();
+                cur = nn;
+            } else {
+                cur = it->second;
+            }
+        }
+        nodes[cur].value = id;
+    }
+    const size_t N = nodes.size();
+    first.assign(N + 1, 0);
+    value.assign(N, -1);
+    edge_byte.clear();
+    edge_child.clear();
+    root_child.assign(256, -1);
+    for (size_t i = 0; i < N; ++i) {
+        first[i] = (int32_t)edge_byte.size();
+        value[i] = nodes[i].value;
+        for (const auto& [b, ch] : nodes[i].kids) {
+            edge_byte.push_back(b);
+            edge_child.push_back(ch);
+            if (i == 0) root_child[b] = ch;
+        }
+    }
+    first[N] = (int32_t)edge_byte.size();
+    if (edge_byte.empty()) { edge_byte.push_back(0); edge_child.push_back(-1); }  // keep device buffers non-empty
+}
+
+static std::string str_at(const b200tok_strings& s, int64_t i) {
+    return std::string((const char*)s.chars + s.begins[i], (const char*)s.chars + s.ends[i]);
+}
+
+static bool check_strings(const b200tok_strings& s, const char* what, std::string& err, bool allow_empty = true) {
+    if (s.n < 0 || (s.n > 0 && (!s.begins || !s.ends)) || (!allow_empty && s.n == 0)) { err = std::string("bad string tensor: ") + what; return false; }
+    for (int64_t i = 0; i < s.n; ++i)
+        if (s.begins[i] < 0 || s.ends[i] < s.begins[i] || s.ends[i] > s.n_chars) { err = std::string("string offsets out of range in ") + what; return false; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// BPE tables.
+// ------------------------------------------------------------------------------------------
+int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
+    if (!check_strings(d.vocab, "vocab", err) || !check_strings(d.merges_left, "merges", err)) return B200TOK_E_INVALID;
+    const bool pairs = d.merges_right.begins != nullptr;
+    if (pairs && (!check_strings(d.merges_right, "merges(right)", err) || d.merges_right.n != d.merges_left.n)) {
+        if (err.empty()) err = "left/right merge tensors differ in length";
+        return B200TOK_E_INVALID;
+    }
+    if (d.added_tokens.n > 0 && (!check_strings(d.added_tokens, "added tokens", err) || !d.added_ids)) return B200TOK_E_INVALID;
+
+    // bpe_tokenizer.cpp:62-66 (std::map::insert: first occurrence of a key wins)
+    std::map<std::string, int32_t> added;
+    for (int64_t i = 0; i < d.added_tokens.n; ++i) added.insert({str_at(d.added_tokens, i), d.added_ids[i]});
+    // :77-82 (insert_or_assign: last id wins)
+    std::unordered_map<std::string, int32_t> vocab;
+    vocab.reserve((size_t)(d.vocab.n + d.added_tokens.n) * 2);
+    for (int64_t i = 0; i < d.vocab.n; ++i) vocab[str_at(d.vocab, i)] = (int32_t)i;
+    // :110-114 (insert: an existing key keeps its id)
+    for (const auto& kv : added) vocab.insert({kv.first, kv.second});
+
+    const std::string unk(d.unk_token ? d.unk_token : "", d.unk_token ? (size_t)d.unk_token_len : 0);
+    out.unk_id = -1;
+    if (auto it = vocab.find(unk); it != vocab.end()) out.unk_id = it->second;   // :353-355
+    out.end_suffix.assign(d.end_suffix ? d.end_suffix : "", d.end_suffix ? (size_t)d.end_suffix_len : 0);
+
+    const int64_t M = d.merges_left.n;
+    out.n_merges = M;
+    if (M >= (1ll << 20)) { err = "BPE: more than 2^20 merges is not supported by the packed (rank,birth) key"; return B200TOK_E_UNSUPPORTED; }
+    // :361-373 — key (left_id,right_id); a later duplicate key overwrites (bpe_tokenizer.hpp:61-65)
+    std::unordered_map<uint64_t, std::pair<int32_t, int32_t>> merges;
+    merges.reserve((size_t)M * 2);
+    std::vector<std::string> products;
+    products.reserve((size_t)M);
+    std::unordered_map<int32_t, int> product_count;
+    for (int64_t i = 0; i < M; ++i) {
+        std::string l, r;
+        if (pairs) { l = str_at(d.merges_left, i); r = str_at(d.merges_right, i); }
+        else {   // :91-96 split on the first ' '
+            const std::string m = str_at(d.merges_left, i);
+            const size_t sp = m.find(' ');
+            l = m.substr(0, sp);
+            r = sp == std::string::npos ? m : m.substr(sp + 1);
+        }
+        auto li = vocab.find(l), ri = vocab.find(r);
+        std::string joined = l + r;
+        auto ji = vocab.find(joined);
+        if (li == vocab.end() || ri == vocab.end() || ji == vocab.end()) {   // vocab.at() throws in the reference
+            err = "merge #" + std::to_string(i) + " refers to a token that is not in the vocab";
+            return B200TOK_E_VOCAB;
+        }
+        merges[((uint64_t)(uint32_t)li->second << 32) | (uint32_t)ri->second] = {(int32_t)i, ji->second};
+        if (++product_count[ji->second] == 2) ++out.n_duplicate_products;
+        products.push_back(std::move(joined));
+    }
+    for (const auto& p : products) vocab.erase(p);   // :375-377
+
+    // trie over what is left (:382-386) and the per-byte shortcuts
+    std::vector<std::pair<std::string, int32_t>> entries;
+    entries.reserve(vocab.size());
+    for (const auto& kv : vocab) entries.emplace_back(kv.first, kv.second);
+    out.trie.build(entries);
+    out.byte_sym.assign(256, -1);
+    out.byte_miss.assign(256, -1);
+    out.bytes_only = true;
+    for (int c = 0; c < 256; ++c) {
+        const int32_t node = out.trie.root_child[c];
+        if (node >= 0) {
+            const bool has_kids = out.trie.first[node + 1] > out.trie.first[node];
+            if (has_kids) { out.byte_sym[c] = kSymWalk; out.bytes_only = false; }
+            else out.byte_sym[c] = out.trie.value[node];   // a leaf always carries a value
+        }
+        int32_t miss = -1;
+        if (d.byte_fallback) {   // :242-248, looked up in the post-erase vocab
+            char name[8];
+            std::snprintf(name, sizeof(name), "<0x%02X>", (unsigned)c);
+            if (auto it = vocab.find(name); it != vocab.end()) miss = it->second;
+        }
+        if (miss == -1 && out.unk_id != -1) miss = out.unk_id;   // :250-254 (fuse_unk never suppresses: it compares with -1)
+        out.byte_miss[c] = miss;
+    }
+
+    // device hash table: power-of-two capacity, load factor <= 0.5
+    size_t cap = 16;
+    while (cap < merges.size() * 2 + 2) cap <<= 1;
+    out.slots.assign(cap, MergeSlot{kEmptyKey, kEmptyKey, kNoRank, -1});
+    out.mask = (uint32_t)(cap - 1);
+    for (const auto& kv : merges) {
+        const uint32_t l = (uint32_t)(kv.first >> 32), r = (uint32_t)kv.first;
+        uint32_t h = merge_hash(l, r) & out.mask;
+        while (out.slots[h].left != kEmptyKey) h = (h + 1) & out.mask;
+        out.slots[h] = MergeSlot{l, r, kv.second.first, kv.second.second};
+    }
+    return B200TOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// WordPiece tries (wordpiece_tokenizer.cpp:61-71).
+// ------------------------------------------------------------------------------------------
+int build_wordpiece(const b200tok_wordpiece_desc& d, HostWordpiece& out, std::string& err) {
+    if (!check_strings(d.vocab, "vocab", err)) return B200TOK_E_INVALID;
+    const std::string ind(d.suffix_indicator ? d.suffix_indicator : "", d.suffix_indicator ? (size_t)d.suffix_indicator_len : 0);
+    std::vector<std::pair<std::string, int32_t>> r, s;
+    for (int64_t i = 0; i < d.vocab.n; ++i) {
+        std::string w = str_at(d.vocab, i);
+        if (w.compare(0, ind.size(), ind) == 0 && w.size() >= ind.size()) s.emplace_back(w.substr(ind.size()), (int32_t)i);
+        else r.emplace_back(std::move(w), (int32_t)i);
+    }
+    out.root.build(r);
+    out.sub.build(s);
+    out.max_bytes = d.max_bytes_per_word;
+    return B200TOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// VocabEncoder table (vocab_encoder.cpp:63-78: insert => first duplicate key wins).
+// ------------------------------------------------------------------------------------------
+int build_vocabenc(const b200tok_vocabenc_desc& d, HostVocabEnc& out, std::string& err) {
+    if (!check_strings(d.keys, "vocab keys", err) || (d.keys.n > 0 && !d.values)) { if (err.empty()) err = "missing values"; return B200TOK_E_INVALID; }
+    size_t cap = 16;
+    while (cap < (size_t)d.keys.n * 2 + 2) cap <<= 1;
+    out.slots.assign(cap, VocabEncSlot{0, 0, -1, 0});
+    out.mask = (uint32_t)(cap - 1);
+    out.key_bytes.assign(d.keys.chars, d.keys.chars + d.keys.n_chars);
+    if (out.key_bytes.empty()) out.key_bytes.push_back(0);
+    out.max_len = 0;
+    for (int64_t i = 0; i < d.keys.n; ++i) {
+        const int32_t b = d.keys.begins[i], len = d.keys.ends[i] - b;
+        const uint64_t h = fnv1a64(d.keys.chars + b, len);
+        uint32_t k = (uint32_t)h & out.mask;
+        bool dup = false;
+        while (out.slots[k].len >= 0) {
+            const auto& sl = out.slots[k];
+            if (sl.hash == h && sl.len == len && std::memcmp(d.keys.chars + sl.begin, d.keys.chars + b, (size_t)len) == 0) { dup = true; break; }
+            k = (k + 1) & out.mask;
+        }
+        if (dup) continue;
+        const int64_t v = d.values_are_i64 ? ((const int64_t*)d.values)[i] : (int64_t)((const int32_t*)d.values)[i];
+        out.slots[k] = VocabEncSlot{h, b, len, v};
+        out.max_len = std::max(out.max_len, len);
+    }
+    return B200TOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Split pattern recognition.
+// ------------------------------------------------------------------------------------------
+static const char* kGpt2 = R"('s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+)";
+static const char* kGpt2Digits = R"('s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+)";
+static const char* kLlama3 = R"((?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+)";
+static const char* kBertPunct =
+    R"([!-/]|[:-@]|[\[-`]|[{-~]|[\p{P}]|[\x{4E00}-\x{9FFF}]|[\x{3400}-\x{4DBF}]|[\x{20000}-\x{2A6DF}]|[\x{2A700}-\x{2B73F}]|[\x{2B740}-\x{2B81F}]|[\x{2B820}-\x{2CEAF}]|[\x{F900}-\x{FAFF}]|[\x{2F800}-\x{2FA1F}])";
+
+int parse_split(const b200tok_regexsplit_desc& d, HostSplit& out, std::string& err) {
+    if (!d.pattern || d.pattern_len < 0 || !d.behaviour) { err = "RegexSplit: missing pattern or behaviour"; return B200TOK_E_INVALID; }
+    const std::string pat(d.pattern, (size_t)d.pattern_len), beh(d.behaviour);
+    // modes: src/regex_split.cpp:16-22
+    if (beh == "remove") out.mode = MODE_REMOVED;
+    else if (beh == "isolate" || beh == "contiguous") out.mode = MODE_ISOLATED;
+    else if (beh == "mergedwithprevious") out.mode = MODE_MERGED_PREV;
+    else if (beh == "mergedwithnext") out.mode = MODE_MERGED_NEXT;
+    else { err = "RegexSplit doesn't support unknown split mode: " + beh; return B200TOK_E_INVALID; }
+    if (!(d.max_splits == -1 || d.max_splits > 0)) {   // src/regex_split.cpp:114-117
+        err = "RegexSplit max_splits attribute must be greater then `0` or equal to `-1`, got " + std::to_string(d.max_splits);
+        return B200TOK_E_INVALID;
+    }
+    out.invert = d.invert != 0;
+    out.max_splits = d.max_splits;
+    out.pattern = pat;
+    out.repeat = beh == "contiguous" && !pat.empty() && pat.back() != '+';   // :33-37
+    out.spec = SplitSpec{};
+    auto cls = [&](uint8_t mask) { out.spec.pat = PAT_CLASS_CHAR; out.spec.class_mask = mask; return B200TOK_OK; };
+    if (pat == kGpt2) { out.spec.pat = PAT_GPT2; return B200TOK_OK; }
+    if (pat == kGpt2Digits) { out.spec.pat = PAT_GPT2_DIGITS; return B200TOK_OK; }
+    if (pat == kLlama3) { out.spec.pat = PAT_LLAMA3; return B200TOK_OK; }
+    if (pat == R"(\s+)") { out.spec.pat = PAT_WS; return B200TOK_OK; }
+    if (pat == kBertPunct) { out.spec.pat = PAT_BERT_PUNCT; return B200TOK_OK; }
+    if (pat == R"(\w+|[^\w\s]+)") { out.spec.pat = PAT_WORD_OR_PUNCT; return B200TOK_OK; }
+    if (pat == ".") { out.spec.pat = PAT_ANYCHAR; return B200TOK_OK; }
+    if (pat == R"(\p{N})" || pat == R"(\p{Nd}|\p{Nl}|\p{No})") return cls(C_N);
+    if (pat == R"(\p{P})" || pat == R"([\p{P}])") return cls(C_P);
+    if (pat == R"(\p{Nd}|\p{Nl}|\p{No}|\p{P})" || pat == R"(\p{P}|\p{Nd}|\p{Nl}|\p{No})") return cls(C_N | C_P);
+    if (pat == R"(\p{L})") return cls(C_L);
+    // a literal: no regex metacharacters at all (metaspace "▁", " ", ...)
+    if (!pat.empty() && pat.size() <= sizeof(out.spec.lit) && pat.find_first_of("\\^$.|?*+()[]{}") == std::string::npos) {
+        out.spec.pat = PAT_LITERAL;
+        out.spec.lit_len = (uint8_t)pat.size();
+        std::memcpy(out.spec.lit, pat.data(), pat.size());
+        return B200TOK_OK;
+    }
+    err = "RegexSplit: pattern is not one of the tokenizer patterns the GPU splitter implements: " + pat;
+    return B200TOK_E_UNSUPPORTED;
+}
+
+}  // namespace b200tok

@@ -1,0 +1,89 @@
+// tables.hpp — host-side construction of the read-only device tables (pure C++17, no CUDA).
+// Corresponds to the reference's lazy first-evaluate initialisation:
+//   BPETokenizer::evaluate call_once block   src/bpe_tokenizer.cpp:50-120
+//   BPETokenizerImpl ctor                     src/bpe_tokenizer.cpp:341-388
+//   WordpieceTokenizer trie construction      src/wordpiece_tokenizer.cpp:50-73
+//   VocabEncoder map construction             src/vocab_encoder.cpp:63-78
+//   RegexSplit::compile_pattern_if_necessary  src/regex_split.cpp:26-39
+#pragma once
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b200tok.h"
+#include "tok_core.cuh"
+
+namespace b200tok {
+
+struct HostClassTables {
+    std::vector<uint8_t> ascii;
+    std::vector<uint16_t> stage1;
+    std::vector<uint8_t> stage2;
+    ClassTables view() const { return ClassTables{ascii.data(), stage1.data(), stage2.data()}; }
+};
+const HostClassTables& host_class_tables();
+
+struct HostTrie {
+    std::vector<int32_t> first, value, edge_child, root_child;
+    std::vector<uint8_t> edge_byte;
+    // entries: (key bytes, id); later duplicates of a key overwrite earlier ones; empty keys ignored
+    void build(const std::vector<std::pair<std::string, int32_t>>& entries);
+    FlatTrie view() const {
+        return FlatTrie{first.data(), value.data(), edge_byte.data(), edge_child.data(), root_child.data()};
+    }
+    size_t n_nodes() const { return value.size(); }
+};
+
+struct HostBpe {
+    std::vector<int32_t> byte_sym, byte_miss;
+    HostTrie trie;
+    std::vector<MergeSlot> slots;
+    uint32_t mask = 0;
+    std::string end_suffix;
+    int32_t unk_id = -1;
+    int64_t n_merges = 0;
+    int64_t n_duplicate_products = 0;   // merges whose product token another merge also produces (tie hazard)
+    bool bytes_only = false;            // every byte symbolises without a trie walk
+    BpeTables view() const {
+        return BpeTables{byte_sym.data(), byte_miss.data(), trie.view(), MergeTable{slots.data(), mask}};
+    }
+};
+// returns B200TOK_OK or an error code (message in err)
+int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err);
+
+struct HostWordpiece {
+    HostTrie root, sub;
+    int32_t max_bytes = 100;
+    WordpieceTables view() const { return WordpieceTables{root.view(), sub.view(), max_bytes}; }
+};
+int build_wordpiece(const b200tok_wordpiece_desc& d, HostWordpiece& out, std::string& err);
+
+// String -> value open-addressing table for VocabEncoder (FNV-1a 64; full key compare on hit).
+struct VocabEncSlot { uint64_t hash; int32_t begin, len; int64_t value; };   // len < 0 => empty
+struct HostVocabEnc {
+    std::vector<VocabEncSlot> slots;
+    std::vector<uint8_t> key_bytes;
+    uint32_t mask = 0;
+    int32_t max_len = 0;
+};
+int build_vocabenc(const b200tok_vocabenc_desc& d, HostVocabEnc& out, std::string& err);
+
+enum SplitMode : int { MODE_REMOVED = 0, MODE_ISOLATED = 1, MODE_MERGED_PREV = 2, MODE_MERGED_NEXT = 3 };
+struct HostSplit {
+    SplitSpec spec{};
+    int mode = MODE_REMOVED;
+    bool invert = false;
+    int max_splits = -1;
+    bool repeat = false;   // "contiguous" rewrite (p)+ applied (src/regex_split.cpp:33-37)
+    std::string pattern;
+};
+int parse_split(const b200tok_regexsplit_desc& d, HostSplit& out, std::string& err);
+
+inline uint64_t fnv1a64(const uint8_t* p, int64_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (int64_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+}  // namespace b200tok

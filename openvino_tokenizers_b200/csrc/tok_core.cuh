@@ -1,0 +1,695 @@
+// tok_core.cuh — the algorithmic core of the hot path, written once as __host__ __device__ inline
+// functions over plain pointers.  The CUDA kernels (kernels.cu) call these on shared / global
+// memory; tests/harness compiles the very same header with g++ so that the matching, merge and
+// trie logic can be checked against the oracle in the CPU-only test tier (the harness is test
+// code: the product library has no CPU execution path).
+//
+// Reference semantics restated here (paths relative to /root/reference):
+//   * regex matching for the tokenizer patterns  — PCRE2 leftmost / ordered-alternation /
+//     backtracking semantics as driven by src/regex_split.cpp:287-309 and src/utils.cpp:396-420
+//   * BPE merge order (rank, push-sequence)       — src/bpe_tokenizer.cpp:166-172,269-323
+//   * trie longest match                          — src/utils.cpp:517-538
+//   * WordPiece word loop                         — src/wordpiece_tokenizer.cpp:96-130
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b200tok {
+
+// ------------------------------------------------------------------------------------------
+// Character classes (PCRE2_UTF|PCRE2_UCP semantics; tables generated from PCRE2 itself).
+// ------------------------------------------------------------------------------------------
+enum : uint8_t {
+    C_L = 1,      // \p{L}
+    C_N = 2,      // \p{N}
+    C_S = 4,      // \s
+    C_P = 8,      // \p{P}
+    C_W = 16,     // \w
+    C_BP = 32,    // BERT "punctuation or CJK" class (tokenizer_pipeline.py:403-431)
+    C_NL = 64,    // \r or \n
+    C_CONT = 128  // UTF-8 continuation byte (class bits copied from the owning character)
+};
+
+struct ClassTables {
+    const uint8_t* ascii;     // [128]
+    const uint16_t* stage1;   // [0x1100]  cp >> 8 -> block
+    const uint8_t* stage2;    // [n_blocks * 256]
+};
+
+B2_HD bool is_cont_byte(uint8_t b) { return (b & 0xC0) == 0x80; }
+
+// Class of the character whose first byte is s[i]; `end` bounds the character's bytes.
+// Malformed sequences (out of contract for the reference: PCRE2 JIT skips validation,
+// SURVEY App. B item 6) are classified as "other" deterministically.
+B2_HD uint8_t char_class(const uint8_t* s, int i, int end, const ClassTables& t) {
+    const uint8_t b0 = s[i];
+    if (b0 < 0x80) return t.ascii[b0];
+    const int need = b0 >= 0xF0 ? 3 : b0 >= 0xE0 ? 2 : b0 >= 0xC0 ? 1 : -1;
+    if (need < 0 || b0 >= 0xF8 || i + need >= end) return 0;
+    uint32_t cp = need == 1 ? (b0 & 0x1Fu) : need == 2 ? (b0 & 0x0Fu) : (b0 & 0x07u);
+    for (int k = 1; k <= need; ++k) {
+        const uint8_t b = s[i + k];
+        if (!is_cont_byte(b)) return 0;
+        cp = (cp << 6) | (b & 0x3Fu);
+    }
+    if (cp >= 0x110000u) return 0;
+    return t.stage2[(uint32_t)t.stage1[cp >> 8] * 256u + (cp & 255u)];
+}
+
+// ------------------------------------------------------------------------------------------
+// Split patterns the GPU splitter implements.  Each is a direct transcription of the regex's
+// alternatives in order (PCRE2 tries alternatives left to right and takes the first that
+// matches, with greedy quantifiers and backtracking).
+// ------------------------------------------------------------------------------------------
+enum PatternId : int {
+    PAT_NONE = 0,
+    PAT_GPT2 = 1,          // 's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
+    PAT_GPT2_DIGITS = 2,   // same with \p{N} in place of " ?\p{N}+"
+    PAT_LLAMA3 = 3,        // (?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+    PAT_WS = 4,            // \s+
+    PAT_BERT_PUNCT = 5,    // [!-/]|[:-@]|[\[-`]|[{-~]|[\p{P}]|<CJK ranges>
+    PAT_WORD_OR_PUNCT = 6, // \w+|[^\w\s]+
+    PAT_LITERAL = 7,       // one literal string (metaspace etc.)
+    PAT_ANYCHAR = 8,       // .
+    PAT_CLASS_CHAR = 9,    // one character of a class: \p{N} == \p{Nd}|\p{Nl}|\p{No}, or \p{P}
+    PAT_BERT_FUSED = 10    // internal: \s+ (remove) followed by PAT_BERT_PUNCT (isolate), one pass
+};
+
+// Partition of characters into "kinds" such that every quantified class of the pattern is a
+// maximal run of one kind.
+B2_HD int kind_of(uint8_t cls, int pat, uint8_t class_mask) {
+    switch (pat) {
+    case PAT_GPT2: case PAT_GPT2_DIGITS: case PAT_LLAMA3:
+        return (cls & C_L) ? 0 : (cls & C_N) ? 1 : (cls & C_S) ? 2 : 3;
+    case PAT_WS: return (cls & C_S) ? 2 : 3;
+    case PAT_BERT_PUNCT: return (cls & C_BP) ? 1 : 3;
+    case PAT_BERT_FUSED: return (cls & C_S) ? 2 : (cls & C_BP) ? 1 : 3;
+    case PAT_WORD_OR_PUNCT: return (cls & C_W) ? 0 : (cls & C_S) ? 2 : 3;
+    case PAT_CLASS_CHAR: return (cls & class_mask) ? 1 : 3;
+    default: return 3;
+    }
+}
+
+struct SplitSpec {
+    int pat;
+    uint8_t class_mask;       // PAT_CLASS_CHAR
+    uint8_t lit_len;          // PAT_LITERAL
+    uint8_t lit[22];
+};
+
+struct Match {
+    int len;    // 0 => the pattern does not match at p
+    int peek;   // 1 + highest byte index examined while deciding
+    int drop;   // PAT_BERT_FUSED only: 1 => this match is a removed delimiter (whitespace)
+};
+
+// A context gives the matcher random access to one element [lo, end) of the chars buffer.
+//   byte(i), cls(i): defined for lo <= i < lim()
+//   run_end(i): end (exclusive, <= known()) of the maximal same-kind run starting at char i
+//   last_nl(i): index of the last \r|\n inside the \s-run that contains i, at or after i; -1 if none
+//   known(): everything below this index is exact; lim(): bytes below this index may be read
+// ScanCtx computes everything by scanning (used for pieces that outgrow a shared-memory window,
+// and by the host harness); the kernels' window context reads precomputed arrays.
+struct ScanCtx {
+    const uint8_t* s;
+    int end;
+    ClassTables t;
+    int pat;
+    uint8_t class_mask;
+    B2_HD int known() const { return end; }
+    B2_HD int lim() const { return end; }
+    B2_HD uint8_t byte(int i) const { return s[i]; }
+    B2_HD uint8_t cls(int i) const { return (i > 0 && is_cont_byte(s[i])) ? (uint8_t)C_CONT : char_class(s, i, end, t); }
+    B2_HD int next(int i) const {
+        ++i;
+        while (i < end && is_cont_byte(s[i])) ++i;
+        return i;
+    }
+    B2_HD int run_end(int i) const {
+        const int k = kind_of(cls(i), pat, class_mask);
+        int j = next(i);
+        while (j < end && kind_of(cls(j), pat, class_mask) == k) j = next(j);
+        return j;
+    }
+    B2_HD int last_nl(int i) const {
+        int r = -1;
+        for (int j = i; j < end; j = next(j)) {
+            const uint8_t c = cls(j);
+            if (!(c & C_S)) break;
+            if (c & C_NL) r = j;
+        }
+        return r;
+    }
+};
+
+template <class C>
+B2_HD bool ctx_has(const C& c, int i, int& peek) {
+    if (i + 1 > peek) peek = i + 1;
+    return i < c.lim();
+}
+
+template <class C>
+B2_HD int prev_char_start(const C& c, int e, int lo) {
+    int j = e - 1;
+    while (j > lo && (c.cls(j) & C_CONT)) --j;
+    return j;
+}
+
+// \s+(?!\S) | \s+   at a whitespace character p  (shared by GPT-2 and Llama-3 patterns)
+template <class C>
+B2_HD Match match_ws_tail(const C& c, int p, int end, int peek) {
+    const int e = c.run_end(p);
+    if (e + 1 > peek) peek = e + 1;
+    if (e >= end) return Match{e - p, peek, 0};          // (?!\S) holds at end of subject
+    const int last = prev_char_start(c, e, p);
+    if (last > p) return Match{last - p, peek, 0};       // give back one character
+    return Match{e - p, peek, 0};                        // single whitespace char: plain \s+
+}
+
+template <class C>
+B2_HD Match match_gpt2(const C& c, int p, int end, bool single_digits) {
+    int peek = p + 1;
+    const uint8_t b0 = c.byte(p);
+    const uint8_t k0 = c.cls(p);
+    if (b0 == '\'') {  // 's|'t|'re|'ve|'m|'ll|'d
+        if (ctx_has(c, p + 1, peek) && p + 1 < end) {
+            const uint8_t b1 = c.byte(p + 1);
+            if (b1 == 's' || b1 == 't' || b1 == 'm' || b1 == 'd') return Match{2, peek, 0};
+            if ((b1 == 'r' || b1 == 'v' || b1 == 'l') && ctx_has(c, p + 2, peek) && p + 2 < end) {
+                const uint8_t b2 = c.byte(p + 2);
+                if ((b1 == 'l') ? (b2 == 'l') : (b2 == 'e')) return Match{3, peek, 0};
+            }
+        }
+    }
+    int q = p;
+    uint8_t kq = k0;
+    if (b0 == ' ' && ctx_has(c, p + 1, peek) && p + 1 < end) {  // optional leading U+0020
+        const uint8_t k1 = c.cls(p + 1);
+        if (!(k1 & C_S) && !(single_digits && (k1 & C_N))) { q = p + 1; kq = k1; }
+    }
+    if (!(kq & C_S)) {
+        if (single_digits && (kq & C_N)) {  // \p{N}
+            const int e = c.next(q);
+            return Match{e - p, peek > e ? peek : e, 0};
+        }
+        const int e = c.run_end(q);   //  ?\p{L}+ |  ?\p{N}+ |  ?[^\s\p{L}\p{N}]+
+        if (e + 1 > peek) peek = e + 1;
+        return Match{e - p, peek, 0};
+    }
+    return match_ws_tail(c, p, end, peek);
+}
+
+B2_HD bool ci_eq(uint8_t b, char lower) { return (b | 0x20) == (uint8_t)lower && ((b | 0x20) >= 'a'); }
+
+template <class C>
+B2_HD Match match_llama3(const C& c, int p, int end) {
+    int peek = p + 1;
+    const uint8_t b0 = c.byte(p);
+    const uint8_t k0 = c.cls(p);
+    if (b0 == '\'' && ctx_has(c, p + 1, peek) && p + 1 < end) {  // (?i:'s|'t|'re|'ve|'m|'ll|'d)
+        const uint8_t b1 = c.byte(p + 1);
+        if (ci_eq(b1, 's') || ci_eq(b1, 't') || ci_eq(b1, 'm') || ci_eq(b1, 'd')) return Match{2, peek, 0};
+        if (ctx_has(c, p + 2, peek) && p + 2 < end) {
+            const uint8_t b2 = c.byte(p + 2);
+            if (b1 == 0xC5 && b2 == 0xBF) return Match{3, peek, 0};  // U+017F folds to 's' under PCRE2 caseless UTF
+            if ((ci_eq(b1, 'r') || ci_eq(b1, 'v')) && ci_eq(b2, 'e')) return Match{3, peek, 0};
+            if (ci_eq(b1, 'l') && ci_eq(b2, 'l')) return Match{3, peek, 0};
+        }
+    }
+    // [^\r\n\p{L}\p{N}]?\p{L}+
+    if (k0 & C_L) {
+        const int e = c.run_end(p);
+        if (e + 1 > peek) peek = e + 1;
+        return Match{e - p, peek, 0};
+    }
+    if (!(k0 & (C_N | C_NL))) {
+        const int q = c.next(p);
+        if (ctx_has(c, q, peek) && q < end && (c.cls(q) & C_L)) {
+            const int e = c.run_end(q);
+            if (e + 1 > peek) peek = e + 1;
+            return Match{e - p, peek, 0};
+        }
+    }
+    // \p{N}{1,3}
+    if (k0 & C_N) {
+        const int re = c.run_end(p);
+        if (re + 1 > peek) peek = re + 1;
+        int e = c.next(p), n = 1;
+        while (n < 3 && e < re) { e = c.next(e); ++n; }
+        return Match{e - p, peek, 0};
+    }
+    //  ?[^\s\p{L}\p{N}]+[\r\n]*
+    {
+        int q = p;
+        uint8_t kq = k0;
+        if (b0 == ' ' && ctx_has(c, p + 1, peek) && p + 1 < end) { q = p + 1; kq = c.cls(q); }
+        if (!(kq & (C_L | C_N | C_S))) {
+            int e = c.run_end(q);
+            while (ctx_has(c, e, peek) && e < end && (c.byte(e) == '\r' || c.byte(e) == '\n')) ++e;
+            return Match{e - p, peek, 0};
+        }
+    }
+    // here k0 is whitespace:  \s*[\r\n]+ | \s+(?!\S) | \s+
+    {
+        const int e = c.run_end(p);
+        if (e + 1 > peek) peek = e + 1;
+        const int j = c.last_nl(p);
+        if (j >= 0) return Match{j + 1 - p, peek, 0};
+    }
+    return match_ws_tail(c, p, end, peek);
+}
+
+// Returns the match of `spec` anchored at character position p of the element ending at `end`.
+template <class C>
+B2_HD Match match_at(const C& c, const SplitSpec& spec, int p, int end) {
+    switch (spec.pat) {
+    case PAT_GPT2: return match_gpt2(c, p, end, false);
+    case PAT_GPT2_DIGITS: return match_gpt2(c, p, end, true);
+    case PAT_LLAMA3: return match_llama3(c, p, end);
+    case PAT_WS: {
+        if (!(c.cls(p) & C_S)) return Match{0, p + 1, 0};
+        const int e = c.run_end(p);
+        return Match{e - p, e + 1, 0};
+    }
+    case PAT_BERT_PUNCT: case PAT_CLASS_CHAR: {
+        const uint8_t m = spec.pat == PAT_BERT_PUNCT ? (uint8_t)C_BP : spec.class_mask;
+        if (!(c.cls(p) & m)) return Match{0, p + 1, 0};
+        const int e = c.next(p);
+        return Match{e - p, e, 0};
+    }
+    case PAT_BERT_FUSED: {
+        const uint8_t k = c.cls(p);
+        if (k & C_S) { const int e = c.run_end(p); return Match{e - p, e + 1, 1}; }
+        if (k & C_BP) { const int e = c.next(p); return Match{e - p, e, 0}; }
+        return Match{0, p + 1, 0};
+    }
+    case PAT_WORD_OR_PUNCT: {
+        if (c.cls(p) & C_S) return Match{0, p + 1, 0};
+        const int e = c.run_end(p);
+        return Match{e - p, e + 1, 0};
+    }
+    case PAT_ANYCHAR: {
+        if (c.byte(p) == '\n') return Match{0, p + 1, 0};
+        const int e = c.next(p);
+        return Match{e - p, e, 0};
+    }
+    case PAT_LITERAL: {
+        int peek = p + 1;
+        for (int k = 0; k < spec.lit_len; ++k) {
+            if (!ctx_has(c, p + k, peek) || p + k >= end || c.byte(p + k) != spec.lit[k]) return Match{0, peek, 0};
+        }
+        return Match{(int)spec.lit_len, peek, 0};
+    }
+    default: return Match{0, p + 1, 0};
+    }
+}
+
+// (p)+ for the "contiguous" rewrite (src/regex_split.cpp:33-37): greedy repetition of the pattern.
+template <class C>
+B2_HD Match match_rep(const C& c, const SplitSpec& spec, bool repeat, int p, int end) {
+    Match m = match_at(c, spec, p, end);
+    if (!repeat || m.len == 0) return m;
+    int q = p + m.len;
+    while (q < end && q < c.known()) {
+        const Match n = match_at(c, spec, q, end);
+        if (n.peek > m.peek) m.peek = n.peek;
+        if (n.len == 0) break;
+        q += n.len;
+    }
+    if (q >= c.known() && q < end && q + 1 > m.peek) m.peek = q + 1;
+    m.len = q - p;
+    return m;
+}
+
+// The behaviour logic of RegexSplit's add_split lambda (src/regex_split.cpp:243-284), kept in the
+// reference's element-relative coordinates including its quirks: `last_begin` is never reset,
+// an unset last_begin (-1) clamps to 0, and `max_splits` only stretches the end of one piece.
+enum : int { SPLIT_REMOVED = 0, SPLIT_ISOLATED = 1, SPLIT_MERGED_PREV = 2, SPLIT_MERGED_NEXT = 3 };
+struct SplitEmitter {
+    int mode;
+    bool invert;
+    int max_splits;
+    int len;            // element length in bytes
+    int64_t last_begin; // -1 = unset (size_t(-1) in the reference)
+    uint32_t n_splits;
+    B2_HD void reset(int mode_, bool invert_, int max_splits_, int len_) {
+        mode = mode_; invert = invert_; max_splits = max_splits_; len = len_; last_begin = -1; n_splits = 0;
+    }
+    // Returns true if a piece [ob, oe) (relative to the element) is produced.
+    B2_HD bool add(int begin, int end, bool inv, int& ob, int& oe) {
+        switch (mode) {
+        case SPLIT_REMOVED: if (inv) return false; break;
+        case SPLIT_ISOLATED: break;
+        case SPLIT_MERGED_PREV:
+            if (!inv && end != len) { last_begin = begin; return false; }
+            else if (inv) begin = (int)last_begin;
+            break;
+        case SPLIT_MERGED_NEXT:
+            if (!inv) { if (last_begin != -1) begin = (int)last_begin; }
+            else { last_begin = begin; return false; }
+            break;
+        }
+        if (begin < 0) begin = 0;
+        if (end > len) end = len;
+        if (n_splits == (uint32_t)max_splits) end = len;
+        ob = begin; oe = end;
+        ++n_splits;
+        return true;
+    }
+    // after the match loop (src/regex_split.cpp:302-309); `start` = end of the last match
+    B2_HD bool finish(int start, int& ob, int& oe) {
+        if (start < len) return add(start, len, invert, ob, oe);
+        if (mode == SPLIT_MERGED_NEXT && last_begin != (int64_t)len) return add((int)last_begin, len, invert, ob, oe);
+        return false;
+    }
+};
+
+// Sequential split of one element [lo, end) (reference loop src/regex_split.cpp:287-309).
+// sink(b, e) receives absolute piece offsets.  Used for elements that outgrow the window path
+// and by the host harness; the window kernels run the same chain in parallel.
+template <class C, class Sink>
+B2_HD void split_element_scan(const C& c, const SplitSpec& spec, bool repeat, int lo, int end,
+                              SplitEmitter& em, Sink&& sink) {
+    em.len = end - lo;
+    int start = lo, p = lo, ob, oe;
+    while (p < end) {
+        const Match m = match_rep(c, spec, repeat, p, end);
+        if (m.len > 0) {
+            if (p != start && em.add(start - lo, p - lo, em.invert, ob, oe)) sink(lo + ob, lo + oe);
+            if (em.add(p - lo, p + m.len - lo, !em.invert, ob, oe)) sink(lo + ob, lo + oe);
+            p += m.len;
+            start = p;
+        } else {
+            p = c.next(p);
+        }
+    }
+    if (em.finish(start - lo, ob, oe)) sink(lo + ob, lo + oe);
+}
+
+// ------------------------------------------------------------------------------------------
+// Merge-rank table: open addressing over (left,right) -> (rank,new_id), 16-byte slots so one
+// probe is one vector load.  (The reference's MergesMap, src/bpe_tokenizer.hpp:40-115, plays the
+// same role on the CPU; hash function and load factor here are our own.)
+// ------------------------------------------------------------------------------------------
+struct MergeSlot { uint32_t left, right; int32_t rank, new_id; };
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr int32_t kNoRank = 0x7FFFFFFF;
+
+B2_HD uint32_t merge_hash(uint32_t l, uint32_t r) {
+    uint32_t h = l * 0x9E3779B1u ^ (r + 0x7F4A7C15u) * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
+}
+
+struct MergeTable {
+    const MergeSlot* slots;
+    uint32_t mask;
+};
+
+#if defined(__CUDA_ARCH__)
+B2_HD MergeSlot load_slot(const MergeSlot* p) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    return MergeSlot{(uint32_t)v.x, (uint32_t)v.y, v.z, v.w};
+}
+#else
+B2_HD MergeSlot load_slot(const MergeSlot* p) { return *p; }
+#endif
+
+B2_HD bool merge_find(const MergeTable& t, int32_t l, int32_t r, int32_t& rank, int32_t& new_id) {
+    uint32_t h = merge_hash((uint32_t)l, (uint32_t)r) & t.mask;
+    for (;;) {
+        const MergeSlot s = load_slot(t.slots + h);
+        if (s.left == (uint32_t)l && s.right == (uint32_t)r) { rank = s.rank; new_id = s.new_id; return true; }
+        if (s.left == kEmptyKey) { rank = kNoRank; new_id = -1; return false; }
+        h = (h + 1) & t.mask;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Flattened byte trie (longest match).  Node n owns edges [first[n], first[n+1]) sorted by byte.
+// ------------------------------------------------------------------------------------------
+struct FlatTrie {
+    const int32_t* first;       // [n_nodes + 1]
+    const int32_t* value;       // [n_nodes]   (-1 = no token ends here)
+    const uint8_t* edge_byte;   // [n_edges]
+    const int32_t* edge_child;  // [n_edges]
+    const int32_t* root_child;  // [256] child of the root per byte, -1 if none
+};
+
+B2_HD int32_t trie_child(const FlatTrie& t, int32_t node, uint8_t ch) {
+    int32_t lo = t.first[node], hi = t.first[node + 1];
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        const uint8_t b = t.edge_byte[mid];
+        if (b == ch) return t.edge_child[mid];
+        if (b < ch) lo = mid + 1; else hi = mid;
+    }
+    return -1;
+}
+
+// Longest match starting at s[idx] (idx < end).  On success returns the token id and advances
+// idx to the end of the match; otherwise returns -1 and leaves idx unchanged (utils.cpp:517-538).
+B2_HD int32_t trie_longest(const FlatTrie& t, const uint8_t* s, int& idx, int end) {
+    int32_t node = t.root_child[s[idx]];
+    int32_t found = -1;
+    int best = idx, i = idx;
+    while (node >= 0) {
+        ++i;
+        const int32_t v = t.value[node];
+        if (v != -1) { found = v; best = i; }
+        if (i >= end) break;
+        node = trie_child(t, node, s[i]);
+    }
+    idx = best;
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------
+// BPE.  Per-byte symbolisation tables are precomputed on the host from the trie over
+// "vocab minus merge products" (src/bpe_tokenizer.cpp:375-386):
+//   byte_sym[c]  >= 0  : c starts no longer token; the single-byte token id
+//                == -2 : must walk the trie (a longer token starts with c)
+//                == -1 : no token starts with c (use byte_miss)
+//   byte_miss[c] >= 0  : <0xNN> byte-fallback id or the unk id (src/bpe_tokenizer.cpp:242-254)
+//                == -1 : the byte is dropped
+// ------------------------------------------------------------------------------------------
+struct BpeTables {
+    const int32_t* byte_sym;   // [256]
+    const int32_t* byte_miss;  // [256]
+    FlatTrie trie;
+    MergeTable merges;
+};
+constexpr int32_t kSymWalk = -2;
+
+// Symbolise s[b..e) (+ optional suffix bytes) into ids[]; returns the number of symbols.
+B2_HD int bpe_symbolize(const BpeTables& T, const uint8_t* s, int b, int e, int32_t* ids) {
+    int n = 0;
+    for (int i = b; i < e;) {
+        const uint8_t c = s[i];
+        int32_t id = T.byte_sym[c];
+        if (id == kSymWalk) {
+            int j = i;
+            id = trie_longest(T.trie, s, j, e);
+            if (id >= 0) { ids[n++] = id; i = j; continue; }
+            id = -1;
+        }
+        if (id < 0) id = T.byte_miss[c];
+        if (id >= 0) ids[n++] = id;
+        ++i;
+    }
+    return n;
+}
+
+// In-place merge loop for a piece of n symbols held in ids[0..n).  rank/newid/birth are scratch
+// arrays of at least n-1 entries.  Order: smallest (rank, birth) first, where birth is the
+// reference's push-sequence number: pair k of the initial sequence gets k, and the (up to two)
+// pairs created by the m-th merge get n-1+m  (src/bpe_tokenizer.cpp:269-285,314-322).
+// Returns the number of tokens left in ids[].
+template <class BirthT>
+B2_HD int bpe_merge_serial(const MergeTable& M, int32_t* ids, int32_t* rank, int32_t* newid, BirthT* birth, int n) {
+    if (n < 2) return n;
+    bool any = false;
+    for (int k = 0; k + 1 < n; ++k) {
+        int32_t r, v;
+        any |= merge_find(M, ids[k], ids[k + 1], r, v);
+        rank[k] = r; newid[k] = v; birth[k] = (BirthT)k;
+    }
+    if (!any) return n;
+    int seq = n - 1;
+    while (n >= 2) {
+        int32_t best = kNoRank;
+        int bk = -1;
+        uint32_t bb = 0xFFFFFFFFu;
+        for (int k = 0; k + 1 < n; ++k) {
+            const int32_t r = rank[k];
+            if (r < best || (r == best && r != kNoRank && (uint32_t)birth[k] < bb)) { best = r; bk = k; bb = (uint32_t)birth[k]; }
+        }
+        if (bk < 0) break;
+        ids[bk] = newid[bk];
+        for (int k = bk + 1; k + 1 < n; ++k) ids[k] = ids[k + 1];
+        for (int k = bk + 1; k + 2 < n; ++k) { rank[k] = rank[k + 1]; newid[k] = newid[k + 1]; birth[k] = birth[k + 1]; }
+        --n;
+        ++seq;
+        if (bk > 0) {
+            int32_t r, v;
+            merge_find(M, ids[bk - 1], ids[bk], r, v);
+            rank[bk - 1] = r; newid[bk - 1] = v; birth[bk - 1] = (BirthT)seq;
+        }
+        if (bk + 1 < n) {
+            int32_t r, v;
+            merge_find(M, ids[bk], ids[bk + 1], r, v);
+            rank[bk] = r; newid[bk] = v; birth[bk] = (BirthT)seq;
+        }
+    }
+    return n;
+}
+
+// Same loop with (rank, birth) packed into one 32-bit key = rank << 12 | birth, so the argmin is a
+// single unsigned compare and the state fits in shared memory.  Valid for n <= 2048 symbols
+// (birth <= 2n-2 < 4096) and ranks < 2^20; the table builder enforces the latter.
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+constexpr int kPackedBirthBits = 12;
+constexpr int kPackedMaxSymbols = 2048;
+B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int32_t* newid, int n) {
+    if (n < 2) return n;
+    bool any = false;
+    for (int k = 0; k + 1 < n; ++k) {
+        int32_t r, v;
+        const bool f = merge_find(M, ids[k], ids[k + 1], r, v);
+        any |= f;
+        key[k] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)k) : kNoKey;
+        newid[k] = v;
+    }
+    if (!any) return n;
+    int seq = n - 1;
+    while (n >= 2) {
+        uint32_t best = kNoKey;
+        int bk = -1;
+        for (int k = 0; k + 1 < n; ++k) {
+            const uint32_t q = key[k];
+            if (q < best) { best = q; bk = k; }
+        }
+        if (bk < 0) break;
+        ids[bk] = newid[bk];
+        for (int k = bk + 1; k + 1 < n; ++k) ids[k] = ids[k + 1];
+        for (int k = bk + 1; k + 2 < n; ++k) { key[k] = key[k + 1]; newid[k] = newid[k + 1]; }
+        --n;
+        ++seq;
+        if (bk > 0) {
+            int32_t r, v;
+            const bool f = merge_find(M, ids[bk - 1], ids[bk], r, v);
+            key[bk - 1] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
+            newid[bk - 1] = v;
+        }
+        if (bk + 1 < n) {
+            int32_t r, v;
+            const bool f = merge_find(M, ids[bk], ids[bk + 1], r, v);
+            key[bk] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
+            newid[bk] = v;
+        }
+    }
+    return n;
+}
+
+// Heap form of the same loop for very long pieces: O(n log n), state in caller-provided scratch.
+//   sym_id/prev/next : [2n]   (dead symbols have id == -1 after being merged)
+//   heap             : [3n] entries (at most n-1 initial pushes + 2 per merge)
+// Ties on (rank, birth) are broken left pair first (only reachable with duplicate vocab strings,
+// SURVEY App. B item 1).  Returns the token count; tokens are written to out[0..count).
+struct HeapEntry { int32_t rank, birth, a, b; };
+B2_HD bool heap_less(const HeapEntry& x, const HeapEntry& y) {
+    if (x.rank != y.rank) return x.rank < y.rank;
+    if (x.birth != y.birth) return x.birth < y.birth;
+    return x.a < y.a;
+}
+B2_HD void heap_push(HeapEntry* h, int& n, HeapEntry e) {
+    int i = n++;
+    while (i > 0) {
+        const int p = (i - 1) >> 1;
+        if (!heap_less(e, h[p])) break;
+        h[i] = h[p];
+        i = p;
+    }
+    h[i] = e;
+}
+B2_HD HeapEntry heap_pop(HeapEntry* h, int& n) {
+    const HeapEntry top = h[0];
+    const HeapEntry last = h[--n];
+    int i = 0;
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= n) break;
+        if (c + 1 < n && heap_less(h[c + 1], h[c])) ++c;
+        if (!heap_less(h[c], last)) break;
+        h[i] = h[c];
+        i = c;
+    }
+    if (n > 0) h[i] = last;
+    return top;
+}
+B2_HD int bpe_merge_heap(const MergeTable& M, int n, int32_t* sym_id, int32_t* sym_prev, int32_t* sym_next,
+                         HeapEntry* heap, int32_t* out) {
+    if (n == 0) return 0;
+    int hn = 0, total = n, seq = 0;
+    for (int k = 0; k < n; ++k) { sym_prev[k] = k - 1; sym_next[k] = (k + 1 < n) ? k + 1 : -1; }
+    for (int k = 0; k + 1 < n; ++k) {
+        int32_t r, v;
+        if (merge_find(M, sym_id[k], sym_id[k + 1], r, v)) heap_push(heap, hn, HeapEntry{r, seq, k, k + 1});
+        ++seq;
+    }
+    int head = 0, live = n;
+    while (hn > 0 && live >= 2) {
+        const HeapEntry e = heap_pop(heap, hn);
+        if (sym_id[e.a] < 0 || sym_id[e.b] < 0 || sym_next[e.a] != e.b) continue;
+        int32_t r, v;
+        merge_find(M, sym_id[e.a], sym_id[e.b], r, v);
+        const int32_t pv = sym_prev[e.a], nx = sym_next[e.b], m = total++;
+        sym_id[m] = v; sym_prev[m] = pv; sym_next[m] = nx;
+        sym_id[e.a] = -1; sym_id[e.b] = -1;
+        if (pv != -1) sym_next[pv] = m; else head = m;
+        if (nx != -1) sym_prev[nx] = m;
+        --live;
+        ++seq;
+        int32_t r1, v1;
+        if (pv != -1 && merge_find(M, sym_id[pv], v, r1, v1)) heap_push(heap, hn, HeapEntry{r1, seq, pv, m});
+        int32_t r2, v2;
+        if (nx != -1 && merge_find(M, v, sym_id[nx], r2, v2)) heap_push(heap, hn, HeapEntry{r2, seq, m, nx});
+    }
+    int cnt = 0;
+    for (int k = head; k != -1; k = sym_next[k]) out[cnt++] = sym_id[k];
+    return cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// WordPiece: one word s[b..e) -> ids; returns count (>= 1).  src/wordpiece_tokenizer.cpp:96-130.
+// A zero-length word yields [unk] (the reference reads out of bounds there).
+// ------------------------------------------------------------------------------------------
+struct WordpieceTables {
+    FlatTrie root;
+    FlatTrie sub;
+    int32_t max_bytes;
+};
+
+B2_HD int wordpiece_word(const WordpieceTables& T, const uint8_t* s, int b, int e, int32_t unk, int32_t* out) {
+    if (e - b > T.max_bytes || e <= b) { out[0] = unk; return 1; }
+    int idx = b;
+    int32_t id = trie_longest(T.root, s, idx, e);
+    if (id < 0) { out[0] = unk; return 1; }
+    int n = 0;
+    out[n++] = id;
+    while (idx < e) {
+        id = trie_longest(T.sub, s, idx, e);
+        if (id < 0) { out[0] = unk; return 1; }
+        out[n++] = id;
+    }
+    return n;
+}
+
+}  // namespace b200tok

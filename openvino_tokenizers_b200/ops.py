@@ -1,0 +1,303 @@
+"""Host-side mirror of the reference's hot-path operators, over the C ABI (include/b200tok.h).
+
+Each class has the reference op's name, attributes and *input list* (the same tensors, in the same
+order, that `ov::Op::evaluate(outputs, inputs)` receives), and `evaluate(inputs)` returns the op's
+output list — so the parity tests read like the reference's own op tests.
+
+  RegexSplit          src/regex_split.{hpp,cpp}        6 / 7 inputs   -> 5 / 6 outputs
+  BPETokenizer        src/bpe_tokenizer.{hpp,cpp}      11/14/15/18    -> 3 outputs
+  WordpieceTokenizer  src/wordpiece_tokenizer.{hpp,cpp} 9 inputs      -> 3 outputs
+  VocabEncoder        src/vocab_encoder.{hpp,cpp}      8 inputs       -> 1 output
+  VocabDecoder        src/vocab_decoder.{hpp,cpp}      4 / 5 inputs   -> 5 outputs
+  ByteFallback        src/byte_fallback.{hpp,cpp}      3 inputs       -> 3 outputs
+
+All compute happens in libb200tok.so on the GPU; this module only marshals pointers.  Tables are
+built on the first `evaluate` from the Constant inputs (as the reference does under call_once).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+
+__all__ = ["RegexSplit", "BPETokenizer", "WordpieceTokenizer", "VocabEncoder", "VocabDecoder", "ByteFallback",
+           "split_bpe", "split_wordpiece", "B200TokError"]
+
+B200TokError = K.B200TokError
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    if isinstance(a, (bytes, bytearray)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class _Handle:
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launches(self) -> int:
+        return int(K.lib().b200tok_launch_count(self._h)) if self._h else 0
+
+    def close(self):
+        if self._h:
+            K.lib().b200tok_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ragged_in(rb, re_, begins, ends, chars, skips=None, keep=None):
+    rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+    sk = None if skips is None else _u8(np.asarray(skips, dtype=np.uint8))
+    keep.extend([rb, re_, begins, ends, chars, sk])
+    if len(begins) != len(ends) or len(rb) != len(re_):
+        raise ValueError("ragged string tensor: begins/ends length mismatch")
+    r = K.RaggedStrings(_ptr(rb), _ptr(re_), len(rb), _ptr(begins), _ptr(ends), len(begins), _ptr(chars), chars.size,
+                        _ptr(sk) if sk is not None else None, K.MEM_HOST)
+    return r
+
+
+def _ids_out(n_rows, capacity):
+    ob, oe = np.empty(n_rows, np.int32), np.empty(n_rows, np.int32)
+    ids = np.empty(max(capacity, 1), np.int32)
+    out = K.RaggedIds(_ptr(ob), _ptr(oe), _ptr(ids), capacity, 0, None, K.MEM_HOST)
+    return out, ob, oe, ids
+
+
+class RegexSplit(_Handle):
+    """RegexSplit(behaviour, invert, max_splits); inputs: ragged strings [0..4], optional skips [5], pattern."""
+
+    def __init__(self, behaviour="remove", invert=False, max_splits=-1, device=0):
+        super().__init__()
+        self.behaviour, self.invert, self.max_splits, self.device = behaviour, bool(invert), int(max_splits), device
+        self._pattern = None
+
+    def _ensure(self, pattern: bytes):
+        if self._h:
+            return
+        self._pattern = bytes(pattern)
+        d = K.RegexSplitDesc(self._pattern, len(self._pattern), self.behaviour.lower().encode(), int(self.invert),
+                             self.max_splits, self.device)
+        K.check(K.lib().b200tok_regexsplit_create(C.byref(d), C.byref(self._h)))
+
+    def with_pattern(self, pattern):
+        self._ensure(pattern.encode() if isinstance(pattern, str) else pattern)
+        return self
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (6, 7):
+            raise ValueError("Incorrect number of inputs passed to RegexSplit: %d" % len(inputs))
+        has_skips = len(inputs) == 7
+        self._ensure(_u8(inputs[5 + has_skips]).tobytes())
+        keep = []
+        rin = _ragged_in(*inputs[:5], skips=inputs[5] if has_skips else None, keep=keep)
+        n_rows, cap = rin.n_rows, rin.n_chars + rin.n_elems
+        orb, ore = np.empty(max(n_rows, 1), np.int32), np.empty(max(n_rows, 1), np.int32)
+        ob, oe = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32)
+        osk = np.empty(max(cap, 1), np.uint8) if has_skips else None
+        out = K.RaggedStringsOut(_ptr(orb), _ptr(ore), _ptr(ob), _ptr(oe), _ptr(osk) if has_skips else None, cap, 0, 0,
+                                 K.MEM_HOST)
+        K.check(K.lib().b200tok_regexsplit_run(self._h, C.byref(rin), C.byref(out), None))
+        P, R = out.n_elems, out.n_rows
+        res = [orb[:R].copy(), ore[:R].copy(), ob[:P].copy(), oe[:P].copy(), keep[4]]
+        if has_skips:
+            res.append(osk[:P].astype(bool))
+        return res
+
+
+class BPETokenizer(_Handle):
+    """BPETokenizer(unk_token, fuse_unk, suffix_indicator, end_suffix, byte_fallback, cache_capacity)."""
+
+    def __init__(self, unk_token="", fuse_unk=False, suffix_indicator="", end_suffix="", byte_fallback=False,
+                 cache_capacity=20000, device=0):
+        super().__init__()
+        enc = lambda s: s.encode() if isinstance(s, str) else bytes(s)
+        self.unk_token, self.suffix_indicator, self.end_suffix = enc(unk_token), enc(suffix_indicator), enc(end_suffix)
+        self.fuse_unk, self.byte_fallback, self.cache_capacity, self.device = bool(fuse_unk), bool(byte_fallback), int(cache_capacity), device
+
+    def _ensure(self, consts):
+        if self._h:
+            return
+        n = len(consts) + 5
+        if n not in (11, 14, 15, 18):
+            raise ValueError("Incorrect number of inputs passed to BPETokenizer, try to reconvert tokenizer with newer "
+                             "version of OpenVINO Tokenizers")
+        keep = []
+        d = K.BpeDesc()
+        d.vocab = K.make_strings(consts[0:3], keep)
+        d.merges_left = K.make_strings(consts[3:6], keep)
+        pairs = n in (14, 18)
+        d.merges_right = K.make_strings(consts[6:9], keep) if pairs else K.Strings(None, None, None, 0, 0)
+        if n in (15, 18):
+            a = consts[-4:]
+            d.added_tokens = K.make_strings(a[0:3], keep)
+            aid = _i32(a[3])
+            keep.append(aid)
+            d.added_ids = aid.ctypes.data_as(K.i32p)
+        else:
+            d.added_tokens = K.Strings(None, None, None, 0, 0)
+        d.unk_token, d.unk_token_len = self.unk_token, len(self.unk_token)
+        d.suffix_indicator, d.suffix_indicator_len = self.suffix_indicator, len(self.suffix_indicator)
+        d.end_suffix, d.end_suffix_len = self.end_suffix, len(self.end_suffix)
+        d.fuse_unk, d.byte_fallback, d.cache_capacity, d.device = int(self.fuse_unk), int(self.byte_fallback), self.cache_capacity, self.device
+        K.check(K.lib().b200tok_bpe_create(C.byref(d), C.byref(self._h)))
+
+    def with_constants(self, consts):
+        self._ensure(list(consts))
+        return self
+
+    def evaluate(self, inputs):
+        self._ensure(list(inputs[5:]))
+        keep = []
+        rin = _ragged_in(*inputs[:5], keep=keep)
+        out, ob, oe, ids = _ids_out(rin.n_rows, rin.n_chars + rin.n_elems * len(self.end_suffix))
+        K.check(K.lib().b200tok_bpe_run(self._h, C.byref(rin), C.byref(out), None))
+        return [ob, oe, ids[:out.n_ids].copy()]
+
+
+class WordpieceTokenizer(_Handle):
+    """WordpieceTokenizer(suffix_indicator, max_bytes_per_word); inputs [0..4] words, [5..7] vocab, [8] unk id."""
+
+    def __init__(self, suffix_indicator="##", max_bytes_per_word=100, device=0):
+        super().__init__()
+        self.suffix_indicator = suffix_indicator.encode() if isinstance(suffix_indicator, str) else bytes(suffix_indicator)
+        self.max_bytes_per_word, self.device = int(max_bytes_per_word), device
+
+    def _ensure(self, vocab):
+        if self._h:
+            return
+        keep = []
+        d = K.WordpieceDesc(K.make_strings(vocab, keep), self.suffix_indicator, len(self.suffix_indicator),
+                            self.max_bytes_per_word, self.device)
+        K.check(K.lib().b200tok_wordpiece_create(C.byref(d), C.byref(self._h)))
+
+    def with_constants(self, vocab):
+        self._ensure(vocab)
+        return self
+
+    def evaluate(self, inputs):
+        if len(inputs) != 9:
+            raise ValueError("WordpieceTokenizer expects 9 inputs")
+        self._ensure(inputs[5:8])
+        unk = int(np.asarray(inputs[8]).reshape(-1)[0])
+        keep = []
+        rin = _ragged_in(*inputs[:5], keep=keep)
+        out, ob, oe, ids = _ids_out(rin.n_rows, rin.n_chars + rin.n_elems)
+        K.check(K.lib().b200tok_wordpiece_run(self._h, C.byref(rin), C.c_int32(unk), C.byref(out), None))
+        return [ob, oe, ids[:out.n_ids].copy()]
+
+
+class VocabEncoder(_Handle):
+    """VocabEncoder; inputs [0..2] strings, [3..5] keys, [6] values (i32|i64), [7] default."""
+
+    def __init__(self, device=0):
+        super().__init__()
+        self.device = device
+        self._dtype = None
+
+    def evaluate(self, inputs):
+        if len(inputs) != 8:
+            raise ValueError("VocabEncoder expects 8 inputs")
+        values = np.asarray(inputs[6])
+        if values.dtype not in (np.int32, np.int64):
+            raise ValueError("VocabEncoder: unsupported element type: %s" % values.dtype)
+        if not self._h:
+            keep = []
+            vals = np.ascontiguousarray(values)
+            d = K.VocabEncDesc(K.make_strings(inputs[3:6], keep), C.c_void_p(vals.ctypes.data),
+                               int(vals.dtype == np.int64), self.device)
+            K.check(K.lib().b200tok_vocabenc_create(C.byref(d), C.byref(self._h)))
+            self._dtype = vals.dtype
+        b, e, c = _i32(inputs[0]), _i32(inputs[1]), _u8(inputs[2])
+        out = np.empty(len(b), self._dtype)
+        default = int(np.asarray(inputs[7]).reshape(-1)[0])
+        K.check(K.lib().b200tok_vocabenc_run(self._h, _ptr(b), _ptr(e), C.c_int64(len(b)), _ptr(c), C.c_int64(c.size),
+                                             C.c_int64(default), _ptr(out), K.MEM_HOST, None))
+        return [out]
+
+
+class VocabDecoder(_Handle):
+    """VocabDecoder(skip_tokens); inputs [0] ids i32[B,S], [1..3] vocab, optional [4] skip tokens.
+    `byte_fallback=True` fuses the ByteFallback op that follows it in detokenizer IRs."""
+
+    def __init__(self, skip_tokens=(), device=0, byte_fallback=False):
+        super().__init__()
+        self.skip_tokens, self.device, self.byte_fallback = list(skip_tokens), device, bool(byte_fallback)
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (4, 5):
+            raise ValueError("Too few inputs passed to VocabDecoder, it means it is not converted properly or it is "
+                             "not used in the supported pattern")
+        if not self._h:
+            keep = []
+            d = K.VocabDecDesc(K.make_strings(inputs[1:4], keep), self.device)
+            K.check(K.lib().b200tok_vocabdec_create(C.byref(d), C.byref(self._h)))
+        ids = _i32(inputs[0])
+        if ids.ndim != 2:
+            raise ValueError("VocabDecoder expects ids of shape [batch, seq]")
+        B, S = ids.shape
+        skip = _i32(inputs[4] if len(inputs) == 5 else np.asarray(self.skip_tokens, dtype=np.int32))
+        n = B * max(S, 1)
+        cap = max(int(K.lib().b200tok_vocabdec_max_chars(self._h, B, S)), 1)
+        rb, re_ = np.empty(B, np.int32), np.empty(B, np.int32)
+        ob, oe = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+        oc = np.empty(cap, np.uint8)
+        out = K.Decoded(_ptr(rb), _ptr(re_), _ptr(ob), _ptr(oe), _ptr(oc), cap, 0, K.MEM_HOST)
+        K.check(K.lib().b200tok_vocabdec_run(self._h, _ptr(ids), C.c_int64(B), C.c_int64(S), _ptr(skip),
+                                             C.c_int64(len(skip)), int(self.byte_fallback), C.byref(out), K.MEM_HOST, None))
+        return [rb, re_, ob[:n].copy(), oe[:n].copy(), oc[:out.n_chars].copy()]
+
+
+class ByteFallback:
+    """ByteFallback; inputs [0..2] strings -> strings."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def evaluate(self, inputs):
+        b, e, c = _i32(inputs[0]), _i32(inputs[1]), _u8(inputs[2])
+        ob, oe = np.empty(len(b), np.int32), np.empty(len(b), np.int32)
+        oc = np.empty(max(c.size, 1), np.uint8)
+        n = C.c_int64(0)
+        K.check(K.lib().b200tok_bytefallback_run(self.device, _ptr(b), _ptr(e), C.c_int64(len(b)), _ptr(c), C.c_int64(c.size),
+                                                 _ptr(ob), _ptr(oe), _ptr(oc), C.byref(n), K.MEM_HOST, None))
+        return [ob, oe, oc[:n.value].copy()]
+
+
+def split_bpe(split: RegexSplit, bpe: BPETokenizer, inputs):
+    """Fused RegexSplit -> BPETokenizer on ragged strings `inputs[0..4]` (+ optional skips [5])."""
+    keep = []
+    rin = _ragged_in(*inputs[:5], skips=inputs[5] if len(inputs) > 5 else None, keep=keep)
+    out, ob, oe, ids = _ids_out(rin.n_rows, rin.n_chars + rin.n_elems * len(bpe.end_suffix))
+    K.check(K.lib().b200tok_split_bpe_run(split.handle, bpe.handle, C.byref(rin), C.byref(out), None))
+    return [ob, oe, ids[:out.n_ids].copy()]
+
+
+def split_wordpiece(split1: RegexSplit, split2, wp: WordpieceTokenizer, inputs, unk_token_id: int):
+    """Fused RegexSplit [-> RegexSplit] -> WordpieceTokenizer (BERT pre-tokenisation chain)."""
+    keep = []
+    rin = _ragged_in(*inputs[:5], skips=inputs[5] if len(inputs) > 5 else None, keep=keep)
+    out, ob, oe, ids = _ids_out(rin.n_rows, rin.n_chars + rin.n_elems)
+    K.check(K.lib().b200tok_split_wordpiece_run(split1.handle, split2.handle if split2 is not None else None, wp.handle,
+                                                C.byref(rin), C.c_int32(int(unk_token_id)), C.byref(out), None))
+    return [ob, oe, ids[:out.n_ids].copy()]

@@ -1,0 +1,93 @@
+// TEST CODE — compiles the product's algorithmic core (csrc/tok_core.cuh) and host table builders
+// (csrc/tables.cpp) with g++ so that tests/test_core_host.py can check the matcher / merge / trie
+// logic against the oracle on a machine without a GPU.  Never linked into libb200tok.so.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../openvino_tokenizers_b200/csrc/tables.hpp"
+
+using namespace b200tok;
+#define HZ extern "C" __attribute__((visibility("default")))
+
+HZ int hz_char_class(uint32_t cp) {
+    const auto& t = host_class_tables();
+    if (cp >= 0x110000) return 0;
+    return t.stage2[(uint32_t)t.stage1[cp >> 8] * 256u + (cp & 255u)];
+}
+
+// Split one element with the sequential chain.  Returns piece count or a negative error.
+HZ int64_t hz_split(const char* pattern, int64_t plen, const char* behaviour, int invert, int max_splits,
+                    const uint8_t* chars, int64_t n, int32_t* out_b, int32_t* out_e, int64_t cap) {
+    b200tok_regexsplit_desc d{pattern, plen, behaviour, invert, max_splits, 0};
+    HostSplit hs;
+    std::string err;
+    int rc = parse_split(d, hs, err);
+    if (rc) return rc;
+    ScanCtx c{chars, (int)n, host_class_tables().view(), hs.spec.pat, hs.spec.class_mask};
+    SplitEmitter em;
+    em.reset(hs.mode, hs.invert, hs.max_splits, (int)n);
+    int64_t k = 0;
+    split_element_scan(c, hs.spec, hs.repeat, 0, (int)n, em, [&](int b, int e) {
+        if (k < cap) { out_b[k] = b; out_e[k] = e; }
+        ++k;
+    });
+    return k;
+}
+
+struct HzBpe { HostBpe t; };
+HZ void* hz_bpe_create(const b200tok_bpe_desc* d) {
+    auto h = std::make_unique<HzBpe>();
+    std::string err;
+    if (build_bpe(*d, h->t, err)) return nullptr;
+    return h.release();
+}
+HZ void hz_bpe_destroy(void* h) { delete (HzBpe*)h; }
+HZ int64_t hz_bpe_info(void* h, int what) {
+    auto* b = (HzBpe*)h;
+    switch (what) {
+    case 0: return b->t.n_duplicate_products;
+    case 1: return b->t.bytes_only;
+    case 2: return (int64_t)b->t.trie.n_nodes();
+    case 3: return b->t.unk_id;
+    default: return -1;
+    }
+}
+// mode 0: in-place serial loop, 1: heap loop, 2: packed-key serial loop.  The end_suffix is appended like the reference does.
+HZ int64_t hz_bpe_piece(void* h, const uint8_t* bytes, int64_t n, int mode, int32_t* out) {
+    auto* b = (HzBpe*)h;
+    std::string s((const char*)bytes, (size_t)n);
+    s += b->t.end_suffix;
+    const BpeTables T = b->t.view();
+    const int L = (int)s.size();
+    std::vector<int32_t> ids(2 * L + 2), rank(L + 2), newid(L + 2), prev(2 * L + 2), next(2 * L + 2);
+    std::vector<uint16_t> birth(L + 2);
+    std::vector<HeapEntry> heap(3 * L + 3);
+    int m = bpe_symbolize(T, (const uint8_t*)s.data(), 0, L, ids.data());
+    int cnt;
+    if (mode == 0) {
+        cnt = bpe_merge_serial(T.merges, ids.data(), rank.data(), newid.data(), birth.data(), m);
+        std::memcpy(out, ids.data(), (size_t)cnt * 4);
+    } else if (mode == 2) {
+        if (m > kPackedMaxSymbols) return -1;
+        std::vector<uint32_t> key(L + 2);
+        cnt = bpe_merge_packed(T.merges, ids.data(), key.data(), newid.data(), m);
+        std::memcpy(out, ids.data(), (size_t)cnt * 4);
+    } else {
+        cnt = bpe_merge_heap(T.merges, m, ids.data(), prev.data(), next.data(), heap.data(), out);
+    }
+    return cnt;
+}
+
+struct HzWp { HostWordpiece t; };
+HZ void* hz_wp_create(const b200tok_wordpiece_desc* d) {
+    auto h = std::make_unique<HzWp>();
+    std::string err;
+    if (build_wordpiece(*d, h->t, err)) return nullptr;
+    return h.release();
+}
+HZ void hz_wp_destroy(void* h) { delete (HzWp*)h; }
+HZ int64_t hz_wp_word(void* h, const uint8_t* bytes, int64_t n, int32_t unk, int32_t* out) {
+    return wordpiece_word(((HzWp*)h)->t.view(), bytes, 0, (int)n, unk, out);
+}

@@ -1,0 +1,91 @@
+"""Loader for tests/harness/libharness.so — the product's algorithmic core (csrc/tok_core.cuh +
+csrc/tables.cpp) compiled for the host so that it can be compared with the oracle without a GPU."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from openvino_tokenizers_b200 import _capi as K
+
+HERE = Path(__file__).resolve().parent / "harness"
+CSRC = HERE.parent.parent / "openvino_tokenizers_b200" / "csrc"
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = HERE / "libharness.so"
+        srcs = [HERE / "harness.cpp", CSRC / "tables.cpp", CSRC / "tables.hpp", CSRC / "tok_core.cuh"]
+        if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-o", str(so),
+                                   str(HERE / "harness.cpp"), str(CSRC / "tables.cpp")])
+        _lib = C.CDLL(str(so))
+        _lib.hz_split.restype = C.c_int64
+        _lib.hz_bpe_create.restype = C.c_void_p
+        _lib.hz_wp_create.restype = C.c_void_p
+        _lib.hz_bpe_piece.restype = C.c_int64
+        _lib.hz_wp_word.restype = C.c_int64
+        _lib.hz_bpe_info.restype = C.c_int64
+    return _lib
+
+
+def split(pattern, behaviour, invert, max_splits, data: bytes):
+    pat = pattern.encode() if isinstance(pattern, str) else pattern
+    arr = np.frombuffer(data, np.uint8) if len(data) else np.zeros(1, np.uint8)
+    cap = len(data) + 2
+    ob, oe = np.empty(cap, np.int32), np.empty(cap, np.int32)
+    n = lib().hz_split(pat, C.c_int64(len(pat)), behaviour.encode(), int(invert), int(max_splits),
+                       arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), ob.ctypes.data_as(K.i32p),
+                       oe.ctypes.data_as(K.i32p), C.c_int64(cap))
+    if n < 0:
+        raise ValueError(f"hz_split error {n}")
+    return list(zip(ob[:n].tolist(), oe[:n].tolist()))
+
+
+class HostBpe:
+    def __init__(self, vocab, ml, mr=None, added=None, added_ids=None, unk_token=b"", end_suffix=b"",
+                 byte_fallback=False, fuse_unk=False):
+        self._keep = []
+        d = K.BpeDesc()
+        d.vocab = K.make_strings(vocab, self._keep)
+        d.merges_left = K.make_strings(ml, self._keep)
+        d.merges_right = K.make_strings(mr, self._keep)
+        d.added_tokens = K.make_strings(added, self._keep)
+        if added_ids is not None:
+            aid = np.ascontiguousarray(added_ids, np.int32)
+            self._keep.append(aid)
+            d.added_ids = aid.ctypes.data_as(K.i32p)
+        d.unk_token, d.unk_token_len = unk_token, len(unk_token)
+        d.end_suffix, d.end_suffix_len = end_suffix, len(end_suffix)
+        d.suffix_indicator, d.suffix_indicator_len = b"", 0
+        d.byte_fallback, d.fuse_unk, d.cache_capacity, d.device = int(byte_fallback), int(fuse_unk), 0, 0
+        self.h = C.c_void_p(lib().hz_bpe_create(C.byref(d)))
+        if not self.h:
+            raise ValueError("hz_bpe_create failed")
+
+    def info(self, what):
+        return lib().hz_bpe_info(self.h, what)
+
+    def piece(self, data: bytes, mode=0):
+        arr = np.frombuffer(data, np.uint8) if len(data) else np.zeros(1, np.uint8)
+        out = np.empty(len(data) + 64, np.int32)
+        n = lib().hz_bpe_piece(self.h, arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), mode, out.ctypes.data_as(K.i32p))
+        return out[:n].tolist()
+
+
+class HostWordpiece:
+    def __init__(self, vocab, suffix=b"##", max_bytes=100):
+        self._keep = []
+        d = K.WordpieceDesc()
+        d.vocab = K.make_strings(vocab, self._keep)
+        d.suffix_indicator, d.suffix_indicator_len = suffix, len(suffix)
+        d.max_bytes_per_word, d.device = max_bytes, 0
+        self.h = C.c_void_p(lib().hz_wp_create(C.byref(d)))
+
+    def word(self, data: bytes, unk: int):
+        arr = np.frombuffer(data, np.uint8) if len(data) else np.zeros(1, np.uint8)
+        out = np.empty(len(data) + 4, np.int32)
+        n = lib().hz_wp_word(self.h, arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), C.c_int32(unk), out.ctypes.data_as(K.i32p))
+        return out[:n].tolist()

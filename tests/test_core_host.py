@@ -1,0 +1,128 @@
+"""CPU tier: the product's algorithmic core (csrc/tok_core.cuh + csrc/tables.cpp, the code the kernels run)
+compiled for the host by tests/harness and compared with the oracle."""
+import numpy as np
+import pytest
+
+import cases
+import hostcore as H
+from openvino_tokenizers_b200 import assets as A
+from openvino_tokenizers_b200.strings import pack_strings
+
+SPLIT_CASES = [
+    (A.GPT2_PATTERN, "isolate", False), (A.GPT2_DIGITS_PATTERN, "isolate", False), (A.LLAMA3_PATTERN, "isolate", False),
+    (A.LLAMA3_PATTERN, "contiguous", False), (r"\s+", "remove", False), (A.BERT_PUNCT_PATTERN, "isolate", False),
+    (r"\w+|[^\w\s]+", "remove", True), (".", "isolate", False), ("▁", "mergedwithnext", False),
+    ("▁", "mergedwithprevious", False), (r"\p{N}", "isolate", False), (r"\p{P}", "contiguous", False),
+    (r"\s+", "mergedwithprevious", True), (r"\s+", "mergedwithnext", True), (r"\p{Nd}|\p{Nl}|\p{No}", "remove", False),
+]
+ALPHA = ["a", "s", "t", "'", "l", "r", "e", "v", "1", "2", " ", " ", "\n", "\r", "\t", "!", "?", "é", "ſ", " ", "測", "😁",
+         "▁", "_", "S", "L", "٣"]
+
+
+def _oracle_split(o, data):
+    rb, re_, b, e, c = cases.batch_from_strings([data])
+    r = o(rb, re_, b, e, c)
+    return list(zip(r[2].tolist(), r[3].tolist()))
+
+
+@pytest.mark.parametrize("pattern,behaviour,invert", SPLIT_CASES)
+def test_matcher_equals_pcre2(oracle_mod, pattern, behaviour, invert):
+    o = oracle_mod.SplitOracle(pattern, behaviour, invert)
+    rng = np.random.default_rng(0)
+    for _ in range(1500):
+        s = "".join(rng.choice(ALPHA, size=int(rng.integers(1, 14)))).encode()
+        assert H.split(pattern, behaviour, invert, -1, s) == _oracle_split(o, s), s
+    for s in cases.EDGE_STRINGS:
+        if s:
+            assert H.split(pattern, behaviour, invert, -1, s.encode()) == _oracle_split(o, s.encode()), s
+
+
+def test_max_splits_quirk(oracle_mod):
+    for ms in (1, 2, 3):
+        o = oracle_mod.SplitOracle(r"\s+", "remove", False, ms)
+        for s in (b"a b c d e", b" a  b ", b"abc"):
+            assert H.split(r"\s+", "remove", False, ms, s) == _oracle_split(o, s)
+
+
+def test_unknown_pattern_rejected():
+    with pytest.raises(ValueError):
+        H.split(r"(a|b)+c", "isolate", False, -1, b"abc")
+
+
+@pytest.mark.parametrize("name", ["gpt2_synth", "llama3_synth"])
+def test_bpe_merge_loops_equal_oracle(oracle_mod, name):
+    a = A.load_bpe(name)
+    v, ml, mr, ad, aid = a.tensors()
+    o = oracle_mod.BpeOracle(v, ml, mr, ad, aid, use_cache=False)
+    h = H.HostBpe(v, ml, mr, ad, aid)
+    assert h.info(0) == 0          # no two merges produce the same token: the (rank, birth) tie is unreachable
+    rng = np.random.default_rng(1)
+    words = cases.long_prompts()[0].encode().split()
+    pieces = [b" " + w for w in words] + words
+    pieces += [bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(1, 40)), dtype=np.uint8)) for _ in range(1500)]
+    pieces += ["Тест".encode(), " 測試".encode(), "😁😁".encode(), b"a" * 300, b" " * 256, b"<|endoftext|>",
+               b"<|endoftext", b"ab<|endoftext|>cd", bytes(range(256)), b"ab" * 500]
+    b, e, c = pack_strings(pieces)
+    rb = np.arange(len(pieces), dtype=np.int32)
+    ob, oe, ids = o(rb, rb + 1, b, e, c)
+    for i, p in enumerate(pieces):
+        exp = ids[ob[i]:oe[i]].tolist()
+        assert h.piece(p, 0) == exp and h.piece(p, 1) == exp and h.piece(p, 2) == exp, p[:30]
+
+
+def test_bpe_suffix_unk_fallback_tables(oracle_mod):
+    vocab = ["<unk>", "a", "b", "c", "</w>", "ab", "abc", "c</w>", "bc</w>", "<0x64>", "<0x65>", "d</w>", "ab</w>"]
+    merges = ["a b", "ab c", "c </w>", "b c</w>", "ab </w>"]
+    v, mg = pack_strings(vocab), pack_strings(merges)
+    words = [b"abc", b"ab", b"abcd", b"xabc", b"de", b"cab", b"abab" * 20]
+    b, e, c = pack_strings(words)
+    rb = np.arange(len(words), dtype=np.int32)
+    for bf in (False, True):
+        for unk in (b"<unk>", b""):
+            o = oracle_mod.BpeOracle(v, mg, None, unk_token=unk, end_suffix=b"</w>", byte_fallback=bf, use_cache=False)
+            ob, oe, ids = o(rb, rb + 1, b, e, c)
+            h = H.HostBpe(v, mg, None, unk_token=unk, end_suffix=b"</w>", byte_fallback=bf)
+            for i, w in enumerate(words):
+                for mode in (0, 1, 2):
+                    assert h.piece(w, mode) == ids[ob[i]:oe[i]].tolist(), (w, bf, unk, mode)
+
+
+def test_birth_order_differs_from_position_order(oracle_mod):
+    """equal ranks are ordered by push sequence, not by position."""
+    vocab = ["u", "v", "q", "p", "X", "XX", "pq"]
+    vocab = ["u", "v", "q", "uv", "uvq", "uvquvq"]
+    merges = ["u v", "uv q", "uvq uvq"]
+    v, mg = pack_strings(vocab), pack_strings(merges)
+    o = oracle_mod.BpeOracle(v, mg, None, use_cache=False)
+    h = H.HostBpe(v, mg, None)
+    for w in (b"uvquvquvq", b"uvquvq", b"uvquvquvquvq", b"quvquvquv"):
+        b, e, c = pack_strings([w])
+        z = np.zeros(1, np.int32)
+        exp = o(z, z + 1, b, e, c)[2].tolist()
+        for mode in (0, 1, 2):
+            assert h.piece(w, mode) == exp, (w, mode)
+
+
+def test_wordpiece_word_equals_oracle(oracle_mod):
+    a = A.load_wordpiece("bert_synth")
+    v = pack_strings(a.vocab)
+    o = oracle_mod.WordpieceOracle(v, a.suffix_indicator, a.max_bytes_per_word)
+    h = H.HostWordpiece(v, a.suffix_indicator, a.max_bytes_per_word)
+    words = [w.lower() for w in cases.long_prompts()[0].encode().split()]
+    words += [b"a" * 100, b"a" * 101, b"unaffable", b"xyzzyqq", "тест".encode(), b"##", b"#"]
+    b, e, c = pack_strings(words)
+    rb = np.arange(len(words), dtype=np.int32)
+    ob, oe, ids = o(rb, rb + 1, b, e, c, a.unk_token_id)
+    for i, w in enumerate(words):
+        assert h.word(w, a.unk_token_id) == ids[ob[i]:oe[i]].tolist(), w
+
+
+def test_class_table_spot_checks():
+    L, N, S, P, W, BP, NL = 1, 2, 4, 8, 16, 32, 64
+    assert H.lib().hz_char_class(ord("a")) & L
+    assert H.lib().hz_char_class(ord("7")) & N
+    assert H.lib().hz_char_class(0x20) & S and H.lib().hz_char_class(0xA0) & S and H.lib().hz_char_class(0x3000) & S
+    assert H.lib().hz_char_class(ord("\n")) & NL and H.lib().hz_char_class(ord("\n")) & S
+    assert H.lib().hz_char_class(ord("!")) & BP and H.lib().hz_char_class(0x4E2D) & BP and not H.lib().hz_char_class(ord("a")) & BP
+    assert H.lib().hz_char_class(ord("$")) & BP and not H.lib().hz_char_class(ord("$")) & P   # BERT's ASCII ranges beyond \p{P}
+    assert H.lib().hz_char_class(0x0416) & L and H.lib().hz_char_class(0x0663) & N and H.lib().hz_char_class(ord("_")) & W

@@ -1,0 +1,420 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ops.py -> libb200tok.so), against the
+CPU oracle on the same inputs.  Bit-exact (integer / byte / index work)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+from openvino_tokenizers_b200 import assets as A
+from openvino_tokenizers_b200.strings import pack_strings, ragged_rows, unpack_strings
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from openvino_tokenizers_b200 import ops as O
+    return O
+
+
+@pytest.fixture(scope="module")
+def gpt2(ops, oracle_mod):
+    a = A.load_bpe("gpt2_synth")
+    v, ml, mr, ad, aid = a.tensors()
+    consts = [*v, *ml, *mr] + ([*ad, aid] if ad is not None else [])
+    return dict(assets=a, consts=consts,
+                bpe=ops.BPETokenizer().with_constants(consts),
+                split=ops.RegexSplit("isolate").with_pattern(a.split_pattern),
+                o_bpe=oracle_mod.BpeOracle(v, ml, mr, ad, aid, cache_capacity=a.cache_capacity),
+                o_split=oracle_mod.SplitOracle(a.split_pattern, "isolate"))
+
+
+@pytest.fixture(scope="module")
+def llama3(ops, oracle_mod):
+    a = A.load_bpe("llama3_synth")
+    v, ml, mr, ad, aid = a.tensors()
+    consts = [*v, *ml, *mr] + ([*ad, aid] if ad is not None else [])
+    return dict(assets=a, consts=consts,
+                bpe=ops.BPETokenizer().with_constants(consts),
+                split=ops.RegexSplit("isolate").with_pattern(a.split_pattern),
+                o_bpe=oracle_mod.BpeOracle(v, ml, mr, ad, aid, cache_capacity=a.cache_capacity),
+                o_split=oracle_mod.SplitOracle(a.split_pattern, "isolate"))
+
+
+@pytest.fixture(scope="module")
+def bert(ops, oracle_mod):
+    a = A.load_wordpiece("bert_synth")
+    v = pack_strings(a.vocab)
+    return dict(assets=a, vocab=v,
+                wp=ops.WordpieceTokenizer(a.suffix_indicator, a.max_bytes_per_word).with_constants(v),
+                s1=ops.RegexSplit("remove").with_pattern(A.BERT_WHITESPACE_PATTERN),
+                s2=ops.RegexSplit("isolate").with_pattern(A.BERT_PUNCT_PATTERN),
+                o_wp=oracle_mod.WordpieceOracle(v, a.suffix_indicator, a.max_bytes_per_word),
+                o_s1=oracle_mod.SplitOracle(A.BERT_WHITESPACE_PATTERN, "remove"),
+                o_s2=oracle_mod.SplitOracle(A.BERT_PUNCT_PATTERN, "isolate"))
+
+
+def oracle_chain_bpe(m, batch):
+    s = m["o_split"](*batch)
+    return m["o_bpe"](s[0], s[1], s[2], s[3], batch[4])
+
+
+def check_bpe_model(ops, m, batch):
+    rb, re_, b, e, c = batch
+    pat = np.frombuffer(m["assets"].split_pattern.encode(), np.uint8)
+    exp_split = m["o_split"](rb, re_, b, e, c)
+    exp = m["o_bpe"](exp_split[0], exp_split[1], exp_split[2], exp_split[3], c)
+    # 1. stand-alone RegexSplit op (6-input form)
+    got_split = m["split"].evaluate([rb, re_, b, e, c, pat])
+    for k in range(4):
+        assert np.array_equal(got_split[k], exp_split[k]), f"RegexSplit output {k} differs"
+    # 2. stand-alone BPETokenizer op on the split result
+    got = m["bpe"].evaluate([*got_split[:5], *m["consts"]])
+    assert cases.ragged_rows_equal(got, exp), "BPETokenizer differs"
+    # 3. fused split+BPE
+    got_f = ops.split_bpe(m["split"], m["bpe"], [rb, re_, b, e, c])
+    assert cases.ragged_rows_equal(got_f, exp), "fused split+BPE differs"
+    return exp
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_loads_and_sees_gpu():
+    from openvino_tokenizers_b200 import _capi as K
+    assert K.lib().b200tok_device_count() >= 1
+
+
+@pytest.mark.parametrize("model", ["gpt2", "llama3"])
+def test_bpe_edge_corpus(ops, model, request):
+    m = request.getfixturevalue(model)
+    strings = cases.EDGE_STRINGS + cases.long_prompts()
+    check_bpe_model(ops, m, cases.batch_from_strings(strings))
+    # every string alone too (row boundaries / single-row batches)
+    for s in strings[:12] + [" " * 256, ""]:
+        check_bpe_model(ops, m, cases.batch_from_strings([s]))
+
+
+def test_bpe_c0_random_ascii(ops, gpt2):
+    """BASELINE config 0: 256 x 128 B printable ASCII."""
+    exp = check_bpe_model(ops, gpt2, cases.random_ascii_batch(256, 128))
+    assert len(exp[2]) > 0
+
+
+def test_bpe_c1_slice_random_ascii(ops, gpt2):
+    """BASELINE config 1 shape (512-byte docs), 4096 rows."""
+    check_bpe_model(ops, gpt2, cases.random_ascii_batch(4096, 512))
+
+
+def test_bpe_english_like(ops, gpt2, llama3):
+    batch = cases.english_like_batch(2048, 512)
+    check_bpe_model(ops, gpt2, batch)
+    check_bpe_model(ops, llama3, batch)
+
+
+def test_bpe_c3_slice_mixed_utf8(ops, llama3, gpt2):
+    """BASELINE config 3 shape (1 KiB mixed UTF-8 docs), 1024 rows."""
+    batch = cases.mixed_utf8_batch(1024, 1024)
+    check_bpe_model(ops, llama3, batch)
+    check_bpe_model(ops, gpt2, batch)
+
+
+def test_bpe_ragged_lengths_and_multi_element_rows(ops, gpt2):
+    rng = np.random.default_rng(5)
+    strings = []
+    for i in range(600):
+        L = int(rng.integers(0, 1500))
+        strings.append(bytes(rng.integers(0x20, 0x7F, size=L, dtype=np.uint8)))
+    b, e, c = pack_strings(strings)
+    # rows of 0..4 elements
+    cuts = np.sort(rng.integers(0, len(strings) + 1, size=299))
+    rb = np.concatenate([[0], cuts]).astype(np.int32)
+    re_ = np.concatenate([cuts, [len(strings)]]).astype(np.int32)
+    check_bpe_model(ops, gpt2, (rb, re_, b, e, c))
+
+
+def test_bpe_skips_pass_special_tokens_through(ops, gpt2, oracle_mod):
+    """7-input RegexSplit form: skip-flagged elements are not split and reach BPE whole."""
+    parts = [b"Hello world", b"<|endoftext|>", b" more text here", b"<|endoftext|>", b""]
+    b, e, c = pack_strings(parts)
+    rb, re_ = np.array([0, 3], np.int32), np.array([3, 5], np.int32)
+    skips = np.array([0, 1, 0, 1, 0], np.uint8)
+    pat = np.frombuffer(gpt2["assets"].split_pattern.encode(), np.uint8)
+    exp_s = gpt2["o_split"](rb, re_, b, e, c, skips=skips)
+    got_s = gpt2["split"].evaluate([rb, re_, b, e, c, skips.astype(bool), pat])
+    for k in range(4):
+        assert np.array_equal(got_s[k], exp_s[k])
+    assert np.array_equal(got_s[5].astype(np.uint8), exp_s[4])
+    exp = gpt2["o_bpe"](exp_s[0], exp_s[1], exp_s[2], exp_s[3], c)
+    got = ops.split_bpe(gpt2["split"], gpt2["bpe"], [rb, re_, b, e, c, skips])
+    assert cases.ragged_rows_equal(got, exp)
+    eot = gpt2["assets"].vocab.index(b"<|endoftext|>")
+    assert eot in got[2]
+
+
+def test_hf_golden_ids(ops, gpt2, llama3):
+    """Second oracle: ids HuggingFace `tokenizers` produced for the same vocab (tests/golden, made by tools/make_golden.py)."""
+    for name, m in (("gpt2_synth", gpt2), ("llama3_synth", llama3)):
+        g = json.loads((GOLDEN / f"hf_{name}.json").read_text())
+        got = ops.split_bpe(m["split"], m["bpe"], list(cases.batch_from_strings(g["texts"])))
+        for i, ids in enumerate(g["ids"]):
+            assert got[2][got[0][i]:got[1][i]].tolist() == ids, (name, g["texts"][i][:40])
+
+
+def test_regex_split_golden_vectors(ops):
+    """The reference's own known-answer vectors (tests/layer_tests.py:331-389)."""
+    g = json.loads((GOLDEN / "regex_split_layer_tests.json").read_text())
+    n_run = 0
+    for case in g["cases"]:
+        op = ops.RegexSplit(case["behaviour"], case["invert"], case["max_splits"])
+        rb, re_, b, e, c = cases.batch_from_strings([case["text"]])
+        pat = np.frombuffer(case["pattern"].encode(), np.uint8)
+        try:
+            out = op.evaluate([rb, re_, b, e, c, pat])
+        except ops.B200TokError as err:
+            assert err.code == -4 and not case["gpu_supported"], case
+            continue
+        assert case["gpu_supported"], case
+        pieces = [p.decode() for p in unpack_strings(out[2], out[3], c)]
+        if case["text"] == "":
+            assert out[0].tolist() == [0] and out[1].tolist() == [0]   # shape-[1] shortcut
+        else:
+            assert pieces == case["expected"], case
+        n_run += 1
+    assert n_run >= 23
+
+
+SPLIT_CASES = [
+    (A.GPT2_PATTERN, "isolate", False), (A.GPT2_DIGITS_PATTERN, "isolate", False), (A.LLAMA3_PATTERN, "isolate", False),
+    (A.LLAMA3_PATTERN, "contiguous", False), (r"\s+", "remove", False), (A.BERT_PUNCT_PATTERN, "isolate", False),
+    (r"\w+|[^\w\s]+", "remove", True), (".", "isolate", False), ("▁", "mergedwithnext", False),
+    ("▁", "mergedwithprevious", False), (r"\p{N}", "isolate", False), (r"\p{P}", "contiguous", False),
+    (r"\s+", "mergedwithprevious", True), (r"\s+", "mergedwithnext", True), (r"\p{Nd}|\p{Nl}|\p{No}", "remove", False),
+    (r"\s+", "isolate", True),
+]
+
+
+@pytest.mark.parametrize("pattern,behaviour,invert", SPLIT_CASES)
+def test_regex_split_random(ops, oracle_mod, pattern, behaviour, invert):
+    alpha = ["a", "s", "t", "'", "l", "r", "e", "v", "1", "2", " ", " ", "\n", "\r", "\t", "!", "?", "é", "ſ", " ",
+             "測", "😁", "▁", "_", "S", "L", "٣", "word", "  ", "...", "12345"]
+    rng = np.random.default_rng(11)
+    strings = ["".join(rng.choice(alpha, size=int(rng.integers(0, 40)))) for _ in range(1500)]
+    strings += ["".join(rng.choice(alpha, size=int(rng.integers(300, 900)))) for _ in range(40)]
+    strings += cases.EDGE_STRINGS
+    if all(s == "" for s in strings):
+        strings.append("x")
+    batch = cases.batch_from_strings(strings)
+    o = oracle_mod.SplitOracle(pattern, behaviour, invert)
+    exp = o(*batch)
+    op = ops.RegexSplit(behaviour, invert)
+    got = op.evaluate([*batch, np.frombuffer(pattern.encode(), np.uint8)])
+    for k in range(4):
+        assert np.array_equal(got[k], exp[k]), f"output {k} differs"
+
+
+def test_regex_split_max_splits(ops, oracle_mod):
+    batch = cases.batch_from_strings(["a b c d e f", "no-space", " lead", "x  y", ""])
+    for ms in (1, 2, 4):
+        o = oracle_mod.SplitOracle(r"\s+", "remove", False, ms)
+        exp = o(*batch)
+        got = ops.RegexSplit("remove", False, ms).evaluate([*batch, np.frombuffer(rb"\s+", np.uint8)])
+        for k in range(4):
+            assert np.array_equal(got[k], exp[k])
+
+
+def test_regex_split_unknown_pattern_is_an_error(ops):
+    with pytest.raises(ops.B200TokError) as ei:
+        ops.RegexSplit("isolate").with_pattern(r"(foo|bar)+baz")
+    assert ei.value.code == -4
+    with pytest.raises(ops.B200TokError):
+        ops.RegexSplit("nonsense").with_pattern(r"\s+")
+    with pytest.raises(ops.B200TokError):
+        ops.RegexSplit("remove", max_splits=0).with_pattern(r"\s+")
+
+
+def test_bpe_end_suffix_unk_and_byte_fallback(ops, oracle_mod):
+    """Non-byte-level BPE (11-input "L R" merges form) with end_suffix, unk token and byte_fallback tokens."""
+    vocab = ["<unk>", "a", "b", "c", "</w>", "ab", "abc", "c</w>", "bc</w>", "<0x64>", "<0x65>", "d</w>", "ab</w>"]
+    merges = ["a b", "ab c", "c </w>", "b c</w>", "ab </w>"]
+    v, mg = pack_strings(vocab), pack_strings(merges)
+    words = [b"abc", b"ab", b"abcd", b"xabc", b"de", b"", b"cab", b"abab" * 50]
+    b, e, c = pack_strings(words)
+    rb = np.arange(len(words), dtype=np.int32)
+    for bf in (False, True):
+        for unk in ("<unk>", ""):
+            o = oracle_mod.BpeOracle(v, mg, None, unk_token=unk.encode(), end_suffix=b"</w>", byte_fallback=bf)
+            exp = o(rb, rb + 1, b, e, c)
+            op = ops.BPETokenizer(unk_token=unk, end_suffix="</w>", byte_fallback=bf)
+            got = op.evaluate([rb, rb + 1, b, e, c, *v, *mg])
+            assert cases.ragged_rows_equal(got, exp), (bf, unk)
+
+
+def test_bpe_missing_merge_token_is_an_error(ops):
+    v, mg = pack_strings(["a", "b"]), pack_strings(["a b"])
+    with pytest.raises(ops.B200TokError) as ei:
+        ops.BPETokenizer().with_constants([*v, *mg])
+    assert ei.value.code == -5
+
+
+def test_bpe_giant_pieces(ops, gpt2):
+    strings = ["a" * 5000, " " * 3000, "ab" * 4000 + " tail", "x" * 513, "y" * 512, "z" * 511, "q" * 1024 + " " + "w" * 1025]
+    check_bpe_model(ops, gpt2, cases.batch_from_strings(strings))
+
+
+def test_bpe_empty_inputs(ops, gpt2):
+    batch = cases.batch_from_strings(["", "", ""])
+    got = gpt2["bpe"].evaluate([*batch, *gpt2["consts"]])
+    assert got[0].tolist() == [0, 0, 0] and got[1].tolist() == [0, 0, 0] and len(got[2]) == 0
+    got = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
+    assert len(got[2]) == 0
+    z = np.zeros(0, np.int32)
+    got = gpt2["bpe"].evaluate([z, z, z, z, np.zeros(0, np.uint8), *gpt2["consts"]])
+    assert len(got[0]) == 0 and len(got[2]) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_chain_wp(m, batch):
+    s1 = m["o_s1"](*batch)
+    s2 = m["o_s2"](s1[0], s1[1], s1[2], s1[3], batch[4])
+    return s2, m["o_wp"](s2[0], s2[1], s2[2], s2[3], batch[4], m["assets"].unk_token_id)
+
+
+def check_wp(ops, m, batch):
+    unk = m["assets"].unk_token_id
+    words, exp = oracle_chain_wp(m, batch)
+    # stand-alone ops chained like the BERT IR: RegexSplit -> RegexSplit -> WordpieceTokenizer
+    p1 = np.frombuffer(A.BERT_WHITESPACE_PATTERN.encode(), np.uint8)
+    p2 = np.frombuffer(A.BERT_PUNCT_PATTERN.encode(), np.uint8)
+    g1 = m["s1"].evaluate([*batch, p1])
+    g2 = m["s2"].evaluate([*g1[:5], p2])
+    for k in range(4):
+        assert np.array_equal(g2[k], words[k]), f"BERT split output {k} differs"
+    got = m["wp"].evaluate([*g2[:5], *m["vocab"], np.array(unk, np.int32)])
+    assert cases.ragged_rows_equal(got, exp), "WordpieceTokenizer differs"
+    got_f = ops.split_wordpiece(m["s1"], m["s2"], m["wp"], list(batch), unk)
+    assert cases.ragged_rows_equal(got_f, exp), "fused split+WordPiece differs"
+    return exp
+
+
+def test_wordpiece_edge_corpus(ops, bert):
+    strings = [s.lower() for s in cases.EDGE_STRINGS + cases.long_prompts()]
+    if all(len(s) == 0 for s in strings):
+        strings.append("x")
+    check_wp(ops, bert, cases.batch_from_strings(strings))
+
+
+def test_wordpiece_c2_slice(ops, bert):
+    """BASELINE config 2 shape: 256-byte lower-cased printable ASCII docs, 4096 rows."""
+    exp = check_wp(ops, bert, cases.random_ascii_batch(4096, 256, lower=True))
+    assert len(exp[2]) > 0
+
+
+def test_wordpiece_english_like(ops, bert):
+    rb, re_, b, e, c = cases.english_like_batch(2048, 256)
+    up = (c >= 0x41) & (c <= 0x5A)
+    c = np.where(up, c + 32, c).astype(np.uint8)
+    check_wp(ops, bert, (rb, re_, b, e, c))
+
+
+def test_wordpiece_long_and_unknown_words(ops, bert, oracle_mod):
+    words = [b"a" * 100, b"a" * 101, b"a" * 700, b"unaffable", b"\xe6\xb8\xac", b"zzzzqqqqxxxx", b"the"]
+    b, e, c = pack_strings(words)
+    rb = np.arange(len(words), dtype=np.int32)
+    unk = bert["assets"].unk_token_id
+    exp = bert["o_wp"](rb, rb + 1, b, e, c, unk)
+    got = bert["wp"].evaluate([rb, rb + 1, b, e, c, *bert["vocab"], np.array(unk, np.int32)])
+    assert cases.ragged_rows_equal(got, exp)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_vocab_encoder(ops, oracle_mod):
+    rng = np.random.default_rng(3)
+    keys = [f"tok{i}".encode() for i in range(5000)] + [b"", b"dup", b"dup", "測試".encode()]
+    for dt in (np.int32, np.int64):
+        values = rng.integers(-5, 1 << 20, size=len(keys)).astype(dt)
+        k = pack_strings(keys)
+        queries = [keys[int(i)] for i in rng.integers(0, len(keys), size=3000)] + [b"missing", b"tok", b"", b"dup"]
+        q = pack_strings(queries)
+        exp = oracle_mod.VocabEncoderOracle(k, values)(q[0], q[1], q[2], -7)
+        got = ops.VocabEncoder().evaluate([*q, *k, values, np.array(-7, dt)])[0]
+        assert got.dtype == dt
+        assert np.array_equal(got.astype(np.int64), exp)
+
+
+def test_vocab_decoder_and_byte_fallback(ops, oracle_mod):
+    vocab_list = A.load_detok_vocab()
+    v = pack_strings(vocab_list)
+    rng = np.random.default_rng(9)
+    ids = rng.integers(-3, len(vocab_list) + 3, size=(64, 257)).astype(np.int32)
+    for skip in ([], [0, 1, 2]):
+        exp = oracle_mod.vocab_decoder(ids, v, skip)
+        got = ops.VocabDecoder(skip_tokens=skip).evaluate([ids, *v])
+        for k in range(5):
+            assert np.array_equal(got[k], exp[k]), f"VocabDecoder output {k} differs"
+        got5 = ops.VocabDecoder().evaluate([ids, *v, np.asarray(skip, np.int32)])
+        for k in range(5):
+            assert np.array_equal(got5[k], exp[k])
+        # ByteFallback stand-alone on the decoder's strings, and fused into the decoder
+        exp_bf = oracle_mod.byte_fallback(exp[2], exp[3], exp[4])
+        got_bf = ops.ByteFallback().evaluate([got[2], got[3], got[4]])
+        for k in range(3):
+            assert np.array_equal(got_bf[k], exp_bf[k]), f"ByteFallback output {k} differs"
+        fused = ops.VocabDecoder(skip_tokens=skip, byte_fallback=True).evaluate([ids, *v])
+        assert np.array_equal(fused[2], exp_bf[0]) and np.array_equal(fused[3], exp_bf[1]) and np.array_equal(fused[4], exp_bf[2])
+    # seq == 0 special case (src/vocab_decoder.cpp:46-47,61-65)
+    z = np.zeros((3, 0), np.int32)
+    exp = oracle_mod.vocab_decoder(z, v, [])
+    got = ops.VocabDecoder().evaluate([z, *v])
+    for k in range(5):
+        assert np.array_equal(got[k], exp[k])
+
+
+def test_byte_fallback_odd_tokens(ops, oracle_mod):
+    toks = [b"<0x41>", b"<0xZZ>", b"<0x4g>", b"<<0x4>", b"<0x41", b"abcdef", b"<abcd>", b"", b"<0xff>", b"<0xFF>", b"x"]
+    t = pack_strings(toks)
+    exp = oracle_mod.byte_fallback(*t)
+    got = ops.ByteFallback().evaluate(list(t))
+    for k in range(3):
+        assert np.array_equal(got[k], exp[k])
+
+
+def test_c4_detokenize_full_size(ops, oracle_mod):
+    """BASELINE config 4 at full size: 1024 x 1024 ids, VocabDecoder + ByteFallback fused, vs the oracle."""
+    vocab_list = A.load_detok_vocab()
+    v = pack_strings(vocab_list)
+    ids = np.random.default_rng(1234).integers(0, len(vocab_list), size=(1024, 1024)).astype(np.int32)
+    exp = oracle_mod.vocab_decoder(ids, v, [0, 1, 2])
+    exp_bf = oracle_mod.byte_fallback(exp[2], exp[3], exp[4])
+    got = ops.VocabDecoder(skip_tokens=[0, 1, 2], byte_fallback=True).evaluate([ids, *v])
+    assert np.array_equal(got[2], exp_bf[0]) and np.array_equal(got[3], exp_bf[1]) and np.array_equal(got[4], exp_bf[2])
+
+
+def test_c1_full_size_properties(ops, gpt2):
+    """BASELINE config 1 at full size (65 536 x 512 B): size-independent properties + a sampled oracle check."""
+    batch = cases.random_ascii_batch(65536, 512)
+    rb, re_, b, e, c = batch
+    got = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
+    ob, oe, ids = got
+    assert ob[0] == 0 and np.array_equal(ob[1:], oe[:-1]) and oe[-1] == len(ids)
+    assert ids.min() >= 0 and ids.max() < len(gpt2["assets"].vocab)
+    # decode(ids) reproduces the input bytes exactly (byte-level BPE is lossless)
+    lens = np.array([len(t) for t in gpt2["assets"].vocab], dtype=np.int64)
+    assert int(lens[ids].sum()) == len(c)
+    row_bytes = np.add.reduceat(lens[ids], ob.astype(np.int64))
+    assert np.all(row_bytes == 512)
+    vb, ve, vc = pack_strings(gpt2["assets"].vocab)
+    sample = np.r_[0:64, 30000:30064, 65472:65536]
+    for r in sample:
+        dec = b"".join(gpt2["assets"].vocab[t] for t in ids[ob[r]:oe[r]])
+        assert dec == bytes(c[b[r]:e[r]])
+    # sampled rows against the oracle
+    sel = (rb[sample], re_[sample], b, e, c)
+    exp = oracle_chain_bpe(gpt2, (np.arange(len(sample), dtype=np.int32), np.arange(1, len(sample) + 1, dtype=np.int32),
+                                  b[sample], e[sample], c))
+    for i, r in enumerate(sample):
+        assert np.array_equal(ids[ob[r]:oe[r]], exp[2][exp[0][i]:exp[1][i]])
+    # idempotence: same call, same answer
+    again = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
+    assert cases.ragged_rows_equal(again, got)

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures under tests/golden/ (run in the build container, where
+/root/reference and HuggingFace `tokenizers` are available; the fixtures travel, this script is provenance).
+
+  regex_split_layer_tests.json  the reference's own known-answer vectors for RegexSplit, extracted by evaluating
+                                the parametrize list of tests/layer_tests.py:331-389 against the RegexSplitStep
+                                factory methods of python/openvino_tokenizers/tokenizer_pipeline.py:354-470
+  hf_<vocab>.json               ids produced by HuggingFace `tokenizers` for the frozen synthetic vocabularies
+                                (second oracle; the reference reports 100 % agreement with HF for these families)
+"""
+import ast
+import json
+import re
+import sys
+from dataclasses import dataclass, field  # noqa: F401  (used by the exec'd reference snippet)
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+REF = Path("/root/reference")
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def reference_regex_cases():
+    src = (REF / "python/openvino_tokenizers/tokenizer_pipeline.py").read_text()
+    a = src.index("@dataclass\nclass RegexSplitStep")
+    b = src.index("    def get_ov_subgraph", a)
+    ns = {"dataclass": dataclass, "field": field, "PreTokenizatinStep": object}
+    exec(src[a:b], ns)
+    RegexSplitStep = ns["RegexSplitStep"]
+    lt = (REF / "tests/layer_tests.py").read_text()
+    a = lt.index("clip_regex_pattern = (")
+    b = lt.index("@pytest.mark.parametrize", a)
+    ns2 = {"re": re, "RegexSplitStep": RegexSplitStep}
+    exec(lt[a:b], ns2)
+    tree = ast.parse(lt)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "test_regex_split":
+            lst = node.decorator_list[0].args[1]
+            cases = eval(compile(ast.Expression(lst), "layer_tests", "eval"), ns2)
+            return cases
+    raise RuntimeError("test_regex_split not found")
+
+
+def make_regex_golden():
+    import hostcore
+    from oracle import SplitOracle
+    from openvino_tokenizers_b200.strings import add_ragged_dimension, pack_strings, unpack_strings
+    out = []
+    for text, expected, layer in reference_regex_cases():
+        pat, beh, inv, ms = layer.split_pattern, layer.behaviour, layer.invert, layer.max_splits
+        try:
+            hostcore.split(pat, beh, inv, ms, b"x")
+            supported = True
+        except ValueError:
+            supported = False
+        b, e, c = pack_strings([text])
+        rb, re_ = add_ragged_dimension(b, e)
+        r = SplitOracle(pat, beh, inv, ms)(rb, re_, b, e, c)
+        got = [p.decode() for p in unpack_strings(r[2], r[3], c)]
+        assert got == list(expected), (text, expected, got)   # the oracle reproduces the reference's vector
+        out.append(dict(text=text, expected=list(expected), pattern=pat, behaviour=beh, invert=bool(inv),
+                        max_splits=ms, gpu_supported=supported))
+    (GOLDEN / "regex_split_layer_tests.json").write_text(json.dumps(
+        dict(source="reference tests/layer_tests.py:331-389", cases=out), ensure_ascii=False, indent=1))
+    print("regex cases", len(out), "gpu-supported", sum(c["gpu_supported"] for c in out))
+
+
+def make_hf_golden():
+    import numpy as np
+    import cases
+    from tokenizers import Tokenizer
+    from openvino_tokenizers_b200 import assets as A
+    rng = np.random.default_rng(99)
+    rand = [bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(1, 300)), dtype=np.uint8)).decode() for _ in range(60)]
+    # special-token strings need SpecialTokensSplit upstream (out of scope); HF would extract them
+    texts = [s for s in cases.EDGE_STRINGS if len(s) < 600 and "<|" not in s] + [p[:1500] for p in cases.long_prompts()] + rand
+    for name in ("gpt2_synth", "llama3_synth"):
+        a = A.load_bpe(name)
+        hf = Tokenizer.from_str(a.hf_json)
+        ids = [hf.encode(t, add_special_tokens=False).ids for t in texts]
+        (GOLDEN / f"hf_{name}.json").write_text(json.dumps(dict(texts=texts, ids=ids), ensure_ascii=False))
+        print(name, len(texts), "texts", sum(map(len, ids)), "ids")
+    w = A.load_wordpiece("bert_synth")
+    hf = Tokenizer.from_str(w.hf_json)
+    btexts = [t.lower() for t in texts if t.isascii() and all(c >= " " or c in "\n\t\r" for c in t)]
+    ids = [hf.encode(t, add_special_tokens=False).ids for t in btexts]
+    (GOLDEN / "hf_bert_synth.json").write_text(json.dumps(dict(texts=btexts, ids=ids), ensure_ascii=False))
+    print("bert_synth", len(btexts), "texts")
+
+
+if __name__ == "__main__":
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    make_regex_golden()
+    make_hf_golden()
