@@ -217,7 +217,8 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     const bool host = in->mem == B200TOK_MEM_HOST;
     const int out_mem = out_ids ? out_ids->mem : out_split->mem;
     if (out_mem != in->mem) return fail(B200TOK_E_INVALID, "input and output must live in the same memory kind");
-    cudaStream_t st = user_stream ? (cudaStream_t)user_stream : w.stream;
+    // NULL stream: host-memory calls use the handle's own stream; device-memory calls mean the legacy default stream
+    cudaStream_t st = (user_stream || !host) ? (cudaStream_t)user_stream : w.stream;
     const int64_t B = in->n_rows, E = in->n_elems, N = in->n_chars;
     const bool is_split = call.op == OP_SPLIT;
 

@@ -293,6 +293,23 @@ __device__ __noinline__ int giant_segment(const RowParams& P, int pos, int end_r
     return q;
 }
 
+// Reserve (end-begin)+suffix_len slots for a BPE piece handled by giant_bpe_kernel and queue it.
+__device__ __forceinline__ void reserve_giant_bpe(const RowParams& P, int row, int begin, int end, int64_t base, int lane,
+                                                  int& emitted, int& holes) {
+    const int reserve = (end - begin) + P.suffix_len;
+    const int64_t o = base + emitted;
+    if (o + reserve <= P.tmp_cap) {
+        for (int t = lane; t < reserve; t += 32) P.tmp_a[o + t] = -1;
+        if (lane == 0) {
+            const int gi = atomicAdd(&P.status[ST_NGIANT], 1);
+            if (gi < P.giants_cap) P.giants[gi] = GiantItem{row, begin, end, emitted};
+            else atomicOr(&P.status[ST_ERROR], ERR_GIANT_LIST);
+        }
+    } else if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+    emitted += reserve;
+    holes += reserve;
+}
+
 template <int OP>
 __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -336,6 +353,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams 
             if (OP == OP_WORDPIECE && whole && ee <= eb) {   // zero-length word -> [unk] (see tok_core.cuh)
                 if (lane == 0) { const int64_t o = base + emitted; if (o < P.tmp_cap) P.tmp_a[o] = P.unk_id; else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW); }
                 ++emitted;
+                continue;
+            }
+            if (OP == OP_BPE && whole && P.suffix_len > 0 && ee <= eb) {   // "" + end_suffix still yields tokens
+                reserve_giant_bpe(P, row, eb, eb, base, lane, emitted, holes);
                 continue;
             }
             int pos = eb;
@@ -392,18 +413,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams 
                             }
                             emitted = __shfl_sync(0xFFFFFFFFu, emitted, 0);
                         } else {
-                            const int reserve = glen + P.suffix_len;
-                            const int64_t o = base + emitted;
-                            if (o + reserve <= P.tmp_cap) {
-                                for (int t = lane; t < reserve; t += 32) P.tmp_a[o + t] = -1;
-                                if (lane == 0) {
-                                    const int gi = atomicAdd(&P.status[ST_NGIANT], 1);
-                                    if (gi < P.giants_cap) P.giants[gi] = GiantItem{row, pos, pos + glen, emitted};
-                                    else atomicOr(&P.status[ST_ERROR], ERR_GIANT_LIST);
-                                }
-                            } else if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
-                            emitted += reserve;
-                            holes += reserve;
+                            reserve_giant_bpe(P, row, pos, pos + glen, base, lane, emitted, holes);
                         }
                     }
                     pos += glen;

@@ -36,7 +36,9 @@ ob = torch.empty(B, dtype=torch.int32, device=dev); oe = torch.empty(B, dtype=to
 ids = torch.empty(B * L, dtype=torch.int32, device=dev); nid = torch.zeros(1, dtype=torch.int64, device=dev)
 rin = K.RaggedStrings(d[0].data_ptr(), d[1].data_ptr(), B, d[2].data_ptr(), d[3].data_ptr(), B, dc.data_ptr(), B * L, None, K.MEM_DEVICE)
 out = K.RaggedIds(ob.data_ptr(), oe.data_ptr(), ids.data_ptr(), B * L, 0, nid.data_ptr(), K.MEM_DEVICE)
-st = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+st = stream.cuda_stream
 lib = K.lib()
 for _ in range(3):
     K.check(lib.b200tok_split_bpe_run(split.handle, bpe.handle, C.byref(rin), C.byref(out), C.c_void_p(st)))
