@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — MB/s of input text tokenized (bit-exact ids) on the BASELINE.json headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3]
+
+A "step" is one pass of the fused RegexSplit -> BPETokenizer hot path over one synthetic batch
+(C1: gpt2-shaped BPE, 65 536 x 512-byte printable-ASCII docs per GPU; weak scaling: every rank tokenises its
+own 65 536-row shard and, for N > 1, the ragged id rows are all-gathered over NCCL).
+  value       whole-job MB/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e         the same metric through the host-buffer C-ABI call an ov::Op::evaluate() shim makes
+              (pinned host buffers; H2D and D2H copies inside the timed region)
+  roofline    dominant kernel (rows_kernel<BPE>) algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  cpu_baseline  the CPU oracle (restatement of the reference ops, 1 thread like the reference's serial evaluate())
+                on a bounded sample of the same workload
+`--impl reference` times the reference's CPU path (the oracle port; the reference itself cannot be built here —
+it needs OpenVINO) with all host threads on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    "c1": dict(kind="bpe", vocab="gpt2_synth", rows=65536, row_bytes=512, gen="ascii",
+               name="C1: gpt2-shaped byte-level BPE (50 257 vocab / 50 000 merges, synthetic stand-in gpt2_synth), "
+                    "65 536 x 512 B printable-ASCII docs per GPU, fused RegexSplit->BPETokenizer"),
+    "c2": dict(kind="wordpiece", vocab="bert_synth", rows=65536, row_bytes=256, gen="ascii_lower",
+               name="C2: bert-shaped WordPiece (30 522 vocab, synthetic stand-in bert_synth), 65 536 x 256 B lower-cased "
+                    "printable-ASCII docs per GPU, fused RegexSplit x2->WordpieceTokenizer"),
+    "c3": dict(kind="bpe", vocab="llama3_synth", rows=32768, row_bytes=1024, gen="utf8",
+               name="C3 shard: Llama-3-shaped BPE (128 256 vocab, synthetic stand-in llama3_synth), 32 768 x 1 KiB "
+                    "mixed-UTF-8 docs per GPU (262 144 rows at 8 GPUs), fused RegexSplit->BPETokenizer"),
+}
+
+
+def make_batch(w, seed):
+    import cases
+    if w["gen"] == "ascii":
+        return cases.random_ascii_batch(w["rows"], w["row_bytes"], seed)
+    if w["gen"] == "ascii_lower":
+        return cases.random_ascii_batch(w["rows"], w["row_bytes"], seed, lower=True)
+    return cases.mixed_utf8_batch(w["rows"], w["row_bytes"], seed)
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = sm[len(sm) // 2:] if sm else []     # the upper half of the samples = under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_sample(w, batch, rows):
+    rb, re_, b, e, c = batch
+    n = min(rows, len(rb))
+    L = w["row_bytes"]
+    return (rb[:n], re_[:n], b[:n], e[:n], c[: n * L])
+
+
+def oracle_runner(w):
+    """Returns f(batch, threads) -> n_ids running the CPU oracle chain for the workload."""
+    import oracle
+    from openvino_tokenizers_b200 import assets as A
+    from openvino_tokenizers_b200.strings import pack_strings
+    if w["kind"] == "bpe":
+        a = A.load_bpe(w["vocab"])
+        v, ml, mr, ad, aid = a.tensors()
+        sp = oracle.SplitOracle(a.split_pattern, "isolate")
+        bpe = oracle.BpeOracle(v, ml, mr, ad, aid, cache_capacity=a.cache_capacity)
+
+        def run(batch, threads):
+            s = sp(*batch, threads=threads)
+            return len(bpe(s[0], s[1], s[2], s[3], batch[4], threads=threads)[2])
+        return run
+    a = A.load_wordpiece(w["vocab"])
+    s1 = oracle.SplitOracle(A.BERT_WHITESPACE_PATTERN, "remove")
+    s2 = oracle.SplitOracle(A.BERT_PUNCT_PATTERN, "isolate")
+    wp = oracle.WordpieceOracle(pack_strings(a.vocab), a.suffix_indicator, a.max_bytes_per_word)
+
+    def run(batch, threads):
+        r1 = s1(*batch, threads=threads)
+        r2 = s2(r1[0], r1[1], r1[2], r1[3], batch[4], threads=threads)
+        return len(wp(r2[0], r2[1], r2[2], r2[3], batch[4], a.unk_token_id, threads=threads)[2])
+    return run
+
+
+def time_cpu(run, batch, threads, repeats=3):
+    run(batch, threads)   # warm-up: builds nothing new but fills the reference's 20 000-entry BPE cache
+    best = 1e30
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run(batch, threads)
+        best = min(best, time.perf_counter() - t0)
+    return len(batch[4]) / 1e6 / best
+
+
+def main_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    batch = make_batch(w, 1234)
+    cores = os.cpu_count() or 1
+    sample_rows = 16384
+    sample = cpu_sample(w, batch, sample_rows)
+    run = oracle_runner(w)
+    for _ in range(args.warmup):
+        run(sample, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(sample, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    mbs = len(sample[4]) / 1e6 / dt
+    desc = f"{len(sample[0])} of {w['rows']} rows x {w['row_bytes']} B per step (bounded sample of the workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": "input text tokenized (bit-exact ids)", "value": mbs, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": w["name"], "note": "CPU oracle port of the reference ops (reference not buildable: needs OpenVINO)"},
+        "cpu_baseline": {"value": mbs, "unit": "MB/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": mbs, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return main_reference(args, w, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from openvino_tokenizers_b200 import runtime as R
+    from openvino_tokenizers_b200.sharded import allgatherv_ragged
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pipe = R.TokenizerPipeline(w["kind"], w["vocab"], device=local_rank)
+    batch = make_batch(w, 1234 + rank)                    # weak scaling: every rank has its own shard
+    n_bytes = int(len(batch[4]))
+    db = R.to_device(batch, dev)
+    hb = R.to_pinned(batch)
+    ho = pipe.alloc_host_out(db.n_rows, db.n_chars + db.n_elems)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        o = pipe.run_device(db)
+        if world > 1:
+            n = int(o["n"].item())
+            counts = o["ends"] - o["begins"]
+            allgatherv_ragged(o["ids"][:n], counts)
+        return o
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        step_device()
+        pipe.run_host(hb, ho)
+    barrier()
+
+    # ---- device-resident timed region: K steps, one CUDA-event pair per step, L2 flushed between steps ----
+    pipe.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = pipe.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        o = step_device()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+        km = pipe.last_kernel_ms()
+        if km > 0:
+            kernel_ms.append(km)
+    barrier()
+    launches = pipe.launches - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    pipe.set_timing(False)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    n_ids = int(o["n"].item())
+
+    # ---- end to end: host (pinned) buffers -> C ABI -> host buffers, every step ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_host = pipe.run_host(hb, ho)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item()) / args.steps
+    assert n_host == n_ids
+    h2d = n_bytes + 8 * db.n_rows + 8 * db.n_elems
+    d2h = 4 * n_ids + 8 * db.n_rows
+
+    total_bytes = n_bytes * world
+    value = total_bytes / 1e6 / (ms_per_step / 1e3)
+    e2e_value = total_bytes / 1e6 / e2e_s
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo_bytes = n_bytes + 16 * db.n_rows + 4 * n_ids
+        k_ms = statistics.mean(kernel_ms) if kernel_ms else None
+        achieved = algo_bytes / 1e9 / (k_ms / 1e3) if k_ms else None
+        traffic = None
+        tp = ROOT / "profiles" / "roofline_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(args.workload)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                    "traffic": traffic, "kernel": f"rows_kernel<{w['kind']}>", "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                    "kernel_share_of_step": (k_ms / ms_per_step) if k_ms else None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            run = oracle_runner(w)
+            cores = os.cpu_count() or 1
+            s1 = cpu_sample(w, batch, 4096)
+            v1 = time_cpu(run, s1, 1)
+            sN = cpu_sample(w, batch, 16384)
+            vN = time_cpu(run, sN, cores)
+            cpu = {"value": v1, "unit": "MB/s", "cores": 1, "kind": "port",
+                   "sample": f"first 4096 of {w['rows']} rows x {w['row_bytes']} B, best of 3 after 1 warm-up pass; the reference's "
+                             "evaluate() for RegexSplit/BPE is a serial loop, hence 1 thread",
+                   "all_cores": {"value": vN, "cores": cores, "sample": "first 16384 rows, rows sharded over threads"}}
+        print(json.dumps({
+            "metric": "input text tokenized (bit-exact ids)", "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": w["name"], "rows_per_gpu": db.n_rows, "row_bytes": w["row_bytes"], "tokens_per_gpu": n_ids,
+                       "l2": "256 MiB buffer zeroed between timed steps (L2 flush), outside the per-step event pair",
+                       "multi_gpu": "row shards + all-gatherv of ragged ids over NCCL" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3, "path": "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,11 @@ B200TOK_API int b200tok_device_count(void);
 B200TOK_API void b200tok_destroy(b200tok_handle h);     /* any handle kind */
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 B200TOK_API int64_t b200tok_launch_count(b200tok_handle h);
+/* Optional CUDA-event timing of the dominant kernel (the row kernel) of the row ops: enable once, then after a
+ * call has completed (stream synchronised) read the duration of that call's row kernel in milliseconds.
+ * Returns a negative value if timing is disabled or no call has been made. */
+B200TOK_API void b200tok_set_timing(b200tok_handle h, int enabled);
+B200TOK_API float b200tok_last_kernel_ms(b200tok_handle h);
 
 /* ---- RegexSplit ----------------------------------------------------------------------------
  * attributes: behaviour / invert / max_splits (src/regex_split.hpp:42-47); pattern = input [5|6].

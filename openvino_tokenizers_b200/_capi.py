@@ -114,6 +114,9 @@ def lib():
         L.b200tok_launch_count.restype = C.c_int64
         L.b200tok_launch_count.argtypes = [C.c_void_p]
         L.b200tok_destroy.argtypes = [C.c_void_p]
+        L.b200tok_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.b200tok_last_kernel_ms.argtypes = [C.c_void_p]
+        L.b200tok_last_kernel_ms.restype = C.c_float
         L.b200tok_vocabdec_max_chars.restype = C.c_int64
         L.b200tok_vocabdec_max_chars.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
         _lib = L
@@ -127,6 +130,7 @@ def check(rc: int):
 
 EXPORTED_SYMBOLS = [
     "b200tok_version", "b200tok_last_error", "b200tok_device_count", "b200tok_destroy", "b200tok_launch_count",
+    "b200tok_set_timing", "b200tok_last_kernel_ms",
     "b200tok_regexsplit_create", "b200tok_regexsplit_run",
     "b200tok_bpe_create", "b200tok_bpe_run", "b200tok_split_bpe_run",
     "b200tok_wordpiece_create", "b200tok_wordpiece_run", "b200tok_split_wordpiece_run",

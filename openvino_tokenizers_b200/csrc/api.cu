@@ -106,7 +106,11 @@ struct RowWorkspace {
     cudaStream_t stream = nullptr;
     size_t giants_cap = 4096;
     size_t pool_bytes = 8u << 20;
+    bool timing = false, timed = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~RowWorkspace() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
         if (h_status) cudaFreeHost(h_status);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -323,9 +327,14 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
             else CU(cudaFuncSetAttribute(rows_kernel<OP_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set[call.op][owner->device] = true;
         }
+        if (w.timing) {
+            if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); }
+            CU(cudaEventRecord(w.ev0, st));
+        }
         if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
         else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
         else rows_kernel<OP_SPLIT><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
+        if (w.timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
         owner->launches += 2;
         if (call.op == OP_BPE) {
             CU(w.pool.ensure(w.pool_bytes));
@@ -413,6 +422,21 @@ B200TOK_API void b200tok_destroy(b200tok_handle h) {
     delete h;
 }
 B200TOK_API int64_t b200tok_launch_count(b200tok_handle h) { return h ? h->launches : 0; }
+B200TOK_API void b200tok_set_timing(b200tok_handle h, int enabled) {
+    if (!h) return;
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->ws.timing = enabled != 0;
+    h->ws.timed = false;
+}
+B200TOK_API float b200tok_last_kernel_ms(b200tok_handle h) {
+    if (!h) return -1.f;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!h->ws.timing || !h->ws.timed) return -1.f;
+    DeviceGuard g(h->device);
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ws.ev0, h->ws.ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
 
 // ---- RegexSplit ----
 B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* d, b200tok_handle* out) {
