@@ -61,8 +61,10 @@ struct RowParams {
 
 struct __align__(16) WarpSmem {
     uint8_t bytes[WBYTES];
-    uint16_t seg[WIN + 4];
-    uint16_t cnt[WIN + 4];
+    uint16_t seg[WIN + 4];          // segment list: start | flags, plus an end sentinel
+    uint16_t act[WIN + 4];          // indices of the segments that still have a mergeable pair
+    uint32_t segbits[NWORDS];       // bit per position: a segment starts here
+    uint32_t actbits[NWORDS];       // bit per position: the pair (w, w+1) is mergeable
     union {
         struct {
             uint8_t cls[WBYTES];
@@ -261,8 +263,10 @@ __device__ __forceinline__ int split_window(WarpSmem& S, const RowParams& P, con
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
         if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = sg;
+        if (lane == 0) S.segbits[it] = m;
         ns += __popc(m);
     }
+    for (int it = (wlen + 31) / 32 + lane; it < NWORDS; it += 32) S.segbits[it] = 0;
     __syncwarp();
     // completeness
     if (hi_is_end && !unc) {
@@ -291,6 +295,154 @@ __device__ __noinline__ int giant_segment(const RowParams& P, int pos, int end_r
     int q = sc.next(0);
     while (q < end_rel && match_rep(sc, P.spec, P.repeat != 0, q, end_rel).len == 0) q = sc.next(q);
     return q;
+}
+
+// any set bit in [a, b)
+__device__ __forceinline__ bool range_any(const uint32_t* words, int a, int b) {
+    if (b <= a) return false;
+    int wa = a >> 5;
+    const int wb = (b - 1) >> 5;
+    uint32_t m = words[wa] & (0xFFFFFFFFu << (a & 31));
+    for (; wa < wb; ++wa, m = words[wa]) if (m) return true;
+    return (m & (0xFFFFFFFFu >> (31 - ((b - 1) & 31)))) != 0;
+}
+
+// BPE for all kept segments of a window.  Fast path (every symbol is one byte): symbolisation and the initial
+// pair lookups run position-parallel; only segments that own a mergeable pair enter a lane-level work queue, where
+// each lane performs one merge step per iteration (argmin over packed (rank,birth) keys, lazy deletion, two new
+// lookups).  Windows with multi-byte symbols or dropped bytes take the serial per-lane path.
+__device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& BT, const RowParams& P, int lane,
+                                                  int ns, int send, bool whole) {
+    auto& bp = S.u.bp;
+    const uint32_t lt = (1u << lane) - 1u;
+    bool complex = false;
+    for (int w = lane; w < send; w += 32) {
+        const uint8_t c = S.bytes[w];
+        int32_t id = BT.byte_sym[c];
+        if (id == kSymWalk) {
+            const int pe = next_bit(S.segbits, w, send);
+            int j = w;
+            id = trie_longest(BT.trie, S.bytes, j, pe);
+            if (id >= 0 && j != w + 1) complex = true;
+        }
+        if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
+        bp.ids[w] = id;
+    }
+    complex = __any_sync(0xFFFFFFFFu, complex);
+    __syncwarp();
+    if (complex) {
+        for (int j = lane; j < ns; j += 32) {
+            const uint16_t sg = S.seg[j];
+            const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
+            int c = 0;
+            if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
+                const int n = bpe_symbolize(BT, S.bytes, s, e, bp.ids + s);
+                c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, bp.newid + s, n);
+            }
+            for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
+        }
+        return;
+    }
+    // initial pair lookups, one position per lane
+    for (int it = 0; it * 32 < send; ++it) {
+        const int w = it * 32 + lane;
+        bool found = false;
+        if (w < send) {
+            uint32_t k = kNoKey;
+            if (w + 1 < send && !((S.segbits[(w + 1) >> 5] >> ((w + 1) & 31)) & 1u)) {
+                int32_t r, v;
+                found = merge_find(BT.merges, bp.ids[w], bp.ids[w + 1], r, v);
+                if (found) { k = ((uint32_t)r << kPackedBirthBits) | (uint32_t)w; bp.newid[w] = v; }
+            }
+            bp.key[w] = k;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, found);
+        if (lane == 0) S.actbits[it] = m;
+    }
+    __syncwarp();
+    // segments that need merging -> S.act[]; dropped segments are erased; 2-symbol segments finish here
+    int nact = 0;
+    for (int j0 = 0; j0 < ns; j0 += 32) {
+        const int j = j0 + lane;
+        bool act = false;
+        if (j < ns) {
+            const uint16_t sg = S.seg[j];
+            const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
+            if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
+                for (int t = s; t < e; ++t) bp.ids[t] = -1;
+            } else if (e - s >= 2 && range_any(S.actbits, s, e - 1)) {
+                if (e - s == 2) { bp.ids[s] = bp.newid[s]; bp.ids[s + 1] = -1; }
+                else act = true;
+            }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, act);
+        if (act) S.act[nact + __popc(m & lt)] = (uint16_t)j;
+        nact += __popc(m);
+    }
+    __syncwarp();
+    // lane-level work queue: one merge step per iteration
+    int head = 0, s = 0, n0 = 0, merges = 0;
+    bool have = false;
+    for (;;) {
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
+        if (!have) {
+            const int qi = head + __popc(need & lt);
+            if (qi < nact) {
+                const int j = S.act[qi];
+                s = S.seg[j] & POS_MASK;
+                n0 = (S.seg[j + 1] & POS_MASK) - s;
+                merges = 0;
+                have = true;
+            }
+        }
+        head += __popc(need);
+        if (!__any_sync(0xFFFFFFFFu, have)) break;
+        if (have) {
+            uint32_t best = kNoKey;
+            int bk = -1;
+            for (int k = 0; k + 1 < n0; ++k) {
+                const uint32_t q = bp.key[s + k];
+                if (q < best) { best = q; bk = k; }
+            }
+            if (bk < 0) { have = false; continue; }
+            int t = bk + 1;
+            while (bp.ids[s + t] < 0) ++t;                    // right operand (skip dead slots)
+            const int32_t nid = bp.newid[s + bk];
+            bp.ids[s + bk] = nid;
+            bp.ids[s + t] = -1;
+            bp.key[s + t] = kNoKey;
+            ++merges;
+            const uint32_t birth = (uint32_t)(WIN + merges);    // after every initial birth (< WIN), increasing per merge
+            int pl = bk - 1;
+            while (pl >= 0 && bp.ids[s + pl] < 0) --pl;
+            int nr = t + 1;
+            while (nr < n0 && bp.ids[s + nr] < 0) ++nr;
+            if (pl >= 0) {
+                int32_t r, v;
+                const bool f = merge_find(BT.merges, bp.ids[s + pl], nid, r, v);
+                bp.key[s + pl] = f ? (((uint32_t)r << kPackedBirthBits) | birth) : kNoKey;
+                bp.newid[s + pl] = v;
+            }
+            uint32_t kk = kNoKey;
+            if (nr < n0) {
+                int32_t r, v;
+                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) { kk = ((uint32_t)r << kPackedBirthBits) | birth; bp.newid[s + bk] = v; }
+            }
+            bp.key[s + bk] = kk;
+        }
+    }
+}
+
+// WordPiece for all kept segments (words) of a window: one lane per word, longest-match trie walks.
+__device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowParams& P, int lane, int ns, bool whole) {
+    auto& bp = S.u.bp;
+    for (int j = lane; j < ns; j += 32) {
+        const uint16_t sg = S.seg[j];
+        const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
+        int c = 0;
+        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) c = wordpiece_word(P.wp, S.bytes, s, e, P.unk_id, bp.ids + s);
+        for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
+    }
 }
 
 // Reserve (end-begin)+suffix_len slots for a BPE piece handled by giant_bpe_kernel and queue it.
@@ -371,6 +523,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams 
                     __syncwarp();
                     if (whole) {
                         if (lane == 0) { S.seg[0] = F_MATCH; S.seg[1] = (uint16_t)wlen; }
+                        if (lane < NWORDS) S.segbits[lane] = lane == 0 ? 1u : 0u;
                         ns = 1; advance = wlen;
                         __syncwarp();
                     } else {
@@ -454,35 +607,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams 
                         }
                     }
                 } else {
-                    // piece phase: lanes take segments round-robin
-                    for (int j = lane; j < ns; j += 32) {
-                        const uint16_t sg = S.seg[j];
-                        int c = 0;
-                        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
-                            const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
-                            if (OP == OP_BPE) {
-                                const int n = bpe_symbolize(BT, S.bytes, s, e, S.u.bp.ids + s);
-                                c = bpe_merge_packed(BT.merges, S.u.bp.ids + s, S.u.bp.key + s, S.u.bp.newid + s, n);
-                            } else {
-                                c = wordpiece_word(P.wp, S.bytes, s, e, P.unk_id, S.u.bp.ids + s);
-                            }
-                        }
-                        S.cnt[j] = (uint16_t)c;
-                    }
+                    // piece phase: every kept segment becomes tokens in S.u.bp.ids[start..], dead slots = -1
+                    const int send = S.seg[ns] & POS_MASK;
+                    if (OP == OP_BPE) bpe_window_pieces(S, BT, P, lane, ns, send, whole);
+                    else wordpiece_window_pieces(S, P, lane, ns, whole);
                     __syncwarp();
-                    // output phase: scan the counts, copy tokens to the row slot
-                    for (int j0 = 0; j0 < ns; j0 += 32) {
-                        const int j = j0 + lane;
-                        const int c = j < ns ? S.cnt[j] : 0;
-                        const int incl = warp_incl_scan(c, lane);
-                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                        if (c) {
-                            const int s = S.seg[j] & POS_MASK;
-                            const int64_t o = base + emitted + incl - c;
-                            if (o + c <= P.tmp_cap) { for (int t = 0; t < c; ++t) P.tmp_a[o + t] = S.u.bp.ids[s + t]; }
+                    // output phase: position-parallel compaction of the live tokens into the row slot
+                    for (int it = 0; it * 32 < send; ++it) {
+                        const int w = it * 32 + lane;
+                        const int32_t tok = w < send ? S.u.bp.ids[w] : -1;
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, tok >= 0);
+                        if (tok >= 0) {
+                            const int64_t o = base + emitted + __popc(m & ((1u << lane) - 1u));
+                            if (o < P.tmp_cap) P.tmp_a[o] = tok;
                             else atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
                         }
-                        emitted += total;
+                        emitted += __popc(m);
                     }
                     __syncwarp();
                 }
