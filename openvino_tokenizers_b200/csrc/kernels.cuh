@@ -19,6 +19,7 @@ namespace b200tok {
 constexpr int WIN = 512;            // fresh bytes per window
 constexpr int LA = 16;              // look-ahead bytes staged beyond the window
 constexpr int WBYTES = WIN + LA + 16;
+constexpr int LBK = 16;             // look-back bytes staged before the window (closed-form splitters)
 constexpr int NWORDS = (WIN + LA + 31) / 32 + 1;
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
@@ -60,14 +61,16 @@ struct RowParams {
 };
 
 struct __align__(16) WarpSmem {
-    uint8_t bytes[WBYTES];
+    uint8_t raw_bytes[LBK + WBYTES];
+    __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }   // index 0 = window position
     uint16_t seg[WIN + 4];          // segment list: start | flags, plus an end sentinel
     uint16_t act[WIN + 4];          // indices of the segments that still have a mergeable pair
     uint32_t segbits[NWORDS];       // bit per position: a segment starts here
     uint32_t actbits[NWORDS];       // bit per position: the pair (w, w+1) is mergeable
     union {
         struct {
-            uint8_t cls[WBYTES];
+            uint8_t raw_cls[LBK + WBYTES];
+            __device__ __forceinline__ uint8_t* K() { return raw_cls + LBK; }
             uint32_t bnd[NWORDS], cs[NWORDS], nl[NWORDS], mm[NWORDS], chain[NWORDS];
             uint16_t entry[32];
             uint16_t nxt[WIN + LA + 8];
@@ -149,26 +152,26 @@ __device__ __forceinline__ int split_window(WarpSmem& S, const RowParams& P, con
     T.ascii = ascii_smem;
     // pass A: class per byte (continuation bytes copy their owner's class, plus C_CONT)
     for (int w = lane; w < nload; w += 32) {
-        const uint8_t b = S.bytes[w];
+        const uint8_t b = S.B()[w];
         uint8_t k;
         if (b < 0x80) k = ascii_smem[b];
         else if (is_cont_byte(b) && w > 0) {   // (index 0 is always treated as a character start)
             int j = w - 1;
-            while (j >= 0 && j > w - 4 && is_cont_byte(S.bytes[j])) --j;
+            while (j >= 0 && j > w - 4 && is_cont_byte(S.B()[j])) --j;
             k = C_CONT;
-            if (j >= 0 && j > w - 4 && S.bytes[j] >= 0xC0) k |= char_class(S.bytes, j, end_rel, T);
-        } else k = char_class(S.bytes, w, end_rel, T);
-        sp.cls[w] = k;
+            if (j >= 0 && j > w - 4 && S.B()[j] >= 0xC0) k |= char_class(S.B(), j, end_rel, T);
+        } else k = char_class(S.B(), w, end_rel, T);
+        sp.K()[w] = k;
     }
     __syncwarp();
     // pass B: run-boundary / char-start / newline bitmasks
     for (int it = 0; it < NWORDS; ++it) {
         const int w = it * 32 + lane;
         const bool valid = w < nload;
-        const uint8_t k = valid ? sp.cls[w] : 0;
+        const uint8_t k = valid ? sp.K()[w] : 0;
         const bool start = valid && !(k & C_CONT);
         bool bnd = false;
-        if (start) bnd = (w == 0) || kind_of(k, P.spec.pat, P.spec.class_mask) != kind_of(sp.cls[w - 1], P.spec.pat, P.spec.class_mask);
+        if (start) bnd = (w == 0) || kind_of(k, P.spec.pat, P.spec.class_mask) != kind_of(sp.K()[w - 1], P.spec.pat, P.spec.class_mask);
         const uint32_t mb = __ballot_sync(0xFFFFFFFFu, bnd);
         const uint32_t mc = __ballot_sync(0xFFFFFFFFu, start);
         const uint32_t mn = __ballot_sync(0xFFFFFFFFu, valid && (k & C_NL) && !(k & C_CONT));
@@ -176,12 +179,12 @@ __device__ __forceinline__ int split_window(WarpSmem& S, const RowParams& P, con
     }
     __syncwarp();
     // pass C: the match that would start at every character position
-    WinCtx ctx{S.bytes, sp.cls, sp.bnd, sp.cs, sp.nl, wlen, nload};
+    WinCtx ctx{S.B(), sp.K(), sp.bnd, sp.cs, sp.nl, wlen, nload};
     const bool hi_is_end = (wlen == end_rel);
     for (int it = 0; it * 32 < wlen; ++it) {
         const int w = it * 32 + lane;
         bool is_m = false;
-        if (w < wlen && !(sp.cls[w] & C_CONT)) {
+        if (w < wlen && !(sp.K()[w] & C_CONT)) {
             const Match m = match_rep(ctx, P.spec, P.repeat != 0, w, end_rel);
             const bool unc = !hi_is_end && m.peek > wlen;
             int step = m.len > 0 ? w + m.len : ctx.next(w);
@@ -285,6 +288,54 @@ __device__ __forceinline__ int split_window(WarpSmem& S, const RowParams& P, con
     return ns;
 }
 
+// Split phase for the GPT-2 byte-level patterns in isolate mode: the closed-form per-position predicate
+// (tok_core.cuh gpt2_piece_starts_at) replaces match evaluation + chain resolution.  `lb` look-back bytes of the
+// same element are staged before the window so that every position sees its true left context.
+__device__ __forceinline__ int split_window_gpt2(WarpSmem& S, const RowParams& P, const uint8_t* ascii_smem, int lane,
+                                                 int wlen, int end_rel, int nload, int lb, int& advance) {
+    auto& sp = S.u.sp;
+    uint8_t* const B = S.B();
+    uint8_t* const KC = sp.K();
+    ClassTables T = P.cls;
+    T.ascii = ascii_smem;
+    for (int w = lane - lb; w < nload; w += 32) {
+        const uint8_t b = B[w];
+        uint8_t k;
+        if (b < 0x80) k = ascii_smem[b];
+        else if (is_cont_byte(b) && w > -lb) {
+            int j = w - 1;
+            while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
+            k = C_CONT;
+            if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
+        } else k = char_class(B, w, end_rel, T);
+        KC[w] = k;
+    }
+    __syncwarp();
+    const bool digits = P.spec.pat == PAT_GPT2_DIGITS;
+    int ns = 0;
+    for (int it = 0; it * 32 < wlen; ++it) {
+        const int w = it * 32 + lane;
+        const bool st = w < wlen && (w == 0 || gpt2_piece_starts_at(B, KC, w, -lb, end_rel, digits));
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
+        if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(w | F_MATCH);
+        if (lane == 0) S.segbits[it] = m;
+        ns += __popc(m);
+    }
+    for (int it = (wlen + 31) / 32 + lane; it < NWORDS; it += 32) S.segbits[it] = 0;
+    __syncwarp();
+    if (wlen == end_rel) {
+        advance = wlen;
+        if (lane == 0) S.seg[ns] = (uint16_t)wlen;
+    } else {
+        // the last piece may continue beyond the window: redo it from its start in the next window
+        --ns;
+        advance = S.seg[ns] & POS_MASK;
+        if (lane == 0 && advance > 0) S.segbits[advance >> 5] &= ~(1u << (advance & 31));
+    }
+    __syncwarp();
+    return ns;
+}
+
 // Sequentially (lane 0) find the extent of the segment starting at chars[pos] when it does not fit
 // a window.  Returns its length; is_match/drop describe it.
 __device__ __noinline__ int giant_segment(const RowParams& P, int pos, int end_rel, int& is_match, int& drop) {
@@ -317,12 +368,12 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
     const uint32_t lt = (1u << lane) - 1u;
     bool complex = false;
     for (int w = lane; w < send; w += 32) {
-        const uint8_t c = S.bytes[w];
+        const uint8_t c = S.B()[w];
         int32_t id = BT.byte_sym[c];
         if (id == kSymWalk) {
             const int pe = next_bit(S.segbits, w, send);
             int j = w;
-            id = trie_longest(BT.trie, S.bytes, j, pe);
+            id = trie_longest(BT.trie, S.B(), j, pe);
             if (id >= 0 && j != w + 1) complex = true;
         }
         if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
@@ -336,7 +387,7 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
             const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
             int c = 0;
             if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
-                const int n = bpe_symbolize(BT, S.bytes, s, e, bp.ids + s);
+                const int n = bpe_symbolize(BT, S.B(), s, e, bp.ids + s);
                 c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, bp.newid + s, n);
             }
             for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
@@ -440,7 +491,7 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
         const uint16_t sg = S.seg[j];
         const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
         int c = 0;
-        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) c = wordpiece_word(P.wp, S.bytes, s, e, P.unk_id, bp.ids + s);
+        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) c = wordpiece_word(P.wp, S.B(), s, e, P.unk_id, bp.ids + s);
         for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
     }
 }
@@ -519,7 +570,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams 
                 const bool fits = !(whole && end_rel > WIN) && !(OP == OP_BPE && P.suffix_len > 0);
                 if (fits) {
                     const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
-                    for (int w = lane; w < nload + 4; w += 32) S.bytes[w] = (w < nload) ? __ldg(P.chars + pos + w) : 0;
+                    const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
+                    for (int w = lane - lb; w < nload + 4; w += 32) S.B()[w] = (w < nload) ? __ldg(P.chars + pos + w) : 0;
                     __syncwarp();
                     if (whole) {
                         if (lane == 0) { S.seg[0] = F_MATCH; S.seg[1] = (uint16_t)wlen; }
@@ -527,7 +579,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams 
                         ns = 1; advance = wlen;
                         __syncwarp();
                     } else {
-                        ns = split_window(S, P, ascii_smem, lane, wlen, end_rel, nload, advance);
+                        if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1)
+                            ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
+                        else
+                            ns = split_window(S, P, ascii_smem, lane, wlen, end_rel, nload, advance);
                     }
                 }
                 if (advance == 0) {

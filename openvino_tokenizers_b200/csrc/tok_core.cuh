@@ -309,6 +309,63 @@ B2_HD Match match_at(const C& c, const SplitSpec& spec, int p, int end) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Closed form of the GPT-2 byte-level pattern in "isolate" mode.  The pattern tiles the subject, and
+// whether a piece starts at a character depends only on a few neighbouring characters, so the
+// sequential match loop collapses to a per-position predicate (checked against PCRE2 exhaustively
+// in tests/test_core_host.py).  Inputs: b[] bytes, k[] per-byte classes where continuation bytes
+// carry their owner's class bits plus C_CONT; [eb, ee) = the element.  Derivation (alternatives in
+// order 's|'t|'re|'ve|'m|'ll|'d,  ?\p{L}+,  ?\p{N}+ (or \p{N}),  ?[^\s\p{L}\p{N}]+, \s+(?!\S), \s+):
+//   * a whitespace run followed by a non-space gives up its last character (\s+(?!\S) backtracks);
+//     if that character is U+0020 it becomes the optional prefix of the following run;
+//   * runs of one kind (letter / number / other) are consumed whole, except that a contraction
+//     ("'" reached as the start of a match, i.e. not preceded by an "other" character or by U+0020)
+//     takes its one or two letters out of the following letter run.
+// ------------------------------------------------------------------------------------------
+B2_HD bool gpt2_apostrophe_starts_match(const uint8_t* b, const uint8_t* k, int q, int eb) {
+    if (q == eb) return true;
+    const uint8_t p = k[q - 1];
+    if (p & (C_L | C_N)) return true;
+    if (p & C_S) return b[q - 1] != 0x20;
+    return false;
+}
+B2_HD int gpt2_contraction_len(const uint8_t* b, int q, int ee) {
+    if (q + 1 >= ee) return 0;
+    const uint8_t b1 = b[q + 1];
+    if (b1 == 's' || b1 == 't' || b1 == 'm' || b1 == 'd') return 2;
+    if (q + 2 < ee) {
+        const uint8_t b2 = b[q + 2];
+        if ((b1 == 'r' || b1 == 'v') && b2 == 'e') return 3;
+        if (b1 == 'l' && b2 == 'l') return 3;
+    }
+    return 0;
+}
+B2_HD bool gpt2_piece_starts_at(const uint8_t* b, const uint8_t* k, int i, int eb, int ee, bool single_digits) {
+    const uint8_t c = k[i];
+    if (c & C_CONT) return false;
+    if (i == eb) return true;
+    const uint8_t p = k[i - 1];
+    if (c & C_S) {
+        if (!(p & C_S)) return true;
+        int j = i + 1;
+        while (j < ee && (k[j] & C_CONT)) ++j;
+        return j < ee && !(k[j] & C_S);
+    }
+    if (single_digits && (c & C_N)) return true;
+    if (b[i - 1] == 0x20) return false;
+    if (c & C_N) return !(p & C_N);
+    if (!(c & C_L)) return (p & (C_L | C_N | C_S)) != 0;          // "other": starts unless it continues an other-run
+    bool inside = false, ends_here = false;
+    if (b[i - 1] == '\'' && gpt2_apostrophe_starts_match(b, k, i - 1, eb) && gpt2_contraction_len(b, i - 1, ee) >= 2) inside = true;
+    if (i - 2 >= eb && b[i - 2] == '\'' && gpt2_apostrophe_starts_match(b, k, i - 2, eb)) {
+        const int cl = gpt2_contraction_len(b, i - 2, ee);
+        if (cl == 3) inside = true;
+        else if (cl == 2) ends_here = true;
+    }
+    if (i - 3 >= eb && b[i - 3] == '\'' && gpt2_apostrophe_starts_match(b, k, i - 3, eb) && gpt2_contraction_len(b, i - 3, ee) == 3) ends_here = true;
+    return !inside && (ends_here || !(p & C_L));
+}
+
 // (p)+ for the "contiguous" rewrite (src/regex_split.cpp:33-37): greedy repetition of the pattern.
 template <class C>
 B2_HD Match match_rep(const C& c, const SplitSpec& spec, bool repeat, int p, int end) {

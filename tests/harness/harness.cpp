@@ -91,3 +91,27 @@ HZ void hz_wp_destroy(void* h) { delete (HzWp*)h; }
 HZ int64_t hz_wp_word(void* h, const uint8_t* bytes, int64_t n, int32_t unk, int32_t* out) {
     return wordpiece_word(((HzWp*)h)->t.view(), bytes, 0, (int)n, unk, out);
 }
+
+// Closed-form GPT-2 piece-start predicate (tok_core.cuh gpt2_piece_starts_at) over one element; the class array is
+// built exactly like the kernel's pass A.  Writes piece begins; returns the count.
+HZ int64_t hz_gpt2_closed_form(const uint8_t* s, int64_t n, int single_digits, int32_t* out_begins) {
+    const ClassTables T = host_class_tables().view();
+    std::vector<uint8_t> k((size_t)n + 8, 0);
+    const int end = (int)n;
+    for (int w = 0; w < end; ++w) {
+        const uint8_t b = s[w];
+        uint8_t c;
+        if (b < 0x80) c = T.ascii[b];
+        else if (is_cont_byte(b) && w > 0) {
+            int j = w - 1;
+            while (j >= 0 && j > w - 4 && is_cont_byte(s[j])) --j;
+            c = C_CONT;
+            if (j >= 0 && j > w - 4 && s[j] >= 0xC0) c |= char_class(s, j, end, T);
+        } else c = char_class(s, w, end, T);
+        k[w] = c;
+    }
+    int64_t cnt = 0;
+    for (int i = 0; i < end; ++i)
+        if (gpt2_piece_starts_at(s, k.data(), i, 0, end, single_digits != 0)) out_begins[cnt++] = i;
+    return cnt;
+}

@@ -89,3 +89,15 @@ class HostWordpiece:
         out = np.empty(len(data) + 4, np.int32)
         n = lib().hz_wp_word(self.h, arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), C.c_int32(unk), out.ctypes.data_as(K.i32p))
         return out[:n].tolist()
+
+
+def gpt2_closed_form(data: bytes, single_digits=False):
+    """Piece (begin, end) list from the closed-form GPT-2 predicate."""
+    if not data:
+        return []
+    arr = np.frombuffer(data, np.uint8)
+    out = np.empty(len(data) + 1, np.int32)
+    lib().hz_gpt2_closed_form.restype = C.c_int64
+    n = lib().hz_gpt2_closed_form(arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), int(single_digits), out.ctypes.data_as(K.i32p))
+    b = out[:n].tolist()
+    return list(zip(b, b[1:] + [len(data)]))

@@ -126,3 +126,25 @@ def test_class_table_spot_checks():
     assert H.lib().hz_char_class(ord("!")) & BP and H.lib().hz_char_class(0x4E2D) & BP and not H.lib().hz_char_class(ord("a")) & BP
     assert H.lib().hz_char_class(ord("$")) & BP and not H.lib().hz_char_class(ord("$")) & P   # BERT's ASCII ranges beyond \p{P}
     assert H.lib().hz_char_class(0x0416) & L and H.lib().hz_char_class(0x0663) & N and H.lib().hz_char_class(ord("_")) & W
+
+
+@pytest.mark.parametrize("digits", [False, True])
+def test_gpt2_closed_form_equals_pcre2(oracle_mod, digits):
+    """The per-position piece-start predicate the GPT-2 window splitter uses, against PCRE2: exhaustive over short
+    strings of a small alphabet plus random strings of a wide one."""
+    import itertools
+    pat = A.GPT2_DIGITS_PATTERN if digits else A.GPT2_PATTERN
+    o = oracle_mod.SplitOracle(pat, "isolate")
+    small = ["a", "'", "s", "r", "e", "l", " ", "\n", "1", "!"]
+    for L in range(1, 5):
+        for tup in itertools.product(small, repeat=L):
+            s = "".join(tup).encode()
+            assert H.gpt2_closed_form(s, digits) == _oracle_split(o, s), s
+    rng = np.random.default_rng(3)
+    wide = ALPHA + ["m", "d", "'", "'"]
+    for _ in range(5000):
+        s = "".join(rng.choice(wide, size=int(rng.integers(1, 18)))).encode()
+        assert H.gpt2_closed_form(s, digits) == _oracle_split(o, s), s
+    for s in cases.EDGE_STRINGS + cases.long_prompts():
+        if s:
+            assert H.gpt2_closed_form(s.encode(), digits) == _oracle_split(o, s.encode()), s[:40]
