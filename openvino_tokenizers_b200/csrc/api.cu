@@ -139,8 +139,10 @@ struct BpeObj : b200tok_object {
     DBuf<int32_t> byte_sym, byte_miss;
     DevTrie trie;
     DBuf<MergeSlot> slots;
+    DBuf<int32_t> rank_newid;
+    DBuf<uint32_t> pair_rank;
     DBuf<uint8_t> suffix;
-    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, trie.view(), MergeTable{slots.p, h.mask}}; }
+    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p}}; }
 };
 struct WordpieceObj : b200tok_object {
     HostWordpiece h;
@@ -307,9 +309,10 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     if (!d_ob || !d_oe || (!d_oa && out_cap > 0)) return fail(B200TOK_E_INVALID, "missing output buffers");
 
     const size_t smem = 128 + 1024 + WARPS_PER_BLOCK * sizeof(WarpSmem);
+    const int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
     static bool attr_set[3][64] = {};
     const int nthreads = 256;
-    const int rows_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * 3);
+    const int rows_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * blocks_per_sm);
     const bool async = out_ids && !host && out_ids->n_ids_device;
 
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -494,6 +497,8 @@ B200TOK_API int b200tok_bpe_create(const b200tok_bpe_desc* d, b200tok_handle* ou
     CU(o->byte_miss.upload(o->h.byte_miss));
     CU(o->trie.upload(o->h.trie));
     CU(o->slots.upload(o->h.slots));
+    CU(o->rank_newid.upload(o->h.rank_newid));
+    CU(o->pair_rank.upload(o->h.pair_rank));
     std::vector<uint8_t> sfx(o->h.end_suffix.begin(), o->h.end_suffix.end());
     if (sfx.empty()) sfx.push_back(0);
     CU(o->suffix.upload(sfx));

@@ -64,7 +64,7 @@ struct __align__(16) WarpSmem {
     uint8_t raw_bytes[LBK + WBYTES];
     __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }   // index 0 = window position
     uint16_t seg[WIN + 4];          // segment list: start | flags, plus an end sentinel
-    uint16_t act[WIN + 4];          // indices of the segments that still have a mergeable pair
+    uint16_t act[WIN / 3 + 8];      // indices of the segments (>= 3 symbols) that still have a mergeable pair
     uint32_t segbits[NWORDS];       // bit per position: a segment starts here
     uint32_t actbits[NWORDS];       // bit per position: the pair (w, w+1) is mergeable
     union {
@@ -79,7 +79,6 @@ struct __align__(16) WarpSmem {
         struct {
             int32_t ids[WIN];
             uint32_t key[WIN];
-            int32_t newid[WIN];
         } bp;
     } u;
 };
@@ -388,22 +387,22 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
             int c = 0;
             if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
                 const int n = bpe_symbolize(BT, S.B(), s, e, bp.ids + s);
-                c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, bp.newid + s, n);
+                c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, n);
             }
             for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
         }
         return;
     }
-    // initial pair lookups, one position per lane
+    // initial pair keys, one position per lane: all symbols are one byte here, so the rank comes straight from the
+    // 64 K-entry byte-pair table (no hashing, no probing)
     for (int it = 0; it * 32 < send; ++it) {
         const int w = it * 32 + lane;
         bool found = false;
         if (w < send) {
             uint32_t k = kNoKey;
             if (w + 1 < send && !((S.segbits[(w + 1) >> 5] >> ((w + 1) & 31)) & 1u)) {
-                int32_t r, v;
-                found = merge_find(BT.merges, bp.ids[w], bp.ids[w + 1], r, v);
-                if (found) { k = ((uint32_t)r << kPackedBirthBits) | (uint32_t)w; bp.newid[w] = v; }
+                const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)S.B()[w] << 8) | S.B()[w + 1]));
+                if (r != kNoKey) { found = true; k = (r << kPackedBirthBits) | (uint32_t)w; }
             }
             bp.key[w] = k;
         }
@@ -422,7 +421,7 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
             if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
                 for (int t = s; t < e; ++t) bp.ids[t] = -1;
             } else if (e - s >= 2 && range_any(S.actbits, s, e - 1)) {
-                if (e - s == 2) { bp.ids[s] = bp.newid[s]; bp.ids[s + 1] = -1; }
+                if (e - s == 2) { bp.ids[s] = __ldg(BT.merges.rank_newid + (bp.key[s] >> kPackedBirthBits)); bp.ids[s + 1] = -1; }
                 else act = true;
             }
         }
@@ -458,7 +457,7 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
             if (bk < 0) { have = false; continue; }
             int t = bk + 1;
             while (bp.ids[s + t] < 0) ++t;                    // right operand (skip dead slots)
-            const int32_t nid = bp.newid[s + bk];
+            const int32_t nid = __ldg(BT.merges.rank_newid + (best >> kPackedBirthBits));
             bp.ids[s + bk] = nid;
             bp.ids[s + t] = -1;
             bp.key[s + t] = kNoKey;
@@ -472,12 +471,11 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
                 int32_t r, v;
                 const bool f = merge_find(BT.merges, bp.ids[s + pl], nid, r, v);
                 bp.key[s + pl] = f ? (((uint32_t)r << kPackedBirthBits) | birth) : kNoKey;
-                bp.newid[s + pl] = v;
             }
             uint32_t kk = kNoKey;
             if (nr < n0) {
                 int32_t r, v;
-                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) { kk = ((uint32_t)r << kPackedBirthBits) | birth; bp.newid[s + bk] = v; }
+                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) kk = ((uint32_t)r << kPackedBirthBits) | birth;
             }
             bp.key[s + bk] = kk;
         }
@@ -514,7 +512,7 @@ __device__ __forceinline__ void reserve_giant_bpe(const RowParams& P, int row, i
 }
 
 template <int OP>
-__global__ void __launch_bounds__(BLOCK_THREADS, 3) rows_kernel(const RowParams P) {
+__global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams P) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                   // [128]
     int32_t* bytesym_smem = reinterpret_cast<int32_t*>(smem_raw + 128);   // [256]

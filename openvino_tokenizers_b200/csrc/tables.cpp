@@ -201,12 +201,30 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
     while (cap < merges.size() * 4 + 2) cap <<= 1;
     out.slots.assign(cap, MergeSlot{kEmptyKey, kEmptyKey, kNoRank, -1});
     out.mask = (uint32_t)(cap - 1);
+    out.rank_newid.assign((size_t)std::max<int64_t>(M, 1), -1);
     for (const auto& kv : merges) {
         const uint32_t l = (uint32_t)(kv.first >> 32), r = (uint32_t)kv.first;
+        out.rank_newid[(size_t)kv.second.first] = kv.second.second;
         uint32_t h = merge_hash(l, r) & out.mask;
         while (out.slots[h].left != kEmptyKey) h = (h + 1) & out.mask;
         out.slots[h] = MergeSlot{l, r, kv.second.first, kv.second.second};
     }
+    // direct table for the initial pairs of one-byte symbols: sym1(b) is what the position-parallel symbolisation
+    // assigns to byte b when no longer token starts there (the one-byte token, else the byte-fallback / unk id)
+    out.pair_rank.assign(65536, kNoKey);
+    int32_t sym1[256];
+    for (int c = 0; c < 256; ++c) {
+        const int32_t node = out.trie.root_child[c];
+        int32_t id = (node >= 0) ? out.trie.value[node] : -1;
+        if (id < 0) id = out.byte_miss[c];
+        sym1[c] = id;
+    }
+    for (int b0 = 0; b0 < 256; ++b0)
+        for (int b1 = 0; b1 < 256; ++b1) {
+            if (sym1[b0] < 0 || sym1[b1] < 0) continue;
+            auto it = merges.find(((uint64_t)(uint32_t)sym1[b0] << 32) | (uint32_t)sym1[b1]);
+            if (it != merges.end()) out.pair_rank[(size_t)(b0 << 8 | b1)] = (uint32_t)it->second.first;
+        }
     return B200TOK_OK;
 }
 

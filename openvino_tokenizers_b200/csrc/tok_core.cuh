@@ -468,6 +468,7 @@ B2_HD uint32_t merge_hash(uint32_t l, uint32_t r) {
 struct MergeTable {
     const MergeSlot* slots;
     uint32_t mask;
+    const int32_t* rank_newid;   // [n_merges] token produced by the merge of that rank
 };
 
 #if defined(__CUDA_ARCH__)
@@ -540,6 +541,7 @@ B2_HD int32_t trie_longest(const FlatTrie& t, const uint8_t* s, int& idx, int en
 struct BpeTables {
     const int32_t* byte_sym;   // [256]
     const int32_t* byte_miss;  // [256]
+    const uint32_t* pair_rank; // [65536] rank of the merge of the one-byte symbols of (b0,b1), index b0<<8|b1; kNoKey if none
     FlatTrie trie;
     MergeTable merges;
 };
@@ -614,7 +616,7 @@ B2_HD int bpe_merge_serial(const MergeTable& M, int32_t* ids, int32_t* rank, int
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kPackedBirthBits = 12;
 constexpr int kPackedMaxSymbols = 2048;
-B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int32_t* newid, int n) {
+B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int n) {
     if (n < 2) return n;
     bool any = false;
     for (int k = 0; k + 1 < n; ++k) {
@@ -622,7 +624,6 @@ B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int
         const bool f = merge_find(M, ids[k], ids[k + 1], r, v);
         any |= f;
         key[k] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)k) : kNoKey;
-        newid[k] = v;
     }
     if (!any) return n;
     int seq = n - 1;
@@ -634,22 +635,20 @@ B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int
             if (q < best) { best = q; bk = k; }
         }
         if (bk < 0) break;
-        ids[bk] = newid[bk];
+        ids[bk] = M.rank_newid[best >> kPackedBirthBits];
         for (int k = bk + 1; k + 1 < n; ++k) ids[k] = ids[k + 1];
-        for (int k = bk + 1; k + 2 < n; ++k) { key[k] = key[k + 1]; newid[k] = newid[k + 1]; }
+        for (int k = bk + 1; k + 2 < n; ++k) key[k] = key[k + 1];
         --n;
         ++seq;
         if (bk > 0) {
             int32_t r, v;
             const bool f = merge_find(M, ids[bk - 1], ids[bk], r, v);
             key[bk - 1] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
-            newid[bk - 1] = v;
         }
         if (bk + 1 < n) {
             int32_t r, v;
             const bool f = merge_find(M, ids[bk], ids[bk + 1], r, v);
             key[bk] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
-            newid[bk] = v;
         }
     }
     return n;

@@ -72,7 +72,7 @@ HZ int64_t hz_bpe_piece(void* h, const uint8_t* bytes, int64_t n, int mode, int3
     } else if (mode == 2) {
         if (m > kPackedMaxSymbols) return -1;
         std::vector<uint32_t> key(L + 2);
-        cnt = bpe_merge_packed(T.merges, ids.data(), key.data(), newid.data(), m);
+        cnt = bpe_merge_packed(T.merges, ids.data(), key.data(), m);
         std::memcpy(out, ids.data(), (size_t)cnt * 4);
     } else {
         cnt = bpe_merge_heap(T.merges, m, ids.data(), prev.data(), next.data(), heap.data(), out);
