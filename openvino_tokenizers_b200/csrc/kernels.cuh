@@ -314,7 +314,7 @@ __device__ __forceinline__ int split_window_gpt2(WarpSmem& S, const RowParams& P
     int ns = 0;
     for (int it = 0; it * 32 < wlen; ++it) {
         const int w = it * 32 + lane;
-        const bool st = w < wlen && (w == 0 || gpt2_piece_starts_at(B, KC, w, -lb, end_rel, digits));
+        const bool st = w < wlen && (w == 0 || gpt2_piece_starts_t(B, ClsArray{KC}, w, -lb, end_rel, digits));
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
         if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(w | F_MATCH);
         if (lane == 0) S.segbits[it] = m;
@@ -357,51 +357,38 @@ __device__ __forceinline__ bool range_any(const uint32_t* words, int a, int b) {
     return (m & (0xFFFFFFFFu >> (31 - ((b - 1) & 31)))) != 0;
 }
 
-// BPE for all kept segments of a window.  Fast path (every symbol is one byte): symbolisation and the initial
-// pair lookups run position-parallel; only segments that own a mergeable pair enter a lane-level work queue, where
-// each lane performs one merge step per iteration (argmin over packed (rank,birth) keys, lazy deletion, two new
-// lookups).  Windows with multi-byte symbols or dropped bytes take the serial per-lane path.
-__device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& BT, const RowParams& P, int lane,
-                                                  int ns, int send, bool whole) {
+// ---------------------------------------------------------------------------------------------------------
+// BPE over the kept segments of a window.  Conventions of the shared-memory state (S.u.bp):
+//   ids[w]  token id of the symbol living at position w, -1 = no symbol (merged away / dropped segment)
+//   key[w]  packed (rank << 12 | birth) of the pair (previous live symbol, symbol at w); kNoKey if none.
+//           Initial births are the window positions (< WIN), the pairs created by the m-th merge of a
+//           segment get WIN + m: the same order as the reference's push-sequence numbers.
+//   S.actbits bit w = key[w] != kNoKey after the initial lookups.
+// ---------------------------------------------------------------------------------------------------------
+
+// Position-parallel symbolisation + initial pair keys (every symbol one byte; ranks from the byte-pair table).
+// Returns true if the window needs the serial path (a multi-byte symbol or a dropped byte was seen).
+__device__ __forceinline__ bool bpe_symbolize_keys(WarpSmem& S, const BpeTables& BT, int lane, int send) {
     auto& bp = S.u.bp;
-    const uint32_t lt = (1u << lane) - 1u;
+    const uint8_t* B = S.B();
     bool complex = false;
-    for (int w = lane; w < send; w += 32) {
-        const uint8_t c = S.B()[w];
-        int32_t id = BT.byte_sym[c];
-        if (id == kSymWalk) {
-            const int pe = next_bit(S.segbits, w, send);
-            int j = w;
-            id = trie_longest(BT.trie, S.B(), j, pe);
-            if (id >= 0 && j != w + 1) complex = true;
-        }
-        if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
-        bp.ids[w] = id;
-    }
-    complex = __any_sync(0xFFFFFFFFu, complex);
-    __syncwarp();
-    if (complex) {
-        for (int j = lane; j < ns; j += 32) {
-            const uint16_t sg = S.seg[j];
-            const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
-            int c = 0;
-            if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
-                const int n = bpe_symbolize(BT, S.B(), s, e, bp.ids + s);
-                c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, n);
-            }
-            for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
-        }
-        return;
-    }
-    // initial pair keys, one position per lane: all symbols are one byte here, so the rank comes straight from the
-    // 64 K-entry byte-pair table (no hashing, no probing)
     for (int it = 0; it * 32 < send; ++it) {
         const int w = it * 32 + lane;
         bool found = false;
         if (w < send) {
+            const uint8_t c = B[w];
+            int32_t id = BT.byte_sym[c];
+            if (id == kSymWalk) {
+                const int pe = next_bit(S.segbits, w, send);
+                int j = w;
+                id = trie_longest(BT.trie, B, j, pe);
+                if (id >= 0 && j != w + 1) complex = true;
+            }
+            if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
+            bp.ids[w] = id;
             uint32_t k = kNoKey;
-            if (w + 1 < send && !((S.segbits[(w + 1) >> 5] >> ((w + 1) & 31)) & 1u)) {
-                const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)S.B()[w] << 8) | S.B()[w + 1]));
+            if (w > 0 && !((S.segbits[w >> 5] >> (w & 31)) & 1u)) {
+                const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)B[w - 1] << 8) | c));
                 if (r != kNoKey) { found = true; k = (r << kPackedBirthBits) | (uint32_t)w; }
             }
             bp.key[w] = k;
@@ -409,7 +396,29 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, found);
         if (lane == 0) S.actbits[it] = m;
     }
-    __syncwarp();
+    return __any_sync(0xFFFFFFFFu, complex);
+}
+
+// Serial per-lane path for windows with multi-byte symbols / dropped bytes.
+__device__ __noinline__ void bpe_window_serial(WarpSmem& S, const BpeTables& BT, const RowParams& P, int lane, int ns, bool whole) {
+    auto& bp = S.u.bp;
+    for (int j = lane; j < ns; j += 32) {
+        const uint16_t sg = S.seg[j];
+        const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
+        int c = 0;
+        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
+            const int n = bpe_symbolize(BT, S.B(), s, e, bp.ids + s);
+            c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, n);
+        }
+        for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
+    }
+}
+
+// Merge phase: segments that own a mergeable pair enter a lane-level work queue; each lane performs one merge
+// step per iteration (argmin over the packed keys, lazy deletion of the right operand, two new lookups).
+__device__ __forceinline__ void bpe_merge_queue(WarpSmem& S, const BpeTables& BT, const RowParams& P, int lane, int ns, bool whole) {
+    auto& bp = S.u.bp;
+    const uint32_t lt = (1u << lane) - 1u;
     // segments that need merging -> S.act[]; dropped segments are erased; 2-symbol segments finish here
     int nact = 0;
     for (int j0 = 0; j0 < ns; j0 += 32) {
@@ -420,8 +429,8 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
             const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
             if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
                 for (int t = s; t < e; ++t) bp.ids[t] = -1;
-            } else if (e - s >= 2 && range_any(S.actbits, s, e - 1)) {
-                if (e - s == 2) { bp.ids[s] = __ldg(BT.merges.rank_newid + (bp.key[s] >> kPackedBirthBits)); bp.ids[s + 1] = -1; }
+            } else if (e - s >= 2 && range_any(S.actbits, s + 1, e)) {
+                if (e - s == 2) { bp.ids[s] = __ldg(BT.merges.rank_newid + (bp.key[s + 1] >> kPackedBirthBits)); bp.ids[s + 1] = -1; }
                 else act = true;
             }
         }
@@ -430,7 +439,6 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
         nact += __popc(m);
     }
     __syncwarp();
-    // lane-level work queue: one merge step per iteration
     int head = 0, s = 0, n0 = 0, merges = 0;
     bool have = false;
     for (;;) {
@@ -449,37 +457,105 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
         if (!__any_sync(0xFFFFFFFFu, have)) break;
         if (have) {
             uint32_t best = kNoKey;
-            int bk = -1;
-            for (int k = 0; k + 1 < n0; ++k) {
+            int bk = -1, live = 0;
+            for (int k = 1; k < n0; ++k) {
                 const uint32_t q = bp.key[s + k];
+                live += (q != kNoKey);
                 if (q < best) { best = q; bk = k; }
             }
             if (bk < 0) { have = false; continue; }
-            int t = bk + 1;
-            while (bp.ids[s + t] < 0) ++t;                    // right operand (skip dead slots)
-            const int32_t nid = __ldg(BT.merges.rank_newid + (best >> kPackedBirthBits));
-            bp.ids[s + bk] = nid;
-            bp.ids[s + t] = -1;
-            bp.key[s + t] = kNoKey;
-            ++merges;
-            const uint32_t birth = (uint32_t)(WIN + merges);    // after every initial birth (< WIN), increasing per merge
             int pl = bk - 1;
-            while (pl >= 0 && bp.ids[s + pl] < 0) --pl;
-            int nr = t + 1;
+            while (bp.ids[s + pl] < 0) --pl;                  // left operand (skip dead slots)
+            const int32_t nid = __ldg(BT.merges.rank_newid + (best >> kPackedBirthBits));
+            bp.ids[s + pl] = nid;
+            bp.ids[s + bk] = -1;
+            bp.key[s + bk] = kNoKey;
+            --live;
+            ++merges;
+            const uint32_t birth = (uint32_t)(WIN + merges);
+            int pp = pl - 1;
+            while (pp >= 0 && bp.ids[s + pp] < 0) --pp;
+            int nr = bk + 1;
             while (nr < n0 && bp.ids[s + nr] < 0) ++nr;
-            if (pl >= 0) {
+            if (pl > 0) {
+                live -= (bp.key[s + pl] != kNoKey);
+                uint32_t kk = kNoKey;
                 int32_t r, v;
-                const bool f = merge_find(BT.merges, bp.ids[s + pl], nid, r, v);
-                bp.key[s + pl] = f ? (((uint32_t)r << kPackedBirthBits) | birth) : kNoKey;
+                if (pp >= 0 && merge_find(BT.merges, bp.ids[s + pp], nid, r, v)) { kk = ((uint32_t)r << kPackedBirthBits) | birth; ++live; }
+                bp.key[s + pl] = kk;
             }
-            uint32_t kk = kNoKey;
             if (nr < n0) {
+                live -= (bp.key[s + nr] != kNoKey);
+                uint32_t kk = kNoKey;
                 int32_t r, v;
-                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) kk = ((uint32_t)r << kPackedBirthBits) | birth;
+                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) { kk = ((uint32_t)r << kPackedBirthBits) | birth; ++live; }
+                bp.key[s + nr] = kk;
             }
-            bp.key[s + bk] = kk;
+            if (live == 0) have = false;                      // nothing left to merge in this segment
         }
     }
+}
+
+__device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& BT, const RowParams& P, int lane,
+                                                  int ns, int send, bool whole, bool keys_ready, bool complex) {
+    if (!keys_ready) complex = bpe_symbolize_keys(S, BT, lane, send);
+    __syncwarp();
+    if (complex) bpe_window_serial(S, BT, P, lane, ns, whole);
+    else bpe_merge_queue(S, BT, P, lane, ns, whole);
+}
+
+// GPT-2 (isolate) split + symbolisation + initial keys in ONE position-parallel pass, for windows whose bytes are all
+// ASCII (classes come from the 128-entry table applied to the neighbouring bytes directly).  Returns the segment
+// count like split_window_gpt2; `complex` reports that the serial BPE path is needed.
+__device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint8_t* ascii_smem,
+                                                       int lane, int wlen, int end_rel, int nload, int lb, int& advance, bool& complex_out) {
+    auto& bp = S.u.bp;
+    const uint8_t* B = S.B();
+    const ClsAsciiLut K{B, ascii_smem};
+    const bool digits = P.spec.pat == PAT_GPT2_DIGITS;
+    bool complex = false;
+    int ns = 0;
+    for (int it = 0; it * 32 < wlen; ++it) {
+        const int w = it * 32 + lane;
+        bool st = false, found = false;
+        if (w < wlen) {
+            st = (w == 0) || gpt2_piece_starts_t(B, K, w, -lb, end_rel, digits);
+            const uint8_t c = B[w];
+            int32_t id = BT.byte_sym[c];
+            if (id < 0) {
+                if (id == kSymWalk) {           // a longer token may start here: if one does (even across a piece
+                    int j = w;                  // boundary), the exact piece-limited walk is left to the serial path
+                    id = trie_longest(BT.trie, B, j, nload);
+                    if (id >= 0 && j != w + 1) complex = true;
+                }
+                if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
+            }
+            bp.ids[w] = id;
+            uint32_t k = kNoKey;
+            if (!st) {
+                const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)B[w - 1] << 8) | c));
+                if (r != kNoKey) { found = true; k = (r << kPackedBirthBits) | (uint32_t)w; }
+            }
+            bp.key[w] = k;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
+        const uint32_t ma = __ballot_sync(0xFFFFFFFFu, found);
+        if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(w | F_MATCH);
+        if (lane == 0) { S.segbits[it] = m; S.actbits[it] = ma; }
+        ns += __popc(m);
+    }
+    for (int it = (wlen + 31) / 32 + lane; it < NWORDS; it += 32) S.segbits[it] = 0;
+    complex_out = __any_sync(0xFFFFFFFFu, complex);
+    __syncwarp();
+    if (wlen == end_rel) {
+        advance = wlen;
+        if (lane == 0) S.seg[ns] = (uint16_t)wlen;
+    } else {
+        --ns;
+        advance = S.seg[ns] & POS_MASK;
+    }
+    __syncwarp();
+    return ns;
 }
 
 // WordPiece for all kept segments (words) of a window: one lane per word, longest-match trie walks.
@@ -565,11 +641,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                 const int end_rel = ee - pos;
                 const int wlen = end_rel < WIN ? end_rel : WIN;
                 int ns = 0, advance = 0;
+                bool keys_ready = false, complex_win = false;
                 const bool fits = !(whole && end_rel > WIN) && !(OP == OP_BPE && P.suffix_len > 0);
                 if (fits) {
                     const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
                     const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
-                    for (int w = lane - lb; w < nload + 4; w += 32) S.B()[w] = (w < nload) ? __ldg(P.chars + pos + w) : 0;
+                    uint32_t hibits = 0;
+                    for (int w = lane - lb; w < nload + 4; w += 32) {
+                        const uint8_t bb = (w < nload) ? __ldg(P.chars + pos + w) : 0;
+                        S.B()[w] = bb;
+                        hibits |= bb;
+                    }
+                    const bool all_ascii = !__any_sync(0xFFFFFFFFu, hibits & 0x80u);
                     __syncwarp();
                     if (whole) {
                         if (lane == 0) { S.seg[0] = F_MATCH; S.seg[1] = (uint16_t)wlen; }
@@ -577,9 +660,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                         ns = 1; advance = wlen;
                         __syncwarp();
                     } else {
-                        if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1)
-                            ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
-                        else
+                        if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1) {
+                            if (OP == OP_BPE && all_ascii) {
+                                ns = gpt2_ascii_fused_window(S, BT, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance, complex_win);
+                                keys_ready = true;
+                            } else
+                                ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
+                        } else
                             ns = split_window(S, P, ascii_smem, lane, wlen, end_rel, nload, advance);
                     }
                 }
@@ -662,7 +749,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                 } else {
                     // piece phase: every kept segment becomes tokens in S.u.bp.ids[start..], dead slots = -1
                     const int send = S.seg[ns] & POS_MASK;
-                    if (OP == OP_BPE) bpe_window_pieces(S, BT, P, lane, ns, send, whole);
+                    if (OP == OP_BPE) bpe_window_pieces(S, BT, P, lane, ns, send, whole, keys_ready, complex_win);
                     else wordpiece_window_pieces(S, P, lane, ns, whole);
                     __syncwarp();
                     // output phase: position-parallel compaction of the live tokens into the row slot

@@ -322,9 +322,14 @@ B2_HD Match match_at(const C& c, const SplitSpec& spec, int p, int end) {
 //     ("'" reached as the start of a match, i.e. not preceded by an "other" character or by U+0020)
 //     takes its one or two letters out of the following letter run.
 // ------------------------------------------------------------------------------------------
-B2_HD bool gpt2_apostrophe_starts_match(const uint8_t* b, const uint8_t* k, int q, int eb) {
+// class accessors: per-byte class array, or (ASCII-only subjects) the 128-entry table applied to the byte itself
+struct ClsArray { const uint8_t* k; B2_HD uint8_t operator()(int i) const { return k[i]; } };
+struct ClsAsciiLut { const uint8_t* b; const uint8_t* lut; B2_HD uint8_t operator()(int i) const { return lut[b[i]]; } };
+
+template <class KF>
+B2_HD bool gpt2_apostrophe_t(const uint8_t* b, const KF& K, int q, int eb) {
     if (q == eb) return true;
-    const uint8_t p = k[q - 1];
+    const uint8_t p = K(q - 1);
     if (p & (C_L | C_N)) return true;
     if (p & C_S) return b[q - 1] != 0x20;
     return false;
@@ -340,30 +345,34 @@ B2_HD int gpt2_contraction_len(const uint8_t* b, int q, int ee) {
     }
     return 0;
 }
-B2_HD bool gpt2_piece_starts_at(const uint8_t* b, const uint8_t* k, int i, int eb, int ee, bool single_digits) {
-    const uint8_t c = k[i];
+template <class KF>
+B2_HD bool gpt2_piece_starts_t(const uint8_t* b, const KF& K, int i, int eb, int ee, bool single_digits) {
+    const uint8_t c = K(i);
     if (c & C_CONT) return false;
     if (i == eb) return true;
-    const uint8_t p = k[i - 1];
+    const uint8_t p = K(i - 1);
     if (c & C_S) {
         if (!(p & C_S)) return true;
         int j = i + 1;
-        while (j < ee && (k[j] & C_CONT)) ++j;
-        return j < ee && !(k[j] & C_S);
+        while (j < ee && (K(j) & C_CONT)) ++j;
+        return j < ee && !(K(j) & C_S);
     }
     if (single_digits && (c & C_N)) return true;
     if (b[i - 1] == 0x20) return false;
     if (c & C_N) return !(p & C_N);
     if (!(c & C_L)) return (p & (C_L | C_N | C_S)) != 0;          // "other": starts unless it continues an other-run
     bool inside = false, ends_here = false;
-    if (b[i - 1] == '\'' && gpt2_apostrophe_starts_match(b, k, i - 1, eb) && gpt2_contraction_len(b, i - 1, ee) >= 2) inside = true;
-    if (i - 2 >= eb && b[i - 2] == '\'' && gpt2_apostrophe_starts_match(b, k, i - 2, eb)) {
+    if (b[i - 1] == '\'' && gpt2_apostrophe_t(b, K, i - 1, eb) && gpt2_contraction_len(b, i - 1, ee) >= 2) inside = true;
+    if (i - 2 >= eb && b[i - 2] == '\'' && gpt2_apostrophe_t(b, K, i - 2, eb)) {
         const int cl = gpt2_contraction_len(b, i - 2, ee);
         if (cl == 3) inside = true;
         else if (cl == 2) ends_here = true;
     }
-    if (i - 3 >= eb && b[i - 3] == '\'' && gpt2_apostrophe_starts_match(b, k, i - 3, eb) && gpt2_contraction_len(b, i - 3, ee) == 3) ends_here = true;
+    if (i - 3 >= eb && b[i - 3] == '\'' && gpt2_apostrophe_t(b, K, i - 3, eb) && gpt2_contraction_len(b, i - 3, ee) == 3) ends_here = true;
     return !inside && (ends_here || !(p & C_L));
+}
+B2_HD bool gpt2_piece_starts_at(const uint8_t* b, const uint8_t* k, int i, int eb, int ee, bool single_digits) {
+    return gpt2_piece_starts_t(b, ClsArray{k}, i, eb, ee, single_digits);
 }
 
 // (p)+ for the "contiguous" rewrite (src/regex_split.cpp:33-37): greedy repetition of the pattern.
