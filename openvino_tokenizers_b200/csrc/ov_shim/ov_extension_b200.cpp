@@ -1,0 +1,332 @@
+// ov_extension_b200.cpp — the host side that stays C++ inside OpenVINO: registers the SAME op names, attributes and
+// input/output signatures as the reference extension (src/ov_extension.cpp:72-109) so a converted tokenizer IR loads
+// unchanged, and forwards each evaluate() to the C ABI of libb200tok.so (include/b200tok.h).
+//
+// Built only when OpenVINO is available:  g++ -shared -fPIC -DIMPLEMENT_OPENVINO_EXTENSION_API ov_extension_b200.cpp
+//   -I<openvino>/include -I../../../include -L.. -lb200tok -lopenvino  (see INTEGRATION.md).
+// OpenVINO headers/libraries do not exist in the build container, so this file is NOT compiled or
+// tested there; every behaviour it relies on is exercised through the C ABI by tests/test_gpu_parity.py, and the Python
+// mirror openvino_tokenizers_b200/ops.py follows the same marshalling line by line.
+#if __has_include(<openvino/op/op.hpp>)
+#include <openvino/core/extension.hpp>
+#include <openvino/core/op_extension.hpp>
+#include <openvino/op/constant.hpp>
+#include <openvino/op/op.hpp>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b200tok.h"
+
+namespace b200 {
+
+inline void check(int rc) { OPENVINO_ASSERT(rc == B200TOK_OK, "b200tok: ", b200tok_last_error()); }
+
+inline b200tok_strings strings_of(const ov::TensorVector& in, size_t i) {
+    return b200tok_strings{in[i].data<const int32_t>(), in[i + 1].data<const int32_t>(), in[i + 2].data<const uint8_t>(),
+                           (int64_t)in[i].get_size(), (int64_t)in[i + 2].get_size()};
+}
+inline b200tok_ragged_strings ragged_of(const ov::TensorVector& in, const uint8_t* skips = nullptr) {
+    return b200tok_ragged_strings{in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(),
+                                  in[2].data<const int32_t>(), in[3].data<const int32_t>(), (int64_t)in[2].get_size(),
+                                  in[4].data<const uint8_t>(), (int64_t)in[4].get_size(), skips, B200TOK_MEM_HOST};
+}
+inline void ragged_ids_out(ov::TensorVector& out, const ov::TensorVector& in, int64_t capacity,
+                           const std::function<int(b200tok_ragged_ids*)>& run) {
+    out[0].set_shape(in[0].get_shape());
+    out[1].set_shape(in[1].get_shape());
+    out[2].set_shape({(size_t)capacity});                       // worst case first (src/bpe_tokenizer.cpp:135)
+    b200tok_ragged_ids r{out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<int32_t>(), capacity, 0, nullptr, B200TOK_MEM_HOST};
+    check(run(&r));
+    out[2].set_shape({(size_t)r.n_ids});                        // then the real size (src/bpe_tokenizer.cpp:162)
+}
+
+struct Handle {   // shared by clones, like the reference's shared_ptr<BPETokenizerImpl> (src/bpe_tokenizer.hpp:215-218)
+    b200tok_handle h = nullptr;
+    std::once_flag once;
+    ~Handle() { b200tok_destroy(h); }
+};
+
+// ---- RegexSplit (src/regex_split.hpp:15-73) ---------------------------------------------------------------------
+class RegexSplit : public ov::op::Op {
+public:
+    OPENVINO_OP("RegexSplit");
+    RegexSplit() = default;
+    RegexSplit(const ov::OutputVector& args, const std::string& behaviour = "remove", bool invert = false, int max_splits = -1)
+        : ov::op::Op(args), m_behaviour(behaviour), m_invert(invert), m_max_splits(max_splits) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto n = get_input_size();
+        OPENVINO_ASSERT(n == 6 || n == 7, "Incorrect number of inputs passed to RegexSplit: ", n,
+                        " (the legacy 9-input skip-token form is not supported by the B200 path)");
+        for (size_t i = 0; i < 4; ++i) set_output_type(i, ov::element::i32, i < 2 ? get_input_partial_shape(0) : ov::PartialShape{ov::Dimension()});
+        set_output_type(4, ov::element::u8, ov::PartialShape{ov::Dimension()});
+        if (n == 7) set_output_type(5, get_input_element_type(5), get_input_partial_shape(5));
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<RegexSplit>(in, m_behaviour, m_invert, m_max_splits);
+        c->m_state = m_state;
+        return c;
+    }
+    bool visit_attributes(ov::AttributeVisitor& v) override {
+        v.on_attribute("behaviour", m_behaviour);
+        v.on_attribute("invert", m_invert);
+        v.on_attribute("max_splits", m_max_splits);
+        return true;
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const bool has_skips = in.size() == 7;
+        std::call_once(m_state->once, [&] {
+            const auto& p = in[5 + has_skips];
+            b200tok_regexsplit_desc d{p.data<const char>(), (int64_t)p.get_size(), m_behaviour.c_str(), m_invert, m_max_splits, 0};
+            check(b200tok_regexsplit_create(&d, &m_state->h));
+        });
+        const size_t cap = in[4].get_size() + in[2].get_size();          // src/regex_split.cpp:182
+        out[0].set_shape(in[0].get_shape());
+        out[1].set_shape(in[1].get_shape());
+        out[2].set_shape({cap});
+        out[3].set_shape({cap});
+        out[4] = in[4];                                                   // chars are aliased (src/regex_split.cpp:203)
+        if (has_skips) out[5].set_shape({cap});
+        auto rin = ragged_of(in, has_skips ? reinterpret_cast<const uint8_t*>(in[5].data<bool>()) : nullptr);
+        b200tok_ragged_strings_out r{out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<int32_t>(), out[3].data<int32_t>(),
+                                     has_skips ? reinterpret_cast<uint8_t*>(out[5].data<bool>()) : nullptr, (int64_t)cap, 0, 0, B200TOK_MEM_HOST};
+        check(b200tok_regexsplit_run(m_state->h, &rin, &r, nullptr));
+        if ((size_t)r.n_rows != in[0].get_size()) { out[0].set_shape({(size_t)r.n_rows}); out[1].set_shape({(size_t)r.n_rows}); }  // :129-143
+        out[2].set_shape({(size_t)r.n_elems});
+        out[3].set_shape({(size_t)r.n_elems});
+        if (has_skips) out[5].set_shape({(size_t)r.n_elems});
+        return true;
+    }
+private:
+    std::string m_behaviour = "remove";
+    bool m_invert = false;
+    int m_max_splits = -1;
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+// ---- BPETokenizer (src/bpe_tokenizer.hpp:168-246) ---------------------------------------------------------------
+class BPETokenizer : public ov::op::Op {
+public:
+    OPENVINO_OP("BPETokenizer");
+    BPETokenizer() = default;
+    BPETokenizer(const ov::OutputVector& args, const std::string& unk_token = "", bool fuse_unk = false,
+                 const std::string& suffix_indicator = "", const std::string& end_suffix = "", bool byte_fallback = false,
+                 size_t cache_capacity = 20000)
+        : ov::op::Op(args), m_unk_token(unk_token), m_fuse_unk(fuse_unk), m_suffix_indicator(suffix_indicator),
+          m_end_suffix(end_suffix), m_byte_fallback(byte_fallback), m_cache_capacity(cache_capacity) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto n = get_input_size();
+        OPENVINO_ASSERT(n == 11 || n == 14 || n == 15 || n == 18,
+                        "Incorrect number of inputs passed to BPETokenizer, try to reconvert tokenizer with newer version of OpenVINO Tokenizers");
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::i32, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<BPETokenizer>(in, m_unk_token, m_fuse_unk, m_suffix_indicator, m_end_suffix, m_byte_fallback, m_cache_capacity);
+        c->m_state = m_state;
+        return c;
+    }
+    bool visit_attributes(ov::AttributeVisitor& v) override {
+        v.on_attribute("unk_token", m_unk_token);
+        v.on_attribute("fuse_unk", m_fuse_unk);
+        v.on_attribute("suffix_indicator", m_suffix_indicator);
+        v.on_attribute("end_suffix", m_end_suffix);
+        v.on_attribute("byte_fallback", m_byte_fallback);
+        v.on_attribute("cache_capacity", m_cache_capacity);
+        return true;
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const auto n = in.size();
+        std::call_once(m_state->once, [&] {                              // src/bpe_tokenizer.cpp:50-120
+            b200tok_bpe_desc d{};
+            d.vocab = strings_of(in, 5);
+            d.merges_left = strings_of(in, 8);
+            if (n == 14 || n == 18) d.merges_right = strings_of(in, 11);
+            if (n == 15 || n == 18) { d.added_tokens = strings_of(in, n - 4); d.added_ids = in[n - 1].data<const int32_t>(); }
+            d.unk_token = m_unk_token.data(); d.unk_token_len = (int64_t)m_unk_token.size();
+            d.suffix_indicator = m_suffix_indicator.data(); d.suffix_indicator_len = (int64_t)m_suffix_indicator.size();
+            d.end_suffix = m_end_suffix.data(); d.end_suffix_len = (int64_t)m_end_suffix.size();
+            d.fuse_unk = m_fuse_unk; d.byte_fallback = m_byte_fallback; d.cache_capacity = (int64_t)m_cache_capacity; d.device = 0;
+            check(b200tok_bpe_create(&d, &m_state->h));
+        });
+        auto rin = ragged_of(in);
+        ragged_ids_out(out, in, (int64_t)(in[4].get_size() + in[2].get_size() * m_end_suffix.size()),
+                       [&](b200tok_ragged_ids* r) { return b200tok_bpe_run(m_state->h, &rin, r, nullptr); });
+        return true;
+    }
+private:
+    std::string m_unk_token, m_suffix_indicator, m_end_suffix;
+    bool m_fuse_unk = false, m_byte_fallback = false;
+    size_t m_cache_capacity = 20000;
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+// ---- WordpieceTokenizer (src/wordpiece_tokenizer.hpp:15-59) -------------------------------------------------------
+class WordpieceTokenizer : public ov::op::Op {
+public:
+    OPENVINO_OP("WordpieceTokenizer");
+    WordpieceTokenizer() = default;
+    WordpieceTokenizer(const ov::OutputVector& args, const std::string& suffix_indicator = "##", int max_bytes_per_word = 100)
+        : ov::op::Op(args), m_suffix_indicator(suffix_indicator), m_max_bytes_per_word(max_bytes_per_word) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::i32, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<WordpieceTokenizer>(in, m_suffix_indicator, m_max_bytes_per_word);
+        c->m_state = m_state;
+        return c;
+    }
+    bool visit_attributes(ov::AttributeVisitor& v) override {
+        v.on_attribute("suffix_indicator", m_suffix_indicator);
+        v.on_attribute("max_bytes_per_word", m_max_bytes_per_word);
+        return true;
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        std::call_once(m_state->once, [&] {
+            b200tok_wordpiece_desc d{strings_of(in, 5), m_suffix_indicator.data(), (int64_t)m_suffix_indicator.size(), m_max_bytes_per_word, 0};
+            check(b200tok_wordpiece_create(&d, &m_state->h));
+        });
+        const int32_t unk = *in[8].data<const int32_t>();
+        auto rin = ragged_of(in);
+        ragged_ids_out(out, in, (int64_t)(in[4].get_size() + in[2].get_size()),
+                       [&](b200tok_ragged_ids* r) { return b200tok_wordpiece_run(m_state->h, &rin, unk, r, nullptr); });
+        return true;
+    }
+private:
+    std::string m_suffix_indicator = "##";
+    int m_max_bytes_per_word = 100;
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+// ---- VocabEncoder (src/vocab_encoder.hpp) / VocabDecoder (src/vocab_decoder.hpp) / ByteFallback (src/byte_fallback.hpp)
+class VocabEncoder : public ov::op::Op {
+public:
+    OPENVINO_OP("VocabEncoder");
+    VocabEncoder() = default;
+    explicit VocabEncoder(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override { set_output_type(0, get_input_element_type(6), get_input_partial_shape(0)); }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<VocabEncoder>(in);
+        c->m_state = m_state;
+        return c;
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const bool i64 = in[6].get_element_type() == ov::element::i64;
+        OPENVINO_ASSERT(i64 || in[6].get_element_type() == ov::element::i32, "VocabEncoder: unsupported element type: ", in[6].get_element_type());
+        std::call_once(m_state->once, [&] {
+            b200tok_vocabenc_desc d{strings_of(in, 3), in[6].data(), i64, 0};
+            check(b200tok_vocabenc_create(&d, &m_state->h));
+        });
+        out[0].set_shape({in[0].get_size()});
+        const int64_t def = i64 ? *in[7].data<const int64_t>() : (int64_t)*in[7].data<const int32_t>();
+        check(b200tok_vocabenc_run(m_state->h, in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(),
+                                   in[2].data<const uint8_t>(), (int64_t)in[2].get_size(), def, out[0].data(), B200TOK_MEM_HOST, nullptr));
+        return true;
+    }
+private:
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+class VocabDecoder : public ov::op::Op {
+public:
+    OPENVINO_OP("VocabDecoder");
+    VocabDecoder() = default;
+    VocabDecoder(const ov::OutputVector& args, std::vector<int> skip_tokens = {}) : ov::op::Op(args), m_skip_tokens(std::move(skip_tokens)) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto shape = get_input_partial_shape(0);
+        set_output_type(0, ov::element::i32, {shape[0]});
+        set_output_type(1, ov::element::i32, {shape[0]});
+        set_output_type(2, ov::element::i32, ov::PartialShape{ov::Dimension()});
+        set_output_type(3, ov::element::i32, ov::PartialShape{ov::Dimension()});
+        set_output_type(4, ov::element::u8, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<VocabDecoder>(in, m_skip_tokens);
+        c->m_state = m_state;
+        return c;
+    }
+    bool visit_attributes(ov::AttributeVisitor& v) override { v.on_attribute("skip_tokens", m_skip_tokens); return true; }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        OPENVINO_ASSERT(in.size() == 4 || in.size() == 5, "Too few inputs passed to VocabDecoder, it means it is not converted properly or it is not used in the supported pattern");
+        std::call_once(m_state->once, [&] {
+            b200tok_vocabdec_desc d{strings_of(in, 1), 0};
+            check(b200tok_vocabdec_create(&d, &m_state->h));
+        });
+        const int64_t B = (int64_t)in[0].get_shape()[0], S = (int64_t)in[0].get_shape()[1], W = S > 0 ? S : 1;
+        const int32_t* skip = in.size() == 5 ? in[4].data<const int32_t>() : m_skip_tokens.data();
+        const int64_t n_skip = in.size() == 5 ? (int64_t)in[4].get_shape()[0] : (int64_t)m_skip_tokens.size();
+        const int64_t cap = std::max<int64_t>(b200tok_vocabdec_max_chars(m_state->h, B, S), 1);
+        out[0].set_shape({(size_t)B}); out[1].set_shape({(size_t)B});
+        out[2].set_shape({(size_t)(B * W)}); out[3].set_shape({(size_t)(B * W)});
+        out[4].set_shape({(size_t)cap});
+        b200tok_decoded r{out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<int32_t>(), out[3].data<int32_t>(),
+                          out[4].data<uint8_t>(), cap, 0, B200TOK_MEM_HOST};
+        check(b200tok_vocabdec_run(m_state->h, in[0].data<const int32_t>(), B, S, skip, n_skip, /*byte_fallback=*/0, &r, B200TOK_MEM_HOST, nullptr));
+        out[4].set_shape({(size_t)r.n_chars});
+        return true;
+    }
+private:
+    std::vector<int> m_skip_tokens;
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+class ByteFallback : public ov::op::Op {
+public:
+    OPENVINO_OP("ByteFallback");
+    ByteFallback() = default;
+    explicit ByteFallback(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::u8, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<ByteFallback>(in); }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        out[0].set_shape(in[0].get_shape()); out[1].set_shape(in[1].get_shape()); out[2].set_shape({in[2].get_size()});
+        int64_t n_chars = 0;
+        check(b200tok_bytefallback_run(0, in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(),
+                                       in[2].data<const uint8_t>(), (int64_t)in[2].get_size(), out[0].data<int32_t>(), out[1].data<int32_t>(),
+                                       out[2].data<uint8_t>(), &n_chars, B200TOK_MEM_HOST, nullptr));
+        out[2].set_shape({(size_t)n_chars});
+        return true;
+    }
+};
+
+}  // namespace b200
+
+// Same registration entry point as the reference (src/ov_extension.cpp:72); only the hot-path ops are provided here —
+// load the reference extension as well for the remaining 27 ops, ours registered last so that these six names resolve here.
+OPENVINO_CREATE_EXTENSIONS(std::vector<ov::Extension::Ptr>({
+    std::make_shared<ov::OpExtension<b200::RegexSplit>>(),
+    std::make_shared<ov::OpExtension<b200::BPETokenizer>>(),
+    std::make_shared<ov::OpExtension<b200::WordpieceTokenizer>>(),
+    std::make_shared<ov::OpExtension<b200::VocabEncoder>>(),
+    std::make_shared<ov::OpExtension<b200::VocabDecoder>>(),
+    std::make_shared<ov::OpExtension<b200::ByteFallback>>(),
+}));
+
+// GenAI's GGUF path dlsym()s this factory (src/tokenizers_factory.hpp:32-33); the signature is frozen.
+namespace ov { namespace tokenizers {
+OPENVINO_API_C(ov::OutputVector)
+create_tokenizer_node(const std::string& op_type, const ov::OutputVector& inputs, const ov::AnyMap& attributes) {
+    auto get = [&](const char* k, auto def) { auto it = attributes.find(k); return it == attributes.end() ? def : it->second.as<decltype(def)>(); };
+    if (op_type == "RegexSplit") return std::make_shared<b200::RegexSplit>(inputs, get("behaviour", std::string("remove")), get("invert", false), get("max_splits", -1))->outputs();
+    if (op_type == "BPETokenizer") return std::make_shared<b200::BPETokenizer>(inputs, get("unk_token", std::string()), get("fuse_unk", false), get("suffix_indicator", std::string()), get("end_suffix", std::string()), get("byte_fallback", false))->outputs();
+    if (op_type == "WordpieceTokenizer") return std::make_shared<b200::WordpieceTokenizer>(inputs, get("suffix_indicator", std::string("##")), get("max_bytes_per_word", 100))->outputs();
+    if (op_type == "VocabEncoder") return std::make_shared<b200::VocabEncoder>(inputs)->outputs();
+    if (op_type == "VocabDecoder") return std::make_shared<b200::VocabDecoder>(inputs, get("skip_tokens", std::vector<int>{}))->outputs();
+    if (op_type == "ByteFallback") return std::make_shared<b200::ByteFallback>(inputs)->outputs();
+    OPENVINO_THROW("Unsupported operation type in the B200 hot-path extension: ", op_type);
+}
+}}  // namespace ov::tokenizers
+#endif  // __has_include(<openvino/op/op.hpp>)
