@@ -647,12 +647,29 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                     const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
                     const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
                     uint32_t hibits = 0;
-                    for (int w = lane - lb; w < nload + 4; w += 32) {
-                        const uint8_t bb = (w < nload) ? __ldg(P.chars + pos + w) : 0;
-                        S.B()[w] = bb;
-                        hibits |= bb;
+                    const uint8_t* src = P.chars + pos - lb;
+                    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
+                        // 16-byte vector loads (rows of the benchmark configs start on 16-byte boundaries); the last
+                        // quad may read up to 15 bytes past the element — inside the padded chars allocation
+                        uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
+                        const int nq = (lb + nload + 15) >> 4;
+                        for (int q = lane; q < nq; q += 32) {
+                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                            dst[q] = v;
+                            if ((q << 4) + 16 <= lb + nload) hibits |= v.x | v.y | v.z | v.w;
+                            else {
+                                const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+                                for (int t = 0; t < 16; ++t) if ((q << 4) + t < lb + nload) hibits |= (ww[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
+                            }
+                        }
+                    } else {
+                        for (int w = lane - lb; w < nload; w += 32) {
+                            const uint8_t bb = __ldg(P.chars + pos + w);
+                            S.B()[w] = bb;
+                            hibits |= bb;
+                        }
                     }
-                    const bool all_ascii = !__any_sync(0xFFFFFFFFu, hibits & 0x80u);
+                    const bool all_ascii = !__any_sync(0xFFFFFFFFu, hibits & 0x80808080u);
                     __syncwarp();
                     if (whole) {
                         if (lane == 0) { S.seg[0] = F_MATCH; S.seg[1] = (uint16_t)wlen; }
