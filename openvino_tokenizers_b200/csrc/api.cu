@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -268,6 +269,7 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
             return fail(B200TOK_E_UNSUPPORTED, "fused split+tokenize supports remove/isolate behaviours without max_splits; run the two ops separately");
     }
     P.cls = owner->cls.view();
+    { static const int dbg = [] { const char* e = getenv("B200TOK_DEBUG_FLAGS"); return e ? atoi(e) : 0; }(); P.dbg_flags = dbg; }
     int per_elem_extra = 1;
     if (call.op == OP_BPE) {
         P.bpe = call.bpe->view();
@@ -308,7 +310,7 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     }
     if (!d_ob || !d_oe || (!d_oa && out_cap > 0)) return fail(B200TOK_E_INVALID, "missing output buffers");
 
-    const size_t smem = 128 + 1024 + WARPS_PER_BLOCK * sizeof(WarpSmem);
+    const size_t smem = 128 + 1024 + 256 + WARPS_PER_BLOCK * sizeof(WarpSmem);
     const int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
     static bool attr_set[3][64] = {};
     const int nthreads = 256;

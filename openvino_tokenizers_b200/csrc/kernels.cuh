@@ -58,6 +58,7 @@ struct RowParams {
     // giants
     GiantItem* giants; int32_t giants_cap;
     int32_t* status;
+    int32_t dbg_flags;         // development switches (env B200TOK_DEBUG_FLAGS), 0 in production
 };
 
 struct __align__(16) WarpSmem {
@@ -505,22 +506,37 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
 }
 
 // GPT-2 (isolate) split + symbolisation + initial keys in ONE position-parallel pass, for windows whose bytes are all
-// ASCII (classes come from the 128-entry table applied to the neighbouring bytes directly).  Returns the segment
-// count like split_window_gpt2; `complex` reports that the serial BPE path is needed.
-__device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint8_t* ascii_smem,
-                                                       int lane, int wlen, int end_rel, int nload, int lb, int& advance, bool& complex_out) {
+// ASCII.  The piece-start predicate is the branch-free neighbour form (tok_core.cuh gpt2_start_nb) over 11-bit class
+// words read from a 128-entry shared-memory table; the contraction logic is skipped warp-wide when no apostrophe is
+// near.  Returns the segment count like split_window_gpt2; `complex` reports that the serial BPE path is needed.
+__device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint16_t* glut, const uint8_t* ascii_lut,
+                                                       int lane, int wlen, int end_rel, int nload, int lb, bool bos,
+                                                       int& advance, bool& complex_out) {
     auto& bp = S.u.bp;
     const uint8_t* B = S.B();
-    const ClsAsciiLut K{B, ascii_smem};
     const bool digits = P.spec.pat == PAT_GPT2_DIGITS;
+    auto word = [&](int i) -> uint32_t {      // class word of position i (0 = does not exist)
+        if (i >= nload) return 0u;
+        if (i >= -lb) return glut[B[i]];
+        return (bos && i == -lb - 1) ? (uint32_t)G_BOS : 0u;
+    };
     bool complex = false;
     int ns = 0;
+    uint32_t ap_prev = __ballot_sync(0xFFFFFFFFu, word(lane - 32) & G_AP);
     for (int it = 0; it * 32 < wlen; ++it) {
         const int w = it * 32 + lane;
+        const uint32_t cw = word(w);
+        const uint32_t ap = __ballot_sync(0xFFFFFFFFu, cw & G_AP);
+        const bool apos_near = ((ap & 0x7FFFFFFFu) | (ap_prev >> 29)) != 0;     // warp-uniform
+        ap_prev = ap;
         bool st = false, found = false;
         if (w < wlen) {
-            st = (w == 0) || gpt2_piece_starts_t(B, K, w, -lb, end_rel, digits);
             const uint8_t c = B[w];
+            const uint32_t p1 = word(w - 1), n1 = word(w + 1);
+            uint32_t p2 = 0, p3 = 0, p4 = 0;
+            if (apos_near) { p2 = word(w - 2); p3 = word(w - 3); p4 = word(w - 4); }
+            if (P.dbg_flags & 1) st = (w == 0) || gpt2_piece_starts_t(B, ClsAsciiLut{B, ascii_lut}, w, -lb, end_rel, digits);
+            else st = (w == 0) || gpt2_start_nb(cw, p1, p2, p3, p4, n1, digits, apos_near);
             int32_t id = BT.byte_sym[c];
             if (id < 0) {
                 if (id == kSymWalk) {           // a longer token may start here: if one does (even across a piece
@@ -592,10 +608,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                   // [128]
     int32_t* bytesym_smem = reinterpret_cast<int32_t*>(smem_raw + 128);   // [256]
-    WarpSmem* warps = reinterpret_cast<WarpSmem*>(smem_raw + 128 + 1024);
+    uint16_t* glut_smem = reinterpret_cast<uint16_t*>(smem_raw + 128 + 1024);  // [128] GPT-2 class words
+    WarpSmem* warps = reinterpret_cast<WarpSmem*>(smem_raw + 128 + 1024 + 256);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem& S = warps[wib];
-    if (threadIdx.x < 128) ascii_smem[threadIdx.x] = P.cls.ascii[threadIdx.x];
+    if (threadIdx.x < 128) {
+        const uint8_t k = P.cls.ascii[threadIdx.x];
+        ascii_smem[threadIdx.x] = k;
+        glut_smem[threadIdx.x] = (uint16_t)gpt2_class_word((uint8_t)threadIdx.x, k);
+    }
     if (OP == OP_BPE) bytesym_smem[threadIdx.x] = P.bpe.byte_sym[threadIdx.x];
     __syncthreads();
     BpeTables BT = P.bpe;
@@ -679,7 +700,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                     } else {
                         if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1) {
                             if (OP == OP_BPE && all_ascii) {
-                                ns = gpt2_ascii_fused_window(S, BT, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance, complex_win);
+                                ns = gpt2_ascii_fused_window(S, BT, P, glut_smem, ascii_smem, lane, wlen, end_rel, nload, lb, (pos - eb) == lb, advance, complex_win);
                                 keys_ready = true;
                             } else
                                 ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);

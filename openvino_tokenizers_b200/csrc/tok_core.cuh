@@ -375,6 +375,42 @@ B2_HD bool gpt2_piece_starts_at(const uint8_t* b, const uint8_t* k, int i, int e
     return gpt2_piece_starts_t(b, ClsArray{k}, i, eb, ee, single_digits);
 }
 
+// Branch-free form of the same predicate for all-ASCII subjects, driven by the class words of the five neighbours
+// (the window kernel obtains them with warp shuffles).  Class word bits: G_L / G_N / G_S as above, G_SP = U+0020,
+// G_AP = apostrophe, G_ES = one of s t m d, G_ERV = r or v, G_EE = e, G_EL = l, G_X = "this position exists",
+// G_BOS = the virtual position just before the element start.  A missing neighbour has word 0.
+enum : uint32_t { G_L = 1, G_N = 2, G_S = 4, G_SP = 8, G_AP = 16, G_ES = 32, G_ERV = 64, G_EE = 128, G_EL = 256, G_BOS = 512, G_X = 1024 };
+B2_HD uint32_t gpt2_class_word(uint8_t byte, uint8_t cls) {
+    uint32_t w = G_X | (cls & (C_L | C_N | C_S));
+    if (byte == 0x20) w |= G_SP;
+    if (byte == '\'') w |= G_AP;
+    if (byte == 's' || byte == 't' || byte == 'm' || byte == 'd') w |= G_ES;
+    if (byte == 'r' || byte == 'v') w |= G_ERV;
+    if (byte == 'e') w |= G_EE;
+    if (byte == 'l') w |= G_EL;
+    return w;
+}
+B2_HD bool gpt2_nb_okprev(uint32_t x) { return (x & (G_L | G_N | G_BOS)) || ((x & G_S) && !(x & G_SP)); }
+B2_HD bool gpt2_nb_len3(uint32_t a, uint32_t b) { return !(a & G_ES) && (((a & G_ERV) && (b & G_EE)) || ((a & G_EL) && (b & G_EL))); }
+// `apos_near` = an apostrophe exists among p1..p3 (lets the caller skip fetching p2..p4 when false).
+B2_HD bool gpt2_start_nb(uint32_t c, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, uint32_t n1, bool digits, bool apos_near) {
+    const bool prev_sp = (p1 & G_SP) != 0;
+    const bool s_start = !(p1 & G_S) || ((n1 & G_X) && !(n1 & G_S));
+    const bool n_start = digits || (!prev_sp && !(p1 & G_N));
+    const bool o_start = !prev_sp && (p1 & (G_L | G_N | G_S));
+    bool inside = false, ends = false;
+    if (apos_near) {
+        const bool d1 = (p1 & G_AP) && gpt2_nb_okprev(p2);
+        const bool d2 = (p2 & G_AP) && gpt2_nb_okprev(p3);
+        const bool d3 = (p3 & G_AP) && gpt2_nb_okprev(p4);
+        inside = (d1 && ((c & G_ES) || gpt2_nb_len3(c, n1))) || (d2 && gpt2_nb_len3(p1, c));
+        ends = (d2 && (p1 & G_ES)) || (d3 && gpt2_nb_len3(p2, p1));
+    }
+    const bool l_start = !prev_sp && !inside && (ends || !(p1 & G_L));
+    const bool r = (c & G_S) ? s_start : (c & G_N) ? n_start : (c & G_L) ? l_start : o_start;
+    return r || (p1 & G_BOS);
+}
+
 // (p)+ for the "contiguous" rewrite (src/regex_split.cpp:33-37): greedy repetition of the pattern.
 template <class C>
 B2_HD Match match_rep(const C& c, const SplitSpec& spec, bool repeat, int p, int end) {

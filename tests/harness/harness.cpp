@@ -115,3 +115,20 @@ HZ int64_t hz_gpt2_closed_form(const uint8_t* s, int64_t n, int single_digits, i
         if (gpt2_piece_starts_at(s, k.data(), i, 0, end, single_digits != 0)) out_begins[cnt++] = i;
     return cnt;
 }
+
+// The shuffle-driven neighbour form (gpt2_start_nb), evaluated sequentially over an all-ASCII element.
+HZ int64_t hz_gpt2_neighbour_form(const uint8_t* s, int64_t n, int single_digits, int32_t* out_begins) {
+    const ClassTables T = host_class_tables().view();
+    auto word = [&](int64_t i) -> uint32_t {
+        if (i == -1) return G_BOS;
+        if (i < 0 || i >= n) return 0;
+        return gpt2_class_word(s[i], T.ascii[s[i] & 0x7F]);
+    };
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const bool apos = (word(i - 1) | word(i - 2) | word(i - 3)) & G_AP;
+        if (gpt2_start_nb(word(i), word(i - 1), word(i - 2), word(i - 3), word(i - 4), word(i + 1), single_digits != 0, apos))
+            out_begins[cnt++] = (int32_t)i;
+    }
+    return cnt;
+}

@@ -101,3 +101,15 @@ def gpt2_closed_form(data: bytes, single_digits=False):
     n = lib().hz_gpt2_closed_form(arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), int(single_digits), out.ctypes.data_as(K.i32p))
     b = out[:n].tolist()
     return list(zip(b, b[1:] + [len(data)]))
+
+
+def gpt2_neighbour_form(data: bytes, single_digits=False):
+    """Piece (begin, end) list from the branch-free neighbour form (ASCII subjects only)."""
+    if not data:
+        return []
+    arr = np.frombuffer(data, np.uint8)
+    out = np.empty(len(data) + 1, np.int32)
+    lib().hz_gpt2_neighbour_form.restype = C.c_int64
+    n = lib().hz_gpt2_neighbour_form(arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), int(single_digits), out.ctypes.data_as(K.i32p))
+    b = out[:n].tolist()
+    return list(zip(b, b[1:] + [len(data)]))

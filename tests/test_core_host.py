@@ -148,3 +148,18 @@ def test_gpt2_closed_form_equals_pcre2(oracle_mod, digits):
     for s in cases.EDGE_STRINGS + cases.long_prompts():
         if s:
             assert H.gpt2_closed_form(s.encode(), digits) == _oracle_split(o, s.encode()), s[:40]
+
+
+@pytest.mark.parametrize("digits", [False, True])
+def test_gpt2_neighbour_form_equals_closed_form(digits):
+    """The branch-free neighbour form the fused ASCII window pass evaluates == the closed form (== PCRE2, above)."""
+    import itertools
+    small = ["a", "'", "s", "r", "e", "l", " ", "\n", "1", "!", "v", "d"]
+    for L in range(1, 5):
+        for tup in itertools.product(small, repeat=L):
+            s = "".join(tup).encode()
+            assert H.gpt2_neighbour_form(s, digits) == H.gpt2_closed_form(s, digits), s
+    rng = np.random.default_rng(5)
+    for _ in range(5000):
+        s = bytes(rng.integers(0x09, 0x7F, size=int(rng.integers(1, 40)), dtype=np.uint8))
+        assert H.gpt2_neighbour_form(s, digits) == H.gpt2_closed_form(s, digits), s
