@@ -68,6 +68,8 @@ struct __align__(16) WarpSmem {
     uint16_t act[WIN / 3 + 8];      // indices of the segments (>= 3 symbols) that still have a mergeable pair
     uint32_t segbits[NWORDS];       // bit per position: a segment starts here
     uint32_t actbits[NWORDS];       // bit per position: the pair (w, w+1) is mergeable
+    uint8_t raw_kind[LBK + 16 + WBYTES];   // GPT-2 fused pass: compact class byte per position (index 0 at raw_kind + LBK + 16)
+    __device__ __forceinline__ uint8_t* K8() { return raw_kind + LBK + 16; }
     union {
         struct {
             uint8_t raw_cls[LBK + WBYTES];
@@ -506,39 +508,53 @@ __device__ __forceinline__ void bpe_window_pieces(WarpSmem& S, const BpeTables& 
 }
 
 // GPT-2 (isolate) split + symbolisation + initial keys in ONE position-parallel pass, for windows whose bytes are all
-// ASCII.  The piece-start predicate is the branch-free neighbour form (tok_core.cuh gpt2_start_nb) over 11-bit class
-// words read from a 128-entry shared-memory table; the contraction logic is skipped warp-wide when no apostrophe is
-// near.  Returns the segment count like split_window_gpt2; `complex` reports that the serial BPE path is needed.
-__device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint16_t* glut, const uint8_t* ascii_lut,
+// ASCII.  A short pre-pass writes one compact class byte per position (with the virtual BOS position and zero
+// terminators), so the main pass reads its neighbours unconditionally and evaluates the branch-free neighbour form of
+// the piece-start predicate (tok_core.cuh gpt2_start_nb); the contraction logic runs only when an apostrophe is near
+// (warp-uniform).  Returns the segment count like split_window_gpt2; `complex` = the serial BPE path is needed.
+__device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint16_t* glut,
                                                        int lane, int wlen, int end_rel, int nload, int lb, bool bos,
                                                        int& advance, bool& complex_out) {
     auto& bp = S.u.bp;
     const uint8_t* B = S.B();
+    uint8_t* K8 = S.K8();
     const bool digits = P.spec.pat == PAT_GPT2_DIGITS;
-    auto word = [&](int i) -> uint32_t {      // class word of position i (0 = does not exist)
+    // class bytes: the low 7 bits of the class word (G_L G_N G_S G_SP G_AP | exists 0x20 | BOS 0x40)
+    constexpr uint32_t K_X = 0x20, K_BOS = 0x40;
+    for (int i = lane - lb - 2; i <= nload + 1; i += 32) {
+        uint32_t k = 0;
+        if (i >= -lb && i < nload) k = (glut[B[i]] & 0x1Fu) | K_X;
+        else if (bos && i == -lb - 1) k = K_BOS;
+        K8[i] = (uint8_t)k;
+    }
+    __syncwarp();
+    auto word = [&](int i) -> uint32_t {      // full class word of position i (0 = does not exist); contraction path only
         if (i >= nload) return 0u;
         if (i >= -lb) return glut[B[i]];
         return (bos && i == -lb - 1) ? (uint32_t)G_BOS : 0u;
     };
     bool complex = false;
     int ns = 0;
-    uint32_t ap_prev = __ballot_sync(0xFFFFFFFFu, word(lane - 32) & G_AP);
+    uint32_t ap_prev = __ballot_sync(0xFFFFFFFFu, K8[lane - 32 < -lb - 2 ? -lb - 2 : lane - 32] & G_AP);
     for (int it = 0; it * 32 < wlen; ++it) {
         const int w = it * 32 + lane;
-        const uint32_t cw = word(w);
-        const uint32_t ap = __ballot_sync(0xFFFFFFFFu, cw & G_AP);
+        const uint32_t c8 = K8[w], p8 = K8[w - 1], n8 = K8[w + 1];
+        const uint8_t c = B[w];
+        const uint32_t ap = __ballot_sync(0xFFFFFFFFu, c8 & G_AP);
         const bool apos_near = ((ap & 0x7FFFFFFFu) | (ap_prev >> 29)) != 0;     // warp-uniform
         ap_prev = ap;
-        bool st = false, found = false;
-        if (w < wlen) {
-            const uint8_t c = B[w];
-            const uint32_t p1 = word(w - 1), n1 = word(w + 1);
-            uint32_t p2 = 0, p3 = 0, p4 = 0;
-            if (apos_near) { p2 = word(w - 2); p3 = word(w - 3); p4 = word(w - 4); }
-            if (P.dbg_flags & 1) st = (w == 0) || gpt2_piece_starts_t(B, ClsAsciiLut{B, ascii_lut}, w, -lb, end_rel, digits);
-            else st = (w == 0) || gpt2_start_nb(cw, p1, p2, p3, p4, n1, digits, apos_near);
-            int32_t id = BT.byte_sym[c];
-            if (id < 0) {
+        const bool valid = w < wlen;
+        // map the class bytes to the class-word layout gpt2_start_nb expects (exists -> G_X, BOS -> G_BOS)
+        const uint32_t cw = (c8 & 0x1Fu) | ((c8 & K_X) ? (uint32_t)G_X : 0u);
+        const uint32_t p1 = (p8 & 0x1Fu) | ((p8 & K_X) ? (uint32_t)G_X : 0u) | ((p8 & K_BOS) ? (uint32_t)G_BOS : 0u);
+        const uint32_t n1 = (n8 & 0x1Fu) | ((n8 & K_X) ? (uint32_t)G_X : 0u);
+        bool st;
+        if (apos_near) st = gpt2_start_nb(word(w), word(w - 1), word(w - 2), word(w - 3), word(w - 4), word(w + 1), digits, true);
+        else st = gpt2_start_nb(cw, p1, 0, 0, 0, n1, digits, false);
+        st = valid && (st || w == 0);
+        int32_t id = BT.byte_sym[c];
+        if (__any_sync(0xFFFFFFFFu, valid && id < 0)) {
+            if (valid && id < 0) {
                 if (id == kSymWalk) {           // a longer token may start here: if one does (even across a piece
                     int j = w;                  // boundary), the exact piece-limited walk is left to the serial path
                     id = trie_longest(BT.trie, B, j, nload);
@@ -546,13 +562,12 @@ __device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTab
                 }
                 if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
             }
+        }
+        const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)B[w - 1] << 8) | c));
+        const bool found = valid && !st && r != kNoKey;
+        if (w < WIN) {
             bp.ids[w] = id;
-            uint32_t k = kNoKey;
-            if (!st) {
-                const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)B[w - 1] << 8) | c));
-                if (r != kNoKey) { found = true; k = (r << kPackedBirthBits) | (uint32_t)w; }
-            }
-            bp.key[w] = k;
+            bp.key[w] = found ? ((r << kPackedBirthBits) | (uint32_t)w) : kNoKey;
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
         const uint32_t ma = __ballot_sync(0xFFFFFFFFu, found);
@@ -700,7 +715,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                     } else {
                         if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1) {
                             if (OP == OP_BPE && all_ascii) {
-                                ns = gpt2_ascii_fused_window(S, BT, P, glut_smem, ascii_smem, lane, wlen, end_rel, nload, lb, (pos - eb) == lb, advance, complex_win);
+                                ns = gpt2_ascii_fused_window(S, BT, P, glut_smem, lane, wlen, end_rel, nload, lb, (pos - eb) == lb, advance, complex_win);
                                 keys_ready = true;
                             } else
                                 ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
