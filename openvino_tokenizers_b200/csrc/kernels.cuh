@@ -589,6 +589,60 @@ __device__ __forceinline__ int gpt2_ascii_fused_window(WarpSmem& S, const BpeTab
     return ns;
 }
 
+// GPT-2 (isolate) split + symbolisation + initial keys in ONE position-parallel pass, for windows whose bytes are all
+// ASCII (classes come from the 128-entry table applied to the neighbouring bytes directly).  Returns the segment
+// count like split_window_gpt2; `complex` reports that the serial BPE path is needed.
+__device__ __forceinline__ int gpt2_ascii_fused_window_v5(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint8_t* ascii_smem,
+                                                       int lane, int wlen, int end_rel, int nload, int lb, int& advance, bool& complex_out) {
+    auto& bp = S.u.bp;
+    const uint8_t* B = S.B();
+    const ClsAsciiLut K{B, ascii_smem};
+    const bool digits = P.spec.pat == PAT_GPT2_DIGITS;
+    bool complex = false;
+    int ns = 0;
+    for (int it = 0; it * 32 < wlen; ++it) {
+        const int w = it * 32 + lane;
+        bool st = false, found = false;
+        if (w < wlen) {
+            st = (w == 0) || gpt2_piece_starts_t(B, K, w, -lb, end_rel, digits);
+            const uint8_t c = B[w];
+            int32_t id = BT.byte_sym[c];
+            if (id < 0) {
+                if (id == kSymWalk) {           // a longer token may start here: if one does (even across a piece
+                    int j = w;                  // boundary), the exact piece-limited walk is left to the serial path
+                    id = trie_longest(BT.trie, B, j, nload);
+                    if (id >= 0 && j != w + 1) complex = true;
+                }
+                if (id < 0) { id = BT.byte_miss[c]; if (id < 0) complex = true; }
+            }
+            bp.ids[w] = id;
+            uint32_t k = kNoKey;
+            if (!st) {
+                const uint32_t r = __ldg(BT.pair_rank + (((uint32_t)B[w - 1] << 8) | c));
+                if (r != kNoKey) { found = true; k = (r << kPackedBirthBits) | (uint32_t)w; }
+            }
+            bp.key[w] = k;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
+        const uint32_t ma = __ballot_sync(0xFFFFFFFFu, found);
+        if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(w | F_MATCH);
+        if (lane == 0) { S.segbits[it] = m; S.actbits[it] = ma; }
+        ns += __popc(m);
+    }
+    for (int it = (wlen + 31) / 32 + lane; it < NWORDS; it += 32) S.segbits[it] = 0;
+    complex_out = __any_sync(0xFFFFFFFFu, complex);
+    __syncwarp();
+    if (wlen == end_rel) {
+        advance = wlen;
+        if (lane == 0) S.seg[ns] = (uint16_t)wlen;
+    } else {
+        --ns;
+        advance = S.seg[ns] & POS_MASK;
+    }
+    __syncwarp();
+    return ns;
+}
+
 // WordPiece for all kept segments (words) of a window: one lane per word, longest-match trie walks.
 __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowParams& P, int lane, int ns, bool whole) {
     auto& bp = S.u.bp;
@@ -715,7 +769,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
                     } else {
                         if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1) {
                             if (OP == OP_BPE && all_ascii) {
-                                ns = gpt2_ascii_fused_window(S, BT, P, glut_smem, lane, wlen, end_rel, nload, lb, (pos - eb) == lb, advance, complex_win);
+                                ns = (P.dbg_flags & 2) ? gpt2_ascii_fused_window(S, BT, P, glut_smem, lane, wlen, end_rel, nload, lb, (pos - eb) == lb, advance, complex_win)
+                                                       : gpt2_ascii_fused_window_v5(S, BT, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance, complex_win);
                                 keys_ready = true;
                             } else
                                 ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
