@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -109,7 +110,17 @@ struct RowWorkspace {
     size_t pool_bytes = 8u << 20;
     bool timing = false, timed = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};      // host-buffer pipeline: H2D / kernels / D2H of row chunks
+    cudaEvent_t pipe_ev[34] = {};                            // [k] chunk done, [16] offsets uploaded, [17+k] chunk base chained
+    DBuf<long long> running_total;
+    int32_t* h_pipe = nullptr;                               // pinned + mapped status words per chunk (written by a kernel,
+    int32_t* d_hpipe = nullptr;                              //  so no copy-engine traffic sits between compute and D2H)
+    cudaEvent_t last_done = nullptr;                         // end of the previous call's work (it may have run on another stream)
     ~RowWorkspace() {
+        for (auto s_ : pipe) if (s_) cudaStreamDestroy(s_);
+        for (auto e_ : pipe_ev) if (e_) cudaEventDestroy(e_);
+        if (h_pipe) cudaFreeHost(h_pipe);
+        if (last_done) cudaEventDestroy(last_done);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (h_status) cudaFreeHost(h_status);
@@ -188,6 +199,7 @@ int ensure_ws(b200tok_object* o) {
     CU(w.status.ensure(ST_WORDS));
     CU(w.pool_used.ensure(1));
     CU(w.total.ensure(1));
+    if (!w.last_done) CU(cudaEventCreateWithFlags(&w.last_done, cudaEventDisableTiming));
     return B200TOK_OK;
 }
 
@@ -208,6 +220,277 @@ int validate_in(const b200tok_ragged_strings* in) {
     if (in->n_chars > 0 && !in->chars) return fail(B200TOK_E_INVALID, "missing chars");
     if (in->n_chars >= (1ll << 31) - (1 << 20) || in->n_elems >= (1ll << 31) - (1 << 20)) return fail(B200TOK_E_INVALID, "int32 offsets: batch too large");
     if (in->mem != B200TOK_MEM_HOST && in->mem != B200TOK_MEM_DEVICE) return fail(B200TOK_E_INVALID, "bad mem kind");
+    return B200TOK_OK;
+}
+
+// One launch sequence (row capacities -> scan -> rows kernel -> giant pieces -> scan of counts -> offsets -> compaction)
+// over a contiguous block of rows, with every buffer supplied by the caller.
+struct ChunkLaunch {
+    RowParams P;                 // inputs, splitter, tables; row/tmp/status pointers already offset to this chunk
+    int64_t rows = 0;
+    int per_elem_extra = 0;
+    int32_t* row_cap = nullptr;
+    uint8_t* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int32_t *d_ob = nullptr, *d_oe = nullptr, *d_oa = nullptr, *d_obb = nullptr;
+    uint8_t* d_oc = nullptr;
+    int64_t out_cap = 0;
+    int64_t* total_dev = nullptr;
+    uint8_t* pool = nullptr;
+    size_t pool_bytes = 0;
+    unsigned long long* pool_used = nullptr;
+    bool is_split = false;
+    // zero-copy tail (pipelined host path with pinned outputs)
+    bool zero_copy = false;
+    long long* running_total = nullptr;
+    int32_t *host_begins = nullptr, *host_ends = nullptr;
+    cudaEvent_t ev_prev = nullptr, ev_mine = nullptr;
+    bool lean = false;           // pipelined chunks: direct row bases, folded finish, status cleared by the caller
+};
+
+constexpr size_t kRowsSmem = 128 + 1024 + 256 + WARPS_PER_BLOCK * sizeof(WarpSmem);
+
+int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cudaStream_t st, bool timing) {
+    RowWorkspace& w = owner->ws;
+    const int nthreads = 256;
+    const int64_t B = c.rows;
+    const int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (kRowsSmem + 1024)));
+    const int rows_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * blocks_per_sm);
+    static bool attr_set[3][64] = {};
+    if (!attr_set[call.op][owner->device]) {
+        if (call.op == OP_BPE) CU(cudaFuncSetAttribute(rows_kernel<OP_BPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+        else if (call.op == OP_WORDPIECE) CU(cudaFuncSetAttribute(rows_kernel<OP_WORDPIECE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+        else CU(cudaFuncSetAttribute(rows_kernel<OP_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
+        attr_set[call.op][owner->device] = true;
+    }
+    if (!c.lean) {
+        CU(cudaMemsetAsync(c.P.status, 0, ST_WORDS * 4, st));
+        CU(cudaMemsetAsync(c.pool_used, 0, 8, st));
+    }
+    if (!c.P.direct_base) {
+        row_capacity_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.P.rb, c.P.re, c.P.begins, c.P.ends, (int32_t)B, c.per_elem_extra, c.row_cap);
+        cub::DeviceScan::ExclusiveSum(c.cub_tmp, c.cub_bytes, c.row_cap, const_cast<int32_t*>(c.P.row_base), (int)B, st);
+        ++owner->launches;
+    }
+    if (timing) {
+        if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); }
+        CU(cudaEventRecord(w.ev0, st));
+    }
+    if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
+    else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
+    else rows_kernel<OP_SPLIT><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
+    if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
+    ++owner->launches;
+    if (call.op == OP_BPE) {
+        GiantParams G{c.P.giants, c.P.status, c.P.giants_cap, c.P.chars, call.bpe->view(), call.bpe->suffix.p, c.P.suffix_len,
+                      c.P.row_base, c.P.row_cnt, c.P.tmp_a, c.pool, (unsigned long long)c.pool_bytes, c.pool_used, c.P.status};
+        giant_bpe_kernel<<<std::max(1, owner->sm_count), 64, 0, st>>>(G);
+        ++owner->launches;
+    }
+    cub::DeviceScan::ExclusiveSum(c.cub_tmp, c.cub_bytes, c.P.row_cnt, c.d_ob, (int)B, st);
+    if (c.zero_copy) {
+        if (c.ev_prev) CU(cudaStreamWaitEvent(st, c.ev_prev, 0));
+        chunk_base_kernel<<<1, 1, 0, st>>>(c.d_ob, c.P.row_cnt, (int32_t)B, c.running_total, c.P.status);
+        if (c.ev_mine) CU(cudaEventRecord(c.ev_mine, st));
+        finish_offsets_host_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.d_ob, c.P.row_cnt, (int32_t)B, c.P.status, c.host_begins, c.host_ends);
+        compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, nullptr, nullptr, c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, (int32_t)B,
+                                                                  c.d_oa, nullptr, nullptr, c.out_cap, c.P.status, c.P.status + ST_BASE, nullptr, nullptr);
+        owner->launches += 3;
+    } else if (c.lean) {
+        compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, nullptr, nullptr, c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, (int32_t)B,
+                                                                  c.d_oa, nullptr, nullptr, c.out_cap, c.P.status, nullptr, c.P.row_cnt, c.d_oe);
+        ++owner->launches;
+    } else {
+        finish_offsets_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.d_ob, c.P.row_cnt, (int32_t)B, c.d_oe, c.P.status, c.total_dev);
+        compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, c.is_split ? c.P.tmp_b : nullptr, (c.is_split && c.d_oc) ? c.P.tmp_c : nullptr,
+                                                                  c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, (int32_t)B, c.d_oa, c.d_obb, c.d_oc,
+                                                                  c.out_cap, c.P.status, nullptr, nullptr, nullptr);
+        owner->launches += 2;
+    }
+    CU(cudaGetLastError());
+    return B200TOK_OK;
+}
+
+constexpr int kMaxChunks = 16;
+constexpr int kPipeStreams = 3;
+
+// Host-buffer token ops on large batches: the batch is cut into row chunks that flow through H2D copy -> kernels ->
+// D2H copy on three streams, so the PCIe transfers in both directions overlap each other and the compute.
+// Returns 1 if the batch does not qualify (caller uses the single-shot path), 0 on success, < 0 on error.
+int run_rows_host_pipelined(b200tok_object* owner, const RowCall& call, const b200tok_ragged_strings* in, b200tok_ragged_ids* out,
+                            RowParams P, int per_elem_extra, int64_t tmp_cap) {
+    RowWorkspace& w = owner->ws;
+    const int64_t B = in->n_rows, E = in->n_elems, N = in->n_chars;
+    if (N < (8 << 20) || B < 1024 || E > 4 * B + 1024 || in->skips) return 1;
+    // qualify: rows contiguous, elements increasing and non-overlapping (what StringTensorUnpack / RegexSplit produce)
+    const int32_t *rb = in->ragged_begins, *re = in->ragged_ends, *eb = in->begins, *ee = in->ends;
+    if (rb[0] != 0 || re[B - 1] != E) return 1;
+    for (int64_t r = 0; r + 1 < B; ++r) if (rb[r + 1] != re[r] || re[r] < rb[r]) return 1;
+    if (re[B - 1] < rb[B - 1]) return 1;
+    for (int64_t p = 0; p < E; ++p) if (eb[p] < 0 || ee[p] < eb[p] || ee[p] > N || (p + 1 < E && eb[p + 1] < ee[p])) return 1;
+    // chunk plan (MiB of text per chunk; the last entry repeats): small first chunks so the D2H stream starts early,
+    // then sizes that keep the kernels efficient while compute stays ahead of the copy engine
+    static const std::vector<double> plan = [] {
+        std::vector<double> v;
+        if (const char* e = getenv("B200TOK_PIPE_PLAN")) { char* end = nullptr; for (const char* q = e; *q;) { const double x = strtod(q, &end); if (end == q) break; if (x > 0) v.push_back(x); q = (*end == ',') ? end + 1 : end; } }
+        if (v.empty()) v = {2, 2, 4};
+        return v;
+    }();
+    int64_t row_cut[kMaxChunks + 1];
+    int C = 0;
+    {
+        const double bytes_per_row = (double)N / (double)B;
+        int64_t r = 0;
+        row_cut[0] = 0;
+        while (r < B && C < kMaxChunks) {
+            const double mb = plan[std::min<size_t>((size_t)C, plan.size() - 1)];
+            int64_t nr = std::max<int64_t>(256, (int64_t)(mb * 1048576.0 / bytes_per_row));
+            if (C == kMaxChunks - 1 || r + nr + 256 >= B) nr = B - r;
+            r += nr;
+            row_cut[++C] = r;
+        }
+    }
+    const int64_t rows_per = [&] { int64_t m = 0; for (int k = 0; k < C; ++k) m = std::max(m, row_cut[k + 1] - row_cut[k]); return m; }();
+    if (!w.pipe[0]) {
+        for (int i = 0; i < kPipeStreams; ++i) CU(cudaStreamCreateWithFlags(&w.pipe[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * kMaxChunks + 2; ++i) CU(cudaEventCreateWithFlags(&w.pipe_ev[i], cudaEventDisableTiming));
+        CU(cudaHostAlloc(&w.h_pipe, kMaxChunks * 16 * sizeof(int32_t), cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer(&w.d_hpipe, w.h_pipe, 0));
+    }
+    CU(w.rb.ensure(B)); CU(w.re.ensure(B)); CU(w.begins.ensure(E + 1)); CU(w.ends.ensure(E + 1)); CU(w.chars.ensure(N + 64));
+    CU(w.row_cap.ensure(B)); CU(w.row_base.ensure(B)); CU(w.row_ext.ensure(B)); CU(w.row_cnt.ensure(B)); CU(w.row_flag.ensure(B));
+    CU(w.tmp_a.ensure(tmp_cap + kMaxChunks)); CU(w.out_a.ensure(tmp_cap + kMaxChunks)); CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B));
+    CU(w.status.ensure(ST_WORDS * (kMaxChunks + 1))); CU(w.pool_used.ensure(kMaxChunks + 1)); CU(w.total.ensure(kMaxChunks + 1));
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)rows_per, w.pipe[0]);
+    cub_bytes = (cub_bytes + 511) & ~(size_t)255;
+    CU(w.cub_tmp.ensure(cub_bytes * kMaxChunks + 256));
+    if (call.op == OP_BPE) { CU(w.giants.ensure(w.giants_cap)); CU(w.pool.ensure(w.pool_bytes)); }
+
+    // pinned output buffers can be written by the kernels directly (no staging copy, no host in the loop)
+    int32_t *zc_ids = nullptr, *zc_begins = nullptr, *zc_ends = nullptr;
+    static const bool zc_allowed = [] { const char* e = getenv("B200TOK_ZERO_COPY"); return e && atoi(e); }();   // opt-in: GPU-initiated PCIe stores measured slower than the copy engine
+    if (zc_allowed && out->capacity > 0) {
+        auto devptr = [](void* hp) -> int32_t* {
+            cudaPointerAttributes a{};
+            if (cudaPointerGetAttributes(&a, hp) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return a.type == cudaMemoryTypeHost ? (int32_t*)a.devicePointer : nullptr;
+        };
+        zc_ids = devptr(out->ids); zc_begins = devptr(out->begins); zc_ends = devptr(out->ends);
+        if (!zc_ids || !zc_begins || !zc_ends) zc_ids = nullptr;
+    }
+    CU(w.running_total.ensure(1));
+    cudaStream_t s0 = w.stream;
+    CU(cudaMemsetAsync(w.running_total.p, 0, 8, s0));
+    CU(cudaMemsetAsync(w.status.p, 0, ST_WORDS * 4 * (kMaxChunks + 1), s0));
+    CU(cudaMemsetAsync(w.pool_used.p, 0, 8 * (kMaxChunks + 1), s0));
+    CU(cudaMemcpyAsync(w.rb.p, rb, B * 4, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(w.re.p, re, B * 4, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(w.begins.p, eb, E * 4, cudaMemcpyHostToDevice, s0));
+    CU(cudaMemcpyAsync(w.ends.p, ee, E * 4, cudaMemcpyHostToDevice, s0));
+    CU(cudaEventRecord(w.pipe_ev[kMaxChunks], s0));
+
+    struct Chunk { int64_t r0, r1, tmp_off, cap; } ch[kMaxChunks];
+    int nch = 0;
+    static const bool trace = [] { const char* e = getenv("B200TOK_PIPE_TRACE"); return e && atoi(e); }();
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_start = now_us();
+    double t_ev[kMaxChunks];
+    int64_t off = 0;
+    int result = B200TOK_OK;
+    int64_t bases[kMaxChunks];
+    int next_out = 0;
+    // Hand finished chunks to the D2H stream: called between enqueues (non-blocking) and at the end (blocking).
+    auto drain = [&](bool block) -> int {
+        while (next_out < nch) {
+            const int k = next_out;
+            if (block) CU(cudaEventSynchronize(w.pipe_ev[k]));
+            else {
+                const cudaError_t q = cudaEventQuery(w.pipe_ev[k]);
+                if (q == cudaErrorNotReady) return B200TOK_OK;
+                if (q != cudaSuccess) return fail(B200TOK_E_CUDA, "cudaEventQuery failed: %s", cudaGetErrorString(q));
+            }
+            t_ev[k] = now_us();
+            ++next_out;
+            const int32_t* hs = w.h_pipe + 16 * k;
+            if (result == B200TOK_OK) {
+                if (hs[ST_ERROR] & (ERR_GIANT_LIST | ERR_GIANT_POOL)) result = 1;          // rare: let the single-shot path size the resources
+                else if (hs[ST_ERROR]) result = fail(B200TOK_E_INVALID, "row slots overflowed: overlapping or unordered input elements are not supported");
+                else if (off + hs[ST_TOTAL] > out->capacity) result = fail(B200TOK_E_CAPACITY, "output capacity %lld is smaller than the result", (long long)out->capacity);
+            }
+            if (result != B200TOK_OK) continue;
+            const int64_t T = hs[ST_TOTAL];
+            bases[k] = off;
+            if (!zc_ids) {
+                cudaStream_t st = w.pipe[kPipeStreams - 1];           // all D2H copies go to their own stream, behind nothing else
+                if (T) CU(cudaMemcpyAsync(out->ids + off, w.out_a.p + ch[k].tmp_off, T * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(out->begins + ch[k].r0, w.out_begins.p + ch[k].r0, (ch[k].r1 - ch[k].r0) * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaMemcpyAsync(out->ends + ch[k].r0, w.out_ends.p + ch[k].r0, (ch[k].r1 - ch[k].r0) * 4, cudaMemcpyDeviceToHost, st));
+            }
+            off += T;
+        }
+        return B200TOK_OK;
+    };
+    for (int k = 0; k < C; ++k) {
+        const int64_t r0 = row_cut[k], r1 = row_cut[k + 1];
+        if (r0 >= r1) break;
+        const int64_t p_lo = rb[r0], p_hi = re[r1 - 1];
+        const int64_t byte_lo = p_hi > p_lo ? eb[p_lo] : 0, byte_hi = p_hi > p_lo ? ee[p_hi - 1] : 0;
+        ch[nch] = Chunk{r0, r1, byte_lo + p_lo * per_elem_extra + k, (byte_hi - byte_lo) + (p_hi - p_lo) * per_elem_extra + 1};
+        // three streams: pipe[0] uploads chunk after chunk, pipe[1] runs the kernels of each chunk as soon as its bytes
+        // have landed, pipe[2] downloads finished chunks — so H2D, compute and D2H all run continuously
+        cudaStream_t st = w.pipe[1];
+        if (k == 0) CU(cudaStreamWaitEvent(w.pipe[0], w.pipe_ev[kMaxChunks], 0));
+        if (byte_hi > byte_lo) CU(cudaMemcpyAsync(w.chars.p + byte_lo, in->chars + byte_lo, byte_hi - byte_lo, cudaMemcpyHostToDevice, w.pipe[0]));
+        CU(cudaEventRecord(w.pipe_ev[kMaxChunks + 1 + k], w.pipe[0]));
+        CU(cudaStreamWaitEvent(st, w.pipe_ev[kMaxChunks + 1 + k], 0));
+        ChunkLaunch c;
+        c.P = P;
+        c.P.rb = w.rb.p + r0; c.P.re = w.re.p + r0; c.P.n_rows = (int32_t)(r1 - r0);
+        c.P.begins = w.begins.p; c.P.ends = w.ends.p; c.P.chars = w.chars.p; c.P.skips = nullptr;
+        c.P.row_base = w.row_base.p + r0; c.P.row_ext = w.row_ext.p + r0; c.P.row_cnt = w.row_cnt.p + r0; c.P.row_flag = w.row_flag.p + r0;
+        c.P.tmp_a = w.tmp_a.p + ch[nch].tmp_off; c.P.tmp_b = nullptr; c.P.tmp_c = nullptr; c.P.tmp_cap = ch[nch].cap;
+        c.P.status = w.status.p + ST_WORDS * k;
+        if (call.op == OP_BPE) {
+            const size_t gper = w.giants_cap / C;
+            c.P.giants = w.giants.p + gper * k; c.P.giants_cap = (int32_t)gper;
+            c.pool_bytes = (w.pool_bytes / C) & ~(size_t)255; c.pool = w.pool.p + c.pool_bytes * k;
+        }
+        c.pool_used = w.pool_used.p + k;
+        c.rows = r1 - r0; c.per_elem_extra = per_elem_extra; c.row_cap = w.row_cap.p + r0;
+        c.cub_tmp = w.cub_tmp.p + cub_bytes * k; c.cub_bytes = cub_bytes;
+        c.d_ob = w.out_begins.p + r0; c.d_oe = w.out_ends.p + r0; c.d_oa = w.out_a.p + ch[nch].tmp_off; c.out_cap = ch[nch].cap;
+        c.total_dev = w.total.p + k;
+        c.lean = !zc_ids;
+        c.P.direct_base = 1; c.P.direct_byte0 = (int32_t)byte_lo; c.P.direct_elem0 = (int32_t)p_lo; c.P.direct_extra = per_elem_extra;
+        if (zc_ids) {
+            c.zero_copy = true;
+            c.running_total = w.running_total.p;
+            c.host_begins = zc_begins + r0; c.host_ends = zc_ends + r0;
+            c.d_oa = zc_ids; c.out_cap = out->capacity;
+            c.ev_prev = nullptr; c.ev_mine = nullptr;     // one compute stream: chunk totals chain in stream order
+        }
+        int rc = launch_chunk(owner, call, c, st, false);
+        if (rc) return rc;
+        publish_status_kernel<<<1, 32, 0, st>>>(c.P.status, w.d_hpipe + 16 * k);
+        CU(cudaEventRecord(w.pipe_ev[k], st));
+        ++nch;
+        if ((rc = drain(false)) < 0) return rc;
+    }
+    if (int rc = drain(true); rc < 0) return rc;
+    for (int i = 0; i < kPipeStreams; ++i) CU(cudaStreamSynchronize(w.pipe[i]));
+    if (trace) {
+        fprintf(stderr, "[pipe] chunks=%d enqueue->", nch);
+        for (int k = 0; k < nch; ++k) fprintf(stderr, " ev%d@%.0fus", k, t_ev[k] - t_start);
+        fprintf(stderr, " end@%.0fus\n", now_us() - t_start);
+    }
+    if (result != B200TOK_OK) return result;
+    for (int k = 1; k < nch && !zc_ids; ++k) {          // chunk-relative row offsets -> batch offsets
+        const int32_t add = (int32_t)bases[k];
+        for (int64_t r = ch[k].r0; r < ch[k].r1; ++r) { out->begins[r] += add; out->ends[r] += add; }
+    }
+    out->n_ids = off;
+    w.timed = false;
     return B200TOK_OK;
 }
 
@@ -235,25 +518,13 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
         return B200TOK_OK;
     }
 
-    // ---- inputs on the device ----
-    const int32_t *d_rb, *d_re, *d_b, *d_e;
-    const uint8_t *d_c, *d_sk = nullptr;
-    if (host) {
-        CU(w.rb.ensure(B)); CU(w.re.ensure(B)); CU(w.begins.ensure(E + 1)); CU(w.ends.ensure(E + 1)); CU(w.chars.ensure(N + 64));
-        CU(cudaMemcpyAsync(w.rb.p, in->ragged_begins, B * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(w.re.p, in->ragged_ends, B * 4, cudaMemcpyHostToDevice, st));
-        if (E) CU(cudaMemcpyAsync(w.begins.p, in->begins, E * 4, cudaMemcpyHostToDevice, st));
-        if (E) CU(cudaMemcpyAsync(w.ends.p, in->ends, E * 4, cudaMemcpyHostToDevice, st));
-        if (N) CU(cudaMemcpyAsync(w.chars.p, in->chars, N, cudaMemcpyHostToDevice, st));
-        if (in->skips && E) { CU(w.skips.ensure(E)); CU(cudaMemcpyAsync(w.skips.p, in->skips, E, cudaMemcpyHostToDevice, st)); d_sk = w.skips.p; }
-        d_rb = w.rb.p; d_re = w.re.p; d_b = w.begins.p; d_e = w.ends.p; d_c = w.chars.p;
-    } else {
-        d_rb = in->ragged_begins; d_re = in->ragged_ends; d_b = in->begins; d_e = in->ends; d_c = in->chars; d_sk = in->skips;
-    }
+    // the workspace is shared by all calls on this handle: order this call after the previous one, whatever stream it used
+    CU(cudaStreamWaitEvent(st, w.last_done, 0));
+    if (host && st != w.stream) CU(cudaStreamWaitEvent(w.stream, w.last_done, 0));
 
-    // ---- parameters ----
+    // ---- parameters that do not depend on where the data lives ----
     RowParams P{};
-    P.rb = d_rb; P.re = d_re; P.n_rows = (int32_t)B; P.begins = d_b; P.ends = d_e; P.chars = d_c; P.n_chars = (int32_t)N; P.skips = d_sk;
+    P.n_chars = (int32_t)N;
     P.spec = SplitSpec{}; P.spec.pat = PAT_NONE; P.mode = SPLIT_ISOLATED; P.invert = 0; P.max_splits = -1; P.repeat = 0;
     if (call.split) {
         const HostSplit& hs = call.split->h;
@@ -280,10 +551,33 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
         P.unk_id = call.unk_id;
     }
     const int64_t tmp_cap = N + E * per_elem_extra + 1;
-    if (tmp_cap >= (1ll << 31)) return fail(B200TOK_E_INVALID, "batch too large for int32 offsets");
+    if (tmp_cap >= (1ll << 31) - 64) return fail(B200TOK_E_INVALID, "batch too large for int32 offsets");
+
+    if (host && out_ids && !user_stream && !w.timing && !(P.dbg_flags & 4)) {
+        if (!out_ids->begins || !out_ids->ends || (!out_ids->ids && out_ids->capacity > 0)) return fail(B200TOK_E_INVALID, "missing output buffers");
+        rc = run_rows_host_pipelined(owner, call, in, out_ids, P, per_elem_extra, tmp_cap);
+        if (rc <= 0) return rc;          // done or failed; rc == 1: not eligible / needs bigger giant-piece resources
+    }
+
+    // ---- inputs on the device ----
+    const int32_t *d_rb, *d_re, *d_b, *d_e;
+    const uint8_t *d_c, *d_sk = nullptr;
+    if (host) {
+        CU(w.rb.ensure(B)); CU(w.re.ensure(B)); CU(w.begins.ensure(E + 1)); CU(w.ends.ensure(E + 1)); CU(w.chars.ensure(N + 64));
+        CU(cudaMemcpyAsync(w.rb.p, in->ragged_begins, B * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(w.re.p, in->ragged_ends, B * 4, cudaMemcpyHostToDevice, st));
+        if (E) CU(cudaMemcpyAsync(w.begins.p, in->begins, E * 4, cudaMemcpyHostToDevice, st));
+        if (E) CU(cudaMemcpyAsync(w.ends.p, in->ends, E * 4, cudaMemcpyHostToDevice, st));
+        if (N) CU(cudaMemcpyAsync(w.chars.p, in->chars, N, cudaMemcpyHostToDevice, st));
+        if (in->skips && E) { CU(w.skips.ensure(E)); CU(cudaMemcpyAsync(w.skips.p, in->skips, E, cudaMemcpyHostToDevice, st)); d_sk = w.skips.p; }
+        d_rb = w.rb.p; d_re = w.re.p; d_b = w.begins.p; d_e = w.ends.p; d_c = w.chars.p;
+    } else {
+        d_rb = in->ragged_begins; d_re = in->ragged_ends; d_b = in->begins; d_e = in->ends; d_c = in->chars; d_sk = in->skips;
+    }
+    P.rb = d_rb; P.re = d_re; P.n_rows = (int32_t)B; P.begins = d_b; P.ends = d_e; P.chars = d_c; P.skips = d_sk;
 
     CU(w.row_cap.ensure(B)); CU(w.row_base.ensure(B)); CU(w.row_ext.ensure(B)); CU(w.row_cnt.ensure(B)); CU(w.row_flag.ensure(B));
-    CU(w.tmp_a.ensure(tmp_cap));
+    CU(w.tmp_a.ensure(tmp_cap + kMaxChunks));
     if (is_split) { CU(w.tmp_b.ensure(tmp_cap)); CU(w.tmp_c.ensure(tmp_cap)); }
     size_t cub_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)B, st);
@@ -296,66 +590,39 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     if (out_ids) {
         out_cap = out_ids->capacity;
         if (host) {
-            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap));
+            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap + kMaxChunks));
             d_ob = w.out_begins.p; d_oe = w.out_ends.p; d_oa = w.out_a.p;
             out_cap = std::min<int64_t>(out_cap, tmp_cap);
         } else { d_ob = out_ids->begins; d_oe = out_ids->ends; d_oa = out_ids->ids; }
     } else {
         out_cap = out_split->capacity;
         if (host) {
-            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap)); CU(w.out_b.ensure(tmp_cap)); CU(w.out_c.ensure(tmp_cap));
+            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap + kMaxChunks)); CU(w.out_b.ensure(tmp_cap)); CU(w.out_c.ensure(tmp_cap));
             d_ob = w.out_begins.p; d_oe = w.out_ends.p; d_oa = w.out_a.p; d_obb = w.out_b.p; d_oc = out_split->skips ? w.out_c.p : nullptr;
             out_cap = std::min<int64_t>(out_cap, tmp_cap);
         } else { d_ob = out_split->ragged_begins; d_oe = out_split->ragged_ends; d_oa = out_split->begins; d_obb = out_split->ends; d_oc = out_split->skips; }
     }
     if (!d_ob || !d_oe || (!d_oa && out_cap > 0)) return fail(B200TOK_E_INVALID, "missing output buffers");
-
-    const size_t smem = 128 + 1024 + 256 + WARPS_PER_BLOCK * sizeof(WarpSmem);
-    const int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
-    static bool attr_set[3][64] = {};
-    const int nthreads = 256;
-    const int rows_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * blocks_per_sm);
     const bool async = out_ids && !host && out_ids->n_ids_device;
 
     for (int attempt = 0; attempt < 4; ++attempt) {
-        CU(cudaMemsetAsync(w.status.p, 0, ST_WORDS * 4, st));
-        CU(cudaMemsetAsync(w.pool_used.p, 0, 8, st));
-        row_capacity_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(d_rb, d_re, d_b, d_e, (int32_t)B, per_elem_extra, w.row_cap.p);
-        cub::DeviceScan::ExclusiveSum(w.cub_tmp.p, cub_bytes, w.row_cap.p, w.row_base.p, (int)B, st);
-        P.row_base = w.row_base.p; P.row_ext = w.row_ext.p; P.row_cnt = w.row_cnt.p; P.row_flag = w.row_flag.p;
-        P.tmp_a = w.tmp_a.p; P.tmp_b = w.tmp_b.p; P.tmp_c = w.tmp_c.p; P.tmp_cap = tmp_cap;
-        P.status = w.status.p;
-        if (call.op == OP_BPE) { CU(w.giants.ensure(w.giants_cap)); P.giants = w.giants.p; P.giants_cap = (int32_t)w.giants_cap; }
-        if (!attr_set[call.op][owner->device]) {
-            if (call.op == OP_BPE) CU(cudaFuncSetAttribute(rows_kernel<OP_BPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else if (call.op == OP_WORDPIECE) CU(cudaFuncSetAttribute(rows_kernel<OP_WORDPIECE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else CU(cudaFuncSetAttribute(rows_kernel<OP_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[call.op][owner->device] = true;
-        }
-        if (w.timing) {
-            if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); }
-            CU(cudaEventRecord(w.ev0, st));
-        }
-        if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
-        else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
-        else rows_kernel<OP_SPLIT><<<rows_blocks, BLOCK_THREADS, smem, st>>>(P);
-        if (w.timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
-        owner->launches += 2;
+        ChunkLaunch c;
+        c.P = P;
+        c.P.row_base = w.row_base.p; c.P.row_ext = w.row_ext.p; c.P.row_cnt = w.row_cnt.p; c.P.row_flag = w.row_flag.p;
+        c.P.tmp_a = w.tmp_a.p; c.P.tmp_b = w.tmp_b.p; c.P.tmp_c = w.tmp_c.p; c.P.tmp_cap = tmp_cap;
+        c.P.status = w.status.p;
         if (call.op == OP_BPE) {
-            CU(w.pool.ensure(w.pool_bytes));
-            GiantParams G{w.giants.p, w.status.p, (int32_t)w.giants_cap, d_c, call.bpe->view(), call.bpe->suffix.p, P.suffix_len,
-                          w.row_base.p, w.row_cnt.p, w.tmp_a.p, w.pool.p, (unsigned long long)w.pool_bytes, w.pool_used.p, w.status.p};
-            giant_bpe_kernel<<<std::max(1, owner->sm_count), 64, 0, st>>>(G);
-            ++owner->launches;
+            CU(w.giants.ensure(w.giants_cap)); CU(w.pool.ensure(w.pool_bytes));
+            c.P.giants = w.giants.p; c.P.giants_cap = (int32_t)w.giants_cap;
+            c.pool = w.pool.p; c.pool_bytes = w.pool_bytes;
         }
-        cub::DeviceScan::ExclusiveSum(w.cub_tmp.p, cub_bytes, w.row_cnt.p, d_ob, (int)B, st);
-        finish_offsets_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(d_ob, w.row_cnt.p, (int32_t)B, d_oe, w.status.p,
-                                                                                            async ? out_ids->n_ids_device : w.total.p);
-        compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(w.tmp_a.p, is_split ? w.tmp_b.p : nullptr, (is_split && d_oc) ? w.tmp_c.p : nullptr,
-                                                                  w.row_base.p, w.row_ext.p, w.row_flag.p, d_ob, (int32_t)B, d_oa, d_obb, d_oc,
-                                                                  out_cap, w.status.p);
-        owner->launches += 2;
-        CU(cudaGetLastError());
+        c.pool_used = w.pool_used.p;
+        c.rows = B; c.per_elem_extra = per_elem_extra; c.row_cap = w.row_cap.p; c.cub_tmp = w.cub_tmp.p; c.cub_bytes = cub_bytes;
+        c.d_ob = d_ob; c.d_oe = d_oe; c.d_oa = d_oa; c.d_obb = d_obb; c.d_oc = d_oc; c.out_cap = out_cap;
+        c.total_dev = async ? out_ids->n_ids_device : w.total.p;
+        c.is_split = is_split;
+        if ((rc = launch_chunk(owner, call, c, st, w.timing))) return rc;
+        CU(cudaEventRecord(w.last_done, st));
         if (async) return B200TOK_OK;
 
         CU(cudaMemcpyAsync(w.h_status, w.status.p, ST_WORDS * 4, cudaMemcpyDeviceToHost, st));

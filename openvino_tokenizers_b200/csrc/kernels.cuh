@@ -29,7 +29,7 @@ constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK =
 enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2 };
 
 // status words (device int32 array)
-enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_POOL_NEED_LO = 4, ST_POOL_NEED_HI = 5, ST_WORDS = 8 };
+enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_WORDS = 8 };
 enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
 
 struct GiantItem { int32_t row, begin, end, slot; };
@@ -59,6 +59,9 @@ struct RowParams {
     GiantItem* giants; int32_t giants_cap;
     int32_t* status;
     int32_t dbg_flags;         // development switches (env B200TOK_DEBUG_FLAGS), 0 in production
+    // contiguous, increasing elements (verified by the host): a row's slot base follows from its first element's byte
+    // offset, so the capacity kernel + scan are skipped:  base = begins[rb[row]] - direct_byte0 + (rb[row] - direct_elem0) * extra
+    int32_t direct_base; int32_t direct_byte0; int32_t direct_elem0; int32_t direct_extra;
 };
 
 struct __align__(16) WarpSmem {
@@ -696,10 +699,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const RowParams 
         if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
         row = __shfl_sync(0xFFFFFFFFu, row, 0);
         if (row >= P.n_rows) break;
-        const int64_t base = P.row_base[row];
+        const int p0 = P.rb[row], p1 = P.re[row];
+        int64_t base;
+        if (P.direct_base) {
+            base = p1 > p0 ? (int64_t)(P.begins[p0] - P.direct_byte0) + (int64_t)(p0 - P.direct_elem0) * P.direct_extra : 0;
+            if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
+        } else base = P.row_base[row];
         int emitted = 0;       // slots used in this row's range
         int holes = 0;         // reserved-but-unfilled slots (giant BPE pieces)
-        const int p0 = P.rb[row], p1 = P.re[row];
         for (int p = p0; p < p1; ++p) {
             const int eb = P.begins[p], ee = P.ends[p];
             const bool skip = P.skips && P.skips[p];
@@ -942,6 +949,12 @@ __global__ void giant_bpe_kernel(const GiantParams G) {
     }
 }
 
+// Copies a chunk's status words into mapped host memory (the pipelined host path polls them after an event).
+__global__ void publish_status_kernel(const int32_t* status, int32_t* host_mapped) {
+    if (threadIdx.x < ST_WORDS) host_mapped[threadIdx.x] = status[threadIdx.x];
+    __threadfence_system();
+}
+
 // out_begins = exclusive scan(row_cnt) is done with cub; this finishes ends + total.
 __global__ void finish_offsets_kernel(const int32_t* begins, const int32_t* cnt, int32_t n_rows, int32_t* ends,
                                       int32_t* status, int64_t* total_out) {
@@ -952,17 +965,42 @@ __global__ void finish_offsets_kernel(const int32_t* begins, const int32_t* cnt,
     if (r == n_rows - 1) { status[ST_TOTAL] = e; if (total_out) *total_out = e; }
 }
 
+// Pipelined host path, zero-copy variant: chunk totals are chained on the device (base of chunk k = sum of the totals
+// of chunks < k), so final row offsets and ids can be stored straight into the caller's pinned host buffers.
+__global__ void chunk_base_kernel(const int32_t* begins, const int32_t* cnt, int32_t n_rows, long long* running_total, int32_t* status) {
+    const long long base = *running_total;
+    const int32_t total = begins[n_rows - 1] + cnt[n_rows - 1];
+    status[ST_TOTAL] = total;
+    status[ST_BASE] = (int32_t)base;
+    *running_total = base + total;
+}
+__global__ void finish_offsets_host_kernel(const int32_t* begins, const int32_t* cnt, int32_t n_rows, const int32_t* status,
+                                           int32_t* host_begins, int32_t* host_ends) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int32_t b = status[ST_BASE] + begins[r];
+    host_begins[r] = b;
+    host_ends[r] = b + cnt[r];
+}
+
 // Copy every row's slots to their final place (warp per row); rows with holes are filtered.
 __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, const uint8_t* tmp_c,
                                     const int32_t* row_base, const int32_t* row_ext, const uint8_t* row_flag,
                                     const int32_t* out_begin, int32_t n_rows,
-                                    int32_t* out_a, int32_t* out_b, uint8_t* out_c, int64_t out_cap, int32_t* status) {
+                                    int32_t* out_a, int32_t* out_b, uint8_t* out_c, int64_t out_cap, int32_t* status,
+                                    const int32_t* dst_base, const int32_t* row_cnt, int32_t* out_end) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int64_t base = dst_base ? (int64_t)*dst_base : 0;
     for (int r = warp; r < n_rows; r += nwarps) {
         const int64_t src = row_base[r];
         const int ext = row_ext[r];
-        int64_t dst = out_begin[r];
+        int64_t dst = base + out_begin[r];
+        if (out_end && lane == 0) {          // folded finish_offsets: row end + chunk total
+            const int32_t e = out_begin[r] + row_cnt[r];
+            out_end[r] = e;
+            if (r == n_rows - 1) status[ST_TOTAL] = e;
+        }
         if (!row_flag[r]) {
             if (dst + ext > out_cap) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
             for (int t = lane; t < ext; t += 32) {

@@ -418,3 +418,29 @@ def test_c1_full_size_properties(ops, gpt2):
     # idempotence: same call, same answer
     again = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
     assert cases.ragged_rows_equal(again, got)
+
+
+def test_host_pipeline_equals_device_path_and_oracle(ops, gpt2):
+    """Large host-buffer calls are cut into row chunks that overlap H2D / kernels / D2H; the result must equal the
+    single-launch device-resident path and (on sampled rows) the oracle.  Ragged row lengths, ~12 MB."""
+    import torch
+    from openvino_tokenizers_b200 import runtime as R
+    rng = np.random.default_rng(21)
+    lens = rng.integers(0, 700, size=36000)
+    strings = [bytes(rng.integers(0x20, 0x7F, size=int(n), dtype=np.uint8)) for n in lens]
+    batch = cases.batch_from_strings(strings)
+    assert len(batch[4]) > (8 << 20)
+    got = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))          # host path (pipelined)
+    pipe = R.TokenizerPipeline("bpe", "gpt2_synth")
+    db = R.to_device(batch, torch.device("cuda", 0))
+    o = pipe.run_device(db)
+    torch.cuda.synchronize()
+    n = int(o["n"].item())
+    assert n == len(got[2])
+    assert np.array_equal(o["ids"][:n].cpu().numpy(), got[2])
+    assert np.array_equal(o["begins"].cpu().numpy(), got[0]) and np.array_equal(o["ends"].cpu().numpy(), got[1])
+    sample = np.r_[0:50, 17990:18040, 35950:36000]
+    sub = cases.batch_from_strings([strings[i] for i in sample])
+    exp = oracle_chain_bpe(gpt2, sub)
+    for i, r in enumerate(sample):
+        assert np.array_equal(got[2][got[0][r]:got[1][r]], exp[2][exp[0][i]:exp[1][i]])
