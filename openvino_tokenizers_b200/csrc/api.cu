@@ -152,9 +152,9 @@ struct BpeObj : b200tok_object {
     DevTrie trie;
     DBuf<MergeSlot> slots;
     DBuf<int32_t> rank_newid;
-    DBuf<uint32_t> pair_rank;
+    DBuf<uint32_t> pair_rank, pair_bits;
     DBuf<uint8_t> suffix;
-    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p}}; }
+    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p}, pair_bits.p}; }
 };
 struct WordpieceObj : b200tok_object {
     HostWordpiece h;
@@ -248,7 +248,7 @@ struct ChunkLaunch {
     bool lean = false;           // pipelined chunks: direct row bases, folded finish, status cleared by the caller
 };
 
-constexpr size_t kRowsSmem = 128 + 1024 + 256 + WARPS_PER_BLOCK * sizeof(WarpSmem);
+constexpr size_t kRowsSmem = kRowsSmemFixed + WARPS_PER_BLOCK * sizeof(WarpSmem);
 
 int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cudaStream_t st, bool timing) {
     RowWorkspace& w = owner->ws;
@@ -768,6 +768,7 @@ B200TOK_API int b200tok_bpe_create(const b200tok_bpe_desc* d, b200tok_handle* ou
     CU(o->slots.upload(o->h.slots));
     CU(o->rank_newid.upload(o->h.rank_newid));
     CU(o->pair_rank.upload(o->h.pair_rank));
+    CU(o->pair_bits.upload(o->h.pair_bits));
     std::vector<uint8_t> sfx(o->h.end_suffix.begin(), o->h.end_suffix.end());
     if (sfx.empty()) sfx.push_back(0);
     CU(o->suffix.upload(sfx));

@@ -225,6 +225,20 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
             auto it = merges.find(((uint64_t)(uint32_t)sym1[b0] << 32) | (uint32_t)sym1[b1]);
             if (it != merges.end()) out.pair_rank[(size_t)(b0 << 8 | b1)] = (uint32_t)it->second.first;
         }
+    // [0, 512): mergeable ASCII byte pairs; [512, 512 + 2048): for every first byte, the second bytes that continue a
+    // token of the symbolisation trie (bit b1 of words [512 + 8 * b0, +8)) — lets the window kernel skip trie walks
+    out.pair_bits.assign(512 + 2048, 0u);
+    for (int b0 = 0; b0 < 256; ++b0) {
+        const int32_t node = out.trie.root_child[b0];
+        if (node < 0) continue;
+        for (int32_t e = out.trie.first[node]; e < out.trie.first[node + 1]; ++e) {
+            const int b1 = out.trie.edge_byte[e];
+            out.pair_bits[(size_t)(512 + 8 * b0 + (b1 >> 5))] |= 1u << (b1 & 31);
+        }
+    }
+    for (int b0 = 0; b0 < 128; ++b0)
+        for (int b1 = 0; b1 < 128; ++b1)
+            if (out.pair_rank[(size_t)(b0 << 8 | b1)] != kNoKey) out.pair_bits[(size_t)(b0 << 2 | b1 >> 5)] |= 1u << (b1 & 31);
     return B200TOK_OK;
 }
 

@@ -411,6 +411,38 @@ B2_HD bool gpt2_start_nb(uint32_t c, uint32_t p1, uint32_t p2, uint32_t p3, uint
     return r || (p1 & G_BOS);
 }
 
+// Word form of the same predicate: 32 byte positions at a time as bit masks (bit i = position base + i), so one thread
+// evaluates 32 positions with ~40 logic operations.  Per-word class masks: L / N / S (continuation bytes carry their
+// owner's bits), SP = byte 0x20, A2 / A3 = an apostrophe followed by a 2- / 3-byte contraction ('s 't 'm 'd / 're 've 'll),
+// CONT = UTF-8 continuation byte, MB = a multi-byte whitespace character whose next character exists and is not
+// whitespace, X = the position exists (inside the element and loaded).  Masks of positions that do not exist are 0.
+struct G2Word { uint32_t L, N, S, SP, A2, A3, CONT, MB, X; };
+B2_HD uint32_t g2_fsl(uint32_t lo, uint32_t hi, int k) { return k == 0 ? hi : (hi << k) | (lo >> (32 - k)); }   // bits of (hi:lo) moved up by k
+B2_HD uint32_t g2_fsr(uint32_t lo, uint32_t hi, int k) { return k == 0 ? lo : (lo >> k) | (hi << (32 - k)); }   // moved down by k
+B2_HD uint32_t g2_ok1(const G2Word& w) { return w.L | w.N | (w.S & ~w.SP); }
+// contraction starts of this word: apostrophes reached as the start of a match (gpt2_apostrophe_t).  p_ok1 = g2_ok1 of
+// the previous word, bos = bit of the element's first position if it lies in this word.
+B2_HD void g2_contractions(const G2Word& w, uint32_t p_ok1, uint32_t bos, uint32_t& c2, uint32_t& c3) {
+    const uint32_t okp = g2_fsl(p_ok1, g2_ok1(w), 1) | bos;
+    c2 = w.A2 & okp;
+    c3 = w.A3 & okp;
+}
+// piece starts of this word.  p = previous word's masks, (pc2, pc3) / (c2, c3) = g2_contractions of the previous / this
+// word, n_ns = X & ~S of the next word.
+B2_HD uint32_t g2_starts(const G2Word& w, const G2Word& p, uint32_t c2, uint32_t c3, uint32_t pc2, uint32_t pc3, uint32_t n_ns,
+                         uint32_t bos, bool single_digits) {
+    const uint32_t p1L = g2_fsl(p.L, w.L, 1), p1N = g2_fsl(p.N, w.N, 1), p1S = g2_fsl(p.S, w.S, 1), p1SP = g2_fsl(p.SP, w.SP, 1);
+    const uint32_t n1ns = g2_fsr(w.X & ~w.S, n_ns, 1);
+    const uint32_t s_start = w.S & (~p1S | n1ns | w.MB);
+    const uint32_t n_start = single_digits ? w.N : (w.N & ~p1SP & ~p1N);
+    const uint32_t o_start = w.X & ~(w.L | w.N | w.S) & ~p1SP & (p1L | p1N | p1S);
+    const uint32_t c23 = c2 | c3, pc23 = pc2 | pc3;
+    const uint32_t inside = g2_fsl(pc23, c23, 1) | g2_fsl(pc3, c3, 2);
+    const uint32_t ends = g2_fsl(pc2, c2, 2) | g2_fsl(pc3, c3, 3);
+    const uint32_t l_start = w.L & ~p1SP & ~inside & (ends | ~p1L);
+    return (s_start | n_start | o_start | l_start | bos) & w.X & ~w.CONT;
+}
+
 // (p)+ for the "contiguous" rewrite (src/regex_split.cpp:33-37): greedy repetition of the pattern.
 template <class C>
 B2_HD Match match_rep(const C& c, const SplitSpec& spec, bool repeat, int p, int end) {
@@ -589,6 +621,8 @@ struct BpeTables {
     const uint32_t* pair_rank; // [65536] rank of the merge of the one-byte symbols of (b0,b1), index b0<<8|b1; kNoKey if none
     FlatTrie trie;
     MergeTable merges;
+    const uint32_t* pair_bits; // [512] bit (b0 << 7 | b1) set iff pair_rank[b0 << 8 | b1] != kNoKey, for b0, b1 < 128;
+                               // then [2048]: bit (b0 << 8 | b1) set iff the trie has a token prefix b0 b1
 };
 constexpr int32_t kSymWalk = -2;
 

@@ -132,3 +132,59 @@ HZ int64_t hz_gpt2_neighbour_form(const uint8_t* s, int64_t n, int single_digits
     }
     return cnt;
 }
+
+// The word (bit-mask) form of the predicate (tok_core.cuh g2_starts), evaluated over one element the way the window
+// kernel does: class bytes as in pass A, masks per 32 positions, carries from the neighbouring words.
+HZ int64_t hz_gpt2_word_form(const uint8_t* s, int64_t n, int single_digits, int32_t* out_begins) {
+    const ClassTables T = host_class_tables().view();
+    const int end = (int)n;
+    std::vector<uint8_t> k((size_t)n + 8, 0);
+    for (int w = 0; w < end; ++w) {
+        const uint8_t b = s[w];
+        uint8_t c;
+        if (b < 0x80) c = T.ascii[b];
+        else if (is_cont_byte(b) && w > 0) {
+            int j = w - 1;
+            while (j >= 0 && j > w - 4 && is_cont_byte(s[j])) --j;
+            c = C_CONT;
+            if (j >= 0 && j > w - 4 && s[j] >= 0xC0) c |= char_class(s, j, end, T);
+        } else c = char_class(s, w, end, T);
+        k[w] = c;
+    }
+    const int nw = (end + 31) / 32;
+    std::vector<G2Word> W((size_t)nw + 2, G2Word{0, 0, 0, 0, 0, 0, 0, 0, 0});   // W[i + 1] = word i; W[0] and W[nw + 1] stay empty
+    for (int w = 0; w < end; ++w) {
+        G2Word& g = W[(size_t)(w >> 5) + 1];
+        const uint32_t bit = 1u << (w & 31);
+        g.X |= bit;
+        if (k[w] & C_L) g.L |= bit;
+        if (k[w] & C_N) g.N |= bit;
+        if (k[w] & C_S) g.S |= bit;
+        if (k[w] & C_CONT) g.CONT |= bit;
+        if (s[w] == 0x20) g.SP |= bit;
+        if (s[w] == '\'') {
+            const int cl = gpt2_contraction_len(s, w, end);
+            if (cl == 2) g.A2 |= bit;
+            if (cl == 3) g.A3 |= bit;
+        }
+        if ((k[w] & C_S) && s[w] >= 0x80 && !(k[w] & C_CONT)) {
+            int j = w + 1;
+            while (j < end && (k[j] & C_CONT)) ++j;
+            if (j < end && !(k[j] & C_S)) g.MB |= bit;
+        }
+    }
+    int64_t cnt = 0;
+    uint32_t pc2 = 0, pc3 = 0;
+    for (int i = 0; i < nw; ++i) {
+        const G2Word& g = W[(size_t)i + 1];
+        const G2Word& p = W[(size_t)i];
+        const G2Word& nx = W[(size_t)i + 2];
+        const uint32_t bos = i == 0 ? 1u : 0u;
+        uint32_t c2, c3;
+        g2_contractions(g, g2_ok1(p), bos, c2, c3);
+        const uint32_t st = g2_starts(g, p, c2, c3, pc2, pc3, nx.X & ~nx.S, bos, single_digits != 0);
+        for (int b = 0; b < 32; ++b) if ((st >> b) & 1u) out_begins[cnt++] = i * 32 + b;
+        pc2 = c2; pc3 = c3;
+    }
+    return cnt;
+}

@@ -163,3 +163,28 @@ def test_gpt2_neighbour_form_equals_closed_form(digits):
     for _ in range(5000):
         s = bytes(rng.integers(0x09, 0x7F, size=int(rng.integers(1, 40)), dtype=np.uint8))
         assert H.gpt2_neighbour_form(s, digits) == H.gpt2_closed_form(s, digits), s
+
+
+@pytest.mark.parametrize("digits", [False, True])
+def test_gpt2_word_form_equals_closed_form(digits):
+    """The word (bit-mask) form the window kernel evaluates == the closed form (== PCRE2, above); subjects longer than one
+    32-position word exercise the carries, UTF-8 subjects the continuation-byte and multi-byte-whitespace handling."""
+    import itertools
+    small = ["a", "'", "s", "r", "e", "l", " ", "\n", "1", "!", "v", "d"]
+    for L in range(1, 5):
+        for tup in itertools.product(small, repeat=L):
+            s = "".join(tup).encode()
+            assert H.gpt2_word_form(s, digits) == H.gpt2_closed_form(s, digits), s
+    rng = np.random.default_rng(7)
+    for _ in range(4000):
+        s = bytes(rng.integers(0x09, 0x7F, size=int(rng.integers(1, 200)), dtype=np.uint8))
+        assert H.gpt2_word_form(s, digits) == H.gpt2_closed_form(s, digits), s
+    dense = ["a", "b", "'", "'", "s", "t", "m", "d", "r", "e", "v", "l", " ", " ", "\n", "\t", "1", "2", "!", "?"]
+    uni = dense + [chr(0xA0), chr(0x2003), chr(0x3000), chr(0x416), chr(0x4E2D), chr(0x1F600), chr(0x663), chr(0xE9), chr(0x85), chr(0x1680)]
+    for alpha in (dense, uni):
+        for _ in range(4000):
+            s = "".join(rng.choice(alpha, size=int(rng.integers(1, 120)))).encode()
+            assert H.gpt2_word_form(s, digits) == H.gpt2_closed_form(s, digits), s
+    for s in cases.EDGE_STRINGS + cases.long_prompts():
+        if s:
+            assert H.gpt2_word_form(s.encode(), digits) == H.gpt2_closed_form(s.encode(), digits), s[:40]

@@ -24,9 +24,12 @@ split = ops.RegexSplit("isolate").with_pattern(a.split_pattern)
 bpe = ops.BPETokenizer().with_constants(consts)
 batch = cases.random_ascii_batch(B, L) if kind == "ascii" else cases.english_like_batch(B, L)
 rb, re_, b, e, c = batch
-t0 = time.time(); got = ops.split_bpe(split, bpe, list(batch)); t1 = time.time()
-print("first host call", t1 - t0, "s; tokens", len(got[2]))
-for _ in range(3):
+NOHOST = "nohost" in sys.argv
+got = None
+if not NOHOST:
+    t0 = time.time(); got = ops.split_bpe(split, bpe, list(batch)); t1 = time.time()
+    print("first host call", t1 - t0, "s; tokens", len(got[2]))
+for _ in range(0 if NOHOST else 3):
     t0 = time.time(); got = ops.split_bpe(split, bpe, list(batch)); t1 = time.time()
     print("host-to-host MB/s", B * L / 1e6 / (t1 - t0))
 dev = torch.device("cuda:0")
@@ -52,4 +55,4 @@ ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / K_STEPS
 T = int(nid.item())
 print(f"device-resident: {ms:.3f} ms/step, {B*L/1e6/(ms/1e3):.1f} MB/s text, T={T}, algorithmic GB/s {(B*L+16*B+4*T)/1e9/(ms/1e3):.1f}")
-assert np.array_equal(ids[:T].cpu().numpy(), got[2])
+assert got is None or np.array_equal(ids[:T].cpu().numpy(), got[2])
