@@ -16,6 +16,7 @@
 
 #include "../../include/b200tok.h"
 #include "kernels.cuh"
+#include "kernels_fast.cuh"
 #include "kernels_misc.cuh"
 #include "tables.hpp"
 
@@ -154,7 +155,7 @@ struct BpeObj : b200tok_object {
     DBuf<int32_t> rank_newid;
     DBuf<uint32_t> pair_rank, pair_bits;
     DBuf<uint8_t> suffix;
-    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p}, pair_bits.p}; }
+    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p}, pair_bits.p, h.newid_base}; }
 };
 struct WordpieceObj : b200tok_object {
     HostWordpiece h;
@@ -276,11 +277,32 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); }
         CU(cudaEventRecord(w.ev0, st));
     }
-    if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
-    else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
-    else rows_kernel<OP_SPLIT><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
-    if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
-    ++owner->launches;
+    // GPT-2 byte-level split + BPE without end_suffix: the dedicated bit-mask kernel takes every row; rows it hands back
+    // (multi-byte symbols, pieces longer than a window, skip-flagged elements) are redone by the generic kernel in list mode
+    const bool fast = call.op == OP_BPE && (c.P.spec.pat == PAT_GPT2 || c.P.spec.pat == PAT_GPT2_DIGITS) && c.P.mode == SPLIT_ISOLATED &&
+                      !c.P.repeat && c.P.max_splits == -1 && c.P.suffix_len == 0 && !(c.P.dbg_flags & 2);
+    if (fast) {
+        static bool fast_attr[64] = {};
+        if (!fast_attr[owner->device]) {
+            CU(cudaFuncSetAttribute(gpt2_bpe_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+            fast_attr[owner->device] = true;
+        }
+        static const int fast_ctas_env = [] { const char* e = getenv("B200TOK_FAST_CTAS"); return e ? atoi(e) : 0; }();
+        const int fast_per_sm = fast_ctas_env > 0 ? fast_ctas_env : (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (kFastSmem + 1024)));
+        const int fast_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * fast_per_sm);
+        gpt2_bpe_fast_kernel<<<fast_blocks, BLOCK_THREADS, kFastSmem, st>>>(c.P, c.row_cap);
+        if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
+        RowParams P2 = c.P;
+        P2.row_list = c.row_cap;
+        rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(P2);
+        owner->launches += 2;
+    } else {
+        if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
+        else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
+        else rows_kernel<OP_SPLIT><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
+        if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
+        ++owner->launches;
+    }
     if (call.op == OP_BPE) {
         GiantParams G{c.P.giants, c.P.status, c.P.giants_cap, c.P.chars, call.bpe->view(), call.bpe->suffix.p, c.P.suffix_len,
                       c.P.row_base, c.P.row_cnt, c.P.tmp_a, c.pool, (unsigned long long)c.pool_bytes, c.pool_used, c.P.status};

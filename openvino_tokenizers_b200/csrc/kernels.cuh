@@ -24,14 +24,14 @@ constexpr int NWORDS = (WIN + LA + 31) / 32 + 1;
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
-constexpr int kRowsSmemFixed = 128 + 1024 + 1024 + 2048;   // per-CTA tables in front of the per-warp state
+constexpr int kRowsSmemFixed = 128 + 1024;   // per-CTA tables in front of the per-warp state
 
 constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK = 0x03FF;
 
 enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2 };
 
 // status words (device int32 array)
-enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_WORDS = 8 };
+enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_WORDS = 8 };
 enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
 
 struct GiantItem { int32_t row, begin, end, slot; };
@@ -64,6 +64,8 @@ struct RowParams {
     // contiguous, increasing elements (verified by the host): a row's slot base follows from its first element's byte
     // offset, so the capacity kernel + scan are skipped:  base = begins[rb[row]] - direct_byte0 + (rb[row] - direct_elem0) * extra
     int32_t direct_base; int32_t direct_byte0; int32_t direct_elem0; int32_t direct_extra;
+    // list mode: process rows row_list[0 .. status[ST_NREDO]) (rows the fast kernel handed back) instead of [0, n_rows)
+    const int32_t* row_list;
 };
 
 struct __align__(16) WarpSmem {
@@ -565,11 +567,7 @@ __device__ __forceinline__ int gpt2_ascii_fused_window_v5(WarpSmem& S, const Bpe
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// GPT-2 (isolate) -> BPE, bit-mask form ("v7").  One pass over the window produces, per 32 positions, the class masks
-// as warp ballots (lane j keeps the masks of word j - 1; word -1 is the look-back); the piece-start predicate
-// (tok_core.cuh g2_starts, checked against PCRE2 through the closed form) is then evaluated once per WORD instead of
-// once per position; segments owning a mergeable pair are found with a carry chain over the reversed masks, and the
-// merge loop keeps each segment's live symbols / live pair keys as two 32-bit masks.
+// Helpers of the bit-mask GPT-2 -> BPE kernel (kernels_fast.cuh).
 //   lut32[c]: class bits below | one-byte symbol id << 12
 // ---------------------------------------------------------------------------------------------------------
 enum : uint32_t { V7_L = 1, V7_N = 2, V7_S = 4, V7_SP = 8, V7_AP = 16, V7_WALK = 32, V7_BAD = 64, V7_CONT = 128 };
@@ -602,216 +600,6 @@ __device__ __forceinline__ uint32_t ballot_bits(uint32_t g, uint32_t mask) {
 __device__ __forceinline__ uint32_t v7_below(int limit, int base) {
     const int r = limit - base;
     return r >= 32 ? FULL : r > 0 ? ((1u << r) - 1u) : 0u;
-}
-
-// Returns `send` = end of the complete segments (= how far the window advances; 0 => the first segment does not fit).
-// On return with complex_out == false, S.u.bp.ids[0 .. send) holds the final tokens of the window (-1 = merged away).
-__device__ __noinline__ int gpt2_bitmask_window(WarpSmem& S, const BpeTables& BT, const RowParams& P, const uint32_t* lut32,
-                                                   const uint32_t* pbits, const uint8_t* ascii_smem, int lane, int wlen, int end_rel,
-                                                   int nload, int lb, bool at_start, bool ascii, bool& complex_out) {
-    auto& bp = S.u.bp;
-    const uint8_t* B = S.B();
-    uint8_t* KC = reinterpret_cast<uint8_t*>(S.seg) + LBK;      // class bytes of non-ASCII windows (S.seg is otherwise unused here)
-    const bool digits = P.spec.pat == PAT_GPT2_DIGITS;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t* const pair_rank = BT.pair_rank;
-    const int32_t* const rank_newid = BT.merges.rank_newid;
-    const MergeTable MT = BT.merges;
-    if (!ascii) {
-        ClassTables T = P.cls;
-        T.ascii = ascii_smem;
-        for (int w = lane - lb; w < nload; w += 32) {
-            const uint8_t b = B[w];
-            uint8_t k;
-            if (b < 0x80) k = ascii_smem[b];
-            else if (is_cont_byte(b) && w > -lb) {
-                int j = w - 1;
-                while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
-                k = C_CONT;
-                if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
-            } else k = char_class(B, w, end_rel, T);
-            KC[w] = k;
-        }
-        __syncwarp();
-    }
-    // ---- pass 1: class masks, one-byte symbols, initial pair keys ----
-    uint32_t mL = 0, mN = 0, mS = 0, mSP = 0, mA2 = 0, mA3 = 0, mC = 0, mMB = 0, mF = 0;
-    bool complex = false;
-    const int nw = (nload + 31) >> 5;
-    const int it0 = lb > 0 ? -1 : 0;
-    const uint32_t span = (uint32_t)(nload + lb);
-    const uint8_t* bq = B + it0 * 32 + lane;                  // this lane's byte of the current word
-    int32_t* idq = bp.ids + it0 * 32 + lane;
-    uint32_t* keyq = bp.key + it0 * 32 + lane;
-    int w = it0 * 32 + lane;
-    for (int it = it0; it < nw; ++it, bq += 32, idq += 32, keyq += 32, w += 32) {
-        const bool valid = (uint32_t)(w + lb) < span;
-        const uint32_t c = *bq;
-        uint32_t g = lut32[c];
-        if (!ascii) g |= bq[KC - B] & (uint32_t)(C_L | C_N | C_S | C_CONT);
-        g = valid ? g : 0u;
-        const bool inwin = (uint32_t)w < (uint32_t)wlen;
-        if (inwin) *idq = (int32_t)(g >> V7_ID_SHIFT);
-        const uint32_t bL = ballot_bits(g, V7_L), bN = ballot_bits(g, V7_N), bS = ballot_bits(g, V7_S), bSP = ballot_bits(g, V7_SP);
-        const uint32_t bAP = ballot_bits(g, V7_AP);
-        uint32_t bA2 = 0, bA3 = 0, bC = 0, bMB = 0;
-        if (bAP) {
-            int cl = 0;
-            if (g & V7_AP) cl = gpt2_contraction_len(B, w, nload);
-            bA2 = __ballot_sync(FULL, cl == 2);
-            bA3 = __ballot_sync(FULL, cl == 3);
-        }
-        if (!ascii) {
-            bC = ballot_bits(g, V7_CONT);
-            bool mb = false;
-            if ((g & V7_S) && c >= 0x80 && !(g & V7_CONT)) {      // multi-byte whitespace: is the next character a non-space?
-                int j = w + 1;
-                while (j < nload && (KC[j] & C_CONT)) ++j;
-                mb = j < nload && !(KC[j] & C_S);
-            }
-            bMB = __ballot_sync(FULL, mb);
-        }
-        if (ballot_bits(g, V7_WALK | V7_BAD)) {
-            if (g & V7_BAD) complex = true;
-            else if ((g & V7_WALK) && w + 1 < nload) {            // could a longer token start here?  second-byte filter, then the walk
-                const uint32_t b1 = bq[1];
-                if ((__ldg(BT.pair_bits + 512 + 8 * c + (b1 >> 5)) >> (b1 & 31u)) & 1u) {
-                    int j = w;
-                    const int32_t t = trie_longest(BT.trie, B, j, nload);   // (even across a piece boundary -> serial path)
-                    if (t >= 0 && j != w + 1) complex = true;
-                }
-            }
-        }
-        bool fb = false;
-        if (inwin) {
-            const uint32_t p = bq[-1];
-            fb = (ascii || (p | c) < 0x80u) ? (((pbits[(p << 2) | (c >> 5)] >> (c & 31u)) & 1u) != 0u) : true;
-            if (fb) {
-                const uint32_t r = __ldg(pair_rank + ((p << 8) | c));
-                fb = r != kNoKey;
-                *keyq = (r << kPackedBirthBits) | (uint32_t)w;
-            }
-        }
-        const uint32_t bF = __ballot_sync(FULL, fb);
-        if (lane == it + 1) { mL = bL; mN = bN; mS = bS; mSP = bSP; mA2 = bA2; mA3 = bA3; mC = bC; mMB = bMB; mF = bF; }
-    }
-    complex_out = __any_sync(FULL, complex);
-    if (complex_out) return wlen;
-    // ---- pass 2: piece starts, one word per lane ----
-    const int word = lane - 1, base = word * 32;
-    G2Word W{mL, mN, mS, mSP, mA2, mA3, mC, mMB, word >= 0 ? v7_below(nload, base) : 0u};
-    G2Word PW;
-    PW.L = __shfl_up_sync(FULL, mL, 1); PW.N = __shfl_up_sync(FULL, mN, 1); PW.S = __shfl_up_sync(FULL, mS, 1);
-    PW.SP = __shfl_up_sync(FULL, mSP, 1);
-    uint32_t pok1 = __shfl_up_sync(FULL, g2_ok1(W), 1);
-    if (lane == 0) { PW.L = PW.N = PW.S = PW.SP = 0; pok1 = 0; }
-    const uint32_t bos = (word == 0 && at_start) ? 1u : 0u;
-    uint32_t c2, c3;
-    g2_contractions(W, pok1, bos, c2, c3);
-    uint32_t pc2 = __shfl_up_sync(FULL, c2, 1), pc3 = __shfl_up_sync(FULL, c3, 1);
-    if (lane == 0) { pc2 = 0; pc3 = 0; }
-    uint32_t nns = __shfl_down_sync(FULL, W.X & ~W.S, 1);
-    if (lane == 31) nns = 0;
-    uint32_t start = g2_starts(W, PW, c2, c3, pc2, pc3, nns, bos, digits);
-    start &= word >= 0 ? v7_below(wlen, base) : 0u;
-    if (word == 0) start |= 1u;
-    int send = wlen;
-    if (wlen != end_rel) {        // the last piece may continue beyond the window: redo it from its start in the next window
-        const int hb = start ? base + 31 - __clz(start) : -1;
-        send = __reduce_max_sync(FULL, hb);
-        start &= word >= 0 ? v7_below(send, base) : 0u;
-        if (send <= 0) return 0;
-    }
-    const uint32_t found = mF & ~start & (word >= 0 ? v7_below(send, base) : 0u);
-    if (word >= 0 && word < NWORDS) { S.segbits[word] = start; S.actbits[word] = found; }
-    // ---- pass 3: segments that own a mergeable pair.  In the bit-reversed word a segment's start is its top bit; adding the
-    // found bits to "all non-start bits" carries every found bit up to (and only to) its segment's start.
-    const uint32_t sr = __brev(start), fr = __brev(found), kk = ~sr;
-    const bool gen = (uint32_t)(fr + kk) < fr;                          // carry out of the word (towards lower positions)
-    const uint32_t gm = __ballot_sync(FULL, gen), pm = __ballot_sync(FULL, start == 0u);
-    uint32_t cin = 0;
-    if (lane < 31) {                                                    // carry in = a generating word above, reached through start-less words
-        const uint32_t up = gm >> (lane + 1), pr = pm >> (lane + 1);
-        const int t = __ffs(~pr) - 1;
-        cin = (up & (FULL >> (31 - t))) != 0u;
-    }
-    const uint32_t actst = __brev((fr + kk + cin) & sr);
-    uint32_t stx = start;                                               // starts + the end sentinel at `send`
-    if ((send >> 5) == word) stx |= 1u << (send & 31);
-    uint32_t nstx = __shfl_down_sync(FULL, stx, 1);
-    if (lane == 31) nstx = 0;
-    const uint32_t len2 = start & ~g2_fsr(stx, nstx, 1) & g2_fsr(stx, nstx, 2);
-    __syncwarp();
-    for (uint32_t a = actst & len2; a; a &= a - 1u) {                   // two symbols, one pair: done here
-        const int s = base + __ffs(a) - 1;
-        bp.ids[s] = __ldg(rank_newid + (bp.key[s + 1] >> kPackedBirthBits));
-        bp.ids[s + 1] = -1;
-    }
-    const uint32_t a3 = actst & ~len2;
-    const int cnt = __popc(a3);
-    const int incl = warp_incl_scan(cnt, lane);
-    const int nact = __shfl_sync(FULL, incl, 31);
-    {
-        int off = incl - cnt;
-        for (uint32_t a = a3; a; a &= a - 1u) S.act[off++] = (uint16_t)(base + __ffs(a) - 1);
-    }
-    __syncwarp();
-    // ---- pass 4: merge queue, one segment per lane, one merge per iteration ----
-    int head = 0, s = 0, merges = 0;
-    uint32_t alive = 0, km = 0;
-    bool have = false;
-    while (head < nact || __any_sync(FULL, have)) {
-        const uint32_t need = __ballot_sync(FULL, !have);
-        if (!have) {
-            const int qi = head + __popc(need & lt);
-            if (qi < nact) {
-                s = S.act[qi];
-                const int e = next_bit(S.segbits, s, send), n = e - s;
-                if (n > 32) {                                           // long run: serial loop over the whole segment
-                    const int c = bpe_merge_packed(MT, bp.ids + s, bp.key + s, n);
-                    for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
-                } else {
-                    const uint32_t mask = n == 32 ? FULL : ((1u << n) - 1u);
-                    km = g2_fsr(S.actbits[s >> 5], S.actbits[(s >> 5) + 1], s & 31) & mask;
-                    alive = mask;
-                    merges = 0;
-                    have = true;
-                }
-            }
-        }
-        head += __popc(need);
-        if (have) {
-            uint32_t best = kNoKey;
-            int bk = 0;
-            for (uint32_t m = km; m; m &= m - 1u) {
-                const int k = __ffs(m) - 1;
-                const uint32_t q = bp.key[s + k];
-                if (q < best) { best = q; bk = k; }
-            }
-            const int pl = 31 - __clz(alive & ((1u << bk) - 1u));       // left operand = nearest live symbol below
-            const int32_t nid = __ldg(rank_newid + (best >> kPackedBirthBits));
-            bp.ids[s + pl] = nid;
-            bp.ids[s + bk] = -1;
-            alive &= ~(1u << bk);
-            km &= ~((1u << bk) | (1u << pl));
-            ++merges;
-            const uint32_t birth = (uint32_t)(WIN + merges);
-            const uint32_t below = alive & ((1u << pl) - 1u);
-            if (below) {
-                int32_t r, v;
-                if (merge_find(MT, bp.ids[s + 31 - __clz(below)], nid, r, v)) { bp.key[s + pl] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << pl; }
-            }
-            const uint32_t above = alive & ~((2u << bk) - 1u);
-            if (above) {
-                const int nr = __ffs(above) - 1;
-                km &= ~(1u << nr);
-                int32_t r, v;
-                if (merge_find(MT, nid, bp.ids[s + nr], r, v)) { bp.key[s + nr] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << nr; }
-            }
-            if (!km) have = false;
-        }
-    }
-    return send;
 }
 
 // WordPiece for all kept segments (words) of a window: one lane per word, longest-match trie walks.
@@ -848,27 +636,25 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                            // [128]
     int32_t* bytesym_smem = reinterpret_cast<int32_t*>(smem_raw + 128);        // [256]
-    uint32_t* lut32_smem = reinterpret_cast<uint32_t*>(smem_raw + 128 + 1024); // [256] class bits | one-byte symbol id (v7)
-    uint32_t* pbits_smem = lut32_smem + 256;                                   // [512] mergeable ASCII byte pairs (v7)
     WarpSmem* warps = reinterpret_cast<WarpSmem*>(smem_raw + kRowsSmemFixed);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpSmem& S = warps[wib];
+    const bool listed = P.row_list != nullptr;
+    if (listed && P.status[ST_NREDO] == 0) return;
     if (threadIdx.x < 128) ascii_smem[threadIdx.x] = P.cls.ascii[threadIdx.x];
-    if (OP == OP_BPE) {
-        bytesym_smem[threadIdx.x] = P.bpe.byte_sym[threadIdx.x];
-        lut32_smem[threadIdx.x] = v7_lut_entry(P, threadIdx.x);
-        pbits_smem[threadIdx.x] = P.bpe.pair_bits[threadIdx.x];
-        pbits_smem[threadIdx.x + 256] = P.bpe.pair_bits[threadIdx.x + 256];
-    }
+    if (OP == OP_BPE) bytesym_smem[threadIdx.x] = P.bpe.byte_sym[threadIdx.x];
     __syncthreads();
     BpeTables BT = P.bpe;
     BT.byte_sym = bytesym_smem;
 
     for (;;) {
         int row = 0;
-        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+        if (lane == 0) row = atomicAdd(&P.status[listed ? ST_TICKET2 : ST_TICKET], 1);
         row = __shfl_sync(0xFFFFFFFFu, row, 0);
-        if (row >= P.n_rows) break;
+        if (listed) {
+            if (row >= P.status[ST_NREDO]) break;
+            row = P.row_list[row];
+        } else if (row >= P.n_rows) break;
         const int p0 = P.rb[row], p1 = P.re[row];
         int64_t base;
         if (P.direct_base) {
@@ -908,8 +694,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
                 const int end_rel = ee - pos;
                 const int wlen = end_rel < WIN ? end_rel : WIN;
                 int ns = 0, advance = 0;
-                bool keys_ready = false, complex_win = false, v7_done = false;
-                int v7_send = 0;
+                bool keys_ready = false, complex_win = false;
                 const bool fits = !(whole && end_rel > WIN) && !(OP == OP_BPE && P.suffix_len > 0);
                 if (fits) {
                     const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
@@ -946,20 +731,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
                         __syncwarp();
                     } else {
                         if ((P.spec.pat == PAT_GPT2 || P.spec.pat == PAT_GPT2_DIGITS) && P.mode == SPLIT_ISOLATED && !P.repeat && P.max_splits == -1) {
-                            if (OP == OP_BPE && !(P.dbg_flags & 2)) {
-                                v7_send = gpt2_bitmask_window(S, BT, P, lut32_smem, pbits_smem, ascii_smem, lane, wlen, end_rel, nload, lb, pos == eb,
-                                                              all_ascii, complex_win);
-                                v7_done = !complex_win;
-                                advance = v7_send;
-                            }
-                            if (!v7_done) {
-                                complex_win = false;
-                                if (OP == OP_BPE && all_ascii) {
-                                    ns = gpt2_ascii_fused_window_v5(S, BT, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance, complex_win);
-                                    keys_ready = true;
-                                } else
-                                    ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
-                            }
+                            if (OP == OP_BPE && all_ascii) {
+                                ns = gpt2_ascii_fused_window_v5(S, BT, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance, complex_win);
+                                keys_ready = true;
+                            } else
+                                ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
                         } else
                             ns = split_window(S, P, ascii_smem, lane, wlen, end_rel, nload, advance);
                     }
@@ -1042,8 +818,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
                     }
                 } else {
                     // piece phase: every kept segment becomes tokens in S.u.bp.ids[start..], dead slots = -1
-                    const int send = v7_done ? v7_send : (S.seg[ns] & POS_MASK);
-                    if (OP == OP_BPE) { if (!v7_done) bpe_window_pieces(S, BT, P, lane, ns, send, whole, keys_ready, complex_win); }
+                    const int send = S.seg[ns] & POS_MASK;
+                    if (OP == OP_BPE) bpe_window_pieces(S, BT, P, lane, ns, send, whole, keys_ready, complex_win);
                     else wordpiece_window_pieces(S, P, lane, ns, whole);
                     __syncwarp();
                     // output phase: position-parallel compaction of the live tokens into the row slot

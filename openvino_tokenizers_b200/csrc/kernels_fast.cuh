@@ -1,0 +1,382 @@
+// kernels_fast.cuh — the dedicated kernel of the headline path: RegexSplit(GPT-2 byte-level pattern, isolate) ->
+// BPETokenizer (reference src/regex_split.cpp:287-309 + src/bpe_tokenizer.cpp:196-339) for rows whose pieces fit a
+// 512-byte window and symbolise byte by byte.  Same work decomposition as rows_kernel (one warp per row, 512-byte
+// windows, row-local output slots), but only the bit-mask formulation lives here, so the register budget is spent on
+// it alone.  Anything it cannot finish exactly — a window with a multi-byte symbol, a dropped byte, a piece longer
+// than a window, a skip-flagged element — makes the warp put the row on a redo list that rows_kernel<OP_BPE>
+// (kernels.cuh) processes afterwards from scratch.
+//
+// Per window:
+//   pass 1  position-parallel: byte -> lut32 (class bits | one-byte symbol id); ids[] stored; one warp ballot per class
+//           gives the class masks of 32 positions (lane 0 parks them in shared memory); mergeable (previous, this)
+//           byte pairs are found with a 2 KB bitmap and only those fetch their rank (initial key) from the L2 table
+//   pass 2  one WORD per lane: tok_core.cuh g2_starts evaluates the piece-start predicate for 32 positions at once
+//   pass 3  segments owning a mergeable pair: carry chain over the bit-reversed masks; two-symbol segments finish
+//           here, longer ones go to a queue
+//   pass 4  merge queue, one segment per lane per round; live symbols / live keys are two 32-bit masks
+//   emit    position-parallel ballot compaction of the surviving ids into the row slot
+#pragma once
+#include "kernels.cuh"
+
+namespace b200tok {
+
+constexpr int kMStride = NWORDS + 4;   // pass 1 writes four words per iteration
+
+struct __align__(16) FastSmem {
+    uint8_t raw_bytes[LBK + WBYTES];
+    uint8_t raw_kc[LBK + WBYTES];            // class bytes, non-ASCII windows only
+    uint16_t act[WIN / 3 + 10];
+    uint32_t segbits[NWORDS], actbits[NWORDS];
+    uint32_t m[9][kMStride];                 // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F
+    int32_t ids[WIN];
+    uint32_t key[WIN];
+    __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }
+    __device__ __forceinline__ uint8_t* KC() { return raw_kc + LBK; }
+};
+enum : int { M_L = 0, M_N, M_S, M_SP, M_A2, M_A3, M_CONT, M_MB, M_F };
+
+constexpr int kFastSmemFixed = 128 + 1024 + 2048;   // ascii classes, lut32, pair bitmap
+constexpr size_t kFastSmem = kFastSmemFixed + WARPS_PER_BLOCK * sizeof(FastSmem);
+
+// One window.  Returns `send` (how far the window advances; 0 => the first piece does not fit) or -1 when the window
+// needs the generic path.  On success S.ids[0 .. send) holds the window's tokens (-1 = merged away).
+__device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, const uint32_t* lut32, const uint32_t* pbits,
+                                           const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
+                                           bool ascii) {
+    const uint8_t* B = S.B();
+    const uint32_t lt = (1u << lane) - 1u;
+    const int lb = off < LBK ? off : LBK;           // look-back bytes staged before the window (off = window start - element start)
+    if (!ascii) {
+        uint8_t* KC = S.KC();
+        ClassTables T = P.cls;
+        T.ascii = ascii_smem;
+        for (int w = lane - lb; w < nload; w += 32) {
+            const uint8_t b = B[w];
+            uint8_t k;
+            if (b < 0x80) k = ascii_smem[b];
+            else if (is_cont_byte(b) && w > -lb) {
+                int j = w - 1;
+                while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
+                k = C_CONT;
+                if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
+            } else k = char_class(B, w, end_rel, T);
+            KC[w] = k;
+        }
+        __syncwarp();
+    }
+    // ---- pass 1: four words (stride 32) per iteration ----
+    bool complex = false;
+    const int nw = (nload + 31) >> 5;
+    {
+        const int it0 = lb > 0 ? -1 : 0;
+        if (it0 == 0 && lane < 9) S.m[lane][0] = 0u;
+        const uint32_t span = (uint32_t)(nload + lb);
+        const uint32_t* const pair_rank = P.bpe.pair_rank;
+        const uint16_t* const rank16 = reinterpret_cast<const uint16_t*>(P.bpe.pair_bits + 2560);
+        for (int it = it0; it < nw; it += 4) {
+            const int w0 = it * 32 + lane;
+            const uint8_t* bq = B + w0;                           // this lane's byte of word `it`
+            uint32_t c[4], g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                c[u] = bq[32 * u];
+                g[u] = lut32[c[u]];
+                if (!ascii) g[u] |= bq[32 * u + sizeof(S.raw_bytes)] & (uint32_t)(C_L | C_N | C_S | C_CONT);   // raw_kc follows raw_bytes
+                g[u] = ((uint32_t)(w0 + 32 * u + lb) < span) ? g[u] : 0u;
+                if ((uint32_t)(w0 + 32 * u) < (uint32_t)wlen) S.ids[w0 + 32 * u] = (int32_t)(g[u] >> V7_ID_SHIFT);
+            }
+            uint32_t* const mm = &S.m[0][it + 1];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t bL = ballot_bits(g[u], V7_L), bN = ballot_bits(g[u], V7_N), bS = ballot_bits(g[u], V7_S), bSP = ballot_bits(g[u], V7_SP);
+                if (lane == 0) { mm[M_L * kMStride + u] = bL; mm[M_N * kMStride + u] = bN; mm[M_S * kMStride + u] = bS; mm[M_SP * kMStride + u] = bSP; }
+            }
+            const uint32_t gor = g[0] | g[1] | g[2] | g[3];
+            if (ballot_bits(gor, V7_AP)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int cl = 0;
+                    if (g[u] & V7_AP) cl = gpt2_contraction_len(B, w0 + 32 * u, nload);
+                    const uint32_t bA2 = __ballot_sync(FULL, cl == 2), bA3 = __ballot_sync(FULL, cl == 3);
+                    if (lane == 0) { mm[M_A2 * kMStride + u] = bA2; mm[M_A3 * kMStride + u] = bA3; }
+                }
+            } else if (lane < 4) { mm[M_A2 * kMStride + lane] = 0u; mm[M_A3 * kMStride + lane] = 0u; }
+            if (!ascii) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t bC = ballot_bits(g[u], V7_CONT);
+                    bool mb = false;
+                    if ((g[u] & V7_S) && c[u] >= 0x80 && !(g[u] & V7_CONT)) {      // multi-byte whitespace: is the next character a non-space?
+                        const uint8_t* KC = S.KC();
+                        int j = w0 + 32 * u + 1;
+                        while (j < nload && (KC[j] & C_CONT)) ++j;
+                        mb = j < nload && !(KC[j] & C_S);
+                    }
+                    const uint32_t bMB = __ballot_sync(FULL, mb);
+                    if (lane == 0) { mm[M_CONT * kMStride + u] = bC; mm[M_MB * kMStride + u] = bMB; }
+                }
+            }
+            if (ballot_bits(gor, V7_WALK | V7_BAD)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int w = w0 + 32 * u;
+                    if (g[u] & V7_BAD) complex = true;
+                    else if ((g[u] & V7_WALK) && w + 1 < nload) {        // could a longer token start here?  second-byte filter, then the walk
+                        const uint32_t b1 = bq[32 * u + 1];
+                        if ((__ldg(P.bpe.pair_bits + 512 + 8 * c[u] + (b1 >> 5)) >> (b1 & 31u)) & 1u) {
+                            int j = w;
+                            const int32_t t = trie_longest(P.bpe.trie, B, j, nload);   // (even across a piece boundary -> generic path)
+                            if (t >= 0 && j != w + 1) complex = true;
+                        }
+                    }
+                }
+            }
+            // mergeable (previous byte, this byte) pairs: ASCII pairs from the compact u16 rank table, others from the full one
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int w = w0 + 32 * u;
+                bool fb = false;
+                if ((uint32_t)w < (uint32_t)wlen) {
+                    const uint32_t p = bq[32 * u - 1];
+                    uint32_t r;
+                    if (ascii || (p | c[u]) < 0x80u) {
+                        r = __ldg(rank16 + ((p << 7) | c[u]));
+                        if (r >= 0xFFFEu) r = r == 0xFFFFu ? kNoKey : __ldg(pair_rank + ((p << 8) | c[u]));
+                    } else r = __ldg(pair_rank + ((p << 8) | c[u]));
+                    fb = r != kNoKey;
+                    if (fb) S.key[w] = (r << kPackedBirthBits) | (uint32_t)w;
+                }
+                const uint32_t bF = __ballot_sync(FULL, fb);
+                if (lane == 0) mm[M_F * kMStride + u] = bF;
+            }
+        }
+    }
+    if (__any_sync(FULL, complex)) return -1;
+    __syncwarp();
+    // ---- pass 2: piece starts, lane = word ----
+    const int word = lane, base = lane * 32;
+    const bool live = word < nw;
+    G2Word W{0, 0, 0, 0, 0, 0, 0, 0, 0}, PW{0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t found = 0;
+    if (live) {
+        W.L = S.m[M_L][word + 1]; W.N = S.m[M_N][word + 1]; W.S = S.m[M_S][word + 1]; W.SP = S.m[M_SP][word + 1];
+        W.A2 = S.m[M_A2][word + 1]; W.A3 = S.m[M_A3][word + 1];
+        PW.L = S.m[M_L][word]; PW.N = S.m[M_N][word]; PW.S = S.m[M_S][word]; PW.SP = S.m[M_SP][word];
+        found = S.m[M_F][word + 1];
+        if (!ascii) { W.CONT = S.m[M_CONT][word + 1]; W.MB = S.m[M_MB][word + 1]; }
+        W.X = v7_below(nload, base);
+    }
+    const uint32_t bos = (word == 0 && off == 0) ? 1u : 0u;
+    uint32_t c2, c3;
+    g2_contractions(W, g2_ok1(PW), bos, c2, c3);
+    uint32_t pc2 = __shfl_up_sync(FULL, c2, 1), pc3 = __shfl_up_sync(FULL, c3, 1);
+    if (lane == 0) {      // contractions starting in the look-back word (their apostrophe is at most 3 positions back)
+        pc2 = 0; pc3 = 0;
+        if (lb > 0) {
+            G2Word LBW{PW.L, PW.N, PW.S, PW.SP, S.m[M_A2][0], S.m[M_A3][0], 0, 0, 0};
+            g2_contractions(LBW, 0u, off <= LBK ? 1u << (32 - off) : 0u, pc2, pc3);   // (element start inside the look-back)
+        }
+    }
+    const uint32_t nns = __shfl_down_sync(FULL, W.X & ~W.S, 1);
+    uint32_t start = g2_starts(W, PW, c2, c3, pc2, pc3, lane == 31 ? 0u : nns, bos, P.spec.pat == PAT_GPT2_DIGITS);
+    start &= v7_below(wlen, base);
+    if (word == 0) start |= 1u;
+    int send = wlen;
+    if (wlen != end_rel) {        // the last piece may continue beyond the window: redo it from its start in the next window
+        const int hb = start ? base + 31 - __clz(start) : -1;
+        send = __reduce_max_sync(FULL, hb);
+        start &= v7_below(send, base);
+        if (send <= 0) return 0;
+    }
+    found &= ~start & v7_below(send, base);
+    if (word < NWORDS) { S.segbits[word] = start; S.actbits[word] = found; }
+    // ---- pass 3: segments that own a mergeable pair.  In the bit-reversed word a segment's start is its top bit; adding the
+    // found bits to "all non-start bits" carries every found bit up to (and only to) its segment's start.
+    const uint32_t sr = __brev(start), fr = __brev(found), kk = ~sr;
+    const bool gen = (uint32_t)(fr + kk) < fr;                          // carry out of the word (towards lower positions)
+    const uint32_t gm = __ballot_sync(FULL, gen), pm = __ballot_sync(FULL, start == 0u);
+    uint32_t cin = 0;
+    if (lane < 31) {                                                    // carry in = a generating word above, reached through start-less words
+        const uint32_t up = gm >> (lane + 1), pr = pm >> (lane + 1);
+        const int t = __ffs(~pr) - 1;
+        cin = (up & (FULL >> (31 - t))) != 0u;
+    }
+    const uint32_t actst = __brev((fr + kk + cin) & sr);
+    uint32_t stx = start;                                               // starts + the end sentinel at `send`
+    if ((send >> 5) == word) stx |= 1u << (send & 31);
+    const uint32_t nstx0 = __shfl_down_sync(FULL, stx, 1);
+    const uint32_t nstx = lane == 31 ? 0u : nstx0;
+    const uint32_t len2 = start & ~g2_fsr(stx, nstx, 1) & g2_fsr(stx, nstx, 2);
+    const int32_t* const rank_newid = P.bpe.merges.rank_newid;
+    __syncwarp();
+    const int32_t nb = P.bpe.newid_base;
+    for (uint32_t a = actst & len2; a; a &= a - 1u) {                   // two symbols, one pair: done here
+        const int s = base + __ffs(a) - 1;
+        const uint32_t r = S.key[s + 1] >> kPackedBirthBits;
+        S.ids[s] = nb >= 0 ? nb + (int32_t)r : __ldg(rank_newid + r);
+        S.ids[s + 1] = -1;
+    }
+    const uint32_t a3 = actst & ~len2;
+    const int cnt = __popc(a3);
+    const int incl = warp_incl_scan(cnt, lane);
+    const int nact = __shfl_sync(FULL, incl, 31);
+    {
+        int off = incl - cnt;
+        for (uint32_t a = a3; a; a &= a - 1u) S.act[off++] = (uint16_t)(base + __ffs(a) - 1);
+    }
+    __syncwarp();
+    // ---- pass 4: merge queue, one segment per lane, one merge per iteration ----
+    const MergeTable MT = P.bpe.merges;
+    int head = 0, s = 0, merges = 0;
+    uint32_t alive = 0, km = 0;
+    bool have = false;
+    while (head < nact || __any_sync(FULL, have)) {
+        const uint32_t need = __ballot_sync(FULL, !have);
+        if (!have) {
+            const int qi = head + __popc(need & lt);
+            if (qi < nact) {
+                s = S.act[qi];
+                const int e = next_bit(S.segbits, s, send), n = e - s;
+                if (n > 32) {                                           // long run: serial loop over the whole segment
+                    const int c = bpe_merge_packed(MT, S.ids + s, S.key + s, n);
+                    for (int t = s + c; t < e; ++t) S.ids[t] = -1;
+                } else {
+                    const uint32_t mask = n == 32 ? FULL : ((1u << n) - 1u);
+                    km = g2_fsr(S.actbits[s >> 5], S.actbits[(s >> 5) + 1], s & 31) & mask;
+                    alive = mask;
+                    merges = 0;
+                    have = true;
+                }
+            }
+        }
+        head += __popc(need);
+        if (have) {
+            uint32_t best = kNoKey;
+            int bk = 0;
+            for (uint32_t m = km; m; m &= m - 1u) {
+                const int k = __ffs(m) - 1;
+                const uint32_t q = S.key[s + k];
+                if (q < best) { best = q; bk = k; }
+            }
+            const int pl = 31 - __clz(alive & ((1u << bk) - 1u));       // left operand = nearest live symbol below
+            const int32_t nid = nb >= 0 ? nb + (int32_t)(best >> kPackedBirthBits) : __ldg(rank_newid + (best >> kPackedBirthBits));
+            S.ids[s + pl] = nid;
+            S.ids[s + bk] = -1;
+            alive &= ~(1u << bk);
+            km &= ~((1u << bk) | (1u << pl));
+            ++merges;
+            const uint32_t birth = (uint32_t)(WIN + merges);
+            const uint32_t below = alive & ((1u << pl) - 1u);
+            if (below) {
+                int32_t r, v;
+                if (merge_find(MT, S.ids[s + 31 - __clz(below)], nid, r, v)) { S.key[s + pl] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << pl; }
+            }
+            const uint32_t above = alive & ~((2u << bk) - 1u);
+            if (above) {
+                const int nr = __ffs(above) - 1;
+                km &= ~(1u << nr);
+                int32_t r, v;
+                if (merge_find(MT, nid, S.ids[s + nr], r, v)) { S.key[s + nr] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << nr; }
+            }
+            if (!km) have = false;
+        }
+    }
+    __syncwarp();
+    return send;
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 4) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* ascii_smem = smem_raw;                                            // [128]
+    uint32_t* lut32_smem = reinterpret_cast<uint32_t*>(smem_raw + 128);        // [256]
+    uint32_t* pbits_smem = lut32_smem + 256;                                   // [512]
+    FastSmem* warps = reinterpret_cast<FastSmem*>(smem_raw + kFastSmemFixed);
+    const int lane = threadIdx.x & 31;
+    FastSmem& S = warps[threadIdx.x >> 5];
+    if (threadIdx.x < 128) ascii_smem[threadIdx.x] = P.cls.ascii[threadIdx.x];
+    lut32_smem[threadIdx.x] = v7_lut_entry(P, threadIdx.x);
+    pbits_smem[threadIdx.x] = P.bpe.pair_bits[threadIdx.x];
+    pbits_smem[threadIdx.x + 256] = P.bpe.pair_bits[threadIdx.x + 256];
+    __syncthreads();
+    const uint32_t ltm = (1u << lane) - 1u;
+
+    for (;;) {
+        int row = 0;
+        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+        row = __shfl_sync(FULL, row, 0);
+        if (row >= P.n_rows) break;
+        const int p0 = P.rb[row], p1 = P.re[row];
+        int64_t base;
+        if (P.direct_base) {
+            base = p1 > p0 ? (int64_t)(P.begins[p0] - P.direct_byte0) + (int64_t)(p0 - P.direct_elem0) * P.direct_extra : 0;
+            if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
+        } else base = P.row_base[row];
+        int emitted = 0;
+        bool redo = false;
+        for (int p = p0; p < p1 && !redo; ++p) {
+            const int eb = P.begins[p], ee = P.ends[p];
+            if (P.skips && P.skips[p]) { redo = true; break; }
+            int pos = eb;
+            while (pos < ee) {
+                const int end_rel = ee - pos;
+                const int wlen = end_rel < WIN ? end_rel : WIN;
+                const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
+                const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
+                uint32_t hibits = 0;
+                const uint8_t* src = P.chars + pos - lb;
+                if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
+                    // 16-byte vector loads; the last quad may read up to 15 bytes past the element (padded chars allocation)
+                    uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
+                    const int nq = (lb + nload + 15) >> 4;
+                    for (int q = lane; q < nq; q += 32) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                        dst[q] = v;
+                        if ((q << 4) + 16 <= lb + nload) hibits |= v.x | v.y | v.z | v.w;
+                        else {
+                            const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+                            for (int t = 0; t < 16; ++t) if ((q << 4) + t < lb + nload) hibits |= (ww[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
+                        }
+                    }
+                } else {
+                    for (int w = lane - lb; w < nload; w += 32) {
+                        const uint8_t bb = __ldg(P.chars + pos + w);
+                        S.B()[w] = bb;
+                        hibits |= bb;
+                    }
+                }
+                const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
+                __syncwarp();
+                const int send = fast_window(S, P, lut32_smem, pbits_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                if (send <= 0) { redo = true; break; }
+                if (base + emitted + send > P.tmp_cap) {
+                    if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                } else {
+                    int32_t* outp = P.tmp_a + base + emitted;
+                    int n_out = 0;
+                    for (int w = lane; w - lane < send; w += 128) {
+                        int32_t tok[4];
+                        uint32_t m[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) tok[u] = (w + 32 * u) < send ? S.ids[w + 32 * u] : -1;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
+                            n_out += __popc(m[u]);
+                        }
+                    }
+                    emitted += n_out;
+                }
+                __syncwarp();
+                pos += send;
+            }
+        }
+        if (lane == 0) {
+            if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
+            else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = 0; }
+        }
+    }
+}
+
+}  // namespace b200tok

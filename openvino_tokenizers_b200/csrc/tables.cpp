@@ -209,6 +209,9 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
         while (out.slots[h].left != kEmptyKey) h = (h + 1) & out.mask;
         out.slots[h] = MergeSlot{l, r, kv.second.first, kv.second.second};
     }
+    out.newid_base = M > 0 ? out.rank_newid[0] : -1;
+    for (int64_t r = 0; r < M && out.newid_base >= 0; ++r)
+        if (out.rank_newid[(size_t)r] != out.newid_base + (int32_t)r) out.newid_base = -1;
     // direct table for the initial pairs of one-byte symbols: sym1(b) is what the position-parallel symbolisation
     // assigns to byte b when no longer token starts there (the one-byte token, else the byte-fallback / unk id)
     out.pair_rank.assign(65536, kNoKey);
@@ -227,7 +230,17 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
         }
     // [0, 512): mergeable ASCII byte pairs; [512, 512 + 2048): for every first byte, the second bytes that continue a
     // token of the symbolisation trie (bit b1 of words [512 + 8 * b0, +8)) — lets the window kernel skip trie walks
-    out.pair_bits.assign(512 + 2048, 0u);
+    // [2560, 2560 + 8192): ranks of the ASCII pairs as u16 (index b0 << 7 | b1; 0xFFFF = none, 0xFFFE = rank too large for
+    // 16 bits, look in pair_rank) — 32 KB, stays L1-resident in the window kernel
+    out.pair_bits.assign(512 + 2048 + 8192, 0u);
+    {
+        uint16_t* r16 = reinterpret_cast<uint16_t*>(out.pair_bits.data() + 2560);
+        for (int b0 = 0; b0 < 128; ++b0)
+            for (int b1 = 0; b1 < 128; ++b1) {
+                const uint32_t r = out.pair_rank[(size_t)(b0 << 8 | b1)];
+                r16[b0 << 7 | b1] = r == kNoKey ? (uint16_t)0xFFFF : r >= 0xFFFEu ? (uint16_t)0xFFFE : (uint16_t)r;
+            }
+    }
     for (int b0 = 0; b0 < 256; ++b0) {
         const int32_t node = out.trie.root_child[b0];
         if (node < 0) continue;

@@ -42,6 +42,7 @@ struct HostBpe {
     std::vector<int32_t> rank_newid;
     std::vector<uint32_t> pair_rank;
     std::vector<uint32_t> pair_bits;
+    int32_t newid_base = -1;
     uint32_t mask = 0;
     std::string end_suffix;
     int32_t unk_id = -1;
@@ -49,7 +50,7 @@ struct HostBpe {
     int64_t n_duplicate_products = 0;   // merges whose product token another merge also produces (tie hazard)
     bool bytes_only = false;            // every byte symbolises without a trie walk
     BpeTables view() const {
-        return BpeTables{byte_sym.data(), byte_miss.data(), pair_rank.data(), trie.view(), MergeTable{slots.data(), mask, rank_newid.data()}, pair_bits.data()};
+        return BpeTables{byte_sym.data(), byte_miss.data(), pair_rank.data(), trie.view(), MergeTable{slots.data(), mask, rank_newid.data()}, pair_bits.data(), newid_base};
     }
 };
 // returns B200TOK_OK or an error code (message in err)

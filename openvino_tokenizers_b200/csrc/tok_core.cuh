@@ -622,7 +622,8 @@ struct BpeTables {
     FlatTrie trie;
     MergeTable merges;
     const uint32_t* pair_bits; // [512] bit (b0 << 7 | b1) set iff pair_rank[b0 << 8 | b1] != kNoKey, for b0, b1 < 128;
-                               // then [2048]: bit (b0 << 8 | b1) set iff the trie has a token prefix b0 b1
+                               // then [2048]: bit (b0 << 8 | b1) set iff the trie has a token prefix b0 b1; then the u16 ASCII rank table
+    int32_t newid_base;        // >= 0: the token produced by the merge of rank r is newid_base + r (vocab in merge order); -1: use rank_newid
 };
 constexpr int32_t kSymWalk = -2;
 
