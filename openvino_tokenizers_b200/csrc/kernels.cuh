@@ -961,10 +961,22 @@ __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, 
         }
         if (!row_flag[r]) {
             if (dst + ext > out_cap) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
-            for (int t = lane; t < ext; t += 32) {
-                out_a[dst + t] = tmp_a[src + t];
-                if (out_b) out_b[dst + t] = tmp_b[src + t];
-                if (out_c) out_c[dst + t] = tmp_c[src + t];
+            if (!out_b && !out_c) {            // ids only: four independent loads in flight per lane
+                const int32_t* sp = tmp_a + src;
+                int32_t* dp = out_a + dst;
+                for (int t = lane; t < ext; t += 128) {
+                    int32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < ext) ? __ldcs(sp + t + 32 * u) : 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (t + 32 * u < ext) dp[t + 32 * u] = v[u];
+                }
+            } else {
+                for (int t = lane; t < ext; t += 32) {
+                    out_a[dst + t] = tmp_a[src + t];
+                    if (out_b) out_b[dst + t] = tmp_b[src + t];
+                    if (out_c) out_c[dst + t] = tmp_c[src + t];
+                }
             }
         } else {
             for (int t0 = 0; t0 < ext; t0 += 32) {

@@ -22,48 +22,48 @@ namespace b200tok {
 
 constexpr int kMStride = NWORDS + 4;   // pass 1 writes four words per iteration
 
+template <class IdT>
 struct __align__(16) FastSmem {
     uint8_t raw_bytes[LBK + WBYTES];
-    uint8_t raw_kc[LBK + WBYTES];            // class bytes, non-ASCII windows only
-    uint16_t act[WIN / 3 + 10];
     uint32_t segbits[NWORDS], actbits[NWORDS];
     uint32_t m[9][kMStride];                 // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F
-    int32_t ids[WIN];
+    IdT ids[WIN];                            // symbol per position; kDead = merged away
     uint32_t key[WIN];
     __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }
-    __device__ __forceinline__ uint8_t* KC() { return raw_kc + LBK; }
+    __device__ __forceinline__ uint16_t* act() { return reinterpret_cast<uint16_t*>(&m[0][0]); }   // merge queue; the masks are consumed by then
+    static constexpr IdT kDead = (IdT)-1;
 };
+static_assert(sizeof(uint32_t) * 9 * kMStride >= sizeof(uint16_t) * (WIN / 3 + 10), "merge queue must fit the mask area");
 enum : int { M_L = 0, M_N, M_S, M_SP, M_A2, M_A3, M_CONT, M_MB, M_F };
 
 constexpr int kFastSmemFixed = 128 + 1024 + 2048;   // ascii classes, lut32, pair bitmap
-constexpr size_t kFastSmem = kFastSmemFixed + WARPS_PER_BLOCK * sizeof(FastSmem);
+template <class IdT> constexpr size_t fast_smem_bytes() { return kFastSmemFixed + WARPS_PER_BLOCK * sizeof(FastSmem<IdT>); }
+
+// Class bits of byte position w of a non-ASCII window: continuation bytes carry their owner's class plus C_CONT.
+__device__ __forceinline__ uint32_t fast_byte_class(const uint8_t* B, int w, int lo, int end_rel, const ClassTables& T) {
+    const uint8_t b = B[w];
+    if (b < 0x80) return T.ascii[b];
+    if (is_cont_byte(b) && w > lo) {
+        int j = w - 1;
+        while (j >= lo && j > w - 4 && is_cont_byte(B[j])) --j;
+        uint32_t k = C_CONT;
+        if (j >= lo && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
+        return k;
+    }
+    return char_class(B, w, end_rel, T);
+}
 
 // One window.  Returns `send` (how far the window advances; 0 => the first piece does not fit) or -1 when the window
 // needs the generic path.  On success S.ids[0 .. send) holds the window's tokens (-1 = merged away).
-__device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, const uint32_t* lut32, const uint32_t* pbits,
+template <class IdT>
+__device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32, const uint32_t* pbits,
                                            const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
                                            bool ascii) {
     const uint8_t* B = S.B();
     const uint32_t lt = (1u << lane) - 1u;
     const int lb = off < LBK ? off : LBK;           // look-back bytes staged before the window (off = window start - element start)
-    if (!ascii) {
-        uint8_t* KC = S.KC();
-        ClassTables T = P.cls;
-        T.ascii = ascii_smem;
-        for (int w = lane - lb; w < nload; w += 32) {
-            const uint8_t b = B[w];
-            uint8_t k;
-            if (b < 0x80) k = ascii_smem[b];
-            else if (is_cont_byte(b) && w > -lb) {
-                int j = w - 1;
-                while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
-                k = C_CONT;
-                if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
-            } else k = char_class(B, w, end_rel, T);
-            KC[w] = k;
-        }
-        __syncwarp();
-    }
+    ClassTables T = P.cls;
+    T.ascii = ascii_smem;
     // ---- pass 1: four words (stride 32) per iteration ----
     bool complex = false;
     const int nw = (nload + 31) >> 5;
@@ -81,9 +81,10 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
             for (int u = 0; u < 4; ++u) {
                 c[u] = bq[32 * u];
                 g[u] = lut32[c[u]];
-                if (!ascii) g[u] |= bq[32 * u + sizeof(S.raw_bytes)] & (uint32_t)(C_L | C_N | C_S | C_CONT);   // raw_kc follows raw_bytes
-                g[u] = ((uint32_t)(w0 + 32 * u + lb) < span) ? g[u] : 0u;
-                if ((uint32_t)(w0 + 32 * u) < (uint32_t)wlen) S.ids[w0 + 32 * u] = (int32_t)(g[u] >> V7_ID_SHIFT);
+                const bool valid = (uint32_t)(w0 + 32 * u + lb) < span;
+                if (!ascii && valid && c[u] >= 0x80) g[u] |= fast_byte_class(B, w0 + 32 * u, -lb, end_rel, T) & (uint32_t)(C_L | C_N | C_S | C_CONT);
+                g[u] = valid ? g[u] : 0u;
+                if ((uint32_t)(w0 + 32 * u) < (uint32_t)wlen) S.ids[w0 + 32 * u] = (IdT)(g[u] >> V7_ID_SHIFT);
             }
             uint32_t* const mm = &S.m[0][it + 1];
 #pragma unroll
@@ -107,10 +108,9 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
                     const uint32_t bC = ballot_bits(g[u], V7_CONT);
                     bool mb = false;
                     if ((g[u] & V7_S) && c[u] >= 0x80 && !(g[u] & V7_CONT)) {      // multi-byte whitespace: is the next character a non-space?
-                        const uint8_t* KC = S.KC();
                         int j = w0 + 32 * u + 1;
-                        while (j < nload && (KC[j] & C_CONT)) ++j;
-                        mb = j < nload && !(KC[j] & C_S);
+                        while (j < nload && is_cont_byte(B[j])) ++j;
+                        mb = j < nload && !(fast_byte_class(B, j, -lb, end_rel, T) & C_S);
                     }
                     const uint32_t bMB = __ballot_sync(FULL, mb);
                     if (lane == 0) { mm[M_CONT * kMStride + u] = bC; mm[M_MB * kMStride + u] = bMB; }
@@ -213,8 +213,8 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
     for (uint32_t a = actst & len2; a; a &= a - 1u) {                   // two symbols, one pair: done here
         const int s = base + __ffs(a) - 1;
         const uint32_t r = S.key[s + 1] >> kPackedBirthBits;
-        S.ids[s] = nb >= 0 ? nb + (int32_t)r : __ldg(rank_newid + r);
-        S.ids[s + 1] = -1;
+        S.ids[s] = (IdT)(nb >= 0 ? nb + (int32_t)r : __ldg(rank_newid + r));
+        S.ids[s + 1] = S.kDead;
     }
     const uint32_t a3 = actst & ~len2;
     const int cnt = __popc(a3);
@@ -222,7 +222,8 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
     const int nact = __shfl_sync(FULL, incl, 31);
     {
         int off = incl - cnt;
-        for (uint32_t a = a3; a; a &= a - 1u) S.act[off++] = (uint16_t)(base + __ffs(a) - 1);
+        uint16_t* act = S.act();
+        for (uint32_t a = a3; a; a &= a - 1u) act[off++] = (uint16_t)(base + __ffs(a) - 1);
     }
     __syncwarp();
     // ---- pass 4: merge queue, one segment per lane, one merge per iteration ----
@@ -235,12 +236,10 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
         if (!have) {
             const int qi = head + __popc(need & lt);
             if (qi < nact) {
-                s = S.act[qi];
+                s = S.act()[qi];
                 const int e = next_bit(S.segbits, s, send), n = e - s;
-                if (n > 32) {                                           // long run: serial loop over the whole segment
-                    const int c = bpe_merge_packed(MT, S.ids + s, S.key + s, n);
-                    for (int t = s + c; t < e; ++t) S.ids[t] = -1;
-                } else {
+                if (n > 32) complex = true;                             // a run longer than the 32-bit masks: generic path
+                else {
                     const uint32_t mask = n == 32 ? FULL : ((1u << n) - 1u);
                     km = g2_fsr(S.actbits[s >> 5], S.actbits[(s >> 5) + 1], s & 31) & mask;
                     alive = mask;
@@ -260,8 +259,8 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
             }
             const int pl = 31 - __clz(alive & ((1u << bk) - 1u));       // left operand = nearest live symbol below
             const int32_t nid = nb >= 0 ? nb + (int32_t)(best >> kPackedBirthBits) : __ldg(rank_newid + (best >> kPackedBirthBits));
-            S.ids[s + pl] = nid;
-            S.ids[s + bk] = -1;
+            S.ids[s + pl] = (IdT)nid;
+            S.ids[s + bk] = S.kDead;
             alive &= ~(1u << bk);
             km &= ~((1u << bk) | (1u << pl));
             ++merges;
@@ -269,30 +268,32 @@ __device__ __forceinline__ int fast_window(FastSmem& S, const RowParams& P, cons
             const uint32_t below = alive & ((1u << pl) - 1u);
             if (below) {
                 int32_t r, v;
-                if (merge_find(MT, S.ids[s + 31 - __clz(below)], nid, r, v)) { S.key[s + pl] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << pl; }
+                if (merge_find(MT, (int32_t)S.ids[s + 31 - __clz(below)], nid, r, v)) { S.key[s + pl] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << pl; }
             }
             const uint32_t above = alive & ~((2u << bk) - 1u);
             if (above) {
                 const int nr = __ffs(above) - 1;
                 km &= ~(1u << nr);
                 int32_t r, v;
-                if (merge_find(MT, nid, S.ids[s + nr], r, v)) { S.key[s + nr] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << nr; }
+                if (merge_find(MT, nid, (int32_t)S.ids[s + nr], r, v)) { S.key[s + nr] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << nr; }
             }
             if (!km) have = false;
         }
     }
     __syncwarp();
+    if (__any_sync(FULL, complex)) return -1;
     return send;
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, 4) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
+template <class IdT, int CTAS>
+__global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                            // [128]
     uint32_t* lut32_smem = reinterpret_cast<uint32_t*>(smem_raw + 128);        // [256]
     uint32_t* pbits_smem = lut32_smem + 256;                                   // [512]
-    FastSmem* warps = reinterpret_cast<FastSmem*>(smem_raw + kFastSmemFixed);
+    FastSmem<IdT>* warps = reinterpret_cast<FastSmem<IdT>*>(smem_raw + kFastSmemFixed);
     const int lane = threadIdx.x & 31;
-    FastSmem& S = warps[threadIdx.x >> 5];
+    FastSmem<IdT>& S = warps[threadIdx.x >> 5];
     if (threadIdx.x < 128) ascii_smem[threadIdx.x] = P.cls.ascii[threadIdx.x];
     lut32_smem[threadIdx.x] = v7_lut_entry(P, threadIdx.x);
     pbits_smem[threadIdx.x] = P.bpe.pair_bits[threadIdx.x];
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) gpt2_bpe_fast_kernel(const _
                         int32_t tok[4];
                         uint32_t m[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) tok[u] = (w + 32 * u) < send ? S.ids[w + 32 * u] : -1;
+                        for (int u = 0; u < 4; ++u) tok[u] = ((w + 32 * u) < send && S.ids[w + 32 * u] != S.kDead) ? (int32_t)S.ids[w + 32 * u] : -1;
 #pragma unroll
                         for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
 #pragma unroll

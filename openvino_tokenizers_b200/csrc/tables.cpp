@@ -209,6 +209,9 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
         while (out.slots[h].left != kEmptyKey) h = (h + 1) & out.mask;
         out.slots[h] = MergeSlot{l, r, kv.second.first, kv.second.second};
     }
+    out.max_id = 0;
+    for (const auto& kv : vocab) out.max_id = std::max<int64_t>(out.max_id, kv.second);
+    for (int32_t v : out.rank_newid) out.max_id = std::max<int64_t>(out.max_id, v);
     out.newid_base = M > 0 ? out.rank_newid[0] : -1;
     for (int64_t r = 0; r < M && out.newid_base >= 0; ++r)
         if (out.rank_newid[(size_t)r] != out.newid_base + (int32_t)r) out.newid_base = -1;

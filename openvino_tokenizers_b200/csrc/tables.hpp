@@ -43,6 +43,7 @@ struct HostBpe {
     std::vector<uint32_t> pair_rank;
     std::vector<uint32_t> pair_bits;
     int32_t newid_base = -1;
+    int64_t max_id = 0;                 // largest token id any symbol can take (vocab + added tokens)
     uint32_t mask = 0;
     std::string end_suffix;
     int32_t unk_id = -1;

@@ -81,6 +81,13 @@ class TokenizerPipeline:
     def launches(self) -> int:
         return self.tok.launches
 
+    @property
+    def dominant_kernel(self) -> str:
+        """Name of the kernel b200tok_last_kernel_ms() times (csrc/api.cu launch_chunk)."""
+        if self.kind == "bpe" and self.assets.split_pattern in (A.GPT2_PATTERN, A.GPT2_DIGITS_PATTERN) and not self.assets.end_suffix:
+            return "gpt2_bpe_fast_kernel" + ("<u16,5>" if len(self.assets.vocab) < 0xFFFF else "<i32,4>")
+        return f"rows_kernel<{self.kind}>"
+
     def set_timing(self, on: bool):
         K.lib().b200tok_set_timing(self.tok.handle, int(on))
 
