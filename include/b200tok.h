@@ -13,6 +13,9 @@
  *   b200tok_vocabenc_*     replaces VocabEncoder::evaluate_impl   src/vocab_encoder.cpp:56-94
  *   b200tok_vocabdec_*     replaces VocabDecoder::evaluate        src/vocab_decoder.cpp:23-87
  *   b200tok_bytefallback_run replaces ByteFallback::evaluate      src/byte_fallback.cpp:16-50
+ *   b200tok_truncate_run / b200tok_combine_segments_run / b200tok_ragged_to_dense_run replace Truncate / CombineSegments /
+ *                          RaggedToDense::evaluate (src/truncate.cpp:37-147, src/combine_segments.cpp:36-134,
+ *                          src/ragged_to_dense.cpp:70-174); b200tok_post_dense_run fuses the three
  *   b200tok_split_bpe_run / b200tok_split_wordpiece_run  fuse RegexSplit(+RegexSplit) -> tokenizer
  *                          in one kernel (pieces never leave shared memory); same results as the
  *                          two ops run back to back.
@@ -225,6 +228,44 @@ B200TOK_API int b200tok_bytefallback_run(int device, const int32_t* begins, cons
                                          const uint8_t* chars, int64_t n_chars,
                                          int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
                                          int64_t* out_n_chars, int mem, void* cuda_stream);
+
+/* ---- Post-tokenizer tail (stateless): Truncate, CombineSegments, RaggedToDense ----------------------
+ * i32 elements (what the converted tokenizer IRs feed these ops: token ids).  `mem` as above.            */
+/* Truncate, src/truncate.cpp:37-147.  num_inputs 1: (begins0, ends0); 2: plus (begins1, ends1).  The arrays are
+ * edited in place (the reference aliases its outputs to its inputs, :52-56).  side "left" | "right";
+ * mode "only_first" | "only_second" | "longest_first" (used with two inputs).                              */
+B200TOK_API int b200tok_truncate_run(int device, int num_inputs, int32_t* begins0, int32_t* ends0, int32_t* begins1, int32_t* ends1,
+                                     int64_t n, int32_t max_length, const char* side, const char* mode, int mem, void* cuda_stream);
+/* One ragged i32 input of CombineSegments: inputs [3j .. 3j+2] of the op. */
+typedef struct {
+    const int32_t* begins;   /* [n]  */
+    const int32_t* ends;     /* [n]  */
+    int64_t n;               /* rows; 1 = broadcast to every output row (src/combine_segments.cpp:102-104) */
+    const int32_t* elems;    /* [n_elems] */
+    int64_t n_elems;
+} b200tok_ragged_i32;
+/* CombineSegments, src/combine_segments.cpp:36-134.  segment_ids = the op's last input (one id per segment).
+ * Outputs: begins/ends [rows] (both output ragged tensors share them, :30-32), elems and ids [capacity];
+ * *n_out = produced elements.  At most 16 segments.                                                         */
+B200TOK_API int b200tok_combine_segments_run(int device, const b200tok_ragged_i32* segments, int num_segments, const int32_t* segment_ids,
+                                             int32_t* out_begins, int32_t* out_ends, int32_t* out_elems, int32_t* out_ids,
+                                             int64_t capacity, int64_t* n_out, int mem, void* cuda_stream);
+/* RaggedToDense, src/ragged_to_dense.cpp:70-174.  out: i32[n, target_dim]; out_mask: u8[n, target_dim] or NULL.
+ * pad_right = attribute or input [5]; pad_max_length = attribute m_pad_max_length.                          */
+B200TOK_API int b200tok_ragged_to_dense_run(int device, const int32_t* begins, const int32_t* ends, int64_t n, const int32_t* elems,
+                                            int64_t n_elems, int32_t target_dim, int32_t default_value, int pad_right, int pad_max_length,
+                                            int32_t* out, uint8_t* out_mask, int mem, void* cuda_stream);
+/* The three chained as the converted IRs do for single-sequence inputs — Truncate(max_length, side) ->
+ * CombineSegments(prefix constants, tokens, suffix constants) -> RaggedToDense(target_dim, pad_value) — in one pass
+ * over the ragged ids; same result as running the three ops back to back.  prefix / suffix: host arrays, <= 8 ids. */
+typedef struct {
+    int32_t max_length; int truncate_left;
+    const int32_t* prefix; int32_t n_prefix;
+    const int32_t* suffix; int32_t n_suffix;
+    int32_t target_dim; int32_t pad_value; int pad_right;
+} b200tok_post_desc;
+B200TOK_API int b200tok_post_dense_run(int device, const b200tok_post_desc* desc, const int32_t* begins, const int32_t* ends, int64_t n_rows,
+                                       const int32_t* ids, int64_t n_ids, int32_t* out_ids, uint8_t* out_mask, int mem, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,16 @@ class Decoded(C.Structure):
                 ("mem", C.c_int)]
 
 
+class RaggedI32(C.Structure):
+    _fields_ = [("begins", C.c_void_p), ("ends", C.c_void_p), ("n", C.c_int64), ("elems", C.c_void_p), ("n_elems", C.c_int64)]
+
+
+class PostDesc(C.Structure):
+    _fields_ = [("max_length", C.c_int32), ("truncate_left", C.c_int), ("prefix", i32p), ("n_prefix", C.c_int32),
+                ("suffix", i32p), ("n_suffix", C.c_int32), ("target_dim", C.c_int32), ("pad_value", C.c_int32),
+                ("pad_right", C.c_int)]
+
+
 def make_strings(triple, keep: list) -> Strings:
     """(begins, ends, chars) numpy triple -> Strings struct; arrays are appended to `keep` to stay alive."""
     if triple is None:
@@ -137,4 +147,5 @@ EXPORTED_SYMBOLS = [
     "b200tok_vocabenc_create", "b200tok_vocabenc_run",
     "b200tok_vocabdec_create", "b200tok_vocabdec_run", "b200tok_vocabdec_max_chars",
     "b200tok_bytefallback_run",
+    "b200tok_truncate_run", "b200tok_combine_segments_run", "b200tok_ragged_to_dense_run", "b200tok_post_dense_run",
 ]

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_tail.cuh"
 #include "tables.hpp"
 
 using namespace b200tok;
@@ -1067,6 +1068,225 @@ B200TOK_API int b200tok_bytefallback_run(int device, const int32_t* begins, cons
         CU(cudaMemcpyAsync(out_begins, d_ob, n * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out_ends, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
         if (t) CU(cudaMemcpyAsync(out_chars, d_oc, t, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+}  // extern "C"
+
+// ---- Post-tokenizer tail (stateless) ----
+namespace {
+int tail_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B200TOK_E_CUDA, "no such CUDA device %d (there is no CPU fallback)", device);
+    return 0;
+}
+// stream-ordered scratch: freed on the same stream when the object dies
+struct AsyncBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+}  // namespace
+
+extern "C" {
+
+B200TOK_API int b200tok_truncate_run(int device, int num_inputs, int32_t* b0, int32_t* e0, int32_t* b1, int32_t* e1, int64_t n, int32_t max_length,
+                                     const char* side, const char* mode, int mem, void* stream) {
+    if (num_inputs != 1 && num_inputs != 2) return fail(B200TOK_E_INVALID, "Only single or pair inputs are supported in Truncation op");
+    if (n < 0 || !side || (n > 0 && (!b0 || !e0 || (num_inputs == 2 && (!b1 || !e1))))) return fail(B200TOK_E_INVALID, "bad arguments");
+    const std::string sd(side), md(mode ? mode : "");
+    if (sd != "left" && sd != "right") return fail(B200TOK_E_INVALID, "Unknown truncation side: %s", side);
+    int m = TRUNC_LONGEST_FIRST;
+    if (num_inputs == 2) {
+        if (md == "only_first") m = TRUNC_ONLY_FIRST;
+        else if (md == "only_second") m = TRUNC_ONLY_SECOND;
+        else if (md == "longest_first") m = TRUNC_LONGEST_FIRST;
+        else return fail(B200TOK_E_INVALID, "Unknown truncation mode: %s", md.c_str());
+    }
+    if (n == 0) return B200TOK_OK;
+    int rc = tail_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = mem == B200TOK_MEM_HOST;
+    AsyncBuf buf;
+    int32_t* d[4] = {b0, e0, b1, e1};
+    int32_t* h[4] = {b0, e0, b1, e1};
+    const int na = 2 * num_inputs;
+    if (host) {
+        CU(buf.alloc((size_t)na * n * 4, st));
+        for (int k = 0; k < na; ++k) {
+            d[k] = buf.as<int32_t>() + (size_t)k * n;
+            CU(cudaMemcpyAsync(d[k], h[k], n * 4, cudaMemcpyHostToDevice, st));
+        }
+    }
+    truncate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(num_inputs, d[0], d[1], d[2], d[3], n, max_length, sd == "left" ? TRUNC_LEFT : TRUNC_RIGHT, m);
+    CU(cudaGetLastError());
+    if (host) {
+        for (int k = 0; k < na; ++k) CU(cudaMemcpyAsync(h[k], d[k], n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_combine_segments_run(int device, const b200tok_ragged_i32* segs, int num, const int32_t* seg_ids, int32_t* out_begins,
+                                             int32_t* out_ends, int32_t* out_elems, int32_t* out_ids, int64_t capacity, int64_t* n_out,
+                                             int mem, void* stream) {
+    if (!segs || num < 1 || num > kMaxSegments || !seg_ids || !n_out || capacity < 0) return fail(B200TOK_E_INVALID, "bad arguments (1..16 segments)");
+    *n_out = 0;
+    int64_t rows = 0;
+    for (int j = 0; j < num; ++j) {
+        if (segs[j].n < 0 || segs[j].n_elems < 0 || (segs[j].n > 0 && (!segs[j].begins || !segs[j].ends))) return fail(B200TOK_E_INVALID, "bad segment %d", j);
+        rows = std::max(rows, segs[j].n);
+    }
+    for (int j = 0; j < num; ++j)
+        if (segs[j].n != 1 && segs[j].n != rows) return fail(B200TOK_E_INVALID, "segment %d has %lld rows; expected 1 (broadcast) or %lld", j, (long long)segs[j].n, (long long)rows);
+    if (rows == 0) return B200TOK_OK;
+    if (!out_begins || !out_ends || (capacity > 0 && (!out_elems || !out_ids))) return fail(B200TOK_E_INVALID, "missing output buffers");
+    int rc = tail_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = mem == B200TOK_MEM_HOST;
+    SegmentList S{};
+    S.num = num;
+    AsyncBuf in, out, scratch;
+    size_t in_words = 0;
+    for (int j = 0; j < num; ++j) in_words += (size_t)2 * segs[j].n + (size_t)segs[j].n_elems;
+    if (host) {
+        // the caller's seg_ids pointer is host memory here
+        CU(in.alloc(in_words * 4, st));
+        int32_t* p = in.as<int32_t>();
+        for (int j = 0; j < num; ++j) {
+            CU(cudaMemcpyAsync(p, segs[j].begins, segs[j].n * 4, cudaMemcpyHostToDevice, st)); S.begins[j] = p; p += segs[j].n;
+            CU(cudaMemcpyAsync(p, segs[j].ends, segs[j].n * 4, cudaMemcpyHostToDevice, st)); S.ends[j] = p; p += segs[j].n;
+            if (segs[j].n_elems) CU(cudaMemcpyAsync(p, segs[j].elems, segs[j].n_elems * 4, cudaMemcpyHostToDevice, st));
+            S.elems[j] = p; p += segs[j].n_elems;
+            S.ids[j] = seg_ids[j];
+        }
+    } else {
+        std::vector<int32_t> ids((size_t)num);
+        CU(cudaMemcpyAsync(ids.data(), seg_ids, (size_t)num * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int j = 0; j < num; ++j) { S.begins[j] = segs[j].begins; S.ends[j] = segs[j].ends; S.elems[j] = segs[j].elems; S.ids[j] = ids[(size_t)j]; }
+    }
+    for (int j = 0; j < num; ++j) S.broadcast[j] = (segs[j].n == 1 && rows != 1) ? 1 : 0;
+    int32_t *d_ob = out_begins, *d_oe = out_ends, *d_ox = out_elems, *d_oi = out_ids;
+    if (host) {
+        CU(out.alloc(((size_t)2 * rows + (size_t)2 * capacity) * 4, st));
+        d_ob = out.as<int32_t>(); d_oe = d_ob + rows; d_ox = d_oe + rows; d_oi = d_ox + capacity;
+    }
+    size_t cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)rows, st);
+    const size_t len_off = (cub_bytes + 255) & ~(size_t)255;
+    CU(scratch.alloc(len_off + (size_t)rows * 4 + 16, st));
+    int32_t* d_len = reinterpret_cast<int32_t*>(scratch.as<uint8_t>() + len_off);
+    int64_t* d_total = reinterpret_cast<int64_t*>(scratch.as<uint8_t>() + len_off + (((size_t)rows * 4 + 7) & ~(size_t)7));
+    combine_len_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(S, rows, d_len);
+    cub::DeviceScan::ExclusiveSum(scratch.p, cub_bytes, d_len, d_ob, (int)rows, st);
+    // the total is needed before the copy to honour `capacity`
+    int32_t last[2] = {0, 0};
+    CU(cudaMemcpyAsync(&last[0], d_ob + rows - 1, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&last[1], d_len + rows - 1, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int64_t total = (int64_t)last[0] + last[1];
+    *n_out = total;
+    if (total > capacity) return fail(B200TOK_E_CAPACITY, "capacity %lld is smaller than the result (%lld elements)", (long long)capacity, (long long)total);
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    combine_copy_kernel<<<(unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm * 8), 256, 0, st>>>(S, rows, d_ob, d_len, d_oe, d_ox, d_oi, d_total);
+    CU(cudaGetLastError());
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, rows * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, rows * 4, cudaMemcpyDeviceToHost, st));
+        if (total) {
+            CU(cudaMemcpyAsync(out_elems, d_ox, total * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(out_ids, d_oi, total * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_ragged_to_dense_run(int device, const int32_t* begins, const int32_t* ends, int64_t n, const int32_t* elems, int64_t n_elems,
+                                            int32_t target_dim, int32_t default_value, int pad_right, int pad_max_length, int32_t* out,
+                                            uint8_t* out_mask, int mem, void* stream) {
+    if (n < 0 || n_elems < 0 || target_dim < 0 || (n > 0 && (!begins || !ends))) return fail(B200TOK_E_INVALID, "bad arguments");
+    const int64_t total = n * (int64_t)target_dim;
+    if (total == 0) return B200TOK_OK;
+    if (!out) return fail(B200TOK_E_INVALID, "missing output buffer");
+    int rc = tail_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = mem == B200TOK_MEM_HOST;
+    AsyncBuf buf;
+    const int32_t *d_b = begins, *d_e = ends, *d_x = elems;
+    int32_t* d_o = out;
+    uint8_t* d_m = out_mask;
+    if (host) {
+        CU(buf.alloc(((size_t)2 * n + (size_t)n_elems + (size_t)total) * 4 + (size_t)total + 64, st));
+        int32_t* p = buf.as<int32_t>();
+        CU(cudaMemcpyAsync(p, begins, n * 4, cudaMemcpyHostToDevice, st)); d_b = p; p += n;
+        CU(cudaMemcpyAsync(p, ends, n * 4, cudaMemcpyHostToDevice, st)); d_e = p; p += n;
+        if (n_elems) CU(cudaMemcpyAsync(p, elems, n_elems * 4, cudaMemcpyHostToDevice, st));
+        d_x = p; p += n_elems;
+        d_o = p; p += total;
+        d_m = out_mask ? reinterpret_cast<uint8_t*>(p) : nullptr;
+    }
+    ragged_to_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_b, d_e, n, d_x, n_elems, target_dim, default_value, pad_right != 0,
+                                                                            pad_max_length != 0, d_o, d_m);
+    CU(cudaGetLastError());
+    if (host) {
+        CU(cudaMemcpyAsync(out, d_o, total * 4, cudaMemcpyDeviceToHost, st));
+        if (out_mask) CU(cudaMemcpyAsync(out_mask, d_m, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_post_dense_run(int device, const b200tok_post_desc* d, const int32_t* begins, const int32_t* ends, int64_t n_rows,
+                                       const int32_t* ids, int64_t n_ids, int32_t* out_ids, uint8_t* out_mask, int mem, void* stream) {
+    if (!d || n_rows < 0 || n_ids < 0 || d->target_dim < 0 || d->n_prefix < 0 || d->n_prefix > 8 || d->n_suffix < 0 || d->n_suffix > 8 ||
+        (d->n_prefix > 0 && !d->prefix) || (d->n_suffix > 0 && !d->suffix) || (n_rows > 0 && (!begins || !ends)))
+        return fail(B200TOK_E_INVALID, "bad arguments (at most 8 prefix and 8 suffix ids)");
+    const int64_t total = n_rows * (int64_t)d->target_dim;
+    if (total == 0) return B200TOK_OK;
+    if (!out_ids) return fail(B200TOK_E_INVALID, "missing output buffer");
+    int rc = tail_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = mem == B200TOK_MEM_HOST;
+    PostParams Q{};
+    Q.max_length = d->max_length; Q.trunc_left = d->truncate_left != 0;
+    Q.n_prefix = d->n_prefix; Q.n_suffix = d->n_suffix;
+    for (int k = 0; k < d->n_prefix; ++k) Q.prefix[k] = d->prefix[k];
+    for (int k = 0; k < d->n_suffix; ++k) Q.suffix[k] = d->suffix[k];
+    Q.target_dim = d->target_dim; Q.pad_value = d->pad_value; Q.pad_right = d->pad_right != 0;
+    AsyncBuf buf;
+    const int32_t *d_b = begins, *d_e = ends, *d_x = ids;
+    int32_t* d_o = out_ids;
+    uint8_t* d_m = out_mask;
+    if (host) {
+        CU(buf.alloc(((size_t)2 * n_rows + (size_t)n_ids + (size_t)total) * 4 + (size_t)total + 64, st));
+        int32_t* p = buf.as<int32_t>();
+        CU(cudaMemcpyAsync(p, begins, n_rows * 4, cudaMemcpyHostToDevice, st)); d_b = p; p += n_rows;
+        CU(cudaMemcpyAsync(p, ends, n_rows * 4, cudaMemcpyHostToDevice, st)); d_e = p; p += n_rows;
+        if (n_ids) CU(cudaMemcpyAsync(p, ids, n_ids * 4, cudaMemcpyHostToDevice, st));
+        d_x = p; p += n_ids;
+        d_o = p; p += total;
+        d_m = out_mask ? reinterpret_cast<uint8_t*>(p) : nullptr;
+    }
+    post_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, d_b, d_e, n_rows, d_x, n_ids, d_o, d_m);
+    CU(cudaGetLastError());
+    if (host) {
+        CU(cudaMemcpyAsync(out_ids, d_o, total * 4, cudaMemcpyDeviceToHost, st));
+        if (out_mask) CU(cudaMemcpyAsync(out_mask, d_m, total, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return B200TOK_OK;

@@ -42,6 +42,15 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def _as_text(a) -> str:
+    """A u8 string-scalar input (what string attributes passed as tensors look like) or a Python str/bytes."""
+    if isinstance(a, str):
+        return a
+    if isinstance(a, (bytes, bytearray)):
+        return bytes(a).decode()
+    return bytes(np.asarray(a, dtype=np.uint8).reshape(-1)).decode()
+
+
 class _Handle:
     def __init__(self):
         self._h = C.c_void_p()
@@ -282,6 +291,97 @@ class ByteFallback:
         K.check(K.lib().b200tok_bytefallback_run(self.device, _ptr(b), _ptr(e), C.c_int64(len(b)), _ptr(c), C.c_int64(c.size),
                                                  _ptr(ob), _ptr(oe), _ptr(oc), C.byref(n), K.MEM_HOST, None))
         return [ob, oe, oc[:n.value].copy()]
+
+
+class Truncate:
+    """Truncate(num_inputs): inputs [3i..3i+2] ragged i32 (begins, ends, elems) per sequence, then max_length (i32 scalar),
+    truncation side ("left"|"right") and mode ("only_first"|"only_second"|"longest_first") as u8 strings
+    (reference src/truncate.cpp:37-147).  Outputs: the inputs with edited begins / ends."""
+
+    def __init__(self, num_inputs=1, device=0):
+        self.num_inputs, self.device = int(num_inputs), device
+
+    def evaluate(self, inputs):
+        n_in = self.num_inputs
+        if len(inputs) != 3 * n_in + 3:
+            raise ValueError("Truncate expects 3 * num_inputs + 3 inputs")
+        max_length = int(np.asarray(inputs[-3]).reshape(-1)[0])
+        side, mode = _as_text(inputs[-2]), _as_text(inputs[-1])
+        arr = [_i32(inputs[3 * i + k]).copy() for i in range(n_in) for k in (0, 1)]
+        n = len(arr[0])
+        if any(len(a) != n for a in arr):
+            raise ValueError("Begin and end tensors should have the same size")
+        ptrs = [_ptr(a) for a in arr] + [None] * (4 - len(arr))
+        K.check(K.lib().b200tok_truncate_run(self.device, n_in, *ptrs, C.c_int64(n), C.c_int32(max_length), side.encode(),
+                                             mode.encode(), K.MEM_HOST, None))
+        out = []
+        for i in range(n_in):
+            out += [arr[2 * i], arr[2 * i + 1], np.asarray(inputs[3 * i + 2])]
+        return out
+
+
+class CombineSegments:
+    """CombineSegments: inputs [3j..3j+2] ragged i32 segments, last input = one id per segment (reference
+    src/combine_segments.cpp:36-134).  Outputs: (begins, ends, elems) and (begins, ends, ids)."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def evaluate(self, inputs):
+        num = (len(inputs) - 1) // 3
+        ids = _i32(inputs[-1]).reshape(-1)
+        if num < 1 or len(inputs) != 3 * num + 1 or len(ids) != num:
+            raise ValueError("CombineSegments expects 3 * n + 1 inputs with one id per segment")
+        segs = (K.RaggedI32 * num)()
+        keep, cap, rows = [], 0, 0
+        for j in range(num):
+            b, e, x = _i32(inputs[3 * j]).reshape(-1), _i32(inputs[3 * j + 1]).reshape(-1), _i32(inputs[3 * j + 2]).reshape(-1)
+            keep += [b, e, x]
+            segs[j] = K.RaggedI32(b.ctypes.data, e.ctypes.data, len(b), x.ctypes.data if x.size else None, x.size)
+            rows = max(rows, len(b))
+        for j in range(num):   # the reference's flat_out_size estimate (:65-71)
+            cap += (rows if segs[j].n == 1 else 1) * segs[j].n_elems
+        ob, oe = np.empty(rows, np.int32), np.empty(rows, np.int32)
+        ox, oi = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32)
+        n = C.c_int64(0)
+        K.check(K.lib().b200tok_combine_segments_run(self.device, segs, num, _ptr(ids), _ptr(ob), _ptr(oe), _ptr(ox), _ptr(oi),
+                                                     C.c_int64(cap), C.byref(n), K.MEM_HOST, None))
+        return [ob, oe, ox[:n.value].copy(), ob.copy(), oe.copy(), oi[:n.value].copy()]
+
+
+class RaggedToDense:
+    """RaggedToDense(pad_right, pad_max_length): inputs begins, ends, elems (i32), target_dim, default value, optional
+    pad_right bool (reference src/ragged_to_dense.cpp:70-174).  Outputs: dense i32[n, target_dim], mask bool."""
+
+    def __init__(self, pad_right=True, pad_max_length=False, device=0):
+        self.pad_right, self.pad_max_length, self.device = bool(pad_right), bool(pad_max_length), device
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (5, 6):
+            raise ValueError("RaggedToDense expects 5 or 6 inputs")
+        b, e, x = _i32(inputs[0]).reshape(-1), _i32(inputs[1]).reshape(-1), _i32(inputs[2]).reshape(-1)
+        target = int(np.asarray(inputs[3]).reshape(-1)[0])
+        default = int(np.asarray(inputs[4]).reshape(-1)[0])
+        pad_right = bool(np.asarray(inputs[5]).reshape(-1)[0]) if len(inputs) == 6 else self.pad_right
+        out = np.empty((len(b), target), np.int32)
+        mask = np.empty((len(b), target), np.uint8)
+        K.check(K.lib().b200tok_ragged_to_dense_run(self.device, _ptr(b), _ptr(e), C.c_int64(len(b)), _ptr(x) if x.size else None,
+                                                    C.c_int64(x.size), C.c_int32(target), C.c_int32(default), int(pad_right),
+                                                    int(self.pad_max_length), _ptr(out), _ptr(mask), K.MEM_HOST, None))
+        return [out, mask.astype(bool)]
+
+
+def post_dense(begins, ends, ids, max_length, target_dim, pad_value, prefix=(), suffix=(), truncate_left=False, pad_right=True, device=0):
+    """Fused Truncate -> CombineSegments(prefix, tokens, suffix) -> RaggedToDense on ragged ids (host arrays)."""
+    b, e, x = _i32(begins), _i32(ends), _i32(ids)
+    pre, suf = _i32(np.asarray(list(prefix), np.int32)), _i32(np.asarray(list(suffix), np.int32))
+    d = K.PostDesc(int(max_length), int(truncate_left), pre.ctypes.data_as(K.i32p) if pre.size else None, pre.size,
+                   suf.ctypes.data_as(K.i32p) if suf.size else None, suf.size, int(target_dim), int(pad_value), int(pad_right))
+    out = np.empty((len(b), target_dim), np.int32)
+    mask = np.empty((len(b), target_dim), np.uint8)
+    K.check(K.lib().b200tok_post_dense_run(device, C.byref(d), _ptr(b), _ptr(e), C.c_int64(len(b)), _ptr(x) if x.size else None,
+                                           C.c_int64(x.size), _ptr(out), _ptr(mask), K.MEM_HOST, None))
+    return out, mask.astype(bool)
 
 
 def split_bpe(split: RegexSplit, bpe: BPETokenizer, inputs):

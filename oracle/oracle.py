@@ -18,7 +18,7 @@ _LIB_PATH = _HERE / "liboracle.so"
 
 __all__ = [
     "build", "lib", "pcre2_available", "BpeOracle", "WordpieceOracle", "SplitOracle", "VocabEncoderOracle",
-    "vocab_decoder", "byte_fallback",
+    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense",
 ]
 
 
@@ -245,3 +245,47 @@ def byte_fallback(begins, ends, chars):
     N = lib().orc_bytefallback_run(_p(begins, _i32p), _p(ends, _i32p), _p(chars, _u8p), C.c_int64(len(begins)),
                                    _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p))
     return ob, oe, oc[:N].copy()
+
+
+def truncate(pairs, max_length, side="right", mode="longest_first"):
+    """Truncate (reference src/truncate.cpp:37-147).  pairs: [(begins, ends)] for one or two ragged inputs; returns new
+    [(begins, ends)] (the reference edits its aliased outputs in place)."""
+    out = [(_i32(b).copy(), _i32(e).copy()) for b, e in pairs]
+    b0, e0 = out[0]
+    b1, e1 = out[1] if len(out) > 1 else (None, None)
+    rc = lib().orc_truncate(len(out), _p(b0, _i32p), _p(e0, _i32p), _p(b1, _i32p), _p(e1, _i32p), C.c_int64(len(b0)),
+                            C.c_int32(max_length), side.encode(), mode.encode())
+    if rc:
+        raise ValueError(f"Unknown truncation side/mode: {side}/{mode}")
+    return out
+
+
+def combine_segments(segments, ids):
+    """CombineSegments (reference src/combine_segments.cpp:36-134), i32 elements.  segments: [(begins, ends, elems)];
+    a segment with one row is broadcast.  Returns (begins, ends, elems, ids) of the combined ragged tensor."""
+    segs = [(_i32(b), _i32(e), _i32(x)) for b, e, x in segments]
+    ids = _i32(ids)
+    num = len(segs)
+    rows = max(len(s[0]) for s in segs)
+    total = sum((int((s[1] - s[0]).sum()) if len(s[0]) > 1 or rows == 1 else int(s[1][0] - s[0][0]) * rows) for s in segs)
+    PP = _i32p * num
+    nn = (C.c_int64 * num)(*[len(s[0]) for s in segs])
+    ob, oe = np.empty(rows, np.int32), np.empty(rows, np.int32)
+    ox, oi = np.empty(total + 1, np.int32), np.empty(total + 1, np.int32)
+    lib().orc_combine_segments.restype = C.c_int64
+    n = lib().orc_combine_segments(num, PP(*[_p(s[0], _i32p) for s in segs]), PP(*[_p(s[1], _i32p) for s in segs]), nn,
+                                   PP(*[_p(s[2], _i32p) for s in segs]), _p(ids, _i32p), _p(ob, _i32p), _p(oe, _i32p),
+                                   _p(ox, _i32p), _p(oi, _i32p))
+    assert n == total
+    return ob, oe, ox[:n].copy(), oi[:n].copy()
+
+
+def ragged_to_dense(begins, ends, elems, target_dim, default_value, pad_right=True, pad_max_length=False):
+    """RaggedToDense (reference src/ragged_to_dense.cpp:70-174), i32 elements.  Returns (dense i32[n, target], mask u8)."""
+    begins, ends, elems = _i32(begins), _i32(ends), _i32(elems)
+    n = len(begins)
+    out = np.empty((n, target_dim), np.int32)
+    mask = np.empty((n, target_dim), np.uint8)
+    lib().orc_ragged_to_dense(_p(begins, _i32p), _p(ends, _i32p), C.c_int64(n), _p(elems, _i32p), C.c_int32(target_dim),
+                              C.c_int32(default_value), int(bool(pad_right)), int(bool(pad_max_length)), _p(out, _i32p), _p(mask, _u8p))
+    return out, mask

@@ -5,6 +5,8 @@
   regex_split_layer_tests.json  the reference's own known-answer vectors for RegexSplit, extracted by evaluating
                                 the parametrize list of tests/layer_tests.py:331-389 against the RegexSplitStep
                                 factory methods of python/openvino_tokenizers/tokenizer_pipeline.py:354-470
+  post_ops_layer_tests.json     the reference's known-answer vectors for RaggedToDense and CombineSegments
+                                (tests/layer_tests.py:497-644)
   hf_<vocab>.json               ids produced by HuggingFace `tokenizers` for the frozen synthetic vocabularies
                                 (second oracle; the reference reports 100 % agreement with HF for these families)
 """
@@ -67,6 +69,39 @@ def make_regex_golden():
     print("regex cases", len(out), "gpu-supported", sum(c["gpu_supported"] for c in out))
 
 
+def reference_parametrize(func_name: str):
+    """The (evaluated) argvalues list of the @pytest.mark.parametrize decorator of a test in the reference's layer_tests.py."""
+    import numpy as np  # noqa: F401
+    lt = (REF / "tests/layer_tests.py").read_text()
+    tree = ast.parse(lt)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == func_name:
+            lst = node.decorator_list[0].args[1]
+            return eval(compile(ast.Expression(lst), "layer_tests", "eval"), {"np": __import__("numpy")})
+    raise RuntimeError(func_name + " not found")
+
+
+def make_post_golden():
+    """Known-answer vectors of RaggedToDense (reference tests/layer_tests.py:497-591) and CombineSegments (:594-644);
+    each is checked against the oracle before it is written.  (The reference holds no Truncate vectors.)"""
+    import numpy as np
+    import oracle
+    r2d = []
+    for inp, expected in reference_parametrize("test_ragged_to_dense"):
+        pad_right = inp["pad_right"] if "pad_right" in inp else inp["padding_side"] == "right"   # input [5] has priority over the attribute
+        got, _ = oracle.ragged_to_dense(inp["begins"], inp["ends"], inp["data"], inp["padding_size"], inp["value"], pad_right)
+        assert got.tolist() == expected, (inp, expected, got)
+        r2d.append(dict(inputs=inp, expected=expected))
+    comb = []
+    for segs, expected in reference_parametrize("test_combine_segments"):
+        got = oracle.combine_segments([(s["begins"], s["ends"], s["data"]) for s in segs], np.arange(len(segs)))
+        assert got[0].tolist() == expected["begins"] and got[1].tolist() == expected["ends"] and got[2].tolist() == expected["data"]
+        comb.append(dict(segments=segs, expected=expected))
+    (GOLDEN / "post_ops_layer_tests.json").write_text(json.dumps(
+        dict(source="reference tests/layer_tests.py:497-644", ragged_to_dense=r2d, combine_segments=comb), indent=1))
+    print("ragged_to_dense cases", len(r2d), "combine_segments cases", len(comb))
+
+
 def make_hf_golden():
     import numpy as np
     import cases
@@ -92,5 +127,10 @@ def make_hf_golden():
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    make_regex_golden()
-    make_hf_golden()
+    which = sys.argv[1:] or ["regex", "hf", "post"]
+    if "regex" in which:
+        make_regex_golden()
+    if "hf" in which:
+        make_hf_golden()
+    if "post" in which:
+        make_post_golden()
