@@ -7,6 +7,7 @@
  * in front for ragged tensors (reference src/utils.cpp:84-102) — as plain pointers + sizes.
  *
  *   b200tok_regexsplit_*   replaces RegexSplit::evaluate          src/regex_split.cpp:124-324
+ *   b200tok_specialsplit_* replaces SpecialTokensSplit::evaluate  src/special_tokens_split.cpp:61-162
  *   b200tok_bpe_*          replaces BPETokenizer::evaluate        src/bpe_tokenizer.cpp:47-164
  *                          (+ BPETokenizerImpl ctor :341-388, tokenize_into :196-339)
  *   b200tok_wordpiece_*    replaces WordpieceTokenizer::evaluate  src/wordpiece_tokenizer.cpp:49-133
@@ -138,6 +139,15 @@ typedef struct {
 B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* desc, b200tok_handle* out);
 B200TOK_API int b200tok_regexsplit_run(b200tok_handle h, const b200tok_ragged_strings* in,
                                        b200tok_ragged_strings_out* out, void* cuda_stream);
+
+/* ---- SpecialTokensSplit ---------------------------------------------------------------------
+ * replaces SpecialTokensSplit::evaluate (src/special_tokens_split.cpp:61-162); pattern = input [5|6], the alternation of
+ *   (?:\s*)?(tok|tok|...)(?:\s*)?   groups the converter builds (python/openvino_tokenizers/tokenizer_pipeline.py:138-158);
+ * anything else => B200TOK_E_UNSUPPORTED.  in->skips = input [5] of the 7-input form (may be NULL); outputs as RegexSplit's,
+ * with out->skips = output [5] (required).  Worst case n_chars + n_elems elements.                                    */
+B200TOK_API int b200tok_specialsplit_create(const char* pattern, int64_t pattern_len, int device, b200tok_handle* out);
+B200TOK_API int b200tok_specialsplit_run(b200tok_handle h, const b200tok_ragged_strings* in,
+                                         b200tok_ragged_strings_out* out, void* cuda_stream);
 
 /* ---- BPETokenizer --------------------------------------------------------------------------
  * Constant inputs [5..] of the 11/14/15/18-input forms (src/bpe_tokenizer.cpp:18-21,69-114):

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_special.cuh"
 #include "kernels_tail.cuh"
 #include "tables.hpp"
 
@@ -130,7 +131,7 @@ struct RowWorkspace {
     }
 };
 
-enum Kind { K_SPLIT = 1, K_BPE, K_WORDPIECE, K_VOCABENC, K_VOCABDEC };
+enum Kind { K_SPLIT = 1, K_BPE, K_WORDPIECE, K_VOCABENC, K_VOCABDEC, K_SPECIAL };
 
 }  // namespace
 
@@ -148,6 +149,18 @@ struct b200tok_object {
 namespace {
 
 struct SplitObj : b200tok_object { HostSplit h; };
+struct SpecialObj : b200tok_object {
+    HostSpecial h;
+    DevTrie trie[kSpecialGroups];
+    SpecialTables view() const {
+        SpecialTables t{};
+        t.n_groups = (int32_t)h.groups.size();
+        for (int g = 0; g < t.n_groups; ++g) { t.trie[g] = trie[g].view(); t.strip_left[g] = h.groups[(size_t)g].strip_left; t.strip_right[g] = h.groups[(size_t)g].strip_right; }
+        for (int k = 0; k < 8; ++k) t.first[k] = h.first[(size_t)k];
+        t.ws_token = h.ws_token;
+        return t;
+    }
+};
 struct BpeObj : b200tok_object {
     HostBpe h;
     DBuf<int32_t> byte_sym, byte_miss;
@@ -209,6 +222,7 @@ struct RowCall {
     int op;                       // OP_*
     const SplitObj* split = nullptr;   // may be null (PAT_NONE)
     const SplitObj* split2 = nullptr;
+    const SpecialObj* special = nullptr;
     BpeObj* bpe = nullptr;
     WordpieceObj* wp = nullptr;
     int32_t unk_id = 0;
@@ -258,8 +272,8 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
     const int64_t B = c.rows;
     const int blocks_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (kRowsSmem + 1024)));
     const int rows_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * blocks_per_sm);
-    static bool attr_set[3][64] = {};
-    if (!attr_set[call.op][owner->device]) {
+    static bool attr_set[4][64] = {};
+    if (call.op != OP_SPECIAL && !attr_set[call.op][owner->device]) {
         if (call.op == OP_BPE) CU(cudaFuncSetAttribute(rows_kernel<OP_BPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
         else if (call.op == OP_WORDPIECE) CU(cudaFuncSetAttribute(rows_kernel<OP_WORDPIECE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
         else CU(cudaFuncSetAttribute(rows_kernel<OP_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmem));
@@ -302,6 +316,10 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         P2.row_list = c.row_cap;
         rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(P2);
         owner->launches += 2;
+    } else if (call.op == OP_SPECIAL) {
+        special_split_kernel<<<(int)std::min<int64_t>((B + 7) / 8, (int64_t)owner->sm_count * 8), 256, 0, st>>>(c.P, call.special->view());
+        if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
+        ++owner->launches;
     } else {
         if (call.op == OP_BPE) rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
         else if (call.op == OP_WORDPIECE) rows_kernel<OP_WORDPIECE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(c.P);
@@ -538,7 +556,7 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     // NULL stream: host-memory calls use the handle's own stream; device-memory calls mean the legacy default stream
     cudaStream_t st = (user_stream || !host) ? (cudaStream_t)user_stream : w.stream;
     const int64_t B = in->n_rows, E = in->n_elems, N = in->n_chars;
-    const bool is_split = call.op == OP_SPLIT;
+    const bool is_split = call.op == OP_SPLIT || call.op == OP_SPECIAL;
 
     if (B == 0) {
         if (out_ids) { out_ids->n_ids = 0; if (out_ids->n_ids_device) CU(cudaMemsetAsync(out_ids->n_ids_device, 0, 8, st)); }
@@ -777,6 +795,33 @@ B200TOK_API int b200tok_regexsplit_run(b200tok_handle h, const b200tok_ragged_st
     RowCall call;
     call.op = OP_SPLIT;
     call.split = s;
+    return run_rows(s, call, in, nullptr, out, stream);
+}
+
+// ---- SpecialTokensSplit ----
+B200TOK_API int b200tok_specialsplit_create(const char* pattern, int64_t pattern_len, int device, b200tok_handle* out) {
+    if (!out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<SpecialObj>();
+    std::string err;
+    int rc = parse_special(pattern, pattern_len, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    if ((rc = init_object(o.get(), K_SPECIAL, device))) return rc;
+    DeviceGuard g(device);
+    CU(o->cls.upload());
+    for (size_t k = 0; k < o->h.groups.size(); ++k) CU(o->trie[k].upload(o->h.groups[k].trie));
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_specialsplit_run(b200tok_handle h, const b200tok_ragged_strings* in, b200tok_ragged_strings_out* out, void* stream) {
+    SpecialObj* s = as<SpecialObj>(h, K_SPECIAL);
+    if (!s || !out) return fail(B200TOK_E_INVALID, "not a SpecialTokensSplit handle");
+    int rc = validate_in(in);
+    if (rc) return rc;
+    RowCall call;
+    call.op = OP_SPECIAL;
+    call.special = s;
     return run_rows(s, call, in, nullptr, out, stream);
 }
 

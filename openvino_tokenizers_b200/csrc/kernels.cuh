@@ -28,7 +28,7 @@ constexpr int kRowsSmemFixed = 128 + 1024;   // per-CTA tables in front of the p
 
 constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK = 0x03FF;
 
-enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2 };
+enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2, OP_SPECIAL = 3 };
 
 // status words (device int32 array)
 enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_WORDS = 8 };

@@ -2,6 +2,7 @@
 #include "tables.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <cstring>
 #include <map>
 #include <unordered_map>
@@ -354,6 +355,78 @@ int parse_split(const b200tok_regexsplit_desc& d, HostSplit& out, std::string& e
     }
     err = "RegexSplit: pattern is not one of the tokenizer patterns the GPU splitter implements: " + pat;
     return B200TOK_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------
+// SpecialTokensSplit pattern.
+// ------------------------------------------------------------------------------------------
+int parse_special(const char* pattern, int64_t len, HostSpecial& out, std::string& err) {
+    if (!pattern || len < 0) { err = "SpecialTokensSplit: missing pattern"; return B200TOK_E_INVALID; }
+    const std::string pat(pattern, (size_t)len);
+    out.pattern = pat;
+    out.groups.clear();
+    auto unsupported = [&](const char* why) {
+        err = std::string("SpecialTokensSplit: pattern is not an alternation of (?:\\s*)?(literal|...)(?:\\s*)? groups (") + why + "): " + pat;
+        return B200TOK_E_UNSUPPORTED;
+    };
+    static const std::string kWs = "(?:\\s*)";
+    size_t i = 0;
+    while (i < pat.size()) {
+        HostSpecialGroup g;
+        if (pat.compare(i, kWs.size(), kWs) == 0) { g.strip_left = true; i += kWs.size(); }
+        if (i >= pat.size() || pat[i] != '(' || (i + 1 < pat.size() && pat[i + 1] == '?')) return unsupported("expected a capture group");
+        ++i;
+        std::string tok;
+        bool closed = false;
+        while (i < pat.size()) {
+            const char c = pat[i];
+            if (c == '\\') {
+                if (i + 1 >= pat.size()) return unsupported("dangling backslash");
+                const unsigned char n = (unsigned char)pat[i + 1];
+                if (std::isalnum(n)) return unsupported("escape sequence with a meaning");   // \s, \d, \x.. are not literals
+                tok.push_back((char)n);
+                i += 2;
+            } else if (c == '|') { g.tokens.push_back(tok); tok.clear(); ++i; }
+            else if (c == ')') { g.tokens.push_back(tok); closed = true; ++i; break; }
+            else if (std::strchr("^$.?*+([{}]", c)) return unsupported("unescaped metacharacter inside a group");
+            else { tok.push_back(c); ++i; }
+        }
+        if (!closed) return unsupported("unterminated group");
+        if (pat.compare(i, kWs.size(), kWs) == 0) { g.strip_right = true; i += kWs.size(); }
+        if (i < pat.size()) {
+            if (pat[i] != '|') return unsupported("expected | between groups");
+            ++i;
+            if (i >= pat.size()) return unsupported("empty alternative");
+        }
+        // neighbouring groups with the same flags behave like one group with the alternatives concatenated
+        if (!out.groups.empty() && out.groups.back().strip_left == g.strip_left && out.groups.back().strip_right == g.strip_right)
+            out.groups.back().tokens.insert(out.groups.back().tokens.end(), g.tokens.begin(), g.tokens.end());
+        else out.groups.push_back(std::move(g));
+    }
+    if (out.groups.empty()) return unsupported("empty pattern");
+    if ((int)out.groups.size() > kMaxSpecialGroups) return unsupported("too many groups");
+    out.first.assign(8, 0u);
+    out.ws_token = false;
+    const HostClassTables& ct = host_class_tables();
+    bool any_strip_left = false;
+    for (auto& g : out.groups) {
+        std::vector<std::pair<std::string, int32_t>> entries;
+        for (size_t k = g.tokens.size(); k-- > 0;) {      // reversed: an earlier duplicate overwrites a later one
+            if (g.tokens[k].empty()) return unsupported("empty alternative");   // would match the empty string everywhere
+            entries.emplace_back(g.tokens[k], (int32_t)k);
+        }
+        g.trie.build(entries);
+        for (const auto& t : g.tokens) {
+            const unsigned char b = (unsigned char)t[0];
+            out.first[b >> 5] |= 1u << (b & 31);
+            if (g.strip_left && (b >= 0x80 || (ct.ascii[b] & C_S))) out.ws_token = true;
+        }
+        any_strip_left |= g.strip_left;
+    }
+    if (any_strip_left)      // whitespace can start a match: ASCII \s bytes and every multi-byte lead (classified exactly later)
+        for (int b = 0; b < 256; ++b)
+            if (b >= 0xC2 || (b < 0x80 && (ct.ascii[b] & C_S))) out.first[b >> 5] |= 1u << (b & 31);
+    return B200TOK_OK;
 }
 
 }  // namespace b200tok

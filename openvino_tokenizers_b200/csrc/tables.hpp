@@ -85,6 +85,19 @@ struct HostSplit {
 };
 int parse_split(const b200tok_regexsplit_desc& d, HostSplit& out, std::string& err);
 
+// SpecialTokensSplit pattern (src/special_tokens_split.cpp + the converter's tokenizer_pipeline.py:138-158): an alternation
+// of groups  (?:\s*)?(tok|tok|...)(?:\s*)?  of quote_meta-escaped literals.  value of a trie entry = position of the token
+// inside its group (PCRE2 takes the first alternative that matches).
+constexpr int kMaxSpecialGroups = 8;
+struct HostSpecialGroup { bool strip_left = false, strip_right = false; std::vector<std::string> tokens; HostTrie trie; };
+struct HostSpecial {
+    std::vector<HostSpecialGroup> groups;
+    std::vector<uint32_t> first;     // [8]: bytes at which a match can start
+    bool ws_token = false;           // some token of a strip_left group starts with a whitespace byte (forces full backtracking)
+    std::string pattern;
+};
+int parse_special(const char* pattern, int64_t len, HostSpecial& out, std::string& err);
+
 inline uint64_t fnv1a64(const uint8_t* p, int64_t n) {
     uint64_t h = 1469598103934665603ull;
     for (int64_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }

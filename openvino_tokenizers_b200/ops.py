@@ -134,6 +134,37 @@ class RegexSplit(_Handle):
         return res
 
 
+class SpecialTokensSplit(_Handle):
+    """SpecialTokensSplit; inputs: ragged strings [0..4], optional skips [5], split pattern (reference
+    src/special_tokens_split.cpp:61-162).  Outputs: ragged strings [0..4] and skips [5] (always)."""
+
+    def __init__(self, device=0):
+        super().__init__()
+        self.device = device
+
+    def with_pattern(self, pattern):
+        if not self._h:
+            p = pattern.encode() if isinstance(pattern, str) else bytes(pattern)
+            K.check(K.lib().b200tok_specialsplit_create(p, C.c_int64(len(p)), self.device, C.byref(self._h)))
+        return self
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (6, 7):
+            raise ValueError("Incorrect number of inputs passed to SpecialTokensSplit: %d; try to reconvert tokenizer with newer "
+                             "version of OpenVINO Tokenizers" % len(inputs))
+        has_skips = len(inputs) == 7
+        self.with_pattern(_u8(inputs[5 + has_skips]).tobytes())
+        keep = []
+        rin = _ragged_in(*inputs[:5], skips=inputs[5] if has_skips else None, keep=keep)
+        n_rows, cap = rin.n_rows, rin.n_chars + rin.n_elems
+        orb, ore = np.empty(max(n_rows, 1), np.int32), np.empty(max(n_rows, 1), np.int32)
+        ob, oe, osk = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.uint8)
+        out = K.RaggedStringsOut(_ptr(orb), _ptr(ore), _ptr(ob), _ptr(oe), _ptr(osk), cap, 0, 0, K.MEM_HOST)
+        K.check(K.lib().b200tok_specialsplit_run(self._h, C.byref(rin), C.byref(out), None))
+        P = out.n_elems
+        return [orb[:n_rows].copy(), ore[:n_rows].copy(), ob[:P].copy(), oe[:P].copy(), keep[4], osk[:P].astype(bool)]
+
+
 class BPETokenizer(_Handle):
     """BPETokenizer(unk_token, fuse_unk, suffix_indicator, end_suffix, byte_fallback, cache_capacity)."""
 

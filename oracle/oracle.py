@@ -18,7 +18,7 @@ _LIB_PATH = _HERE / "liboracle.so"
 
 __all__ = [
     "build", "lib", "pcre2_available", "BpeOracle", "WordpieceOracle", "SplitOracle", "VocabEncoderOracle",
-    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense",
+    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense", "SpecialTokensSplitOracle", "special_tokens_pattern",
 ]
 
 
@@ -194,6 +194,40 @@ class SplitOracle:
         if getattr(self, "_h", None):
             lib().orc_split_destroy(self._h)
             self._h = None
+
+
+def special_tokens_pattern(tokens):
+    """The split pattern the reference converter builds for a list of special tokens — a restatement of
+    SpecialTokensSplit.get_ov_subgraph (reference python/openvino_tokenizers/tokenizer_pipeline.py:138-158) and quote_meta
+    (utils.py:421-429).  tokens: iterable of (text, strip_left, strip_right); sorted descending like __post_init__ (:95-97)."""
+    def quote_meta(t):
+        return "".join(("" if (ch.isalnum() or ch in ("_", "\u2581", "\uff5c")) else "\\") + ch for ch in t)
+    toks = sorted({(str(t[0]), bool(t[1]), bool(t[2])) for t in tokens}, reverse=True)
+    groups = {}
+    for text, sl, sr in toks:
+        groups.setdefault((sl, sr), []).append(text)
+    return "|".join(r"(?:\s*)" * sl + "(" + "|".join(quote_meta(t) for t in ts) + ")" + r"(?:\s*)" * sr for (sl, sr), ts in groups.items())
+
+
+class SpecialTokensSplitOracle(SplitOracle):
+    """SpecialTokensSplit (reference src/special_tokens_split.cpp:61-162) on the system PCRE2."""
+
+    def __init__(self, pattern):
+        super().__init__(pattern, "isolate")
+
+    def __call__(self, rb, re_, begins, ends, chars, skips=None):
+        rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+        B = len(rb)
+        sk = None if skips is None else _u8(np.asarray(skips, dtype=np.uint8))
+        cap = len(chars) + len(begins) + 16
+        orb, ore = np.empty(B, np.int32), np.empty(B, np.int32)
+        ob, oe, osk = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.uint8)
+        lib().orc_special_split_run.restype = C.c_int64
+        P = lib().orc_special_split_run(self._h, _p(rb, _i32p), _p(re_, _i32p), C.c_int64(B), _p(begins, _i32p), _p(ends, _i32p),
+                                        _p(chars, _u8p), _p(sk, _u8p), _p(orb, _i32p), _p(ore, _i32p), _p(ob, _i32p), _p(oe, _i32p),
+                                        _p(osk, _u8p), C.c_int64(cap))
+        assert P >= 0
+        return orb, ore, ob[:P].copy(), oe[:P].copy(), osk[:P].copy()
 
 
 class VocabEncoderOracle:

@@ -7,6 +7,7 @@
                                 factory methods of python/openvino_tokenizers/tokenizer_pipeline.py:354-470
   post_ops_layer_tests.json     the reference's known-answer vectors for RaggedToDense and CombineSegments
                                 (tests/layer_tests.py:497-644)
+  special_tokens_split_layer_tests.json  the reference's known-answer vectors for SpecialTokensSplit (tests/layer_tests.py:405-457)
   hf_<vocab>.json               ids produced by HuggingFace `tokenizers` for the frozen synthetic vocabularies
                                 (second oracle; the reference reports 100 % agreement with HF for these families)
 """
@@ -102,6 +103,56 @@ def make_post_golden():
     print("ragged_to_dense cases", len(r2d), "combine_segments cases", len(comb))
 
 
+def make_special_golden():
+    """The reference's SpecialTokensSplit known-answer vectors (tests/layer_tests.py:405-457).  The split pattern of every
+    case is built by the reference's own code (SpecialToken / SpecialTokensSplit.get_ov_subgraph of
+    python/openvino_tokenizers/tokenizer_pipeline.py:80-158, exec'd up to the node construction) and the oracle must
+    reproduce the expected pieces and skip flags before the case is written."""
+    from collections import defaultdict
+    import oracle
+    from openvino_tokenizers_b200.strings import add_ragged_dimension, pack_strings, unpack_strings
+    utils_src = (REF / "python/openvino_tokenizers/utils.py").read_text()
+    a = utils_src.index("def quote_meta(")
+    b = utils_src.index("\n\n\n", a)
+    ns = {"Union": __import__("typing").Union}
+    exec(utils_src[a:b], ns)
+    src = (REF / "python/openvino_tokenizers/tokenizer_pipeline.py").read_text()
+    a = src.index("@dataclass(frozen=True, order=True)\nclass SpecialToken:")
+    b = src.index("@dataclass\nclass SpecialTokensSplit", a)
+    ns.update({"dataclass": dataclass, "field": field})
+    exec(src[a:b], ns)
+    SpecialToken = ns["SpecialToken"]
+    a = src.index("        grouped_tokens = defaultdict(list)", b)
+    b2 = src.index("        input_nodes.extend(create_string_constant_node(split_pattern))", a)
+    body = "def build_pattern(self):\n" + src[a:b2] + "        return split_pattern\n"
+    ns.update({"defaultdict": defaultdict})
+    exec(body, ns)
+
+    class Step:
+        def __init__(self, toks):
+            self.special_tokens = sorted(toks, reverse=True)
+    out = []
+    lt = (REF / "tests/layer_tests.py").read_text()
+    tree = ast.parse(lt)
+    cases_ = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "test_special_tokens_split":
+            cases_ = eval(compile(ast.Expression(node.decorator_list[0].args[1]), "layer_tests", "eval"), {"SpecialToken": SpecialToken})
+    for toks, text, expected, expected_skips in cases_:
+        pattern = ns["build_pattern"](Step(toks))
+        assert pattern == oracle.special_tokens_pattern([(t.text, t.strip_left, t.strip_right) for t in toks]), pattern
+        bb, ee, cc = pack_strings([text])
+        rb, re_ = add_ragged_dimension(bb, ee)
+        r = oracle.SpecialTokensSplitOracle(pattern)(rb, re_, bb, ee, cc)
+        got = [p.decode() for p in unpack_strings(r[2], r[3], cc)]
+        assert got == list(expected) and r[4].tolist() == list(expected_skips), (text, got, r[4])
+        out.append(dict(tokens=[[t.text, t.strip_left, t.strip_right] for t in toks], pattern=pattern, text=text,
+                        expected=list(expected), expected_skips=list(expected_skips)))
+    (GOLDEN / "special_tokens_split_layer_tests.json").write_text(json.dumps(
+        dict(source="reference tests/layer_tests.py:405-457", cases=out), ensure_ascii=False, indent=1))
+    print("special tokens split cases", len(out))
+
+
 def make_hf_golden():
     import numpy as np
     import cases
@@ -127,10 +178,12 @@ def make_hf_golden():
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["regex", "hf", "post"]
+    which = sys.argv[1:] or ["regex", "hf", "post", "special"]
     if "regex" in which:
         make_regex_golden()
     if "hf" in which:
         make_hf_golden()
     if "post" in which:
         make_post_golden()
+    if "special" in which:
+        make_special_golden()
