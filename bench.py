@@ -211,7 +211,7 @@ def main():
     import torch
     import torch.distributed as dist
     from openvino_tokenizers_b200 import runtime as R
-    from openvino_tokenizers_b200.sharded import allgatherv_ragged
+    from openvino_tokenizers_b200.sharded import allgather_ragged_slots
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -229,13 +229,25 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
+    # N > 1: the shard is cut into row blocks; block k+1 is tokenised while block k's id rows are all-gathered (NCCL runs the
+    # collective on its own stream once the producing kernels are done), so the exchange overlaps the compute
+    n_blocks = int(os.environ.get("B200TOK_BENCH_BLOCKS", "2")) if world > 1 else 1
+    if world > 1:
+        blocks = [R.to_device(bk, dev) for bk in R.split_rows(batch, n_blocks)]
+        block_out = [pipe.alloc_device_out(bk.n_rows, bk.n_chars + bk.n_elems) for bk in blocks]
+        gathered = [torch.empty(world * bk.n_chars, dtype=torch.int32, device=dev) for bk in blocks]
+
     def step_device():
-        o = pipe.run_device(db)
-        if world > 1:
-            n = int(o["n"].item())
-            counts = o["ends"] - o["begins"]
-            allgatherv_ragged(o["ids"][:n], counts)
-        return o
+        if world == 1:
+            return pipe.run_device(db)
+        works = []
+        for bk, bo, g in zip(blocks, block_out, gathered):
+            o = pipe.run_device(bk, bo)
+            # ids <= bytes (src/bpe_tokenizer.cpp:135): gather the first n_chars slots of every rank's buffer, no host sync
+            works.append(allgather_ragged_slots(o["ids"][: bk.n_chars], o["begins"], o["ends"], g, async_op=True))
+        for wk in works:
+            wk()
+        return block_out
 
     def barrier():
         torch.cuda.synchronize()
@@ -276,7 +288,7 @@ def main():
     pipe.set_timing(False)
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
-    n_ids = int(o["n"].item())
+    n_ids = int(o["n"].item()) if world == 1 else int(sum(int(x["n"].item()) for x in o))
 
     # ---- end to end: host (pinned) buffers -> C ABI -> host buffers, every step ----
     barrier()
@@ -298,7 +310,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        algo_bytes = n_bytes + 16 * db.n_rows + 4 * n_ids
+        algo_bytes = (n_bytes + 16 * db.n_rows + 4 * n_ids) // n_blocks     # per launch: N > 1 launches the kernel once per row block
         k_ms = statistics.mean(kernel_ms) if kernel_ms else None
         achieved = algo_bytes / 1e9 / (k_ms / 1e3) if k_ms else None
         traffic = None
@@ -311,7 +323,7 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                     "traffic": traffic, "kernel": pipe.dominant_kernel, "kernel_ms": k_ms,
                     "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                    "kernel_share_of_step": (k_ms / ms_per_step) if k_ms else None}
+                    "kernel_share_of_step": (k_ms * n_blocks / ms_per_step) if k_ms else None, "launches_per_step": n_blocks}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             run = oracle_runner(w)
@@ -330,7 +342,7 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": w["name"], "rows_per_gpu": db.n_rows, "row_bytes": w["row_bytes"], "tokens_per_gpu": n_ids,
                        "l2": "256 MiB buffer zeroed between timed steps (L2 flush), outside the per-step event pair",
-                       "multi_gpu": "row shards + all-gatherv of ragged ids over NCCL" if world > 1 else "single GPU"},
+                       "multi_gpu": "row shards in %d row block(s);" % n_blocks + " all-gatherv of block k's ragged id rows over NCCL (fixed-capacity slots, no host sync) overlaps the tokenisation of block k+1" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "path": "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -47,6 +47,20 @@ def to_device(batch, device) -> DeviceBatch:
     return DeviceBatch(t(rb), t(re_), t(b), t(e), t(np.concatenate([c, pad])), int(len(c)))
 
 
+def split_rows(batch, parts: int):
+    """Cut a host batch (rb, re, begins, ends, chars) with one element per row and contiguous chars into `parts` row blocks
+    (each rebased to its own chars slice) — the unit the multi-GPU step pipelines: tokenise block k+1 while block k is gathered."""
+    rb, re_, b, e, c = batch
+    n = len(rb)
+    out = []
+    for k in range(parts):
+        lo, hi = n * k // parts, n * (k + 1) // parts
+        p0, p1 = int(rb[lo]), int(re_[hi - 1])
+        c0, c1 = int(b[p0]), int(e[p1 - 1])
+        out.append((rb[lo:hi] - p0, re_[lo:hi] - p0, b[p0:p1] - c0, e[p0:p1] - c0, c[c0:c1]))
+    return out
+
+
 def to_pinned(batch):
     rb, re_, b, e, c = batch
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
@@ -111,9 +125,9 @@ class TokenizerPipeline:
                          n=torch.zeros(1, dtype=torch.int64, device=dev), cap=capacity)
         return self._out
 
-    def run_device(self, db: DeviceBatch):
-        """Asynchronous on the current torch stream; results in self._out (ids[:n])."""
-        o = self._out
+    def run_device(self, db: DeviceBatch, out=None):
+        """Asynchronous on the current torch stream; results in `out` (from alloc_device_out) or self._out (ids[:n])."""
+        o = out if out is not None else self._out
         if o is None or o["begins"].numel() != db.n_rows or o["cap"] < db.n_chars + db.n_elems:
             o = self.alloc_device_out(db.n_rows, db.n_chars + db.n_elems)
         rin = K.RaggedStrings(db.rb.data_ptr(), db.re.data_ptr(), db.n_rows, db.begins.data_ptr(), db.ends.data_ptr(),

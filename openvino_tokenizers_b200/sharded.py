@@ -49,3 +49,36 @@ def allgatherv_ragged(local_ids: torch.Tensor, local_row_counts: torch.Tensor, g
     ends = torch.cumsum(counts, 0, dtype=torch.int64).to(torch.int32)
     begins = ends - counts
     return begins, ends, ids
+
+
+def allgather_ragged_slots(ids_buf: torch.Tensor, begins: torch.Tensor, ends: torch.Tensor, out_ids: torch.Tensor = None, group=None,
+                           async_op: bool = False):
+    """All-gatherv of ragged int32 rows without a host synchronisation or staging copy.
+
+    Every rank contributes its whole fixed-capacity id buffer (ids_buf: int32[cap], rows at [begins[i], ends[i]), the
+    tail beyond the last row unspecified) straight from where the tokenizer wrote it; rank r's buffer lands in slot r of
+    the result and its row offsets are shifted by r * cap.  The gaps between the slots are legal in the reference's
+    ragged representation (begins/ends need not be contiguous, e.g. after Truncate).  Requires the same cap and the same
+    number of rows on every rank (the weak-scaling layout: equal shards).
+    returns (begins int32[W*B], ends int32[W*B], ids int32[W*cap]), identical on every rank.  With async_op=True the
+    collectives are only enqueued (the caller's stream does not wait for them) and a function is returned that waits and
+    yields the tuple — this is how a multi-block step overlaps the exchange of block k with the tokenisation of block k+1.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    cap, B = ids_buf.numel(), begins.numel()
+    dev = ids_buf.device
+    if out_ids is None:
+        out_ids = torch.empty(world * cap, dtype=torch.int32, device=dev)
+    w1 = dist.all_gather_into_tensor(out_ids, ids_buf, group=group, async_op=async_op)
+    be = (torch.cat([begins, ends]) + rank * cap).to(torch.int32)  # [2 * B], offsets into the gathered buffer
+    all_be = torch.empty(world * 2 * B, dtype=torch.int32, device=dev)
+    w2 = dist.all_gather_into_tensor(all_be, be, group=group, async_op=async_op)
+
+    def finish():
+        if async_op:
+            w1.wait()
+            w2.wait()
+        v = all_be.view(world, 2, B)
+        return v[:, 0].reshape(-1), v[:, 1].reshape(-1), out_ids
+    return finish if async_op else finish()

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from openvino_tokenizers_b200.sharded import allgatherv_ragged, shard_bounds
+from openvino_tokenizers_b200.sharded import allgather_ragged_slots, allgatherv_ragged, shard_bounds
 
 
 def _free_port():
@@ -41,6 +41,46 @@ def test_allgatherv_ragged_world2(n_rows):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_rows, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def _slots_worker(rank, world, port, n_rows, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cap = 10 * n_rows + 5
+    rows = []
+    for r in range(world):                       # every rank can rebuild every shard: seeded per shard
+        rng = np.random.default_rng(100 + r)
+        counts = rng.integers(0, 9, size=n_rows).astype(np.int32)
+        ids = rng.integers(0, 50000, size=int(counts.sum())).astype(np.int32)
+        ends = np.cumsum(counts).astype(np.int32)
+        rows.append((ends - counts, ends, ids))
+    b, e, ids = rows[rank]
+    buf = torch.full((cap,), -1, dtype=torch.int32)
+    buf[: len(ids)] = torch.from_numpy(ids)
+    gb, ge, gids = allgather_ragged_slots(buf, torch.from_numpy(b.copy()), torch.from_numpy(e.copy()))
+    ok = gb.numel() == world * n_rows and gids.numel() == world * cap
+    for r in range(world):
+        rb, re_, rids = rows[r]
+        for i in range(n_rows):
+            k = r * n_rows + i
+            ok &= bool(np.array_equal(gids[int(gb[k]): int(ge[k])].numpy(), rids[rb[i]: re_[i]]))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows", [1, 64])
+def test_allgather_ragged_slots_world2(n_rows):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slots_worker, args=(r, 2, port, n_rows, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
