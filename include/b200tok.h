@@ -277,6 +277,27 @@ typedef struct {
 B200TOK_API int b200tok_post_dense_run(int device, const b200tok_post_desc* desc, const int32_t* begins, const int32_t* ends, int64_t n_rows,
                                        const int32_t* ids, int64_t n_ids, int32_t* out_ids, uint8_t* out_mask, int mem, void* cuda_stream);
 
+/* ---- Byte-level shims and detokenizer tail (stateless) -------------------------------------------
+ * BytesToChars, src/bytes_to_chars.cpp:284-339: every byte of every non-skipped element becomes the 1-2 UTF-8 bytes of its
+ * GPT-2 printable character; outputs begins/ends [n_elems] and chars (worst case 2 * n_chars); in->skips optional.
+ * Rows must cover the elements contiguously and in order (what StringTensorUnpack / RegexSplit produce).               */
+B200TOK_API int b200tok_bytes_to_chars_run(int device, const b200tok_ragged_strings* in, int32_t* out_begins, int32_t* out_ends,
+                                           uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars, void* cuda_stream);
+/* CharsToBytes, src/chars_to_bytes.cpp:31-68: the inverse map; the ragged dimension is fused (one output string per row):
+ * outputs begins/ends [n_rows] and chars (worst case n_chars).                                                         */
+B200TOK_API int b200tok_chars_to_bytes_run(int device, const b200tok_ragged_strings* in, int32_t* out_begins, int32_t* out_ends,
+                                           uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars, void* cuda_stream);
+/* FuzeRagged, src/fuze.cpp:20-40: out_begins[r] = begins[rb[r]], out_ends[r] = ends[re[r] - 1].                        */
+B200TOK_API int b200tok_fuze_ragged_run(int device, const int32_t* ragged_begins, const int32_t* ragged_ends, int64_t n_rows,
+                                        const int32_t* begins, const int32_t* ends, int64_t n_elems, int32_t* out_begins,
+                                        int32_t* out_ends, int mem, void* cuda_stream);
+/* UTF8Validate, src/utf8_validate.cpp:18-137: malformed sequences are replaced by U+FFFD (replace_mode != 0) or dropped.
+ * Worst case 3 * n_chars output bytes.  Like the reference, output offsets start at begins[0]; *n_chars = the extent of
+ * out_chars in use.                                                                                                    */
+B200TOK_API int b200tok_utf8_validate_run(int device, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
+                                          int64_t n_chars, int replace_mode, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                          int64_t chars_capacity, int64_t* n_chars_out, int mem, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,5 +147,6 @@ EXPORTED_SYMBOLS = [
     "b200tok_vocabenc_create", "b200tok_vocabenc_run",
     "b200tok_vocabdec_create", "b200tok_vocabdec_run", "b200tok_vocabdec_max_chars",
     "b200tok_bytefallback_run",
+    "b200tok_bytes_to_chars_run", "b200tok_chars_to_bytes_run", "b200tok_fuze_ragged_run", "b200tok_utf8_validate_run",
     "b200tok_truncate_run", "b200tok_combine_segments_run", "b200tok_ragged_to_dense_run", "b200tok_post_dense_run",
 ]

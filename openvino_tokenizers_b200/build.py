@@ -9,7 +9,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libb200tok.so"
 SOURCES = ["api.cu", "tables.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "kernels_fast.cuh", "kernels_misc.cuh", "kernels_special.cuh", "kernels_tail.cuh", "tok_core.cuh", "tables.hpp", "unicode_ranges.inc",
+DEPS = SOURCES + ["kernels.cuh", "kernels_fast.cuh", "kernels_misc.cuh", "kernels_shim.cuh", "kernels_special.cuh", "kernels_tail.cuh", "tok_core.cuh", "tables.hpp", "unicode_ranges.inc",
                   "../../include/b200tok.h"]
 
 

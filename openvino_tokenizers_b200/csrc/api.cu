@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_shim.cuh"
 #include "kernels_special.cuh"
 #include "kernels_tail.cuh"
 #include "tables.hpp"
@@ -1332,6 +1333,202 @@ B200TOK_API int b200tok_post_dense_run(int device, const b200tok_post_desc* d, c
     if (host) {
         CU(cudaMemcpyAsync(out_ids, d_o, total * 4, cudaMemcpyDeviceToHost, st));
         if (out_mask) CU(cudaMemcpyAsync(out_mask, d_m, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+}  // extern "C"
+
+// ---- byte-level shims and detokenizer tail (stateless) ----
+namespace {
+// stages a host array on the device (stream-ordered scratch) or passes a device pointer through
+template <class T>
+int stage_in(AsyncBuf& buf, const T* src, int64_t n, bool host, cudaStream_t st, const T*& dev) {
+    dev = src;
+    if (!host || n <= 0) { if (n <= 0) dev = nullptr; return 0; }
+    CU(buf.alloc((size_t)n * sizeof(T) + 64, st));
+    CU(cudaMemcpyAsync(buf.p, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st));
+    dev = buf.as<T>();
+    return 0;
+}
+int scan_i32(AsyncBuf& tmp, const int32_t* in, int32_t* out, int64_t n, cudaStream_t st) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st);
+    CU(tmp.alloc(bytes + 256, st));
+    cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st);
+    return 0;
+}
+bool rows_partition_elems(const b200tok_ragged_strings* in) {     // rows cover the elements contiguously and in order
+    const int32_t *rb = in->ragged_begins, *re = in->ragged_ends;
+    int32_t cur = 0;
+    for (int64_t r = 0; r < in->n_rows; ++r) { if (rb[r] != cur || re[r] < rb[r]) return false; cur = re[r]; }
+    return cur == in->n_elems;
+}
+}  // namespace
+
+extern "C" {
+
+B200TOK_API int b200tok_bytes_to_chars_run(int device, const b200tok_ragged_strings* in, int32_t* out_begins, int32_t* out_ends,
+                                           uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars_out, void* stream) {
+    int rc = validate_in(in);
+    if (rc) return rc;
+    if (!n_chars_out || chars_capacity < 0) return fail(B200TOK_E_INVALID, "bad arguments");
+    *n_chars_out = 0;
+    const int64_t E = in->n_elems, N = in->n_chars;
+    if (E == 0) return B200TOK_OK;
+    if (!out_begins || !out_ends || (chars_capacity > 0 && !out_chars)) return fail(B200TOK_E_INVALID, "missing output buffers");
+    const bool host = in->mem == B200TOK_MEM_HOST;
+    if (host && !rows_partition_elems(in)) return fail(B200TOK_E_UNSUPPORTED, "BytesToChars: rows must cover the elements contiguously and in order");
+    if ((rc = tail_device(device))) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    AsyncBuf bb, be, bc, bs, bt, blen, bob, boe, boc, bscan, btot;
+    const int32_t *d_b, *d_e; const uint8_t *d_c, *d_s;
+    if ((rc = stage_in(bb, in->begins, E, host, st, d_b)) || (rc = stage_in(be, in->ends, E, host, st, d_e)) ||
+        (rc = stage_in(bc, in->chars, N, host, st, d_c)) || (rc = stage_in(bs, in->skips, in->skips ? E : 0, host, st, d_s))) return rc;
+    uint16_t cp[256];
+    gpt2_build_byte_codepoints(cp);
+    CU(bt.alloc(512, st));
+    CU(cudaMemcpyAsync(bt.p, cp, 512, cudaMemcpyHostToDevice, st));
+    CU(blen.alloc((size_t)E * 4, st)); CU(btot.alloc(8, st));
+    int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
+    if (host) { CU(bob.alloc((size_t)E * 4, st)); CU(boe.alloc((size_t)E * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
+    const unsigned blocks = (unsigned)((E + 255) / 256);
+    b2c_len_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, d_s, E, bt.as<uint16_t>(), blen.as<int32_t>());
+    if ((rc = scan_i32(bscan, blen.as<int32_t>(), d_ob, E, st))) return rc;
+    b2c_write_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, d_s, E, bt.as<uint16_t>(), d_ob, blen.as<int32_t>(), d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    CU(cudaGetLastError());
+    int64_t total = 0;
+    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_chars_out = total;
+    if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, E * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, E * 4, cudaMemcpyDeviceToHost, st));
+        if (total) CU(cudaMemcpyAsync(out_chars, d_oc, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_chars_to_bytes_run(int device, const b200tok_ragged_strings* in, int32_t* out_begins, int32_t* out_ends,
+                                           uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars_out, void* stream) {
+    int rc = validate_in(in);
+    if (rc) return rc;
+    if (!n_chars_out || chars_capacity < 0) return fail(B200TOK_E_INVALID, "bad arguments");
+    *n_chars_out = 0;
+    const int64_t B = in->n_rows, E = in->n_elems, N = in->n_chars;
+    if (B == 0) return B200TOK_OK;
+    if (!out_begins || !out_ends || (chars_capacity > 0 && !out_chars)) return fail(B200TOK_E_INVALID, "missing output buffers");
+    const bool host = in->mem == B200TOK_MEM_HOST;
+    if (host && !rows_partition_elems(in)) return fail(B200TOK_E_UNSUPPORTED, "CharsToBytes: rows must cover the elements contiguously and in order");
+    if ((rc = tail_device(device))) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    AsyncBuf brb, bre, bb, be, bc, bt, blen, boff, bob, boe, boc, bscan, btot;
+    const int32_t *d_rb, *d_re, *d_b, *d_e; const uint8_t* d_c;
+    if ((rc = stage_in(brb, in->ragged_begins, B, host, st, d_rb)) || (rc = stage_in(bre, in->ragged_ends, B, host, st, d_re)) ||
+        (rc = stage_in(bb, in->begins, E, host, st, d_b)) || (rc = stage_in(be, in->ends, E, host, st, d_e)) ||
+        (rc = stage_in(bc, in->chars, N, host, st, d_c))) return rc;
+    uint16_t cp[256];
+    gpt2_build_byte_codepoints(cp);
+    uint8_t pair_map[256] = {};                       // src/chars_to_bytes.cpp:20-29
+    for (int b = 0; b < 256; ++b)
+        if (cp[b] >= 0x80) pair_map[((0xC0 | (cp[b] >> 6)) - 194) * 64 + ((0x80 | (cp[b] & 0x3F)) - 128)] = (uint8_t)b;
+    CU(bt.alloc(256, st));
+    CU(cudaMemcpyAsync(bt.p, pair_map, 256, cudaMemcpyHostToDevice, st));
+    CU(blen.alloc((size_t)std::max<int64_t>(E, 1) * 4, st)); CU(boff.alloc((size_t)std::max<int64_t>(E, 1) * 4, st)); CU(btot.alloc(8, st));
+    CU(cudaMemsetAsync(btot.p, 0, 8, st));
+    int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
+    if (host) { CU(bob.alloc((size_t)B * 4, st)); CU(boe.alloc((size_t)B * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
+    if (E > 0) {
+        const unsigned blocks = (unsigned)((E + 255) / 256);
+        c2b_len_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, E, blen.as<int32_t>());
+        if ((rc = scan_i32(bscan, blen.as<int32_t>(), boff.as<int32_t>(), E, st))) return rc;
+        c2b_write_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, E, N, bt.as<uint8_t>(), boff.as<int32_t>(), blen.as<int32_t>(), d_oc, chars_capacity, btot.as<int64_t>());
+    }
+    c2b_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_rb, d_re, B, boff.as<int32_t>(), blen.as<int32_t>(), E, d_ob, d_oe);
+    CU(cudaGetLastError());
+    int64_t total = 0;
+    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_chars_out = total;
+    if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, B * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, B * 4, cudaMemcpyDeviceToHost, st));
+        if (total) CU(cudaMemcpyAsync(out_chars, d_oc, total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_fuze_ragged_run(int device, const int32_t* rb, const int32_t* re, int64_t n_rows, const int32_t* begins,
+                                        const int32_t* ends, int64_t n_elems, int32_t* out_begins, int32_t* out_ends, int mem, void* stream) {
+    if (n_rows < 0 || n_elems < 0 || (n_rows > 0 && (!rb || !re || !out_begins || !out_ends || !begins || !ends))) return fail(B200TOK_E_INVALID, "bad arguments");
+    if (n_rows == 0) return B200TOK_OK;
+    const bool host = mem == B200TOK_MEM_HOST;
+    if (host)
+        for (int64_t r = 0; r < n_rows; ++r) {
+            const int64_t last = re[r] > rb[r] ? re[r] - 1 : re[r];
+            if (rb[r] < 0 || rb[r] >= n_elems || last < 0 || last >= n_elems) return fail(B200TOK_E_INVALID, "FuzeRagged: row %lld refers to an element outside [0, %lld)", (long long)r, (long long)n_elems);
+        }
+    int rc = tail_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    AsyncBuf brb, bre, bb, be, bo;
+    const int32_t *d_rb, *d_re, *d_b, *d_e;
+    if ((rc = stage_in(brb, rb, n_rows, host, st, d_rb)) || (rc = stage_in(bre, re, n_rows, host, st, d_re)) ||
+        (rc = stage_in(bb, begins, n_elems, host, st, d_b)) || (rc = stage_in(be, ends, n_elems, host, st, d_e))) return rc;
+    int32_t *d_ob = out_begins, *d_oe = out_ends;
+    if (host) { CU(bo.alloc((size_t)n_rows * 8, st)); d_ob = bo.as<int32_t>(); d_oe = d_ob + n_rows; }
+    fuze_ragged_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(d_rb, d_re, n_rows, d_b, d_e, d_ob, d_oe);
+    CU(cudaGetLastError());
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, n_rows * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, n_rows * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_utf8_validate_run(int device, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
+                                          int64_t n_chars, int replace_mode, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                          int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
+    if (n < 0 || n_chars < 0 || chars_capacity < 0 || !n_chars_out || (n > 0 && (!begins || !ends || !out_begins || !out_ends))) return fail(B200TOK_E_INVALID, "bad arguments");
+    *n_chars_out = 0;
+    if (n == 0) return B200TOK_OK;
+    int rc = tail_device(device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = mem == B200TOK_MEM_HOST;
+    AsyncBuf bb, be, bc, blen, boff, bob, boe, boc, bscan, btot;
+    const int32_t *d_b, *d_e; const uint8_t* d_c;
+    if ((rc = stage_in(bb, begins, n, host, st, d_b)) || (rc = stage_in(be, ends, n, host, st, d_e)) || (rc = stage_in(bc, chars, n_chars, host, st, d_c))) return rc;
+    int32_t base = 0;                                   // the reference's output cursor starts at begins[0] (src/utf8_validate.cpp:50)
+    if (host) base = begins[0];
+    else { CU(cudaMemcpyAsync(&base, begins, 4, cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+    CU(blen.alloc((size_t)n * 4, st)); CU(boff.alloc((size_t)n * 4, st)); CU(btot.alloc(8, st));
+    int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
+    if (host) { CU(bob.alloc((size_t)n * 4, st)); CU(boe.alloc((size_t)n * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    utf8_len_kernel<<<blocks, 128, 0, st>>>(d_b, d_e, d_c, n, replace_mode, blen.as<int32_t>());
+    if ((rc = scan_i32(bscan, blen.as<int32_t>(), boff.as<int32_t>(), n, st))) return rc;
+    utf8_write_kernel<<<blocks, 128, 0, st>>>(d_b, d_e, d_c, n, replace_mode, base, boff.as<int32_t>(), blen.as<int32_t>(), d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    CU(cudaGetLastError());
+    int64_t total = 0;
+    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_chars_out = total;                               // extent of out_chars in use (= begins[0] + produced bytes)
+    if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
+        if (total > base) CU(cudaMemcpyAsync(out_chars + base, d_oc + base, total - base, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return B200TOK_OK;

@@ -324,6 +324,80 @@ class ByteFallback:
         return [ob, oe, oc[:n.value].copy()]
 
 
+class BytesToChars:
+    """BytesToChars; inputs ragged strings [0..4], optional skips [5] (reference src/bytes_to_chars.cpp:284-339)."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (5, 6):
+            raise ValueError("supported input sizes are 5 or 6")
+        keep = []
+        rin = _ragged_in(*inputs[:5], skips=inputs[5] if len(inputs) == 6 else None, keep=keep)
+        ob, oe = np.empty(max(rin.n_elems, 1), np.int32), np.empty(max(rin.n_elems, 1), np.int32)
+        cap = 2 * rin.n_chars
+        oc = np.empty(max(cap, 1), np.uint8)
+        n = C.c_int64(0)
+        K.check(K.lib().b200tok_bytes_to_chars_run(self.device, C.byref(rin), _ptr(ob), _ptr(oe), _ptr(oc), C.c_int64(cap), C.byref(n), None))
+        res = [keep[0], keep[1], ob[:rin.n_elems].copy(), oe[:rin.n_elems].copy(), oc[:n.value].copy()]
+        if len(inputs) == 6:
+            res.append(np.asarray(inputs[5]))
+        return res
+
+
+class CharsToBytes:
+    """CharsToBytes; inputs ragged strings [0..4]; outputs one string per row (reference src/chars_to_bytes.cpp:31-68)."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def evaluate(self, inputs):
+        if len(inputs) != 5:
+            raise ValueError("CharsToBytes expects 5 inputs")
+        keep = []
+        rin = _ragged_in(*inputs[:5], keep=keep)
+        ob, oe = np.empty(max(rin.n_rows, 1), np.int32), np.empty(max(rin.n_rows, 1), np.int32)
+        cap = rin.n_chars
+        oc = np.empty(max(cap, 1), np.uint8)
+        n = C.c_int64(0)
+        K.check(K.lib().b200tok_chars_to_bytes_run(self.device, C.byref(rin), _ptr(ob), _ptr(oe), _ptr(oc), C.c_int64(cap), C.byref(n), None))
+        return [ob[:rin.n_rows].copy(), oe[:rin.n_rows].copy(), oc[:n.value].copy()]
+
+
+class FuzeRagged:
+    """FuzeRagged; inputs ragged_begins, ragged_ends, begins, ends (reference src/fuze.cpp:20-40)."""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def evaluate(self, inputs):
+        if len(inputs) != 4:
+            raise ValueError("FuzeRagged expects 4 inputs")
+        rb, re_, b, e = (_i32(x).reshape(-1) for x in inputs)
+        ob, oe = np.empty(len(rb), np.int32), np.empty(len(rb), np.int32)
+        K.check(K.lib().b200tok_fuze_ragged_run(self.device, _ptr(rb), _ptr(re_), C.c_int64(len(rb)), _ptr(b), _ptr(e), C.c_int64(len(b)),
+                                                _ptr(ob), _ptr(oe), K.MEM_HOST, None))
+        return [ob, oe]
+
+
+class UTF8Validate:
+    """UTF8Validate(replace_mode); inputs strings [0..2] (reference src/utf8_validate.cpp:18-137)."""
+
+    def __init__(self, replace_mode=False, device=0):
+        self.replace_mode, self.device = bool(replace_mode), device
+
+    def evaluate(self, inputs):
+        b, e, c = _i32(inputs[0]).reshape(-1), _i32(inputs[1]).reshape(-1), _u8(inputs[2]).reshape(-1)
+        cap = 3 * c.size + (int(b[0]) if len(b) else 0)
+        ob, oe = np.empty(max(len(b), 1), np.int32), np.empty(max(len(b), 1), np.int32)
+        oc = np.zeros(max(cap, 1), np.uint8)
+        n = C.c_int64(0)
+        K.check(K.lib().b200tok_utf8_validate_run(self.device, _ptr(b), _ptr(e), C.c_int64(len(b)), _ptr(c) if c.size else None, C.c_int64(c.size),
+                                                  int(self.replace_mode), _ptr(ob), _ptr(oe), _ptr(oc), C.c_int64(cap), C.byref(n), K.MEM_HOST, None))
+        return [ob[:len(b)].copy(), oe[:len(b)].copy(), oc[:n.value].copy()]
+
+
 class Truncate:
     """Truncate(num_inputs): inputs [3i..3i+2] ragged i32 (begins, ends, elems) per sequence, then max_length (i32 scalar),
     truncation side ("left"|"right") and mode ("only_first"|"only_second"|"longest_first") as u8 strings

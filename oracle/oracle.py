@@ -18,7 +18,7 @@ _LIB_PATH = _HERE / "liboracle.so"
 
 __all__ = [
     "build", "lib", "pcre2_available", "BpeOracle", "WordpieceOracle", "SplitOracle", "VocabEncoderOracle",
-    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense", "SpecialTokensSplitOracle", "special_tokens_pattern",
+    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense", "SpecialTokensSplitOracle", "special_tokens_pattern", "bytes_to_chars", "chars_to_bytes", "fuze_ragged", "utf8_validate",
 ]
 
 
@@ -323,3 +323,45 @@ def ragged_to_dense(begins, ends, elems, target_dim, default_value, pad_right=Tr
     lib().orc_ragged_to_dense(_p(begins, _i32p), _p(ends, _i32p), C.c_int64(n), _p(elems, _i32p), C.c_int32(target_dim),
                               C.c_int32(default_value), int(bool(pad_right)), int(bool(pad_max_length)), _p(out, _i32p), _p(mask, _u8p))
     return out, mask
+
+
+def bytes_to_chars(rb, re_, begins, ends, chars, skips=None):
+    """BytesToChars (reference src/bytes_to_chars.cpp:284-339).  Returns (begins, ends, chars)."""
+    rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+    sk = None if skips is None else _u8(np.asarray(skips, dtype=np.uint8))
+    ob, oe = np.zeros(len(begins), np.int32), np.zeros(len(begins), np.int32)
+    oc = np.empty(2 * len(chars) + 16, np.uint8)
+    lib().orc_bytes_to_chars.restype = C.c_int64
+    n = lib().orc_bytes_to_chars(_p(rb, _i32p), _p(re_, _i32p), C.c_int64(len(rb)), _p(begins, _i32p), _p(ends, _i32p), _p(chars, _u8p),
+                                 _p(sk, _u8p), _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p))
+    return ob, oe, oc[:n].copy()
+
+
+def chars_to_bytes(rb, re_, begins, ends, chars):
+    """CharsToBytes (reference src/chars_to_bytes.cpp:31-68).  Returns one string per row: (begins, ends, chars)."""
+    rb, re_, begins, ends, chars = _i32(rb), _i32(re_), _i32(begins), _i32(ends), _u8(chars)
+    ob, oe = np.zeros(len(rb), np.int32), np.zeros(len(rb), np.int32)
+    oc = np.empty(len(chars) + 16, np.uint8)
+    lib().orc_chars_to_bytes.restype = C.c_int64
+    n = lib().orc_chars_to_bytes(_p(rb, _i32p), _p(re_, _i32p), C.c_int64(len(rb)), _p(begins, _i32p), _p(ends, _i32p), _p(chars, _u8p),
+                                 _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p))
+    return ob, oe, oc[:n].copy()
+
+
+def fuze_ragged(rb, re_, begins, ends):
+    """FuzeRagged (reference src/fuze.cpp:20-40)."""
+    rb, re_, begins, ends = _i32(rb), _i32(re_), _i32(begins), _i32(ends)
+    ob, oe = np.empty(len(rb), np.int32), np.empty(len(rb), np.int32)
+    lib().orc_fuze_ragged(_p(rb, _i32p), _p(re_, _i32p), C.c_int64(len(rb)), _p(begins, _i32p), _p(ends, _i32p), _p(ob, _i32p), _p(oe, _i32p))
+    return ob, oe
+
+
+def utf8_validate(begins, ends, chars, replace_mode):
+    """UTF8Validate (reference src/utf8_validate.cpp:18-137).  Returns (begins, ends, chars[: extent])."""
+    begins, ends, chars = _i32(begins), _i32(ends), _u8(chars)
+    ob, oe = np.empty(len(begins), np.int32), np.empty(len(begins), np.int32)
+    oc = np.zeros(3 * len(chars) + 16 + (int(begins[0]) if len(begins) else 0), np.uint8)
+    lib().orc_utf8_validate.restype = C.c_int64
+    n = lib().orc_utf8_validate(_p(begins, _i32p), _p(ends, _i32p), C.c_int64(len(begins)), _p(chars, _u8p), int(bool(replace_mode)),
+                                _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p))
+    return ob, oe, oc[:n].copy()

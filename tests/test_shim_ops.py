@@ -1,0 +1,104 @@
+"""Byte-level shims and detokenizer tail: BytesToChars, CharsToBytes, FuzeRagged, UTF8Validate.
+CPU tier: the oracle against the reference's known-answer material (tests/golden/shim_ops_layer_tests.json: the UTF8Validate
+string list of the reference's tests/layer_tests.py:84-139 with the expectation its test uses, and the reference's literal
+byte -> char table).  GPU tier: the CUDA ops through the C ABI against the oracle, bit-exact."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import cases
+from openvino_tokenizers_b200.strings import add_ragged_dimension, pack_strings, unpack_strings
+
+GOLDEN = json.loads((Path(__file__).resolve().parent / "golden" / "shim_ops_layer_tests.json").read_text())
+
+
+def test_oracle_utf8_validate_reference_vectors(oracle_mod):
+    for c in GOLDEN["utf8_validate"]:
+        s = bytes.fromhex(c["input_hex"])
+        b, e, ch = pack_strings([s])
+        got = oracle_mod.utf8_validate(b, e, ch, c["mode"] == "replace")
+        assert bytes(got[2]).hex() == c["expected_hex"], (s, c["mode"])
+
+
+def test_oracle_byte_char_map_is_the_reference_table(oracle_mod):
+    table = [bytes.fromhex(h) for h in GOLDEN["bytes_to_chars_table_hex"]]
+    b, e, ch = pack_strings([bytes(range(256))])
+    rb, re_ = add_ragged_dimension(b, e)
+    ob, oe, oc = oracle_mod.bytes_to_chars(rb, re_, b, e, ch)
+    assert bytes(oc) == b"".join(table)
+    back = oracle_mod.chars_to_bytes(rb, re_, ob, oe, oc)
+    assert bytes(back[2]) == bytes(range(256)) and back[0].tolist() == [0] and back[1].tolist() == [256]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from openvino_tokenizers_b200 import ops as O
+    return O
+
+
+def _ragged(rng, strings, rows):
+    """Pack strings as elements and cut them into `rows` contiguous rows (some empty)."""
+    b, e, ch = pack_strings(strings)
+    cuts = np.sort(rng.integers(0, len(strings) + 1, size=rows - 1)) if rows > 1 else np.array([], np.int64)
+    rb = np.concatenate([[0], cuts]).astype(np.int32)
+    re_ = np.concatenate([cuts, [len(strings)]]).astype(np.int32)
+    return rb, re_, b, e, ch
+
+
+@pytest.mark.gpu
+def test_gpu_bytes_to_chars_and_back(ops, oracle_mod):
+    rng = np.random.default_rng(31)
+    strings = [bytes(rng.integers(0, 256, size=int(rng.integers(0, 40)), dtype=np.uint8)) for _ in range(3000)] + [b"", bytes(range(256))]
+    for rows in (1, 7, 500):
+        rb, re_, b, e, ch = _ragged(rng, strings, rows)
+        for skips in (None, rng.integers(0, 2, size=len(strings)).astype(bool)):
+            exp = oracle_mod.bytes_to_chars(rb, re_, b, e, ch, skips)
+            got = ops.BytesToChars().evaluate([rb, re_, b, e, ch] + ([skips] if skips is not None else []))
+            assert np.array_equal(got[2], exp[0]) and np.array_equal(got[3], exp[1]) and np.array_equal(got[4], exp[2])
+        # ... and back: CharsToBytes of the unskipped result restores the bytes, one string per row
+        exp = oracle_mod.bytes_to_chars(rb, re_, b, e, ch)
+        back_exp = oracle_mod.chars_to_bytes(rb, re_, exp[0], exp[1], exp[2])
+        back = ops.CharsToBytes().evaluate([rb, re_, exp[0], exp[1], exp[2]])
+        for k in range(3):
+            assert np.array_equal(back[k], back_exp[k])
+        rows_bytes = [b"".join(strings[int(rb[r]):int(re_[r])]) for r in range(rows)]
+        assert [bytes(x) for x in unpack_strings(back[0], back[1], back[2])] == rows_bytes
+
+
+@pytest.mark.gpu
+def test_gpu_fuze_ragged(ops, oracle_mod):
+    rng = np.random.default_rng(32)
+    strings = [b"x" * int(rng.integers(0, 9)) for _ in range(1000)]
+    for rows in (1, 13, 400):
+        rb, re_, b, e, _ = _ragged(rng, strings, rows)
+        keep = re_ > rb          # the reference reads element re[r] for an empty row: keep the test inside the buffer
+        rb2, re2 = rb[keep], re_[keep]
+        exp = oracle_mod.fuze_ragged(rb2, re2, b, e)
+        got = ops.FuzeRagged().evaluate([rb2, re2, b, e])
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+
+
+@pytest.mark.gpu
+def test_gpu_utf8_validate(ops, oracle_mod):
+    for c in GOLDEN["utf8_validate"]:
+        s = bytes.fromhex(c["input_hex"])
+        b, e, ch = pack_strings([s])
+        got = ops.UTF8Validate(c["mode"] == "replace").evaluate([b, e, ch])
+        assert bytes(got[2]).hex() == c["expected_hex"], (s, c["mode"])
+    rng = np.random.default_rng(33)
+    alphabet = [b"a", b" ", "é".encode(), "€".encode(), "😁".encode(), b"\x80", b"\xc3", b"\xe2\x82", b"\xf0\x9f", b"\xc0\x80", b"\xff", b"\xed\xa0\x80"]
+    strings = [b"".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=int(rng.integers(0, 30)))) for _ in range(4000)]
+    strings += [s.encode() for s in cases.EDGE_STRINGS] + [b"", b"\xe2", b"\xf0\x9f\x98"]
+    b, e, ch = pack_strings(strings)
+    for mode in (False, True):
+        exp = oracle_mod.utf8_validate(b, e, ch, mode)
+        got = ops.UTF8Validate(mode).evaluate([b, e, ch])
+        for k in range(3):
+            assert np.array_equal(got[k], exp[k]), (k, mode)
+    # offsets that do not start at 0: the reference's cursor starts at begins[0]
+    exp = oracle_mod.utf8_validate(b[5:], e[5:], ch, True)
+    got = ops.UTF8Validate(True).evaluate([b[5:], e[5:], ch])
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
+    assert np.array_equal(got[2][int(b[5]):], exp[2][int(b[5]):])

@@ -8,6 +8,7 @@
   post_ops_layer_tests.json     the reference's known-answer vectors for RaggedToDense and CombineSegments
                                 (tests/layer_tests.py:497-644)
   special_tokens_split_layer_tests.json  the reference's known-answer vectors for SpecialTokensSplit (tests/layer_tests.py:405-457)
+  shim_ops_layer_tests.json     UTF8Validate known-answer strings (tests/layer_tests.py:84-139) and the byte -> char table
   hf_<vocab>.json               ids produced by HuggingFace `tokenizers` for the frozen synthetic vocabularies
                                 (second oracle; the reference reports 100 % agreement with HF for these families)
 """
@@ -153,6 +154,39 @@ def make_special_golden():
     print("special tokens split cases", len(out))
 
 
+def make_shim_golden():
+    """UTF8Validate: the reference's own string list (tests/layer_tests.py:84-117) with the expectation its test uses
+    (`bytes.decode(errors=mode)`, :131-139), checked against the oracle.  BytesToChars: the reference's literal byte -> char
+    table (src/bytes_to_chars.cpp:11-268) as hex, checked against the oracle's generated map and against the converter's
+    unicode_to_bytes (python/openvino_tokenizers/utils.py:196-210)."""
+    import oracle
+    from openvino_tokenizers_b200.strings import add_ragged_dimension, pack_strings
+    lt = (REF / "tests/layer_tests.py").read_text()
+    a = lt.index("utf8_validate_strings = [")
+    b = lt.index("\n]\n", a) + 3
+    ns = {}
+    exec(lt[a:b], ns)
+    out = []
+    for sbytes in ns["utf8_validate_strings"]:
+        for mode in ("ignore", "replace"):
+            exp = sbytes.decode(errors=mode).encode()
+            bb, ee, cc = pack_strings([sbytes])
+            got = oracle.utf8_validate(bb, ee, cc, mode == "replace")
+            assert bytes(got[2]) == exp, (sbytes, mode)
+            out.append(dict(input_hex=sbytes.hex(), mode=mode, expected_hex=exp.hex()))
+    cpp = (REF / "src/bytes_to_chars.cpp").read_text()
+    body = cpp[cpp.index("create_bytes_to_chars_map"):cpp.index("}};")]
+    table = [bytes(int(x) for x in e.replace(" ", "").split(",") if x) for e in re.findall(r"\{\s*([\d,\s]+)\}", body)][-256:]
+    assert len(table) == 256
+    bb, ee, cc = pack_strings([bytes(range(256))])
+    rb, re_ = add_ragged_dimension(bb, ee)
+    assert bytes(oracle.bytes_to_chars(rb, re_, bb, ee, cc)[2]) == b"".join(table)
+    (GOLDEN / "shim_ops_layer_tests.json").write_text(json.dumps(
+        dict(source="reference tests/layer_tests.py:84-139, src/bytes_to_chars.cpp:11-268", utf8_validate=out,
+             bytes_to_chars_table_hex=[t.hex() for t in table]), indent=1))
+    print("utf8_validate cases", len(out), "byte map entries", len(table))
+
+
 def make_hf_golden():
     import numpy as np
     import cases
@@ -178,7 +212,7 @@ def make_hf_golden():
 
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["regex", "hf", "post", "special"]
+    which = sys.argv[1:] or ["regex", "hf", "post", "special", "shim"]
     if "regex" in which:
         make_regex_golden()
     if "hf" in which:
@@ -187,3 +221,5 @@ if __name__ == "__main__":
         make_post_golden()
     if "special" in which:
         make_special_golden()
+    if "shim" in which:
+        make_shim_golden()
