@@ -295,23 +295,27 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
     }
     // GPT-2 byte-level split + BPE without end_suffix: the dedicated bit-mask kernel takes every row; rows it hands back
     // (multi-byte symbols, pieces longer than a window, skip-flagged elements) are redone by the generic kernel in list mode
-    const bool fast = call.op == OP_BPE && (c.P.spec.pat == PAT_GPT2 || c.P.spec.pat == PAT_GPT2_DIGITS) && c.P.mode == SPLIT_ISOLATED &&
+    const bool fast = call.op == OP_BPE && (c.P.spec.pat == PAT_GPT2 || c.P.spec.pat == PAT_GPT2_DIGITS || c.P.spec.pat == PAT_LLAMA3) && c.P.mode == SPLIT_ISOLATED &&
                       !c.P.repeat && c.P.max_splits == -1 && c.P.suffix_len == 0 && !(c.P.dbg_flags & 2);
     if (fast) {
         // ids fit 16 bits: slimmer per-warp state, five CTAs per SM instead of four (the kernel is latency-bound: warps = speed)
         const bool narrow = call.bpe->h.max_id < 0xFFFF && !(c.P.dbg_flags & 8);
-        static bool fast_attr[2][64] = {};
+        const bool l3 = c.P.spec.pat == PAT_LLAMA3;
+        static bool fast_attr[4][64] = {};
         const size_t fsm = narrow ? fast_smem_bytes<uint16_t>() : fast_smem_bytes<int32_t>();
-        if (!fast_attr[narrow][owner->device]) {
-            if (narrow) CU(cudaFuncSetAttribute(gpt2_bpe_fast_kernel<uint16_t, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            else CU(cudaFuncSetAttribute(gpt2_bpe_fast_kernel<int32_t, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            fast_attr[narrow][owner->device] = true;
+        const void* fn = narrow ? (l3 ? (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, true> : (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, false>)
+                                : (l3 ? (const void*)gpt2_bpe_fast_kernel<int32_t, 4, true> : (const void*)gpt2_bpe_fast_kernel<int32_t, 4, false>);
+        if (!fast_attr[narrow * 2 + l3][owner->device]) {
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            fast_attr[narrow * 2 + l3][owner->device] = true;
         }
         static const int fast_ctas_env = [] { const char* e = getenv("B200TOK_FAST_CTAS"); return e ? atoi(e) : 0; }();
         const int fast_per_sm = fast_ctas_env > 0 ? fast_ctas_env : (int)std::max<size_t>(1, std::min<size_t>(narrow ? 5 : 4, (227 * 1024) / (fsm + 1024)));
         const int fast_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * fast_per_sm);
-        if (narrow) gpt2_bpe_fast_kernel<uint16_t, 5><<<fast_blocks, BLOCK_THREADS, fsm, st>>>(c.P, c.row_cap);
-        else gpt2_bpe_fast_kernel<int32_t, 4><<<fast_blocks, BLOCK_THREADS, fsm, st>>>(c.P, c.row_cap);
+        RowParams Pk = c.P;
+        int32_t* redo = c.row_cap;
+        void* args[] = {&Pk, &redo};
+        CU(cudaLaunchKernel(fn, dim3((unsigned)fast_blocks), dim3(BLOCK_THREADS), args, fsm, st));
         if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
         RowParams P2 = c.P;
         P2.row_list = c.row_cap;

@@ -570,7 +570,7 @@ __device__ __forceinline__ int gpt2_ascii_fused_window_v5(WarpSmem& S, const Bpe
 // Helpers of the bit-mask GPT-2 -> BPE kernel (kernels_fast.cuh).
 //   lut32[c]: class bits below | one-byte symbol id << 12
 // ---------------------------------------------------------------------------------------------------------
-enum : uint32_t { V7_L = 1, V7_N = 2, V7_S = 4, V7_SP = 8, V7_AP = 16, V7_WALK = 32, V7_BAD = 64, V7_CONT = 128 };
+enum : uint32_t { V7_L = 1, V7_N = 2, V7_S = 4, V7_SP = 8, V7_AP = 16, V7_WALK = 32, V7_BAD = 64, V7_CONT = 128, V7_NL = 256 };
 constexpr int V7_ID_SHIFT = 12;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
@@ -578,6 +578,7 @@ __device__ __forceinline__ uint32_t v7_lut_entry(const RowParams& P, int c) {
     uint32_t g = c < 128 ? (uint32_t)(P.cls.ascii[c] & (C_L | C_N | C_S)) : 0u;
     if (c == 0x20) g |= V7_SP;
     if (c == '\'') g |= V7_AP;
+    if (c < 128 && (P.cls.ascii[c] & C_NL)) g |= V7_NL;
     int32_t id = P.bpe.byte_sym[c];
     if (id == kSymWalk) {                      // a longer token may start with c: the one-byte result is used unless the walk finds one
         g |= V7_WALK;

@@ -26,36 +26,22 @@ template <class IdT>
 struct __align__(16) FastSmem {
     uint8_t raw_bytes[LBK + WBYTES];
     uint32_t segbits[NWORDS], actbits[NWORDS];
-    uint32_t m[9][kMStride];                 // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F
+    uint32_t m[11][kMStride];                // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F NL PG
     IdT ids[WIN];                            // symbol per position; kDead = merged away
     uint32_t key[WIN];
     __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }
     __device__ __forceinline__ uint16_t* act() { return reinterpret_cast<uint16_t*>(&m[0][0]); }   // merge queue; the masks are consumed by then
     static constexpr IdT kDead = (IdT)-1;
 };
-static_assert(sizeof(uint32_t) * 9 * kMStride >= sizeof(uint16_t) * (WIN / 3 + 10), "merge queue must fit the mask area");
-enum : int { M_L = 0, M_N, M_S, M_SP, M_A2, M_A3, M_CONT, M_MB, M_F };
+static_assert(sizeof(uint32_t) * 11 * kMStride >= sizeof(uint16_t) * (WIN / 3 + 10), "merge queue must fit the mask area");
+enum : int { M_L = 0, M_N, M_S, M_SP, M_A2, M_A3, M_CONT, M_MB, M_F, M_NL, M_PG };
 
 constexpr int kFastSmemFixed = 128 + 1024 + 2048;   // ascii classes, lut32, pair bitmap
 template <class IdT> constexpr size_t fast_smem_bytes() { return kFastSmemFixed + WARPS_PER_BLOCK * sizeof(FastSmem<IdT>); }
 
-// Class bits of byte position w of a non-ASCII window: continuation bytes carry their owner's class plus C_CONT.
-__device__ __forceinline__ uint32_t fast_byte_class(const uint8_t* B, int w, int lo, int end_rel, const ClassTables& T) {
-    const uint8_t b = B[w];
-    if (b < 0x80) return T.ascii[b];
-    if (is_cont_byte(b) && w > lo) {
-        int j = w - 1;
-        while (j >= lo && j > w - 4 && is_cont_byte(B[j])) --j;
-        uint32_t k = C_CONT;
-        if (j >= lo && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
-        return k;
-    }
-    return char_class(B, w, end_rel, T);
-}
-
 // One window.  Returns `send` (how far the window advances; 0 => the first piece does not fit) or -1 when the window
 // needs the generic path.  On success S.ids[0 .. send) holds the window's tokens (-1 = merged away).
-template <class IdT>
+template <class IdT, bool L3>
 __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32, const uint32_t* pbits,
                                            const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
                                            bool ascii) {
@@ -64,16 +50,40 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
     const int lb = off < LBK ? off : LBK;           // look-back bytes staged before the window (off = window start - element start)
     ClassTables T = P.cls;
     T.ascii = ascii_smem;
-    // ---- pass 1: four words (stride 32) per iteration ----
+    // ---- non-ASCII windows: one class byte per position (continuation bytes carry their owner's class plus C_CONT), parked in
+    // the bytes of the ids array that pass 1 has not written yet: pass 1 walks the words from the top down and reads the class
+    // bytes of an iteration before it stores that iteration's ids, so a class byte is always read before it is overwritten
+    // (the class byte of position q lives at byte q + LBK, the id of position p at byte sizeof(IdT) * p >= p + LBK for p >= LBK).
+    uint8_t* const KC = reinterpret_cast<uint8_t*>(S.ids) + LBK;
+    if (!ascii) {
+        for (int w = lane - lb; w < nload; w += 32) {            // characters: decoded once, by the lane of their first byte
+            const uint8_t b = B[w];
+            if (b < 0x80) KC[w] = ascii_smem[b];
+            else if (!is_cont_byte(b) || w == -lb) KC[w] = char_class(B, w, end_rel, T);
+        }
+        __syncwarp();
+        for (int w = lane - lb; w < nload; w += 32) {            // continuation bytes copy their owner
+            const uint8_t b = B[w];
+            if (is_cont_byte(b) && w > -lb) {
+                int j = w - 1;
+                while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
+                uint8_t k = C_CONT;
+                if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= KC[j] & (uint8_t)~C_CONT;
+                KC[w] = k;
+            }
+        }
+        __syncwarp();
+    }
+    // ---- pass 1: four words (stride 32) per iteration, top word first ----
     bool complex = false;
     const int nw = (nload + 31) >> 5;
     {
         const int it0 = lb > 0 ? -1 : 0;
-        if (it0 == 0 && lane < 9) S.m[lane][0] = 0u;
+        if (it0 == 0 && lane < 11) S.m[lane][0] = 0u;
         const uint32_t span = (uint32_t)(nload + lb);
         const uint32_t* const pair_rank = P.bpe.pair_rank;
         const uint16_t* const rank16 = reinterpret_cast<const uint16_t*>(P.bpe.pair_bits + 2560);
-        for (int it = it0; it < nw; it += 4) {
+        for (int it = it0 + ((nw - 1 - it0) & ~3); it >= it0; it -= 4) {
             const int w0 = it * 32 + lane;
             const uint8_t* bq = B + w0;                           // this lane's byte of word `it`
             uint32_t c[4], g[4];
@@ -82,22 +92,22 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                 c[u] = bq[32 * u];
                 g[u] = lut32[c[u]];
                 const bool valid = (uint32_t)(w0 + 32 * u + lb) < span;
-                if (!ascii && valid && c[u] >= 0x80) g[u] |= fast_byte_class(B, w0 + 32 * u, -lb, end_rel, T) & (uint32_t)(C_L | C_N | C_S | C_CONT);
+                if (!ascii && valid) g[u] |= KC[w0 + 32 * u] & (uint32_t)(C_L | C_N | C_S | C_CONT);
                 g[u] = valid ? g[u] : 0u;
-                if ((uint32_t)(w0 + 32 * u) < (uint32_t)wlen) S.ids[w0 + 32 * u] = (IdT)(g[u] >> V7_ID_SHIFT);
             }
             uint32_t* const mm = &S.m[0][it + 1];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t bL = ballot_bits(g[u], V7_L), bN = ballot_bits(g[u], V7_N), bS = ballot_bits(g[u], V7_S), bSP = ballot_bits(g[u], V7_SP);
                 if (lane == 0) { mm[M_L * kMStride + u] = bL; mm[M_N * kMStride + u] = bN; mm[M_S * kMStride + u] = bS; mm[M_SP * kMStride + u] = bSP; }
+                if (L3) { const uint32_t bNL = ballot_bits(g[u], V7_NL); if (lane == 0) mm[M_NL * kMStride + u] = bNL; }
             }
             const uint32_t gor = g[0] | g[1] | g[2] | g[3];
             if (ballot_bits(gor, V7_AP)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     int cl = 0;
-                    if (g[u] & V7_AP) cl = gpt2_contraction_len(B, w0 + 32 * u, nload);
+                    if (g[u] & V7_AP) cl = L3 ? llama3_contraction_len(B, w0 + 32 * u, nload) : gpt2_contraction_len(B, w0 + 32 * u, nload);
                     const uint32_t bA2 = __ballot_sync(FULL, cl == 2), bA3 = __ballot_sync(FULL, cl == 3);
                     if (lane == 0) { mm[M_A2 * kMStride + u] = bA2; mm[M_A3 * kMStride + u] = bA3; }
                 }
@@ -110,10 +120,23 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                     if ((g[u] & V7_S) && c[u] >= 0x80 && !(g[u] & V7_CONT)) {      // multi-byte whitespace: is the next character a non-space?
                         int j = w0 + 32 * u + 1;
                         while (j < nload && is_cont_byte(B[j])) ++j;
-                        mb = j < nload && !(fast_byte_class(B, j, -lb, end_rel, T) & C_S);
+                        mb = j < nload && !(KC[j] & C_S);
                     }
                     const uint32_t bMB = __ballot_sync(FULL, mb);
                     if (lane == 0) { mm[M_CONT * kMStride + u] = bC; mm[M_MB * kMStride + u] = bMB; }
+                    if (L3) {
+                        const int w = w0 + 32 * u;
+                        if ((g[u] & V7_N) && c[u] >= 0x80) complex = true;          // digit groups are evaluated for ASCII digits only
+                        bool pg = false;                                           // letter after a multi-byte "other" char at which a match starts
+                        if ((g[u] & V7_L) && !(g[u] & V7_CONT) && w > -lb && is_cont_byte(B[w - 1])) {
+                            int j = w - 1;
+                            while (j > -lb && is_cont_byte(B[j])) --j;
+                            if (!(KC[j] & (C_L | C_N | C_S)))
+                                pg = j == -lb || (B[j - 1] != 0x20 && (KC[j - 1] & (C_L | C_N | C_S)));
+                        }
+                        const uint32_t bPG = __ballot_sync(FULL, pg);
+                        if (lane == 0) mm[M_PG * kMStride + u] = bPG;
+                    }
                 }
             }
             if (ballot_bits(gor, V7_WALK | V7_BAD)) {
@@ -149,6 +172,10 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                 const uint32_t bF = __ballot_sync(FULL, fb);
                 if (lane == 0) mm[M_F * kMStride + u] = bF;
             }
+            if (!ascii) __syncwarp();                            // every class byte of this iteration has been read
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((uint32_t)(w0 + 32 * u) < (uint32_t)wlen) S.ids[w0 + 32 * u] = (IdT)(g[u] >> V7_ID_SHIFT);
         }
     }
     if (__any_sync(FULL, complex)) return -1;
@@ -156,29 +183,94 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
     // ---- pass 2: piece starts, lane = word ----
     const int word = lane, base = lane * 32;
     const bool live = word < nw;
-    G2Word W{0, 0, 0, 0, 0, 0, 0, 0, 0}, PW{0, 0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t found = 0;
-    if (live) {
-        W.L = S.m[M_L][word + 1]; W.N = S.m[M_N][word + 1]; W.S = S.m[M_S][word + 1]; W.SP = S.m[M_SP][word + 1];
-        W.A2 = S.m[M_A2][word + 1]; W.A3 = S.m[M_A3][word + 1];
-        PW.L = S.m[M_L][word]; PW.N = S.m[M_N][word]; PW.S = S.m[M_S][word]; PW.SP = S.m[M_SP][word];
-        found = S.m[M_F][word + 1];
-        if (!ascii) { W.CONT = S.m[M_CONT][word + 1]; W.MB = S.m[M_MB][word + 1]; }
-        W.X = v7_below(nload, base);
-    }
+    uint32_t found = live ? S.m[M_F][word + 1] : 0u;
     const uint32_t bos = (word == 0 && off == 0) ? 1u : 0u;
-    uint32_t c2, c3;
-    g2_contractions(W, g2_ok1(PW), bos, c2, c3);
-    uint32_t pc2 = __shfl_up_sync(FULL, c2, 1), pc3 = __shfl_up_sync(FULL, c3, 1);
-    if (lane == 0) {      // contractions starting in the look-back word (their apostrophe is at most 3 positions back)
-        pc2 = 0; pc3 = 0;
-        if (lb > 0) {
-            G2Word LBW{PW.L, PW.N, PW.S, PW.SP, S.m[M_A2][0], S.m[M_A3][0], 0, 0, 0};
-            g2_contractions(LBW, 0u, off <= LBK ? 1u << (32 - off) : 0u, pc2, pc3);   // (element start inside the look-back)
+    uint32_t start;
+    if (!L3) {
+        G2Word W{0, 0, 0, 0, 0, 0, 0, 0, 0}, PW{0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (live) {
+            W.L = S.m[M_L][word + 1]; W.N = S.m[M_N][word + 1]; W.S = S.m[M_S][word + 1]; W.SP = S.m[M_SP][word + 1];
+            W.A2 = S.m[M_A2][word + 1]; W.A3 = S.m[M_A3][word + 1];
+            PW.L = S.m[M_L][word]; PW.N = S.m[M_N][word]; PW.S = S.m[M_S][word]; PW.SP = S.m[M_SP][word];
+            if (!ascii) { W.CONT = S.m[M_CONT][word + 1]; W.MB = S.m[M_MB][word + 1]; }
+            W.X = v7_below(nload, base);
+        }
+        uint32_t c2, c3;
+        g2_contractions(W, g2_ok1(PW), bos, c2, c3);
+        uint32_t pc2 = __shfl_up_sync(FULL, c2, 1), pc3 = __shfl_up_sync(FULL, c3, 1);
+        if (lane == 0) {      // contractions starting in the look-back word (their apostrophe is at most 3 positions back)
+            pc2 = 0; pc3 = 0;
+            if (lb > 0) {
+                G2Word LBW{PW.L, PW.N, PW.S, PW.SP, S.m[M_A2][0], S.m[M_A3][0], 0, 0, 0};
+                g2_contractions(LBW, 0u, off <= LBK ? 1u << (32 - off) : 0u, pc2, pc3);   // (element start inside the look-back)
+            }
+        }
+        const uint32_t nns = __shfl_down_sync(FULL, W.X & ~W.S, 1);
+        start = g2_starts(W, PW, c2, c3, pc2, pc3, lane == 31 ? 0u : nns, bos, P.spec.pat == PAT_GPT2_DIGITS);
+    } else {
+        L3Word W{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, PW{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (live) {
+            W.L = S.m[M_L][word + 1]; W.N = S.m[M_N][word + 1]; W.S = S.m[M_S][word + 1]; W.SP = S.m[M_SP][word + 1];
+            W.NL = S.m[M_NL][word + 1]; W.A2 = S.m[M_A2][word + 1]; W.A3 = S.m[M_A3][word + 1];
+            PW.L = S.m[M_L][word]; PW.N = S.m[M_N][word]; PW.S = S.m[M_S][word]; PW.SP = S.m[M_SP][word]; PW.NL = S.m[M_NL][word];
+            if (!ascii) { W.CONT = S.m[M_CONT][word + 1]; W.MB = S.m[M_MB][word + 1]; W.PG = S.m[M_PG][word + 1]; }
+            W.X = v7_below(nload, base);
+            PW.X = word > 0 ? FULL : (lb > 0 ? FULL << (32 - lb) : 0u);
+        }
+        const uint32_t mso = l3_mso(W, PW), d2 = W.A2 & mso, d3 = W.A3 & mso;
+        uint32_t p_mso = __shfl_up_sync(FULL, mso, 1), pd2 = __shfl_up_sync(FULL, d2, 1), pd3 = __shfl_up_sync(FULL, d3, 1);
+        if (lane == 0) {      // the look-back word's own contribution (its predecessor is unknown: treated as empty)
+            p_mso = 0; pd2 = 0; pd3 = 0;
+            if (lb > 0) {
+                L3Word LBW = PW, Z{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                LBW.A2 = S.m[M_A2][0]; LBW.A3 = S.m[M_A3][0];
+                if (!ascii) LBW.CONT = S.m[M_CONT][0];
+                p_mso = l3_mso(LBW, Z); pd2 = LBW.A2 & p_mso; pd3 = LBW.A3 & p_mso;
+            }
+        }
+        // newline runs right after an other char belong to its piece: fill them upwards, carrying across words
+        uint32_t lead;
+        {
+            const uint32_t seeds = l3_lead_seeds(W, PW);
+            lead = l3_fill_up(W.NL, seeds);
+            const uint32_t G = __ballot_sync(FULL, (lead >> 31) != 0u), Pm = __ballot_sync(FULL, W.NL == FULL);
+            const uint32_t np = ~Pm & lt;
+            const int j = np ? 31 - __clz(np) : 0;
+            if ((G & lt & ~((1u << j) - 1u)) && (W.NL & 1u)) lead = l3_fill_up(W.NL, seeds | 1u);
+        }
+        uint32_t p_lead = __shfl_up_sync(FULL, lead, 1);
+        if (lane == 0) p_lead = 0;      // (a window never starts inside such a run: its newlines are not piece starts)
+        // the tail of every whitespace run (non-newline chars after its last newline, up to a non-space): fill downwards
+        uint32_t tail;
+        {
+            const uint32_t nS0 = __shfl_down_sync(FULL, W.S, 1);
+            const uint32_t Tb = W.S & ~W.NL, seeds = l3_tail_seeds(W, lane == 31 ? 0u : nS0);
+            tail = l3_fill_down(Tb, seeds);
+            const uint32_t G = __ballot_sync(FULL, (tail & 1u) != 0u), Pm = __ballot_sync(FULL, Tb == FULL);
+            const uint32_t above = lane == 31 ? 0u : (FULL << (lane + 1));
+            const uint32_t np = ~Pm & above;
+            const int j = np ? __ffs(np) - 1 : 31;
+            if ((G & above & (FULL >> (31 - j))) && (Tb >> 31)) tail = l3_fill_down(Tb, seeds | 0x80000000u);
+        }
+        // every third digit from the start of its run; a run entering the word from below needs its digit count so far
+        int phase = 0;
+        if (word > 0 && (W.N & 1u) && (PW.N >> 31))
+            for (int p = base - 1; p >= 0 && (lut32[B[p]] & V7_N); --p) ++phase;
+        const uint32_t nst = l3_number_starts(W.N, PW.N >> 31, phase, word == 0);
+        const uint32_t nns = __shfl_down_sync(FULL, W.X & ~W.S, 1);
+        start = l3_starts(W, PW, mso, p_mso, d2, d3, pd2, pd3, lead, p_lead, tail, nst, lane == 31 ? 0u : nns, bos);
+        if (nload < end_rel) {      // the loaded bytes end inside the element: a whitespace run touching their end is undecided
+            const int lastp = nload - 1;
+            if ((S.m[M_S][(lastp >> 5) + 1] >> (lastp & 31)) & 1u) {
+                int a = 0;
+                for (int wi = lastp >> 5, top = lastp & 31; wi >= 0; --wi, top = 31) {
+                    const uint32_t zeros = ~S.m[M_S][wi + 1] & (top == 31 ? FULL : ((2u << top) - 1u));
+                    if (zeros) { a = wi * 32 + 32 - __clz(zeros); break; }
+                }
+                start &= v7_below(a + 1, base);      // keep the run's first piece start at most; the rest is redone in the next window
+            }
         }
     }
-    const uint32_t nns = __shfl_down_sync(FULL, W.X & ~W.S, 1);
-    uint32_t start = g2_starts(W, PW, c2, c3, pc2, pc3, lane == 31 ? 0u : nns, bos, P.spec.pat == PAT_GPT2_DIGITS);
     start &= v7_below(wlen, base);
     if (word == 0) start |= 1u;
     int send = wlen;
@@ -238,8 +330,10 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
             if (qi < nact) {
                 s = S.act()[qi];
                 const int e = next_bit(S.segbits, s, send), n = e - s;
-                if (n > 32) complex = true;                             // a run longer than the 32-bit masks: generic path
-                else {
+                if (n > 32) {                                           // a run longer than the 32-bit masks: serial loop over the whole segment
+                    const int c = bpe_merge_packed(MT, S.ids + s, S.key + s, n);
+                    for (int t = s + c; t < e; ++t) S.ids[t] = S.kDead;
+                } else {
                     const uint32_t mask = n == 32 ? FULL : ((1u << n) - 1u);
                     km = g2_fsr(S.actbits[s >> 5], S.actbits[(s >> 5) + 1], s & 31) & mask;
                     alive = mask;
@@ -285,7 +379,7 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
     return send;
 }
 
-template <class IdT, int CTAS>
+template <class IdT, int CTAS, bool L3>
 __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                            // [128]
@@ -347,7 +441,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                 }
                 const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
                 __syncwarp();
-                const int send = fast_window(S, P, lut32_smem, pbits_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                const int send = fast_window<IdT, L3>(S, P, lut32_smem, pbits_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
                 if (send <= 0) { redo = true; break; }
                 if (base + emitted + send > P.tmp_cap) {
                     if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);

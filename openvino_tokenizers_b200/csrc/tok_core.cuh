@@ -411,6 +411,19 @@ B2_HD bool gpt2_start_nb(uint32_t c, uint32_t p1, uint32_t p2, uint32_t p3, uint
     return r || (p1 & G_BOS);
 }
 
+// Length of the case-insensitive contraction (?i:'s|'t|'re|'ve|'m|'ll|'d) at the apostrophe s[q] (0 = none); U+017F folds to 's'.
+B2_HD int llama3_contraction_len(const uint8_t* b, int q, int ee) {
+    if (q + 1 >= ee) return 0;
+    const uint8_t b1 = b[q + 1];
+    if (ci_eq(b1, 's') || ci_eq(b1, 't') || ci_eq(b1, 'm') || ci_eq(b1, 'd')) return 2;
+    if (q + 2 < ee) {
+        const uint8_t b2 = b[q + 2];
+        if (b1 == 0xC5 && b2 == 0xBF) return 3;
+        if ((ci_eq(b1, 'r') || ci_eq(b1, 'v')) && ci_eq(b2, 'e')) return 3;
+        if (ci_eq(b1, 'l') && ci_eq(b2, 'l')) return 3;
+    }
+    return 0;
+}
 // Word form of the same predicate: 32 byte positions at a time as bit masks (bit i = position base + i), so one thread
 // evaluates 32 positions with ~40 logic operations.  Per-word class masks: L / N / S (continuation bytes carry their
 // owner's bits), SP = byte 0x20, A2 / A3 = an apostrophe followed by a 2- / 3-byte contraction ('s 't 'm 'd / 're 've 'll),
@@ -441,6 +454,76 @@ B2_HD uint32_t g2_starts(const G2Word& w, const G2Word& p, uint32_t c2, uint32_t
     const uint32_t ends = g2_fsl(pc2, c2, 2) | g2_fsl(pc3, c3, 3);
     const uint32_t l_start = w.L & ~p1SP & ~inside & (ends | ~p1L);
     return (s_start | n_start | o_start | l_start | bos) & w.X & ~w.CONT;
+}
+
+// ------------------------------------------------------------------------------------------
+// Word form of the Llama-3 / cl100k pattern in "isolate" mode
+//   (?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+
+// The pattern tiles the subject; which characters start a piece (derived from PCRE2's leftmost / first-alternative /
+// backtracking semantics, checked against PCRE2 in tests/test_core_host.py):
+//   other (not space / letter / number) char: starts a piece iff it is the first of its run and the byte before is not U+0020
+//          ("a match starts here", MSO); a following newline run belongs to the same piece ([\r\n]*)
+//   letter: starts iff the previous char is a newline, a number, the element start, or an "other" char at which NO match starts;
+//          a letter run is glued to one preceding non-newline space or MSO char ([^\r\n\p{L}\p{N}]?\p{L}+), except that a
+//          contraction ('s 't 'm 'd 're 've 'll, any case) at an MSO apostrophe takes its letters first and the next letter starts
+//   number (ASCII digits): every third digit from the start of its run
+//   whitespace run [a, b): a' = a, or a + its leading newlines if an "other" char precedes (they went to that piece); a' starts;
+//          the char after the last newline starts (\s*[\r\n]+ ends there); the last char starts if it is not a newline and a
+//          non-space follows (\s+(?!\S) gives it back; it then glues to a following letter, or, if U+0020, to a following other run)
+// Masks per 32 byte positions as for the GPT-2 form, plus NL = \r or \n and PG = "the previous char is a MULTI-byte other char
+// at which a match starts" (for one-byte chars this is a shift of MSO).
+// ------------------------------------------------------------------------------------------
+struct L3Word { uint32_t L, N, S, NL, SP, A2, A3, CONT, MB, PG, X; };
+B2_HD uint32_t l3_mod3(int r) { return r == 0 ? 0x49249249u : r == 1 ? 0x92492492u : 0x24924924u; }     // bit positions = r (mod 3)
+// fill every run of `run` upwards from its seed bit (at most one seed per run), inside one word
+B2_HD uint32_t l3_fill_up(uint32_t run, uint32_t seeds) { return ((run + seeds) ^ run) & run; }
+B2_HD uint32_t l3_brev(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+B2_HD uint32_t l3_fill_down(uint32_t run, uint32_t seeds) { return l3_brev(l3_fill_up(l3_brev(run), l3_brev(seeds))); }
+B2_HD uint32_t l3_other(const L3Word& w) { return w.X & ~(w.L | w.N | w.S); }
+// "a match starts at this other char": first of its run, byte before is not U+0020.  p = previous word.
+B2_HD uint32_t l3_mso(const L3Word& w, const L3Word& p) {
+    return l3_other(w) & ~w.CONT & ~g2_fsl(l3_other(p), l3_other(w), 1) & ~g2_fsl(p.SP, w.SP, 1);
+}
+// seeds of the two cross-word fills: newline runs right after an other char (upwards), tails of whitespace runs (downwards)
+B2_HD uint32_t l3_lead_seeds(const L3Word& w, const L3Word& p) { return w.NL & g2_fsl(l3_other(p), l3_other(w), 1); }
+B2_HD uint32_t l3_tail_seeds(const L3Word& w, uint32_t n_s /* S of the next word */) { return (w.S & ~w.NL) & ~g2_fsr(w.S, n_s, 1); }
+// number starts of one word.  phase_in = digits of the run that continues into bit 0, before it (only used if it does).
+B2_HD uint32_t l3_number_starts(uint32_t N, uint32_t pN_bit31, int phase_in, bool force0) {
+    const uint32_t cont0 = (N & 1u) && pN_bit31 && !force0 ? 1u : 0u;     // bit 0 continues a run from the previous word
+    const uint32_t rs = N & ~((N << 1) | (pN_bit31 && !force0 ? 1u : 0u));
+    const int r0 = (3 - phase_in % 3) % 3;
+    uint32_t st = 0;
+    for (int r = 0; r < 3; ++r) {
+        uint32_t seeds = rs & l3_mod3(r);
+        if (cont0 && r == r0) seeds |= 1u;
+        st |= l3_fill_up(N, seeds) & l3_mod3(r);
+    }
+    return st;
+}
+// piece starts of one word.  lead / tail = the filled masks of this word, p_lead = of the previous word; (d2, d3) / (pd2, pd3)
+// = contraction starts (A2 / A3 & MSO) of this / the previous word; nst = number starts; n_ns = X & ~S of the next word.
+B2_HD uint32_t l3_starts(const L3Word& w, const L3Word& p, uint32_t mso, uint32_t p_mso, uint32_t d2, uint32_t d3, uint32_t pd2, uint32_t pd3,
+                         uint32_t lead, uint32_t p_lead, uint32_t tail, uint32_t nst, uint32_t n_ns, uint32_t bos) {
+    const uint32_t O = l3_other(w), pO = l3_other(p);
+    const uint32_t p1L = g2_fsl(p.L, w.L, 1), p1S = g2_fsl(p.S, w.S, 1), p1NL = g2_fsl(p.NL, w.NL, 1), p1O = g2_fsl(pO, O, 1);
+    const uint32_t p1T = p1S & ~p1NL;
+    const uint32_t p1MSO = g2_fsl(p_mso, mso, 1) | w.PG;                 // (a one-byte MSO char right before, or a multi-byte one)
+    const uint32_t ends = g2_fsl(pd2, d2, 2) | g2_fsl(pd3, d3, 3);
+    const uint32_t l_start = w.L & ((~p1L & ~p1T & ~(p1O & p1MSO)) | ends);
+    const uint32_t T = w.S & ~w.NL;
+    const uint32_t n1ns = g2_fsr(w.X & ~w.S, n_ns, 1);
+    const uint32_t s_start = (w.S & ~p1S & ~(p1O & w.NL)) | (T & g2_fsl(p_lead, lead, 1)) | (tail & p1NL) | (T & n1ns) | w.MB;
+    return (l_start | nst | mso | s_start | bos) & w.X & ~w.CONT;
 }
 
 // (p)+ for the "contiguous" rewrite (src/regex_split.cpp:33-37): greedy repetition of the pattern.
@@ -696,12 +779,13 @@ B2_HD int bpe_merge_serial(const MergeTable& M, int32_t* ids, int32_t* rank, int
 constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kPackedBirthBits = 12;
 constexpr int kPackedMaxSymbols = 2048;
-B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int n) {
+template <class IdT>
+B2_HD int bpe_merge_packed(const MergeTable& M, IdT* ids, uint32_t* key, int n) {
     if (n < 2) return n;
     bool any = false;
     for (int k = 0; k + 1 < n; ++k) {
         int32_t r, v;
-        const bool f = merge_find(M, ids[k], ids[k + 1], r, v);
+        const bool f = merge_find(M, (int32_t)ids[k], (int32_t)ids[k + 1], r, v);
         any |= f;
         key[k] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)k) : kNoKey;
     }
@@ -715,19 +799,19 @@ B2_HD int bpe_merge_packed(const MergeTable& M, int32_t* ids, uint32_t* key, int
             if (q < best) { best = q; bk = k; }
         }
         if (bk < 0) break;
-        ids[bk] = M.rank_newid[best >> kPackedBirthBits];
+        ids[bk] = (IdT)M.rank_newid[best >> kPackedBirthBits];
         for (int k = bk + 1; k + 1 < n; ++k) ids[k] = ids[k + 1];
         for (int k = bk + 1; k + 2 < n; ++k) key[k] = key[k + 1];
         --n;
         ++seq;
         if (bk > 0) {
             int32_t r, v;
-            const bool f = merge_find(M, ids[bk - 1], ids[bk], r, v);
+            const bool f = merge_find(M, (int32_t)ids[bk - 1], (int32_t)ids[bk], r, v);
             key[bk - 1] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
         }
         if (bk + 1 < n) {
             int32_t r, v;
-            const bool f = merge_find(M, ids[bk], ids[bk + 1], r, v);
+            const bool f = merge_find(M, (int32_t)ids[bk], (int32_t)ids[bk + 1], r, v);
             key[bk] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
         }
     }

@@ -98,8 +98,9 @@ class TokenizerPipeline:
     @property
     def dominant_kernel(self) -> str:
         """Name of the kernel b200tok_last_kernel_ms() times (csrc/api.cu launch_chunk)."""
-        if self.kind == "bpe" and self.assets.split_pattern in (A.GPT2_PATTERN, A.GPT2_DIGITS_PATTERN) and not self.assets.end_suffix:
-            return "gpt2_bpe_fast_kernel" + ("<u16,5>" if len(self.assets.vocab) < 0xFFFF else "<i32,4>")
+        if self.kind == "bpe" and self.assets.split_pattern in (A.GPT2_PATTERN, A.GPT2_DIGITS_PATTERN, A.LLAMA3_PATTERN) and not self.assets.end_suffix:
+            pat = "llama3" if self.assets.split_pattern == A.LLAMA3_PATTERN else "gpt2"
+            return "gpt2_bpe_fast_kernel" + ("<u16,5," if len(self.assets.vocab) < 0xFFFF else "<i32,4,") + pat + ">"
         return f"rows_kernel<{self.kind}>"
 
     def set_timing(self, on: bool):

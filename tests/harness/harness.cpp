@@ -188,3 +188,89 @@ HZ int64_t hz_gpt2_word_form(const uint8_t* s, int64_t n, int single_digits, int
     }
     return cnt;
 }
+
+// The word (bit-mask) form of the Llama-3 pattern (tok_core.cuh l3_starts) over one element: class bytes as in pass A, masks per
+// 32 positions, the two cross-word fills and the number phase resolved sequentially (the kernel resolves them with ballots).
+HZ int64_t hz_llama3_word_form(const uint8_t* s, int64_t n, int32_t* out_begins) {
+    const ClassTables T = host_class_tables().view();
+    const int end = (int)n;
+    std::vector<uint8_t> k((size_t)n + 8, 0);
+    for (int w = 0; w < end; ++w) {
+        const uint8_t b = s[w];
+        uint8_t c;
+        if (b < 0x80) c = T.ascii[b];
+        else if (is_cont_byte(b) && w > 0) {
+            int j = w - 1;
+            while (j >= 0 && j > w - 4 && is_cont_byte(s[j])) --j;
+            c = C_CONT;
+            if (j >= 0 && j > w - 4 && s[j] >= 0xC0) c |= char_class(s, j, end, T);
+        } else c = char_class(s, w, end, T);
+        k[w] = c;
+    }
+    auto is_other = [&](int i) { return !(k[i] & (C_L | C_N | C_S)); };
+    const int nw = (end + 31) / 32;
+    const L3Word Z{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<L3Word> W((size_t)nw + 2, Z);      // W[i + 1] = word i
+    for (int w = 0; w < end; ++w) {
+        L3Word& g = W[(size_t)(w >> 5) + 1];
+        const uint32_t bit = 1u << (w & 31);
+        g.X |= bit;
+        if (k[w] & C_L) g.L |= bit;
+        if (k[w] & C_N) { g.N |= bit; if (s[w] >= 0x80) return -2; }      // non-ASCII digit: the kernel hands such rows to the generic path
+        if (k[w] & C_S) g.S |= bit;
+        if ((k[w] & C_NL) && !(k[w] & C_CONT)) g.NL |= bit;
+        if (k[w] & C_CONT) g.CONT |= bit;
+        if (s[w] == 0x20) g.SP |= bit;
+        if (s[w] == '\'') {
+            const int cl = llama3_contraction_len(s, w, end);
+            if (cl == 2) g.A2 |= bit;
+            if (cl == 3) g.A3 |= bit;
+        }
+        if ((k[w] & C_S) && s[w] >= 0x80 && !(k[w] & C_CONT)) {
+            int j = w + 1;
+            while (j < end && (k[j] & C_CONT)) ++j;
+            if (j < end && !(k[j] & C_S)) g.MB |= bit;
+        }
+        if (w > 0 && !(k[w] & C_CONT) && (k[w - 1] & C_CONT)) {          // previous char is multi-byte: is it an other char at which a match starts?
+            int j = w - 1;
+            while (j > 0 && (k[j] & C_CONT)) --j;
+            if (is_other(j) && (j == 0 || (!is_other(j - 1) && s[j - 1] != 0x20))) g.PG |= bit;
+        }
+    }
+    std::vector<uint32_t> mso((size_t)nw + 2, 0), d2((size_t)nw + 2, 0), d3((size_t)nw + 2, 0), lead((size_t)nw + 2, 0), tail((size_t)nw + 2, 0), nst((size_t)nw + 2, 0);
+    for (int i = 1; i <= nw; ++i) {
+        mso[(size_t)i] = l3_mso(W[(size_t)i], W[(size_t)i - 1]);
+        d2[(size_t)i] = W[(size_t)i].A2 & mso[(size_t)i];
+        d3[(size_t)i] = W[(size_t)i].A3 & mso[(size_t)i];
+    }
+    uint32_t carry = 0;                                                     // upward fill of newline runs that follow an other char
+    for (int i = 1; i <= nw; ++i) {
+        const L3Word& g = W[(size_t)i];
+        uint32_t seeds = l3_lead_seeds(g, W[(size_t)i - 1]);
+        if (carry && (g.NL & 1u)) seeds |= 1u;
+        lead[(size_t)i] = l3_fill_up(g.NL, seeds);
+        carry = lead[(size_t)i] >> 31;
+    }
+    carry = 0;                                                              // downward fill of the tail of every whitespace run
+    for (int i = nw; i >= 1; --i) {
+        const L3Word& g = W[(size_t)i];
+        const uint32_t Tb = g.S & ~g.NL;
+        uint32_t seeds = l3_tail_seeds(g, W[(size_t)i + 1].S);
+        if (carry && (Tb >> 31)) seeds |= 0x80000000u;
+        tail[(size_t)i] = l3_fill_down(Tb, seeds);
+        carry = tail[(size_t)i] & 1u;
+    }
+    for (int i = 1; i <= nw; ++i) {                                         // digits of the run before the word's first bit
+        int phase = 0;
+        for (int p = (i - 1) * 32 - 1; p >= 0 && (k[p] & C_N); --p) ++phase;
+        nst[(size_t)i] = l3_number_starts(W[(size_t)i].N, W[(size_t)i - 1].N >> 31, phase, i == 1);
+    }
+    int64_t cnt = 0;
+    for (int i = 1; i <= nw; ++i) {
+        const uint32_t st = l3_starts(W[(size_t)i], W[(size_t)i - 1], mso[(size_t)i], mso[(size_t)i - 1], d2[(size_t)i], d3[(size_t)i], d2[(size_t)i - 1],
+                                      d3[(size_t)i - 1], lead[(size_t)i], lead[(size_t)i - 1], tail[(size_t)i], nst[(size_t)i],
+                                      W[(size_t)i + 1].X & ~W[(size_t)i + 1].S, i == 1 ? 1u : 0u);
+        for (int b = 0; b < 32; ++b) if ((st >> b) & 1u) out_begins[cnt++] = (i - 1) * 32 + b;
+    }
+    return cnt;
+}

@@ -125,3 +125,18 @@ def gpt2_word_form(data: bytes, single_digits=False):
     n = lib().hz_gpt2_word_form(arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), int(single_digits), out.ctypes.data_as(K.i32p))
     b = out[:n].tolist()
     return list(zip(b, b[1:] + [len(data)]))
+
+
+def llama3_word_form(data: bytes):
+    """Piece (begin, end) list from the word (bit-mask) form of the Llama-3 predicate, or None if the subject holds a non-ASCII
+    digit (such rows are handed to the generic kernel)."""
+    if not data:
+        return []
+    arr = np.frombuffer(data, np.uint8)
+    out = np.empty(len(data) + 1, np.int32)
+    lib().hz_llama3_word_form.restype = C.c_int64
+    n = lib().hz_llama3_word_form(arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), out.ctypes.data_as(K.i32p))
+    if n == -2:
+        return None
+    b = out[:n].tolist()
+    return list(zip(b, b[1:] + [len(data)]))

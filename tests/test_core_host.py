@@ -188,3 +188,35 @@ def test_gpt2_word_form_equals_closed_form(digits):
     for s in cases.EDGE_STRINGS + cases.long_prompts():
         if s:
             assert H.gpt2_word_form(s.encode(), digits) == H.gpt2_closed_form(s.encode(), digits), s[:40]
+
+
+def test_llama3_word_form_equals_pcre2(oracle_mod):
+    """The word (bit-mask) form of the Llama-3 / cl100k pattern that the window kernel evaluates, against PCRE2: exhaustive over
+    short strings of a small alphabet, random strings of wider ones (long enough to cross 32-position words), UTF-8 subjects."""
+    import itertools
+    o = oracle_mod.SplitOracle(A.LLAMA3_PATTERN, "isolate")
+    small = ["a", "'", "s", "L", " ", "\n", "\t", "1", "!", "\r"]
+    for L in range(1, 6):
+        for tup in itertools.product(small, repeat=L):
+            s = "".join(tup).encode()
+            assert H.llama3_word_form(s) == _oracle_split(o, s), s
+    rng = np.random.default_rng(17)
+    dense = ["a", "b", "'", "'", "s", "t", "m", "d", "r", "e", "v", "l", "S", "T", "R", "E", "L", " ", " ", " ", "\n", "\n", "\t", "\r",
+             "1", "2", "3", "!", "?", "-"]
+    uni = dense + [chr(0xA0), chr(0x2003), chr(0x3000), chr(0x416), chr(0x4E2D), chr(0x1F600), chr(0xE9), chr(0x85), chr(0x17F), chr(0xFF0C), chr(0x2028)]
+    for alpha in (dense, uni):
+        for _ in range(6000):
+            s = "".join(rng.choice(alpha, size=int(rng.integers(1, 150)))).encode()
+            assert H.llama3_word_form(s) == _oracle_split(o, s), s
+    for _ in range(3000):
+        s = bytes(rng.integers(0x09, 0x7F, size=int(rng.integers(1, 200)), dtype=np.uint8))
+        assert H.llama3_word_form(s) == _oracle_split(o, s), s
+    for _ in range(300):      # long runs: digits, newlines, spaces crossing several words
+        parts = [rng.choice(["7", "\n", " ", "a", "!", "\t"]) * int(rng.integers(1, 90)) for _ in range(int(rng.integers(1, 8)))]
+        s = "".join(parts).encode()
+        assert H.llama3_word_form(s) == _oracle_split(o, s), s
+    for s in cases.EDGE_STRINGS + cases.long_prompts():
+        if s:
+            got = H.llama3_word_form(s.encode())
+            if got is not None:      # (None: a non-ASCII digit — such rows go to the generic kernel)
+                assert got == _oracle_split(o, s.encode()), s[:40]
