@@ -65,10 +65,10 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
         for (int w = lane - lb; w < nload; w += 32) {            // continuation bytes copy their owner
             const uint8_t b = B[w];
             if (is_cont_byte(b) && w > -lb) {
-                int j = w - 1;
-                while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
+                int j = w - 1;                                    // first byte of the character: at most three bytes back
+                if (j > -lb && is_cont_byte(B[j])) { --j; if (j > -lb && is_cont_byte(B[j])) --j; }
                 uint8_t k = C_CONT;
-                if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= KC[j] & (uint8_t)~C_CONT;
+                if (B[j] >= 0xC0) k |= KC[j] & (uint8_t)~C_CONT;
                 KC[w] = k;
             }
         }
@@ -128,7 +128,8 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                         const int w = w0 + 32 * u;
                         if ((g[u] & V7_N) && c[u] >= 0x80) complex = true;          // digit groups are evaluated for ASCII digits only
                         bool pg = false;                                           // letter after a multi-byte "other" char at which a match starts
-                        if ((g[u] & V7_L) && !(g[u] & V7_CONT) && w > -lb && is_cont_byte(B[w - 1])) {
+                        // (the previous byte carries its character's class: only a multi-byte OTHER char needs the look-back)
+                        if ((g[u] & V7_L) && !(g[u] & V7_CONT) && w > -lb && (KC[w - 1] & (C_CONT | C_L | C_N | C_S)) == C_CONT) {
                             int j = w - 1;
                             while (j > -lb && is_cont_byte(B[j])) --j;
                             if (!(KC[j] & (C_L | C_N | C_S)))
