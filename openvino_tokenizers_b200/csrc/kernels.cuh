@@ -343,6 +343,66 @@ __device__ __forceinline__ int split_window_gpt2(WarpSmem& S, const RowParams& P
     return ns;
 }
 
+// Split phase for the fused BERT pre-tokenisation ( \s+ removed, then punctuation / CJK characters isolated ): a closed-form
+// per-position predicate replaces match evaluation + chain resolution.  A whitespace run is one dropped segment, every
+// punctuation / CJK character is its own segment, everything else forms words that start after whitespace, after a punctuation
+// character, or at the element start (same segments as the generic chain for PAT_BERT_FUSED, which the tests compare with the
+// two reference RegexSplit ops run back to back).
+__device__ __forceinline__ int split_window_bert(WarpSmem& S, const RowParams& P, const uint8_t* ascii_smem, int lane,
+                                                 int wlen, int end_rel, int nload, int lb, int& advance) {
+    auto& sp = S.u.sp;
+    uint8_t* const B = S.B();
+    uint8_t* const KC = sp.K();
+    ClassTables T = P.cls;
+    T.ascii = ascii_smem;
+    for (int w = lane - lb; w < nload; w += 32) {
+        const uint8_t b = B[w];
+        uint8_t k;
+        if (b < 0x80) k = ascii_smem[b];
+        else if (is_cont_byte(b) && w > -lb) {
+            int j = w - 1;
+            while (j >= -lb && j > w - 4 && is_cont_byte(B[j])) --j;
+            k = C_CONT;
+            if (j >= -lb && j > w - 4 && B[j] >= 0xC0) k |= char_class(B, j, end_rel, T);
+        } else k = char_class(B, w, end_rel, T);
+        KC[w] = k;
+    }
+    __syncwarp();
+    int ns = 0;
+    for (int it = 0; it * 32 < wlen; ++it) {
+        const int w = it * 32 + lane;
+        bool st = false;
+        uint16_t sg = 0;
+        if (w < wlen) {
+            const uint8_t c = KC[w];
+            if (!(c & C_CONT)) {
+                const uint8_t p = (w > -lb) ? KC[w - 1] : (uint8_t)C_S;       // (element start behaves like "after whitespace")
+                if (c & C_S) { st = w == 0 || !(p & C_S); sg = F_MATCH | F_DROP; }
+                else if (c & C_BP) { st = true; sg = F_MATCH; }
+                else st = w == 0 || (p & (C_S | C_BP)) != 0;
+            }
+            sg |= (uint16_t)w;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, st);
+        if (st) S.seg[ns + __popc(m & ((1u << lane) - 1u))] = sg;
+        if (lane == 0) S.segbits[it] = m;
+        ns += __popc(m);
+    }
+    for (int it = (wlen + 31) / 32 + lane; it < NWORDS; it += 32) S.segbits[it] = 0;
+    __syncwarp();
+    if (wlen == end_rel) {
+        advance = wlen;
+        if (lane == 0) S.seg[ns] = (uint16_t)wlen;
+    } else {
+        // the last segment may continue beyond the window: redo it from its start in the next window
+        --ns;
+        advance = S.seg[ns] & POS_MASK;
+        if (lane == 0 && advance > 0) S.segbits[advance >> 5] &= ~(1u << (advance & 31));
+    }
+    __syncwarp();
+    return ns;
+}
+
 // Sequentially (lane 0) find the extent of the segment starting at chars[pos] when it does not fit
 // a window.  Returns its length; is_match/drop describe it.
 __device__ __noinline__ int giant_segment(const RowParams& P, int pos, int end_rel, int& is_match, int& drop) {
@@ -737,7 +797,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
                                 keys_ready = true;
                             } else
                                 ns = split_window_gpt2(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
-                        } else
+                        } else if (P.spec.pat == PAT_BERT_FUSED && OP != OP_SPLIT && !(P.dbg_flags & 16))
+                            ns = split_window_bert(S, P, ascii_smem, lane, wlen, end_rel, nload, lb, advance);
+                        else
                             ns = split_window(S, P, ascii_smem, lane, wlen, end_rel, nload, advance);
                     }
                 }
