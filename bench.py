@@ -40,6 +40,9 @@ WORKLOADS = {
     "c2": dict(kind="wordpiece", vocab="bert_synth", rows=65536, row_bytes=256, gen="ascii_lower",
                name="C2: bert-shaped WordPiece (30 522 vocab, synthetic stand-in bert_synth), 65 536 x 256 B lower-cased "
                     "printable-ASCII docs per GPU, fused RegexSplit x2->WordpieceTokenizer"),
+    "c4": dict(kind="detok", vocab="llama2_detok_synth", rows=1024, row_bytes=1024, gen="ids",
+               name="C4: detokenize, VocabDecoder + ByteFallback fused, 1 024 x 1 024 token ids (Llama-2-shaped 32 000 vocab with 256 <0xHH> "
+                    "tokens, synthetic stand-in), skip_tokens {0,1,2}"),
     "c3": dict(kind="bpe", vocab="llama3_synth", rows=32768, row_bytes=1024, gen="utf8",
                name="C3 shard: Llama-3-shaped BPE (128 256 vocab, synthetic stand-in llama3_synth), 32 768 x 1 KiB "
                     "mixed-UTF-8 docs per GPU (262 144 rows at 8 GPUs), fused RegexSplit->BPETokenizer"),
@@ -191,6 +194,83 @@ def main_reference(args, w, rank, world):
     }))
 
 
+def main_detok(args, w, rank, world, local_rank):
+    """C4: metric = MB/s of detokenized text produced (bit-exact bytes); a step = one VocabDecoder+ByteFallback pass over 1 Mi ids."""
+    import ctypes as C
+    import torch
+    import oracle
+    from openvino_tokenizers_b200 import _capi as K
+    from openvino_tokenizers_b200 import assets as A
+    from openvino_tokenizers_b200 import ops
+    from openvino_tokenizers_b200.strings import pack_strings
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    vocab = pack_strings(A.load_detok_vocab(w["vocab"]))
+    Bn, Sn = w["rows"], w["row_bytes"]
+    ids = np.random.default_rng(1234).integers(0, len(vocab[0]), size=(Bn, Sn)).astype(np.int32)
+    skip = np.array([0, 1, 2], np.int32)
+    dec = ops.VocabDecoder(skip_tokens=[0, 1, 2], byte_fallback=True, device=local_rank)
+    ref = dec.evaluate([ids, *vocab])                      # creates the handle; host path
+    n_out = int(len(ref[4]))
+    L = K.lib()
+    cap = int(L.b200tok_vocabdec_max_chars(dec.handle, Bn, Sn))
+    d_ids = torch.from_numpy(ids).to(dev)
+    d_skip = torch.from_numpy(skip).to(dev)
+    d_rb, d_re = torch.empty(Bn, dtype=torch.int32, device=dev), torch.empty(Bn, dtype=torch.int32, device=dev)
+    d_b, d_e = torch.empty(Bn * Sn, dtype=torch.int32, device=dev), torch.empty(Bn * Sn, dtype=torch.int32, device=dev)
+    d_c = torch.empty(cap, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        out = K.Decoded(d_rb.data_ptr(), d_re.data_ptr(), d_b.data_ptr(), d_e.data_ptr(), d_c.data_ptr(), cap, 0, K.MEM_DEVICE)
+        K.check(L.b200tok_vocabdec_run(dec.handle, C.c_void_p(d_ids.data_ptr()), C.c_int64(Bn), C.c_int64(Sn), C.c_void_p(d_skip.data_ptr()),
+                                       C.c_int64(3), 1, C.byref(out), K.MEM_DEVICE, C.c_void_p(stream.cuda_stream)))
+        return out.n_chars
+    for _ in range(args.warmup):
+        step_device(); dec.evaluate([ids, *vocab])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = dec.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        n_dev = step_device()
+        ev[k][1].record()
+        torch.cuda.synchronize()
+    launches = dec.launches - launches0
+    clocks = sampler.stop()
+    assert n_dev == n_out and bytes(d_c[:n_out].cpu().numpy()) == bytes(ref[4])
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.evaluate([ids, *vocab])
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    peak, peak_src = measured_peak()
+    algo = 4 * Bn * Sn + 8 * Bn * Sn + n_out + 8 * Bn            # SURVEY 8d: ids in, per-token offsets + bytes + row extents out
+    t0 = time.perf_counter()
+    for _ in range(3):
+        o = oracle.vocab_decoder(ids, vocab, [0, 1, 2]); oracle.byte_fallback(o[2], o[3], o[4])
+    cpu_s = (time.perf_counter() - t0) / 3
+    print(json.dumps({
+        "metric": "detokenized text produced (bit-exact bytes)", "value": n_out / 1e6 / (ms / 1e3), "unit": "MB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": w["name"], "ids": Bn * Sn, "out_bytes": n_out, "l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
+                   "note": "the device-resident call returns the byte count to the host: one stream synchronisation is inside the step"},
+        "e2e": {"value": n_out / 1e6 / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": 4 * Bn * Sn, "d2h_bytes_per_step": 8 * Bn * Sn + n_out + 8 * Bn,
+                "ms_per_step": e2e_s * 1e3, "path": "ops.VocabDecoder(byte_fallback=True).evaluate on host arrays (pageable)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": algo / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s", "frac": algo / 1e9 / (ms / 1e3) / peak, "traffic": None,
+                     "kernel": "decode_len_kernel + cub scan + decode_copy_kernel (whole step)", "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},
+        "cpu_baseline": {"value": n_out / 1e6 / cpu_s, "unit": "MB/s", "cores": 1, "kind": "port", "sample": "the full 1 Mi ids, mean of 3"},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +285,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if w["kind"] == "detok":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the tokenize workloads; C4 reports its CPU port inline"}))
+            return
+        return main_detok(args, w, rank, world, local_rank)
     if args.impl == "reference":
         return main_reference(args, w, rank, world)
 
