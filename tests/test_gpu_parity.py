@@ -444,3 +444,89 @@ def test_host_pipeline_equals_device_path_and_oracle(ops, gpt2):
     exp = oracle_chain_bpe(gpt2, sub)
     for i, r in enumerate(sample):
         assert np.array_equal(got[2][got[0][r]:got[1][r]], exp[2][exp[0][i]:exp[1][i]])
+
+
+def _sample_rows(batch, rows, L):
+    rb, re_, b, e, c = batch
+    chars = np.concatenate([c[b[r]:e[r]] for r in rows])
+    return cases.uniform_batch(chars, len(rows), L)
+
+
+def test_c3_full_shard_properties(ops, llama3):
+    """BASELINE config 3, one GPU's shard at full size (32 768 x 1 KiB mixed UTF-8, Llama-3 pattern on the bit-mask kernel):
+    size-independent properties (lossless decode of every row, contiguous row extents, idempotence) + sampled rows vs the oracle."""
+    batch = cases.mixed_utf8_batch(32768, 1024)
+    rb, re_, b, e, c = batch
+    got = ops.split_bpe(llama3["split"], llama3["bpe"], list(batch))
+    ob, oe, ids = got
+    assert ob[0] == 0 and np.array_equal(ob[1:], oe[:-1]) and oe[-1] == len(ids)
+    vocab = llama3["assets"].vocab
+    assert ids.min() >= 0 and ids.max() < len(vocab)
+    lens = np.array([len(t) for t in vocab], dtype=np.int64)
+    assert int(lens[ids].sum()) == len(c)
+    assert np.all(np.add.reduceat(lens[ids], ob.astype(np.int64)) == 1024)
+    sample = np.r_[0:48, 16000:16048, 32720:32768]
+    for r in sample:
+        assert b"".join(vocab[t] for t in ids[ob[r]:oe[r]]) == bytes(c[b[r]:e[r]])
+    exp = oracle_chain_bpe(llama3, _sample_rows(batch, sample, 1024))
+    for i, r in enumerate(sample):
+        assert np.array_equal(ids[ob[r]:oe[r]], exp[2][exp[0][i]:exp[1][i]])
+    again = ops.split_bpe(llama3["split"], llama3["bpe"], list(batch))
+    assert cases.ragged_rows_equal(again, got)
+
+
+def test_c2_full_size_properties(ops, bert):
+    """BASELINE config 2 at full size (65 536 x 256 B lower-cased ASCII through the fused BERT splitter + WordPiece):
+    contiguous row extents, ids in range, idempotence, sampled rows vs the oracle chain of the three reference ops."""
+    batch = cases.random_ascii_batch(65536, 256, lower=True)
+    unk = bert["assets"].unk_token_id
+    got = ops.split_wordpiece(bert["s1"], bert["s2"], bert["wp"], list(batch), unk)
+    ob, oe, ids = got
+    assert ob[0] == 0 and np.array_equal(ob[1:], oe[:-1]) and oe[-1] == len(ids)
+    assert ids.min() >= 0 and ids.max() < len(bert["assets"].vocab)
+    sample = np.r_[0:64, 33000:33064, 65472:65536]
+    _, exp = oracle_chain_wp(bert, _sample_rows(batch, sample, 256))
+    for i, r in enumerate(sample):
+        assert np.array_equal(ids[ob[r]:oe[r]], exp[2][exp[0][i]:exp[1][i]])
+    again = ops.split_wordpiece(bert["s1"], bert["s2"], bert["wp"], list(batch), unk)
+    assert cases.ragged_rows_equal(again, got)
+
+
+def test_tokenizer_pipeline_with_special_tokens_and_dense_tail(ops, gpt2, oracle_mod):
+    """The op chain of a converted GPT-2-style tokenizer IR, every op on the GPU through the C ABI:
+    SpecialTokensSplit -> RegexSplit + BPETokenizer (skip-flagged pieces pass through whole) -> Truncate -> CombineSegments
+    (bos + tokens) -> RaggedToDense; against the same chain of oracle ops."""
+    a = gpt2["assets"]
+    specials = [t.decode() for t in (a.added_tokens or [])][:3] or ["<|endoftext|>"]
+    rng = np.random.default_rng(5)
+    texts = []
+    for i in range(400):
+        parts = []
+        for _ in range(int(rng.integers(1, 5))):
+            parts.append(bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(0, 120)), dtype=np.uint8)).decode())
+            if rng.random() < 0.6:
+                parts.append(specials[int(rng.integers(0, len(specials)))])
+        texts.append("".join(parts))
+    b, e, c = pack_strings(texts)
+    rb, re_ = np.arange(len(texts), dtype=np.int32), np.arange(1, len(texts) + 1, dtype=np.int32)
+    pattern = oracle_mod.special_tokens_pattern([(s, False, False) for s in specials])
+    # oracle chain
+    o_sp = oracle_mod.SpecialTokensSplitOracle(pattern)(rb, re_, b, e, c)
+    o_rs = gpt2["o_split"](o_sp[0], o_sp[1], o_sp[2], o_sp[3], c, o_sp[4])
+    o_ids = gpt2["o_bpe"](o_rs[0], o_rs[1], o_rs[2], o_rs[3], c)
+    # GPU chain
+    g_sp = ops.SpecialTokensSplit().evaluate([rb, re_, b, e, c, np.frombuffer(pattern.encode(), np.uint8)])
+    g_ids = ops.split_bpe(gpt2["split"], gpt2["bpe"], [g_sp[0], g_sp[1], g_sp[2], g_sp[3], c, g_sp[5]])
+    assert cases.ragged_rows_equal(g_ids, o_ids)
+    max_len, target, bos, pad = 48, 50, 50256, 0
+    o_t = oracle_mod.truncate([(o_ids[0], o_ids[1])], max_len, "right")[0]
+    one = (np.array([0], np.int32), np.array([1], np.int32), np.array([bos], np.int32))
+    o_c = oracle_mod.combine_segments([one, (o_t[0], o_t[1], o_ids[2])], [0, 0])
+    o_d = oracle_mod.ragged_to_dense(o_c[0], o_c[1], o_c[2], target, pad, True)
+    u8 = lambda s: np.frombuffer(s.encode(), np.uint8)
+    g_t = ops.Truncate(1).evaluate([g_ids[0], g_ids[1], g_ids[2], np.int32(max_len), u8("right"), u8("longest_first")])
+    g_c = ops.CombineSegments().evaluate([*one, g_t[0], g_t[1], g_t[2], np.array([0, 0], np.int32)])
+    g_d = ops.RaggedToDense(pad_right=True).evaluate([g_c[0], g_c[1], g_c[2], np.int32(target), np.int32(pad)])
+    assert np.array_equal(g_d[0], o_d[0]) and np.array_equal(g_d[1], o_d[1].astype(bool))
+    fused, fmask = ops.post_dense(g_ids[0], g_ids[1], g_ids[2], max_len, target, pad, prefix=[bos])
+    assert np.array_equal(fused, o_d[0]) and np.array_equal(fmask, o_d[1].astype(bool))
