@@ -174,8 +174,9 @@ struct BpeObj : b200tok_object {
 };
 struct WordpieceObj : b200tok_object {
     HostWordpiece h;
-    DevTrie root, sub;
-    WordpieceTables view() const { return WordpieceTables{root.view(), sub.view(), h.max_bytes}; }
+    DBuf<RankNode> root_nodes, sub_nodes;
+    DBuf<int32_t> root_first, sub_first;
+    WordpieceTables view() const { return WordpieceTables{RankTrie{root_nodes.p, root_first.p}, RankTrie{sub_nodes.p, sub_first.p}, h.max_bytes}; }
 };
 struct VocabEncObj : b200tok_object {
     HostVocabEnc h;
@@ -887,8 +888,8 @@ B200TOK_API int b200tok_wordpiece_create(const b200tok_wordpiece_desc* d, b200to
     if ((rc = init_object(o.get(), K_WORDPIECE, d->device))) return rc;
     DeviceGuard g(d->device);
     CU(o->cls.upload());
-    CU(o->root.upload(o->h.root));
-    CU(o->sub.upload(o->h.sub));
+    CU(o->root_nodes.upload(o->h.root.rank_nodes)); CU(o->root_first.upload(o->h.root.rank_root));
+    CU(o->sub_nodes.upload(o->h.sub.rank_nodes)); CU(o->sub_first.upload(o->h.sub.rank_root));
     CU(cudaDeviceSynchronize());
     *out = o.release();
     return B200TOK_OK;

@@ -103,6 +103,41 @@ void HostTrie::build(const std::vector<std::pair<std::string, int32_t>>& entries
     if (edge_byte.empty()) { edge_byte.push_back(0); edge_child.push_back(-1); }  // keep device buffers non-empty
 }
 
+void HostTrie::build_rank() {
+    const size_t N = value.size();
+    std::vector<int32_t> order, newid(N, -1);       // breadth-first order over the CSR trie; node 0 = root
+    order.reserve(N);
+    order.push_back(0);
+    newid[0] = 0;
+    for (size_t q = 0; q < order.size(); ++q) {
+        const int32_t n = order[q];
+        for (int32_t e = first[(size_t)n]; e < first[(size_t)n + 1]; ++e) {
+            const int32_t ch = edge_child[(size_t)e];
+            if (ch < 0) continue;
+            newid[(size_t)ch] = (int32_t)order.size();
+            order.push_back(ch);
+        }
+    }
+    rank_nodes.assign(order.size(), RankNode{});
+    for (size_t q = 0; q < order.size(); ++q) {
+        const int32_t n = order[q];
+        RankNode& r = rank_nodes[q];
+        r.value = value[(size_t)n];
+        r.base = -1;
+        for (int32_t e = first[(size_t)n]; e < first[(size_t)n + 1]; ++e) {       // edges are sorted by byte
+            const int32_t ch = edge_child[(size_t)e];
+            if (ch < 0) continue;
+            if (r.base < 0) r.base = newid[(size_t)ch];
+            r.bits[edge_byte[(size_t)e] >> 5] |= 1u << (edge_byte[(size_t)e] & 31);
+        }
+        int c = 0;
+        for (int w = 0; w < 8; ++w) { r.cum[w] = (uint8_t)c; c += __builtin_popcount(r.bits[w]); }   // (at most 255 children before the last word)
+        if (r.base < 0) r.base = 0;
+    }
+    rank_root.assign(256, -1);
+    for (int b = 0; b < 256; ++b) if (root_child[(size_t)b] >= 0) rank_root[(size_t)b] = newid[(size_t)root_child[(size_t)b]];
+}
+
 static std::string str_at(const b200tok_strings& s, int64_t i) {
     return std::string((const char*)s.chars + s.begins[i], (const char*)s.chars + s.ends[i]);
 }
@@ -273,6 +308,8 @@ int build_wordpiece(const b200tok_wordpiece_desc& d, HostWordpiece& out, std::st
     }
     out.root.build(r);
     out.sub.build(s);
+    out.root.build_rank();
+    out.sub.build_rank();
     out.max_bytes = d.max_bytes_per_word;
     return B200TOK_OK;
 }

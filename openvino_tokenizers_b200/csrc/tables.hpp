@@ -33,6 +33,11 @@ struct HostTrie {
         return FlatTrie{first.data(), value.data(), edge_byte.data(), edge_child.data(), root_child.data()};
     }
     size_t n_nodes() const { return value.size(); }
+    // the same trie in rank-indexed form (breadth-first numbering: a node's children are consecutive)
+    std::vector<RankNode> rank_nodes;
+    std::vector<int32_t> rank_root;
+    void build_rank();
+    RankTrie rank_view() const { return RankTrie{rank_nodes.data(), rank_root.data()}; }
 };
 
 struct HostBpe {
@@ -60,7 +65,7 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err);
 struct HostWordpiece {
     HostTrie root, sub;
     int32_t max_bytes = 100;
-    WordpieceTables view() const { return WordpieceTables{root.view(), sub.view(), max_bytes}; }
+    WordpieceTables view() const { return WordpieceTables{root.rank_view(), sub.rank_view(), max_bytes}; }
 };
 int build_wordpiece(const b200tok_wordpiece_desc& d, HostWordpiece& out, std::string& err);
 

@@ -891,21 +891,55 @@ B2_HD int bpe_merge_heap(const MergeTable& M, int n, int32_t* sym_id, int32_t* s
 // WordPiece: one word s[b..e) -> ids; returns count (>= 1).  src/wordpiece_tokenizer.cpp:96-130.
 // A zero-length word yields [unk] (the reference reads out of bounds there).
 // ------------------------------------------------------------------------------------------
+// Rank-indexed byte trie for the WordPiece walks: a node carries a 256-bit child bitmap with per-word prefix counts and the
+// index of its first child (children are numbered consecutively, in byte order), so one step is one round of independent
+// loads — bitmap word, prefix count, base, value — instead of a binary search over an edge list.
+struct RankNode { uint32_t bits[8]; int32_t base; int32_t value; uint8_t cum[8]; };      // 48 bytes
+struct RankTrie {
+    const RankNode* nodes;
+    const int32_t* root_child;   // [256] child of the root per byte, -1 if none
+};
+B2_HD int32_t rank_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+// Longest match starting at s[idx] (same contract as trie_longest).
+B2_HD int32_t rank_trie_longest(const RankTrie& t, const uint8_t* s, int& idx, int end) {
+    int32_t node = t.root_child[s[idx]];
+    int32_t found = -1;
+    int best = idx, i = idx;
+    while (node >= 0) {
+        ++i;
+        const RankNode& nd = t.nodes[node];
+        const int32_t v = nd.value;
+        if (v != -1) { found = v; best = i; }
+        if (i >= end) break;
+        const uint32_t ch = s[i], w = ch >> 5, bit = ch & 31u;
+        const uint32_t bw = nd.bits[w];
+        node = ((bw >> bit) & 1u) ? nd.base + (int32_t)nd.cum[w] + rank_popc(bw & ((1u << bit) - 1u)) : -1;
+    }
+    idx = best;
+    return found;
+}
+
 struct WordpieceTables {
-    FlatTrie root;
-    FlatTrie sub;
+    RankTrie root;
+    RankTrie sub;
     int32_t max_bytes;
 };
 
 B2_HD int wordpiece_word(const WordpieceTables& T, const uint8_t* s, int b, int e, int32_t unk, int32_t* out) {
     if (e - b > T.max_bytes || e <= b) { out[0] = unk; return 1; }
     int idx = b;
-    int32_t id = trie_longest(T.root, s, idx, e);
+    int32_t id = rank_trie_longest(T.root, s, idx, e);
     if (id < 0) { out[0] = unk; return 1; }
     int n = 0;
     out[n++] = id;
     while (idx < e) {
-        id = trie_longest(T.sub, s, idx, e);
+        id = rank_trie_longest(T.sub, s, idx, e);
         if (id < 0) { out[0] = unk; return 1; }
         out[n++] = id;
     }
