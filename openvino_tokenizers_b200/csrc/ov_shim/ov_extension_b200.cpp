@@ -302,10 +302,151 @@ public:
     }
 };
 
+// ---- SpecialTokensSplit (src/special_tokens_split.hpp; evaluate src/special_tokens_split.cpp:61-162) --------------------
+class SpecialTokensSplit : public ov::op::Op {
+public:
+    OPENVINO_OP("SpecialTokensSplit");
+    SpecialTokensSplit() = default;
+    explicit SpecialTokensSplit(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto n = get_input_size();
+        OPENVINO_ASSERT(n == 6 || n == 7, "Incorrect number of inputs passed to SpecialTokensSplit: ", n,
+                        "; try to reconvert tokenizer with newer version of OpenVINO Tokenizers");
+        for (size_t i = 0; i < 4; ++i) set_output_type(i, ov::element::i32, i < 2 ? get_input_partial_shape(0) : ov::PartialShape{ov::Dimension()});
+        set_output_type(4, ov::element::u8, ov::PartialShape{ov::Dimension()});
+        set_output_type(5, ov::element::boolean, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<SpecialTokensSplit>(in);
+        c->m_state = m_state;
+        return c;
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const bool has_skips = in.size() == 7;
+        std::call_once(m_state->once, [&] {                                // src/special_tokens_split.cpp:65-69
+            const auto& p = in[5 + has_skips];
+            check(b200tok_specialsplit_create(p.data<const char>(), (int64_t)p.get_size(), 0, &m_state->h));
+        });
+        const size_t cap = in[4].get_size() + in[2].get_size();
+        out[0].set_shape(in[0].get_shape());
+        out[1].set_shape(in[1].get_shape());
+        out[2].set_shape({cap}); out[3].set_shape({cap}); out[5].set_shape({cap});
+        out[4] = in[4];                                                     // :93
+        auto rin = ragged_of(in, has_skips ? reinterpret_cast<const uint8_t*>(in[5].data<bool>()) : nullptr);
+        b200tok_ragged_strings_out r{out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<int32_t>(), out[3].data<int32_t>(),
+                                     reinterpret_cast<uint8_t*>(out[5].data<bool>()), (int64_t)cap, 0, 0, B200TOK_MEM_HOST};
+        check(b200tok_specialsplit_run(m_state->h, &rin, &r, nullptr));
+        out[2].set_shape({(size_t)r.n_elems}); out[3].set_shape({(size_t)r.n_elems}); out[5].set_shape({(size_t)r.n_elems});   // :155-158
+        return true;
+    }
+private:
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+// ---- Truncate (src/truncate.cpp:37-147): outputs alias the inputs and are edited in place ------------------------------------
+class Truncate : public ov::op::Op {
+public:
+    OPENVINO_OP("Truncate");
+    Truncate() = default;
+    Truncate(const ov::OutputVector& args, int num_inputs = 1) : ov::op::Op(args), m_num_inputs(num_inputs) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        for (int i = 0; i < m_num_inputs; ++i)
+            for (int k = 0; k < 3; ++k) set_output_type(3 * i + k, get_input_element_type(3 * i + k), get_input_partial_shape(3 * i + k));
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<Truncate>(in, m_num_inputs); }
+    bool visit_attributes(ov::AttributeVisitor& v) override { v.on_attribute("m_num_inputs", m_num_inputs); return true; }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const size_t n = in.size();
+        const int32_t max_length = in[n - 3].data<const int32_t>()[0];
+        const std::string side(in[n - 2].data<const char>(), in[n - 2].get_size()), mode(in[n - 1].data<const char>(), in[n - 1].get_size());
+        for (int i = 0; i < 3 * m_num_inputs; ++i) out[i] = in[i];                                   // :52-56
+        int32_t* b1 = m_num_inputs == 2 ? out[3].data<int32_t>() : nullptr;
+        int32_t* e1 = m_num_inputs == 2 ? out[4].data<int32_t>() : nullptr;
+        check(b200tok_truncate_run(0, m_num_inputs, out[0].data<int32_t>(), out[1].data<int32_t>(), b1, e1, (int64_t)out[0].get_size(), max_length,
+                                   side.c_str(), mode.c_str(), B200TOK_MEM_HOST, nullptr));
+        return true;
+    }
+private:
+    int m_num_inputs = 1;
+};
+
+// ---- CombineSegments (src/combine_segments.cpp:36-134), i32 elements ---------------------------------------------------------
+class CombineSegments : public ov::op::Op {
+public:
+    OPENVINO_OP("CombineSegments");
+    CombineSegments() = default;
+    explicit CombineSegments(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        OPENVINO_ASSERT((get_input_size() - 1) % 3 == 0);
+        for (size_t k = 0; k < 6; ++k) set_output_type(k, ov::element::i32, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<CombineSegments>(in); }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const size_t num = (in.size() - 1) / 3;
+        OPENVINO_ASSERT(num == in.back().get_size());
+        std::vector<b200tok_ragged_i32> segs(num);
+        size_t rows = 0, flat = 0;
+        ov::Shape ps;
+        for (size_t j = 0; j < num; ++j) {
+            OPENVINO_ASSERT(in[3 * j + 2].get_element_type() == ov::element::i32, "the B200 path combines i32 segments");
+            segs[j] = b200tok_ragged_i32{in[3 * j].data<const int32_t>(), in[3 * j + 1].data<const int32_t>(), (int64_t)in[3 * j].get_size(),
+                                         in[3 * j + 2].data<const int32_t>(), (int64_t)in[3 * j + 2].get_size()};
+            if (in[3 * j].get_size() >= rows) { rows = in[3 * j].get_size(); ps = in[3 * j].get_shape(); }
+        }
+        for (size_t j = 0; j < num; ++j) flat += (segs[j].n == 1 ? rows : 1) * (size_t)segs[j].n_elems;      // :65-71
+        for (int t = 0; t < 2; ++t) { out[3 * t].set_shape(ps); out[3 * t + 1].set_shape(ps); out[3 * t + 2].set_shape({flat}); }
+        int64_t n_out = 0;
+        check(b200tok_combine_segments_run(0, segs.data(), (int)num, in.back().data<const int32_t>(), out[0].data<int32_t>(), out[1].data<int32_t>(),
+                                           out[2].data<int32_t>(), out[5].data<int32_t>(), (int64_t)flat, &n_out, B200TOK_MEM_HOST, nullptr));
+        std::copy_n(out[0].data<int32_t>(), rows, out[3].data<int32_t>());                                   // both ragged outputs share the offsets (:30-32)
+        std::copy_n(out[1].data<int32_t>(), rows, out[4].data<int32_t>());
+        out[2].set_shape({(size_t)n_out}); out[5].set_shape({(size_t)n_out});                                // :127-128
+        return true;
+    }
+};
+
+// ---- RaggedToDense (src/ragged_to_dense.cpp:70-174), i32 elements, no trailing dense dimensions -------------------------------
+class RaggedToDense : public ov::op::Op {
+public:
+    OPENVINO_OP("RaggedToDense");
+    RaggedToDense() = default;
+    RaggedToDense(const ov::OutputVector& args, bool pad_right = true, bool pad_max_length = false)
+        : ov::op::Op(args), m_pad_right(pad_right), m_pad_max_length(pad_max_length) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        auto shape = get_input_partial_shape(0);
+        shape.push_back(ov::Dimension());
+        set_output_type(0, get_input_element_type(2), shape);
+        set_output_type(1, ov::element::boolean, shape);
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<RaggedToDense>(in, m_pad_right, m_pad_max_length); }
+    bool visit_attributes(ov::AttributeVisitor& v) override { v.on_attribute("pad_right", m_pad_right); v.on_attribute("m_pad_max_length", m_pad_max_length); return true; }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        OPENVINO_ASSERT(in[2].get_element_type() == ov::element::i32 && in[2].get_shape().size() == 1, "the B200 path densifies 1-D i32 data");
+        const int32_t target = in[3].data<const int32_t>()[0];
+        ov::Shape shape = in[0].get_shape();
+        shape.push_back((size_t)target);
+        out[0].set_shape(shape); out[1].set_shape(shape);
+        const bool pad_right = in.size() == 6 ? in[5].data<bool>()[0] : m_pad_right;                          // :113-116
+        check(b200tok_ragged_to_dense_run(0, in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(), in[2].data<const int32_t>(),
+                                          (int64_t)in[2].get_size(), target, in[4].data<const int32_t>()[0], pad_right, m_pad_max_length,
+                                          out[0].data<int32_t>(), out[1] ? reinterpret_cast<uint8_t*>(out[1].data<bool>()) : nullptr, B200TOK_MEM_HOST, nullptr));
+        return true;
+    }
+private:
+    bool m_pad_right = true, m_pad_max_length = false;
+};
+
+// The byte-level shims (BytesToChars, CharsToBytes, FuzeRagged, UTF8Validate) bind the same way to b200tok_bytes_to_chars_run,
+// b200tok_chars_to_bytes_run, b200tok_fuze_ragged_run and b200tok_utf8_validate_run (worst-case chars 2x / 1x / - / 3x, then shrunk).
+
 }  // namespace b200
 
 // Same registration entry point as the reference (src/ov_extension.cpp:72); only the hot-path ops are provided here —
-// load the reference extension as well for the remaining 27 ops, ours registered last so that these six names resolve here.
+// load the reference extension as well for the remaining ops, ours registered last so that these names resolve here.
 OPENVINO_CREATE_EXTENSIONS(std::vector<ov::Extension::Ptr>({
     std::make_shared<ov::OpExtension<b200::RegexSplit>>(),
     std::make_shared<ov::OpExtension<b200::BPETokenizer>>(),
@@ -313,6 +454,10 @@ OPENVINO_CREATE_EXTENSIONS(std::vector<ov::Extension::Ptr>({
     std::make_shared<ov::OpExtension<b200::VocabEncoder>>(),
     std::make_shared<ov::OpExtension<b200::VocabDecoder>>(),
     std::make_shared<ov::OpExtension<b200::ByteFallback>>(),
+    std::make_shared<ov::OpExtension<b200::SpecialTokensSplit>>(),
+    std::make_shared<ov::OpExtension<b200::Truncate>>(),
+    std::make_shared<ov::OpExtension<b200::CombineSegments>>(),
+    std::make_shared<ov::OpExtension<b200::RaggedToDense>>(),
 }));
 
 // GenAI's GGUF path dlsym()s this factory (src/tokenizers_factory.hpp:32-33); the signature is frozen.
@@ -326,6 +471,10 @@ create_tokenizer_node(const std::string& op_type, const ov::OutputVector& inputs
     if (op_type == "VocabEncoder") return std::make_shared<b200::VocabEncoder>(inputs)->outputs();
     if (op_type == "VocabDecoder") return std::make_shared<b200::VocabDecoder>(inputs, get("skip_tokens", std::vector<int>{}))->outputs();
     if (op_type == "ByteFallback") return std::make_shared<b200::ByteFallback>(inputs)->outputs();
+    if (op_type == "SpecialTokensSplit") return std::make_shared<b200::SpecialTokensSplit>(inputs)->outputs();
+    if (op_type == "Truncate") return std::make_shared<b200::Truncate>(inputs, get("m_num_inputs", 1))->outputs();
+    if (op_type == "CombineSegments") return std::make_shared<b200::CombineSegments>(inputs)->outputs();
+    if (op_type == "RaggedToDense") return std::make_shared<b200::RaggedToDense>(inputs, get("pad_right", true), get("m_pad_max_length", false))->outputs();
     OPENVINO_THROW("Unsupported operation type in the B200 hot-path extension: ", op_type);
 }
 }}  // namespace ov::tokenizers
