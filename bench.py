@@ -314,17 +314,35 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
-    # N > 1: the shard is cut into row blocks; block k+1 is tokenised while block k's id rows are all-gathered (NCCL runs the
-    # collective on its own stream once the producing kernels are done), so the exchange overlaps the compute
-    n_blocks = int(os.environ.get("B200TOK_BENCH_BLOCKS", "2")) if world > 1 else 1
+    # N > 1: the emit step stores every id row straight into the result buffers of all ranks over NVLink peer memory
+    # (sharded.PeerGather: torch symmetric memory + b200tok_split_bpe_run_sharded), i.e. the all-gatherv is fused into the
+    # compaction kernel.  B200TOK_BENCH_EXCHANGE=nccl selects the NCCL slot all-gather instead (row blocks pipelined).
+    n_blocks = 1
+    exchange = "single GPU"
     if world > 1:
-        blocks = [R.to_device(bk, dev) for bk in R.split_rows(batch, n_blocks)]
-        block_out = [pipe.alloc_device_out(bk.n_rows, bk.n_chars + bk.n_elems) for bk in blocks]
-        gathered = [torch.empty(world * bk.n_chars, dtype=torch.int32, device=dev) for bk in blocks]
+        mode = os.environ.get("B200TOK_BENCH_EXCHANGE", "peer")
+        pg = None
+        if mode == "peer":
+            try:
+                from openvino_tokenizers_b200.sharded import PeerGather
+                pg = PeerGather(db.n_rows, db.n_chars, dev)
+                exchange = "row shards; emit fused with the all-gatherv: the compaction kernel stores id rows into every rank's buffers over NVLink peer memory"
+            except Exception as ex:      # symmetric memory unavailable on this box: fall back to the NCCL exchange (still GPU-only)
+                print(f"[bench] peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
+        if pg is None:
+            n_blocks = int(os.environ.get("B200TOK_BENCH_BLOCKS", "2"))
+            blocks = [R.to_device(bk, dev) for bk in R.split_rows(batch, n_blocks)]
+            block_out = [pipe.alloc_device_out(bk.n_rows, bk.n_chars + bk.n_elems) for bk in blocks]
+            gathered = [torch.empty(world * bk.n_chars, dtype=torch.int32, device=dev) for bk in blocks]
+            exchange = ("row shards in %d row block(s); all-gatherv of block k's ragged id rows over NCCL (fixed-capacity slots, no host sync) "
+                        "overlaps the tokenisation of block k+1" % n_blocks)
 
     def step_device():
         if world == 1:
             return pipe.run_device(db)
+        if pg is not None:
+            pg.run(pipe, db)
+            return [{"n": pg.n}]
         works = []
         for bk, bo, g in zip(blocks, block_out, gathered):
             o = pipe.run_device(bk, bo)
@@ -427,7 +445,7 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": w["name"], "rows_per_gpu": db.n_rows, "row_bytes": w["row_bytes"], "tokens_per_gpu": n_ids,
                        "l2": "256 MiB buffer zeroed between timed steps (L2 flush), outside the per-step event pair",
-                       "multi_gpu": "row shards in %d row block(s);" % n_blocks + " all-gatherv of block k's ragged id rows over NCCL (fixed-capacity slots, no host sync) overlaps the tokenisation of block k+1" if world > 1 else "single GPU"},
+                       "multi_gpu": exchange},
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "path": "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -174,6 +174,27 @@ B200TOK_API int b200tok_bpe_run(b200tok_handle h, const b200tok_ragged_strings* 
 B200TOK_API int b200tok_split_bpe_run(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
                                       b200tok_ragged_ids* out, void* cuda_stream);
 
+/* ---- Sharded output over NVLink peer memory --------------------------------------------------------
+ * One process per GPU tokenises its own row shard; instead of "emit locally, then all-gatherv", the emit step of this call
+ * stores every id row straight into the result buffers of ALL ranks (peer-mapped device pointers, e.g. from CUDA IPC or
+ * torch symmetric memory), so the exchange is fused into the compaction kernel.  Rank r's rows land in slot r:
+ *   ids[p][r * slot_capacity + ...], begins/ends[p][r * rows_per_rank + row] (offsets already shifted by r * slot_capacity).
+ * The caller orders a cross-rank barrier on the stream before reading (peers finish their stores at their own pace).
+ * `in` must be device memory; every rank must pass the same world, slot_capacity (>= in->n_chars + in->n_elems * suffix)
+ * and rows_per_rank (>= in->n_rows).                                                                              */
+#define B200TOK_MAX_PEERS 8
+typedef struct {
+    int world, rank;
+    int32_t* ids[B200TOK_MAX_PEERS];      /* each [world * slot_capacity]  */
+    int32_t* begins[B200TOK_MAX_PEERS];   /* each [world * rows_per_rank]  */
+    int32_t* ends[B200TOK_MAX_PEERS];
+    int64_t slot_capacity;
+    int64_t rows_per_rank;
+} b200tok_peer_out;
+/* n_ids_device (optional, device): this rank's id count.  Fully asynchronous on `cuda_stream`. */
+B200TOK_API int b200tok_split_bpe_run_sharded(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
+                                              const b200tok_peer_out* peers, int64_t* n_ids_device, void* cuda_stream);
+
 /* ---- WordpieceTokenizer --------------------------------------------------------------------
  * inputs [5..7] vocab, [8] unk_token_id; attributes suffix_indicator / max_bytes_per_word
  * (src/wordpiece_tokenizer.hpp:41-45). */

@@ -264,6 +264,7 @@ struct ChunkLaunch {
     int32_t *host_begins = nullptr, *host_ends = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_mine = nullptr;
     bool lean = false;           // pipelined chunks: direct row bases, folded finish, status cleared by the caller
+    const b200tok_peer_out* peers = nullptr;   // sharded output: the compaction stores into every rank's buffers
 };
 
 constexpr size_t kRowsSmem = kRowsSmemFixed + WARPS_PER_BLOCK * sizeof(WarpSmem);
@@ -351,6 +352,13 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
     } else if (c.lean) {
         compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, nullptr, nullptr, c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, (int32_t)B,
                                                                   c.d_oa, nullptr, nullptr, c.out_cap, c.P.status, nullptr, c.P.row_cnt, c.d_oe);
+        ++owner->launches;
+    } else if (c.peers) {
+        PeerOut Q{};
+        Q.world = c.peers->world; Q.rank = c.peers->rank; Q.slot_capacity = c.peers->slot_capacity; Q.rows_per_rank = c.peers->rows_per_rank;
+        for (int p = 0; p < Q.world; ++p) { Q.ids[p] = c.peers->ids[p]; Q.begins[p] = c.peers->begins[p]; Q.ends[p] = c.peers->ends[p]; }
+        compact_rows_peer_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, c.P.row_cnt, (int32_t)B, Q,
+                                                                       c.P.status, c.total_dev);
         ++owner->launches;
     } else {
         finish_offsets_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.d_ob, c.P.row_cnt, (int32_t)B, c.d_oe, c.P.status, c.total_dev);
@@ -549,7 +557,7 @@ int run_rows_host_pipelined(b200tok_object* owner, const RowCall& call, const b2
 // The shared driver of the row kernels.  `owner` provides workspace / class tables / launch counter.
 // Token ops write (begins, ends, ids); the split op writes (rb', re', begins', ends', skips').
 int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_strings* in,
-             b200tok_ragged_ids* out_ids, b200tok_ragged_strings_out* out_split, void* user_stream) {
+             b200tok_ragged_ids* out_ids, b200tok_ragged_strings_out* out_split, void* user_stream, const b200tok_peer_out* peers = nullptr) {
     int rc = validate_in(in);
     if (rc) return rc;
     DeviceGuard guard(owner->device);
@@ -645,6 +653,9 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
             CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B)); CU(w.out_a.ensure(tmp_cap + kMaxChunks));
             d_ob = w.out_begins.p; d_oe = w.out_ends.p; d_oa = w.out_a.p;
             out_cap = std::min<int64_t>(out_cap, tmp_cap);
+        } else if (peers) {      // sharded output: only the local exclusive scan of the row counts is kept on this device
+            CU(w.out_begins.ensure(B)); CU(w.out_ends.ensure(B));
+            d_ob = w.out_begins.p; d_oe = w.out_ends.p; d_oa = w.tmp_a.p;
         } else { d_ob = out_ids->begins; d_oe = out_ids->ends; d_oa = out_ids->ids; }
     } else {
         out_cap = out_split->capacity;
@@ -655,7 +666,7 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
         } else { d_ob = out_split->ragged_begins; d_oe = out_split->ragged_ends; d_oa = out_split->begins; d_obb = out_split->ends; d_oc = out_split->skips; }
     }
     if (!d_ob || !d_oe || (!d_oa && out_cap > 0)) return fail(B200TOK_E_INVALID, "missing output buffers");
-    const bool async = out_ids && !host && out_ids->n_ids_device;
+    const bool async = out_ids && !host && (out_ids->n_ids_device || peers);
 
     for (int attempt = 0; attempt < 4; ++attempt) {
         ChunkLaunch c;
@@ -671,8 +682,9 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
         c.pool_used = w.pool_used.p;
         c.rows = B; c.per_elem_extra = per_elem_extra; c.row_cap = w.row_cap.p; c.cub_tmp = w.cub_tmp.p; c.cub_bytes = cub_bytes;
         c.d_ob = d_ob; c.d_oe = d_oe; c.d_oa = d_oa; c.d_obb = d_obb; c.d_oc = d_oc; c.out_cap = out_cap;
-        c.total_dev = async ? out_ids->n_ids_device : w.total.p;
+        c.total_dev = (async && out_ids->n_ids_device) ? out_ids->n_ids_device : w.total.p;
         c.is_split = is_split;
+        c.peers = peers;
         if ((rc = launch_chunk(owner, call, c, st, w.timing))) return rc;
         CU(cudaEventRecord(w.last_done, st));
         if (async) return B200TOK_OK;
@@ -876,6 +888,28 @@ B200TOK_API int b200tok_split_bpe_run(b200tok_handle split, b200tok_handle bpe, 
     call.split = s;
     call.bpe = b;
     return run_rows(b, call, in, out, nullptr, stream);
+}
+
+B200TOK_API int b200tok_split_bpe_run_sharded(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
+                                              const b200tok_peer_out* peers, int64_t* n_ids_device, void* stream) {
+    SplitObj* s = as<SplitObj>(split, K_SPLIT);
+    BpeObj* b = as<BpeObj>(bpe, K_BPE);
+    if (!s || !b || !in || !peers) return fail(B200TOK_E_INVALID, "expected (RegexSplit, BPETokenizer) handles, input and peer buffers");
+    if (s->device != b->device) return fail(B200TOK_E_INVALID, "handles live on different devices");
+    if (in->mem != B200TOK_MEM_DEVICE) return fail(B200TOK_E_INVALID, "the sharded call takes device-resident input");
+    if (peers->world < 1 || peers->world > B200TOK_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world || peers->rows_per_rank < in->n_rows ||
+        peers->slot_capacity < in->n_chars + in->n_elems * (int64_t)b->h.end_suffix.size())
+        return fail(B200TOK_E_INVALID, "bad peer layout (world 1..8, rows_per_rank >= rows, slot_capacity >= worst-case ids of the shard)");
+    for (int p = 0; p < peers->world; ++p)
+        if (!peers->ids[p] || !peers->begins[p] || !peers->ends[p]) return fail(B200TOK_E_INVALID, "missing peer buffer %d", p);
+    RowCall call;
+    call.op = OP_BPE;
+    call.split = s;
+    call.bpe = b;
+    int64_t dummy_total = 0;
+    b200tok_ragged_ids out{nullptr, nullptr, nullptr, peers->slot_capacity, 0, n_ids_device, B200TOK_MEM_DEVICE};
+    (void)dummy_total;
+    return run_rows(b, call, in, &out, nullptr, stream, peers);
 }
 
 // ---- WordPiece ----

@@ -1056,4 +1056,51 @@ __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, 
     }
 }
 
+
+// Emit fused with the all-gatherv: every row is copied once from its worst-case slot and stored into the result
+// buffers of all ranks over NVLink peer memory; row offsets are written shifted into this rank's slot.
+struct PeerOut {
+    int32_t* ids[8]; int32_t* begins[8]; int32_t* ends[8];
+    int32_t world, rank; int64_t slot_capacity, rows_per_rank;
+};
+__global__ void compact_rows_peer_kernel(const int32_t* tmp_a, const int32_t* row_base, const int32_t* row_ext, const uint8_t* row_flag,
+                                         const int32_t* out_begin, const int32_t* row_cnt, int32_t n_rows, const PeerOut Q, int32_t* status,
+                                         int64_t* total_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int64_t slot = (int64_t)Q.rank * Q.slot_capacity;
+    for (int r = warp; r < n_rows; r += nwarps) {
+        const int64_t src = row_base[r];
+        const int ext = row_ext[r], cnt = row_cnt[r];
+        const int64_t dst = slot + out_begin[r];
+        if (lane < Q.world) {
+            Q.begins[lane][(int64_t)Q.rank * Q.rows_per_rank + r] = (int32_t)dst;
+            Q.ends[lane][(int64_t)Q.rank * Q.rows_per_rank + r] = (int32_t)(dst + cnt);
+        }
+        if (lane == 0 && r == n_rows - 1) { status[ST_TOTAL] = out_begin[r] + cnt; if (total_out) *total_out = out_begin[r] + cnt; }
+        if (out_begin[r] + cnt > Q.slot_capacity) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
+        if (!row_flag[r]) {
+            for (int t = lane; t < ext; t += 128) {
+                int32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < ext) ? __ldcs(tmp_a + src + t + 32 * u) : 0;
+                for (int p = 0; p < Q.world; ++p) {
+                    int32_t* dp = Q.ids[p] + dst;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (t + 32 * u < ext) dp[t + 32 * u] = v[u];
+                }
+            }
+        } else {      // rows with holes (giant pieces): filter while copying
+            int64_t d = dst;
+            for (int t0 = 0; t0 < ext; t0 += 32) {
+                const int t = t0 + lane;
+                const int v = t < ext ? tmp_a[src + t] : -1;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, v >= 0);
+                if (v >= 0) { const int64_t o = d + __popc(m & ((1u << lane) - 1u)); for (int p = 0; p < Q.world; ++p) Q.ids[p][o] = v; }
+                d += __popc(m);
+            }
+        }
+    }
+}
+
 }  // namespace b200tok

@@ -82,3 +82,41 @@ def allgather_ragged_slots(ids_buf: torch.Tensor, begins: torch.Tensor, ends: to
         v = all_be.view(world, 2, B)
         return v[:, 0].reshape(-1), v[:, 1].reshape(-1), out_ids
     return finish if async_op else finish()
+
+
+class PeerGather:
+    """Emit fused with the all-gatherv over NVLink peer memory: the result buffers of every rank live in torch
+    symmetric memory; `b200tok_split_bpe_run_sharded` stores this rank's compacted id rows into all of them from inside its
+    compaction kernel, and one symmetric-memory barrier on the stream orders the ranks.  Equal shards (rows, capacity) per rank.
+    Result layout = allgather_ragged_slots: rank r's rows in slot r, offsets shifted by r * cap."""
+
+    def __init__(self, rows_per_rank: int, slot_capacity: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _capi as K
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PeerGather supports up to 8 ranks (one NVSwitch domain)")
+        self.rows, self.cap = int(rows_per_rank), int(slot_capacity)
+        mk = lambda n: symm.empty(n, dtype=torch.int32, device=device)
+        self.ids, self.begins, self.ends = mk(self.world * self.cap), mk(self.world * self.rows), mk(self.world * self.rows)
+        self._h = [symm.rendezvous(t, self.group) for t in (self.ids, self.begins, self.ends)]
+        self.n = torch.zeros(1, dtype=torch.int64, device=device)
+        po = K.PeerOut()
+        po.world, po.rank, po.slot_capacity, po.rows_per_rank = self.world, self.rank, self.cap, self.rows
+        for p in range(self.world):
+            po.ids[p], po.begins[p], po.ends[p] = (int(h.buffer_ptrs[p]) for h in self._h)
+        self._po = po
+
+    def run(self, pipe, db):
+        """pipe: runtime.TokenizerPipeline (kind 'bpe'); db: runtime.DeviceBatch of this rank's shard.  Asynchronous on the current
+        torch stream up to the barrier; returns (begins, ends, ids) views of this rank's copy of the gathered result."""
+        import ctypes as C
+        from . import _capi as K
+        rin = K.RaggedStrings(db.rb.data_ptr(), db.re.data_ptr(), db.n_rows, db.begins.data_ptr(), db.ends.data_ptr(), db.n_elems,
+                              db.chars.data_ptr(), db.n_chars, None, K.MEM_DEVICE)
+        self._h[0].barrier(channel=1)   # nobody still reads the previous result (readers are ordered before this on their streams)
+        K.check(K.lib().b200tok_split_bpe_run_sharded(pipe.split1.handle, pipe.tok.handle, C.byref(rin), C.byref(self._po),
+                                                      C.c_void_p(self.n.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self._h[0].barrier(channel=0)   # every rank's stores into my buffers are complete and visible after this
+        return self.begins, self.ends, self.ids

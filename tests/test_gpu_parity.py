@@ -530,3 +530,41 @@ def test_tokenizer_pipeline_with_special_tokens_and_dense_tail(ops, gpt2, oracle
     assert np.array_equal(g_d[0], o_d[0]) and np.array_equal(g_d[1], o_d[1].astype(bool))
     fused, fmask = ops.post_dense(g_ids[0], g_ids[1], g_ids[2], max_len, target, pad, prefix=[bos])
     assert np.array_equal(fused, o_d[0]) and np.array_equal(fmask, o_d[1].astype(bool))
+
+
+def test_sharded_peer_store_emit_world1(ops, gpt2):
+    """b200tok_split_bpe_run_sharded (emit fused with the all-gatherv over peer memory) on a one-rank group: the peer-store
+    compaction kernel must produce the rows of the ordinary path (the multi-rank exchange is checked by
+    tools/peer_gather_check.py under torchrun)."""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from openvino_tokenizers_b200 import runtime as R
+    from openvino_tokenizers_b200.sharded import PeerGather
+    own = not dist.is_initialized()
+    if own:
+        with socket.socket() as s_:
+            s_.bind(("127.0.0.1", 0))
+            port = s_.getsockname()[1]
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rng = np.random.default_rng(8)
+        strings = [bytes(rng.integers(0x20, 0x7F, size=int(n), dtype=np.uint8)) for n in rng.integers(0, 900, size=3000)]
+        strings[17] = b"x" * 2000                                    # a piece longer than a window: giant path, row with holes
+        batch = cases.batch_from_strings(strings)
+        exp = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
+        dev = torch.device("cuda", 0)
+        pipe = R.TokenizerPipeline("bpe", "gpt2_synth")
+        db = R.to_device(batch, dev)
+        pg = PeerGather(db.n_rows, db.n_chars + db.n_elems, dev)
+        b, e, ids = pg.run(pipe, db)
+        torch.cuda.synchronize()
+        assert int(pg.n.item()) == len(exp[2])
+        assert np.array_equal(b.cpu().numpy(), exp[0]) and np.array_equal(e.cpu().numpy(), exp[1])
+        assert np.array_equal(ids[: len(exp[2])].cpu().numpy(), exp[2])
+    finally:
+        if own:
+            dist.destroy_process_group()

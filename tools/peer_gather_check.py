@@ -1,0 +1,68 @@
+"""2..8-GPU check of the fused emit + all-gatherv over peer memory (sharded.PeerGather) against the NCCL slot all-gather:
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29544 tools/peer_gather_check.py
+Every rank tokenises its own C1 shard; both exchanges must give identical (begins, ends, ids-in-rows) on every rank."""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import cases
+from openvino_tokenizers_b200 import runtime as R
+from openvino_tokenizers_b200.sharded import PeerGather, allgather_ragged_slots
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+pipe = R.TokenizerPipeline("bpe", "gpt2_synth", device=local)
+batch = cases.random_ascii_batch(rows, 512, 1234 + rank)
+db = R.to_device(batch, dev)
+cap = db.n_chars
+pg = PeerGather(rows, cap, dev)
+o = pipe.run_device(db)
+ref = allgather_ragged_slots(o["ids"][:cap], o["begins"], o["ends"])
+b, e, ids = pg.run(pipe, db)
+torch.cuda.synchronize()
+ok = bool(torch.equal(b, ref[0]) and torch.equal(e, ref[1]))
+rb, re_, rids = (x.cpu().numpy() for x in ref)
+gb, ge, gids = b.cpu().numpy(), e.cpu().numpy(), ids.cpu().numpy()
+for r in np.r_[0:32, rows * world - 32:rows * world, rows - 3:rows + 3]:
+    ok &= bool(np.array_equal(gids[gb[r]:ge[r]], rids[rb[r]:re_[r]]))
+tot = 0
+for k in range(world):      # every slot: all valid ids equal
+    n = int(ge[(k + 1) * rows - 1] - k * cap)
+    ok &= bool(np.array_equal(gids[k * cap:k * cap + n], rids[k * cap:k * cap + n]))
+    tot += n
+
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) / n], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) * 1e3
+
+
+g = torch.empty(world * cap, dtype=torch.int32, device=dev)
+t_nccl = timed(lambda: allgather_ragged_slots(pipe.run_device(db)["ids"][:cap], o["begins"], o["ends"], g))
+t_peer = timed(lambda: pg.run(pipe, db))
+t_local = timed(lambda: pipe.run_device(db))
+flags = torch.tensor([int(ok)], device=dev)
+dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+if rank == 0:
+    mb = rows * 512 * world / 1e6
+    print(f"peer gather == nccl slot gather on every rank: {bool(flags.item())}; ids {tot}; ms/step local-only {t_local:.3f}, "
+          f"tokenise+NCCL all-gather {t_nccl:.3f} ({mb / t_nccl * 1e3 / 1e3:.1f} GB/s text), tokenise+peer-store emit {t_peer:.3f} ({mb / t_peer:.1f} GB/s text)")
+dist.destroy_process_group()
