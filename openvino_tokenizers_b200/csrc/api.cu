@@ -315,6 +315,11 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         const int fast_per_sm = fast_ctas_env > 0 ? fast_ctas_env : (int)std::max<size_t>(1, std::min<size_t>(narrow ? 5 : 4, (227 * 1024) / (fsm + 1024)));
         const int fast_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * fast_per_sm);
         RowParams Pk = c.P;
+        const bool peer_fast = c.peers != nullptr;        // sharded: the fast kernel stores into every rank's slot, no compaction follows
+        if (peer_fast) {
+            Pk.peer.world = c.peers->world; Pk.peer.rank = c.peers->rank; Pk.peer.slot_capacity = c.peers->slot_capacity; Pk.peer.rows_per_rank = c.peers->rows_per_rank;
+            for (int p = 0; p < c.peers->world; ++p) { Pk.peer.ids[p] = c.peers->ids[p]; Pk.peer.begins[p] = c.peers->begins[p]; Pk.peer.ends[p] = c.peers->ends[p]; }
+        }
         int32_t* redo = c.row_cap;
         void* args[] = {&Pk, &redo};
         CU(cudaLaunchKernel(fn, dim3((unsigned)fast_blocks), dim3(BLOCK_THREADS), args, fsm, st));
@@ -323,6 +328,16 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         P2.row_list = c.row_cap;
         rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(P2);
         owner->launches += 2;
+        if (peer_fast) {
+            GiantParams G{c.P.giants, c.P.status, c.P.giants_cap, c.P.chars, call.bpe->view(), call.bpe->suffix.p, c.P.suffix_len,
+                          c.P.row_base, c.P.row_cnt, c.P.tmp_a, c.pool, (unsigned long long)c.pool_bytes, c.pool_used, c.P.status};
+            giant_bpe_kernel<<<std::max(1, owner->sm_count), 64, 0, st>>>(G);
+            peer_redo_rows_kernel<<<owner->sm_count, 256, 0, st>>>(c.P.tmp_a, c.P.row_base, c.P.row_ext, c.row_cap, Pk.peer, c.P.status);
+            publish_total_kernel<<<1, 1, 0, st>>>(c.P.status, c.total_dev);
+            owner->launches += 3;
+            CU(cudaGetLastError());
+            return B200TOK_OK;
+        }
     } else if (call.op == OP_SPECIAL) {
         special_split_kernel<<<(int)std::min<int64_t>((B + 7) / 8, (int64_t)owner->sm_count * 8), 256, 0, st>>>(c.P, call.special->view());
         if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }

@@ -36,6 +36,12 @@ enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
 
 struct GiantItem { int32_t row, begin, end, slot; };
 
+// Result buffers of every rank, mapped into this device (sharded output); world == 0: not sharded.
+struct PeerOut {
+    int32_t* ids[8]; int32_t* begins[8]; int32_t* ends[8];
+    int32_t world, rank; int64_t slot_capacity, rows_per_rank;
+};
+
 struct RowParams {
     // input ragged strings (device)
     const int32_t* rb; const int32_t* re; int32_t n_rows;
@@ -66,6 +72,9 @@ struct RowParams {
     int32_t direct_base; int32_t direct_byte0; int32_t direct_elem0; int32_t direct_extra;
     // list mode: process rows row_list[0 .. status[ST_NREDO]) (rows the fast kernel handed back) instead of [0, n_rows)
     const int32_t* row_list;
+    // sharded fast path: the emit step stores ids (and row extents) straight into every rank's buffers, rows stay at their
+    // worst-case positions inside this rank's slot (a ragged tensor may have gaps), so no scan / compaction pass follows
+    PeerOut peer;
 };
 
 struct __align__(16) WarpSmem {
@@ -1059,10 +1068,6 @@ __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, 
 
 // Emit fused with the all-gatherv: every row is copied once from its worst-case slot and stored into the result
 // buffers of all ranks over NVLink peer memory; row offsets are written shifted into this rank's slot.
-struct PeerOut {
-    int32_t* ids[8]; int32_t* begins[8]; int32_t* ends[8];
-    int32_t world, rank; int64_t slot_capacity, rows_per_rank;
-};
 __global__ void compact_rows_peer_kernel(const int32_t* tmp_a, const int32_t* row_base, const int32_t* row_ext, const uint8_t* row_flag,
                                          const int32_t* out_begin, const int32_t* row_cnt, int32_t n_rows, const PeerOut Q, int32_t* status,
                                          int64_t* total_out) {
@@ -1102,5 +1107,36 @@ __global__ void compact_rows_peer_kernel(const int32_t* tmp_a, const int32_t* ro
         }
     }
 }
+
+
+// Sharded fast path: rows that the fast kernel handed back were finished by the generic kernels in the local worst-case buffer;
+// copy them (filtering the holes of giant pieces) to the same positions of every rank's slot and publish their extents.
+__global__ void peer_redo_rows_kernel(const int32_t* tmp_a, const int32_t* row_base, const int32_t* row_ext, const int32_t* row_list,
+                                      const PeerOut Q, int32_t* status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n = status[ST_NREDO];
+    const int64_t slot = (int64_t)Q.rank * Q.slot_capacity;
+    for (int i = warp; i < n; i += nwarps) {
+        const int r = row_list[i];
+        const int64_t src = row_base[r];
+        const int ext = row_ext[r];
+        int64_t d = slot + src;
+        for (int t0 = 0; t0 < ext; t0 += 32) {
+            const int t = t0 + lane;
+            const int v = t < ext ? tmp_a[src + t] : -1;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, v >= 0);
+            if (v >= 0) { const int64_t o = d + __popc(m & ((1u << lane) - 1u)); for (int p = 0; p < Q.world; ++p) Q.ids[p][o] = v; }
+            d += __popc(m);
+        }
+        const int cnt = (int)(d - slot - src);
+        if (lane < Q.world) {
+            Q.begins[lane][(int64_t)Q.rank * Q.rows_per_rank + r] = (int32_t)(slot + src);
+            Q.ends[lane][(int64_t)Q.rank * Q.rows_per_rank + r] = (int32_t)(slot + src + cnt);
+        }
+        if (lane == 0) atomicAdd(&status[ST_TOTAL], cnt);
+    }
+}
+__global__ void publish_total_kernel(const int32_t* status, int64_t* total_out) { if (total_out) *total_out = status[ST_TOTAL]; }
 
 }  // namespace b200tok

@@ -447,7 +447,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                 if (base + emitted + send > P.tmp_cap) {
                     if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
                 } else {
-                    int32_t* outp = P.tmp_a + base + emitted;
+                    const int nP = P.peer.world;                  // > 0: sharded output, store into every rank's slot
+                    const int64_t o0 = (nP ? (int64_t)P.peer.rank * P.peer.slot_capacity : 0) + base + emitted;
+                    int32_t* outp = P.tmp_a + o0;
                     int n_out = 0;
                     for (int w = lane; w - lane < send; w += 128) {
                         int32_t tok[4];
@@ -456,10 +458,21 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                         for (int u = 0; u < 4; ++u) tok[u] = ((w + 32 * u) < send && S.ids[w + 32 * u] != S.kDead) ? (int32_t)S.ids[w + 32 * u] : -1;
 #pragma unroll
                         for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
+                        if (!nP) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
-                            n_out += __popc(m[u]);
+                            for (int u = 0; u < 4; ++u) {
+                                if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
+                                n_out += __popc(m[u]);
+                            }
+                        } else {
+                            int idx[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { idx[u] = n_out + __popc(m[u] & ltm); n_out += __popc(m[u]); }
+                            for (int p = 0; p < nP; ++p) {
+                                int32_t* dp = P.peer.ids[p] + o0;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) if (tok[u] >= 0) dp[idx[u]] = tok[u];
+                            }
                         }
                     }
                     emitted += n_out;
@@ -471,6 +484,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
         if (lane == 0) {
             if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
             else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = 0; }
+        }
+        if (P.peer.world && !redo) {                       // sharded: publish the row's extent to every rank
+            const int64_t o0 = (int64_t)P.peer.rank * P.peer.slot_capacity + base;
+            if (lane < P.peer.world) {
+                P.peer.begins[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)o0;
+                P.peer.ends[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)(o0 + emitted);
+            }
+            if (lane == 0) atomicAdd(&P.status[ST_TOTAL], emitted);
         }
     }
 }
