@@ -325,8 +325,10 @@ def main():
         if mode == "peer":
             try:
                 from openvino_tokenizers_b200.sharded import PeerGather
-                pg = PeerGather(db.n_rows, db.n_chars, dev)
-                exchange = "row shards; emit fused with the all-gatherv: the compaction kernel stores id rows into every rank's buffers over NVLink peer memory"
+                wire16 = os.environ.get("B200TOK_WIRE16", "auto")
+                wire16 = (world >= 4 and len(pipe.assets.vocab) < 0xFFFF) if wire16 == "auto" else wire16 == "1"
+                pg = PeerGather(db.n_rows, db.n_chars, dev, wire16=wire16)
+                exchange = "row shards; emit fused with the all-gatherv: the tokenizer kernel stores id rows into every rank's buffers over NVLink peer memory" + (" (16-bit ids on the wire, widened locally)" if wire16 else "") + (" (NVLS multicast stores)" if pg.multicast else "")
             except Exception as ex:      # symmetric memory unavailable on this box: fall back to the NCCL exchange (still GPU-only)
                 print(f"[bench] peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL", file=sys.stderr)
         if pg is None:

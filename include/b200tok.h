@@ -190,10 +190,22 @@ typedef struct {
     int32_t* ends[B200TOK_MAX_PEERS];
     int64_t slot_capacity;
     int64_t rows_per_rank;
+    /* optional 16-bit wire format (every id < 65 536): ids travel over NVLink as u16 into the peers' staging buffers ids16[p]
+     * (each [world * slot_capacity]); after the cross-rank barrier every rank widens its own staging copy into ids[rank] with
+     * b200tok_peer_expand_run.  Halves the NVLink bytes; pays one local pass.  ids[p] for p != rank is then unused.     */
+    int wire16;
+    uint16_t* ids16[B200TOK_MAX_PEERS];
+    /* optional NVLS multicast mappings of the same buffers (NULL if unavailable): one multimem.st through the NVSwitch reaches every
+     * rank's copy, so each GPU sends its rows once instead of world - 1 times.  Used with the 32-bit wire format.               */
+    int32_t* ids_mc;
+    int32_t* begins_mc;
+    int32_t* ends_mc;
 } b200tok_peer_out;
 /* n_ids_device (optional, device): this rank's id count.  Fully asynchronous on `cuda_stream`. */
 B200TOK_API int b200tok_split_bpe_run_sharded(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
                                               const b200tok_peer_out* peers, int64_t* n_ids_device, void* cuda_stream);
+/* wire16 only: after the barrier, widen this rank's staging copy (all world * rows_per_rank rows) into peers->ids[rank]. */
+B200TOK_API int b200tok_peer_expand_run(int device, const b200tok_peer_out* peers, void* cuda_stream);
 
 /* ---- WordpieceTokenizer --------------------------------------------------------------------
  * inputs [5..7] vocab, [8] unk_token_id; attributes suffix_indicator / max_bytes_per_word

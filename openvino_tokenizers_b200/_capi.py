@@ -86,7 +86,8 @@ class PostDesc(C.Structure):
 
 class PeerOut(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("ids", C.c_void_p * 8), ("begins", C.c_void_p * 8), ("ends", C.c_void_p * 8),
-                ("slot_capacity", C.c_int64), ("rows_per_rank", C.c_int64)]
+                ("slot_capacity", C.c_int64), ("rows_per_rank", C.c_int64), ("wire16", C.c_int), ("ids16", C.c_void_p * 8),
+                ("ids_mc", C.c_void_p), ("begins_mc", C.c_void_p), ("ends_mc", C.c_void_p)]
 
 
 def make_strings(triple, keep: list) -> Strings:
@@ -147,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "b200tok_version", "b200tok_last_error", "b200tok_device_count", "b200tok_destroy", "b200tok_launch_count",
     "b200tok_set_timing", "b200tok_last_kernel_ms",
     "b200tok_regexsplit_create", "b200tok_regexsplit_run", "b200tok_specialsplit_create", "b200tok_specialsplit_run",
-    "b200tok_bpe_create", "b200tok_bpe_run", "b200tok_split_bpe_run", "b200tok_split_bpe_run_sharded",
+    "b200tok_bpe_create", "b200tok_bpe_run", "b200tok_split_bpe_run", "b200tok_split_bpe_run_sharded", "b200tok_peer_expand_run",
     "b200tok_wordpiece_create", "b200tok_wordpiece_run", "b200tok_split_wordpiece_run",
     "b200tok_vocabenc_create", "b200tok_vocabenc_run",
     "b200tok_vocabdec_create", "b200tok_vocabdec_run", "b200tok_vocabdec_max_chars",

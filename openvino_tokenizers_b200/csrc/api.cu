@@ -318,7 +318,10 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         const bool peer_fast = c.peers != nullptr;        // sharded: the fast kernel stores into every rank's slot, no compaction follows
         if (peer_fast) {
             Pk.peer.world = c.peers->world; Pk.peer.rank = c.peers->rank; Pk.peer.slot_capacity = c.peers->slot_capacity; Pk.peer.rows_per_rank = c.peers->rows_per_rank;
-            for (int p = 0; p < c.peers->world; ++p) { Pk.peer.ids[p] = c.peers->ids[p]; Pk.peer.begins[p] = c.peers->begins[p]; Pk.peer.ends[p] = c.peers->ends[p]; }
+            Pk.peer.wire16 = c.peers->wire16;
+            Pk.peer.ids_mc = c.peers->ids_mc; Pk.peer.begins_mc = c.peers->ids_mc ? c.peers->begins_mc : nullptr; Pk.peer.ends_mc = c.peers->ids_mc ? c.peers->ends_mc : nullptr;
+            if (!Pk.peer.begins_mc || !Pk.peer.ends_mc) { Pk.peer.begins_mc = nullptr; Pk.peer.ends_mc = nullptr; }
+            for (int p = 0; p < c.peers->world; ++p) { Pk.peer.ids[p] = c.peers->ids[p]; Pk.peer.ids16[p] = c.peers->ids16[p]; Pk.peer.begins[p] = c.peers->begins[p]; Pk.peer.ends[p] = c.peers->ends[p]; }
         }
         int32_t* redo = c.row_cap;
         void* args[] = {&Pk, &redo};
@@ -371,7 +374,8 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
     } else if (c.peers) {
         PeerOut Q{};
         Q.world = c.peers->world; Q.rank = c.peers->rank; Q.slot_capacity = c.peers->slot_capacity; Q.rows_per_rank = c.peers->rows_per_rank;
-        for (int p = 0; p < Q.world; ++p) { Q.ids[p] = c.peers->ids[p]; Q.begins[p] = c.peers->begins[p]; Q.ends[p] = c.peers->ends[p]; }
+        Q.wire16 = c.peers->wire16;
+        for (int p = 0; p < Q.world; ++p) { Q.ids[p] = c.peers->ids[p]; Q.ids16[p] = c.peers->ids16[p]; Q.begins[p] = c.peers->begins[p]; Q.ends[p] = c.peers->ends[p]; }
         compact_rows_peer_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, c.P.row_cnt, (int32_t)B, Q,
                                                                        c.P.status, c.total_dev);
         ++owner->launches;
@@ -916,7 +920,8 @@ B200TOK_API int b200tok_split_bpe_run_sharded(b200tok_handle split, b200tok_hand
         peers->slot_capacity < in->n_chars + in->n_elems * (int64_t)b->h.end_suffix.size())
         return fail(B200TOK_E_INVALID, "bad peer layout (world 1..8, rows_per_rank >= rows, slot_capacity >= worst-case ids of the shard)");
     for (int p = 0; p < peers->world; ++p)
-        if (!peers->ids[p] || !peers->begins[p] || !peers->ends[p]) return fail(B200TOK_E_INVALID, "missing peer buffer %d", p);
+        if ((peers->wire16 ? !peers->ids16[p] : !peers->ids[p]) || !peers->begins[p] || !peers->ends[p]) return fail(B200TOK_E_INVALID, "missing peer buffer %d", p);
+    if (peers->wire16 && b->h.max_id >= 0xFFFF) return fail(B200TOK_E_INVALID, "the 16-bit wire format needs every token id < 65535");
     RowCall call;
     call.op = OP_BPE;
     call.split = s;
@@ -925,6 +930,21 @@ B200TOK_API int b200tok_split_bpe_run_sharded(b200tok_handle split, b200tok_hand
     b200tok_ragged_ids out{nullptr, nullptr, nullptr, peers->slot_capacity, 0, n_ids_device, B200TOK_MEM_DEVICE};
     (void)dummy_total;
     return run_rows(b, call, in, &out, nullptr, stream, peers);
+}
+
+B200TOK_API int b200tok_peer_expand_run(int device, const b200tok_peer_out* peers, void* stream) {
+    if (!peers || !peers->wire16 || peers->world < 1 || peers->world > B200TOK_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
+        return fail(B200TOK_E_INVALID, "expected a 16-bit-wire peer layout");
+    const int r = peers->rank;
+    if (!peers->ids16[r] || !peers->ids[r] || !peers->begins[r] || !peers->ends[r]) return fail(B200TOK_E_INVALID, "missing local buffers");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B200TOK_E_CUDA, "no such CUDA device %d (there is no CPU fallback)", device);
+    DeviceGuard g(device);
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+    peer_expand_kernel<<<sm * 8, 256, 0, (cudaStream_t)stream>>>(peers->ids16[r], peers->begins[r], peers->ends[r], (int64_t)peers->world * peers->rows_per_rank, peers->ids[r]);
+    CU(cudaGetLastError());
+    return B200TOK_OK;
 }
 
 // ---- WordPiece ----

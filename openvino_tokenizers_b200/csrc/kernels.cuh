@@ -40,7 +40,20 @@ struct GiantItem { int32_t row, begin, end, slot; };
 struct PeerOut {
     int32_t* ids[8]; int32_t* begins[8]; int32_t* ends[8];
     int32_t world, rank; int64_t slot_capacity, rows_per_rank;
+    uint16_t* ids16[8]; int32_t wire16;      // 16-bit wire format: ids go to the peers' u16 staging buffers, widened locally afterwards
+    int32_t* ids_mc; int32_t* begins_mc; int32_t* ends_mc;   // NVLS multicast mappings (one store reaches every rank), or null
 };
+// One store through the NVSwitch multicast address: written into every rank's copy of the buffer.
+__device__ __forceinline__ void mc_store(int32_t* p, int32_t v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p), "f"(__int_as_float(v)) : "memory");
+}
+__device__ __forceinline__ void mc_store4(int32_t* p, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+__device__ __forceinline__ void peer_store(const PeerOut& Q, int p, int64_t o, int32_t v) {
+    if (Q.wire16) Q.ids16[p][o] = (uint16_t)v; else Q.ids[p][o] = v;
+}
 
 struct RowParams {
     // input ragged strings (device)
@@ -1090,9 +1103,8 @@ __global__ void compact_rows_peer_kernel(const int32_t* tmp_a, const int32_t* ro
 #pragma unroll
                 for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < ext) ? __ldcs(tmp_a + src + t + 32 * u) : 0;
                 for (int p = 0; p < Q.world; ++p) {
-                    int32_t* dp = Q.ids[p] + dst;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (t + 32 * u < ext) dp[t + 32 * u] = v[u];
+                    for (int u = 0; u < 4; ++u) if (t + 32 * u < ext) peer_store(Q, p, dst + t + 32 * u, v[u]);
                 }
             }
         } else {      // rows with holes (giant pieces): filter while copying
@@ -1101,7 +1113,7 @@ __global__ void compact_rows_peer_kernel(const int32_t* tmp_a, const int32_t* ro
                 const int t = t0 + lane;
                 const int v = t < ext ? tmp_a[src + t] : -1;
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, v >= 0);
-                if (v >= 0) { const int64_t o = d + __popc(m & ((1u << lane) - 1u)); for (int p = 0; p < Q.world; ++p) Q.ids[p][o] = v; }
+                if (v >= 0) { const int64_t o = d + __popc(m & ((1u << lane) - 1u)); for (int p = 0; p < Q.world; ++p) peer_store(Q, p, o, v); }
                 d += __popc(m);
             }
         }
@@ -1126,7 +1138,7 @@ __global__ void peer_redo_rows_kernel(const int32_t* tmp_a, const int32_t* row_b
             const int t = t0 + lane;
             const int v = t < ext ? tmp_a[src + t] : -1;
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, v >= 0);
-            if (v >= 0) { const int64_t o = d + __popc(m & ((1u << lane) - 1u)); for (int p = 0; p < Q.world; ++p) Q.ids[p][o] = v; }
+            if (v >= 0) { const int64_t o = d + __popc(m & ((1u << lane) - 1u)); for (int p = 0; p < Q.world; ++p) peer_store(Q, p, o, v); }
             d += __popc(m);
         }
         const int cnt = (int)(d - slot - src);
@@ -1135,6 +1147,21 @@ __global__ void peer_redo_rows_kernel(const int32_t* tmp_a, const int32_t* row_b
             Q.ends[lane][(int64_t)Q.rank * Q.rows_per_rank + r] = (int32_t)(slot + src + cnt);
         }
         if (lane == 0) atomicAdd(&status[ST_TOTAL], cnt);
+    }
+}
+// 16-bit wire format: widen the rows of every slot of this rank's staging copy into its final i32 buffer (warp per row).
+__global__ void peer_expand_kernel(const uint16_t* staging, const int32_t* begins, const int32_t* ends, int64_t n_rows, int32_t* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += nwarps) {
+        const int64_t b = begins[r], e = ends[r];
+        for (int64_t t = b + lane; t - lane < e; t += 128) {
+            uint16_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < e) ? staging[t + 32 * u] : (uint16_t)0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (t + 32 * u < e) out[t + 32 * u] = (int32_t)v[u];
+        }
     }
 }
 __global__ void publish_total_kernel(const int32_t* status, int64_t* total_out) { if (total_out) *total_out = status[ST_TOTAL]; }

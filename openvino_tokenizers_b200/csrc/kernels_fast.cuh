@@ -28,7 +28,7 @@ struct __align__(16) FastSmem {
     uint32_t segbits[NWORDS], actbits[NWORDS];
     uint32_t m[11][kMStride];                // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F NL PG
     IdT ids[WIN];                            // symbol per position; kDead = merged away
-    uint32_t key[WIN];
+    alignas(16) uint32_t key[WIN + 4];       // merge keys; after the merges: staging of the window's compacted ids for wide peer stores
     __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }
     __device__ __forceinline__ uint16_t* act() { return reinterpret_cast<uint16_t*>(&m[0][0]); }   // merge queue; the masks are consumed by then
     static constexpr IdT kDead = (IdT)-1;
@@ -465,15 +465,45 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                                 n_out += __popc(m[u]);
                             }
                         } else {
-                            int idx[4];
+                            // sharded: compact into shared memory first (same 16-byte misalignment as the destination), stored wide below
+                            const int shift = P.peer.wire16 ? (int)(o0 & 7) : (int)(o0 & 3);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) { idx[u] = n_out + __popc(m[u] & ltm); n_out += __popc(m[u]); }
-                            for (int p = 0; p < nP; ++p) {
-                                int32_t* dp = P.peer.ids[p] + o0;
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) if (tok[u] >= 0) dp[idx[u]] = tok[u];
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = shift + n_out + __popc(m[u] & ltm);
+                                if (tok[u] >= 0) { if (P.peer.wire16) reinterpret_cast<uint16_t*>(S.key)[i] = (uint16_t)tok[u]; else reinterpret_cast<int32_t*>(S.key)[i] = tok[u]; }
+                                n_out += __popc(m[u]);
                             }
                         }
+                    }
+                    if (nP) {
+                        __syncwarp();
+                        // 16-byte chunks of the staged ids go to every rank with one vector store each (remote stores are
+                        // transaction-bound: few wide stores instead of many 2-4 byte ones); ragged head / tail element-wise
+                        const int per = P.peer.wire16 ? 8 : 4;
+                        const int shift = (int)(o0 & (per - 1)), total = shift + n_out;
+                        const int64_t o_al = o0 - shift;                          // 16-byte aligned destination element
+                        const uint4* sv = reinterpret_cast<const uint4*>(S.key);
+                        for (int c = lane; c * per < total; c += 32) {
+                            const int lo = c * per, hi = lo + per;
+                            if (P.peer.ids_mc && !P.peer.wire16) {           // NVLS multicast: one store reaches every rank
+                                int32_t* mc = P.peer.ids_mc + o_al;
+                                if (lo >= shift && hi <= total) mc_store4(mc + lo, sv[c]);
+                                else for (int i = lo < shift ? shift : lo; i < (hi < total ? hi : total); ++i) mc_store(mc + i, reinterpret_cast<const int32_t*>(S.key)[i]);
+                            } else if (lo >= shift && hi <= total) {
+                                const uint4 v = sv[c];
+                                for (int p = 0; p < nP; ++p) {
+                                    uint4* dp = P.peer.wire16 ? reinterpret_cast<uint4*>(P.peer.ids16[p] + o_al) : reinterpret_cast<uint4*>(P.peer.ids[p] + o_al);
+                                    dp[c] = v;
+                                }
+                            } else {
+                                for (int i = lo < shift ? shift : lo; i < (hi < total ? hi : total); ++i)
+                                    for (int p = 0; p < nP; ++p) {
+                                        if (P.peer.wire16) P.peer.ids16[p][o_al + i] = reinterpret_cast<const uint16_t*>(S.key)[i];
+                                        else P.peer.ids[p][o_al + i] = reinterpret_cast<const int32_t*>(S.key)[i];
+                                    }
+                            }
+                        }
+                        __syncwarp();
                     }
                     emitted += n_out;
                 }
@@ -487,7 +517,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
         }
         if (P.peer.world && !redo) {                       // sharded: publish the row's extent to every rank
             const int64_t o0 = (int64_t)P.peer.rank * P.peer.slot_capacity + base;
-            if (lane < P.peer.world) {
+            if (P.peer.begins_mc) {
+                if (lane == 0) {
+                    mc_store(P.peer.begins_mc + (int64_t)P.peer.rank * P.peer.rows_per_rank + row, (int32_t)o0);
+                    mc_store(P.peer.ends_mc + (int64_t)P.peer.rank * P.peer.rows_per_rank + row, (int32_t)(o0 + emitted));
+                }
+            } else if (lane < P.peer.world) {
                 P.peer.begins[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)o0;
                 P.peer.ends[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)(o0 + emitted);
             }

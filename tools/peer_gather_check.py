@@ -25,7 +25,8 @@ pipe = R.TokenizerPipeline("bpe", "gpt2_synth", device=local)
 batch = cases.random_ascii_batch(rows, 512, 1234 + rank)
 db = R.to_device(batch, dev)
 cap = db.n_chars
-pg = PeerGather(rows, cap, dev)
+wire16 = os.environ.get("B200TOK_WIRE16", "0") == "1"
+pg = PeerGather(rows, cap, dev, wire16=wire16, multicast=os.environ.get("B200TOK_MULTICAST", "0") == "1")
 o = pipe.run_device(db)
 ref = allgather_ragged_slots(o["ids"][:cap], o["begins"], o["ends"])
 b, e, ids = pg.run(pipe, db)
@@ -64,6 +65,6 @@ flags = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flags, op=dist.ReduceOp.MIN)
 if rank == 0:
     mb = rows * 512 * world / 1e6
-    print(f"peer gather == nccl slot gather on every rank: {bool(flags.item())}; ids {tot}; ms/step local-only {t_local:.3f}, "
+    print(f"[wire16={wire16} multicast={pg.multicast}] peer gather == nccl slot gather on every rank: {bool(flags.item())}; ids {tot}; ms/step local-only {t_local:.3f}, "
           f"tokenise+NCCL all-gather {t_nccl:.3f} ({mb / t_nccl * 1e3 / 1e3:.1f} GB/s text), tokenise+peer-store emit {t_peer:.3f} ({mb / t_peer:.1f} GB/s text)")
 dist.destroy_process_group()
