@@ -56,10 +56,24 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
     // (the class byte of position q lives at byte q + LBK, the id of position p at byte sizeof(IdT) * p >= p + LBK for p >= LBK).
     uint8_t* const KC = reinterpret_cast<uint8_t*>(S.ids) + LBK;
     if (!ascii) {
-        for (int w = lane - lb; w < nload; w += 32) {            // characters: decoded once, by the lane of their first byte
-            const uint8_t b = B[w];
-            if (b < 0x80) KC[w] = ascii_smem[b];
-            else if (!is_cont_byte(b) || w == -lb) KC[w] = char_class(B, w, end_rel, T);
+        // characters are decoded once: ASCII bytes take their class from the table right away; the first bytes of multi-byte
+        // characters are first gathered into a dense list (in the not-yet-used key array) so that the UTF-8 decode + two-stage
+        // class lookup then runs with every lane busy instead of the few lanes that happen to sit on a lead byte
+        uint16_t* const leads = reinterpret_cast<uint16_t*>(S.key);
+        int n_leads = 0;
+        for (int w0 = -lb; w0 < nload; w0 += 32) {
+            const int w = w0 + lane;
+            const uint8_t b = w < nload ? B[w] : 0;
+            if (w < nload && b < 0x80) KC[w] = ascii_smem[b];
+            const bool lead = w < nload && b >= 0x80 && (!is_cont_byte(b) || w == -lb);
+            const uint32_t m = __ballot_sync(FULL, lead);
+            if (lead) leads[n_leads + __popc(m & lt)] = (uint16_t)(w + LBK);
+            n_leads += __popc(m);
+        }
+        __syncwarp();
+        for (int i = lane; i < n_leads; i += 32) {
+            const int w = (int)leads[i] - LBK;
+            KC[w] = char_class(B, w, end_rel, T);
         }
         __syncwarp();
         for (int w = lane - lb; w < nload; w += 32) {            // continuation bytes copy their owner
@@ -130,8 +144,8 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                         bool pg = false;                                           // letter after a multi-byte "other" char at which a match starts
                         // (the previous byte carries its character's class: only a multi-byte OTHER char needs the look-back)
                         if ((g[u] & V7_L) && !(g[u] & V7_CONT) && w > -lb && (KC[w - 1] & (C_CONT | C_L | C_N | C_S)) == C_CONT) {
-                            int j = w - 1;
-                            while (j > -lb && is_cont_byte(B[j])) --j;
+                            int j = w - 1;                       // first byte of that character: at most three bytes back
+                            if (j > -lb && is_cont_byte(B[j])) { --j; if (j > -lb && is_cont_byte(B[j])) { --j; if (j > -lb && is_cont_byte(B[j])) --j; } }
                             if (!(KC[j] & (C_L | C_N | C_S)))
                                 pg = j == -lb || (B[j - 1] != 0x20 && (KC[j - 1] & (C_L | C_N | C_S)));
                         }
