@@ -687,13 +687,62 @@ __device__ __forceinline__ uint32_t v7_below(int limit, int base) {
 
 // WordPiece for all kept segments (words) of a window: one lane per word, longest-match trie walks.
 __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowParams& P, int lane, int ns, bool whole) {
+    // The word loop of src/wordpiece_tokenizer.cpp:96-130 (tok_core.cuh wordpiece_word) flattened into a per-lane state machine
+    // driven by a warp work queue: every iteration performs ONE trie step for whatever word a lane holds, and a lane that
+    // finishes its word takes the next one — words of different lengths no longer idle the rest of the warp.
     auto& bp = S.u.bp;
-    for (int j = lane; j < ns; j += 32) {
-        const uint16_t sg = S.seg[j];
-        const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
-        int c = 0;
-        if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) c = wordpiece_word(P.wp, S.B(), s, e, P.unk_id, bp.ids + s);
-        for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
+    const uint8_t* B = S.B();
+    const WordpieceTables& T = P.wp;
+    const uint32_t lt = (1u << lane) - 1u;
+    int head = 0, s = 0, e = 0, i = 0, n = 0, best = 0;
+    int32_t node = -1, found = -1;
+    bool have = false, sub = false;
+    while (head < ns || __any_sync(0xFFFFFFFFu, have)) {
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
+        if (!have) {
+            const int j = head + __popc(need & lt);
+            if (j < ns) {
+                const uint16_t sg = S.seg[j];
+                s = sg & POS_MASK; e = S.seg[j + 1] & POS_MASK;
+                if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
+                    for (int t = s; t < e; ++t) bp.ids[t] = -1;
+                } else if (e - s > T.max_bytes || e <= s) {                  // :100-103 (and the zero-length word, see tok_core.cuh)
+                    bp.ids[s] = P.unk_id;
+                    for (int t = s + 1; t < e; ++t) bp.ids[t] = -1;
+                } else {
+                    have = true; sub = false; n = 0; i = s; best = s; found = -1;
+                    node = T.root.root_child[B[s]];
+                }
+            }
+        }
+        head += __popc(need);
+        if (have) {
+            if (node >= 0) {                                              // one step of the longest-match walk
+                ++i;
+                const RankNode& nd = (sub ? T.sub.nodes : T.root.nodes)[node];
+                const int32_t v = nd.value;
+                if (v != -1) { found = v; best = i; }
+                if (i >= e) node = -1;
+                else {
+                    const uint32_t ch = B[i], wd = ch >> 5, bit = ch & 31u;
+                    const uint32_t bw = nd.bits[wd];
+                    node = ((bw >> bit) & 1u) ? nd.base + (int32_t)nd.cum[wd] + __popc(bw & ((1u << bit) - 1u)) : -1;
+                }
+            }
+            if (node < 0) {                                               // the walk ended: a token, or the whole word is unknown
+                bool done = false;
+                if (found < 0) { bp.ids[s] = P.unk_id; n = 1; done = true; }       // :107-112, :116-126
+                else {
+                    bp.ids[s + n++] = found;
+                    if (best >= e) done = true;
+                    else { sub = true; i = best; found = -1; node = T.sub.root_child[B[best]]; }
+                }
+                if (done) {
+                    for (int t = s + n; t < e; ++t) bp.ids[t] = -1;
+                    have = false;
+                }
+            }
+        }
     }
 }
 
