@@ -697,6 +697,11 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
     int head = 0, s = 0, e = 0, i = 0, n = 0, best = 0;
     int32_t node = -1, found = -1;
     bool have = false, sub = false;
+    {   // every slot starts dead (position-parallel); the lanes then write tokens only
+        const int send = S.seg[ns] & POS_MASK;
+        for (int w = lane; w < send; w += 32) bp.ids[w] = -1;
+        __syncwarp();
+    }
     while (head < ns || __any_sync(0xFFFFFFFFu, have)) {
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
         if (!have) {
@@ -705,10 +710,9 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
                 const uint16_t sg = S.seg[j];
                 s = sg & POS_MASK; e = S.seg[j + 1] & POS_MASK;
                 if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
-                    for (int t = s; t < e; ++t) bp.ids[t] = -1;
+                    // dropped segment: its slots stay dead
                 } else if (e - s > T.max_bytes || e <= s) {                  // :100-103 (and the zero-length word, see tok_core.cuh)
                     bp.ids[s] = P.unk_id;
-                    for (int t = s + 1; t < e; ++t) bp.ids[t] = -1;
                 } else {
                     have = true; sub = false; n = 0; i = s; best = s; found = -1;
                     node = T.root.root_child[B[s]];
@@ -731,16 +735,16 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
             }
             if (node < 0) {                                               // the walk ended: a token, or the whole word is unknown
                 bool done = false;
-                if (found < 0) { bp.ids[s] = P.unk_id; n = 1; done = true; }       // :107-112, :116-126
+                if (found < 0) {                                          // :107-112, :116-126: rewind, the word becomes one [unk]
+                    for (int t = s + 1; t < s + n; ++t) bp.ids[t] = -1;
+                    bp.ids[s] = P.unk_id; n = 1; done = true;
+                }
                 else {
                     bp.ids[s + n++] = found;
                     if (best >= e) done = true;
                     else { sub = true; i = best; found = -1; node = T.sub.root_child[B[best]]; }
                 }
-                if (done) {
-                    for (int t = s + n; t < e; ++t) bp.ids[t] = -1;
-                    have = false;
-                }
+                if (done) have = false;
             }
         }
     }
