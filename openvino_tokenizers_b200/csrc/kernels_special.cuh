@@ -11,66 +11,6 @@
 
 namespace b200tok {
 
-constexpr int kSpecialGroups = 8;
-struct SpecialTables {
-    FlatTrie trie[kSpecialGroups];     // value = position of the token inside its group (smaller = earlier alternative)
-    uint8_t strip_left[kSpecialGroups], strip_right[kSpecialGroups];
-    int32_t n_groups;
-    uint32_t first[8];                 // bytes at which a match can start
-    int32_t ws_token;                  // a token of a strip_left group starts with whitespace: full backtracking needed
-};
-
-// Earliest alternative among the group's tokens matching at chars[q..ee); they all lie on one trie path.
-__device__ __forceinline__ bool special_token_at(const FlatTrie& t, const uint8_t* chars, int q, int ee, int& tok_end) {
-    int32_t node = t.root_child[chars[q]];
-    int32_t best = 0x7FFFFFFF;
-    int i = q;
-    while (node >= 0) {
-        ++i;
-        const int32_t v = t.value[node];
-        if (v != -1 && v < best) { best = v; tok_end = i; }
-        if (i >= ee) break;
-        node = trie_child(t, node, chars[i]);
-    }
-    return best != 0x7FFFFFFF;
-}
-
-// Length in bytes of the whitespace character starting at chars[i] (0 if it is not one).
-__device__ __forceinline__ int special_ws_len(const uint8_t* chars, int i, int ee, const ClassTables& T) {
-    const uint8_t b = chars[i];
-    if (b < 0x80) return (T.ascii[b] & C_S) ? 1 : 0;
-    if (b < 0xC2 || !(char_class(chars, i, ee, T) & C_S)) return 0;
-    return b >= 0xF0 ? 4 : b >= 0xE0 ? 3 : 2;
-}
-
-// The match starting exactly at pos, or m1 = 0.  [g0, g1) = the token (capture group), [pos, m1) = the full match.
-__device__ __forceinline__ void special_match_at(const SpecialTables& ST, const ClassTables& T, const uint8_t* chars, int pos, int ee,
-                                                 int& m1, int& g0, int& g1) {
-    m1 = 0;
-    int ws_end = -1;     // end of the whitespace run starting at pos (computed on first use)
-    for (int g = 0; g < ST.n_groups; ++g) {
-        int q = pos, te = 0;
-        bool hit = false;
-        if (ST.strip_left[g]) {
-            if (ws_end < 0) { ws_end = pos; int l; while (ws_end < ee && (l = special_ws_len(chars, ws_end, ee, T)) > 0) ws_end += l; }
-            // greedy \s*, then give back one character at a time
-            q = ws_end;
-            for (;;) {
-                if (q < ee && ((ST.first[chars[q] >> 5] >> (chars[q] & 31)) & 1u) && special_token_at(ST.trie[g], chars, q, ee, te)) { hit = true; break; }
-                if (q <= pos || !ST.ws_token) break;     // no token starts with whitespace: only the end of the run can match
-                --q;
-                while (q > pos && is_cont_byte(chars[q])) --q;
-            }
-        } else {
-            hit = special_token_at(ST.trie[g], chars, pos, ee, te);
-        }
-        if (!hit) continue;
-        g0 = q; g1 = te; m1 = te;
-        if (ST.strip_right[g]) { int l; while (m1 < ee && (l = special_ws_len(chars, m1, ee, T)) > 0) m1 += l; }
-        return;
-    }
-}
-
 __global__ void __launch_bounds__(256) special_split_kernel(const __grid_constant__ RowParams P, const __grid_constant__ SpecialTables ST) {
     const int lane = threadIdx.x & 31;
     const ClassTables T = P.cls;

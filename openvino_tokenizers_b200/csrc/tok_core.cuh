@@ -946,4 +946,86 @@ B2_HD int wordpiece_word(const WordpieceTables& T, const uint8_t* s, int b, int 
     return n;
 }
 
+// ------------------------------------------------------------------------------------------
+// SpecialTokensSplit (src/special_tokens_split.cpp:61-162): the match that starts at a given byte, for a pattern that is an
+// alternation of groups  (?:\s*)?(tok|tok|...)(?:\s*)?  of literal tokens (PCRE2: leftmost, first alternative, greedy \s* with
+// backtracking).  Used by kernels_special.cuh per position and by the host harness for the CPU-tier check against PCRE2.
+// ------------------------------------------------------------------------------------------
+constexpr int kSpecialGroups = 8;
+struct SpecialTables {
+    FlatTrie trie[kSpecialGroups];     // value = position of the token inside its group (smaller = earlier alternative)
+    uint8_t strip_left[kSpecialGroups], strip_right[kSpecialGroups];
+    int32_t n_groups;
+    uint32_t first[8];                 // bytes at which a match can start
+    int32_t ws_token;                  // a token of a strip_left group starts with whitespace: full backtracking needed
+};
+
+// Earliest alternative among the group's tokens matching at chars[q..ee); they all lie on one trie path.
+B2_HD bool special_token_at(const FlatTrie& t, const uint8_t* chars, int q, int ee, int& tok_end) {
+    int32_t node = t.root_child[chars[q]];
+    int32_t best = 0x7FFFFFFF;
+    int i = q;
+    while (node >= 0) {
+        ++i;
+        const int32_t v = t.value[node];
+        if (v != -1 && v < best) { best = v; tok_end = i; }
+        if (i >= ee) break;
+        node = trie_child(t, node, chars[i]);
+    }
+    return best != 0x7FFFFFFF;
+}
+
+// Length in bytes of the whitespace character starting at chars[i] (0 if it is not one).
+B2_HD int special_ws_len(const uint8_t* chars, int i, int ee, const ClassTables& T) {
+    const uint8_t b = chars[i];
+    if (b < 0x80) return (T.ascii[b] & C_S) ? 1 : 0;
+    if (b < 0xC2 || !(char_class(chars, i, ee, T) & C_S)) return 0;
+    return b >= 0xF0 ? 4 : b >= 0xE0 ? 3 : 2;
+}
+
+// The match starting exactly at pos, or m1 = 0.  [g0, g1) = the token (capture group), [pos, m1) = the full match.
+B2_HD void special_match_at(const SpecialTables& ST, const ClassTables& T, const uint8_t* chars, int pos, int ee,
+                                                 int& m1, int& g0, int& g1) {
+    m1 = 0;
+    int ws_end = -1;     // end of the whitespace run starting at pos (computed on first use)
+    for (int g = 0; g < ST.n_groups; ++g) {
+        int q = pos, te = 0;
+        bool hit = false;
+        if (ST.strip_left[g]) {
+            if (ws_end < 0) { ws_end = pos; int l; while (ws_end < ee && (l = special_ws_len(chars, ws_end, ee, T)) > 0) ws_end += l; }
+            // greedy \s*, then give back one character at a time
+            q = ws_end;
+            for (;;) {
+                if (q < ee && ((ST.first[chars[q] >> 5] >> (chars[q] & 31)) & 1u) && special_token_at(ST.trie[g], chars, q, ee, te)) { hit = true; break; }
+                if (q <= pos || !ST.ws_token) break;     // no token starts with whitespace: only the end of the run can match
+                --q;
+                while (q > pos && is_cont_byte(chars[q])) --q;
+            }
+        } else {
+            hit = special_token_at(ST.trie[g], chars, pos, ee, te);
+        }
+        if (!hit) continue;
+        g0 = q; g1 = te; m1 = te;
+        if (ST.strip_right[g]) { int l; while (m1 < ee && (l = special_ws_len(chars, m1, ee, T)) > 0) m1 += l; }
+        return;
+    }
+}
+
+
+// Sequential scan of one element with the matcher above (the kernel resolves the same scan per 32-position chunk).
+template <class Sink>
+B2_HD void special_split_element(const SpecialTables& ST, const ClassTables& T, const uint8_t* chars, int eb, int ee, Sink&& sink) {
+    int cur = eb;
+    for (int pos = eb; pos < ee; ++pos) {
+        if (pos < cur || is_cont_byte(chars[pos]) || !((ST.first[chars[pos] >> 5] >> (chars[pos] & 31)) & 1u)) continue;
+        int m1 = 0, g0 = 0, g1 = 0;
+        special_match_at(ST, T, chars, pos, ee, m1, g0, g1);
+        if (m1 <= pos) continue;
+        if (cur < pos) sink(cur, pos, 0);
+        sink(g0, g1, 1);
+        cur = m1;
+    }
+    if (cur < ee) sink(cur, ee, 0);
+}
+
 }  // namespace b200tok

@@ -274,3 +274,28 @@ HZ int64_t hz_llama3_word_form(const uint8_t* s, int64_t n, int32_t* out_begins)
     }
     return cnt;
 }
+
+// SpecialTokensSplit on the host: the pattern parser (tables.cpp parse_special) + the per-position matcher and scan of
+// tok_core.cuh over one element.  Returns the piece count (< 0: the parser's error code).
+HZ int64_t hz_special_split(const char* pattern, int64_t plen, const uint8_t* chars, int64_t n, int32_t* out_b, int32_t* out_e,
+                            uint8_t* out_skip, int64_t cap) {
+    HostSpecial hs;
+    std::string err;
+    const int rc = parse_special(pattern, plen, hs, err);
+    if (rc) return rc;
+    SpecialTables st{};
+    st.n_groups = (int32_t)hs.groups.size();
+    for (int g = 0; g < st.n_groups; ++g) {
+        st.trie[g] = hs.groups[(size_t)g].trie.view();
+        st.strip_left[g] = hs.groups[(size_t)g].strip_left;
+        st.strip_right[g] = hs.groups[(size_t)g].strip_right;
+    }
+    for (int k = 0; k < 8; ++k) st.first[k] = hs.first[(size_t)k];
+    st.ws_token = hs.ws_token;
+    int64_t k = 0;
+    special_split_element(st, host_class_tables().view(), chars, 0, (int)n, [&](int b, int e, int skip) {
+        if (k < cap) { out_b[k] = b; out_e[k] = e; out_skip[k] = (uint8_t)skip; }
+        ++k;
+    });
+    return k;
+}

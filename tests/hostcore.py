@@ -140,3 +140,17 @@ def llama3_word_form(data: bytes):
         return None
     b = out[:n].tolist()
     return list(zip(b, b[1:] + [len(data)]))
+
+
+def special_split(pattern: str, data: bytes):
+    """SpecialTokensSplit of one element by the product's host-compiled parser + matcher: [(begin, end, skip)]."""
+    pat = pattern.encode()
+    arr = np.frombuffer(data, np.uint8) if len(data) else np.zeros(1, np.uint8)
+    cap = len(data) + 2
+    ob, oe, osk = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.uint8)
+    lib().hz_special_split.restype = C.c_int64
+    n = lib().hz_special_split(pat, C.c_int64(len(pat)), arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), ob.ctypes.data_as(K.i32p),
+                               oe.ctypes.data_as(K.i32p), osk.ctypes.data_as(K.u8p), C.c_int64(cap))
+    if n < 0:
+        raise ValueError(f"hz_special_split error {n}")
+    return list(zip(ob[:n].tolist(), oe[:n].tolist(), osk[:n].tolist()))

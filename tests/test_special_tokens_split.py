@@ -102,3 +102,43 @@ def test_gpu_unsupported_pattern_is_an_error(ops):
         with pytest.raises(B200TokError) as ei:
             ops.SpecialTokensSplit().with_pattern(bad)
         assert ei.value.code == E_UNSUPPORTED
+
+
+def test_host_matcher_equals_pcre2(oracle_mod):
+    """CPU tier: the product's pattern parser + per-position matcher (tok_core.cuh, compiled for the host by tests/harness)
+    against the oracle's PCRE2 capture-group scan — the reference vectors, exhaustive short strings over a small alphabet for
+    every strip combination, and random texts with whitespace / prefix-related / multi-byte tokens."""
+    import itertools
+    import hostcore as H
+
+    def oracle_pieces(o, s):
+        b, e, ch = pack_strings([s])
+        rb, re_ = add_ragged_dimension(b, e)
+        r = o(rb, re_, b, e, ch)
+        return list(zip(r[2].tolist(), r[3].tolist(), r[4].tolist()))
+
+    for c in GOLDEN["cases"]:
+        o = oracle_mod.SpecialTokensSplitOracle(c["pattern"])
+        assert H.special_split(c["pattern"], c["text"].encode()) == oracle_pieces(o, c["text"].encode()), c["text"]
+    small = ["a", "b", " ", "\n", "<", ">", "x"]
+    for sl, sr in itertools.product((False, True), repeat=2):
+        pattern = oracle_mod.special_tokens_pattern([("<a>", sl, sr), ("ab", sl, sr), ("a", sl, sr), (" b", sl, sr), ("x", not sl, sr)])
+        o = oracle_mod.SpecialTokensSplitOracle(pattern)
+        for L in range(0, 6):
+            for tup in itertools.product(small, repeat=L):
+                s = "".join(tup).encode()
+                assert H.special_split(pattern, s) == oracle_pieces(o, s), (pattern, s)
+    rng = np.random.default_rng(77)
+    sets = [
+        [("<|endoftext|>", False, False), ("<|im_start|>", True, False), ("<|im_end|>", False, True), ("<|im", True, True)],
+        [("    ", False, False), ("def", True, True), (" ", True, False), ("\n\n", False, True)],
+        [("▁", False, False), ("<｜begin▁of▁sentence｜>", True, True), ("　　", True, False), ("é", False, True)],
+    ]
+    frag = ["<|endoftext|>", "<|im_start|>", "<|im_end|>", "<|im", "    ", "def", " ", "  ", "\n", "\n\n", "\t", "▁", "<｜begin▁of▁sentence｜>", "　", "é",
+            "a", "b", "<", "|", ">", "hello", "Ж", "\U0001F600", " "]
+    for toks in sets:
+        pattern = oracle_mod.special_tokens_pattern(toks)
+        o = oracle_mod.SpecialTokensSplitOracle(pattern)
+        for _ in range(3000):
+            s = "".join(rng.choice(frag, size=int(rng.integers(0, 30)))).encode()
+            assert H.special_split(pattern, s) == oracle_pieces(o, s), (pattern, s)
