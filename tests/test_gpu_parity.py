@@ -571,3 +571,24 @@ def test_sharded_peer_store_emit_world1(ops, gpt2):
     finally:
         if own:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("vocab,pattern", [("gpt2", "llama3"), ("llama3", "gpt2"), ("gpt2", "gpt2_digits")])
+def test_fast_kernel_every_instantiation(ops, oracle_mod, gpt2, llama3, vocab, pattern):
+    """The dedicated kernel is instantiated per (id width, split pattern): cross the vocabularies and patterns so that
+    <u16, llama3> and <i32, gpt2 / gpt2-digits> run too (the natural pairs are covered by the other tests)."""
+    m = {"gpt2": gpt2, "llama3": llama3}[vocab]
+    pat = {"gpt2": A.GPT2_PATTERN, "llama3": A.LLAMA3_PATTERN, "gpt2_digits": A.GPT2_DIGITS_PATTERN}[pattern]
+    split = ops.RegexSplit("isolate").with_pattern(pat)
+    o_split = oracle_mod.SplitOracle(pat, "isolate")
+    rng = np.random.default_rng(41)
+    strings = [bytes(rng.integers(0x20, 0x7F, size=int(n), dtype=np.uint8)) for n in rng.integers(0, 1500, size=300)]
+    strings += [s.encode() for s in cases.EDGE_STRINGS if "<|" not in s] + [p.encode() for p in cases.long_prompts()]
+    strings += [("12345678901234567890 " * 40).encode(), ("\n\n  \t" * 300).encode(), ("x" * 40 + " ") * 30 and (("x" * 40 + " ") * 30).encode()]
+    batch = cases.batch_from_strings(strings)
+    mix = cases.mixed_utf8_batch(256, 1024, seed=9)
+    for bt in (batch, mix):
+        s = o_split(*bt)
+        exp = m["o_bpe"](s[0], s[1], s[2], s[3], bt[4])
+        got = ops.split_bpe(split, m["bpe"], list(bt))
+        assert cases.ragged_rows_equal(got, exp), (vocab, pattern)
