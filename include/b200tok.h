@@ -204,6 +204,11 @@ typedef struct {
 /* n_ids_device (optional, device): this rank's id count.  Fully asynchronous on `cuda_stream`. */
 B200TOK_API int b200tok_split_bpe_run_sharded(b200tok_handle split, b200tok_handle bpe, const b200tok_ragged_strings* in,
                                               const b200tok_peer_out* peers, int64_t* n_ids_device, void* cuda_stream);
+/* Same for RegexSplit [-> RegexSplit] -> WordpieceTokenizer (rows are compacted, then stored into every rank's slot; with
+ * wire16 the caller guarantees every vocabulary id < 65 535). */
+B200TOK_API int b200tok_split_wordpiece_run_sharded(b200tok_handle split1, b200tok_handle split2, b200tok_handle wordpiece,
+                                                    const b200tok_ragged_strings* in, int32_t unk_token_id, const b200tok_peer_out* peers,
+                                                    int64_t* n_ids_device, void* cuda_stream);
 /* wire16 only: after the barrier, widen this rank's staging copy (all world * rows_per_rank rows) into peers->ids[rank]. */
 B200TOK_API int b200tok_peer_expand_run(int device, const b200tok_peer_out* peers, void* cuda_stream);
 

@@ -149,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "b200tok_set_timing", "b200tok_last_kernel_ms",
     "b200tok_regexsplit_create", "b200tok_regexsplit_run", "b200tok_specialsplit_create", "b200tok_specialsplit_run",
     "b200tok_bpe_create", "b200tok_bpe_run", "b200tok_split_bpe_run", "b200tok_split_bpe_run_sharded", "b200tok_peer_expand_run",
-    "b200tok_wordpiece_create", "b200tok_wordpiece_run", "b200tok_split_wordpiece_run",
+    "b200tok_wordpiece_create", "b200tok_wordpiece_run", "b200tok_split_wordpiece_run", "b200tok_split_wordpiece_run_sharded",
     "b200tok_vocabenc_create", "b200tok_vocabenc_run",
     "b200tok_vocabdec_create", "b200tok_vocabdec_run", "b200tok_vocabdec_max_chars",
     "b200tok_bytefallback_run",

@@ -991,6 +991,29 @@ B200TOK_API int b200tok_split_wordpiece_run(b200tok_handle split1, b200tok_handl
     return run_rows(wp, call, in, out, nullptr, stream);
 }
 
+B200TOK_API int b200tok_split_wordpiece_run_sharded(b200tok_handle split1, b200tok_handle split2, b200tok_handle wordpiece,
+                                                    const b200tok_ragged_strings* in, int32_t unk_token_id, const b200tok_peer_out* peers,
+                                                    int64_t* n_ids_device, void* stream) {
+    SplitObj* s1 = as<SplitObj>(split1, K_SPLIT);
+    SplitObj* s2 = split2 ? as<SplitObj>(split2, K_SPLIT) : nullptr;
+    WordpieceObj* wp = as<WordpieceObj>(wordpiece, K_WORDPIECE);
+    if (!s1 || (split2 && !s2) || !wp || !in || !peers) return fail(B200TOK_E_INVALID, "expected (RegexSplit[, RegexSplit], WordpieceTokenizer) handles, input and peer buffers");
+    if (in->mem != B200TOK_MEM_DEVICE) return fail(B200TOK_E_INVALID, "the sharded call takes device-resident input");
+    if (peers->world < 1 || peers->world > B200TOK_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world || peers->rows_per_rank < in->n_rows ||
+        peers->slot_capacity < in->n_chars + in->n_elems)
+        return fail(B200TOK_E_INVALID, "bad peer layout (world 1..8, rows_per_rank >= rows, slot_capacity >= worst-case ids of the shard)");
+    for (int p = 0; p < peers->world; ++p)
+        if ((peers->wire16 ? !peers->ids16[p] : !peers->ids[p]) || !peers->begins[p] || !peers->ends[p]) return fail(B200TOK_E_INVALID, "missing peer buffer %d", p);
+    RowCall call;
+    call.op = OP_WORDPIECE;
+    call.split = s1;
+    call.split2 = s2;
+    call.wp = wp;
+    call.unk_id = unk_token_id;
+    b200tok_ragged_ids out{nullptr, nullptr, nullptr, peers->slot_capacity, 0, n_ids_device, B200TOK_MEM_DEVICE};
+    return run_rows(wp, call, in, &out, nullptr, stream, peers);
+}
+
 // ---- VocabEncoder ----
 B200TOK_API int b200tok_vocabenc_create(const b200tok_vocabenc_desc* d, b200tok_handle* out) {
     if (!d || !out) return fail(B200TOK_E_INVALID, "null argument");

@@ -133,15 +133,20 @@ class PeerGather:
         self._po = po
 
     def run(self, pipe, db):
-        """pipe: runtime.TokenizerPipeline (kind 'bpe'); db: runtime.DeviceBatch of this rank's shard.  Asynchronous on the current
+        """pipe: runtime.TokenizerPipeline (BPE or WordPiece); db: runtime.DeviceBatch of this rank's shard.  Asynchronous on the current
         torch stream up to the barrier; returns (begins, ends, ids) views of this rank's copy of the gathered result."""
         import ctypes as C
         from . import _capi as K
         rin = K.RaggedStrings(db.rb.data_ptr(), db.re.data_ptr(), db.n_rows, db.begins.data_ptr(), db.ends.data_ptr(), db.n_elems,
                               db.chars.data_ptr(), db.n_chars, None, K.MEM_DEVICE)
         self._h[0].barrier(channel=1)   # nobody still reads the previous result (readers are ordered before this on their streams)
-        K.check(K.lib().b200tok_split_bpe_run_sharded(pipe.split1.handle, pipe.tok.handle, C.byref(rin), C.byref(self._po),
-                                                      C.c_void_p(self.n.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if pipe.kind == "bpe":
+            K.check(K.lib().b200tok_split_bpe_run_sharded(pipe.split1.handle, pipe.tok.handle, C.byref(rin), C.byref(self._po),
+                                                          C.c_void_p(self.n.data_ptr()), st))
+        else:
+            K.check(K.lib().b200tok_split_wordpiece_run_sharded(pipe.split1.handle, pipe.split2.handle, pipe.tok.handle, C.byref(rin),
+                                                                C.c_int32(pipe.unk), C.byref(self._po), C.c_void_p(self.n.data_ptr()), st))
         self._h[0].barrier(channel=0)   # every rank's stores into my buffers are complete and visible after this
         if self.wire16:
             dev_index = self.device.index if isinstance(self.device, torch.device) else int(self.device)

@@ -592,3 +592,63 @@ def test_fast_kernel_every_instantiation(ops, oracle_mod, gpt2, llama3, vocab, p
         exp = m["o_bpe"](s[0], s[1], s[2], s[3], bt[4])
         got = ops.split_bpe(split, m["bpe"], list(bt))
         assert cases.ragged_rows_equal(got, exp), (vocab, pattern)
+
+
+def test_sharded_wordpiece_world1_and_concurrent_calls(ops, bert, gpt2):
+    """(1) The sharded WordPiece entry point (compaction storing into the peer slots) on a one-rank group equals the ordinary
+    path.  (2) A handle may be used from several host threads at once (the reference's evaluate() is const and concurrent):
+    four threads, two handles, interleaved calls, every result identical to the single-threaded one."""
+    import os
+    import socket
+    import threading
+    import torch
+    import torch.distributed as dist
+    from openvino_tokenizers_b200 import runtime as R
+    from openvino_tokenizers_b200.sharded import PeerGather
+    own = not dist.is_initialized()
+    if own:
+        with socket.socket() as s_:
+            s_.bind(("127.0.0.1", 0))
+            port = s_.getsockname()[1]
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        batch = cases.random_ascii_batch(3000, 256, seed=3, lower=True)
+        unk = bert["assets"].unk_token_id
+        exp = ops.split_wordpiece(bert["s1"], bert["s2"], bert["wp"], list(batch), unk)
+        dev = torch.device("cuda", 0)
+        pipe = R.TokenizerPipeline("wordpiece", "bert_synth")
+        db = R.to_device(batch, dev)
+        pg = PeerGather(db.n_rows, db.n_chars + db.n_elems, dev)
+        b, e, ids = pg.run(pipe, db)
+        torch.cuda.synchronize()
+        gb, ge, gi = b.cpu().numpy(), e.cpu().numpy(), ids.cpu().numpy()
+        assert int(pg.n.item()) == len(exp[2]) and np.array_equal(ge - gb, exp[1] - exp[0])
+        for r in range(0, len(gb), 7):
+            assert np.array_equal(gi[gb[r]:ge[r]], exp[2][exp[0][r]:exp[1][r]])
+    finally:
+        if own:
+            dist.destroy_process_group()
+    # concurrent evaluate() calls
+    b1 = cases.random_ascii_batch(2000, 300, seed=11)
+    b2 = cases.random_ascii_batch(1500, 256, seed=12, lower=True)
+    ref1 = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(b1))
+    ref2 = ops.split_wordpiece(bert["s1"], bert["s2"], bert["wp"], list(b2), unk)
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(6):
+                if k % 2 == 0:
+                    assert cases.ragged_rows_equal(ops.split_bpe(gpt2["split"], gpt2["bpe"], list(b1)), ref1)
+                else:
+                    assert cases.ragged_rows_equal(ops.split_wordpiece(bert["s1"], bert["s2"], bert["wp"], list(b2), unk), ref2)
+        except Exception as ex:      # noqa: BLE001
+            errors.append(repr(ex))
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
