@@ -58,3 +58,21 @@ def test_create_fails_loudly_without_gpu(K):
     from openvino_tokenizers_b200 import ops
     with pytest.raises(ops.B200TokError):
         ops.RegexSplit("remove").with_pattern(r"\s+")
+
+
+def test_ctypes_mirrors_match_the_header_layout(K, tmp_path):
+    """The ctypes structures in _capi.py must have the size the C compiler gives the structs of include/b200tok.h (a plain-C
+    translation unit: the header is a C ABI, no C++ needed)."""
+    import subprocess
+    pairs = [("b200tok_strings", K.Strings), ("b200tok_ragged_strings", K.RaggedStrings), ("b200tok_ragged_strings_out", K.RaggedStringsOut),
+             ("b200tok_ragged_ids", K.RaggedIds), ("b200tok_regexsplit_desc", K.RegexSplitDesc), ("b200tok_bpe_desc", K.BpeDesc),
+             ("b200tok_wordpiece_desc", K.WordpieceDesc), ("b200tok_vocabenc_desc", K.VocabEncDesc), ("b200tok_vocabdec_desc", K.VocabDecDesc),
+             ("b200tok_decoded", K.Decoded), ("b200tok_ragged_i32", K.RaggedI32), ("b200tok_post_desc", K.PostDesc), ("b200tok_peer_out", K.PeerOut)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "b200tok.h"\nint main(void) {\n' +
+                   "".join(f'  printf("%zu\\n", sizeof({c}));\n' for c, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-o", str(exe), str(src)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    for (cname, ct), n in zip(pairs, sizes):
+        assert C.sizeof(ct) == n, (cname, C.sizeof(ct), n)

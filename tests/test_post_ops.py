@@ -174,3 +174,25 @@ def test_gpu_fused_tail_equals_the_three_ops(ops, oracle_mod):
                     exp, emask = oracle_mod.ragged_to_dense(cb, ce, cx, target, 0, pad_right)
                     got, gmask = ops.post_dense(b, e, x, ml, target, 0, prefix, suffix, tleft, pad_right)
                     assert np.array_equal(got, exp) and np.array_equal(gmask, emask.astype(bool)), (rows, prefix, tleft, pad_right)
+
+
+@pytest.mark.gpu
+def test_gpu_capacity_and_argument_errors(ops):
+    """Errors come back as codes + message (rethrown by the ov::Op shim as ov::Exception); nothing is written past a too-small buffer."""
+    import ctypes as C
+    from openvino_tokenizers_b200 import _capi as K
+    b, e, x = np.array([0, 3], np.int32), np.array([3, 8], np.int32), np.arange(8, dtype=np.int32)
+    segs = (K.RaggedI32 * 1)(K.RaggedI32(b.ctypes.data, e.ctypes.data, 2, x.ctypes.data, 8))
+    ids = np.zeros(1, np.int32)
+    ob, oe, ox, oi = np.empty(2, np.int32), np.empty(2, np.int32), np.full(4, -9, np.int32), np.full(4, -9, np.int32)
+    n = C.c_int64(0)
+    rc = K.lib().b200tok_combine_segments_run(0, segs, 1, C.c_void_p(ids.ctypes.data), C.c_void_p(ob.ctypes.data), C.c_void_p(oe.ctypes.data),
+                                              C.c_void_p(ox.ctypes.data), C.c_void_p(oi.ctypes.data), C.c_int64(4), C.byref(n), K.MEM_HOST, None)
+    assert rc == K.E_CAPACITY and n.value == 8 and np.all(ox == -9)
+    assert b"capacity" in K.lib().b200tok_last_error()
+    with pytest.raises(K.B200TokError):
+        ops.post_dense(b, e, x, 4, 8, 0, prefix=list(range(9)))          # more than 8 prefix ids
+    out1 = np.empty(1, np.int32)
+    rc = K.lib().b200tok_ragged_to_dense_run(0, C.c_void_p(b.ctypes.data), C.c_void_p(e.ctypes.data), C.c_int64(2), C.c_void_p(x.ctypes.data),
+                                             C.c_int64(8), C.c_int32(-1), C.c_int32(0), 1, 0, C.c_void_p(out1.ctypes.data), None, K.MEM_HOST, None)
+    assert rc == K.E_INVALID                                              # negative target dimension
