@@ -36,13 +36,13 @@ struct __align__(16) FastSmem {
 static_assert(sizeof(uint32_t) * 11 * kMStride >= sizeof(uint16_t) * (WIN / 3 + 10), "merge queue must fit the mask area");
 enum : int { M_L = 0, M_N, M_S, M_SP, M_A2, M_A3, M_CONT, M_MB, M_F, M_NL, M_PG };
 
-constexpr int kFastSmemFixed = 128 + 1024 + 2048;   // ascii classes, lut32, pair bitmap
+constexpr int kFastSmemFixed = 128 + 1024;   // ascii classes, lut32
 template <class IdT> constexpr size_t fast_smem_bytes() { return kFastSmemFixed + WARPS_PER_BLOCK * sizeof(FastSmem<IdT>); }
 
 // One window.  Returns `send` (how far the window advances; 0 => the first piece does not fit) or -1 when the window
 // needs the generic path.  On success S.ids[0 .. send) holds the window's tokens (-1 = merged away).
 template <class IdT, bool L3>
-__device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32, const uint32_t* pbits,
+__device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32,
                                            const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
                                            bool ascii) {
     const uint8_t* B = S.B();
@@ -399,14 +399,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                            // [128]
     uint32_t* lut32_smem = reinterpret_cast<uint32_t*>(smem_raw + 128);        // [256]
-    uint32_t* pbits_smem = lut32_smem + 256;                                   // [512]
     FastSmem<IdT>* warps = reinterpret_cast<FastSmem<IdT>*>(smem_raw + kFastSmemFixed);
     const int lane = threadIdx.x & 31;
     FastSmem<IdT>& S = warps[threadIdx.x >> 5];
     if (threadIdx.x < 128) ascii_smem[threadIdx.x] = P.cls.ascii[threadIdx.x];
     lut32_smem[threadIdx.x] = v7_lut_entry(P, threadIdx.x);
-    pbits_smem[threadIdx.x] = P.bpe.pair_bits[threadIdx.x];
-    pbits_smem[threadIdx.x + 256] = P.bpe.pair_bits[threadIdx.x + 256];
     __syncthreads();
     const uint32_t ltm = (1u << lane) - 1u;
 
@@ -456,7 +453,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                 }
                 const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
                 __syncwarp();
-                const int send = fast_window<IdT, L3>(S, P, lut32_smem, pbits_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
                 if (send <= 0) { redo = true; break; }
                 if (base + emitted + send > P.tmp_cap) {
                     if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
