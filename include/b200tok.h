@@ -336,6 +336,32 @@ B200TOK_API int b200tok_utf8_validate_run(int device, const int32_t* begins, con
                                           int64_t n_chars, int replace_mode, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
                                           int64_t chars_capacity, int64_t* n_chars_out, int mem, void* cuda_stream);
 
+/* ---- normalisers -------------------------------------------------------------------------------------
+ * RegexNormalization(global_replace), reference src/regex_normalization.cpp:59-153 + PCRE2Wrapper::substitute
+ * src/utils.cpp:315-382.  The GPU path covers the search patterns that match exactly ONE character, i.e. every pattern the
+ * BERT normaliser and the prefix / metaspace steps of the converter emit (python/openvino_tokenizers/tokenizer_pipeline.py:
+ * 230-278: del_control_chars, replace_whitespace, handle_chinese_chars, strip_accents, add_prefix_whitespace[_to_not_
+ * whitespace], prepend, replace_spaces_metaspace and the legacy (^)(.) forms), with a replacement made of literal text and
+ * at most one reference to the matched character ($N or \N).  Any other pattern returns B200TOK_E_UNSUPPORTED from
+ * _create (nothing runs on the CPU instead).                                                                            */
+B200TOK_API int b200tok_regexnorm_create(const char* search_pattern, int64_t search_len, const char* replace_pattern,
+                                         int64_t replace_len, int global_replace, int device, b200tok_handle* out);
+/* CharsMapNormalization, reference src/charsmap_normalization.cpp:34-69: sentencepiece 0.2.1 normalizer::Normalizer over a
+ * precompiled charsmap (u32 trie size | Darts-clone double array | '\0'-separated replacements).  The blob is the op's
+ * charsmap input, or what the reference's get_precompiled_charsmap(normalization_form, case_fold) returns for the attribute
+ * form.  add_dummy_prefix / remove_extra_whitespaces / escape_whitespaces must be 0 (what NormalizeUnicode / CaseFold
+ * set); otherwise B200TOK_E_UNSUPPORTED.                                                                                */
+B200TOK_API int b200tok_charsmap_create(const uint8_t* precompiled_charsmap, int64_t charsmap_len, int add_dummy_prefix,
+                                        int remove_extra_whitespaces, int escape_whitespaces, int device, b200tok_handle* out);
+/* evaluate_normalization_helper, reference src/utils.cpp:178-234, for either handle: strings (begins, ends, chars) ->
+ * normalised strings packed back to back from offset 0; elements with skips[i] != 0 are copied unchanged (skips may be
+ * NULL).  Worst case output: RegexNormalization n_chars * (1 + replacement length), CharsMapNormalization bounded by the
+ * longest replacement per input byte; a too small chars_capacity returns B200TOK_E_CAPACITY with *n_chars_out = the size
+ * needed.  Free the handle with b200tok_destroy.                                                                        */
+B200TOK_API int b200tok_normalize_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
+                                      int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                      int64_t chars_capacity, int64_t* n_chars_out, int mem, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_misc.cuh"
+#include "kernels_norm.cuh"
 #include "kernels_shim.cuh"
 #include "kernels_special.cuh"
 #include "kernels_tail.cuh"
@@ -85,8 +86,8 @@ struct DevTrie {
 struct DevClassTables {
     DBuf<uint8_t> ascii, stage2;
     DBuf<uint16_t> stage1;
-    cudaError_t upload() {
-        const HostClassTables& h = host_class_tables();
+    cudaError_t upload() { return upload(host_class_tables()); }
+    cudaError_t upload(const HostClassTables& h) {
         cudaError_t e;
         if ((e = ascii.upload(h.ascii))) return e;
         if ((e = stage1.upload(h.stage1))) return e;
@@ -132,7 +133,7 @@ struct RowWorkspace {
     }
 };
 
-enum Kind { K_SPLIT = 1, K_BPE, K_WORDPIECE, K_VOCABENC, K_VOCABDEC, K_SPECIAL };
+enum Kind { K_SPLIT = 1, K_BPE, K_WORDPIECE, K_VOCABENC, K_VOCABDEC, K_SPECIAL, K_NORM };
 
 }  // namespace
 
@@ -1626,6 +1627,103 @@ B200TOK_API int b200tok_utf8_validate_run(int device, const int32_t* begins, con
         CU(cudaMemcpyAsync(out_begins, d_ob, n * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(out_ends, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
         if (total > base) CU(cudaMemcpyAsync(out_chars + base, d_oc + base, total - base, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return B200TOK_OK;
+}
+
+}  // extern "C"
+
+
+// ---- normalisers: RegexNormalization / CharsMapNormalization ----
+namespace {
+struct NormObj : b200tok_object {
+    HostNorm h;
+    DevClassTables ncls;
+    DBuf<uint32_t> units;
+    DBuf<uint8_t> normalized;
+    NormRule view() const {
+        NormRule r = h.rule;
+        r.cls = ncls.view();
+        r.units = units.p; r.n_units = (uint32_t)h.units.size();
+        r.normalized = normalized.p; r.n_normalized = (uint32_t)h.normalized.size();
+        return r;
+    }
+};
+int finish_norm(std::unique_ptr<NormObj>& o, int device, b200tok_handle* out) {
+    int rc = init_object(o.get(), K_NORM, device);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (o->h.rule.kind == NORM_CLASS) CU(o->ncls.upload(host_norm_class_tables()));
+    CU(o->units.upload(o->h.units));
+    CU(o->normalized.upload(o->h.normalized));
+    CU(cudaDeviceSynchronize());
+    *out = o.release();
+    return B200TOK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+B200TOK_API int b200tok_regexnorm_create(const char* search_pattern, int64_t search_len, const char* replace_pattern, int64_t replace_len,
+                                         int global_replace, int device, b200tok_handle* out) {
+    if (!out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<NormObj>();
+    std::string err;
+    const int rc = parse_regex_norm(search_pattern, search_len, replace_pattern, replace_len, global_replace, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    return finish_norm(o, device, out);
+}
+
+B200TOK_API int b200tok_charsmap_create(const uint8_t* precompiled_charsmap, int64_t charsmap_len, int add_dummy_prefix,
+                                        int remove_extra_whitespaces, int escape_whitespaces, int device, b200tok_handle* out) {
+    if (!out) return fail(B200TOK_E_INVALID, "null argument");
+    auto o = std::make_unique<NormObj>();
+    std::string err;
+    const int rc = parse_charsmap(precompiled_charsmap, charsmap_len, add_dummy_prefix, remove_extra_whitespaces, escape_whitespaces, o->h, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    return finish_norm(o, device, out);
+}
+
+// evaluate_normalization_helper (src/utils.cpp:178-234): out_begins[0] = 0, strings packed back to back.
+B200TOK_API int b200tok_normalize_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
+                                      int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                      int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
+    NormObj* o = as<NormObj>(h, K_NORM);
+    if (!o) return fail(B200TOK_E_INVALID, "not a normaliser handle");
+    if (n < 0 || n_chars < 0 || chars_capacity < 0 || !n_chars_out || (n > 0 && (!begins || !ends || !out_begins || !out_ends))) return fail(B200TOK_E_INVALID, "bad arguments");
+    *n_chars_out = 0;
+    if (n == 0) return B200TOK_OK;
+    if (n > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "more than 2^31 strings in one call");
+    const bool host = mem == B200TOK_MEM_HOST;
+    if (host) for (int64_t i = 0; i < n; ++i) if (begins[i] < 0 || ends[i] < begins[i] || ends[i] > n_chars) return fail(B200TOK_E_INVALID, "element %lld has a bad extent", (long long)i);
+    DeviceGuard g(o->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    AsyncBuf bb, be, bc, bs, blen, bob, boe, boc, bscan, btot;
+    const int32_t *d_b, *d_e; const uint8_t *d_c, *d_s;
+    int rc;
+    if ((rc = stage_in(bb, begins, n, host, st, d_b)) || (rc = stage_in(be, ends, n, host, st, d_e)) ||
+        (rc = stage_in(bc, chars, n_chars, host, st, d_c)) || (rc = stage_in(bs, skips, skips ? n : 0, host, st, d_s))) return rc;
+    CU(blen.alloc((size_t)n * 4, st)); CU(btot.alloc(8, st));
+    int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
+    if (host) { CU(bob.alloc((size_t)n * 4, st)); CU(boe.alloc((size_t)n * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
+    const NormRule R = o->view();
+    const int64_t warps = std::min<int64_t>(n, (int64_t)o->sm_count * 8 * 8);      // 8 CTAs of 8 warps per SM, strings strided over them
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), nullptr, nullptr, nullptr, 0, nullptr);
+    if ((rc = scan_i32(bscan, blen.as<int32_t>(), d_ob, n, st))) return rc;
+    normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    CU(cudaGetLastError());
+    { std::lock_guard<std::mutex> lock(o->mu); o->launches += 2; }
+    int64_t total = 0;
+    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_chars_out = total;
+    if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
+    if (host) {
+        CU(cudaMemcpyAsync(out_begins, d_ob, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(out_ends, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
+        if (total) CU(cudaMemcpyAsync(out_chars, d_oc, total, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     return B200TOK_OK;

@@ -1,0 +1,78 @@
+// kernels_norm.cuh — normalisers:
+//   RegexNormalization     reference src/regex_normalization.cpp:127-153 (+ src/utils.cpp:315-382, pcre2_substitute), for the
+//                          single-character search patterns the converter emits (tables.cpp kNormPatterns)
+//   CharsMapNormalization  reference src/charsmap_normalization.cpp:34-69 (sentencepiece Normalizer over a precompiled charsmap)
+//   both through evaluate_normalization_helper (src/utils.cpp:178-234): per element, skip-flagged elements pass through.
+// The scan "at an active byte, consume c bytes and emit o bytes" is sequential per string.  One warp per string takes 32
+// byte positions at a time: every lane evaluates the step that WOULD start at its byte (tok_core.cuh norm_eval), pointer
+// jumping over the lanes' jump targets (5 rounds of shuffles) marks the positions the scan really visits, a warp scan of
+// their output lengths places the bytes.  Two passes (lengths -> cub scan -> write), like the other byte-stream shims.
+// HBM-bound byte streams; the tables (class stage tables, or the double array, 17-260 KB) stay in L1/L2.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200tok {
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ NormRule R, const int32_t* __restrict__ begins,
+                                                        const int32_t* __restrict__ ends, const uint8_t* __restrict__ chars,
+                                                        const uint8_t* __restrict__ skips, int64_t n, int32_t* __restrict__ len,
+                                                        const int32_t* __restrict__ out_begins, int32_t* __restrict__ out_ends,
+                                                        uint8_t* __restrict__ out, int64_t cap, int64_t* total) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int b = begins[i], e = ends[i];
+        int64_t o0 = 0;
+        if (WRITE) {
+            o0 = out_begins[i];
+            const int64_t oe = o0 + len[i];
+            if (lane == 0) { out_ends[i] = (int32_t)oe; if (i == n - 1) *total = oe; }
+            if (oe > cap) continue;
+        }
+        if (skips && skips[i]) {          // src/utils.cpp:211: the string is copied unchanged
+            if (WRITE) { for (int k = b + lane; k < e; k += 32) out[o0 + (k - b)] = chars[k]; }
+            else if (lane == 0) len[i] = e > b ? e - b : 0;
+            continue;
+        }
+        int cur = b;                      // next byte the scan visits
+        int o = 0;                        // bytes produced so far
+        bool done = false;                // a non-global rule has replaced its match
+        for (int c0 = b; c0 < e; c0 += 32) {
+            if (cur >= c0 + 32) continue;
+            const int pos = c0 + lane;
+            NormStep st;
+            st.consumed = 32; st.olen = 0; st.src = -2; st.matched = 0;
+            if (pos < e && pos >= cur) st = norm_eval(R, chars, b, pos, e, done);
+            // which lanes does the scan visit?  J = where the scan goes after this lane (>= 32: leaves the chunk),
+            // M = lanes visited from here; doubling composes them.
+            int J = lane + st.consumed;
+            uint32_t M = 1u << lane;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const int Jj = __shfl_sync(FULL, J, J & 31);
+                const uint32_t Mj = __shfl_sync(FULL, M, J & 31);
+                if (J < 32) { M |= Mj; J = Jj; }
+            }
+            const int s0 = cur - c0;
+            const uint32_t visited = __shfl_sync(FULL, M, s0);
+            cur = c0 + __shfl_sync(FULL, J, s0);
+            bool active = ((visited >> lane) & 1u) && pos < e;
+            if (!R.global && R.kind == NORM_CLASS && !done) {       // only the first match of the string is replaced
+                const uint32_t hits = __ballot_sync(FULL, active && st.matched);
+                if (hits) {
+                    done = true;
+                    if (active && st.matched && lane != __ffs(hits) - 1) { st.matched = 0; st.src = -2; st.olen = st.consumed; }
+                }
+            }
+            int incl = active ? st.olen : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+            if (WRITE && active) norm_emit(R, st, chars, pos, out + o0 + o + (incl - st.olen));
+            o += __shfl_sync(FULL, incl, 31);
+        }
+        if (!WRITE && lane == 0) len[i] = o;
+    }
+}
+
+}  // namespace b200tok

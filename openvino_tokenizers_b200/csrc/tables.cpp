@@ -28,6 +28,7 @@ bool in_bert_punct_or_cjk(uint32_t cp, uint8_t f) {
         if (cp >= r[0] && cp <= r[1]) return true;
     return false;
 }
+void two_stage(const std::vector<uint8_t>& flat, HostClassTables& t);
 }  // namespace
 
 const HostClassTables& host_class_tables() {
@@ -44,23 +45,153 @@ const HostClassTables& host_class_tables() {
                 flat[cp] = f;
             }
         }
-        t.ascii.assign(flat.begin(), flat.begin() + 128);
-        t.stage1.resize(0x1100);
-        std::map<std::vector<uint8_t>, uint16_t> seen;
-        for (uint32_t blk = 0; blk < 0x1100; ++blk) {
-            std::vector<uint8_t> v(flat.begin() + blk * 256, flat.begin() + blk * 256 + 256);
-            auto it = seen.find(v);
-            if (it == seen.end()) {
-                const uint16_t idx = (uint16_t)seen.size();
-                it = seen.emplace(v, idx).first;
-                t.stage2.insert(t.stage2.end(), v.begin(), v.end());
-            }
-            t.stage1[blk] = it->second;
-        }
+        two_stage(flat, t);
         return t;
     }();
     return tables;
 }
+
+namespace {
+void two_stage(const std::vector<uint8_t>& flat, HostClassTables& t) {
+    t.ascii.assign(flat.begin(), flat.begin() + 128);
+    t.stage1.resize(0x1100);
+    std::map<std::vector<uint8_t>, uint16_t> seen;
+    for (uint32_t blk = 0; blk < 0x1100; ++blk) {
+        std::vector<uint8_t> v(flat.begin() + blk * 256, flat.begin() + blk * 256 + 256);
+        auto it = seen.find(v);
+        if (it == seen.end()) {
+            const uint16_t idx = (uint16_t)seen.size();
+            it = seen.emplace(v, idx).first;
+            t.stage2.insert(t.stage2.end(), v.begin(), v.end());
+        }
+        t.stage1[blk] = it->second;
+    }
+}
+const Run kNormRuns[] = {
+#include "unicode_norm_ranges.inc"
+};
+}  // namespace
+
+const HostClassTables& host_norm_class_tables() {
+    static const HostClassTables tables = [] {
+        HostClassTables t;
+        std::vector<uint8_t> flat(0x110000);
+        const size_t n = sizeof(kNormRuns) / sizeof(kNormRuns[0]);
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t a = kNormRuns[i].cp, b = (i + 1 < n) ? kNormRuns[i + 1].cp : 0x110000u;
+            for (uint32_t cp = a; cp < b; ++cp) flat[cp] = kNormRuns[i].flags;
+        }
+        two_stage(flat, t);
+        return t;
+    }();
+    return tables;
+}
+
+// ------------------------------------------------------------------------------------------
+// Normalisers: pattern recognition (RegexNormalization) and blob parsing (CharsMapNormalization).
+// ------------------------------------------------------------------------------------------
+namespace {
+struct KnownNormPattern { const char* pattern; uint8_t mask; uint8_t any; int32_t literal; uint8_t negate; uint8_t anchored; int char_group; int n_groups; };
+// Search patterns the converter emits that match exactly one character (python/openvino_tokenizers/tokenizer_pipeline.py:230-278
+// of the reference), after the legacy rewrites of src/regex_normalization.cpp:33-37.
+const KnownNormPattern kNormPatterns[] = {
+    {R"(([\x00-\x08\x0B\x0C\x0E-\x1F\x7F-\x9F\p{Cf}]))", NC_DEL, 0, -1, 0, 0, 1, 1},   // del_control_chars_regex
+    {R"(\s)", NC_S, 0, -1, 0, 0, 0, 0},                                                   // replace_whitespace_regex
+    {R"(([\p{Han}]))", NC_HAN, 0, -1, 0, 0, 1, 1},                                         // handle_chinese_chars_regex
+    {R"(\p{Mn})", NC_MN, 0, -1, 0, 0, 0, 0},                                              // strip_accents_regex
+    {R"(^(\S))", NC_S, 0, -1, 1, 1, 1, 1},                                                // add_prefix_whitespace_regex
+    {R"(^([^ ]))", 0, 0, ' ', 1, 1, 1, 1},                                                // add_prefix_whitespace_to_not_whitespace_regex
+    {R"((?:^)([\s\S]))", 0, 1, -1, 0, 1, 1, 1},                                           // prepend_regex
+    {R"((^)([\s\S]))", 0, 1, -1, 0, 1, 2, 2},                                             // legacy (^)(.) / (^)(.+) after the rewrite
+};
+}  // namespace
+
+int parse_regex_norm(const char* search, int64_t slen, const char* replace, int64_t rlen, int global_replace, HostNorm& out, std::string& err) {
+    if (!search || slen < 0 || rlen < 0 || (rlen > 0 && !replace)) { err = "RegexNormalization: null pattern"; return B200TOK_E_INVALID; }
+    std::string pat(search, (size_t)slen);
+    if (pat == R"((^)(.))" || pat == R"((^)(.+))") pat = R"((^)([\s\S]))";       // src/regex_normalization.cpp:35-36
+    NormRule& R = out.rule;
+    R = NormRule{};
+    R.kind = NORM_CLASS;
+    R.literal_cp = -1;
+    R.global = global_replace != 0;
+    int char_group = 0, n_groups = 0;
+    bool known = false;
+    for (const auto& k : kNormPatterns) {
+        if (pat != k.pattern) continue;
+        R.mask = k.mask; R.any = k.any; R.literal_cp = k.literal; R.negate = k.negate; R.anchored = k.anchored;
+        char_group = k.char_group; n_groups = k.n_groups;
+        known = true;
+        break;
+    }
+    if (!known) {
+        // a single literal character that is not a regex metacharacter (e.g. " " -> metaspace, replace_spaces_metaspace)
+        uint32_t cp = 0;
+        const int l = pat.empty() ? 0 : utf8_strict_len((const uint8_t*)pat.data(), 0, (int)pat.size(), cp);
+        static const std::string meta = R"(\^$.|?*+()[]{})";
+        if (l > 0 && (size_t)l == pat.size() && !(cp < 0x80 && meta.find((char)cp) != std::string::npos)) { R.literal_cp = (int32_t)cp; known = true; }
+    }
+    if (!known) {
+        err = "RegexNormalization: search pattern `" + pat + "` is not one of the single-character patterns this build runs on the GPU";
+        return B200TOK_E_UNSUPPORTED;
+    }
+    // replacement: \N was already rewritten to $N by the reference (src/regex_normalization.cpp:19-31); do the same here
+    std::string rep(replace ? replace : "", (size_t)rlen);
+    for (char d = '1'; d <= '9'; ++d) {
+        const std::string from = std::string("\\") + d, to = std::string("$") + d;
+        size_t pos = 0;
+        while ((pos = rep.find(from, pos)) != std::string::npos) { rep.replace(pos, from.size(), to); pos += to.size(); }
+    }
+    std::string pre, post;
+    bool seen_char = false;
+    for (size_t i = 0; i < rep.size();) {
+        if (rep[i] != '$') { (seen_char ? post : pre).push_back(rep[i++]); continue; }
+        if (i + 1 < rep.size() && rep[i + 1] == '$') { (seen_char ? post : pre).push_back('$'); i += 2; continue; }
+        size_t j = i + 1;
+        const bool brace = j < rep.size() && rep[j] == '{';
+        if (brace) ++j;
+        size_t d0 = j;
+        long g = 0;
+        while (j < rep.size() && rep[j] >= '0' && rep[j] <= '9') { g = g * 10 + (rep[j] - '0'); if (g > 1000) break; ++j; }
+        if (j == d0 || (brace && (j >= rep.size() || rep[j] != '}'))) { err = "RegexNormalization: unsupported replacement syntax `" + rep + "`"; return B200TOK_E_UNSUPPORTED; }
+        if (brace) ++j;
+        if (g > n_groups) { err = "RegexNormalization: replacement refers to group " + std::to_string(g) + " which the pattern does not have"; return B200TOK_E_UNSUPPORTED; }
+        if (g == 0 || g == char_group) {
+            if (seen_char) { err = "RegexNormalization: the replacement may refer to the matched character once"; return B200TOK_E_UNSUPPORTED; }
+            seen_char = true;
+        }   // any other group of these patterns is the empty (^) group
+        i = j;
+    }
+    if (pre.size() > sizeof(R.pre) || post.size() > sizeof(R.post)) { err = "RegexNormalization: replacement literal longer than 16 bytes"; return B200TOK_E_UNSUPPORTED; }
+    R.keep = seen_char;
+    R.pre_len = (uint8_t)pre.size(); R.post_len = (uint8_t)post.size();
+    std::memcpy(R.pre, pre.data(), pre.size());
+    std::memcpy(R.post, post.data(), post.size());
+    return B200TOK_OK;
+}
+
+int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int remove_extra_whitespaces, int escape_whitespaces, HostNorm& out, std::string& err) {
+    if (len < 0 || (len > 0 && !blob)) { err = "CharsMapNormalization: null charsmap"; return B200TOK_E_INVALID; }
+    if (add_dummy_prefix || remove_extra_whitespaces || escape_whitespaces) {
+        err = "CharsMapNormalization: add_dummy_prefix / remove_extra_whitespaces / escape_whitespaces are not built for the GPU path (the converter's NormalizeUnicode / CaseFold steps leave them off)";
+        return B200TOK_E_UNSUPPORTED;
+    }
+    NormRule& R = out.rule;
+    R = NormRule{};
+    R.kind = NORM_CHARSMAP;
+    R.literal_cp = -1;
+    out.units.clear(); out.normalized.clear();
+    if (len == 0) return B200TOK_OK;                    // empty charsmap = identity (with U+FFFD for malformed bytes)
+    uint32_t tsz = 0;
+    if (len < 4) { err = "CharsMapNormalization: charsmap blob is truncated"; return B200TOK_E_INVALID; }
+    std::memcpy(&tsz, blob, 4);
+    if ((int64_t)tsz + 4 > len || (tsz & 3u) || tsz < 4) { err = "CharsMapNormalization: charsmap blob has a bad trie size"; return B200TOK_E_INVALID; }
+    out.units.resize(tsz / 4);
+    std::memcpy(out.units.data(), blob + 4, tsz);
+    out.normalized.assign(blob + 4 + tsz, blob + len);
+    return B200TOK_OK;
+}
+
 
 // ------------------------------------------------------------------------------------------
 // Flattened trie.

@@ -23,6 +23,7 @@ struct HostClassTables {
     ClassTables view() const { return ClassTables{ascii.data(), stage1.data(), stage2.data()}; }
 };
 const HostClassTables& host_class_tables();
+const HostClassTables& host_norm_class_tables();   // NC_* flags (normaliser patterns)
 
 struct HostTrie {
     std::vector<int32_t> first, value, edge_child, root_child;
@@ -102,6 +103,15 @@ struct HostSpecial {
     std::string pattern;
 };
 int parse_special(const char* pattern, int64_t len, HostSpecial& out, std::string& err);
+
+// Normalisers.  rule.cls / units / normalized pointers are filled in by the user of the tables (host or device views).
+struct HostNorm {
+    NormRule rule{};
+    std::vector<uint32_t> units;
+    std::vector<uint8_t> normalized;
+};
+int parse_regex_norm(const char* search, int64_t slen, const char* replace, int64_t rlen, int global_replace, HostNorm& out, std::string& err);
+int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int remove_extra_whitespaces, int escape_whitespaces, HostNorm& out, std::string& err);
 
 inline uint64_t fnv1a64(const uint8_t* p, int64_t n) {
     uint64_t h = 1469598103934665603ull;

@@ -1028,4 +1028,154 @@ B2_HD void special_split_element(const SpecialTables& ST, const ClassTables& T, 
     if (cur < ee) sink(cur, ee, 0);
 }
 
+// ------------------------------------------------------------------------------------------
+// Normalisers: RegexNormalization for single-character patterns and CharsMapNormalization.
+// Both are "at an active byte position: consume c bytes, emit o bytes" machines; norm_eval() is that step, shared by
+// the host scan below (tests) and the kernel (kernels_norm.cuh), which evaluates 32 positions at once and resolves which
+// of them the scan really visits.
+// ------------------------------------------------------------------------------------------
+enum : uint8_t { NC_DEL = 1, NC_S = 2, NC_HAN = 4, NC_MN = 8 };   // flags of the second class table (unicode_norm_ranges.inc)
+enum : int { NORM_CLASS = 0, NORM_CHARSMAP = 1 };
+
+struct NormRule {
+    int32_t kind;
+    // NORM_CLASS: the search pattern matches exactly one character of a class, optionally only at the start of the string
+    // (reference patterns: python/openvino_tokenizers/tokenizer_pipeline.py:230-278); the replacement is pre + [the character] + post.
+    ClassTables cls;
+    int32_t literal_cp;      // >= 0: the class is this single code point
+    uint8_t mask;            // else: characters whose NC_* flags intersect mask ...
+    uint8_t any;             // ... or every character ([\s\S])
+    uint8_t negate;          // the class is negated (\S, [^ ])
+    uint8_t anchored;        // ^: only the first character of the string
+    uint8_t global;          // PCRE2_SUBSTITUTE_GLOBAL, else only the first match
+    uint8_t keep;            // the replacement refers to the matched character
+    uint8_t pre_len, post_len;
+    uint8_t pre[16], post[16];
+    // NORM_CHARSMAP: sentencepiece precompiled charsmap = Darts-clone double array + '\0'-separated replacements
+    const uint32_t* units;
+    uint32_t n_units;
+    const uint8_t* normalized;
+    uint32_t n_normalized;
+};
+
+struct NormStep {
+    int32_t consumed;    // input bytes
+    int32_t olen;        // output bytes
+    int32_t src;         // >= 0: copy from normalized + src; -1: the rule's pre/char/post; -2: input bytes verbatim; -3: U+FFFD
+    uint8_t matched;     // NORM_CLASS: the character matched the class
+};
+
+// Well-formed UTF-8 character at s[i] (strict: no overlongs / surrogates, like sentencepiece's DecodeUTF8)?  Returns its
+// length, or 0 if malformed.
+B2_HD int utf8_strict_len(const uint8_t* s, int i, int end, uint32_t& cp) {
+    const uint32_t b0 = s[i];
+    if (b0 < 0x80) { cp = b0; return 1; }
+    const int left = end - i;
+    if ((b0 & 0xE0) == 0xC0) {
+        if (left < 2 || !is_cont_byte(s[i + 1])) return 0;
+        cp = ((b0 & 0x1Fu) << 6) | (s[i + 1] & 0x3Fu);
+        return cp >= 0x80 ? 2 : 0;
+    }
+    if ((b0 & 0xF0) == 0xE0) {
+        if (left < 3 || !is_cont_byte(s[i + 1]) || !is_cont_byte(s[i + 2])) return 0;
+        cp = ((b0 & 0x0Fu) << 12) | ((s[i + 1] & 0x3Fu) << 6) | (s[i + 2] & 0x3Fu);
+        return (cp >= 0x800 && (cp < 0xD800 || cp >= 0xE000)) ? 3 : 0;
+    }
+    if ((b0 & 0xF8) == 0xF0) {
+        if (left < 4 || !is_cont_byte(s[i + 1]) || !is_cont_byte(s[i + 2]) || !is_cont_byte(s[i + 3])) return 0;
+        cp = ((b0 & 0x07u) << 18) | ((s[i + 1] & 0x3Fu) << 12) | ((s[i + 2] & 0x3Fu) << 6) | (s[i + 3] & 0x3Fu);
+        return (cp >= 0x10000 && cp <= 0x10FFFF) ? 4 : 0;
+    }
+    return 0;
+}
+
+// Darts::DoubleArray::commonPrefixSearch + the "longest rule" loop of sentencepiece's Normalizer::NormalizePrefix
+// (at most 32 prefixes are reported; the last reported one is the longest).
+B2_HD int charsmap_longest(const NormRule& R, const uint8_t* s, int i, int end, uint32_t& value) {
+    if (!R.n_units) return 0;
+    uint32_t pos = 0, u = R.units[0];
+    pos ^= (u >> 10) << ((u & (1u << 9)) >> 6);
+    int mlen = 0, found = 0;
+    for (int k = i; k < end; ++k) {
+        const uint32_t c = s[k];
+        pos ^= c;
+        if (pos >= R.n_units) break;
+        u = R.units[pos];
+        if ((u & ((1u << 31) | 0xFFu)) != c) break;
+        pos ^= (u >> 10) << ((u & (1u << 9)) >> 6);
+        if ((u >> 8) & 1u) {
+            if (found < 32 && pos < R.n_units) { mlen = k + 1 - i; value = R.units[pos] & 0x7FFFFFFFu; }
+            ++found;
+        }
+    }
+    return mlen;
+}
+
+// One step of the scan at byte i of the string [b, e).  `first_done`: a non-global rule already replaced its match.
+B2_HD NormStep norm_eval(const NormRule& R, const uint8_t* s, int b, int i, int e, bool first_done) {
+    NormStep st;
+    st.matched = 0;
+    uint32_t cp = 0;
+    if (R.kind == NORM_CHARSMAP) {
+        uint32_t value = 0;
+        const int m = charsmap_longest(R, s, i, e, value);
+        if (m > 0) {
+            int l = 0;
+            if (value < R.n_normalized) while (value + (uint32_t)l < R.n_normalized && R.normalized[value + l]) ++l;
+            st.consumed = m; st.olen = l; st.src = (int32_t)value;
+            return st;
+        }
+        const int l = utf8_strict_len(s, i, e, cp);
+        if (l == 0) { st.consumed = 1; st.olen = 3; st.src = -3; }
+        else { st.consumed = l; st.olen = l; st.src = -2; }
+        return st;
+    }
+    // malformed bytes never match and pass through one at a time (PCRE2 runs with NO_UTF_CHECK: out of contract)
+    const int l = utf8_strict_len(s, i, e, cp);
+    st.consumed = l ? l : 1;
+    st.olen = st.consumed;
+    st.src = -2;
+    if (!l || (R.anchored && i != b) || (!R.global && first_done)) return st;
+    bool in_class;
+    if (R.any) in_class = true;
+    else if (R.literal_cp >= 0) in_class = cp == (uint32_t)R.literal_cp;
+    else {
+        const uint8_t f = cp < 0x80 ? R.cls.ascii[cp] : R.cls.stage2[(uint32_t)R.cls.stage1[cp >> 8] * 256u + (cp & 255u)];
+        in_class = (f & R.mask) != 0;
+    }
+    if (in_class == (R.negate != 0)) return st;
+    st.matched = 1;
+    st.src = -1;
+    st.olen = (int32_t)R.pre_len + (R.keep ? l : 0) + (int32_t)R.post_len;
+    return st;
+}
+
+// Writes the step's output bytes.
+B2_HD void norm_emit(const NormRule& R, const NormStep& st, const uint8_t* s, int i, uint8_t* out) {
+    if (st.src >= 0) { for (int k = 0; k < st.olen; ++k) out[k] = R.normalized[st.src + k]; }
+    else if (st.src == -2) { for (int k = 0; k < st.olen; ++k) out[k] = s[i + k]; }
+    else if (st.src == -3) { out[0] = 0xEF; out[1] = 0xBF; out[2] = 0xBD; }
+    else {
+        int o = 0;
+        for (int k = 0; k < R.pre_len; ++k) out[o++] = R.pre[k];
+        if (R.keep) for (int k = 0; k < st.consumed; ++k) out[o++] = s[i + k];
+        for (int k = 0; k < R.post_len; ++k) out[o++] = R.post[k];
+    }
+}
+
+// Sequential scan of one string (host tests; the kernel does the same 32 positions at a time).  Returns the output length;
+// writes when out != nullptr.
+B2_HD int norm_string(const NormRule& R, const uint8_t* s, int b, int e, uint8_t* out) {
+    int o = 0;
+    bool done = false;
+    for (int i = b; i < e;) {
+        const NormStep st = norm_eval(R, s, b, i, e, done);
+        if (out) norm_emit(R, st, s, i, out + o);
+        done = done || st.matched;
+        o += st.olen;
+        i += st.consumed;
+    }
+    return o;
+}
+
 }  // namespace b200tok

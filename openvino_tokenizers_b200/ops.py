@@ -506,3 +506,84 @@ def split_wordpiece(split1: RegexSplit, split2, wp: WordpieceTokenizer, inputs, 
     K.check(K.lib().b200tok_split_wordpiece_run(split1.handle, split2.handle if split2 is not None else None, wp.handle,
                                                 C.byref(rin), C.c_int32(int(unk_token_id)), C.byref(out), None))
     return [ob, oe, ids[:out.n_ids].copy()]
+
+
+class _Normalizer(_Handle):
+    """Shared evaluate of the normalisers (reference evaluate_normalization_helper, src/utils.cpp:178-234):
+    inputs strings [0..2] (+ skips [3] when `has_skips`); outputs strings (+ the skips tensor unchanged)."""
+
+    device = 0
+    _expand = 4
+
+    def _run(self, inputs, has_skips):
+        b, e, c = _i32(inputs[0]).reshape(-1), _i32(inputs[1]).reshape(-1), _u8(inputs[2]).reshape(-1)
+        sk = np.ascontiguousarray(inputs[3], np.uint8).reshape(-1) if has_skips else None
+        n = len(b)
+        ob, oe = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+        cap = int(self._expand * c.size) + 64
+        for _ in range(2):
+            oc = np.zeros(max(cap, 1), np.uint8)
+            got = C.c_int64(0)
+            rc = K.lib().b200tok_normalize_run(self._h, _ptr(b), _ptr(e), C.c_int64(n), _ptr(c) if c.size else None, C.c_int64(c.size),
+                                               _ptr(sk) if sk is not None and n else None, _ptr(ob), _ptr(oe), _ptr(oc), C.c_int64(cap),
+                                               C.byref(got), K.MEM_HOST, None)
+            if rc == K.E_CAPACITY and got.value > cap:      # the call reports the size it needs
+                cap = got.value
+                continue
+            K.check(rc)
+            break
+        shape = np.asarray(inputs[0]).shape
+        out = [ob[:n].copy().reshape(shape), oe[:n].copy().reshape(shape), oc[:got.value].copy()]
+        if has_skips:
+            out.append(inputs[3])
+        return out
+
+
+class RegexNormalization(_Normalizer):
+    """RegexNormalization(global_replace): inputs strings [0..2], optional skips [3], then search pattern and replace
+    pattern as u8 strings (reference src/regex_normalization.cpp:59-153).  The handle is built from the pattern inputs
+    on the first evaluate, like the reference's lazily compiled PCRE2 object; patterns outside the single-character set
+    raise B200TokError(E_UNSUPPORTED)."""
+
+    def __init__(self, global_replace=True, device=0):
+        super().__init__()
+        self.global_replace, self.device = bool(global_replace), device
+        self._key = None
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (5, 6):
+            raise ValueError(f"supported input sizes are 5 or 6, got {len(inputs)}")
+        has_skips = len(inputs) == 6
+        search, replace = _as_text(inputs[3 + has_skips]).encode(), _as_text(inputs[4 + has_skips]).encode()
+        if self._key != (search, replace):
+            self.close()
+            K.check(K.lib().b200tok_regexnorm_create(search, C.c_int64(len(search)), replace, C.c_int64(len(replace)),
+                                                     int(self.global_replace), self.device, C.byref(self._h)))
+            self._key = (search, replace)
+            self._expand = 2 + len(replace)
+        return self._run(inputs, has_skips)
+
+
+class CharsMapNormalization(_Normalizer):
+    """CharsMapNormalization: inputs strings [0..2], optional skips, then the precompiled charsmap (u8) — the 4/5-input
+    form of the reference op (src/charsmap_normalization.cpp:13-69).  For the attribute form (`normalization_form`,
+    `case_fold`) the caller passes the blob the reference's get_precompiled_charsmap() returns as `precompiled_charsmap`."""
+
+    def __init__(self, precompiled_charsmap=None, add_dummy_prefix=False, remove_extra_whitespaces=False, escape_whitespaces=False, device=0):
+        super().__init__()
+        self.flags = (bool(add_dummy_prefix), bool(remove_extra_whitespaces), bool(escape_whitespaces))
+        self.device = device
+        self._blob = None if precompiled_charsmap is None else bytes(precompiled_charsmap)
+        self._built = None
+        self._expand = 20
+
+    def evaluate(self, inputs):
+        if len(inputs) not in (3, 4, 5):
+            raise ValueError("CharsMapNormalization supports input sizes 3, 4 or 5.")
+        has_skips = len(inputs) == 5 or (self._blob is not None and len(inputs) == 4)     # charsmap_normalization.cpp:35
+        blob = self._blob if self._blob is not None else bytes(_u8(inputs[3 + has_skips]).reshape(-1).tobytes())
+        if self._built != blob:
+            self.close()
+            K.check(K.lib().b200tok_charsmap_create(blob, C.c_int64(len(blob)), *[int(f) for f in self.flags], self.device, C.byref(self._h)))
+            self._built = blob
+        return self._run(inputs, has_skips)

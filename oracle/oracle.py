@@ -18,7 +18,7 @@ _LIB_PATH = _HERE / "liboracle.so"
 
 __all__ = [
     "build", "lib", "pcre2_available", "BpeOracle", "WordpieceOracle", "SplitOracle", "VocabEncoderOracle",
-    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense", "SpecialTokensSplitOracle", "special_tokens_pattern", "bytes_to_chars", "chars_to_bytes", "fuze_ragged", "utf8_validate",
+    "vocab_decoder", "byte_fallback", "truncate", "combine_segments", "ragged_to_dense", "SpecialTokensSplitOracle", "special_tokens_pattern", "bytes_to_chars", "chars_to_bytes", "fuze_ragged", "utf8_validate", "regex_normalize", "charsmap_normalize",
 ]
 
 
@@ -365,3 +365,32 @@ def utf8_validate(begins, ends, chars, replace_mode):
     n = lib().orc_utf8_validate(_p(begins, _i32p), _p(ends, _i32p), C.c_int64(len(begins)), _p(chars, _u8p), int(bool(replace_mode)),
                                 _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p))
     return ob, oe, oc[:n].copy()
+
+
+def _normalize_call(fn, head, begins, ends, chars, skips, expand):
+    begins, ends, chars = _i32(begins), _i32(ends), _u8(chars)
+    sk = None if skips is None else np.ascontiguousarray(skips, np.uint8)
+    n = len(begins)
+    ob, oe = np.empty(n, np.int32), np.empty(n, np.int32)
+    cap = int(expand * max(int((ends - begins).clip(min=0).sum()), 0)) + 64 * n + 64
+    oc = np.zeros(cap, np.uint8)
+    fn.restype = C.c_int64
+    total = fn(*head, _p(begins, _i32p), _p(ends, _i32p), _p(chars, _u8p), None if sk is None else _p(sk, _u8p), C.c_int64(n),
+               _p(ob, _i32p), _p(oe, _i32p), _p(oc, _u8p), C.c_int64(cap))
+    assert total <= cap
+    return ob, oe, oc[:total].copy()
+
+
+def regex_normalize(search_pattern, replace_pattern, global_replace, begins, ends, chars, skips=None):
+    """RegexNormalization (reference src/regex_normalization.cpp:127-153) through PCRE2's own pcre2_substitute."""
+    sp = search_pattern.encode() if isinstance(search_pattern, str) else bytes(search_pattern)
+    rp = replace_pattern.encode() if isinstance(replace_pattern, str) else bytes(replace_pattern)
+    head = (sp, C.c_int64(len(sp)), rp, C.c_int64(len(rp)), int(bool(global_replace)))
+    return _normalize_call(lib().orc_regex_normalize, head, begins, ends, chars, skips, 4 + 4 * len(rp))
+
+
+def charsmap_normalize(blob, begins, ends, chars, skips=None, add_dummy_prefix=False, remove_extra_whitespaces=False, escape_whitespaces=False):
+    """CharsMapNormalization (reference src/charsmap_normalization.cpp:34-69): sentencepiece Normalizer over a precompiled charsmap."""
+    blob = bytes(blob)
+    head = (blob, C.c_int64(len(blob)), int(add_dummy_prefix), int(remove_extra_whitespaces), int(escape_whitespaces))
+    return _normalize_call(lib().orc_charsmap_normalize, head, begins, ends, chars, skips, 20)

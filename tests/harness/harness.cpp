@@ -299,3 +299,30 @@ HZ int64_t hz_special_split(const char* pattern, int64_t plen, const uint8_t* ch
     });
     return k;
 }
+
+
+// Normalisers on the host: the product's pattern / blob parsers (tables.cpp) + the sequential scan of tok_core.cuh over
+// each element.  kind 0: RegexNormalization (a = search, b = replace, flag = global_replace); kind 1: CharsMapNormalization
+// (a = blob).  Returns the bytes produced (< 0: the parser's error code).
+HZ int64_t hz_normalize(int kind, const uint8_t* a, int64_t alen, const uint8_t* b, int64_t blen, int flag, const int32_t* begins,
+                        const int32_t* ends, const uint8_t* chars, const uint8_t* skips, int64_t n, int32_t* ob, int32_t* oe, uint8_t* oc,
+                        int64_t cap) {
+    HostNorm hn;
+    std::string err;
+    const int rc = kind == 0 ? parse_regex_norm((const char*)a, alen, (const char*)b, blen, flag, hn, err) : parse_charsmap(a, alen, 0, 0, 0, hn, err);
+    if (rc) return rc;
+    NormRule R = hn.rule;
+    R.cls = host_norm_class_tables().view();
+    R.units = hn.units.data(); R.n_units = (uint32_t)hn.units.size();
+    R.normalized = hn.normalized.data(); R.n_normalized = (uint32_t)hn.normalized.size();
+    int64_t cur = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        ob[i] = (int32_t)cur;
+        int l;
+        if (skips && skips[i]) { l = ends[i] - begins[i]; if (cur + l <= cap) std::memcpy(oc + cur, chars + begins[i], (size_t)l); }
+        else { l = norm_string(R, chars, begins[i], ends[i], nullptr); if (cur + l <= cap) norm_string(R, chars, begins[i], ends[i], oc + cur); }
+        cur += l;
+        oe[i] = (int32_t)cur;
+    }
+    return cur;
+}

@@ -154,3 +154,22 @@ def special_split(pattern: str, data: bytes):
     if n < 0:
         raise ValueError(f"hz_special_split error {n}")
     return list(zip(ob[:n].tolist(), oe[:n].tolist(), osk[:n].tolist()))
+
+
+def hz_normalize(kind, a, b, flag, begins, ends, chars, skips=None, expand=24):
+    """Normalise strings with the product's host-compiled parser + scan.  kind 0: RegexNormalization(a=search, b=replace,
+    flag=global_replace); kind 1: CharsMapNormalization(a=blob).  Returns (begins, ends, chars); raises ValueError(code)."""
+    begins, ends = np.ascontiguousarray(begins, np.int32), np.ascontiguousarray(ends, np.int32)
+    chars = np.ascontiguousarray(chars, np.uint8) if len(chars) else np.zeros(1, np.uint8)
+    sk = None if skips is None else np.ascontiguousarray(skips, np.uint8)
+    n = len(begins)
+    cap = expand * int(chars.size) + 64 * n + 64
+    ob, oe, oc = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32), np.zeros(cap, np.uint8)
+    a, b = bytes(a), bytes(b)
+    lib().hz_normalize.restype = C.c_int64
+    t = lib().hz_normalize(int(kind), a, C.c_int64(len(a)), b, C.c_int64(len(b)), int(flag), begins.ctypes.data_as(K.i32p),
+                           ends.ctypes.data_as(K.i32p), chars.ctypes.data_as(K.u8p), None if sk is None else sk.ctypes.data_as(K.u8p),
+                           C.c_int64(n), ob.ctypes.data_as(K.i32p), oe.ctypes.data_as(K.i32p), oc.ctypes.data_as(K.u8p), C.c_int64(cap))
+    if t < 0:
+        raise ValueError(int(t))
+    return ob[:n], oe[:n], oc[:t].copy()

@@ -8,6 +8,8 @@
   post_ops_layer_tests.json     the reference's known-answer vectors for RaggedToDense and CombineSegments
                                 (tests/layer_tests.py:497-644)
   special_tokens_split_layer_tests.json  the reference's known-answer vectors for SpecialTokensSplit (tests/layer_tests.py:405-457)
+  normalization_layer_tests.json  RegexNormalization / case-fold known-answer vectors (tests/layer_tests.py:226-290) and the
+                                normaliser pattern set of the converter
   shim_ops_layer_tests.json     UTF8Validate known-answer strings (tests/layer_tests.py:84-139) and the byte -> char table
   hf_<vocab>.json               ids produced by HuggingFace `tokenizers` for the frozen synthetic vocabularies
                                 (second oracle; the reference reports 100 % agreement with HF for these families)
@@ -210,9 +212,45 @@ def make_hf_golden():
     print("bert_synth", len(btexts), "texts")
 
 
+def make_norm_golden():
+    """RegexNormalization known-answer vectors (reference tests/layer_tests.py:253-290): the parametrize list is evaluated
+    against the reference's own RegexNormalizationStep dataclass (its classmethods define the patterns); the case-fold
+    vectors (:226-250, utf-8 rows).  Also records the pattern set of the BERT normaliser (hf_parser.py:84-102)."""
+    src = (REF / "python/openvino_tokenizers/tokenizer_pipeline.py").read_text()
+    a = src.index("@dataclass\nclass RegexNormalizationStep")
+    b = src.index("    def get_ov_subgraph", a)
+    ns = {"dataclass": dataclass, "field": field, "NormalizationStep": object}
+    exec(src[a:b], ns)
+    Step = ns["RegexNormalizationStep"]
+    lt = (REF / "tests/layer_tests.py").read_text()
+    tree = ast.parse(lt)
+    regex_cases, casefold = [], []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "test_regex_normalization":
+            for text, expected, layer in eval(compile(ast.Expression(node.decorator_list[0].args[1]), "layer_tests", "eval"), {"RegexNormalizationStep": Step}):
+                regex_cases.append(dict(text=text, expected=expected, search=layer.regex_search_pattern, replace=layer.replace_term,
+                                        global_replace=layer.global_replace))
+        if isinstance(node, ast.FunctionDef) and node.name == "test_casefold_normalization":
+            for text, expected, is_utf8 in eval(compile(ast.Expression(node.decorator_list[0].args[1]), "layer_tests", "eval"), {}):
+                if is_utf8:
+                    casefold.append(dict(text=text, expected=expected))
+    bert = [dict(name=n, search=getattr(Step, n)().regex_search_pattern, replace=getattr(Step, n)().replace_term,
+                 global_replace=getattr(Step, n)().global_replace)
+            for n in ("del_control_chars_regex", "replace_whitespace_regex", "handle_chinese_chars_regex", "strip_accents_regex")]
+    other = [dict(name=n, search=getattr(Step, n)().regex_search_pattern, replace=getattr(Step, n)().replace_term,
+                  global_replace=getattr(Step, n)().global_replace)
+             for n in ("add_prefix_whitespace_regex", "add_prefix_whitespace_to_not_whitespace_regex", "replace_spaces_metaspace")]
+    p = Step.prepend_regex("\u2581")
+    other.append(dict(name="prepend_regex", search=p.regex_search_pattern, replace=p.replace_term, global_replace=p.global_replace))
+    (GOLDEN / "normalization_layer_tests.json").write_text(json.dumps(
+        dict(source="reference tests/layer_tests.py:226-290, python/openvino_tokenizers/tokenizer_pipeline.py:223-278",
+             regex_normalization=regex_cases, casefold_utf8=casefold, bert_steps=bert, other_steps=other), ensure_ascii=False, indent=1))
+    print("regex normalization cases", len(regex_cases), "casefold", len(casefold), "steps", len(bert) + len(other))
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
-    which = sys.argv[1:] or ["regex", "hf", "post", "special", "shim"]
+    which = sys.argv[1:] or ["regex", "hf", "post", "special", "shim", "norm"]
     if "regex" in which:
         make_regex_golden()
     if "hf" in which:
@@ -223,3 +261,5 @@ if __name__ == "__main__":
         make_special_golden()
     if "shim" in which:
         make_shim_golden()
+    if "norm" in which:
+        make_norm_golden()
