@@ -1641,12 +1641,13 @@ struct NormObj : b200tok_object {
     HostNorm h;
     DevClassTables ncls;
     DBuf<uint32_t> units;
-    DBuf<uint8_t> normalized;
+    DBuf<uint8_t> normalized, atab;
     NormRule view() const {
         NormRule r = h.rule;
         r.cls = ncls.view();
         r.units = units.p; r.n_units = (uint32_t)h.units.size();
         r.normalized = normalized.p; r.n_normalized = (uint32_t)h.normalized.size();
+        r.atab = atab.p;
         return r;
     }
 };
@@ -1657,6 +1658,7 @@ int finish_norm(std::unique_ptr<NormObj>& o, int device, b200tok_handle* out) {
     if (o->h.rule.kind == NORM_CLASS) CU(o->ncls.upload(host_norm_class_tables()));
     CU(o->units.upload(o->h.units));
     CU(o->normalized.upload(o->h.normalized));
+    CU(o->atab.upload(o->h.atab));
     CU(cudaDeviceSynchronize());
     *out = o.release();
     return B200TOK_OK;

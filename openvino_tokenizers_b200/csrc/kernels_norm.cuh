@@ -41,9 +41,50 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
         for (int c0 = b; c0 < e; c0 += 32) {
             if (cur >= c0 + 32) continue;
             const int pos = c0 + lane;
+            const bool valid = pos < e && pos >= cur;
+            const uint32_t byte = pos < e ? chars[pos] : 0u;
             NormStep st;
             st.consumed = 32; st.olen = 0; st.src = -2; st.matched = 0;
-            if (pos < e && pos >= cur) st = norm_eval(R, chars, b, pos, e, done);
+            // ---- a chunk of ASCII bytes: every byte is a step of its own, straight from the per-byte tables ----
+            bool fast = __ballot_sync(FULL, byte >= 0x80u) == 0u;
+            uint32_t mapped = byte;
+            if (fast) {
+                const uint32_t fl = __ldg(R.atab + 128 + byte);
+                if (R.kind == NORM_CHARSMAP) {
+                    mapped = __ldg(R.atab + byte);
+                    bool slow = (fl & (NA_COMPLEX | NA_ASCII_KIDS)) != 0;
+                    if (lane == 31 && (fl & NA_OTHER_KIDS) && pos + 1 < e && chars[pos + 1] >= 0x80u) slow = true;   // a rule may run into the next chunk
+                    fast = __ballot_sync(FULL, valid && slow) == 0u;
+                } else {
+                    const bool in_class = R.any || (R.literal_cp >= 0 ? (int32_t)byte == R.literal_cp : (fl & R.mask) != 0);
+                    st.matched = valid && in_class != (R.negate != 0) && (!R.anchored || pos == b) && (R.global || !done);
+                }
+            }
+            if (fast) {
+                uint32_t hits = R.kind == NORM_CLASS ? __ballot_sync(FULL, st.matched) : 0u;
+                if (hits && !R.global) {                 // only the first match of the string is replaced
+                    done = true;
+                    st.matched = st.matched && lane == __ffs(hits) - 1;
+                    hits &= 0u - hits;
+                }
+                const uint32_t vmask = __ballot_sync(FULL, valid);
+                if (!hits) {                             // nothing changes length: byte k goes to slot k
+                    if (WRITE && valid) out[o0 + o + __popc(vmask & ((1u << lane) - 1u))] = (uint8_t)mapped;
+                    o += __popc(vmask);
+                } else {
+                    st.consumed = 1; st.src = st.matched ? -1 : -2;
+                    st.olen = st.matched ? (int32_t)R.pre_len + (R.keep ? 1 : 0) + (int32_t)R.post_len : 1;
+                    int incl = valid ? st.olen : 0;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+                    if (WRITE && valid) norm_emit(R, st, chars, pos, out + o0 + o + (incl - st.olen));
+                    o += __shfl_sync(FULL, incl, 31);
+                }
+                cur = c0 + 32;
+                continue;
+            }
+            st.matched = 0;
+            if (valid) st = norm_eval(R, chars, b, pos, e, done);
             // which lanes does the scan visit?  J = where the scan goes after this lane (>= 32: leaves the chunk),
             // M = lanes visited from here; doubling composes them.
             int J = lane + st.consumed;

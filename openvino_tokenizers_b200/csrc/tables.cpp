@@ -164,6 +164,8 @@ int parse_regex_norm(const char* search, int64_t slen, const char* replace, int6
     }
     if (pre.size() > sizeof(R.pre) || post.size() > sizeof(R.post)) { err = "RegexNormalization: replacement literal longer than 16 bytes"; return B200TOK_E_UNSUPPORTED; }
     R.keep = seen_char;
+    out.atab.assign(256, 0);
+    for (int a = 0; a < 128; ++a) { out.atab[(size_t)a] = (uint8_t)a; out.atab[128 + (size_t)a] = host_norm_class_tables().ascii[(size_t)a]; }
     R.pre_len = (uint8_t)pre.size(); R.post_len = (uint8_t)post.size();
     std::memcpy(R.pre, pre.data(), pre.size());
     std::memcpy(R.post, post.data(), post.size());
@@ -181,6 +183,8 @@ int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int r
     R.kind = NORM_CHARSMAP;
     R.literal_cp = -1;
     out.units.clear(); out.normalized.clear();
+    out.atab.assign(256, 0);
+    for (int a = 0; a < 128; ++a) out.atab[(size_t)a] = (uint8_t)a;
     if (len == 0) return B200TOK_OK;                    // empty charsmap = identity (with U+FFFD for malformed bytes)
     uint32_t tsz = 0;
     if (len < 4) { err = "CharsMapNormalization: charsmap blob is truncated"; return B200TOK_E_INVALID; }
@@ -189,6 +193,28 @@ int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int r
     out.units.resize(tsz / 4);
     std::memcpy(out.units.data(), blob + 4, tsz);
     out.normalized.assign(blob + 4 + tsz, blob + len);
+    // ASCII shortcuts: what the rule starting with byte a does, and whether longer rules start with it
+    const std::vector<uint32_t>& U = out.units;
+    auto offset = [](uint32_t u) { return (u >> 10) << ((u & (1u << 9)) >> 6); };
+    auto label = [](uint32_t u) { return u & ((1u << 31) | 0xFFu); };
+    const uint32_t root = offset(U[0]);
+    for (uint32_t a = 0; a < 128; ++a) {
+        uint32_t pos = root ^ a;
+        if (pos >= U.size() || label(U[pos]) != a) continue;            // no rule starts with a
+        const uint32_t u = U[pos];
+        pos ^= offset(u);
+        uint8_t fl = 0;
+        if ((u >> 8) & 1u) {
+            const uint32_t v = pos < U.size() ? (U[pos] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+            if (v + 1 < out.normalized.size() && out.normalized[v] && out.normalized[v] < 0x80 && out.normalized[v + 1] == 0) out.atab[a] = out.normalized[v];
+            else fl |= NA_COMPLEX;
+        }
+        for (uint32_t c = 1; c < 256; ++c) {
+            const uint32_t q = pos ^ c;
+            if (q < U.size() && label(U[q]) == c) fl |= c < 0x80 ? NA_ASCII_KIDS : NA_OTHER_KIDS;
+        }
+        out.atab[128 + a] = fl;
+    }
     return B200TOK_OK;
 }
 

@@ -109,6 +109,7 @@ struct HostNorm {
     NormRule rule{};
     std::vector<uint32_t> units;
     std::vector<uint8_t> normalized;
+    std::vector<uint8_t> atab;       // [0,128) amap, [128,256) aflag (NormRule::atab)
 };
 int parse_regex_norm(const char* search, int64_t slen, const char* replace, int64_t rlen, int global_replace, HostNorm& out, std::string& err);
 int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int remove_extra_whitespaces, int escape_whitespaces, HostNorm& out, std::string& err);

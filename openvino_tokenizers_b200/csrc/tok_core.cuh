@@ -1056,7 +1056,13 @@ struct NormRule {
     uint32_t n_units;
     const uint8_t* normalized;
     uint32_t n_normalized;
+    // per-ASCII-byte shortcuts (a chunk of 32 ASCII bytes skips the general step): NORM_CLASS: aflag = the byte's NC_* flags;
+    // NORM_CHARSMAP: amap = the byte it maps to when the rule for it is "one ASCII byte -> one ASCII byte" (or none), aflag =
+    // NA_* reasons why the byte needs the trie walk
+    // (divergent indices: the table lives in global memory, not in the parameter block)
+    const uint8_t* atab;     // [0,128) amap, [128,256) aflag
 };
+enum : uint8_t { NA_COMPLEX = 1, NA_ASCII_KIDS = 2, NA_OTHER_KIDS = 4 };   // replacement not 1 ASCII byte / longer rules continue with an ASCII / non-ASCII byte
 
 struct NormStep {
     int32_t consumed;    // input bytes

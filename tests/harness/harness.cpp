@@ -315,6 +315,7 @@ HZ int64_t hz_normalize(int kind, const uint8_t* a, int64_t alen, const uint8_t*
     R.cls = host_norm_class_tables().view();
     R.units = hn.units.data(); R.n_units = (uint32_t)hn.units.size();
     R.normalized = hn.normalized.data(); R.n_normalized = (uint32_t)hn.normalized.size();
+    R.atab = hn.atab.data();
     int64_t cur = 0;
     for (int64_t i = 0; i < n; ++i) {
         ob[i] = (int32_t)cur;
@@ -325,4 +326,33 @@ HZ int64_t hz_normalize(int kind, const uint8_t* a, int64_t alen, const uint8_t*
         oe[i] = (int32_t)cur;
     }
     return cur;
+}
+
+
+// Consistency of the per-ASCII-byte shortcut tables of a charsmap with the general step: for every ASCII byte a whose
+// flags allow the shortcut, the step at [a, next] must consume 1 byte and emit amap[a].  Returns the number of violations.
+HZ int64_t hz_charsmap_ascii_table_check(const uint8_t* blob, int64_t len) {
+    HostNorm hn;
+    std::string err;
+    if (parse_charsmap(blob, len, 0, 0, 0, hn, err)) return -1;
+    NormRule R = hn.rule;
+    R.units = hn.units.data(); R.n_units = (uint32_t)hn.units.size();
+    R.normalized = hn.normalized.data(); R.n_normalized = (uint32_t)hn.normalized.size();
+    int64_t bad = 0;
+    const uint8_t tails[][3] = {{0xCC, 0x81, 0}, {0xCC, 0x8A, 0}, {0xE3, 0x82, 0x99}, {0xD6, 0xBC, 0}};
+    for (int a = 0; a < 128; ++a) {
+        const uint8_t aflag = hn.atab[128 + (size_t)a], amap = hn.atab[(size_t)a];
+        if (aflag & (NA_COMPLEX | NA_ASCII_KIDS)) continue;
+        for (int nx = 0; nx < 128 + 4; ++nx) {
+            uint8_t s[4] = {(uint8_t)a, 0, 0, 0};
+            int n = 2;
+            if (nx < 128) s[1] = (uint8_t)nx;
+            else { if (aflag & NA_OTHER_KIDS) continue; std::memcpy(s + 1, tails[nx - 128], 3); n = tails[nx - 128][2] ? 4 : 3; }
+            const NormStep st = norm_eval(R, s, 0, 0, n, false);
+            uint8_t out[64] = {0};
+            if (st.olen <= 64) norm_emit(R, st, s, 0, out);
+            if (st.consumed != 1 || st.olen != 1 || out[0] != amap) ++bad;
+        }
+    }
+    return bad;
 }

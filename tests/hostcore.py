@@ -173,3 +173,10 @@ def hz_normalize(kind, a, b, flag, begins, ends, chars, skips=None, expand=24):
     if t < 0:
         raise ValueError(int(t))
     return ob[:n], oe[:n], oc[:t].copy()
+
+
+def hz_charsmap_ascii_table_check(blob):
+    """Violations of the ASCII shortcut tables of a charsmap against the general step (0 = consistent)."""
+    blob = bytes(blob)
+    lib().hz_charsmap_ascii_table_check.restype = C.c_int64
+    return int(lib().hz_charsmap_ascii_table_check(blob, C.c_int64(len(blob))))

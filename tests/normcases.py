@@ -58,6 +58,35 @@ def unicodedata_blob(form=None, case_fold=False, limit=0x30000):
     return _cache[key]
 
 
+def custom_blob():
+    """Rules that stress the ASCII shortcuts: ASCII -> ASCII, ASCII -> multi-byte, ASCII sequences, ASCII + mark, deletions."""
+    key = ("custom",)
+    if key not in _cache:
+        rules = [("41", "61"), ("42", "C9"), ("43 44", "78"), ("45 301", "C9"), ("46", "66 66"), ("71", ""), ("20 20", "20"),
+                 ("7A 7A 7A", "5A"), ("C9", "65"), ("301", ""), ("31", "32"), ("32", "31")]
+        with tempfile.TemporaryDirectory() as d:
+            p = Path(d) / "rules.tsv"
+            p.write_text("".join(f"{a}\t{b}\n" for a, b in rules))
+            _cache[key] = _train_blob(normalization_rule_tsv=str(p))
+    return _cache[key]
+
+
+def ascii_corpus(seed=7, n=400, max_len=200):
+    """ASCII-only strings (the kernels' fast chunks), with tabs / controls, lengths around the 32-byte chunk size, and a
+    sprinkle of strings whose only non-ASCII character sits right after a chunk boundary."""
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        ln = rng.choice([0, 1, 31, 32, 33, 63, 64, 65, rng.randint(0, max_len)])
+        s = bytearray(rng.choice(b"ABCDEFzzq  12 \t\x01abcdefghijklmnop") for _ in range(ln))
+        if i % 5 == 0 and ln >= 32:
+            s[32:32] = "\u0301".encode()
+        elif i % 7 == 0 and ln >= 33:          # (never both: the strings stay well-formed UTF-8)
+            s[31:33] = b"E" + "\u0301".encode()
+        out.append(bytes(s))
+    return out
+
+
 def sp_normalizer(blob, add_dummy_prefix=False, remove_extra_whitespaces=False, escape_whitespaces=False):
     """The real sentencepiece Normalizer over a blob (what CharsMapNormalization::evaluate calls)."""
     import sentencepiece as spm

@@ -78,16 +78,23 @@ def test_host_regex_scan_vs_pcre2(step):
     assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()
 
 
-@pytest.mark.parametrize("which", ["nfkc_cf", "nfd_cf", "nfd", "casefold", "empty"])
+@pytest.mark.parametrize("which", ["nfkc_cf", "nfd_cf", "nfd", "casefold", "empty", "custom"])
 def test_host_charsmap_scan_vs_oracle(which):
     import hostcore
-    blob = {"nfkc_cf": lambda: NC.builtin_blob("nfkc_cf"), "nfd_cf": lambda: NC.unicodedata_blob("NFD", True), "nfd": lambda: NC.unicodedata_blob("NFD", False),
+    blob = {"custom": NC.custom_blob, "nfkc_cf": lambda: NC.builtin_blob("nfkc_cf"), "nfd_cf": lambda: NC.unicodedata_blob("NFD", True), "nfd": lambda: NC.unicodedata_blob("NFD", False),
             "casefold": lambda: NC.unicodedata_blob(None, True), "empty": lambda: b""}[which]()
     raw = NC.corpus(seed=4, n=800, malformed=200)
     b, e, c = NC.pack(raw)
     exp = oracle.charsmap_normalize(blob, b, e, c)
     got = hostcore.hz_normalize(1, blob, b"", 0, b, e, c)
     assert NC.unpack(*got) == NC.unpack(*exp)
+
+
+def test_charsmap_ascii_shortcut_tables_agree_with_the_trie():
+    import hostcore
+    for blob in (NC.builtin_blob("nfkc"), NC.builtin_blob("nfkc_cf"), NC.builtin_blob("nmt_nfkc_cf"), NC.unicodedata_blob("NFD", True),
+                 NC.unicodedata_blob("NFC", False), NC.unicodedata_blob(None, True), NC.custom_blob()):
+        assert hostcore.hz_charsmap_ascii_table_check(blob) == 0
 
 
 @pytest.mark.parametrize("search,replace", UNSUPPORTED)
@@ -122,7 +129,7 @@ def _strings_in(raw):
 @pytest.mark.parametrize("step", STEPS, ids=lambda s: s["name"])
 def test_gpu_regex_normalization_vs_oracle(step):
     from openvino_tokenizers_b200 import ops
-    raw = NC.corpus(seed=21, n=3000, max_len=90)
+    raw = NC.corpus(seed=21, n=3000, max_len=90) + NC.ascii_corpus(seed=24, n=600)
     ins = _strings_in(raw)
     skips = (np.arange(len(raw)) % 5 == 1)
     op = ops.RegexNormalization(step["global_replace"])
@@ -157,12 +164,12 @@ def test_gpu_regex_normalization_reference_vectors():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["nfkc_cf", "nmt_nfkc", "nfd_cf", "nfd", "casefold", "empty"])
+@pytest.mark.parametrize("which", ["nfkc_cf", "nmt_nfkc", "nfd_cf", "nfd", "nfc", "casefold", "empty", "custom"])
 def test_gpu_charsmap_normalization_vs_oracle(which):
     from openvino_tokenizers_b200 import ops
-    blob = {"nfkc_cf": lambda: NC.builtin_blob("nfkc_cf"), "nmt_nfkc": lambda: NC.builtin_blob("nmt_nfkc"), "nfd_cf": lambda: NC.unicodedata_blob("NFD", True),
+    blob = {"custom": NC.custom_blob, "nfc": lambda: NC.unicodedata_blob("NFC", False), "nfkc_cf": lambda: NC.builtin_blob("nfkc_cf"), "nmt_nfkc": lambda: NC.builtin_blob("nmt_nfkc"), "nfd_cf": lambda: NC.unicodedata_blob("NFD", True),
             "nfd": lambda: NC.unicodedata_blob("NFD", False), "casefold": lambda: NC.unicodedata_blob(None, True), "empty": lambda: b""}[which]()
-    raw = NC.corpus(seed=22, n=3000, malformed=600, max_len=90)
+    raw = NC.corpus(seed=22, n=3000, malformed=600, max_len=90) + NC.ascii_corpus(seed=23, n=600)
     ins = _strings_in(raw)
     skips = (np.arange(len(raw)) % 4 == 2)
     exp = oracle.charsmap_normalize(blob, *ins)
