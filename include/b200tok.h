@@ -361,6 +361,14 @@ B200TOK_API int b200tok_charsmap_create(const uint8_t* precompiled_charsmap, int
 B200TOK_API int b200tok_normalize_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
                                       int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
                                       int64_t chars_capacity, int64_t* n_chars_out, int mem, void* cuda_stream);
+/* The same for a chain of normalisers applied one after the other (handles[0] first) — what the converter emits for one
+ * HF normaliser, e.g. BertNormalizer = del_control_chars, replace_whitespace, handle_chinese_chars, NFD, strip_accents,
+ * case fold (python/openvino_tokenizers/hf_parser.py:84-102 of the reference).  Intermediate strings stay on the device;
+ * skips applies to every op, as in the reference graph where each op passes the tensor on (src/utils.cpp:189-191).       */
+B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n_ops, const int32_t* begins, const int32_t* ends, int64_t n,
+                                            const uint8_t* chars, int64_t n_chars, const uint8_t* skips, int32_t* out_begins,
+                                            int32_t* out_ends, uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars_out, int mem,
+                                            void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -155,5 +155,5 @@ EXPORTED_SYMBOLS = [
     "b200tok_bytefallback_run",
     "b200tok_bytes_to_chars_run", "b200tok_chars_to_bytes_run", "b200tok_fuze_ragged_run", "b200tok_utf8_validate_run",
     "b200tok_truncate_run", "b200tok_combine_segments_run", "b200tok_ragged_to_dense_run", "b200tok_post_dense_run",
-    "b200tok_regexnorm_create", "b200tok_charsmap_create", "b200tok_normalize_run",
+    "b200tok_regexnorm_create", "b200tok_charsmap_create", "b200tok_normalize_run", "b200tok_normalize_chain_run",
 ]

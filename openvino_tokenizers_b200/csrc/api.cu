@@ -1687,48 +1687,70 @@ B200TOK_API int b200tok_charsmap_create(const uint8_t* precompiled_charsmap, int
     return finish_norm(o, device, out);
 }
 
-// evaluate_normalization_helper (src/utils.cpp:178-234): out_begins[0] = 0, strings packed back to back.
-B200TOK_API int b200tok_normalize_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
-                                      int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
-                                      int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
-    NormObj* o = as<NormObj>(h, K_NORM);
-    if (!o) return fail(B200TOK_E_INVALID, "not a normaliser handle");
+// evaluate_normalization_helper (src/utils.cpp:178-234): out_begins[0] = 0, strings packed back to back.  A chain of
+// normalisers (what the converter emits for one HF normaliser, e.g. the six ops of BertNormalizer, hf_parser.py:84-102)
+// runs back to back on the device: the strings cross PCIe once each way, every op writes an exactly sized buffer.
+B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n_ops, const int32_t* begins, const int32_t* ends, int64_t n,
+                                            const uint8_t* chars, int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends,
+                                            uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
+    if (!handles || n_ops < 1 || n_ops > 64) return fail(B200TOK_E_INVALID, "a chain has 1..64 normalisers");
+    for (int k = 0; k < n_ops; ++k) {
+        NormObj* o = as<NormObj>(handles[k], K_NORM);
+        if (!o) return fail(B200TOK_E_INVALID, "handle %d is not a normaliser handle", k);
+        if (o->device != handles[0]->device) return fail(B200TOK_E_INVALID, "the normalisers of a chain must live on one device");
+    }
     if (n < 0 || n_chars < 0 || chars_capacity < 0 || !n_chars_out || (n > 0 && (!begins || !ends || !out_begins || !out_ends))) return fail(B200TOK_E_INVALID, "bad arguments");
     *n_chars_out = 0;
     if (n == 0) return B200TOK_OK;
     if (n > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "more than 2^31 strings in one call");
     const bool host = mem == B200TOK_MEM_HOST;
     if (host) for (int64_t i = 0; i < n; ++i) if (begins[i] < 0 || ends[i] < begins[i] || ends[i] > n_chars) return fail(B200TOK_E_INVALID, "element %lld has a bad extent", (long long)i);
-    DeviceGuard g(o->device);
+    NormObj* first = as<NormObj>(handles[0], K_NORM);
+    DeviceGuard g(first->device);
     cudaStream_t st = (cudaStream_t)stream;
-    AsyncBuf bb, be, bc, bs, blen, bob, boe, boc, bscan, btot;
+    AsyncBuf bb, be, bc, bs, blen, bscan, btot;
     const int32_t *d_b, *d_e; const uint8_t *d_c, *d_s;
     int rc;
     if ((rc = stage_in(bb, begins, n, host, st, d_b)) || (rc = stage_in(be, ends, n, host, st, d_e)) ||
         (rc = stage_in(bc, chars, n_chars, host, st, d_c)) || (rc = stage_in(bs, skips, skips ? n : 0, host, st, d_s))) return rc;
     CU(blen.alloc((size_t)n * 4, st)); CU(btot.alloc(8, st));
-    int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
-    if (host) { CU(bob.alloc((size_t)n * 4, st)); CU(boe.alloc((size_t)n * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
-    const NormRule R = o->view();
-    const int64_t warps = std::min<int64_t>(n, (int64_t)o->sm_count * 8 * 8);      // 8 CTAs of 8 warps per SM, strings strided over them
+    const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);      // 8 CTAs of 8 warps per SM, strings strided over them
     const unsigned blocks = (unsigned)((warps + 7) / 8);
-    normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), nullptr, nullptr, nullptr, 0, nullptr);
-    if ((rc = scan_i32(bscan, blen.as<int32_t>(), d_ob, n, st))) return rc;
-    normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
-    CU(cudaGetLastError());
-    { std::lock_guard<std::mutex> lock(o->mu); o->launches += 2; }
+    std::unique_ptr<AsyncBuf> ob[2], oe[2], oc[2];        // ping-pong results
     int64_t total = 0;
-    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    *n_chars_out = total;
-    if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
-    if (host) {
-        CU(cudaMemcpyAsync(out_begins, d_ob, n * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(out_ends, d_oe, n * 4, cudaMemcpyDeviceToHost, st));
-        if (total) CU(cudaMemcpyAsync(out_chars, d_oc, total, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < n_ops; ++k) {
+        NormObj* o = as<NormObj>(handles[k], K_NORM);
+        const NormRule R = o->view();
+        const int w = k & 1;
+        ob[w] = std::make_unique<AsyncBuf>(); oe[w] = std::make_unique<AsyncBuf>(); oc[w] = std::make_unique<AsyncBuf>();
+        CU(ob[w]->alloc((size_t)n * 4, st)); CU(oe[w]->alloc((size_t)n * 4, st));
+        normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), nullptr, nullptr, nullptr, 0, nullptr);
+        if ((rc = scan_i32(bscan, blen.as<int32_t>(), ob[w]->as<int32_t>(), n, st))) return rc;
+        normalize_total_kernel<<<1, 1, 0, st>>>(ob[w]->as<int32_t>(), blen.as<int32_t>(), n, btot.as<int64_t>());
+        CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));                    // the size of this op's result
+        if (total > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "normalised text exceeds 2^31 bytes");
+        CU(oc[w]->alloc((size_t)total + 16, st));
+        normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), ob[w]->as<int32_t>(), oe[w]->as<int32_t>(),
+                                                       oc[w]->as<uint8_t>(), total, btot.as<int64_t>());
+        CU(cudaGetLastError());
+        { std::lock_guard<std::mutex> lock(o->mu); o->launches += 3; }
+        d_b = ob[w]->as<int32_t>(); d_e = oe[w]->as<int32_t>(); d_c = oc[w]->as<uint8_t>();
     }
+    *n_chars_out = total;
+    if (total > chars_capacity) { CU(cudaStreamSynchronize(st)); return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total); }
+    const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpyAsync(out_begins, d_b, n * 4, kind, st));
+    CU(cudaMemcpyAsync(out_ends, d_e, n * 4, kind, st));
+    if (total) CU(cudaMemcpyAsync(out_chars, d_c, total, kind, st));
+    CU(cudaStreamSynchronize(st));
     return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_normalize_run(b200tok_handle h, const int32_t* begins, const int32_t* ends, int64_t n, const uint8_t* chars,
+                                      int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends, uint8_t* out_chars,
+                                      int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
+    return b200tok_normalize_chain_run(&h, 1, begins, ends, n, chars, n_chars, skips, out_begins, out_ends, out_chars, chars_capacity, n_chars_out, mem, stream);
 }
 
 }  // extern "C"

@@ -116,4 +116,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
     }
 }
 
+// Size of a result: offset of the last string + its length.
+__global__ void normalize_total_kernel(const int32_t* off, const int32_t* len, int64_t n, int64_t* total) { *total = (int64_t)off[n - 1] + len[n - 1]; }
+
 }  // namespace b200tok

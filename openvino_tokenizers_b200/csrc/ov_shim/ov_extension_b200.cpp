@@ -18,6 +18,9 @@
 #include <vector>
 
 #include "b200tok.h"
+// CharsMapNormalization's attribute form needs the charsmaps the reference generates at build time; the shim is built inside
+// the reference tree, where this header exists (src/precompiled_charsmap.hpp: get_precompiled_charsmap(form, case_fold)).
+#include "precompiled_charsmap.hpp"
 
 namespace b200 {
 
@@ -440,6 +443,115 @@ private:
     bool m_pad_right = true, m_pad_max_length = false;
 };
 
+// ---- RegexNormalization (src/regex_normalization.hpp; evaluate src/regex_normalization.cpp:127-153) and
+// ---- CharsMapNormalization (src/charsmap_normalization.hpp; evaluate src/charsmap_normalization.cpp:34-69) ----------------
+// Both run evaluate_normalization_helper (src/utils.cpp:178-234) through b200tok_normalize_run.
+inline bool run_normalizer(b200tok_handle h, ov::TensorVector& out, const ov::TensorVector& in, bool has_skips, size_t expand) {
+    const size_t n = in[0].get_size(), n_chars = in[2].get_size();
+    out[0].set_shape(in[0].get_shape());
+    out[1].set_shape(in[1].get_shape());
+    if (has_skips) out[3] = in[3];                                          // src/utils.cpp:189-191
+    int64_t produced = 0;
+    size_t cap = expand * n_chars + 64;
+    for (int attempt = 0; attempt < 2; ++attempt) {                         // a too small guess reports the size needed
+        out[2].set_shape({cap});
+        const int rc = b200tok_normalize_run(h, in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)n, in[2].data<const uint8_t>(),
+                                             (int64_t)n_chars, has_skips ? reinterpret_cast<const uint8_t*>(in[3].data<bool>()) : nullptr,
+                                             out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<uint8_t>(), (int64_t)cap, &produced,
+                                             B200TOK_MEM_HOST, nullptr);
+        if (rc == B200TOK_E_CAPACITY && (size_t)produced > cap) { cap = (size_t)produced; continue; }
+        check(rc);
+        break;
+    }
+    out[2].set_shape({(size_t)produced});                                   // src/utils.cpp:223
+    return true;
+}
+
+class RegexNormalization : public ov::op::Op {
+public:
+    OPENVINO_OP("RegexNormalization");
+    RegexNormalization() = default;
+    RegexNormalization(const ov::OutputVector& args, bool global_replace = true) : ov::op::Op(args), m_global_replace(global_replace) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto n = get_input_size();
+        OPENVINO_ASSERT(n == 5 || n == 6, "supported input sizes are 5 or 6, got", n);
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::u8, ov::PartialShape{ov::Dimension()});
+        if (n == 6) set_output_type(3, get_input_element_type(3), get_input_partial_shape(3));
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<RegexNormalization>(in, m_global_replace);
+        c->m_state = m_state;
+        return c;
+    }
+    bool visit_attributes(ov::AttributeVisitor& v) override { v.on_attribute("global_replace", m_global_replace); return true; }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const bool has_skips = in.size() == 6;
+        const auto& sp = in[3 + has_skips];
+        const auto& rp = in[4 + has_skips];
+        std::call_once(m_state->once, [&] {                                // src/regex_normalization.cpp:133-142 (lazy PCRE2 compile)
+            check(b200tok_regexnorm_create(sp.data<const char>(), (int64_t)sp.get_size(), rp.data<const char>(), (int64_t)rp.get_size(),
+                                           m_global_replace, 0, &m_state->h));   // patterns outside the single-character set throw here
+        });
+        return run_normalizer(m_state->h, out, in, has_skips, 2 + rp.get_size());
+    }
+private:
+    bool m_global_replace = true;
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
+class CharsMapNormalization : public ov::op::Op {
+public:
+    OPENVINO_OP("CharsMapNormalization");
+    CharsMapNormalization() = default;
+    CharsMapNormalization(const ov::OutputVector& args, bool add_dummy_prefix = false, bool remove_extra_whitespaces = true, bool escape_whitespaces = false,
+                          bool case_fold = false, const std::string& normalization_form = "", bool nmt = false)
+        : ov::op::Op(args), m_add_dummy_prefix(add_dummy_prefix), m_remove_extra_whitespaces(remove_extra_whitespaces),
+          m_escape_whitespaces(escape_whitespaces), m_case_fold(case_fold), m_normalization_form(normalization_form), m_nmt(nmt) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto n = get_input_size();
+        OPENVINO_ASSERT(n == 3 || n == 4 || n == 5, "CharsMapNormalization supports input sizes 3, 4 or 5.");
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::u8, ov::PartialShape{ov::Dimension()});
+        const bool has_skips = n == 5 || (n == 4 && get_input_element_type(3) == ov::element::boolean);
+        if (has_skips) set_output_type(3, get_input_element_type(3), get_input_partial_shape(3));
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override {
+        auto c = std::make_shared<CharsMapNormalization>(in, m_add_dummy_prefix, m_remove_extra_whitespaces, m_escape_whitespaces, m_case_fold, m_normalization_form, m_nmt);
+        c->m_state = m_state;
+        return c;
+    }
+    bool visit_attributes(ov::AttributeVisitor& v) override {
+        v.on_attribute("add_dummy_prefix", m_add_dummy_prefix); v.on_attribute("remove_extra_whitespaces", m_remove_extra_whitespaces);
+        v.on_attribute("escape_whitespaces", m_escape_whitespaces); v.on_attribute("normalization_form", m_normalization_form);
+        v.on_attribute("case_fold", m_case_fold); v.on_attribute("nmt", m_nmt);
+        return true;
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const bool has_skips = in.size() == 5 || (!m_normalization_form.empty() && in.size() == 4);          // src/charsmap_normalization.cpp:35
+        std::call_once(m_state->once, [&] {                                // :38-59
+            std::string blob;
+            if (!m_normalization_form.empty()) {
+                blob = get_precompiled_charsmap(m_normalization_form, m_case_fold);                      // the reference's generated header (src/precompiled_charsmap.hpp), built with the extension
+                OPENVINO_ASSERT(!blob.empty(), "Unsupported normalization form: `", m_normalization_form, "` with case_fold=", m_case_fold);
+            } else {
+                blob.assign(in[3 + has_skips].data<const char>(), in[3 + has_skips].get_size());
+            }
+            check(b200tok_charsmap_create(reinterpret_cast<const uint8_t*>(blob.data()), (int64_t)blob.size(), m_add_dummy_prefix,
+                                          m_remove_extra_whitespaces, m_escape_whitespaces, 0, &m_state->h));
+        });
+        return run_normalizer(m_state->h, out, in, has_skips, 3);
+    }
+private:
+    bool m_add_dummy_prefix = false, m_remove_extra_whitespaces = true, m_escape_whitespaces = false, m_case_fold = false, m_nmt = false;
+    std::string m_normalization_form;
+    mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
+};
+
 // The byte-level shims (BytesToChars, CharsToBytes, FuzeRagged, UTF8Validate) bind the same way to b200tok_bytes_to_chars_run,
 // b200tok_chars_to_bytes_run, b200tok_fuze_ragged_run and b200tok_utf8_validate_run (worst-case chars 2x / 1x / - / 3x, then shrunk).
 
@@ -458,6 +570,8 @@ OPENVINO_CREATE_EXTENSIONS(std::vector<ov::Extension::Ptr>({
     std::make_shared<ov::OpExtension<b200::Truncate>>(),
     std::make_shared<ov::OpExtension<b200::CombineSegments>>(),
     std::make_shared<ov::OpExtension<b200::RaggedToDense>>(),
+    std::make_shared<ov::OpExtension<b200::RegexNormalization>>(),
+    std::make_shared<ov::OpExtension<b200::CharsMapNormalization>>(),
 }));
 
 // GenAI's GGUF path dlsym()s this factory (src/tokenizers_factory.hpp:32-33); the signature is frozen.
@@ -475,6 +589,8 @@ create_tokenizer_node(const std::string& op_type, const ov::OutputVector& inputs
     if (op_type == "Truncate") return std::make_shared<b200::Truncate>(inputs, get("m_num_inputs", 1))->outputs();
     if (op_type == "CombineSegments") return std::make_shared<b200::CombineSegments>(inputs)->outputs();
     if (op_type == "RaggedToDense") return std::make_shared<b200::RaggedToDense>(inputs, get("pad_right", true), get("m_pad_max_length", false))->outputs();
+    if (op_type == "RegexNormalization") return std::make_shared<b200::RegexNormalization>(inputs, get("global_replace", true))->outputs();
+    if (op_type == "CharsMapNormalization") return std::make_shared<b200::CharsMapNormalization>(inputs, get("add_dummy_prefix", false), get("remove_extra_whitespaces", true), get("escape_whitespaces", false), get("case_fold", false), get("normalization_form", std::string()), get("nmt", false))->outputs();
     OPENVINO_THROW("Unsupported operation type in the B200 hot-path extension: ", op_type);
 }
 }}  // namespace ov::tokenizers

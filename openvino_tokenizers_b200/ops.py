@@ -516,27 +516,44 @@ class _Normalizer(_Handle):
     _expand = 4
 
     def _run(self, inputs, has_skips):
-        b, e, c = _i32(inputs[0]).reshape(-1), _i32(inputs[1]).reshape(-1), _u8(inputs[2]).reshape(-1)
-        sk = np.ascontiguousarray(inputs[3], np.uint8).reshape(-1) if has_skips else None
-        n = len(b)
-        ob, oe = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
-        cap = int(self._expand * c.size) + 64
-        for _ in range(2):
-            oc = np.zeros(max(cap, 1), np.uint8)
-            got = C.c_int64(0)
-            rc = K.lib().b200tok_normalize_run(self._h, _ptr(b), _ptr(e), C.c_int64(n), _ptr(c) if c.size else None, C.c_int64(c.size),
-                                               _ptr(sk) if sk is not None and n else None, _ptr(ob), _ptr(oe), _ptr(oc), C.c_int64(cap),
-                                               C.byref(got), K.MEM_HOST, None)
-            if rc == K.E_CAPACITY and got.value > cap:      # the call reports the size it needs
-                cap = got.value
-                continue
-            K.check(rc)
-            break
-        shape = np.asarray(inputs[0]).shape
-        out = [ob[:n].copy().reshape(shape), oe[:n].copy().reshape(shape), oc[:got.value].copy()]
-        if has_skips:
-            out.append(inputs[3])
-        return out
+        return _normalize([self], inputs, has_skips)
+
+
+def _normalize(ops_, inputs, has_skips):
+    b, e, c = _i32(inputs[0]).reshape(-1), _i32(inputs[1]).reshape(-1), _u8(inputs[2]).reshape(-1)
+    sk = np.ascontiguousarray(inputs[3], np.uint8).reshape(-1) if has_skips else None
+    n = len(b)
+    ob, oe = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+    cap = int(max(o._expand for o in ops_) * c.size) + 64
+    hs = (C.c_void_p * len(ops_))(*[o.handle for o in ops_])
+    for _ in range(2):
+        oc = np.empty(max(cap, 1), np.uint8)
+        got = C.c_int64(0)
+        rc = K.lib().b200tok_normalize_chain_run(hs, len(ops_), _ptr(b), _ptr(e), C.c_int64(n), _ptr(c) if c.size else None, C.c_int64(c.size),
+                                                 _ptr(sk) if sk is not None and n else None, _ptr(ob), _ptr(oe), _ptr(oc), C.c_int64(cap),
+                                                 C.byref(got), K.MEM_HOST, None)
+        if rc == K.E_CAPACITY and got.value > cap:      # the call reports the size it needs
+            cap = got.value
+            continue
+        K.check(rc)
+        break
+    shape = np.asarray(inputs[0]).shape
+    out = [ob[:n].copy().reshape(shape), oe[:n].copy().reshape(shape), oc[:got.value].copy()]
+    if has_skips:
+        out.append(inputs[3])
+    return out
+
+
+def normalize_chain(steps, inputs):
+    """Run several normaliser ops back to back on the device (b200tok_normalize_chain_run): `steps` are prepared
+    RegexNormalization / CharsMapNormalization objects (see their .prepare), `inputs` the strings [0..2] and optional skips [3]
+    — the subgraph the converter emits for one HF normaliser, without a host round trip between the ops."""
+    if len(inputs) not in (3, 4):
+        raise ValueError("normalize_chain expects the strings and optionally the skips tensor")
+    for s_ in steps:
+        if not s_.handle:
+            raise ValueError("normalize_chain: every step must be prepared (RegexNormalization.prepare / CharsMapNormalization.prepare)")
+    return _normalize(list(steps), inputs, len(inputs) == 4)
 
 
 class RegexNormalization(_Normalizer):
@@ -554,14 +571,19 @@ class RegexNormalization(_Normalizer):
         if len(inputs) not in (5, 6):
             raise ValueError(f"supported input sizes are 5 or 6, got {len(inputs)}")
         has_skips = len(inputs) == 6
-        search, replace = _as_text(inputs[3 + has_skips]).encode(), _as_text(inputs[4 + has_skips]).encode()
+        self.prepare(_as_text(inputs[3 + has_skips]), _as_text(inputs[4 + has_skips]))
+        return self._run(inputs, has_skips)
+
+    def prepare(self, search_pattern, replace_pattern):
+        search = search_pattern.encode() if isinstance(search_pattern, str) else bytes(search_pattern)
+        replace = replace_pattern.encode() if isinstance(replace_pattern, str) else bytes(replace_pattern)
         if self._key != (search, replace):
             self.close()
             K.check(K.lib().b200tok_regexnorm_create(search, C.c_int64(len(search)), replace, C.c_int64(len(replace)),
                                                      int(self.global_replace), self.device, C.byref(self._h)))
             self._key = (search, replace)
             self._expand = 2 + len(replace)
-        return self._run(inputs, has_skips)
+        return self
 
 
 class CharsMapNormalization(_Normalizer):
@@ -575,15 +597,21 @@ class CharsMapNormalization(_Normalizer):
         self.device = device
         self._blob = None if precompiled_charsmap is None else bytes(precompiled_charsmap)
         self._built = None
-        self._expand = 20
+        self._expand = 3          # first guess; the call reports the size it needs if this is too small
 
     def evaluate(self, inputs):
         if len(inputs) not in (3, 4, 5):
             raise ValueError("CharsMapNormalization supports input sizes 3, 4 or 5.")
         has_skips = len(inputs) == 5 or (self._blob is not None and len(inputs) == 4)     # charsmap_normalization.cpp:35
-        blob = self._blob if self._blob is not None else bytes(_u8(inputs[3 + has_skips]).reshape(-1).tobytes())
+        self.prepare(self._blob if self._blob is not None else bytes(_u8(inputs[3 + has_skips]).reshape(-1).tobytes()))
+        return self._run(inputs, has_skips)
+
+    def prepare(self, blob=None):
+        blob = self._blob if blob is None else bytes(blob)
+        if blob is None:
+            raise ValueError("CharsMapNormalization: no precompiled charsmap")
         if self._built != blob:
             self.close()
             K.check(K.lib().b200tok_charsmap_create(blob, C.c_int64(len(blob)), *[int(f) for f in self.flags], self.device, C.byref(self._h)))
             self._built = blob
-        return self._run(inputs, has_skips)
+        return self

@@ -142,7 +142,7 @@ def test_gpu_regex_normalization_vs_oracle(step):
     got = op.evaluate(ins + [skips] + pat)
     assert len(got) == 4 and got[3] is skips
     assert NC.unpack(*got[:3]) == NC.unpack(*exp)
-    assert op.launches == 4
+    assert op.launches == 6          # per call: lengths, size, write (+ the cub scan)
 
 
 @pytest.mark.gpu
@@ -232,11 +232,14 @@ def test_gpu_bert_normalizer_chain_c2_size():
     chain.append((ops.RegexNormalization(s["global_replace"]), [np.frombuffer(_enc(s["search"]), np.uint8), np.frombuffer(_enc(s["replace"]), np.uint8)], s))
     chain.append((ops.CharsMapNormalization(precompiled_charsmap=fold), [], "fold"))
     cur = [b, e, chars]
-    t0 = time.perf_counter()
     for op, extra, _ in chain:
         cur = op.evaluate(cur + extra)
+    fused = ops.normalize_chain([op for op, _, _ in chain], [b, e, chars])                 # one call, intermediates stay on the device
+    t0 = time.perf_counter()
+    fused = ops.normalize_chain([op for op, _, _ in chain], [b, e, chars])
     dt = time.perf_counter() - t0
-    print(f"BERT normaliser chain, host buffers, {B * L / 1e6:.1f} MB: {dt * 1e3:.1f} ms")
+    print(f"BERT normaliser chain, one call, host buffers, {B * L / 1e6:.1f} MB: {dt * 1e3:.1f} ms")
+    assert all(np.array_equal(x, y) for x, y in zip(fused, cur))
     sample = np.arange(0, B, 257)
     ref = [b[sample], e[sample], chars]
     for _, _, s in chain:

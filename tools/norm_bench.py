@@ -70,3 +70,23 @@ for name, h in ops:
     ms = ev0.elapsed_time(ev1) / 10
     alg = 2 * N + got.value + 16 * len(b)     # the text is read by both passes, the result written once, offsets in / out
     print(f"{name:14s} {ms:.3f} ms/call  {N / 1e6 / (ms / 1e3):9.1f} MB/s text  algorithmic {alg / 1e9 / (ms / 1e3):7.1f} GB/s  out {got.value} B")
+
+hs = (C.c_void_p * len(ops))(*[h for _, h in ops])
+
+
+def run_chain():
+    K.check(lib.b200tok_normalize_chain_run(hs, len(ops), C.c_void_p(db.data_ptr()), C.c_void_p(de.data_ptr()), C.c_int64(len(b)), C.c_void_p(dc.data_ptr()),
+                                            C.c_int64(N), None, C.c_void_p(ob.data_ptr()), C.c_void_p(oe.data_ptr()), C.c_void_p(oc.data_ptr()), C.c_int64(cap),
+                                            C.byref(got), K.MEM_DEVICE, st))
+
+
+for _ in range(3):
+    run_chain()
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+for _ in range(10):
+    run_chain()
+ev1.record(); torch.cuda.synchronize()
+ms = ev0.elapsed_time(ev1) / 10
+print(f"BERT chain (6 ops, one call) {ms:.3f} ms  {N / 1e6 / (ms / 1e3):9.1f} MB/s text")
