@@ -1687,9 +1687,53 @@ B200TOK_API int b200tok_charsmap_create(const uint8_t* precompiled_charsmap, int
     return finish_norm(o, device, out);
 }
 
+}  // extern "C"
+
+namespace {
+bool compose_chain(const b200tok_handle* handles, int n_ops, uint8_t* T) {
+    std::vector<const HostNorm*> ops((size_t)n_ops);
+    for (int k = 0; k < n_ops; ++k) ops[(size_t)k] = &static_cast<NormObj*>(handles[k])->h;
+    return compose_norm_chain(ops.data(), n_ops, T);
+}
+
+// The ops one after the other over the strings (d_b, d_e, d_c): results in ping-pong buffers, the last one's in (d_b, d_e, d_c).
+struct ChainBufs { std::unique_ptr<AsyncBuf> ob[2], oe[2], oc[2]; AsyncBuf len, scan, tot; };
+int run_ops(const b200tok_handle* handles, int n_ops, const int32_t*& d_b, const int32_t*& d_e, const uint8_t*& d_c, const uint8_t* d_s, int64_t n,
+            ChainBufs& B, int64_t& total, cudaStream_t st) {
+    NormObj* first = static_cast<NormObj*>(handles[0]);
+    CU(B.len.alloc((size_t)n * 4, st)); CU(B.tot.alloc(8, st));
+    const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);      // 8 CTAs of 8 warps per SM, strings strided over them
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    int rc;
+    for (int k = 0; k < n_ops; ++k) {
+        NormObj* o = static_cast<NormObj*>(handles[k]);
+        const NormRule R = o->view();
+        const int w = k & 1;
+        B.ob[w] = std::make_unique<AsyncBuf>(); B.oe[w] = std::make_unique<AsyncBuf>(); B.oc[w] = std::make_unique<AsyncBuf>();
+        CU(B.ob[w]->alloc((size_t)n * 4, st)); CU(B.oe[w]->alloc((size_t)n * 4, st));
+        normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), nullptr, nullptr, nullptr, 0, nullptr);
+        if ((rc = scan_i32(B.scan, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), n, st))) return rc;
+        normalize_total_kernel<<<1, 1, 0, st>>>(B.ob[w]->as<int32_t>(), B.len.as<int32_t>(), n, B.tot.as<int64_t>());
+        CU(cudaMemcpyAsync(&total, B.tot.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));                    // the size of this op's result
+        if (total > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "normalised text exceeds 2^31 bytes");
+        CU(B.oc[w]->alloc((size_t)total + 16, st));
+        normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), B.oe[w]->as<int32_t>(),
+                                                       B.oc[w]->as<uint8_t>(), total, B.tot.as<int64_t>());
+        CU(cudaGetLastError());
+        { std::lock_guard<std::mutex> lock(o->mu); o->launches += 3; }
+        d_b = B.ob[w]->as<int32_t>(); d_e = B.oe[w]->as<int32_t>(); d_c = B.oc[w]->as<uint8_t>();
+    }
+    return B200TOK_OK;
+}
+}  // namespace
+
+extern "C" {
+
 // evaluate_normalization_helper (src/utils.cpp:178-234): out_begins[0] = 0, strings packed back to back.  A chain of
 // normalisers (what the converter emits for one HF normaliser, e.g. the six ops of BertNormalizer, hf_parser.py:84-102)
-// runs back to back on the device: the strings cross PCIe once each way, every op writes an exactly sized buffer.
+// stays on the device: the strings cross PCIe once each way.  With two or more ops, strings made only of ASCII bytes that
+// every op maps / drops one for one go through ONE composed byte table (compose_kernel); the rest run op by op.
 B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n_ops, const int32_t* begins, const int32_t* ends, int64_t n,
                                             const uint8_t* chars, int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends,
                                             uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
@@ -1708,34 +1752,52 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
     NormObj* first = as<NormObj>(handles[0], K_NORM);
     DeviceGuard g(first->device);
     cudaStream_t st = (cudaStream_t)stream;
-    AsyncBuf bb, be, bc, bs, blen, bscan, btot;
+    AsyncBuf bb, be, bc, bs;
     const int32_t *d_b, *d_e; const uint8_t *d_c, *d_s;
     int rc;
     if ((rc = stage_in(bb, begins, n, host, st, d_b)) || (rc = stage_in(be, ends, n, host, st, d_e)) ||
         (rc = stage_in(bc, chars, n_chars, host, st, d_c)) || (rc = stage_in(bs, skips, skips ? n : 0, host, st, d_s))) return rc;
-    CU(blen.alloc((size_t)n * 4, st)); CU(btot.alloc(8, st));
-    const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);      // 8 CTAs of 8 warps per SM, strings strided over them
-    const unsigned blocks = (unsigned)((warps + 7) / 8);
-    std::unique_ptr<AsyncBuf> ob[2], oe[2], oc[2];        // ping-pong results
+    ChainBufs B;
     int64_t total = 0;
-    for (int k = 0; k < n_ops; ++k) {
-        NormObj* o = as<NormObj>(handles[k], K_NORM);
-        const NormRule R = o->view();
-        const int w = k & 1;
-        ob[w] = std::make_unique<AsyncBuf>(); oe[w] = std::make_unique<AsyncBuf>(); oc[w] = std::make_unique<AsyncBuf>();
-        CU(ob[w]->alloc((size_t)n * 4, st)); CU(oe[w]->alloc((size_t)n * 4, st));
-        normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), nullptr, nullptr, nullptr, 0, nullptr);
-        if ((rc = scan_i32(bscan, blen.as<int32_t>(), ob[w]->as<int32_t>(), n, st))) return rc;
-        normalize_total_kernel<<<1, 1, 0, st>>>(ob[w]->as<int32_t>(), blen.as<int32_t>(), n, btot.as<int64_t>());
+    uint8_t T[128];
+    static const bool no_compose = [] { const char* e = getenv("B200TOK_DEBUG_FLAGS"); return e && (atoi(e) & 32); }();   // debug: always op by op
+    AsyncBuf btab, blen, bgen, bidx, bscan, btot, bsb, bse, bob, boe, boc;
+    if (n_ops >= 2 && !no_compose && compose_chain(handles, n_ops, T)) {
+        const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);
+        const unsigned blocks = (unsigned)((warps + 7) / 8), tblocks = (unsigned)((n + 255) / 256);
+        CU(btab.alloc(128, st)); CU(blen.alloc((size_t)n * 4, st)); CU(bgen.alloc((size_t)n * 4, st)); CU(bidx.alloc((size_t)n * 4, st)); CU(btot.alloc(16, st));
+        CU(bob.alloc((size_t)n * 4, st)); CU(boe.alloc((size_t)n * 4, st));
+        CU(cudaMemcpyAsync(btab.p, T, 128, cudaMemcpyHostToDevice, st));
+        compose_kernel<false><<<blocks, 256, 0, st>>>(btab.as<uint8_t>(), d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), bgen.as<int32_t>(), nullptr, nullptr, nullptr,
+                                                      nullptr, nullptr, nullptr, nullptr);
+        if ((rc = scan_i32(bscan, bgen.as<int32_t>(), bidx.as<int32_t>(), n, st))) return rc;
+        normalize_total_kernel<<<1, 1, 0, st>>>(bidx.as<int32_t>(), bgen.as<int32_t>(), n, btot.as<int64_t>());
+        int64_t n_general = 0;
+        CU(cudaMemcpyAsync(&n_general, btot.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const int32_t* sub_b = nullptr; const uint8_t* sub_c = nullptr;
+        if (n_general > 0) {              // these strings run op by op, as a list of their own over the same chars
+            CU(bsb.alloc((size_t)n_general * 4, st)); CU(bse.alloc((size_t)n_general * 4, st));
+            gather_general_kernel<<<tblocks, 256, 0, st>>>(bgen.as<int32_t>(), bidx.as<int32_t>(), d_b, d_e, n, bsb.as<int32_t>(), bse.as<int32_t>());
+            const int32_t* gb = bsb.as<int32_t>(); const int32_t* ge = bse.as<int32_t>(); const uint8_t* gc = d_c;
+            int64_t sub_total = 0;
+            if ((rc = run_ops(handles, n_ops, gb, ge, gc, nullptr, n_general, B, sub_total, st))) return rc;
+            merge_general_len_kernel<<<tblocks, 256, 0, st>>>(bgen.as<int32_t>(), bidx.as<int32_t>(), gb, ge, n, blen.as<int32_t>());
+            sub_b = gb; sub_c = gc;
+        }
+        if ((rc = scan_i32(bscan, blen.as<int32_t>(), bob.as<int32_t>(), n, st))) return rc;
+        normalize_total_kernel<<<1, 1, 0, st>>>(bob.as<int32_t>(), blen.as<int32_t>(), n, btot.as<int64_t>());
         CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));                    // the size of this op's result
+        CU(cudaStreamSynchronize(st));
         if (total > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "normalised text exceeds 2^31 bytes");
-        CU(oc[w]->alloc((size_t)total + 16, st));
-        normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), ob[w]->as<int32_t>(), oe[w]->as<int32_t>(),
-                                                       oc[w]->as<uint8_t>(), total, btot.as<int64_t>());
+        CU(boc.alloc((size_t)total + 16, st));
+        compose_kernel<true><<<blocks, 256, 0, st>>>(btab.as<uint8_t>(), d_b, d_e, d_c, d_s, n, blen.as<int32_t>(), bgen.as<int32_t>(), bob.as<int32_t>(),
+                                                     boe.as<int32_t>(), boc.as<uint8_t>(), bidx.as<int32_t>(), sub_b, sub_c, btot.as<int64_t>());
         CU(cudaGetLastError());
-        { std::lock_guard<std::mutex> lock(o->mu); o->launches += 3; }
-        d_b = ob[w]->as<int32_t>(); d_e = oe[w]->as<int32_t>(); d_c = oc[w]->as<uint8_t>();
+        { std::lock_guard<std::mutex> lock(first->mu); first->launches += 4 + (n_general > 0 ? 2 : 0); }
+        d_b = bob.as<int32_t>(); d_e = boe.as<int32_t>(); d_c = boc.as<uint8_t>();
+    } else {
+        if ((rc = run_ops(handles, n_ops, d_b, d_e, d_c, d_s, n, B, total, st))) return rc;
     }
     *n_chars_out = total;
     if (total > chars_capacity) { CU(cudaStreamSynchronize(st)); return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total); }

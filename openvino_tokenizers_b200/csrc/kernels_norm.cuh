@@ -119,4 +119,83 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
 // Size of a result: offset of the last string + its length.
 __global__ void normalize_total_kernel(const int32_t* off, const int32_t* len, int64_t n, int64_t* total) { *total = (int64_t)off[n - 1] + len[n - 1]; }
 
+// ---- a chain of normalisers on all-ASCII strings: one composed byte table ----
+// T[a] = what byte a becomes after every op of the chain (api.cu compose_chain): a byte, NT_DEL (dropped) or NT_GENERAL
+// (some op does more than map / drop this byte: the string takes the op-by-op path).  A string made only of bytes with a
+// simple fate is normalised in ONE pass pair whatever the number of ops; the others ("general") are gathered into a
+// sub-list, run op by op, and their results are copied into place by the write pass.
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) compose_kernel(const uint8_t* __restrict__ table, const int32_t* __restrict__ begins,
+                                                      const int32_t* __restrict__ ends, const uint8_t* __restrict__ chars,
+                                                      const uint8_t* __restrict__ skips, int64_t n, int32_t* __restrict__ len,
+                                                      int32_t* __restrict__ general, const int32_t* __restrict__ out_begins,
+                                                      int32_t* __restrict__ out_ends, uint8_t* __restrict__ out, const int32_t* __restrict__ sub_index,
+                                                      const int32_t* __restrict__ sub_begins, const uint8_t* __restrict__ sub_chars, int64_t* total) {
+    __shared__ uint8_t T[256];
+    T[threadIdx.x] = threadIdx.x < 128 ? table[threadIdx.x] : (uint8_t)NT_GENERAL;      // non-ASCII bytes are never simple
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int b = begins[i], e = ends[i];
+        const bool skip = skips && skips[i];
+        if (!WRITE) {
+            int cnt = 0;
+            bool gen = false;
+            if (skip) cnt = e > b ? e - b : 0;
+            else {
+                for (int c0 = b; c0 < e && !gen; c0 += 128) {           // 4 chunks in flight
+                    uint32_t t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int pos = c0 + 32 * u + lane; t[u] = pos < e ? T[chars[pos]] : (uint32_t)NT_DEL; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        gen = gen || __any_sync(FULL, t[u] == NT_GENERAL);
+                        cnt += __popc(__ballot_sync(FULL, t[u] < NT_DEL));
+                    }
+                }
+            }
+            if (lane == 0) { len[i] = gen ? 0 : cnt; general[i] = gen ? 1 : 0; }
+            continue;
+        }
+        const int64_t o0 = out_begins[i];
+        const int l = len[i];
+        if (lane == 0) { out_ends[i] = (int32_t)(o0 + l); if (i == n - 1) *total = o0 + l; }
+        if (general[i]) {                 // normalised op by op: copy the result into place
+            const uint8_t* src = sub_chars + sub_begins[sub_index[i]];
+            for (int k = lane; k < l; k += 32) out[o0 + k] = src[k];
+        } else if (skip) {
+            for (int k = lane; k < l; k += 32) out[o0 + k] = chars[b + k];
+        } else {
+            int o = 0;
+            for (int c0 = b; c0 < e; c0 += 128) {
+                uint32_t t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int pos = c0 + 32 * u + lane; t[u] = pos < e ? T[chars[pos]] : (uint32_t)NT_DEL; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t m = __ballot_sync(FULL, t[u] < NT_DEL);
+                    if (t[u] < NT_DEL) out[o0 + o + __popc(m & ((1u << lane) - 1u))] = (uint8_t)t[u];
+                    o += __popc(m);
+                }
+            }
+        }
+    }
+}
+
+// The general strings as a list of their own (their extents still point into the caller's chars).
+__global__ void gather_general_kernel(const int32_t* general, const int32_t* sub_index, const int32_t* begins, const int32_t* ends, int64_t n,
+                                      int32_t* sub_begins, int32_t* sub_ends) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !general[i]) return;
+    sub_begins[sub_index[i]] = begins[i];
+    sub_ends[sub_index[i]] = ends[i];
+}
+__global__ void merge_general_len_kernel(const int32_t* general, const int32_t* sub_index, const int32_t* sub_begins, const int32_t* sub_ends, int64_t n, int32_t* len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !general[i]) return;
+    len[i] = sub_ends[sub_index[i]] - sub_begins[sub_index[i]];
+}
+
 }  // namespace b200tok

@@ -172,6 +172,29 @@ int parse_regex_norm(const char* search, int64_t slen, const char* replace, int6
     return B200TOK_OK;
 }
 
+// What every ASCII byte becomes after all ops of a chain: a byte, NT_DEL (dropped) or NT_GENERAL (some op does more than
+// map / drop it).  false: the chain has an op whose effect depends on the position in the string (anchored / first match
+// only), so there is no composed table.  Strings made only of bytes with a simple fate take kernels_norm.cuh:compose_kernel.
+bool compose_norm_chain(const HostNorm* const* ops, int n_ops, uint8_t* T) {
+    for (int a = 0; a < 128; ++a) T[a] = (uint8_t)a;
+    for (int k = 0; k < n_ops; ++k) {
+        const HostNorm& h = *ops[k];
+        const NormRule& R = h.rule;
+        if (R.kind == NORM_CLASS && (R.anchored || !R.global)) return false;
+        uint8_t A[128];
+        for (int a = 0; a < 128; ++a) {
+            if (R.kind == NORM_CHARSMAP) { A[a] = (h.atab[128 + (size_t)a] & (NA_COMPLEX | NA_ASCII_KIDS)) ? (uint8_t)NT_GENERAL : h.atab[(size_t)a]; continue; }
+            const bool in_class = R.any || (R.literal_cp >= 0 ? a == R.literal_cp : (h.atab[128 + (size_t)a] & R.mask) != 0);
+            if (in_class == (R.negate != 0)) { A[a] = (uint8_t)a; continue; }
+            const int l = R.pre_len + (R.keep ? 1 : 0) + R.post_len;
+            const uint8_t r = R.pre_len ? R.pre[0] : R.keep ? (uint8_t)a : R.post_len ? R.post[0] : 0;
+            A[a] = l == 0 ? (uint8_t)NT_DEL : (l == 1 && r < 0x80) ? r : (uint8_t)NT_GENERAL;
+        }
+        for (int a = 0; a < 128; ++a) if (T[a] < 0x80) T[a] = A[T[a]];
+    }
+    return true;
+}
+
 int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int remove_extra_whitespaces, int escape_whitespaces, HostNorm& out, std::string& err) {
     if (len < 0 || (len > 0 && !blob)) { err = "CharsMapNormalization: null charsmap"; return B200TOK_E_INVALID; }
     if (add_dummy_prefix || remove_extra_whitespaces || escape_whitespaces) {

@@ -112,6 +112,7 @@ struct HostNorm {
     std::vector<uint8_t> atab;       // [0,128) amap, [128,256) aflag (NormRule::atab)
 };
 int parse_regex_norm(const char* search, int64_t slen, const char* replace, int64_t rlen, int global_replace, HostNorm& out, std::string& err);
+bool compose_norm_chain(const HostNorm* const* ops, int n_ops, uint8_t* T /* [128] */);
 int parse_charsmap(const uint8_t* blob, int64_t len, int add_dummy_prefix, int remove_extra_whitespaces, int escape_whitespaces, HostNorm& out, std::string& err);
 
 inline uint64_t fnv1a64(const uint8_t* p, int64_t n) {

@@ -1062,6 +1062,7 @@ struct NormRule {
     // (divergent indices: the table lives in global memory, not in the parameter block)
     const uint8_t* atab;     // [0,128) amap, [128,256) aflag
 };
+enum : uint8_t { NT_DEL = 0xFE, NT_GENERAL = 0xFF };                     // fates of an ASCII byte in a composed chain table (tables.cpp compose_norm_chain)
 enum : uint8_t { NA_COMPLEX = 1, NA_ASCII_KIDS = 2, NA_OTHER_KIDS = 4 };   // replacement not 1 ASCII byte / longer rules continue with an ASCII / non-ASCII byte
 
 struct NormStep {

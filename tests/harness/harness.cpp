@@ -356,3 +356,23 @@ HZ int64_t hz_charsmap_ascii_table_check(const uint8_t* blob, int64_t len) {
     }
     return bad;
 }
+
+
+// Composed byte table of a chain of normalisers (tables.cpp compose_norm_chain).  hz_chain_reset(); hz_chain_add(...) per
+// op (same arguments as hz_normalize); hz_chain_table(T) -> 1 composable, 0 not, < 0 parser error of the last add.
+namespace { std::vector<std::unique_ptr<HostNorm>> g_chain; int g_chain_err = 0; }
+HZ void hz_chain_reset() { g_chain.clear(); g_chain_err = 0; }
+HZ int hz_chain_add(int kind, const uint8_t* a, int64_t alen, const uint8_t* b, int64_t blen, int flag) {
+    auto hn = std::make_unique<HostNorm>();
+    std::string err;
+    const int rc = kind == 0 ? parse_regex_norm((const char*)a, alen, (const char*)b, blen, flag, *hn, err) : parse_charsmap(a, alen, 0, 0, 0, *hn, err);
+    if (rc) { g_chain_err = rc; return rc; }
+    g_chain.push_back(std::move(hn));
+    return 0;
+}
+HZ int hz_chain_table(uint8_t* T) {
+    if (g_chain_err) return g_chain_err;
+    std::vector<const HostNorm*> ops;
+    for (auto& h : g_chain) ops.push_back(h.get());
+    return compose_norm_chain(ops.data(), (int)ops.size(), T) ? 1 : 0;
+}

@@ -180,3 +180,19 @@ def hz_charsmap_ascii_table_check(blob):
     blob = bytes(blob)
     lib().hz_charsmap_ascii_table_check.restype = C.c_int64
     return int(lib().hz_charsmap_ascii_table_check(blob, C.c_int64(len(blob))))
+
+
+def hz_chain_table(steps):
+    """Composed ASCII byte table of a chain: steps = [(kind, a, b, flag)] as for hz_normalize.  Returns a 128-entry uint8
+    array (0xFE dropped, 0xFF general) or None when the chain is not composable."""
+    lib().hz_chain_reset()
+    for kind, a, b, flag in steps:
+        a, b = bytes(a), bytes(b)
+        rc = lib().hz_chain_add(int(kind), a, C.c_int64(len(a)), b, C.c_int64(len(b)), int(flag))
+        if rc:
+            raise ValueError(rc)
+    T = np.zeros(128, np.uint8)
+    rc = lib().hz_chain_table(T.ctypes.data_as(K.u8p))
+    if rc < 0:
+        raise ValueError(rc)
+    return T if rc == 1 else None

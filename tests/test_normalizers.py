@@ -97,6 +97,58 @@ def test_charsmap_ascii_shortcut_tables_agree_with_the_trie():
         assert hostcore.hz_charsmap_ascii_table_check(blob) == 0
 
 
+def _chain_steps(chain):
+    bs = {s["name"]: s for s in GOLDEN["bert_steps"] + GOLDEN["other_steps"]}
+    R = lambda name: ("regex", bs[name]["search"], bs[name]["replace"], bs[name]["global_replace"])
+    return {
+        "bert": lambda: [R("del_control_chars_regex"), R("replace_whitespace_regex"), R("handle_chinese_chars_regex"), ("charsmap", NC.unicodedata_blob("NFD", False), None, None),
+                         R("strip_accents_regex"), ("charsmap", NC.unicodedata_blob(None, True), None, None)],
+        "custom": lambda: [R("replace_whitespace_regex"), ("charsmap", NC.custom_blob(), None, None), R("del_control_chars_regex"), ("charsmap", NC.custom_blob(), None, None)],
+        "anchored": lambda: [R("replace_whitespace_regex"), R("add_prefix_whitespace_regex"), ("charsmap", NC.unicodedata_blob(None, True), None, None)],
+        "expanding": lambda: [("regex", r"\s", "<$0>", True), ("charsmap", NC.builtin_blob("nfkc_cf"), None, None), R("replace_spaces_metaspace")],
+    }[chain]()
+
+
+def _oracle_chain(steps, ins, skips=None):
+    cur = list(ins)
+    for kind, a, b_, g in steps:
+        if kind == "regex":
+            cur = list(oracle.regex_normalize(a, b_, g, *cur, skips))
+        else:
+            cur = list(oracle.charsmap_normalize(a, *cur, skips))
+    return cur
+
+
+@pytest.mark.skipif(not oracle.pcre2_available(), reason="libpcre2-8 not present")
+@pytest.mark.parametrize("chain", ["bert", "custom", "anchored", "expanding"])
+def test_composed_chain_table_vs_oracle(chain):
+    """The composed per-byte table of a chain (what all-ASCII strings take on the GPU) against the ops applied one after
+    the other by the oracle: every string whose bytes all have a simple fate must come out as the table says."""
+    import hostcore
+    steps = _chain_steps(chain)
+    T = hostcore.hz_chain_table([(0, _enc(a), _enc(b_), g) if kind == "regex" else (1, a, b"", 0) for kind, a, b_, g in steps])
+    if chain == "anchored":
+        assert T is None
+        return
+    assert T is not None
+    if chain == "bert":      # lower-casing, tabs / newlines -> space, controls dropped, everything else itself
+        assert T[ord("A")] == ord("a") and T[9] == 32 and T[10] == 32 and T[1] == 0xFE and T[0x7F] == 0xFE and T[ord("~")] == ord("~")
+        assert not (T == 0xFF).any()
+    if chain == "expanding":
+        assert T[32] == 0xFF and T[9] == 0xFF and T[ord("Q")] == ord("q")
+    raw = [bytes([a]) for a in range(128)] + [r for r in NC.ascii_corpus(seed=41, n=1500) if r.isascii()]
+    ins = NC.pack(raw)
+    exp = NC.unpack(*_oracle_chain(steps, ins)[:3])
+    checked = 0
+    for r, x in zip(raw, exp):
+        fates = T[np.frombuffer(r, np.uint8)] if r else np.zeros(0, np.uint8)
+        if (fates == 0xFF).any():
+            continue
+        assert bytes(fates[fates != 0xFE]) == x, r
+        checked += 1
+    assert checked > 100
+
+
 @pytest.mark.parametrize("search,replace", UNSUPPORTED)
 def test_unsupported_patterns_are_refused(search, replace):
     """No CPU fallback: a pattern outside the single-character set fails at create, with or without a GPU."""
@@ -182,6 +234,28 @@ def test_gpu_charsmap_normalization_vs_oracle(which):
         raw = [c["text"].encode() for c in GOLDEN["casefold_utf8"]]
         got = ops.CharsMapNormalization(precompiled_charsmap=blob).evaluate(_strings_in(raw))
         assert NC.unpack(*got[:3]) == [c["expected"].encode() for c in GOLDEN["casefold_utf8"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chain", ["bert", "custom", "anchored", "expanding"])
+def test_gpu_chain_mixed_vs_oracle(chain):
+    """Chains over a batch that mixes all-ASCII strings (one composed byte table), strings the ops must run one by one
+    (non-ASCII, bytes with multi-byte rules) and skip-flagged strings; with an anchored op the chain is not composable."""
+    from openvino_tokenizers_b200 import ops
+    steps = _chain_steps(chain)
+    raw = NC.corpus(seed=31, n=2500, max_len=90) + NC.ascii_corpus(seed=32, n=1500) + [b"", b"plain ascii only", b"TAB\tand\x01ctl"]
+    ins = _strings_in(raw)
+    prepared = [ops.RegexNormalization(g).prepare(a, b_) if kind == "regex" else ops.CharsMapNormalization().prepare(a) for kind, a, b_, g in steps]
+    for skips in (None, (np.arange(len(raw)) % 6 == 2)):
+        exp = _oracle_chain(steps, ins, skips)
+        got = ops.normalize_chain(prepared, ins + ([skips] if skips is not None else []))
+        assert NC.unpack(*got[:3]) == NC.unpack(*exp[:3])
+        assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()
+    # all-ASCII batch: no string takes the op-by-op path
+    raw = [r for r in NC.ascii_corpus(seed=33, n=800) if r.isascii()]
+    ins = _strings_in(raw)
+    got = ops.normalize_chain(prepared, ins)
+    assert NC.unpack(*got[:3]) == NC.unpack(*_oracle_chain(steps, ins)[:3])
 
 
 @pytest.mark.gpu
