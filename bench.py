@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — MB/s of input text tokenized (bit-exact ids) on the BASELINE.json headline workload.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3|c4|norm]
 
 A "step" is one pass of the fused RegexSplit -> BPETokenizer hot path over one synthetic batch
 (C1: gpt2-shaped BPE, 65 536 x 512-byte printable-ASCII docs per GPU; weak scaling: every rank tokenises its
@@ -43,6 +43,9 @@ WORKLOADS = {
     "c4": dict(kind="detok", vocab="llama2_detok_synth", rows=1024, row_bytes=1024, gen="ids",
                name="C4: detokenize, VocabDecoder + ByteFallback fused, 1 024 x 1 024 token ids (Llama-2-shaped 32 000 vocab with 256 <0xHH> "
                     "tokens, synthetic stand-in), skip_tokens {0,1,2}"),
+    "norm": dict(kind="norm", vocab="-", rows=65536, row_bytes=256, gen="ascii_ctl",
+                 name="BERT normaliser (SURVEY 8f.4): RegexNormalization x4 + CharsMapNormalization NFD + case fold, the six ops of "
+                      "hf_parser.py:84-102 in one b200tok_normalize_chain_run, 65 536 x 256 B printable ASCII with 1 % tabs / 0.5 % control bytes"),
     "c3": dict(kind="bpe", vocab="llama3_synth", rows=32768, row_bytes=1024, gen="utf8",
                name="C3 shard: Llama-3-shaped BPE (128 256 vocab, synthetic stand-in llama3_synth), 32 768 x 1 KiB "
                     "mixed-UTF-8 docs per GPU (262 144 rows at 8 GPUs), fused RegexSplit->BPETokenizer"),
@@ -271,6 +274,107 @@ def main_detok(args, w, rank, world, local_rank):
     }))
 
 
+def main_norm(args, w, rank, world, local_rank):
+    """BERT normaliser chain: metric = MB/s of input text normalised (bit-exact bytes); a step = the six ops over the batch."""
+    import ctypes as C
+    import torch
+    import oracle
+    sys.path.insert(0, str(ROOT / "tests"))
+    import normcases as NC
+    from openvino_tokenizers_b200 import _capi as K
+    from openvino_tokenizers_b200 import ops
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    golden = json.loads((ROOT / "tests" / "golden" / "normalization_layer_tests.json").read_text())
+    bs = golden["bert_steps"]
+    nfd, fold = NC.unicodedata_blob("NFD", False), NC.unicodedata_blob(None, True)      # compiled by the installed sentencepiece from unicodedata rules
+    steps = [("regex", bs[0]), ("regex", bs[1]), ("regex", bs[2]), ("charsmap", nfd), ("regex", bs[3]), ("charsmap", fold)]
+    chain = [ops.RegexNormalization(x["global_replace"], device=local_rank).prepare(x["search"], x["replace"]) if k == "regex"
+             else ops.CharsMapNormalization(device=local_rank).prepare(x) for k, x in steps]
+    Bn, Ln = w["rows"], w["row_bytes"]
+    rng = np.random.default_rng(1234)
+    chars = rng.integers(0x20, 0x7F, size=Bn * Ln, dtype=np.uint8)
+    r = rng.random(Bn * Ln)
+    chars[r < 0.01] = 0x09
+    chars[(r >= 0.01) & (r < 0.015)] = 0x01
+    b = np.arange(Bn, dtype=np.int32) * Ln
+    e = b + Ln
+    N = chars.size
+
+    def oracle_chain(ins):
+        cur = list(ins)
+        for k, x in steps:
+            cur = list(oracle.regex_normalize(x["search"], x["replace"], x["global_replace"], *cur)) if k == "regex" else list(oracle.charsmap_normalize(x, *cur))
+        return cur
+    ref = ops.normalize_chain(chain, [b, e, chars])                      # host path (creates nothing new; also the e2e call)
+    n_out = int(ref[2].size)
+    sample = slice(0, 2048)
+    exp = oracle_chain([b[sample], e[sample], chars])
+    assert bytes(ref[2][: int(ref[1][sample][-1])]) == bytes(exp[2]), "device result differs from the oracle"
+    L = K.lib()
+    hb, he = torch.from_numpy(b).pin_memory(), torch.from_numpy(e).pin_memory()
+    hc = torch.from_numpy(chars).pin_memory()
+    db, de, dc = hb.to(dev), he.to(dev), torch.cat([hc, torch.zeros(64, dtype=torch.uint8)]).to(dev)
+    cap = N + 64
+    ob, oe = torch.empty(Bn, dtype=torch.int32, device=dev), torch.empty(Bn, dtype=torch.int32, device=dev)
+    oc = torch.empty(cap, dtype=torch.uint8, device=dev)
+    hob, hoe, hoc = torch.empty(Bn, dtype=torch.int32).pin_memory(), torch.empty(Bn, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.uint8).pin_memory()
+    hs = (C.c_void_p * len(chain))(*[o.handle for o in chain])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    got = C.c_int64(0)
+
+    def step(mem, tb, te, tc, tob, toe, toc):
+        K.check(L.b200tok_normalize_chain_run(hs, len(chain), C.c_void_p(tb.data_ptr()), C.c_void_p(te.data_ptr()), C.c_int64(Bn), C.c_void_p(tc.data_ptr()),
+                                              C.c_int64(N), None, C.c_void_p(tob.data_ptr()), C.c_void_p(toe.data_ptr()), C.c_void_p(toc.data_ptr()),
+                                              C.c_int64(cap), C.byref(got), mem, C.c_void_p(stream.cuda_stream)))
+    for _ in range(args.warmup):
+        step(K.MEM_DEVICE, db, de, dc, ob, oe, oc); step(K.MEM_HOST, hb, he, hc, hob, hoe, hoc)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sum(o.launches for o in chain)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step(K.MEM_DEVICE, db, de, dc, ob, oe, oc)
+        ev[k][1].record()
+        torch.cuda.synchronize()
+    launches = sum(o.launches for o in chain) - launches0
+    assert got.value == n_out and bytes(oc[:n_out].cpu().numpy()) == bytes(ref[2])
+    ms = sum(a.elapsed_time(b_) for a, b_ in ev) / args.steps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(K.MEM_HOST, hb, he, hc, hob, hoe, hoc)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    assert bytes(hoc[:n_out].numpy()) == bytes(ref[2])
+    peak, peak_src = measured_peak()
+    algo = 2 * N + n_out + 16 * Bn                      # the text is read by the lengths pass and the write pass, the result written once
+    rows = 8192
+    t0 = time.perf_counter()
+    oracle_chain([b[:rows], e[:rows], chars])
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({
+        "metric": "input text normalised (bit-exact bytes)", "value": N / 1e6 / (ms / 1e3), "unit": "MB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": w["name"], "rows": Bn, "row_bytes": Ln, "out_bytes": n_out, "l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
+                   "note": "the device-resident call sizes its result on the host: two stream synchronisations are inside the step"},
+        "e2e": {"value": N / 1e6 / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": N + 8 * Bn, "d2h_bytes_per_step": n_out + 8 * Bn,
+                "ms_per_step": e2e_s * 1e3, "path": "b200tok_normalize_chain_run with B200TOK_MEM_HOST on pinned buffers"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": algo / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s", "frac": algo / 1e9 / (ms / 1e3) / peak, "traffic": None,
+                     "kernel": "compose_kernel<lengths> + cub scan + compose_kernel<write> (whole step, host round trips included)",
+                     "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},
+        "cpu_baseline": {"value": rows * Ln / 1e6 / cpu_s, "unit": "MB/s", "cores": 1, "kind": "port",
+                         "sample": f"first {rows} of {Bn} rows, one pass: PCRE2 pcre2_substitute x4 + the restated sentencepiece Normalizer x2"},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +389,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if w["kind"] == "norm":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the tokenize workloads; the normaliser workload reports its CPU port inline"}))
+            return
+        return main_norm(args, w, rank, world, local_rank)
     if w["kind"] == "detok":
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the reference arm is defined for the tokenize workloads; C4 reports its CPU port inline"}))

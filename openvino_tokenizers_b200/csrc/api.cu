@@ -1231,7 +1231,39 @@ struct AsyncBuf {
     void* p = nullptr;
     cudaStream_t st = nullptr;
     ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
-    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 16, s); }
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        cudaMemPool_t pool = scratch_pool();
+        return pool ? cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, pool, s) : cudaMallocAsync(&p, bytes ? bytes : 16, s);
+    }
+    // The per-call scratch of the stateless entry points comes from a stream-ordered pool of this library's own (one per
+    // device) that keeps its memory across synchronisations: from the second call on an allocation is a pool hit.  (The
+    // device's default pool hands memory back to the driver at every synchronisation, and its settings belong to the host
+    // application.)
+    static cudaMemPool_t scratch_pool() {
+        static std::mutex mu;
+        static cudaMemPool_t pools[64] = {};
+        static bool tried[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!tried[dev]) {
+            tried[dev] = true;
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool = nullptr;
+            if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                pools[dev] = pool;
+            }
+            cudaGetLastError();
+        }
+        return pools[dev];
+    }
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 }  // namespace
@@ -1732,8 +1764,8 @@ extern "C" {
 
 // evaluate_normalization_helper (src/utils.cpp:178-234): out_begins[0] = 0, strings packed back to back.  A chain of
 // normalisers (what the converter emits for one HF normaliser, e.g. the six ops of BertNormalizer, hf_parser.py:84-102)
-// stays on the device: the strings cross PCIe once each way.  With two or more ops, strings made only of ASCII bytes that
-// every op maps / drops one for one go through ONE composed byte table (compose_kernel); the rest run op by op.
+// stays on the device: the strings cross PCIe once each way.  Strings made only of ASCII bytes that every op maps / drops
+// one for one go through ONE composed byte table (compose_kernel) whatever the number of ops; the rest run op by op.
 B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n_ops, const int32_t* begins, const int32_t* ends, int64_t n,
                                             const uint8_t* chars, int64_t n_chars, const uint8_t* skips, int32_t* out_begins, int32_t* out_ends,
                                             uint8_t* out_chars, int64_t chars_capacity, int64_t* n_chars_out, int mem, void* stream) {
@@ -1762,7 +1794,7 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
     uint8_t T[128];
     static const bool no_compose = [] { const char* e = getenv("B200TOK_DEBUG_FLAGS"); return e && (atoi(e) & 32); }();   // debug: always op by op
     AsyncBuf btab, blen, bgen, bidx, bscan, btot, bsb, bse, bob, boe, boc;
-    if (n_ops >= 2 && !no_compose && compose_chain(handles, n_ops, T)) {
+    if (!no_compose && compose_chain(handles, n_ops, T)) {      // (a single op too: its all-ASCII strings skip the general step)
         const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);
         const unsigned blocks = (unsigned)((warps + 7) / 8), tblocks = (unsigned)((n + 255) / 256);
         CU(btab.alloc(128, st)); CU(blen.alloc((size_t)n * 4, st)); CU(bgen.alloc((size_t)n * 4, st)); CU(bidx.alloc((size_t)n * 4, st)); CU(btot.alloc(16, st));
