@@ -1524,10 +1524,16 @@ B200TOK_API int b200tok_bytes_to_chars_run(int device, const b200tok_ragged_stri
     CU(blen.alloc((size_t)E * 4, st)); CU(btot.alloc(8, st));
     int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
     if (host) { CU(bob.alloc((size_t)E * 4, st)); CU(boe.alloc((size_t)E * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
-    const unsigned blocks = (unsigned)((E + 255) / 256);
-    b2c_len_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, d_s, E, bt.as<uint16_t>(), blen.as<int32_t>());
+    // the scan "one byte in, one or two bytes out" on the warp-per-string kernel of the normalisers (kernels_norm.cuh)
+    NormRule R{};
+    R.kind = NORM_B2C; R.literal_cp = -1; R.global = 1;
+    R.normalized = bt.as<uint8_t>(); R.n_normalized = 512;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned blocks = (unsigned)((std::min<int64_t>(E, (int64_t)sms * 64) + 7) / 8);
+    normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
     if ((rc = scan_i32(bscan, blen.as<int32_t>(), d_ob, E, st))) return rc;
-    b2c_write_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, d_s, E, bt.as<uint16_t>(), d_ob, blen.as<int32_t>(), d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), d_ob, 0, nullptr, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
     CU(cudaGetLastError());
     int64_t total = 0;
     CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1645,10 +1651,15 @@ B200TOK_API int b200tok_utf8_validate_run(int device, const int32_t* begins, con
     CU(blen.alloc((size_t)n * 4, st)); CU(boff.alloc((size_t)n * 4, st)); CU(btot.alloc(8, st));
     int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
     if (host) { CU(bob.alloc((size_t)n * 4, st)); CU(boe.alloc((size_t)n * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
-    const unsigned blocks = (unsigned)((n + 127) / 128);
-    utf8_len_kernel<<<blocks, 128, 0, st>>>(d_b, d_e, d_c, n, replace_mode, blen.as<int32_t>());
+    // the reference's byte automaton as the scan "at a start byte: consume c, emit o" (tok_core.cuh norm_eval, NORM_UTF8)
+    NormRule R{};
+    R.kind = NORM_UTF8; R.literal_cp = -1; R.global = replace_mode != 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned blocks = (unsigned)((std::min<int64_t>(n, (int64_t)sms * 64) + 7) / 8);
+    normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, nullptr, n, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
     if ((rc = scan_i32(bscan, blen.as<int32_t>(), boff.as<int32_t>(), n, st))) return rc;
-    utf8_write_kernel<<<blocks, 128, 0, st>>>(d_b, d_e, d_c, n, replace_mode, base, boff.as<int32_t>(), blen.as<int32_t>(), d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, nullptr, n, blen.as<int32_t>(), boff.as<int32_t>(), base, d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
     CU(cudaGetLastError());
     int64_t total = 0;
     CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1743,14 +1754,14 @@ int run_ops(const b200tok_handle* handles, int n_ops, const int32_t*& d_b, const
         const int w = k & 1;
         B.ob[w] = std::make_unique<AsyncBuf>(); B.oe[w] = std::make_unique<AsyncBuf>(); B.oc[w] = std::make_unique<AsyncBuf>();
         CU(B.ob[w]->alloc((size_t)n * 4, st)); CU(B.oe[w]->alloc((size_t)n * 4, st));
-        normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), nullptr, nullptr, nullptr, 0, nullptr);
+        normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
         if ((rc = scan_i32(B.scan, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), n, st))) return rc;
         normalize_total_kernel<<<1, 1, 0, st>>>(B.ob[w]->as<int32_t>(), B.len.as<int32_t>(), n, B.tot.as<int64_t>());
         CU(cudaMemcpyAsync(&total, B.tot.p, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));                    // the size of this op's result
         if (total > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "normalised text exceeds 2^31 bytes");
         CU(B.oc[w]->alloc((size_t)total + 16, st));
-        normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), B.oe[w]->as<int32_t>(),
+        normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), 0, nullptr, B.oe[w]->as<int32_t>(),
                                                        B.oc[w]->as<uint8_t>(), total, B.tot.as<int64_t>());
         CU(cudaGetLastError());
         { std::lock_guard<std::mutex> lock(o->mu); o->launches += 3; }

@@ -17,17 +17,19 @@ template <bool WRITE>
 __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ NormRule R, const int32_t* __restrict__ begins,
                                                         const int32_t* __restrict__ ends, const uint8_t* __restrict__ chars,
                                                         const uint8_t* __restrict__ skips, int64_t n, int32_t* __restrict__ len,
-                                                        const int32_t* __restrict__ out_begins, int32_t* __restrict__ out_ends,
-                                                        uint8_t* __restrict__ out, int64_t cap, int64_t* total) {
+                                                        const int32_t* __restrict__ off, int32_t base, int32_t* __restrict__ out_begins,
+                                                        int32_t* __restrict__ out_ends, uint8_t* __restrict__ out, int64_t cap, int64_t* total) {
+    // off = exclusive scan of len; the strings go to base + off[i] (UTF8Validate starts its cursor at begins[0]); out_begins is
+    // written when given (the normalisers scan straight into it and pass nullptr)
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < n; i += nwarps) {
         const int b = begins[i], e = ends[i];
         int64_t o0 = 0;
         if (WRITE) {
-            o0 = out_begins[i];
+            o0 = (int64_t)base + off[i];
             const int64_t oe = o0 + len[i];
-            if (lane == 0) { out_ends[i] = (int32_t)oe; if (i == n - 1) *total = oe; }
+            if (lane == 0) { if (out_begins) out_begins[i] = (int32_t)o0; out_ends[i] = (int32_t)oe; if (i == n - 1) *total = oe; }
             if (oe > cap) continue;
         }
         if (skips && skips[i]) {          // src/utils.cpp:211: the string is copied unchanged
@@ -48,21 +50,30 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
             // ---- a chunk of ASCII bytes: every byte is a step of its own, straight from the per-byte tables ----
             bool fast = __ballot_sync(FULL, byte >= 0x80u) == 0u;
             uint32_t mapped = byte;
+            int folen = 1;                    // output bytes of this lane's byte on the fast path
             if (fast) {
-                const uint32_t fl = __ldg(R.atab + 128 + byte);
-                if (R.kind == NORM_CHARSMAP) {
-                    mapped = __ldg(R.atab + byte);
-                    bool slow = (fl & (NA_COMPLEX | NA_ASCII_KIDS)) != 0;
-                    if (lane == 31 && (fl & NA_OTHER_KIDS) && pos + 1 < e && chars[pos + 1] >= 0x80u) slow = true;   // a rule may run into the next chunk
-                    fast = __ballot_sync(FULL, valid && slow) == 0u;
+                if (R.kind == NORM_B2C) {
+                    folen = reinterpret_cast<const uint16_t*>(R.normalized)[byte] >= 0x80 ? 2 : 1;
+                    st.matched = valid && folen == 2;
+                } else if (R.kind == NORM_UTF8) {
+                    st.matched = 0;               // ASCII is copied
                 } else {
-                    const bool in_class = R.any || (R.literal_cp >= 0 ? (int32_t)byte == R.literal_cp : (fl & R.mask) != 0);
-                    st.matched = valid && in_class != (R.negate != 0) && (!R.anchored || pos == b) && (R.global || !done);
+                    const uint32_t fl = __ldg(R.atab + 128 + byte);
+                    if (R.kind == NORM_CHARSMAP) {
+                        mapped = __ldg(R.atab + byte);
+                        bool slow = (fl & (NA_COMPLEX | NA_ASCII_KIDS)) != 0;
+                        if (lane == 31 && (fl & NA_OTHER_KIDS) && pos + 1 < e && chars[pos + 1] >= 0x80u) slow = true;   // a rule may run into the next chunk
+                        fast = __ballot_sync(FULL, valid && slow) == 0u;
+                    } else {
+                        const bool in_class = R.any || (R.literal_cp >= 0 ? (int32_t)byte == R.literal_cp : (fl & R.mask) != 0);
+                        st.matched = valid && in_class != (R.negate != 0) && (!R.anchored || pos == b) && (R.global || !done);
+                        folen = (int)R.pre_len + (R.keep ? 1 : 0) + (int)R.post_len;
+                    }
                 }
             }
             if (fast) {
-                uint32_t hits = R.kind == NORM_CLASS ? __ballot_sync(FULL, st.matched) : 0u;
-                if (hits && !R.global) {                 // only the first match of the string is replaced
+                uint32_t hits = (R.kind == NORM_CLASS || R.kind == NORM_B2C) ? __ballot_sync(FULL, st.matched) : 0u;
+                if (hits && !R.global && R.kind == NORM_CLASS) {                 // only the first match of the string is replaced
                     done = true;
                     st.matched = st.matched && lane == __ffs(hits) - 1;
                     hits &= 0u - hits;
@@ -72,8 +83,8 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
                     if (WRITE && valid) out[o0 + o + __popc(vmask & ((1u << lane) - 1u))] = (uint8_t)mapped;
                     o += __popc(vmask);
                 } else {
-                    st.consumed = 1; st.src = st.matched ? -1 : -2;
-                    st.olen = st.matched ? (int32_t)R.pre_len + (R.keep ? 1 : 0) + (int32_t)R.post_len : 1;
+                    st.consumed = 1; st.src = R.kind == NORM_B2C ? -4 : st.matched ? -1 : -2;
+                    st.olen = st.matched ? folen : 1;
                     int incl = valid ? st.olen : 0;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }

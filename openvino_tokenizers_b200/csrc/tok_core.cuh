@@ -1034,8 +1034,18 @@ B2_HD void special_split_element(const SpecialTables& ST, const ClassTables& T, 
 // the host scan below (tests) and the kernel (kernels_norm.cuh), which evaluates 32 positions at once and resolves which
 // of them the scan really visits.
 // ------------------------------------------------------------------------------------------
+// GPT-2 byte -> code point map (public algorithm of the GPT-2 encoder: printable Latin-1 bytes map to themselves, the other
+// 68 bytes to U+0100 + n in byte order); the table BytesToChars indexes (reference src/bytes_to_chars.cpp:11-268).
+inline void gpt2_build_byte_codepoints(uint16_t* cp) {
+    int n = 0;
+    for (int b = 0; b < 256; ++b) {
+        const bool keep = (b >= '!' && b <= '~') || (b >= 0xA1 && b <= 0xAC) || (b >= 0xAE && b <= 0xFF);
+        cp[b] = keep ? (uint16_t)b : (uint16_t)(256 + n++);
+    }
+}
+
 enum : uint8_t { NC_DEL = 1, NC_S = 2, NC_HAN = 4, NC_MN = 8 };   // flags of the second class table (unicode_norm_ranges.inc)
-enum : int { NORM_CLASS = 0, NORM_CHARSMAP = 1 };
+enum : int { NORM_CLASS = 0, NORM_CHARSMAP = 1, NORM_B2C = 2, NORM_UTF8 = 3 };   // + BytesToChars, UTF8Validate: the same kind of scan
 
 struct NormRule {
     int32_t kind;
@@ -1068,7 +1078,8 @@ enum : uint8_t { NA_COMPLEX = 1, NA_ASCII_KIDS = 2, NA_OTHER_KIDS = 4 };   // re
 struct NormStep {
     int32_t consumed;    // input bytes
     int32_t olen;        // output bytes
-    int32_t src;         // >= 0: copy from normalized + src; -1: the rule's pre/char/post; -2: input bytes verbatim; -3: U+FFFD
+    int32_t src;         // >= 0: copy from normalized + src; -1: the rule's pre/char/post; -2: input bytes verbatim; -3: olen / 3 x U+FFFD;
+                         // -4: the byte's BytesToChars character (1 or 2 bytes)
     uint8_t matched;     // NORM_CLASS: the character matched the class
 };
 
@@ -1137,6 +1148,29 @@ B2_HD NormStep norm_eval(const NormRule& R, const uint8_t* s, int b, int i, int 
         else { st.consumed = l; st.olen = l; st.src = -2; }
         return st;
     }
+    if (R.kind == NORM_B2C) {          // reference src/bytes_to_chars.cpp:284-339: every byte becomes one character of the GPT-2 byte map
+        const uint16_t c = reinterpret_cast<const uint16_t*>(R.normalized)[s[i]];
+        st.consumed = 1; st.olen = c >= 0x80 ? 2 : 1; st.src = -4;
+        return st;
+    }
+    if (R.kind == NORM_UTF8) {         // reference src/utf8_validate.cpp:18-137 as "at a start byte: consume c, emit o"; R.global = replace mode
+        const uint32_t c = s[i];
+        const int bad = R.global ? 3 : 0;
+        st.src = -3;
+        if (c < 128) { st.consumed = 1; st.olen = 1; st.src = -2; return st; }
+        const int num = (c >> 5) == 0b110 ? 2 : (c >> 4) == 0b1110 ? 3 : (c >> 3) == 0b11110 ? 4 : 0;
+        if (!num) { st.consumed = 1; st.olen = bad; return st; }               // a continuation or 11111xxx byte at a start position (:80-87)
+        uint32_t v = num == 2 ? (c & 0b11111u) << 6 : num == 3 ? (c & 0b1111u) << 12 : (c & 0b111u) << 18;
+        for (int j = 1; j < num; ++j) {
+            if (i + j >= e || (s[i + j] >> 6) != 0b10) { st.consumed = j; st.olen = bad; return st; }   // broken (:96-105; the byte starts anew) or unfinished (:131-134)
+            v |= (uint32_t)(s[i + j] & 0b111111u) << (6 * (num - 1 - j));
+        }
+        st.consumed = num;
+        const uint32_t starts = num == 2 ? 0x80u : num == 3 ? 0x800u : 0x10000u;
+        if (v < starts) st.olen = bad * num;                                      // overlong: one replacement per byte (:112-122)
+        else { st.olen = num; st.src = -2; }
+        return st;
+    }
     // malformed bytes never match and pass through one at a time (PCRE2 runs with NO_UTF_CHECK: out of contract)
     const int l = utf8_strict_len(s, i, e, cp);
     st.consumed = l ? l : 1;
@@ -1161,7 +1195,12 @@ B2_HD NormStep norm_eval(const NormRule& R, const uint8_t* s, int b, int i, int 
 B2_HD void norm_emit(const NormRule& R, const NormStep& st, const uint8_t* s, int i, uint8_t* out) {
     if (st.src >= 0) { for (int k = 0; k < st.olen; ++k) out[k] = R.normalized[st.src + k]; }
     else if (st.src == -2) { for (int k = 0; k < st.olen; ++k) out[k] = s[i + k]; }
-    else if (st.src == -3) { out[0] = 0xEF; out[1] = 0xBF; out[2] = 0xBD; }
+    else if (st.src == -3) { for (int k = 0; k < st.olen; k += 3) { out[k] = 0xEF; out[k + 1] = 0xBF; out[k + 2] = 0xBD; } }
+    else if (st.src == -4) {
+        const uint16_t c = reinterpret_cast<const uint16_t*>(R.normalized)[s[i]];
+        if (c < 0x80) out[0] = (uint8_t)c;
+        else { out[0] = (uint8_t)(0xC0 | (c >> 6)); out[1] = (uint8_t)(0x80 | (c & 0x3F)); }
+    }
     else {
         int o = 0;
         for (int k = 0; k < R.pre_len; ++k) out[o++] = R.pre[k];

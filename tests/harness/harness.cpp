@@ -309,13 +309,22 @@ HZ int64_t hz_normalize(int kind, const uint8_t* a, int64_t alen, const uint8_t*
                         int64_t cap) {
     HostNorm hn;
     std::string err;
-    const int rc = kind == 0 ? parse_regex_norm((const char*)a, alen, (const char*)b, blen, flag, hn, err) : parse_charsmap(a, alen, 0, 0, 0, hn, err);
-    if (rc) return rc;
+    uint16_t b2c[256];
+    if (kind == 2 || kind == 3) {      // BytesToChars / UTF8Validate(flag = replace mode) run on the same scan (api.cu builds these rules inline)
+        hn.rule = NormRule{};
+        hn.rule.kind = kind == 2 ? NORM_B2C : NORM_UTF8;
+        hn.rule.literal_cp = -1;
+        hn.rule.global = kind == 2 ? 1 : (flag != 0);
+    } else {
+        const int rc = kind == 0 ? parse_regex_norm((const char*)a, alen, (const char*)b, blen, flag, hn, err) : parse_charsmap(a, alen, 0, 0, 0, hn, err);
+        if (rc) return rc;
+    }
     NormRule R = hn.rule;
     R.cls = host_norm_class_tables().view();
     R.units = hn.units.data(); R.n_units = (uint32_t)hn.units.size();
     R.normalized = hn.normalized.data(); R.n_normalized = (uint32_t)hn.normalized.size();
     R.atab = hn.atab.data();
+    if (kind == 2) { gpt2_build_byte_codepoints(b2c); R.normalized = reinterpret_cast<const uint8_t*>(b2c); R.n_normalized = 512; }
     int64_t cur = 0;
     for (int64_t i = 0; i < n; ++i) {
         ob[i] = (int32_t)cur;

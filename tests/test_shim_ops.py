@@ -32,6 +32,34 @@ def test_oracle_byte_char_map_is_the_reference_table(oracle_mod):
     assert bytes(back[2]) == bytes(range(256)) and back[0].tolist() == [0] and back[1].tolist() == [256]
 
 
+def test_host_scan_utf8_validate_and_bytes_to_chars_vs_oracle(oracle_mod):
+    """UTF8Validate and BytesToChars run on the warp-per-string scan kernel of the normalisers; its per-position step
+    (tok_core.cuh norm_eval, compiled for the host) against the oracle's restatement of the reference loops."""
+    import hostcore
+    for c in GOLDEN["utf8_validate"]:
+        s = bytes.fromhex(c["input_hex"])
+        b, e, ch = pack_strings([s])
+        got = hostcore.hz_normalize(3, b"", b"", c["mode"] == "replace", b, e, ch)
+        assert bytes(got[2]).hex() == c["expected_hex"], (s, c["mode"])
+    rng = np.random.default_rng(35)
+    alphabet = [b"a", b" ", "é".encode(), "€".encode(), "😁".encode(), b"\x80", b"\xc3", b"\xe2\x82", b"\xf0\x9f", b"\xc0\x80", b"\xff", b"\xed\xa0\x80",
+                b"\xe0\x80\x80", b"\xf0\x80\x80\x80", b"\xf8", b"\xf4\x90\x80\x80"]
+    strings = [b"".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=int(rng.integers(0, 50)))) for _ in range(3000)]
+    strings += [s.encode() for s in cases.EDGE_STRINGS] + [b"", b"\xe2", b"\xf0\x9f\x98"]
+    b, e, ch = pack_strings(strings)
+    for mode in (False, True):
+        exp = oracle_mod.utf8_validate(b, e, ch, mode)
+        got = hostcore.hz_normalize(3, b"", b"", mode, b, e, ch)
+        assert [bytes(x) for x in unpack_strings(*got)] == [bytes(x) for x in unpack_strings(*exp)], mode
+    strings = [bytes(rng.integers(0, 256, size=int(rng.integers(0, 70)), dtype=np.uint8)) for _ in range(2000)] + [b"", bytes(range(256))]
+    b, e, ch = pack_strings(strings)
+    rb, re_ = add_ragged_dimension(b, e)
+    skips = rng.integers(0, 2, size=len(strings)).astype(np.uint8)
+    exp = oracle_mod.bytes_to_chars(rb, re_, b, e, ch, skips.astype(bool))
+    got = hostcore.hz_normalize(2, b"", b"", 0, b, e, ch, skips)
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+
+
 @pytest.fixture(scope="module")
 def ops():
     from openvino_tokenizers_b200 import ops as O
