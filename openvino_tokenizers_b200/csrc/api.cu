@@ -1489,6 +1489,23 @@ int scan_i32(AsyncBuf& tmp, const int32_t* in, int32_t* out, int64_t n, cudaStre
     cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st);
     return 0;
 }
+// One pass (lengths or write) of a scan rule over n strings: a warp per string, or a thread per string when the strings are
+// short on average (pieces, per-token strings).
+template <bool WRITE>
+void launch_norm(const NormRule& R, int device, int64_t n_chars, const int32_t* b, const int32_t* e, const uint8_t* c, const uint8_t* sk, int64_t n,
+                 int32_t* len, const int32_t* off, int32_t base, int32_t* ob, int32_t* oe, uint8_t* oc, int64_t cap, int64_t* tot, cudaStream_t st) {
+    const char* force = getenv("B200TOK_NORM_PATH");          // tests: "warp" / "thread" pin the path
+    const bool short_strings = force && force[0] == 't' ? true : force && force[0] == 'w' ? false : n_chars < 48 * n;
+    if (short_strings) {
+        normalize_short_kernel<WRITE><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R, b, e, c, sk, n, len, off, base, ob, oe, oc, cap, tot);
+        return;
+    }
+    static int sms[64] = {};
+    const int d = device >= 0 && device < 64 ? device : 0;
+    if (!sms[d]) { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device); sms[d] = v; }
+    const unsigned blocks = (unsigned)((std::min<int64_t>(n, (int64_t)sms[d] * 64) + 7) / 8);      // 8 CTAs of 8 warps per SM, strings strided over them
+    normalize_kernel<WRITE><<<blocks, 256, 0, st>>>(R, b, e, c, sk, n, len, off, base, ob, oe, oc, cap, tot);
+}
 bool rows_partition_elems(const b200tok_ragged_strings* in) {     // rows cover the elements contiguously and in order
     const int32_t *rb = in->ragged_begins, *re = in->ragged_ends;
     int32_t cur = 0;
@@ -1528,12 +1545,9 @@ B200TOK_API int b200tok_bytes_to_chars_run(int device, const b200tok_ragged_stri
     NormRule R{};
     R.kind = NORM_B2C; R.literal_cp = -1; R.global = 1;
     R.normalized = bt.as<uint8_t>(); R.n_normalized = 512;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const unsigned blocks = (unsigned)((std::min<int64_t>(E, (int64_t)sms * 64) + 7) / 8);
-    normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
+    launch_norm<false>(R, device, N, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, st);
     if ((rc = scan_i32(bscan, blen.as<int32_t>(), d_ob, E, st))) return rc;
-    normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), d_ob, 0, nullptr, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    launch_norm<true>(R, device, N, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), d_ob, 0, nullptr, d_oe, d_oc, chars_capacity, btot.as<int64_t>(), st);
     CU(cudaGetLastError());
     int64_t total = 0;
     CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1579,11 +1593,16 @@ B200TOK_API int b200tok_chars_to_bytes_run(int device, const b200tok_ragged_stri
     CU(cudaMemsetAsync(btot.p, 0, 8, st));
     int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
     if (host) { CU(bob.alloc((size_t)B * 4, st)); CU(boe.alloc((size_t)B * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
-    if (E > 0) {
-        const unsigned blocks = (unsigned)((E + 255) / 256);
-        c2b_len_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, E, blen.as<int32_t>());
+    AsyncBuf bee;
+    if (E > 0) {      // per element: the scan "a byte < 128 is itself, a byte >= 128 and its follower are one byte" on the warp-per-string kernel
+        NormRule R{};
+        R.kind = NORM_C2B; R.literal_cp = -1; R.global = 1;
+        R.normalized = bt.as<uint8_t>(); R.n_normalized = 256; R.n_units = (uint32_t)N;
+        CU(bee.alloc((size_t)E * 4, st));
+        launch_norm<false>(R, device, N, d_b, d_e, d_c, nullptr, E, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, st);
         if ((rc = scan_i32(bscan, blen.as<int32_t>(), boff.as<int32_t>(), E, st))) return rc;
-        c2b_write_kernel<<<blocks, 256, 0, st>>>(d_b, d_e, d_c, E, N, bt.as<uint8_t>(), boff.as<int32_t>(), blen.as<int32_t>(), d_oc, chars_capacity, btot.as<int64_t>());
+        launch_norm<true>(R, device, N, d_b, d_e, d_c, nullptr, E, blen.as<int32_t>(), boff.as<int32_t>(), 0, nullptr, bee.as<int32_t>(), d_oc, chars_capacity,
+                          btot.as<int64_t>(), st);
     }
     c2b_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_rb, d_re, B, boff.as<int32_t>(), blen.as<int32_t>(), E, d_ob, d_oe);
     CU(cudaGetLastError());
@@ -1654,12 +1673,9 @@ B200TOK_API int b200tok_utf8_validate_run(int device, const int32_t* begins, con
     // the reference's byte automaton as the scan "at a start byte: consume c, emit o" (tok_core.cuh norm_eval, NORM_UTF8)
     NormRule R{};
     R.kind = NORM_UTF8; R.literal_cp = -1; R.global = replace_mode != 0;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const unsigned blocks = (unsigned)((std::min<int64_t>(n, (int64_t)sms * 64) + 7) / 8);
-    normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, nullptr, n, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
+    launch_norm<false>(R, device, n_chars, d_b, d_e, d_c, nullptr, n, blen.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, st);
     if ((rc = scan_i32(bscan, blen.as<int32_t>(), boff.as<int32_t>(), n, st))) return rc;
-    normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, nullptr, n, blen.as<int32_t>(), boff.as<int32_t>(), base, d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>());
+    launch_norm<true>(R, device, n_chars, d_b, d_e, d_c, nullptr, n, blen.as<int32_t>(), boff.as<int32_t>(), base, d_ob, d_oe, d_oc, chars_capacity, btot.as<int64_t>(), st);
     CU(cudaGetLastError());
     int64_t total = 0;
     CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1745,24 +1761,24 @@ int run_ops(const b200tok_handle* handles, int n_ops, const int32_t*& d_b, const
             ChainBufs& B, int64_t& total, cudaStream_t st) {
     NormObj* first = static_cast<NormObj*>(handles[0]);
     CU(B.len.alloc((size_t)n * 4, st)); CU(B.tot.alloc(8, st));
-    const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);      // 8 CTAs of 8 warps per SM, strings strided over them
-    const unsigned blocks = (unsigned)((warps + 7) / 8);
     int rc;
+    int64_t n_chars = total;             // in: bytes of the strings the first op reads; then each op's result size
     for (int k = 0; k < n_ops; ++k) {
         NormObj* o = static_cast<NormObj*>(handles[k]);
         const NormRule R = o->view();
         const int w = k & 1;
         B.ob[w] = std::make_unique<AsyncBuf>(); B.oe[w] = std::make_unique<AsyncBuf>(); B.oc[w] = std::make_unique<AsyncBuf>();
         CU(B.ob[w]->alloc((size_t)n * 4, st)); CU(B.oe[w]->alloc((size_t)n * 4, st));
-        normalize_kernel<false><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr);
+        launch_norm<false>(R, first->device, n_chars, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, st);
         if ((rc = scan_i32(B.scan, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), n, st))) return rc;
         normalize_total_kernel<<<1, 1, 0, st>>>(B.ob[w]->as<int32_t>(), B.len.as<int32_t>(), n, B.tot.as<int64_t>());
         CU(cudaMemcpyAsync(&total, B.tot.p, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));                    // the size of this op's result
         if (total > INT32_MAX) return fail(B200TOK_E_UNSUPPORTED, "normalised text exceeds 2^31 bytes");
         CU(B.oc[w]->alloc((size_t)total + 16, st));
-        normalize_kernel<true><<<blocks, 256, 0, st>>>(R, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), 0, nullptr, B.oe[w]->as<int32_t>(),
-                                                       B.oc[w]->as<uint8_t>(), total, B.tot.as<int64_t>());
+        launch_norm<true>(R, first->device, n_chars, d_b, d_e, d_c, d_s, n, B.len.as<int32_t>(), B.ob[w]->as<int32_t>(), 0, nullptr, B.oe[w]->as<int32_t>(),
+                          B.oc[w]->as<uint8_t>(), total, B.tot.as<int64_t>(), st);
+        n_chars = total;
         CU(cudaGetLastError());
         { std::lock_guard<std::mutex> lock(o->mu); o->launches += 3; }
         d_b = B.ob[w]->as<int32_t>(); d_e = B.oe[w]->as<int32_t>(); d_c = B.oc[w]->as<uint8_t>();
@@ -1805,7 +1821,9 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
     uint8_t T[128];
     static const bool no_compose = [] { const char* e = getenv("B200TOK_DEBUG_FLAGS"); return e && (atoi(e) & 32); }();   // debug: always op by op
     AsyncBuf btab, blen, bgen, bidx, bscan, btot, bsb, bse, bob, boe, boc;
-    if (!no_compose && compose_chain(handles, n_ops, T)) {      // (a single op too: its all-ASCII strings skip the general step)
+    const char* force = getenv("B200TOK_NORM_PATH");
+    const bool long_strings = force && force[0] == 't' ? false : force && force[0] == 'w' ? true : n_chars >= 48 * n;
+    if (!no_compose && long_strings && compose_chain(handles, n_ops, T)) {      // (short strings: one thread per string runs the ops, launch_norm)      // (a single op too: its all-ASCII strings skip the general step)
         const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);
         const unsigned blocks = (unsigned)((warps + 7) / 8), tblocks = (unsigned)((n + 255) / 256);
         CU(btab.alloc(128, st)); CU(blen.alloc((size_t)n * 4, st)); CU(bgen.alloc((size_t)n * 4, st)); CU(bidx.alloc((size_t)n * 4, st)); CU(btot.alloc(16, st));
@@ -1823,7 +1841,7 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
             CU(bsb.alloc((size_t)n_general * 4, st)); CU(bse.alloc((size_t)n_general * 4, st));
             gather_general_kernel<<<tblocks, 256, 0, st>>>(bgen.as<int32_t>(), bidx.as<int32_t>(), d_b, d_e, n, bsb.as<int32_t>(), bse.as<int32_t>());
             const int32_t* gb = bsb.as<int32_t>(); const int32_t* ge = bse.as<int32_t>(); const uint8_t* gc = d_c;
-            int64_t sub_total = 0;
+            int64_t sub_total = std::max<int64_t>(n_chars / n * n_general, 48 * n_general);      // (in: an estimate of the bytes these strings hold; they were long on average)
             if ((rc = run_ops(handles, n_ops, gb, ge, gc, nullptr, n_general, B, sub_total, st))) return rc;
             merge_general_len_kernel<<<tblocks, 256, 0, st>>>(bgen.as<int32_t>(), bidx.as<int32_t>(), gb, ge, n, blen.as<int32_t>());
             sub_b = gb; sub_c = gc;
@@ -1840,6 +1858,7 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
         { std::lock_guard<std::mutex> lock(first->mu); first->launches += 4 + (n_general > 0 ? 2 : 0); }
         d_b = bob.as<int32_t>(); d_e = boe.as<int32_t>(); d_c = boc.as<uint8_t>();
     } else {
+        total = n_chars;
         if ((rc = run_ops(handles, n_ops, d_b, d_e, d_c, d_s, n, B, total, st))) return rc;
     }
     *n_chars_out = total;

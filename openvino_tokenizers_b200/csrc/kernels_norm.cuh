@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
                 if (R.kind == NORM_B2C) {
                     folen = reinterpret_cast<const uint16_t*>(R.normalized)[byte] >= 0x80 ? 2 : 1;
                     st.matched = valid && folen == 2;
-                } else if (R.kind == NORM_UTF8) {
+                } else if (R.kind == NORM_UTF8 || R.kind == NORM_C2B) {
                     st.matched = 0;               // ASCII is copied
                 } else {
                     const uint32_t fl = __ldg(R.atab + 128 + byte);
@@ -125,6 +125,28 @@ __global__ void __launch_bounds__(256) normalize_kernel(const __grid_constant__ 
         }
         if (!WRITE && lane == 0) len[i] = o;
     }
+}
+
+// Short elements (pieces after a splitter, the per-token strings of a detokenizer: a handful of bytes each): one thread per
+// element runs the sequential scan itself (tok_core.cuh norm_string) — a warp per 5-byte string would idle 27 lanes.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) normalize_short_kernel(const __grid_constant__ NormRule R, const int32_t* __restrict__ begins,
+                                                              const int32_t* __restrict__ ends, const uint8_t* __restrict__ chars,
+                                                              const uint8_t* __restrict__ skips, int64_t n, int32_t* __restrict__ len,
+                                                              const int32_t* __restrict__ off, int32_t base, int32_t* __restrict__ out_begins,
+                                                              int32_t* __restrict__ out_ends, uint8_t* __restrict__ out, int64_t cap, int64_t* total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = begins[i], e = ends[i];
+    const bool skip = skips && skips[i];
+    if (!WRITE) { len[i] = skip ? (e > b ? e - b : 0) : norm_string(R, chars, b, e, nullptr); return; }
+    const int64_t o0 = (int64_t)base + off[i], oe = o0 + len[i];
+    if (out_begins) out_begins[i] = (int32_t)o0;
+    out_ends[i] = (int32_t)oe;
+    if (i == n - 1) *total = oe;
+    if (oe > cap) return;
+    if (skip) { for (int k = b; k < e; ++k) out[o0 + (k - b)] = chars[k]; }
+    else norm_string(R, chars, b, e, out + o0);
 }
 
 // Size of a result: offset of the last string + its length.

@@ -1045,7 +1045,7 @@ inline void gpt2_build_byte_codepoints(uint16_t* cp) {
 }
 
 enum : uint8_t { NC_DEL = 1, NC_S = 2, NC_HAN = 4, NC_MN = 8 };   // flags of the second class table (unicode_norm_ranges.inc)
-enum : int { NORM_CLASS = 0, NORM_CHARSMAP = 1, NORM_B2C = 2, NORM_UTF8 = 3 };   // + BytesToChars, UTF8Validate: the same kind of scan
+enum : int { NORM_CLASS = 0, NORM_CHARSMAP = 1, NORM_B2C = 2, NORM_UTF8 = 3, NORM_C2B = 4 };   // + BytesToChars, UTF8Validate, CharsToBytes: the same kind of scan
 
 struct NormRule {
     int32_t kind;
@@ -1079,7 +1079,7 @@ struct NormStep {
     int32_t consumed;    // input bytes
     int32_t olen;        // output bytes
     int32_t src;         // >= 0: copy from normalized + src; -1: the rule's pre/char/post; -2: input bytes verbatim; -3: olen / 3 x U+FFFD;
-                         // -4: the byte's BytesToChars character (1 or 2 bytes)
+                         // -4: the byte's BytesToChars character (1 or 2 bytes); -5: the byte of a CharsToBytes pair
     uint8_t matched;     // NORM_CLASS: the character matched the class
 };
 
@@ -1153,6 +1153,11 @@ B2_HD NormStep norm_eval(const NormRule& R, const uint8_t* s, int b, int i, int 
         st.consumed = 1; st.olen = c >= 0x80 ? 2 : 1; st.src = -4;
         return st;
     }
+    if (R.kind == NORM_C2B) {          // reference src/chars_to_bytes.cpp:52-60: a byte >= 128 takes the following byte with it (even past the element's end)
+        st.olen = 1;
+        if (s[i] < 128) { st.consumed = 1; st.src = -2; } else { st.consumed = 2; st.src = -5; }
+        return st;
+    }
     if (R.kind == NORM_UTF8) {         // reference src/utf8_validate.cpp:18-137 as "at a start byte: consume c, emit o"; R.global = replace mode
         const uint32_t c = s[i];
         const int bad = R.global ? 3 : 0;
@@ -1196,6 +1201,10 @@ B2_HD void norm_emit(const NormRule& R, const NormStep& st, const uint8_t* s, in
     if (st.src >= 0) { for (int k = 0; k < st.olen; ++k) out[k] = R.normalized[st.src + k]; }
     else if (st.src == -2) { for (int k = 0; k < st.olen; ++k) out[k] = s[i + k]; }
     else if (st.src == -3) { for (int k = 0; k < st.olen; k += 3) { out[k] = 0xEF; out[k + 1] = 0xBF; out[k + 2] = 0xBD; } }
+    else if (st.src == -5) {            // R.normalized = pair map [4 * 64] (src/chars_to_bytes.cpp:20-29), R.n_units = size of the chars buffer
+        const int fi = (int)s[i] - 194, si = ((uint32_t)(i + 1) < R.n_units ? (int)s[i + 1] : 128) - 128;
+        out[0] = (fi >= 0 && fi < 4 && si >= 0 && si < 64) ? R.normalized[fi * 64 + si] : 0;      // outside the map: 0 (the reference reads out of bounds)
+    }
     else if (st.src == -4) {
         const uint16_t c = reinterpret_cast<const uint16_t*>(R.normalized)[s[i]];
         if (c < 0x80) out[0] = (uint8_t)c;

@@ -18,3 +18,11 @@ def oracle_mod():
     import oracle
     oracle.build()
     return oracle
+
+
+@pytest.fixture(params=["warp", "thread"])
+def norm_path(request, monkeypatch):
+    """The scan kernels (normalisers, BytesToChars, CharsToBytes, UTF8Validate) have a warp-per-string and a
+    thread-per-string form chosen by the average string length; tests pin each in turn (B200TOK_NORM_PATH)."""
+    monkeypatch.setenv("B200TOK_NORM_PATH", request.param)
+    return request.param

@@ -310,11 +310,12 @@ HZ int64_t hz_normalize(int kind, const uint8_t* a, int64_t alen, const uint8_t*
     HostNorm hn;
     std::string err;
     uint16_t b2c[256];
-    if (kind == 2 || kind == 3) {      // BytesToChars / UTF8Validate(flag = replace mode) run on the same scan (api.cu builds these rules inline)
+    uint8_t pair_map[256] = {};
+    if (kind >= 2 && kind <= 4) {      // BytesToChars / UTF8Validate(flag = replace mode) / CharsToBytes elements run on the same scan (api.cu builds these rules inline)
         hn.rule = NormRule{};
-        hn.rule.kind = kind == 2 ? NORM_B2C : NORM_UTF8;
+        hn.rule.kind = kind == 2 ? NORM_B2C : kind == 3 ? NORM_UTF8 : NORM_C2B;
         hn.rule.literal_cp = -1;
-        hn.rule.global = kind == 2 ? 1 : (flag != 0);
+        hn.rule.global = kind == 3 ? (flag != 0) : 1;
     } else {
         const int rc = kind == 0 ? parse_regex_norm((const char*)a, alen, (const char*)b, blen, flag, hn, err) : parse_charsmap(a, alen, 0, 0, 0, hn, err);
         if (rc) return rc;
@@ -324,7 +325,12 @@ HZ int64_t hz_normalize(int kind, const uint8_t* a, int64_t alen, const uint8_t*
     R.units = hn.units.data(); R.n_units = (uint32_t)hn.units.size();
     R.normalized = hn.normalized.data(); R.n_normalized = (uint32_t)hn.normalized.size();
     R.atab = hn.atab.data();
-    if (kind == 2) { gpt2_build_byte_codepoints(b2c); R.normalized = reinterpret_cast<const uint8_t*>(b2c); R.n_normalized = 512; }
+    if (kind == 2 || kind == 4) gpt2_build_byte_codepoints(b2c);
+    if (kind == 2) { R.normalized = reinterpret_cast<const uint8_t*>(b2c); R.n_normalized = 512; }
+    if (kind == 4) {                   // flag = size of the chars buffer (the follower of a trailing lead byte may lie beyond the element)
+        for (int x = 0; x < 256; ++x) if (b2c[x] >= 0x80) pair_map[((0xC0 | (b2c[x] >> 6)) - 194) * 64 + ((0x80 | (b2c[x] & 0x3F)) - 128)] = (uint8_t)x;
+        R.normalized = pair_map; R.n_normalized = 256; R.n_units = (uint32_t)flag;
+    }
     int64_t cur = 0;
     for (int64_t i = 0; i < n; ++i) {
         ob[i] = (int32_t)cur;

@@ -179,7 +179,7 @@ def _strings_in(raw):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("step", STEPS, ids=lambda s: s["name"])
-def test_gpu_regex_normalization_vs_oracle(step):
+def test_gpu_regex_normalization_vs_oracle(step, norm_path):
     from openvino_tokenizers_b200 import ops
     raw = NC.corpus(seed=21, n=3000, max_len=90) + NC.ascii_corpus(seed=24, n=600)
     ins = _strings_in(raw)
@@ -217,7 +217,7 @@ def test_gpu_regex_normalization_reference_vectors():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["nfkc_cf", "nmt_nfkc", "nfd_cf", "nfd", "nfc", "casefold", "empty", "custom"])
-def test_gpu_charsmap_normalization_vs_oracle(which):
+def test_gpu_charsmap_normalization_vs_oracle(which, norm_path):
     from openvino_tokenizers_b200 import ops
     blob = {"custom": NC.custom_blob, "nfc": lambda: NC.unicodedata_blob("NFC", False), "nfkc_cf": lambda: NC.builtin_blob("nfkc_cf"), "nmt_nfkc": lambda: NC.builtin_blob("nmt_nfkc"), "nfd_cf": lambda: NC.unicodedata_blob("NFD", True),
             "nfd": lambda: NC.unicodedata_blob("NFD", False), "casefold": lambda: NC.unicodedata_blob(None, True), "empty": lambda: b""}[which]()
@@ -238,7 +238,7 @@ def test_gpu_charsmap_normalization_vs_oracle(which):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("chain", ["bert", "custom", "anchored", "expanding"])
-def test_gpu_chain_mixed_vs_oracle(chain):
+def test_gpu_chain_mixed_vs_oracle(chain, norm_path):
     """Chains over a batch that mixes all-ASCII strings (one composed byte table), strings the ops must run one by one
     (non-ASCII, bytes with multi-byte rules) and skip-flagged strings; with an anchored op the chain is not composable."""
     from openvino_tokenizers_b200 import ops

@@ -58,6 +58,16 @@ def test_host_scan_utf8_validate_and_bytes_to_chars_vs_oracle(oracle_mod):
     exp = oracle_mod.bytes_to_chars(rb, re_, b, e, ch, skips.astype(bool))
     got = hostcore.hz_normalize(2, b"", b"", 0, b, e, ch, skips)
     assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+    # CharsToBytes, element level (one element per row), on the characters BytesToChars produced; every 5th element is cut
+    # right after a lead byte, so its last character reads the follower from beyond the element (src/chars_to_bytes.cpp:52-60)
+    cb, ce, cc = oracle_mod.bytes_to_chars(rb, re_, b, e, ch)
+    cb, ce = cb.copy(), ce.copy()
+    for k in range(0, len(cb), 5):
+        if ce[k] - cb[k] >= 2 and cc[ce[k] - 1] < 0xC0 and cc[ce[k] - 2] >= 0xC0:      # ends with a 2-byte character: drop its follower
+            ce[k] -= 1
+    exp = oracle_mod.chars_to_bytes(rb, re_, cb, ce, cc)
+    got = hostcore.hz_normalize(4, b"", b"", int(cc.size), cb, ce, cc)
+    assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
 
 
 @pytest.fixture(scope="module")
@@ -76,7 +86,7 @@ def _ragged(rng, strings, rows):
 
 
 @pytest.mark.gpu
-def test_gpu_bytes_to_chars_and_back(ops, oracle_mod):
+def test_gpu_bytes_to_chars_and_back(ops, oracle_mod, norm_path):
     rng = np.random.default_rng(31)
     strings = [bytes(rng.integers(0, 256, size=int(rng.integers(0, 40)), dtype=np.uint8)) for _ in range(3000)] + [b"", bytes(range(256))]
     for rows in (1, 7, 500):
@@ -93,6 +103,15 @@ def test_gpu_bytes_to_chars_and_back(ops, oracle_mod):
             assert np.array_equal(back[k], back_exp[k])
         rows_bytes = [b"".join(strings[int(rb[r]):int(re_[r])]) for r in range(rows)]
         assert [bytes(x) for x in unpack_strings(back[0], back[1], back[2])] == rows_bytes
+        # elements cut right after a lead byte: the follower is read from beyond the element (src/chars_to_bytes.cpp:52-60)
+        cb, ce, cc = exp[0].copy(), exp[1].copy(), exp[2]
+        for k in range(0, len(cb), 5):
+            if ce[k] - cb[k] >= 2 and cc[ce[k] - 1] < 0xC0 and cc[ce[k] - 2] >= 0xC0:
+                ce[k] -= 1
+        back_exp = oracle_mod.chars_to_bytes(rb, re_, cb, ce, cc)
+        back = ops.CharsToBytes().evaluate([rb, re_, cb, ce, cc])
+        for k in range(3):
+            assert np.array_equal(back[k], back_exp[k])
 
 
 @pytest.mark.gpu
@@ -109,7 +128,7 @@ def test_gpu_fuze_ragged(ops, oracle_mod):
 
 
 @pytest.mark.gpu
-def test_gpu_utf8_validate(ops, oracle_mod):
+def test_gpu_utf8_validate(ops, oracle_mod, norm_path):
     for c in GOLDEN["utf8_validate"]:
         s = bytes.fromhex(c["input_hex"])
         b, e, ch = pack_strings([s])

@@ -51,3 +51,11 @@ n2 = got.value
 b2, e2, c2 = ob.clone(), oe.clone(), oc[: n2 + 64].clone()
 rin2 = K.RaggedStrings(d[0].data_ptr(), d[1].data_ptr(), B, b2.data_ptr(), e2.data_ptr(), B, c2.data_ptr(), n2, None, K.MEM_DEVICE)
 timeit("CharsToBytes", lambda: K.check(lib.b200tok_chars_to_bytes_run(0, C.byref(rin2), P(ob), P(oe), P(oc), C.c_int64(cap), C.byref(got), st)))
+# short elements (the realistic shape for BytesToChars / CharsToBytes: pieces and per-token strings): 8-byte elements
+E8 = N // 8
+b8 = torch.arange(0, E8, dtype=torch.int32, device=dev) * 8
+e8 = b8 + 8
+r8b = torch.arange(0, E8, dtype=torch.int32, device=dev); r8e = r8b + 1
+ob8 = torch.empty(E8, dtype=torch.int32, device=dev); oe8 = torch.empty_like(ob8)
+rin8 = K.RaggedStrings(r8b.data_ptr(), r8e.data_ptr(), E8, b8.data_ptr(), e8.data_ptr(), E8, dc.data_ptr(), N, None, K.MEM_DEVICE)
+timeit("B2C 8-byte elems", lambda: K.check(lib.b200tok_bytes_to_chars_run(0, C.byref(rin8), P(ob8), P(oe8), P(oc), C.c_int64(cap), C.byref(got), st)))
