@@ -1823,6 +1823,7 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
     AsyncBuf btab, blen, bgen, bidx, bscan, btot, bsb, bse, bob, boe, boc;
     const char* force = getenv("B200TOK_NORM_PATH");
     const bool long_strings = force && force[0] == 't' ? false : force && force[0] == 'w' ? true : n_chars >= 48 * n;
+    bool composed = false;
     if (!no_compose && long_strings && compose_chain(handles, n_ops, T)) {      // (short strings: one thread per string runs the ops, launch_norm)      // (a single op too: its all-ASCII strings skip the general step)
         const int64_t warps = std::min<int64_t>(n, (int64_t)first->sm_count * 8 * 8);
         const unsigned blocks = (unsigned)((warps + 7) / 8), tblocks = (unsigned)((n + 255) / 256);
@@ -1837,6 +1838,8 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
         CU(cudaMemcpyAsync(&n_general, btot.p, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         const int32_t* sub_b = nullptr; const uint8_t* sub_c = nullptr;
+        composed = 2 * n_general <= n;      // mostly strings that need the ops one by one: run them over the whole batch, no gather / copy-back
+        if (composed) {
         if (n_general > 0) {              // these strings run op by op, as a list of their own over the same chars
             CU(bsb.alloc((size_t)n_general * 4, st)); CU(bse.alloc((size_t)n_general * 4, st));
             gather_general_kernel<<<tblocks, 256, 0, st>>>(bgen.as<int32_t>(), bidx.as<int32_t>(), d_b, d_e, n, bsb.as<int32_t>(), bse.as<int32_t>());
@@ -1857,7 +1860,9 @@ B200TOK_API int b200tok_normalize_chain_run(const b200tok_handle* handles, int n
         CU(cudaGetLastError());
         { std::lock_guard<std::mutex> lock(first->mu); first->launches += 4 + (n_general > 0 ? 2 : 0); }
         d_b = bob.as<int32_t>(); d_e = boe.as<int32_t>(); d_c = boc.as<uint8_t>();
-    } else {
+        }
+    }
+    if (!composed) {
         total = n_chars;
         if ((rc = run_ops(handles, n_ops, d_b, d_e, d_c, d_s, n, B, total, st))) return rc;
     }

@@ -243,14 +243,16 @@ def test_gpu_chain_mixed_vs_oracle(chain, norm_path):
     (non-ASCII, bytes with multi-byte rules) and skip-flagged strings; with an anchored op the chain is not composable."""
     from openvino_tokenizers_b200 import ops
     steps = _chain_steps(chain)
-    raw = NC.corpus(seed=31, n=2500, max_len=90) + NC.ascii_corpus(seed=32, n=1500) + [b"", b"plain ascii only", b"TAB\tand\x01ctl"]
-    ins = _strings_in(raw)
     prepared = [ops.RegexNormalization(g).prepare(a, b_) if kind == "regex" else ops.CharsMapNormalization().prepare(a) for kind, a, b_, g in steps]
-    for skips in (None, (np.arange(len(raw)) % 6 == 2)):
-        exp = _oracle_chain(steps, ins, skips)
-        got = ops.normalize_chain(prepared, ins + ([skips] if skips is not None else []))
-        assert NC.unpack(*got[:3]) == NC.unpack(*exp[:3])
-        assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()
+    # mostly non-ASCII strings (the ops run over the whole batch) and mostly ASCII ones (composed table + a gathered sub-list)
+    for n_mixed, n_ascii in ((2500, 1500), (700, 3000)):
+        raw = NC.corpus(seed=31, n=n_mixed, max_len=90) + NC.ascii_corpus(seed=32, n=n_ascii) + [b"", b"plain ascii only", b"TAB\tand\x01ctl"]
+        ins = _strings_in(raw)
+        for skips in (None, (np.arange(len(raw)) % 6 == 2)):
+            exp = _oracle_chain(steps, ins, skips)
+            got = ops.normalize_chain(prepared, ins + ([skips] if skips is not None else []))
+            assert NC.unpack(*got[:3]) == NC.unpack(*exp[:3])
+            assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()
     # all-ASCII batch: no string takes the op-by-op path
     raw = [r for r in NC.ascii_corpus(seed=33, n=800) if r.isascii()]
     ins = _strings_in(raw)
