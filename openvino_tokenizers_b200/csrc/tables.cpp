@@ -450,10 +450,14 @@ int build_bpe(const b200tok_bpe_desc& d, HostBpe& out, std::string& err) {
     // [0, 512): mergeable ASCII byte pairs; [512, 512 + 2048): for every first byte, the second bytes that continue a
     // token of the symbolisation trie (bit b1 of words [512 + 8 * b0, +8)) — lets the window kernel skip trie walks
     // [2560, 2560 + 8192): ranks of the ASCII pairs as u16 (index b0 << 7 | b1; 0xFFFF = none, 0xFFFE = rank too large for
-    // 16 bits, look in pair_rank) — 32 KB, stays L1-resident in the window kernel
-    out.pair_bits.assign(512 + 2048 + 8192, 0u);
+    // 16 bits, look in pair_rank) — 32 KB, stays L1-resident in the window kernel.  The table is allocated for a first byte
+    // up to 255 (another 32 KB of 0xFFFF that is never touched in normal operation): the window kernel indexes it with the byte
+    // BEFORE the window's first position too, whose rank is never used (a window starts at a piece start) but which may be any
+    // byte of the preceding text, or shared-memory garbage at the start of an element — found by compute-sanitizer.
+    out.pair_bits.assign(512 + 2048 + 16384, 0u);
     {
         uint16_t* r16 = reinterpret_cast<uint16_t*>(out.pair_bits.data() + 2560);
+        std::fill(r16 + 16384, r16 + 32768, (uint16_t)0xFFFF);
         for (int b0 = 0; b0 < 128; ++b0)
             for (int b1 = 0; b1 < 128; ++b1) {
                 const uint32_t r = out.pair_rank[(size_t)(b0 << 8 | b1)];
