@@ -311,6 +311,7 @@ __device__ __forceinline__ int split_window(WarpSmem& S, const RowParams& P, con
             if (!(last & F_MATCH)) { --ns; adv = last & POS_MASK; }   // trailing gap may continue: redo from its start
         }
         advance = adv;
+        __syncwarp();                               // every lane has read S.seg[ns - 1] before lane 0 reuses that slot (racecheck)
         if (lane == 0) S.seg[ns] = (uint16_t)adv;
     }
     __syncwarp();
