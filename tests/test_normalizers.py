@@ -90,6 +90,45 @@ def test_host_charsmap_scan_vs_oracle(which):
     assert NC.unpack(*got) == NC.unpack(*exp)
 
 
+def test_host_scan_property_random_unicode():
+    """Property test (hypothesis): for arbitrary Unicode strings the host scan of every supported RegexNormalization rule
+    equals PCRE2's substitute, and the charsmap scan equals the sentencepiece restatement — and, for arbitrary BYTES
+    (malformed UTF-8 included), the charsmap scan and UTF8Validate still equal their oracles."""
+    import hostcore
+    from hypothesis import given, settings, strategies as st
+
+    alphabet = st.one_of(st.characters(min_codepoint=1, max_codepoint=0x7F), st.characters(min_codepoint=0x80, max_codepoint=0x2FFF, exclude_categories=("Cs",)),
+                         st.sampled_from([chr(c) for c in NC.INTERESTING]))
+    blob = NC.unicodedata_blob("NFD", True)
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.lists(st.text(alphabet, max_size=80), min_size=1, max_size=8))
+    def text_case(strings):
+        raw = [s_.encode() for s_ in strings]
+        b, e, c = NC.pack(raw)
+        if not c.size:
+            return
+        for step in STEPS[:9]:
+            if oracle.pcre2_available():
+                exp = oracle.regex_normalize(step["search"], step["replace"], step["global_replace"], b, e, c)
+                got = hostcore.hz_normalize(0, _enc(step["search"]), _enc(step["replace"]), step["global_replace"], b, e, c)
+                assert NC.unpack(*got) == NC.unpack(*exp), (step["name"], raw)
+        assert NC.unpack(*hostcore.hz_normalize(1, blob, b"", 0, b, e, c)) == NC.unpack(*oracle.charsmap_normalize(blob, b, e, c))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.binary(max_size=60), min_size=1, max_size=8))
+    def bytes_case(raw):
+        b, e, c = NC.pack(raw)
+        if not c.size:
+            return
+        assert NC.unpack(*hostcore.hz_normalize(1, blob, b"", 0, b, e, c)) == NC.unpack(*oracle.charsmap_normalize(blob, b, e, c))
+        for mode in (False, True):
+            assert NC.unpack(*hostcore.hz_normalize(3, b"", b"", mode, b, e, c)) == NC.unpack(*oracle.utf8_validate(b, e, c, mode))
+
+    text_case()
+    bytes_case()
+
+
 def test_charsmap_ascii_shortcut_tables_agree_with_the_trie():
     import hostcore
     for blob in (NC.builtin_blob("nfkc"), NC.builtin_blob("nfkc_cf"), NC.builtin_blob("nmt_nfkc_cf"), NC.unicodedata_blob("NFD", True),
