@@ -10,6 +10,8 @@ output list — so the parity tests read like the reference's own op tests.
   VocabEncoder        src/vocab_encoder.{hpp,cpp}      8 inputs       -> 1 output
   VocabDecoder        src/vocab_decoder.{hpp,cpp}      4 / 5 inputs   -> 5 outputs
   ByteFallback        src/byte_fallback.{hpp,cpp}      3 inputs       -> 3 outputs
+and the ops either side of that path: SpecialTokensSplit, Truncate, CombineSegments, RaggedToDense,
+BytesToChars, CharsToBytes, FuzeRagged, UTF8Validate, RegexNormalization (single-character patterns), CharsMapNormalization.
 
 All compute happens in libb200tok.so on the GPU; this module only marshals pointers.  Tables are
 built on the first `evaluate` from the Constant inputs (as the reference does under call_once).
@@ -23,6 +25,8 @@ import numpy as np
 from . import _capi as K
 
 __all__ = ["RegexSplit", "BPETokenizer", "WordpieceTokenizer", "VocabEncoder", "VocabDecoder", "ByteFallback",
+           "SpecialTokensSplit", "BytesToChars", "CharsToBytes", "FuzeRagged", "UTF8Validate", "Truncate", "CombineSegments",
+           "RaggedToDense", "RegexNormalization", "CharsMapNormalization", "post_dense", "normalize_chain",
            "split_bpe", "split_wordpiece", "B200TokError"]
 
 B200TokError = K.B200TokError
