@@ -101,7 +101,7 @@ def test_host_scan_property_random_unicode():
                          st.sampled_from([chr(c) for c in NC.INTERESTING]))
     blob = NC.unicodedata_blob("NFD", True)
 
-    @settings(max_examples=120, deadline=None)
+    @settings(max_examples=120, deadline=None, derandomize=True)
     @given(st.lists(st.text(alphabet, max_size=80), min_size=1, max_size=8))
     def text_case(strings):
         raw = [s_.encode() for s_ in strings]
@@ -115,7 +115,7 @@ def test_host_scan_property_random_unicode():
                 assert NC.unpack(*got) == NC.unpack(*exp), (step["name"], raw)
         assert NC.unpack(*hostcore.hz_normalize(1, blob, b"", 0, b, e, c)) == NC.unpack(*oracle.charsmap_normalize(blob, b, e, c))
 
-    @settings(max_examples=150, deadline=None)
+    @settings(max_examples=150, deadline=None, derandomize=True)
     @given(st.lists(st.binary(max_size=60), min_size=1, max_size=8))
     def bytes_case(raw):
         b, e, c = NC.pack(raw)
