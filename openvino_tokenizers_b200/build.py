@@ -9,8 +9,13 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libb200tok.so"
 SOURCES = ["api.cu", "tables.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "kernels_fast.cuh", "kernels_misc.cuh", "kernels_shim.cuh", "kernels_special.cuh", "kernels_tail.cuh", "tok_core.cuh", "tables.hpp", "unicode_ranges.inc",
-                  "../../include/b200tok.h"]
+
+
+def deps() -> list[Path]:
+    """Every file the library is compiled from: all sources / headers / generated tables under csrc/ plus the public header."""
+    out = [p for pat in ("*.cu", "*.cpp", "*.cuh", "*.hpp", "*.h", "*.inc") for p in CSRC.glob(pat)]
+    out.append(CSRC.parent.parent / "include" / "b200tok.h")
+    return out
 
 
 def nvcc_path() -> str:
@@ -21,7 +26,7 @@ def nvcc_path() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    newest = max((CSRC / d).stat().st_mtime for d in DEPS)
+    newest = max(p.stat().st_mtime for p in deps())
     if not force and LIB.exists() and LIB.stat().st_mtime >= newest:
         return LIB
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
