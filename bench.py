@@ -9,11 +9,15 @@ own 65 536-row shard and, for N > 1, the ragged id rows are all-gathered over NC
   value       whole-job MB/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e         the same metric through the host-buffer C-ABI call an ov::Op::evaluate() shim makes
               (pinned host buffers; H2D and D2H copies inside the timed region)
-  roofline    dominant kernel (rows_kernel<BPE>) algorithmic bytes / its CUDA-event duration vs measured HBM peak
-  cpu_baseline  the CPU oracle (restatement of the reference ops, 1 thread like the reference's serial evaluate())
-                on a bounded sample of the same workload
-`--impl reference` times the reference's CPU path (the oracle port; the reference itself cannot be built here —
-it needs OpenVINO) with all host threads on a bounded sample per step.
+  roofline    dominant kernel (gpt2_bpe_fast_kernel on C1/C3, rows_kernel<wordpiece> on C2) algorithmic bytes / its CUDA-event
+              duration vs the measured HBM peak
+  cpu_baseline  the reference's own op code (oracle/_ref: src/*.cpp of the reference compiled against a stand-in OpenVINO API;
+                the oracle port where that library is absent), 1 thread like the reference's serial evaluate(), on a bounded sample
+After the timed regions the ids of the timed configuration are compared with the CPU result: the whole batch at N = 1 (device-resident
+and host-buffer paths), and at N > 1 every rank checks a remote rank's slot of the gathered result against its own tokenisation of
+that shard.
+`--impl reference` times the reference's own CPU evaluate() chain (oracle/_ref) on the FULL batch, with the fastest thread
+count (concurrent evaluate() calls on one op instance, rows sharded — what several infer requests would do).
 """
 from __future__ import annotations
 
@@ -123,22 +127,26 @@ def cpu_sample(w, batch, rows):
     return (rb[:n], re_[:n], b[:n], e[:n], c[: n * L])
 
 
-def oracle_runner(w):
-    """Returns f(batch, threads) -> n_ids running the CPU oracle chain for the workload."""
-    import oracle
+def cpu_runner(w, cached=True):
+    """Returns (f(batch, threads) -> (begins, ends, ids), kind).  kind "reference": the reference's own op classes
+    (oracle/_ref/libovtok_ref.so, built from /root/reference/src by oracle/Makefile); "port": the oracle restatement."""
     from openvino_tokenizers_b200 import assets as A
+    a = A.load_bpe(w["vocab"]) if w["kind"] == "bpe" else A.load_wordpiece(w["vocab"])
+    if cached:
+        import refops
+        if refops.available():
+            return refops.RefChain(w["kind"], a), "reference"
+    import oracle
     from openvino_tokenizers_b200.strings import pack_strings
     if w["kind"] == "bpe":
-        a = A.load_bpe(w["vocab"])
         v, ml, mr, ad, aid = a.tensors()
         sp = oracle.SplitOracle(a.split_pattern, "isolate")
-        bpe = oracle.BpeOracle(v, ml, mr, ad, aid, cache_capacity=a.cache_capacity)
+        bpe = oracle.BpeOracle(v, ml, mr, ad, aid, cache_capacity=a.cache_capacity, use_cache=cached)
 
         def run(batch, threads):
             s = sp(*batch, threads=threads)
-            return len(bpe(s[0], s[1], s[2], s[3], batch[4], threads=threads)[2])
-        return run
-    a = A.load_wordpiece(w["vocab"])
+            return bpe(s[0], s[1], s[2], s[3], batch[4], threads=threads)
+        return run, "port"
     s1 = oracle.SplitOracle(A.BERT_WHITESPACE_PATTERN, "remove")
     s2 = oracle.SplitOracle(A.BERT_PUNCT_PATTERN, "isolate")
     wp = oracle.WordpieceOracle(pack_strings(a.vocab), a.suffix_indicator, a.max_bytes_per_word)
@@ -146,12 +154,18 @@ def oracle_runner(w):
     def run(batch, threads):
         r1 = s1(*batch, threads=threads)
         r2 = s2(r1[0], r1[1], r1[2], r1[3], batch[4], threads=threads)
-        return len(wp(r2[0], r2[1], r2[2], r2[3], batch[4], a.unk_token_id, threads=threads)[2])
-    return run
+        return wp(r2[0], r2[1], r2[2], r2[3], batch[4], a.unk_token_id, threads=threads)
+    return run, "port"
+
+
+def checker(w):
+    """The fastest exact CPU result for verification: the oracle restatement (equal to the reference's code, tests/test_reference_pin.py)
+    with its result cache off, so that rows shard over all host threads without the cache mutex."""
+    return cpu_runner(w, cached=False)[0]
 
 
 def time_cpu(run, batch, threads, repeats=3):
-    run(batch, threads)   # warm-up: builds nothing new but fills the reference's 20 000-entry BPE cache
+    run(batch, threads)   # warm-up: builds the tables on first use and fills the reference's 20 000-entry BPE cache
     best = 1e30
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -165,12 +179,10 @@ def main_reference(args, w, rank, world):
         return
     batch = make_batch(w, 1234)
     cores = os.cpu_count() or 1
-    sample_rows = 16384
-    sample = cpu_sample(w, batch, sample_rows)
-    run = oracle_runner(w)
+    run, kind = cpu_runner(w)
     # The reference's evaluate() is a serial loop and its BPE result cache sits behind one shared_mutex
     # (src/bpe_tokenizer.cpp:196-205,331-338), so more threads are not always faster: probe 1 .. all cores on a small
-    # sample and time the steps with the best count.
+    # sample (concurrent evaluate() calls on one op instance, rows sharded) and time the steps with the best count.
     probe = cpu_sample(w, batch, 2048)
     cands = sorted({1, 2, 4, 8, cores} & set(range(1, cores + 1)))
     best_t, best_v = 1, 0.0
@@ -179,20 +191,22 @@ def main_reference(args, w, rank, world):
         if v > best_v:
             best_t, best_v = t, v
     for _ in range(args.warmup):
-        run(sample, best_t)
+        run(batch, best_t)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        run(sample, best_t)
+        run(batch, best_t)
     dt = (time.perf_counter() - t0) / args.steps
-    mbs = len(sample[4]) / 1e6 / dt
-    desc = (f"{len(sample[0])} of {w['rows']} rows x {w['row_bytes']} B per step (bounded sample of the workload); "
-            f"{best_t} thread(s) = the fastest of {cands} on this host ({cores} cores)")
+    mbs = len(batch[4]) / 1e6 / dt
+    what = ("the reference's own op classes (oracle/_ref: RegexSplit / BPETokenizer / WordpieceTokenizer evaluate() compiled from the reference sources)"
+            if kind == "reference" else "CPU oracle port of the reference ops (oracle/_ref not present)")
+    desc = (f"all {len(batch[0])} rows x {w['row_bytes']} B per step (the full batch); {best_t} thread(s) = the fastest of {cands} "
+            f"on this host ({cores} cores)")
     print(json.dumps({
         "impl": "reference", "metric": "input text tokenized (bit-exact ids)", "value": mbs, "unit": "MB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": w["name"], "note": "CPU oracle port of the reference ops (reference not buildable: needs OpenVINO)"},
-        "cpu_baseline": {"value": mbs, "unit": "MB/s", "cores": best_t, "kind": "port", "sample": desc},
+        "config": {"workload": w["name"], "rows_per_gpu": len(batch[0]), "row_bytes": w["row_bytes"], "note": what},
+        "cpu_baseline": {"value": mbs, "unit": "MB/s", "cores": best_t, "kind": kind, "sample": desc},
         "e2e": {"value": mbs, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -397,6 +411,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-batch CPU-oracle comparison after the timed regions")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
@@ -528,9 +543,43 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item()) / args.steps
-    assert n_host == n_ids
     h2d = n_bytes + 8 * db.n_rows + 8 * db.n_elems
     d2h = 4 * n_ids + 8 * db.n_rows
+
+    # ---- verification of the timed configuration (outside every timed region) ----
+    # N = 1: the whole batch, device-resident result and host-buffer result, against the CPU oracle.
+    # N > 1: every rank re-tokenises the shard of rank (rank + 1) % N on its own GPU and compares it with that rank's slot of the
+    #        gathered result it holds; rank 0 also checks its own shard against the CPU oracle.
+    verified = {}
+    own = pipe.run_device(db)
+    torch.cuda.synchronize()
+    n_own = int(own["n"].item())
+    own_np = (own["begins"].cpu().numpy(), own["ends"].cpu().numpy(), own["ids"][:n_own].cpu().numpy())
+    host_np = (ho["begins"].numpy(), ho["ends"].numpy(), ho["ids"][:n_host].numpy())
+    assert n_host == n_own and all(np.array_equal(x, y) for x, y in zip(own_np, host_np)), "host-buffer path differs from the device-resident path"
+    if rank == 0 and not args.no_verify:
+        exp = checker(w)(batch, os.cpu_count() or 1)
+        assert all(np.array_equal(x, y) for x, y in zip(own_np, exp)), "GPU ids differ from the CPU oracle on the timed batch"
+        verified["rank0_rows_vs_cpu_oracle"] = int(db.n_rows)
+    if world > 1:
+        peer = (rank + 1) % world
+        pb = R.to_device(make_batch(w, 1234 + peer), dev)
+        po = pipe.run_device(pb, pipe.alloc_device_out(pb.n_rows, pb.n_chars + pb.n_elems))
+        step_device()
+        torch.cuda.synchronize()
+        n_p = int(po["n"].item())
+        pb_, pe_, pids = po["begins"].cpu().numpy().astype(np.int64), po["ends"].cpu().numpy().astype(np.int64), po["ids"][:n_p].cpu().numpy()
+        if pg is not None:
+            gb, ge, gids = (t.cpu().numpy() for t in (pg.begins, pg.ends, pg.ids))
+            rows = slice(peer * db.n_rows, (peer + 1) * db.n_rows)
+            gb, ge = gb[rows].astype(np.int64), ge[rows].astype(np.int64)
+            assert np.array_equal(ge - gb, pe_ - pb_), "gathered row lengths of the peer slot differ"
+            lens = ge - gb
+            idx = np.repeat(gb - (np.cumsum(lens) - lens), lens) + np.arange(int(lens.sum()))
+            assert np.array_equal(gids[idx], pids), "gathered ids of the peer slot differ"
+            verified["peer_slot_rows_vs_local_gpu"] = int(db.n_rows)
+        barrier()
+    n_ids = n_own if world == 1 else n_ids
 
     total_bytes = n_bytes * world
     value = total_bytes / 1e6 / (ms_per_step / 1e3)
@@ -554,16 +603,16 @@ def main():
                     "kernel_share_of_step": (k_ms * n_blocks / ms_per_step) if k_ms else None, "launches_per_step": n_blocks}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            run = oracle_runner(w)
+            run, kind = cpu_runner(w)
             cores = os.cpu_count() or 1
             s1 = cpu_sample(w, batch, 4096)
             v1 = time_cpu(run, s1, 1)
             sN = cpu_sample(w, batch, 16384)
-            vN = time_cpu(run, sN, cores)
-            cpu = {"value": v1, "unit": "MB/s", "cores": 1, "kind": "port",
+            vN = time_cpu(run, sN, cores, repeats=1)
+            cpu = {"value": v1, "unit": "MB/s", "cores": 1, "kind": kind,
                    "sample": f"first 4096 of {w['rows']} rows x {w['row_bytes']} B, best of 3 after 1 warm-up pass; the reference's "
                              "evaluate() for RegexSplit/BPE is a serial loop, hence 1 thread",
-                   "all_cores": {"value": vN, "cores": cores, "sample": "first 16384 rows, rows sharded over threads"}}
+                   "all_cores": {"value": vN, "cores": cores, "sample": "first 16384 rows, rows sharded over concurrent evaluate() calls on one op instance"}}
         print(json.dumps({
             "metric": "input text tokenized (bit-exact ids)", "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -573,7 +622,7 @@ def main():
                        "multi_gpu": exchange},
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "path": "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "verified": verified,
         }))
     if world > 1:
         dist.destroy_process_group()

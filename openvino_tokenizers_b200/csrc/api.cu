@@ -121,6 +121,11 @@ struct RowWorkspace {
     int32_t* h_pipe = nullptr;                               // pinned + mapped status words per chunk (written by a kernel,
     int32_t* d_hpipe = nullptr;                              //  so no copy-engine traffic sits between compute and D2H)
     cudaEvent_t last_done = nullptr;                         // end of the previous call's work (it may have run on another stream)
+    // in-order single-pass emit (OrderedOut): look-back descriptors (never cleared: every launch has its own epoch) and the
+    // per-warp staging area of rows that span several windows
+    DBuf<unsigned long long> desc;
+    uint32_t epoch = 0;
+    DBuf<uint8_t> stage;
     ~RowWorkspace() {
         for (auto s_ : pipe) if (s_) cudaStreamDestroy(s_);
         for (auto e_ : pipe_ev) if (e_) cudaEventDestroy(e_);
@@ -221,6 +226,23 @@ int ensure_ws(b200tok_object* o) {
     return B200TOK_OK;
 }
 
+constexpr int kStageCap = 4096;        // ids per warp in the staging area; longer rows take the generic path
+
+// Descriptor array for `rows` rows and the staging area for `warps` warps; hands out the epoch pair of this launch.
+int ensure_ordered(RowWorkspace& w, int64_t rows, int64_t warps, size_t id_bytes, cudaStream_t st, uint32_t& epoch) {
+    const unsigned long long* before = w.desc.p;
+    const size_t cap_before = w.desc.cap;
+    CU(w.desc.ensure((size_t)rows));
+    if (w.desc.p != before || w.desc.cap != cap_before || w.epoch >= (1u << 30) - 4u) {
+        CU(cudaMemsetAsync(w.desc.p, 0, w.desc.cap * sizeof(unsigned long long), st));
+        w.epoch = 0;
+    }
+    CU(w.stage.ensure((size_t)warps * kStageCap * id_bytes));
+    epoch = w.epoch + 1;
+    w.epoch += 2;          // the gap-closing pass runs its own chain under epoch + 1
+    return B200TOK_OK;
+}
+
 struct RowCall {
     int op;                       // OP_*
     const SplitObj* split = nullptr;   // may be null (PAT_NONE)
@@ -266,6 +288,7 @@ struct ChunkLaunch {
     cudaEvent_t ev_prev = nullptr, ev_mine = nullptr;
     bool lean = false;           // pipelined chunks: direct row bases, folded finish, status cleared by the caller
     const b200tok_peer_out* peers = nullptr;   // sharded output: the compaction stores into every rank's buffers
+    int64_t desc_rows = 0, desc_off = 0;       // in-order emit: rows of the whole call / first row of this chunk (descriptor array slice)
 };
 
 constexpr size_t kRowsSmem = kRowsSmemFixed + WARPS_PER_BLOCK * sizeof(WarpSmem);
@@ -287,7 +310,13 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         CU(cudaMemsetAsync(c.P.status, 0, ST_WORDS * 4, st));
         CU(cudaMemsetAsync(c.pool_used, 0, 8, st));
     }
-    if (!c.P.direct_base) {
+    // GPT-2 byte-level split + BPE without end_suffix: the dedicated bit-mask kernel takes every row; rows it hands back
+    // (multi-byte symbols, pieces longer than a window, skip-flagged elements) are redone by the generic kernel in list mode
+    const bool fast = call.op == OP_BPE && (c.P.spec.pat == PAT_GPT2 || c.P.spec.pat == PAT_GPT2_DIGITS || c.P.spec.pat == PAT_LLAMA3) && c.P.mode == SPLIT_ISOLATED &&
+                      !c.P.repeat && c.P.max_splits == -1 && c.P.suffix_len == 0 && !(c.P.dbg_flags & 2);
+    // in-order emit (no slot bases, no compaction pass) whenever the caller's id buffer can hold the worst case a handed-back row reserves
+    const bool fast_ordered = fast && !c.peers && !c.zero_copy && !(c.P.dbg_flags & 16) && c.out_cap >= c.P.tmp_cap - 1;
+    if (!c.P.direct_base && !fast_ordered) {
         row_capacity_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.P.rb, c.P.re, c.P.begins, c.P.ends, (int32_t)B, c.per_elem_extra, c.row_cap);
         cub::DeviceScan::ExclusiveSum(c.cub_tmp, c.cub_bytes, c.row_cap, const_cast<int32_t*>(c.P.row_base), (int)B, st);
         ++owner->launches;
@@ -296,27 +325,34 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         if (!w.ev0) { CU(cudaEventCreate(&w.ev0)); CU(cudaEventCreate(&w.ev1)); }
         CU(cudaEventRecord(w.ev0, st));
     }
-    // GPT-2 byte-level split + BPE without end_suffix: the dedicated bit-mask kernel takes every row; rows it hands back
-    // (multi-byte symbols, pieces longer than a window, skip-flagged elements) are redone by the generic kernel in list mode
-    const bool fast = call.op == OP_BPE && (c.P.spec.pat == PAT_GPT2 || c.P.spec.pat == PAT_GPT2_DIGITS || c.P.spec.pat == PAT_LLAMA3) && c.P.mode == SPLIT_ISOLATED &&
-                      !c.P.repeat && c.P.max_splits == -1 && c.P.suffix_len == 0 && !(c.P.dbg_flags & 2);
     if (fast) {
         // ids fit 16 bits: slimmer per-warp state, five CTAs per SM instead of four (the kernel is latency-bound: warps = speed)
         const bool narrow = call.bpe->h.max_id < 0xFFFF && !(c.P.dbg_flags & 8);
         const bool l3 = c.P.spec.pat == PAT_LLAMA3;
-        static bool fast_attr[4][64] = {};
+        const bool peer_fast = c.peers != nullptr;        // sharded: the fast kernel stores into every rank's slot, no compaction follows
+        // everything else: in-order single-pass emit — the kernel writes the compact (begins, ends, ids) itself
+        const bool ordered = fast_ordered;
+        static bool fast_attr[8][64] = {};
         const size_t fsm = narrow ? fast_smem_bytes<uint16_t>() : fast_smem_bytes<int32_t>();
-        const void* fn = narrow ? (l3 ? (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, true> : (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, false>)
-                                : (l3 ? (const void*)gpt2_bpe_fast_kernel<int32_t, 4, true> : (const void*)gpt2_bpe_fast_kernel<int32_t, 4, false>);
-        if (!fast_attr[narrow * 2 + l3][owner->device]) {
+        const void* fn;
+        if (ordered) fn = narrow ? (l3 ? (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, true, true> : (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, false, true>)
+                                 : (l3 ? (const void*)gpt2_bpe_fast_kernel<int32_t, 4, true, true> : (const void*)gpt2_bpe_fast_kernel<int32_t, 4, false, true>);
+        else fn = narrow ? (l3 ? (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, true, false> : (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, false, false>)
+                         : (l3 ? (const void*)gpt2_bpe_fast_kernel<int32_t, 4, true, false> : (const void*)gpt2_bpe_fast_kernel<int32_t, 4, false, false>);
+        if (!fast_attr[ordered * 4 + narrow * 2 + l3][owner->device]) {
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            fast_attr[narrow * 2 + l3][owner->device] = true;
+            fast_attr[ordered * 4 + narrow * 2 + l3][owner->device] = true;
         }
         static const int fast_ctas_env = [] { const char* e = getenv("B200TOK_FAST_CTAS"); return e ? atoi(e) : 0; }();
         const int fast_per_sm = fast_ctas_env > 0 ? fast_ctas_env : (int)std::max<size_t>(1, std::min<size_t>(narrow ? 5 : 4, (227 * 1024) / (fsm + 1024)));
         const int fast_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * fast_per_sm);
         RowParams Pk = c.P;
-        const bool peer_fast = c.peers != nullptr;        // sharded: the fast kernel stores into every rank's slot, no compaction follows
+        if (ordered) {
+            uint32_t epoch = 0;
+            if (int rc = ensure_ordered(w, std::max<int64_t>(c.desc_rows, c.desc_off + B), (int64_t)owner->sm_count * 5 * WARPS_PER_BLOCK, narrow ? 2 : 4, st, epoch)) return rc;
+            Pk.oo = OrderedOut{w.desc.p + c.desc_off, epoch, c.d_oa, c.d_ob, c.d_oe, c.out_cap, c.total_dev, w.stage.p, kStageCap};
+            Pk.direct_base = 0;               // handed-back rows: the fast kernel stores their slot base (= gapped output offset)
+        }
         if (peer_fast) {
             Pk.peer.world = c.peers->world; Pk.peer.rank = c.peers->rank; Pk.peer.slot_capacity = c.peers->slot_capacity; Pk.peer.rows_per_rank = c.peers->rows_per_rank;
             Pk.peer.wire16 = c.peers->wire16;
@@ -328,10 +364,22 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         void* args[] = {&Pk, &redo};
         CU(cudaLaunchKernel(fn, dim3((unsigned)fast_blocks), dim3(BLOCK_THREADS), args, fsm, st));
         if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
-        RowParams P2 = c.P;
+        RowParams P2 = ordered ? Pk : c.P;
         P2.row_list = c.row_cap;
         rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(P2);
         owner->launches += 2;
+        if (ordered) {
+            // rows the fast kernel handed back (none on the benchmark workloads: all four kernels below return at once then) are
+            // finished by the generic kernels into tmp_a at their reserved offsets; the gaps are then closed
+            GiantParams G{c.P.giants, c.P.status, c.P.giants_cap, c.P.chars, call.bpe->view(), call.bpe->suffix.p, c.P.suffix_len,
+                          c.P.row_base, c.P.row_cnt, c.P.tmp_a, c.pool, (unsigned long long)c.pool_bytes, c.pool_used, c.P.status};
+            giant_bpe_kernel<<<std::max(1, owner->sm_count), 64, 0, st>>>(G);
+            ordered_stash_kernel<<<owner->sm_count * 8, 256, 0, st>>>(P2);
+            ordered_recompact_kernel<<<owner->sm_count * 8, 256, 0, st>>>(P2);
+            owner->launches += 3;
+            CU(cudaGetLastError());
+            return B200TOK_OK;
+        }
         if (peer_fast) {
             GiantParams G{c.P.giants, c.P.status, c.P.giants_cap, c.P.chars, call.bpe->view(), call.bpe->suffix.p, c.P.suffix_len,
                           c.P.row_base, c.P.row_cnt, c.P.tmp_a, c.pool, (unsigned long long)c.pool_bytes, c.pool_used, c.P.status};
@@ -542,6 +590,7 @@ int run_rows_host_pipelined(b200tok_object* owner, const RowCall& call, const b2
         c.d_ob = w.out_begins.p + r0; c.d_oe = w.out_ends.p + r0; c.d_oa = w.out_a.p + ch[nch].tmp_off; c.out_cap = ch[nch].cap;
         c.total_dev = w.total.p + k;
         c.lean = !zc_ids;
+        c.desc_rows = B; c.desc_off = r0;
         c.P.direct_base = 1; c.P.direct_byte0 = (int32_t)byte_lo; c.P.direct_elem0 = (int32_t)p_lo; c.P.direct_extra = per_elem_extra;
         if (zc_ids) {
             c.zero_copy = true;

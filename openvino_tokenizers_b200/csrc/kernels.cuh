@@ -31,7 +31,8 @@ constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK =
 enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2, OP_SPECIAL = 3 };
 
 // status words (device int32 array)
-enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_WORDS = 8 };
+enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_MINREDO = 8, ST_TICKET3 = 9,
+             ST_WORDS = 12 };
 enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
 
 struct GiantItem { int32_t row, begin, end, slot; };
@@ -53,6 +54,61 @@ __device__ __forceinline__ void mc_store4(int32_t* p, uint4 v) {
 }
 __device__ __forceinline__ void peer_store(const PeerOut& Q, int p, int64_t o, int32_t v) {
     if (Q.wire16) Q.ids16[p][o] = (uint16_t)v; else Q.ids[p][o] = v;
+}
+
+// In-order single-pass emit (fast path): every row obtains its output offset — the exclusive prefix of the token counts of
+// all earlier rows — by decoupled look-back over one 64-bit descriptor per row, so the compact (begins, ends, ids) result
+// is written exactly once, by the kernel that produced the ids (replaces the reference's serial `ragged_offset++`
+// bookkeeping, src/bpe_tokenizer.cpp:146-162, and this library's former capacity scan + slot buffer + compaction pass).
+//   descriptor = epoch[63:34] | flag[33:32] | value[31:0];   flag 1 = the row's own count, 2 = inclusive prefix
+// Rows take their tickets in row order, so every predecessor of a row is already running: the look-back cannot deadlock.
+// The epoch makes descriptors of earlier launches read as "not yet published": the array is never cleared between calls.
+struct OrderedOut {
+    unsigned long long* desc;     // [n_rows]; nullptr = the slot-buffer path
+    uint32_t epoch;               // this launch (30 bits, never 0)
+    int32_t* ids; int32_t* begins; int32_t* ends;
+    int64_t cap;                  // capacity of ids
+    int64_t* total;               // optional device-side total
+    void* stage;                  // per-warp staging (global, L2-resident) for rows that span several windows: stage_cap IdT per warp
+    int32_t stage_cap;
+};
+constexpr unsigned long long kDescAgg = 1ull << 32, kDescPrefix = 2ull << 32;
+__device__ __forceinline__ unsigned long long desc_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void desc_store(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+// Exclusive prefix of `count` over rows [first, row) (+ `seed` for row == first); publishes this row's descriptors.  Warp-uniform.
+__device__ __forceinline__ long long lookback_exclusive(unsigned long long* desc, uint32_t epoch, int first, int row, uint32_t count, long long seed, int lane) {
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    if (row == first) {
+        if (lane == 0) desc_store(desc + row, tag | kDescPrefix | (uint32_t)(seed + count));
+        return seed;
+    }
+    if (lane == 0) desc_store(desc + row, tag | kDescAgg | count);
+    long long excl = 0;
+    for (int idx = row - 1;; idx -= 32) {
+        const int j = idx - lane;
+        unsigned long long d;
+        for (int spin = 0;; ++spin) {
+            d = j >= first ? desc_load(desc + j) : (tag | kDescAgg);            // lanes before the first row contribute nothing
+            const bool ok = (d >> 34) == epoch && ((d >> 32) & 3u) != 0u;
+            if (__all_sync(0xFFFFFFFFu, ok)) break;
+            if (spin > 2) __nanosleep(64);
+        }
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, ((d >> 32) & 3u) == 2u);
+        long long v = (uint32_t)d;
+        if (pm) { const int k = __ffs(pm) - 1; if (lane > k) v = 0; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        excl += v;
+        if (pm || idx - 32 < first) break;
+    }
+    if (lane == 0) desc_store(desc + row, tag | kDescPrefix | (uint32_t)(excl + count));
+    return excl;
 }
 
 struct RowParams {
@@ -88,6 +144,7 @@ struct RowParams {
     // sharded fast path: the emit step stores ids (and row extents) straight into every rank's buffers, rows stay at their
     // worst-case positions inside this rank's slot (a ragged tensor may have gaps), so no scan / compaction pass follows
     PeerOut peer;
+    OrderedOut oo;
 };
 
 struct __align__(16) WarpSmem {
@@ -996,7 +1053,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
         if (lane == 0) {
             P.row_ext[row] = emitted;
             P.row_cnt[row] = emitted - holes;
-            P.row_flag[row] = holes ? 1 : 0;
+            P.row_flag[row] = (uint8_t)((holes ? 1 : 0) | (P.row_list ? 2 : 0));      // bit 1: a row the fast kernel handed back
         }
     }
 }
@@ -1098,7 +1155,7 @@ __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, 
             out_end[r] = e;
             if (r == n_rows - 1) status[ST_TOTAL] = e;
         }
-        if (!row_flag[r]) {
+        if (!(row_flag[r] & 1)) {
             if (dst + ext > out_cap) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
             if (!out_b && !out_c) {            // ids only: four independent loads in flight per lane
                 const int32_t* sp = tmp_a + src;
@@ -1151,7 +1208,7 @@ __global__ void compact_rows_peer_kernel(const int32_t* tmp_a, const int32_t* ro
         }
         if (lane == 0 && r == n_rows - 1) { status[ST_TOTAL] = out_begin[r] + cnt; if (total_out) *total_out = out_begin[r] + cnt; }
         if (out_begin[r] + cnt > Q.slot_capacity) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
-        if (!row_flag[r]) {
+        if (!(row_flag[r] & 1)) {
             for (int t = lane; t < ext; t += 128) {
                 int32_t v[4];
 #pragma unroll

@@ -394,7 +394,143 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
     return send;
 }
 
-template <class IdT, int CTAS, bool L3>
+
+// Stage the bytes of one window (+ look-back / look-ahead) into shared memory; returns true if every byte is ASCII.
+template <class IdT>
+__device__ __forceinline__ bool stage_window(FastSmem<IdT>& S, const RowParams& P, int pos, int lb, int nload, int lane) {
+    uint32_t hibits = 0;
+    const uint8_t* src = P.chars + pos - lb;
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
+        // 16-byte vector loads; the last quad may read up to 15 bytes past the element (padded chars allocation)
+        uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
+        const int nq = (lb + nload + 15) >> 4;
+        for (int q = lane; q < nq; q += 32) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+            dst[q] = v;
+            if ((q << 4) + 16 <= lb + nload) hibits |= v.x | v.y | v.z | v.w;
+            else {
+                const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+                for (int t = 0; t < 16; ++t) if ((q << 4) + t < lb + nload) hibits |= (ww[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
+            }
+        }
+    } else {
+        for (int w = lane - lb; w < nload; w += 32) {
+            const uint8_t bb = __ldg(P.chars + pos + w);
+            S.B()[w] = bb;
+            hibits |= bb;
+        }
+    }
+    const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
+    __syncwarp();
+    return all_ascii;
+}
+
+// Compact the live ids of S.ids[0 .. send) to the front of S.ids, in place (a token only ever moves towards lower indices, and
+// every iteration reads its 128 positions before it writes).  Returns the number of live ids.
+template <class IdT>
+__device__ __forceinline__ int compact_window(FastSmem<IdT>& S, int send, int lane) {
+    const uint32_t ltm = (1u << lane) - 1u;
+    int n_out = 0;
+    for (int w = lane; w - lane < send; w += 128) {
+        IdT tok[4];
+        uint32_t m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tok[u] = (w + 32 * u) < send ? S.ids[w + 32 * u] : S.kDead;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] != S.kDead);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (tok[u] != S.kDead) S.ids[n_out + __popc(m[u] & ltm)] = tok[u];
+            n_out += __popc(m[u]);
+        }
+    }
+    __syncwarp();
+    return n_out;
+}
+
+// The row loop of the in-order single-pass emit (OrderedOut, kernels.cuh): tokenise the row, learn its count, obtain its output
+// offset by look-back, write the compact ids once.  A row the bit-mask path cannot finish reserves its worst-case extent
+// (count <= bytes, src/bpe_tokenizer.cpp:135) instead and goes on the redo list; ordered_recompact_kernel closes those gaps.
+template <class IdT, bool L3>
+__device__ __forceinline__ void ordered_rows(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32_smem, const uint8_t* ascii_smem,
+                                             int lane, int32_t* __restrict__ redo_rows) {
+    const OrderedOut& O = P.oo;
+    IdT* const stage = reinterpret_cast<IdT*>(O.stage) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * (size_t)O.stage_cap;
+    for (;;) {
+        int row = 0;
+        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+        row = __shfl_sync(FULL, row, 0);
+        if (row >= P.n_rows) break;
+        const int p0 = P.rb[row], p1 = P.re[row];
+        int emitted = 0;
+        bool redo = false, direct = false;
+        for (int p = p0; p < p1 && !redo; ++p) {
+            const int eb = P.begins[p], ee = P.ends[p];
+            if (P.skips && P.skips[p]) { redo = true; break; }
+            int pos = eb;
+            while (pos < ee) {
+                const int end_rel = ee - pos;
+                const int wlen = end_rel < WIN ? end_rel : WIN;
+                const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
+                const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
+                const bool all_ascii = stage_window(S, P, pos, lb, nload, lane);
+                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                if (send <= 0) { redo = true; break; }
+                const int n_out = compact_window(S, send, lane);
+                if (p1 - p0 == 1 && pos == eb && send == end_rel) {      // one window covered the whole row: its ids leave from shared memory
+                    direct = true;
+                    emitted = n_out;
+                } else {
+                    if (emitted + n_out > O.stage_cap) { redo = true; break; }      // longer than the staging area: the generic path takes the row
+                    for (int t = lane; t < n_out; t += 32) stage[emitted + t] = S.ids[t];
+                    emitted += n_out;
+                    __syncwarp();
+                }
+                pos += send;
+            }
+        }
+        uint32_t count = (uint32_t)emitted;
+        if (redo) {               // reserve the row's worst case: one id per byte
+            long long c = 0;
+            for (int p = p0 + lane; p < p1; p += 32) { const int l = P.ends[p] - P.begins[p]; c += l > 0 ? l : 0; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+            count = (uint32_t)(c > 0x7FFFFFFF ? 0x7FFFFFFF : c);
+        }
+        const long long excl = lookback_exclusive(O.desc, O.epoch, 0, row, count, 0, lane);
+        const bool fits = excl + (long long)count <= O.cap;
+        if (!fits && lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+        if (redo) {
+            if (lane == 0) {
+                redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
+                atomicMax(&P.status[ST_MINREDO], P.n_rows - row);
+                const_cast<int32_t*>(P.row_base)[row] = (int32_t)excl;       // the generic kernels fill tmp_a[excl ..)
+                O.begins[row] = (int32_t)excl; O.ends[row] = (int32_t)excl;
+                P.row_flag[row] = 2;
+            }
+        } else {
+            if (fits) {
+                int32_t* const outp = O.ids + excl;
+                const IdT* const src = direct ? S.ids : stage;
+                for (int t = lane; t < emitted; t += 128) {
+                    IdT v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < emitted) ? src[t + 32 * u] : (IdT)0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (t + 32 * u < emitted) __stcs(outp + t + 32 * u, (int32_t)v[u]);
+                }
+            }
+            if (lane == 0) { O.begins[row] = (int32_t)excl; O.ends[row] = (int32_t)(excl + count); P.row_flag[row] = 0; }
+        }
+        if (row == P.n_rows - 1 && lane == 0) {
+            P.status[ST_TOTAL] = (int32_t)(excl + count);
+            if (O.total) *O.total = excl + count;
+        }
+        __syncwarp();
+    }
+}
+
+template <class IdT, int CTAS, bool L3, bool ORDERED>
 __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                            // [128]
@@ -407,137 +543,196 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
     __syncthreads();
     const uint32_t ltm = (1u << lane) - 1u;
 
-    for (;;) {
-        int row = 0;
-        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
-        row = __shfl_sync(FULL, row, 0);
-        if (row >= P.n_rows) break;
-        const int p0 = P.rb[row], p1 = P.re[row];
-        int64_t base;
-        if (P.direct_base) {
-            base = p1 > p0 ? (int64_t)(P.begins[p0] - P.direct_byte0) + (int64_t)(p0 - P.direct_elem0) * P.direct_extra : 0;
-            if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
-        } else base = P.row_base[row];
-        int emitted = 0;
-        bool redo = false;
-        for (int p = p0; p < p1 && !redo; ++p) {
-            const int eb = P.begins[p], ee = P.ends[p];
-            if (P.skips && P.skips[p]) { redo = true; break; }
-            int pos = eb;
-            while (pos < ee) {
-                const int end_rel = ee - pos;
-                const int wlen = end_rel < WIN ? end_rel : WIN;
-                const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
-                const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
-                uint32_t hibits = 0;
-                const uint8_t* src = P.chars + pos - lb;
-                if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
-                    // 16-byte vector loads; the last quad may read up to 15 bytes past the element (padded chars allocation)
-                    uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
-                    const int nq = (lb + nload + 15) >> 4;
-                    for (int q = lane; q < nq; q += 32) {
-                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
-                        dst[q] = v;
-                        if ((q << 4) + 16 <= lb + nload) hibits |= v.x | v.y | v.z | v.w;
-                        else {
-                            const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
-                            for (int t = 0; t < 16; ++t) if ((q << 4) + t < lb + nload) hibits |= (ww[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
-                        }
-                    }
-                } else {
-                    for (int w = lane - lb; w < nload; w += 32) {
-                        const uint8_t bb = __ldg(P.chars + pos + w);
-                        S.B()[w] = bb;
-                        hibits |= bb;
-                    }
-                }
-                const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
-                __syncwarp();
-                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
-                if (send <= 0) { redo = true; break; }
-                if (base + emitted + send > P.tmp_cap) {
-                    if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
-                } else {
-                    const int nP = P.peer.world;                  // > 0: sharded output, store into every rank's slot
-                    const int64_t o0 = (nP ? (int64_t)P.peer.rank * P.peer.slot_capacity : 0) + base + emitted;
-                    int32_t* outp = P.tmp_a + o0;
-                    int n_out = 0;
-                    for (int w = lane; w - lane < send; w += 128) {
-                        int32_t tok[4];
-                        uint32_t m[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) tok[u] = ((w + 32 * u) < send && S.ids[w + 32 * u] != S.kDead) ? (int32_t)S.ids[w + 32 * u] : -1;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
-                        if (!nP) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
-                                n_out += __popc(m[u]);
-                            }
-                        } else {
-                            // sharded: compact into shared memory first (same 16-byte misalignment as the destination), stored wide below
-                            const int shift = P.peer.wire16 ? (int)(o0 & 7) : (int)(o0 & 3);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = shift + n_out + __popc(m[u] & ltm);
-                                if (tok[u] >= 0) { if (P.peer.wire16) reinterpret_cast<uint16_t*>(S.key)[i] = (uint16_t)tok[u]; else reinterpret_cast<int32_t*>(S.key)[i] = tok[u]; }
-                                n_out += __popc(m[u]);
+    if constexpr (ORDERED) {
+        ordered_rows<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, redo_rows);
+        return;
+    } else {
+        for (;;) {
+            int row = 0;
+            if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+            row = __shfl_sync(FULL, row, 0);
+            if (row >= P.n_rows) break;
+            const int p0 = P.rb[row], p1 = P.re[row];
+            int64_t base;
+            if (P.direct_base) {
+                base = p1 > p0 ? (int64_t)(P.begins[p0] - P.direct_byte0) + (int64_t)(p0 - P.direct_elem0) * P.direct_extra : 0;
+                if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
+            } else base = P.row_base[row];
+            int emitted = 0;
+            bool redo = false;
+            for (int p = p0; p < p1 && !redo; ++p) {
+                const int eb = P.begins[p], ee = P.ends[p];
+                if (P.skips && P.skips[p]) { redo = true; break; }
+                int pos = eb;
+                while (pos < ee) {
+                    const int end_rel = ee - pos;
+                    const int wlen = end_rel < WIN ? end_rel : WIN;
+                    const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
+                    const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
+                    uint32_t hibits = 0;
+                    const uint8_t* src = P.chars + pos - lb;
+                    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
+                        // 16-byte vector loads; the last quad may read up to 15 bytes past the element (padded chars allocation)
+                        uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
+                        const int nq = (lb + nload + 15) >> 4;
+                        for (int q = lane; q < nq; q += 32) {
+                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+                            dst[q] = v;
+                            if ((q << 4) + 16 <= lb + nload) hibits |= v.x | v.y | v.z | v.w;
+                            else {
+                                const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+                                for (int t = 0; t < 16; ++t) if ((q << 4) + t < lb + nload) hibits |= (ww[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
                             }
                         }
+                    } else {
+                        for (int w = lane - lb; w < nload; w += 32) {
+                            const uint8_t bb = __ldg(P.chars + pos + w);
+                            S.B()[w] = bb;
+                            hibits |= bb;
+                        }
                     }
-                    if (nP) {
-                        __syncwarp();
-                        // 16-byte chunks of the staged ids go to every rank with one vector store each (remote stores are
-                        // transaction-bound: few wide stores instead of many 2-4 byte ones); ragged head / tail element-wise
-                        const int per = P.peer.wire16 ? 8 : 4;
-                        const int shift = (int)(o0 & (per - 1)), total = shift + n_out;
-                        const int64_t o_al = o0 - shift;                          // 16-byte aligned destination element
-                        const uint4* sv = reinterpret_cast<const uint4*>(S.key);
-                        for (int c = lane; c * per < total; c += 32) {
-                            const int lo = c * per, hi = lo + per;
-                            if (P.peer.ids_mc && !P.peer.wire16) {           // NVLS multicast: one store reaches every rank
-                                int32_t* mc = P.peer.ids_mc + o_al;
-                                if (lo >= shift && hi <= total) mc_store4(mc + lo, sv[c]);
-                                else for (int i = lo < shift ? shift : lo; i < (hi < total ? hi : total); ++i) mc_store(mc + i, reinterpret_cast<const int32_t*>(S.key)[i]);
-                            } else if (lo >= shift && hi <= total) {
-                                const uint4 v = sv[c];
-                                for (int p = 0; p < nP; ++p) {
-                                    uint4* dp = P.peer.wire16 ? reinterpret_cast<uint4*>(P.peer.ids16[p] + o_al) : reinterpret_cast<uint4*>(P.peer.ids[p] + o_al);
-                                    dp[c] = v;
+                    const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
+                    __syncwarp();
+                    const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                    if (send <= 0) { redo = true; break; }
+                    if (base + emitted + send > P.tmp_cap) {
+                        if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                    } else {
+                        const int nP = P.peer.world;                  // > 0: sharded output, store into every rank's slot
+                        const int64_t o0 = (nP ? (int64_t)P.peer.rank * P.peer.slot_capacity : 0) + base + emitted;
+                        int32_t* outp = P.tmp_a + o0;
+                        int n_out = 0;
+                        for (int w = lane; w - lane < send; w += 128) {
+                            int32_t tok[4];
+                            uint32_t m[4];
+    #pragma unroll
+                            for (int u = 0; u < 4; ++u) tok[u] = ((w + 32 * u) < send && S.ids[w + 32 * u] != S.kDead) ? (int32_t)S.ids[w + 32 * u] : -1;
+    #pragma unroll
+                            for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
+                            if (!nP) {
+    #pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
+                                    n_out += __popc(m[u]);
                                 }
                             } else {
-                                for (int i = lo < shift ? shift : lo; i < (hi < total ? hi : total); ++i)
-                                    for (int p = 0; p < nP; ++p) {
-                                        if (P.peer.wire16) P.peer.ids16[p][o_al + i] = reinterpret_cast<const uint16_t*>(S.key)[i];
-                                        else P.peer.ids[p][o_al + i] = reinterpret_cast<const int32_t*>(S.key)[i];
-                                    }
+                                // sharded: compact into shared memory first (same 16-byte misalignment as the destination), stored wide below
+                                const int shift = P.peer.wire16 ? (int)(o0 & 7) : (int)(o0 & 3);
+    #pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int i = shift + n_out + __popc(m[u] & ltm);
+                                    if (tok[u] >= 0) { if (P.peer.wire16) reinterpret_cast<uint16_t*>(S.key)[i] = (uint16_t)tok[u]; else reinterpret_cast<int32_t*>(S.key)[i] = tok[u]; }
+                                    n_out += __popc(m[u]);
+                                }
                             }
                         }
-                        __syncwarp();
+                        if (nP) {
+                            __syncwarp();
+                            // 16-byte chunks of the staged ids go to every rank with one vector store each (remote stores are
+                            // transaction-bound: few wide stores instead of many 2-4 byte ones); ragged head / tail element-wise
+                            const int per = P.peer.wire16 ? 8 : 4;
+                            const int shift = (int)(o0 & (per - 1)), total = shift + n_out;
+                            const int64_t o_al = o0 - shift;                          // 16-byte aligned destination element
+                            const uint4* sv = reinterpret_cast<const uint4*>(S.key);
+                            for (int c = lane; c * per < total; c += 32) {
+                                const int lo = c * per, hi = lo + per;
+                                if (P.peer.ids_mc && !P.peer.wire16) {           // NVLS multicast: one store reaches every rank
+                                    int32_t* mc = P.peer.ids_mc + o_al;
+                                    if (lo >= shift && hi <= total) mc_store4(mc + lo, sv[c]);
+                                    else for (int i = lo < shift ? shift : lo; i < (hi < total ? hi : total); ++i) mc_store(mc + i, reinterpret_cast<const int32_t*>(S.key)[i]);
+                                } else if (lo >= shift && hi <= total) {
+                                    const uint4 v = sv[c];
+                                    for (int p = 0; p < nP; ++p) {
+                                        uint4* dp = P.peer.wire16 ? reinterpret_cast<uint4*>(P.peer.ids16[p] + o_al) : reinterpret_cast<uint4*>(P.peer.ids[p] + o_al);
+                                        dp[c] = v;
+                                    }
+                                } else {
+                                    for (int i = lo < shift ? shift : lo; i < (hi < total ? hi : total); ++i)
+                                        for (int p = 0; p < nP; ++p) {
+                                            if (P.peer.wire16) P.peer.ids16[p][o_al + i] = reinterpret_cast<const uint16_t*>(S.key)[i];
+                                            else P.peer.ids[p][o_al + i] = reinterpret_cast<const int32_t*>(S.key)[i];
+                                        }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        emitted += n_out;
                     }
-                    emitted += n_out;
+                    __syncwarp();
+                    pos += send;
                 }
-                __syncwarp();
-                pos += send;
+            }
+            if (lane == 0) {
+                if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
+                else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = 0; }
+            }
+            if (P.peer.world && !redo) {                       // sharded: publish the row's extent to every rank
+                const int64_t o0 = (int64_t)P.peer.rank * P.peer.slot_capacity + base;
+                if (P.peer.begins_mc) {
+                    if (lane == 0) {
+                        mc_store(P.peer.begins_mc + (int64_t)P.peer.rank * P.peer.rows_per_rank + row, (int32_t)o0);
+                        mc_store(P.peer.ends_mc + (int64_t)P.peer.rank * P.peer.rows_per_rank + row, (int32_t)(o0 + emitted));
+                    }
+                } else if (lane < P.peer.world) {
+                    P.peer.begins[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)o0;
+                    P.peer.ends[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)(o0 + emitted);
+                }
+                if (lane == 0) atomicAdd(&P.status[ST_TOTAL], emitted);
             }
         }
+    }
+}
+
+
+// ---- closing the gaps of handed-back rows (both kernels return at once when the fast kernel finished every row) ----------
+// 1. rows after the first handed-back row are parked in tmp_a at their (gapped) offsets, next to the ids the generic kernels
+//    produced for the handed-back rows themselves;
+__global__ void ordered_stash_kernel(const __grid_constant__ RowParams P) {
+    if (P.status[ST_NREDO] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int first = P.n_rows - P.status[ST_MINREDO];
+    for (int r = first + warp; r < P.n_rows; r += nwarps) {
+        if (P.row_flag[r] & 2) continue;
+        const int b = P.oo.begins[r], e = P.oo.ends[r];
+        if ((long long)e > P.oo.cap || (long long)e > P.tmp_cap) continue;
+        for (int t = b + lane; t < e; t += 32) P.tmp_a[t] = P.oo.ids[t];
+    }
+}
+// 2. a second look-back chain over the true counts moves every row to its final offset and rewrites begins / ends / total.
+__global__ void ordered_recompact_kernel(const __grid_constant__ RowParams P) {
+    if (P.status[ST_NREDO] == 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t ltm = (1u << lane) - 1u;
+    const int first = P.n_rows - P.status[ST_MINREDO];
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = first + atomicAdd(&P.status[ST_TICKET3], 1);
+        r = __shfl_sync(FULL, r, 0);
+        if (r >= P.n_rows) break;
+        const uint8_t flag = P.row_flag[r];
+        const int gb = (flag & 2) ? P.row_base[r] : P.oo.begins[r];
+        const int cnt = (flag & 2) ? P.row_cnt[r] : P.oo.ends[r] - gb;
+        const int ext = (flag & 2) ? P.row_ext[r] : cnt;
+        const long long excl = lookback_exclusive(P.oo.desc, P.oo.epoch + 1u, first, r, (uint32_t)cnt, gb, lane);
+        if (excl + cnt <= P.oo.cap && (long long)gb + ext <= P.tmp_cap) {
+            int32_t* outp = P.oo.ids + excl;
+            if (!(flag & 1)) {
+                for (int t = lane; t < ext; t += 32) outp[t] = P.tmp_a[gb + t];
+            } else {                                         // holes of giant pieces are filtered while copying
+                int d = 0;
+                for (int t0 = 0; t0 < ext; t0 += 32) {
+                    const int t = t0 + lane;
+                    const int v = t < ext ? P.tmp_a[gb + t] : -1;
+                    const uint32_t m = __ballot_sync(FULL, v >= 0);
+                    if (v >= 0) outp[d + __popc(m & ltm)] = v;
+                    d += __popc(m);
+                }
+            }
+        } else if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
         if (lane == 0) {
-            if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
-            else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = 0; }
-        }
-        if (P.peer.world && !redo) {                       // sharded: publish the row's extent to every rank
-            const int64_t o0 = (int64_t)P.peer.rank * P.peer.slot_capacity + base;
-            if (P.peer.begins_mc) {
-                if (lane == 0) {
-                    mc_store(P.peer.begins_mc + (int64_t)P.peer.rank * P.peer.rows_per_rank + row, (int32_t)o0);
-                    mc_store(P.peer.ends_mc + (int64_t)P.peer.rank * P.peer.rows_per_rank + row, (int32_t)(o0 + emitted));
-                }
-            } else if (lane < P.peer.world) {
-                P.peer.begins[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)o0;
-                P.peer.ends[lane][(int64_t)P.peer.rank * P.peer.rows_per_rank + row] = (int32_t)(o0 + emitted);
-            }
-            if (lane == 0) atomicAdd(&P.status[ST_TOTAL], emitted);
+            P.oo.begins[r] = (int32_t)excl; P.oo.ends[r] = (int32_t)(excl + cnt);
+            if (r == P.n_rows - 1) { P.status[ST_TOTAL] = (int32_t)(excl + cnt); if (P.oo.total) *P.oo.total = excl + cnt; }
         }
     }
 }

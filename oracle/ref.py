@@ -63,6 +63,8 @@ def lib(path: Path | None = None, prefix: str = "ovref"):
     getattr(L, f"{prefix}_node_last_ms").restype = C.c_double
     getattr(L, f"{prefix}_node_type").argtypes = [C.c_void_p]
     getattr(L, f"{prefix}_node_type").restype = C.c_char_p
+    getattr(L, f"{prefix}_node_share").argtypes = [C.c_void_p]
+    getattr(L, f"{prefix}_node_share").restype = C.c_void_p
     getattr(L, f"{prefix}_node_destroy").argtypes = [C.c_void_p]
     getattr(L, f"{prefix}_last_error").restype = C.c_char_p
     if path is None:
@@ -126,6 +128,14 @@ class StubOp:
         self.name = name
         self.node_type = getattr(L, f"{self._prefix}_node_type")(self._h).decode()
         self.last_ms = 0.0
+
+    def share(self):
+        """Another handle on the same op instance (shared tables / caches), for concurrent evaluate() calls from several threads —
+        what OpenVINO does with several infer requests on one compiled model."""
+        other = object.__new__(type(self))
+        other._keep, other.name, other.node_type, other.last_ms = self._keep, self.name, self.node_type, 0.0
+        other._h = getattr(self._lib(), f"{self._prefix}_node_share")(self._h)
+        return other
 
     @staticmethod
     def _fmt(v):

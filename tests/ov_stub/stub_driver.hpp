@@ -154,6 +154,13 @@ inline int node_output(NodeHandle* h, int i, ovs_tensor* d) {
     extern "C" __attribute__((visibility("default"))) int PREFIX##_node_output(void* h, int i, ovs_tensor* d) {                      \
         return ovs::node_output(static_cast<ovs::NodeHandle*>(h), i, d);                                                             \
     }                                                                                                                                \
+    /* a second handle on the SAME op instance: evaluate() is const and may run concurrently from several infer requests */        \
+    extern "C" __attribute__((visibility("default"))) void* PREFIX##_node_share(void* h) {                                           \
+        auto* n = new ovs::NodeHandle();                                                                                             \
+        n->node = static_cast<ovs::NodeHandle*>(h)->node;                                                                            \
+        n->producers = static_cast<ovs::NodeHandle*>(h)->producers;                                                                  \
+        return n;                                                                                                                    \
+    }                                                                                                                                \
     extern "C" __attribute__((visibility("default"))) double PREFIX##_node_last_ms(void* h) { return static_cast<ovs::NodeHandle*>(h)->last_ms; } \
     extern "C" __attribute__((visibility("default"))) const char* PREFIX##_node_type(void* h) { return static_cast<ovs::NodeHandle*>(h)->node->get_type_name(); } \
     extern "C" __attribute__((visibility("default"))) void PREFIX##_node_destroy(void* h) { delete static_cast<ovs::NodeHandle*>(h); } \

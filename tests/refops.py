@@ -89,3 +89,55 @@ def vocab_decoder(vocab, skip_tokens, as_input=True):
 def simple(name, protos, **attrs):
     op = ref.RefOp(name, protos, **attrs)
     return lambda *ins: tuple(op(*ins))
+
+
+class RefChain:
+    """The op chain of a converted tokenizer IR on the reference's own code: RegexSplit -> BPETokenizer, or RegexSplit ->
+    RegexSplit -> WordpieceTokenizer.  ``chain(batch, threads)`` shards the rows over `threads` concurrent evaluate() calls on
+    the SAME op instances (shared tables and result cache, like several infer requests on one compiled model) and stitches
+    the ragged results; threads = 1 is one plain evaluate() per op, the reference's serial path."""
+
+    def __init__(self, kind, assets):
+        from concurrent.futures import ThreadPoolExecutor
+        from openvino_tokenizers_b200 import assets as A
+        from openvino_tokenizers_b200.strings import pack_strings
+        self.kind, self._pool_cls = kind, ThreadPoolExecutor
+        if kind == "bpe":
+            v, ml, mr, ad, aid = assets.tensors()
+            self.pat = [assets.split_pattern.encode()]
+            self.splits = [regex_split(assets.split_pattern, "isolate").op]
+            self.consts = [*v, *ml, *mr] + ([*ad, np.asarray(aid, np.int32)] if ad is not None else [])
+            self.tok = bpe(v, ml, mr, ad, aid, cache_capacity=assets.cache_capacity).op
+        else:
+            v = pack_strings(assets.vocab)
+            self.pat = [A.BERT_WHITESPACE_PATTERN.encode(), A.BERT_PUNCT_PATTERN.encode()]
+            self.splits = [regex_split(A.BERT_WHITESPACE_PATTERN, "remove").op, regex_split(A.BERT_PUNCT_PATTERN, "isolate").op]
+            self.consts = [*v, np.asarray(assets.unk_token_id, np.int32)]
+            self.tok = wordpiece(v, assets.unk_token_id, assets.suffix_indicator, assets.max_bytes_per_word).op
+        self._shared = {}
+
+    def _ops(self, t):
+        if t not in self._shared:
+            self._shared[t] = ([s if t == 0 else s.share() for s in self.splits], self.tok if t == 0 else self.tok.share())
+        return self._shared[t]
+
+    def _one(self, t, rb, re_, b, e, c):
+        splits, tok = self._ops(t)
+        cur = (rb, re_, b, e)
+        for s, pat in zip(splits, self.pat):
+            o = s(cur[0], cur[1], cur[2], cur[3], c, np.zeros(len(cur[2]), np.bool_), pat)
+            cur = (o[0], o[1], o[2], o[3])
+        return tok(cur[0], cur[1], cur[2], cur[3], c, *self.consts)
+
+    def __call__(self, batch, threads=1):
+        rb, re_, b, e, c = batch
+        n = len(rb)
+        threads = max(1, min(threads, n))
+        if threads == 1:
+            return tuple(self._one(0, rb, re_, b, e, c))
+        cuts = [n * t // threads for t in range(threads + 1)]
+        with self._pool_cls(threads) as ex:
+            parts = list(ex.map(lambda t: self._one(t, rb[cuts[t]:cuts[t + 1]], re_[cuts[t]:cuts[t + 1]], b, e, c), range(threads)))
+        offs = np.cumsum([0] + [len(p[2]) for p in parts])
+        return (np.concatenate([p[0] + np.int32(o) for p, o in zip(parts, offs)]), np.concatenate([p[1] + np.int32(o) for p, o in zip(parts, offs)]),
+                np.concatenate([p[2] for p in parts]))

@@ -57,9 +57,14 @@ def bert(ops, oracle_mod):
                 o_s2=oracle_mod.SplitOracle(A.BERT_PUNCT_PATTERN, "isolate"))
 
 
-def oracle_chain_bpe(m, batch):
-    s = m["o_split"](*batch)
-    return m["o_bpe"](s[0], s[1], s[2], s[3], batch[4])
+def oracle_chain_bpe(m, batch, threads=1):
+    s = m["o_split"](*batch, threads=threads)
+    return m["o_bpe"](s[0], s[1], s[2], s[3], batch[4], threads=threads)
+
+
+def host_threads():
+    import os
+    return max(1, min(32, os.cpu_count() or 1))
 
 
 def check_bpe_model(ops, m, batch):
@@ -275,10 +280,10 @@ def test_bpe_empty_inputs(ops, gpt2):
 
 
 # ------------------------------------------------------------------------------------------------
-def oracle_chain_wp(m, batch):
-    s1 = m["o_s1"](*batch)
-    s2 = m["o_s2"](s1[0], s1[1], s1[2], s1[3], batch[4])
-    return s2, m["o_wp"](s2[0], s2[1], s2[2], s2[3], batch[4], m["assets"].unk_token_id)
+def oracle_chain_wp(m, batch, threads=1):
+    s1 = m["o_s1"](*batch, threads=threads)
+    s2 = m["o_s2"](s1[0], s1[1], s1[2], s1[3], batch[4], threads=threads)
+    return s2, m["o_wp"](s2[0], s2[1], s2[2], s2[3], batch[4], m["assets"].unk_token_id, threads=threads)
 
 
 def check_wp(ops, m, batch):
@@ -392,7 +397,7 @@ def test_c4_detokenize_full_size(ops, oracle_mod):
 
 
 def test_c1_full_size_properties(ops, gpt2):
-    """BASELINE config 1 at full size (65 536 x 512 B): size-independent properties + a sampled oracle check."""
+    """BASELINE config 1 at full size (65 536 x 512 B): size-independent properties + the whole batch against the oracle."""
     batch = cases.random_ascii_batch(65536, 512)
     rb, re_, b, e, c = batch
     got = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
@@ -409,12 +414,10 @@ def test_c1_full_size_properties(ops, gpt2):
     for r in sample:
         dec = b"".join(gpt2["assets"].vocab[t] for t in ids[ob[r]:oe[r]])
         assert dec == bytes(c[b[r]:e[r]])
-    # sampled rows against the oracle
-    sel = (rb[sample], re_[sample], b, e, c)
-    exp = oracle_chain_bpe(gpt2, (np.arange(len(sample), dtype=np.int32), np.arange(1, len(sample) + 1, dtype=np.int32),
-                                  b[sample], e[sample], c))
-    for i, r in enumerate(sample):
-        assert np.array_equal(ids[ob[r]:oe[r]], exp[2][exp[0][i]:exp[1][i]])
+    # EVERY row against the oracle (rows sharded over the host threads; the oracle is pinned to the reference's own code by
+    # tests/test_reference_pin.py)
+    exp = oracle_chain_bpe(gpt2, batch, threads=host_threads())
+    assert cases.ragged_rows_equal(got, exp), "C1 full batch differs from the oracle"
     # idempotence: same call, same answer
     again = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
     assert cases.ragged_rows_equal(again, got)
@@ -468,9 +471,8 @@ def test_c3_full_shard_properties(ops, llama3):
     sample = np.r_[0:48, 16000:16048, 32720:32768]
     for r in sample:
         assert b"".join(vocab[t] for t in ids[ob[r]:oe[r]]) == bytes(c[b[r]:e[r]])
-    exp = oracle_chain_bpe(llama3, _sample_rows(batch, sample, 1024))
-    for i, r in enumerate(sample):
-        assert np.array_equal(ids[ob[r]:oe[r]], exp[2][exp[0][i]:exp[1][i]])
+    exp = oracle_chain_bpe(llama3, batch, threads=host_threads())        # every row of the shard
+    assert cases.ragged_rows_equal(got, exp), "C3 full shard differs from the oracle"
     again = ops.split_bpe(llama3["split"], llama3["bpe"], list(batch))
     assert cases.ragged_rows_equal(again, got)
 
@@ -484,10 +486,8 @@ def test_c2_full_size_properties(ops, bert):
     ob, oe, ids = got
     assert ob[0] == 0 and np.array_equal(ob[1:], oe[:-1]) and oe[-1] == len(ids)
     assert ids.min() >= 0 and ids.max() < len(bert["assets"].vocab)
-    sample = np.r_[0:64, 33000:33064, 65472:65536]
-    _, exp = oracle_chain_wp(bert, _sample_rows(batch, sample, 256))
-    for i, r in enumerate(sample):
-        assert np.array_equal(ids[ob[r]:oe[r]], exp[2][exp[0][i]:exp[1][i]])
+    _, exp = oracle_chain_wp(bert, batch, threads=host_threads())         # every row
+    assert cases.ragged_rows_equal(got, exp), "C2 full batch differs from the oracle"
     again = ops.split_wordpiece(bert["s1"], bert["s2"], bert["wp"], list(batch), unk)
     assert cases.ragged_rows_equal(again, got)
 
@@ -652,3 +652,107 @@ def test_sharded_wordpiece_world1_and_concurrent_calls(ops, bert, gpt2):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ------------------------------------------------------------------------------------------------
+# In-order single-pass emit (csrc/kernels.cuh OrderedOut): the fast kernel writes the compact result itself; rows it hands
+# back reserve their worst case and the gaps are closed afterwards.  Every mix must give the reference's contiguous tensors.
+def _device_run(pipe, batch, capacity=None):
+    import ctypes as C
+    import torch
+    from openvino_tokenizers_b200 import _capi as K
+    from openvino_tokenizers_b200 import runtime as R
+    dev = torch.device("cuda", 0)
+    db = R.to_device(batch, dev)
+    cap = int(capacity if capacity is not None else db.n_chars + db.n_elems)
+    o = pipe.alloc_device_out(db.n_rows, cap)
+    rin = K.RaggedStrings(db.rb.data_ptr(), db.re.data_ptr(), db.n_rows, db.begins.data_ptr(), db.ends.data_ptr(),
+                          db.n_elems, db.chars.data_ptr(), db.n_chars, None, K.MEM_DEVICE)
+    out = K.RaggedIds(o["begins"].data_ptr(), o["ends"].data_ptr(), o["ids"].data_ptr(), cap, 0, o["n"].data_ptr(), K.MEM_DEVICE)
+    pipe._call(rin, out, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    n = int(o["n"].item())
+    return o["begins"].cpu().numpy(), o["ends"].cpu().numpy(), o["ids"][:n].cpu().numpy()
+
+
+def _mixed_rows(rng, n, special="<|endoftext|>"):
+    """Rows of every kind the emit has to order: one-window rows, multi-window rows, rows longer than the staging area, empty rows,
+    rows the bit-mask path hands back (an added token in the text, a piece longer than a window)."""
+    rows = []
+    for i in range(n):
+        k = rng.integers(0, 100)
+        if k < 55:
+            rows.append(bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(1, 513)), dtype=np.uint8)).decode())
+        elif k < 70:
+            rows.append(bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(513, 4000)), dtype=np.uint8)).decode())
+        elif k < 75:
+            rows.append("")
+        elif k < 83:
+            rows.append("ab " + special + bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(0, 300)), dtype=np.uint8)).decode())
+        elif k < 90:
+            rows.append("x" * int(rng.integers(600, 1500)) + " tail")                       # one piece longer than a window
+        elif k < 95:
+            rows.append(bytes(rng.integers(0x20, 0x7F, size=int(rng.integers(9000, 14000)), dtype=np.uint8)).decode())   # > staging area
+        else:
+            rows.append("Тест 測試 😁 " * int(rng.integers(1, 60)))
+    return rows
+
+
+@pytest.mark.parametrize("model", ["gpt2", "llama3"])
+def test_ordered_emit_mixed_rows(ops, model, request):
+    from openvino_tokenizers_b200 import runtime as R
+    m = request.getfixturevalue(model)
+    pipe = R.TokenizerPipeline("bpe", "gpt2_synth" if model == "gpt2" else "llama3_synth")
+    rng = np.random.default_rng(77)
+    for n, first_special in ((700, False), (300, True), (1, False), (1, True), (40, False)):
+        rows = _mixed_rows(rng, n)
+        if first_special:
+            rows[0] = "<|endoftext|>" + rows[0]
+        batch = cases.batch_from_strings(rows)
+        exp = oracle_chain_bpe(m, batch, threads=host_threads())
+        assert exp[0][0] == 0 and np.array_equal(exp[0][1:], exp[1][:-1])
+        got_d = _device_run(pipe, batch)
+        assert cases.ragged_rows_equal(got_d, exp), f"{model}: device-resident in-order emit differs (n={n})"
+        got_h = ops.split_bpe(m["split"], m["bpe"], list(batch))
+        assert cases.ragged_rows_equal(got_h, exp), f"{model}: host path differs (n={n})"
+        again = _device_run(pipe, batch)                 # the descriptor array is reused under a new epoch
+        assert cases.ragged_rows_equal(again, exp)
+
+
+def test_ordered_emit_last_rows_handed_back_and_tight_capacity(ops, gpt2):
+    from openvino_tokenizers_b200 import runtime as R
+    pipe = R.TokenizerPipeline("bpe", "gpt2_synth")
+    rows = ["plain text row %d" % i for i in range(50)] + ["<|endoftext|>", "y" * 900, "<|endoftext|> end"]
+    batch = cases.batch_from_strings(rows)
+    exp = oracle_chain_bpe(gpt2, batch)
+    assert cases.ragged_rows_equal(_device_run(pipe, batch), exp)
+    # a caller buffer that holds the result but not the worst case of a handed-back row: the slot-buffer path takes over
+    tight = _device_run(pipe, batch, capacity=len(exp[2]) + 8)
+    assert cases.ragged_rows_equal(tight, exp)
+    # multi-element rows (several strings per row) with skip flags
+    b, e, c = pack_strings(rows)
+    rb = np.arange(0, len(rows), 3, dtype=np.int32)
+    re_ = np.minimum(rb + 3, len(rows)).astype(np.int32)
+    sk = np.zeros(len(rows), np.uint8)
+    sk[50] = 1
+    s = gpt2["o_split"](rb, re_, b, e, c, skips=sk)
+    exp2 = gpt2["o_bpe"](s[0], s[1], s[2], s[3], c)
+    got2 = ops.split_bpe(gpt2["split"], gpt2["bpe"], [rb, re_, b, e, c, sk])
+    assert cases.ragged_rows_equal(got2, exp2)
+
+
+def test_sharded_exchange_two_ranks():
+    """Every rank's gathered slots must equal the single-GPU result of the shard that produced them, for both wire formats
+    (tools/peer_gather_check.py under torchrun; needs two GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    for wire16 in ("0", "1"):
+        env = dict(__import__("os").environ, B200TOK_WIRE16=wire16, MASTER_ADDR="127.0.0.1")
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29577", str(root / "tools" / "peer_gather_check.py"), "8192"], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "on every rank: True" in r.stdout, r.stdout[-2000:]
