@@ -124,9 +124,18 @@ struct RowWorkspace {
     // in-order single-pass emit (OrderedOut): look-back descriptors (never cleared: every launch has its own epoch) and the
     // per-warp staging area of rows that span several windows
     DBuf<unsigned long long> desc;
-    uint32_t epoch = 0;
     DBuf<uint8_t> stage;
+    // device-resident calls repeated with the same buffers (a serving loop, the benchmark step) replay a captured CUDA graph of the
+    // launch sequence instead of issuing ~10 launches: the kernels are short enough for the launch gaps to show
+    struct GraphKey {
+        const void* ptr[20]; int64_t num[8];
+    };
+    struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; };
+    GraphEntry graphs[4];
+    int64_t graph_launches[4] = {0, 0, 0, 0};     // kernels one replay launches (the handle's launch counter keeps counting them)
+    int graph_next = 0;
     ~RowWorkspace() {
+        for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         for (auto s_ : pipe) if (s_) cudaStreamDestroy(s_);
         for (auto e_ : pipe_ev) if (e_) cudaEventDestroy(e_);
         if (h_pipe) cudaFreeHost(h_pipe);
@@ -226,21 +235,20 @@ int ensure_ws(b200tok_object* o) {
     return B200TOK_OK;
 }
 
-constexpr int kStageCap = 4096;        // ids per warp in the staging area; longer rows take the generic path
+constexpr int kStageCap = 8192;        // ids per warp in the staging ring; rows of up to half of it always fit, longer ones may take the generic path
 
-// Descriptor array for `rows` rows and the staging area for `warps` warps; hands out the epoch pair of this launch.
-int ensure_ordered(RowWorkspace& w, int64_t rows, int64_t warps, size_t id_bytes, cudaStream_t st, uint32_t& epoch) {
-    const unsigned long long* before = w.desc.p;
-    const size_t cap_before = w.desc.cap;
-    CU(w.desc.ensure((size_t)rows));
-    if (w.desc.p != before || w.desc.cap != cap_before || w.epoch >= (1u << 30) - 4u) {
-        CU(cudaMemsetAsync(w.desc.p, 0, w.desc.cap * sizeof(unsigned long long), st));
-        w.epoch = 0;
-    }
-    CU(w.stage.ensure((size_t)warps * kStageCap * id_bytes));
-    epoch = w.epoch + 1;
-    w.epoch += 2;          // the gap-closing pass runs its own chain under epoch + 1
+// Look-back descriptors for `n` rows / tiles, cleared on the stream (a few KB; the memset is part of the launch sequence so that a
+// replayed CUDA graph starts from clean descriptors too).  Epoch 1 is the first chain of the launch, 2 a second one.
+int ensure_desc(RowWorkspace& w, int64_t n, cudaStream_t st, uint32_t& epoch) {
+    CU(w.desc.ensure((size_t)n));
+    CU(cudaMemsetAsync(w.desc.p, 0, (size_t)n * sizeof(unsigned long long), st));
+    epoch = 1;
     return B200TOK_OK;
+}
+// ... plus the staging rings of `warps` warps (in-order emit)
+int ensure_ordered(RowWorkspace& w, int64_t rows, int64_t warps, size_t id_bytes, cudaStream_t st, uint32_t& epoch) {
+    CU(w.stage.ensure((size_t)warps * kStageCap * id_bytes));
+    return ensure_desc(w, rows, st, epoch);
 }
 
 struct RowCall {
@@ -315,8 +323,12 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
     const bool fast = call.op == OP_BPE && (c.P.spec.pat == PAT_GPT2 || c.P.spec.pat == PAT_GPT2_DIGITS || c.P.spec.pat == PAT_LLAMA3) && c.P.mode == SPLIT_ISOLATED &&
                       !c.P.repeat && c.P.max_splits == -1 && c.P.suffix_len == 0 && !(c.P.dbg_flags & 2);
     // in-order emit (no slot bases, no compaction pass) whenever the caller's id buffer can hold the worst case a handed-back row reserves
-    const bool fast_ordered = fast && !c.peers && !c.zero_copy && !(c.P.dbg_flags & 16) && c.out_cap >= c.P.tmp_cap - 1;
-    if (!c.P.direct_base && !fast_ordered) {
+    // (opt-in, B200TOK_ORDERED_EMIT=1: measured slower than slots + compaction on one GPU — every row pays the latency of its look-back
+    // and of reading its ids back from the staging ring)
+    static const bool ordered_env = [] { const char* e = getenv("B200TOK_ORDERED_EMIT"); return e && atoi(e); }();
+    const bool fast_ordered = ordered_env && fast && !c.peers && !c.zero_copy && c.out_cap >= c.P.tmp_cap - 1;
+    const bool fast_alloc = fast && !fast_ordered && !c.peers && !c.P.direct_base;      // slots from the bump allocator: no capacity pass, no scan
+    if (!c.P.direct_base && !fast_ordered && !fast_alloc) {
         row_capacity_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.P.rb, c.P.re, c.P.begins, c.P.ends, (int32_t)B, c.per_elem_extra, c.row_cap);
         cub::DeviceScan::ExclusiveSum(c.cub_tmp, c.cub_bytes, c.row_cap, const_cast<int32_t*>(c.P.row_base), (int)B, st);
         ++owner->launches;
@@ -347,10 +359,11 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         const int fast_per_sm = fast_ctas_env > 0 ? fast_ctas_env : (int)std::max<size_t>(1, std::min<size_t>(narrow ? 5 : 4, (227 * 1024) / (fsm + 1024)));
         const int fast_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * fast_per_sm);
         RowParams Pk = c.P;
+        Pk.alloc_base = fast_alloc ? 1 : 0;
         if (ordered) {
             uint32_t epoch = 0;
-            if (int rc = ensure_ordered(w, std::max<int64_t>(c.desc_rows, c.desc_off + B), (int64_t)owner->sm_count * 5 * WARPS_PER_BLOCK, narrow ? 2 : 4, st, epoch)) return rc;
-            Pk.oo = OrderedOut{w.desc.p + c.desc_off, epoch, c.d_oa, c.d_ob, c.d_oe, c.out_cap, c.total_dev, w.stage.p, kStageCap};
+            if (int rc = ensure_ordered(w, B, (int64_t)owner->sm_count * 5 * WARPS_PER_BLOCK, narrow ? 2 : 4, st, epoch)) return rc;
+            Pk.oo = OrderedOut{w.desc.p, epoch, c.d_oa, c.d_ob, c.d_oe, c.out_cap, c.total_dev, w.stage.p, kStageCap};
             Pk.direct_base = 0;               // handed-back rows: the fast kernel stores their slot base (= gapped output offset)
         }
         if (peer_fast) {
@@ -429,11 +442,11 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
                                                                        c.P.status, c.total_dev);
         ++owner->launches;
     } else {
-        finish_offsets_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.d_ob, c.P.row_cnt, (int32_t)B, c.d_oe, c.P.status, c.total_dev);
+        // one pass: row ends + total (the former finish_offsets kernel) and the copy of every row from its slot to its final place
         compact_rows_kernel<<<owner->sm_count * 8, 256, 0, st>>>(c.P.tmp_a, c.is_split ? c.P.tmp_b : nullptr, (c.is_split && c.d_oc) ? c.P.tmp_c : nullptr,
                                                                   c.P.row_base, c.P.row_ext, c.P.row_flag, c.d_ob, (int32_t)B, c.d_oa, c.d_obb, c.d_oc,
-                                                                  c.out_cap, c.P.status, nullptr, nullptr, nullptr);
-        owner->launches += 2;
+                                                                  c.out_cap, c.P.status, nullptr, c.P.row_cnt, c.d_oe, c.total_dev);
+        ++owner->launches;
     }
     CU(cudaGetLastError());
     return B200TOK_OK;
@@ -754,7 +767,45 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
         c.total_dev = (async && out_ids->n_ids_device) ? out_ids->n_ids_device : w.total.p;
         c.is_split = is_split;
         c.peers = peers;
-        if ((rc = launch_chunk(owner, call, c, st, w.timing))) return rc;
+        // asynchronous device-resident call on a real stream: replay (or capture) the launch sequence as one CUDA graph
+        static const bool graphs_on = [] { const char* e = getenv("B200TOK_GRAPHS"); return !e || atoi(e); }();
+        bool graphed = false;
+        if (async && !peers && !w.timing && graphs_on && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+                RowWorkspace::GraphKey key;
+                std::memset(&key, 0, sizeof(key));
+                const void* ptrs[] = {d_rb, d_re, d_b, d_e, d_c, d_sk, d_ob, d_oe, d_oa, c.total_dev, c.P.status, c.P.tmp_a, c.P.row_base, c.P.row_ext,
+                                      c.P.row_cnt, c.P.row_flag, c.P.giants, c.pool, call.split, call.split2};
+                for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.ptr[i] = ptrs[i];
+                const int64_t nums[] = {B, E, N, out_cap, tmp_cap, (int64_t)c.pool_bytes, (int64_t)c.P.giants_cap, (int64_t)call.op | ((int64_t)call.unk_id << 8) | ((int64_t)P.dbg_flags << 40)};
+                for (size_t i = 0; i < sizeof(nums) / sizeof(nums[0]); ++i) key.num[i] = nums[i];
+                cudaGraphExec_t exec = nullptr;
+                for (auto& g : w.graphs) if (g.exec && std::memcmp(&g.key, &key, sizeof(key)) == 0) exec = g.exec;
+                if (!exec && cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                    const int64_t launches_before = owner->launches;
+                    const int lrc = launch_chunk(owner, call, c, st, false);
+                    cudaGraph_t graph = nullptr;
+                    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                    if (lrc == B200TOK_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                        auto& slot = w.graphs[w.graph_next];
+                        w.graph_next = (w.graph_next + 1) % 4;
+                        if (slot.exec) cudaGraphExecDestroy(slot.exec);
+                        slot.key = key; slot.exec = exec;
+                        slot.key.num[7] ^= 0;      // (key complete)
+                        w.graph_launches[&slot - w.graphs] = owner->launches - launches_before;
+                    } else { exec = nullptr; cudaGetLastError(); }
+                    owner->launches = launches_before;
+                    if (graph) cudaGraphDestroy(graph);
+                }
+                if (exec) {
+                    CU(cudaGraphLaunch(exec, st));
+                    for (int gi = 0; gi < 4; ++gi) if (w.graphs[gi].exec == exec) owner->launches += w.graph_launches[gi];
+                    graphed = true;
+                }
+            }
+        }
+        if (!graphed && (rc = launch_chunk(owner, call, c, st, w.timing))) return rc;
         CU(cudaEventRecord(w.last_done, st));
         if (async) return B200TOK_OK;
 

@@ -31,7 +31,7 @@ constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK =
 enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2, OP_SPECIAL = 3 };
 
 // status words (device int32 array)
-enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_MINREDO = 8, ST_TICKET3 = 9,
+enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_MINREDO = 8, ST_TICKET3 = 9, ST_ALLOC = 10,
              ST_WORDS = 12 };
 enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
 
@@ -81,34 +81,51 @@ __device__ __forceinline__ unsigned long long desc_load(const unsigned long long
 __device__ __forceinline__ void desc_store(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
-// Exclusive prefix of `count` over rows [first, row) (+ `seed` for row == first); publishes this row's descriptors.  Warp-uniform.
-__device__ __forceinline__ long long lookback_exclusive(unsigned long long* desc, uint32_t epoch, int first, int row, uint32_t count, long long seed, int lane) {
+// Publish a row's own count as soon as it is known (row == first: its inclusive prefix right away).  Lane 0 only.
+__device__ __forceinline__ void lookback_publish_count(unsigned long long* desc, uint32_t epoch, int first, int row, uint32_t count, long long seed) {
     const unsigned long long tag = (unsigned long long)epoch << 34;
-    if (row == first) {
-        if (lane == 0) desc_store(desc + row, tag | kDescPrefix | (uint32_t)(seed + count));
-        return seed;
-    }
-    if (lane == 0) desc_store(desc + row, tag | kDescAgg | count);
-    long long excl = 0;
-    for (int idx = row - 1;; idx -= 32) {
-        const int j = idx - lane;
-        unsigned long long d;
-        for (int spin = 0;; ++spin) {
-            d = j >= first ? desc_load(desc + j) : (tag | kDescAgg);            // lanes before the first row contribute nothing
-            const bool ok = (d >> 34) == epoch && ((d >> 32) & 3u) != 0u;
-            if (__all_sync(0xFFFFFFFFu, ok)) break;
-            if (spin > 2) __nanosleep(64);
-        }
-        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, ((d >> 32) & 3u) == 2u);
-        long long v = (uint32_t)d;
-        if (pm) { const int k = __ffs(pm) - 1; if (lane > k) v = 0; }
+    desc_store(desc + row, row == first ? (tag | kDescPrefix | (uint32_t)(seed + count)) : (tag | kDescAgg | count));
+}
+// One look-back step for `row` (> first): examines up to 32 predecessors below `idx` (initially row - 1), adds what has been
+// published to `acc`, moves `idx` down.  Returns 1 once a predecessor's inclusive prefix (or the first row) has been reached:
+// acc is then the exclusive prefix of `row`; 0 = all 32 had published their counts, keep walking; -1 = stopped at a predecessor
+// that has not published yet (try again later: the progress made is kept in idx / acc).  Warp-uniform.
+__device__ __forceinline__ int lookback_poll(const unsigned long long* desc, uint32_t epoch, int first, int& idx, long long& acc, int lane) {
+    // four chunks of 32 descriptors are fetched at once: a walk is a chain of L2 round trips, and this makes each trip cover 128 rows
+    constexpr int U = 4;
+    unsigned long long d[U];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        excl += v;
-        if (pm || idx - 32 < first) break;
+    for (int u = 0; u < U; ++u) {
+        const int j = idx - 32 * u - lane;
+        d[u] = j >= first ? desc_load(desc + j) : (((unsigned long long)epoch << 34) | kDescPrefix);   // below the first row: prefix 0
     }
-    if (lane == 0) desc_store(desc + row, tag | kDescPrefix | (uint32_t)(excl + count));
-    return excl;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t fl = (uint32_t)(d[u] >> 32) & 3u;
+        const bool ok = (d[u] >> 34) == epoch && fl != 0u;
+        const uint32_t okm = __ballot_sync(0xFFFFFFFFu, ok);
+        const int run = okm == 0xFFFFFFFFu ? 32 : __ffs(~okm) - 1;             // predecessors idx, idx-1, ... published without a gap
+        if (run == 0) return -1;
+        const uint32_t runm = run == 32 ? 0xFFFFFFFFu : ((1u << run) - 1u);
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, fl == 2u) & runm;
+        const int k = pm ? __ffs(pm) - 1 : run - 1;                            // last lane that contributes
+        acc += __reduce_add_sync(0xFFFFFFFFu, lane <= k ? (uint32_t)d[u] : 0u);   // (counts and prefixes fit 31 bits: int32 offsets)
+        idx -= k + 1;
+        if (pm) return 1;
+        if (run < 32) return -1;
+    }
+    return 0;
+}
+// Blocking form: exclusive prefix of `count` over rows [first, row) (+ `seed` for row == first); publishes both descriptors.
+__device__ __forceinline__ long long lookback_exclusive(unsigned long long* desc, uint32_t epoch, int first, int row, uint32_t count, long long seed, int lane) {
+    if (lane == 0) lookback_publish_count(desc, epoch, first, row, count, seed);
+    if (row == first) return seed;
+    int idx = row - 1;
+    long long acc = 0;
+    for (int r; (r = lookback_poll(desc, epoch, first, idx, acc, lane)) != 1;)
+        if (r < 0) __nanosleep(128);
+    if (lane == 0) desc_store(desc + row, ((unsigned long long)epoch << 34) | kDescPrefix | (uint32_t)(acc + count));
+    return acc;
 }
 
 struct RowParams {
@@ -139,6 +156,8 @@ struct RowParams {
     // contiguous, increasing elements (verified by the host): a row's slot base follows from its first element's byte
     // offset, so the capacity kernel + scan are skipped:  base = begins[rb[row]] - direct_byte0 + (rb[row] - direct_elem0) * extra
     int32_t direct_base; int32_t direct_byte0; int32_t direct_elem0; int32_t direct_extra;
+    // fast kernel: a row takes its slot range from a bump allocator (status[ST_ALLOC]) when it starts — no capacity pass, no scan
+    int32_t alloc_base;
     // list mode: process rows row_list[0 .. status[ST_NREDO]) (rows the fast kernel handed back) instead of [0, n_rows)
     const int32_t* row_list;
     // sharded fast path: the emit step stores ids (and row extents) straight into every rank's buffers, rows stay at their
@@ -1142,7 +1161,7 @@ __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, 
                                     const int32_t* row_base, const int32_t* row_ext, const uint8_t* row_flag,
                                     const int32_t* out_begin, int32_t n_rows,
                                     int32_t* out_a, int32_t* out_b, uint8_t* out_c, int64_t out_cap, int32_t* status,
-                                    const int32_t* dst_base, const int32_t* row_cnt, int32_t* out_end) {
+                                    const int32_t* dst_base, const int32_t* row_cnt, int32_t* out_end, int64_t* total_out = nullptr) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int64_t base = dst_base ? (int64_t)*dst_base : 0;
@@ -1153,11 +1172,21 @@ __global__ void compact_rows_kernel(const int32_t* tmp_a, const int32_t* tmp_b, 
         if (out_end && lane == 0) {          // folded finish_offsets: row end + chunk total
             const int32_t e = out_begin[r] + row_cnt[r];
             out_end[r] = e;
-            if (r == n_rows - 1) status[ST_TOTAL] = e;
+            if (r == n_rows - 1) { status[ST_TOTAL] = e; if (total_out) *total_out = e; }
         }
         if (!(row_flag[r] & 1)) {
             if (dst + ext > out_cap) { if (lane == 0) atomicOr(&status[ST_ERROR], ERR_TMP_OVERFLOW); continue; }
-            if (!out_b && !out_c) {            // ids only: four independent loads in flight per lane
+            if (row_flag[r] & 4) {             // 16-bit slot written by the fast kernel: widen while copying
+                const uint16_t* sp = reinterpret_cast<const uint16_t*>(tmp_a + src);
+                int32_t* dp = out_a + dst;
+                for (int t = lane; t < ext; t += 128) {
+                    uint16_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < ext) ? __ldcs(sp + t + 32 * u) : (uint16_t)0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (t + 32 * u < ext) __stcs(dp + t + 32 * u, (int32_t)v[u]);
+                }
+            } else if (!out_b && !out_c) {     // ids only: four independent loads in flight per lane
                 const int32_t* sp = tmp_a + src;
                 int32_t* dp = out_a + dst;
                 for (int t = lane; t < ext; t += 128) {

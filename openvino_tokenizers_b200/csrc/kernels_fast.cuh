@@ -29,6 +29,7 @@ struct __align__(16) FastSmem {
     uint32_t m[11][kMStride];                // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F NL PG
     IdT ids[WIN];                            // symbol per position; kDead = merged away
     alignas(16) uint32_t key[WIN + 4];       // merge keys; after the merges: staging of the window's compacted ids for wide peer stores
+    int32_t pend_row[4], pend_cnt[4], pend_off[4];   // in-order emit: rows tokenised but not yet written out (row | redo << 31, count, ring offset)
     __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }
     __device__ __forceinline__ uint16_t* act() { return reinterpret_cast<uint16_t*>(&m[0][0]); }   // merge queue; the masks are consumed by then
     static constexpr IdT kDead = (IdT)-1;
@@ -425,10 +426,9 @@ __device__ __forceinline__ bool stage_window(FastSmem<IdT>& S, const RowParams& 
     return all_ascii;
 }
 
-// Compact the live ids of S.ids[0 .. send) to the front of S.ids, in place (a token only ever moves towards lower indices, and
-// every iteration reads its 128 positions before it writes).  Returns the number of live ids.
+// Compact the live ids of S.ids[0 .. send) into dst[0 ..) (global staging ring).  Returns the number of live ids.
 template <class IdT>
-__device__ __forceinline__ int compact_window(FastSmem<IdT>& S, int send, int lane) {
+__device__ __forceinline__ int compact_window(FastSmem<IdT>& S, int send, int lane, IdT* __restrict__ dst) {
     const uint32_t ltm = (1u << lane) - 1u;
     int n_out = 0;
     for (int w = lane; w - lane < send; w += 128) {
@@ -440,64 +440,48 @@ __device__ __forceinline__ int compact_window(FastSmem<IdT>& S, int send, int la
         for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] != S.kDead);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (tok[u] != S.kDead) S.ids[n_out + __popc(m[u] & ltm)] = tok[u];
+            if (tok[u] != S.kDead) dst[n_out + __popc(m[u] & ltm)] = tok[u];
             n_out += __popc(m[u]);
         }
     }
-    __syncwarp();
     return n_out;
 }
 
-// The row loop of the in-order single-pass emit (OrderedOut, kernels.cuh): tokenise the row, learn its count, obtain its output
-// offset by look-back, write the compact ids once.  A row the bit-mask path cannot finish reserves its worst-case extent
-// (count <= bytes, src/bpe_tokenizer.cpp:135) instead and goes on the redo list; ordered_recompact_kernel closes those gaps.
+// The row loop of the in-order single-pass emit (OrderedOut, kernels.cuh).  A warp tokenises a row into its private staging ring
+// (global memory, L2-resident), publishes the row's count at once and goes on to the next row; up to four rows wait in the ring
+// until the look-back over the counts of all earlier rows yields their output offset, then they are copied — widened to i32 — to
+// their final place.  (Writing a row only when its offset is known but never WAITING for it while there is other work is what
+// keeps the warps from marching in lock step behind the slowest one.)  A row the bit-mask path cannot finish reserves its worst
+// case (count <= bytes, src/bpe_tokenizer.cpp:135) and goes on the redo list; ordered_recompact_kernel closes those gaps.
+constexpr int kPend = 4;
 template <class IdT, bool L3>
 __device__ __forceinline__ void ordered_rows(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32_smem, const uint8_t* ascii_smem,
                                              int lane, int32_t* __restrict__ redo_rows) {
     const OrderedOut& O = P.oo;
-    IdT* const stage = reinterpret_cast<IdT*>(O.stage) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * (size_t)O.stage_cap;
-    for (;;) {
-        int row = 0;
-        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
-        row = __shfl_sync(FULL, row, 0);
-        if (row >= P.n_rows) break;
-        const int p0 = P.rb[row], p1 = P.re[row];
-        int emitted = 0;
-        bool redo = false, direct = false;
-        for (int p = p0; p < p1 && !redo; ++p) {
-            const int eb = P.begins[p], ee = P.ends[p];
-            if (P.skips && P.skips[p]) { redo = true; break; }
-            int pos = eb;
-            while (pos < ee) {
-                const int end_rel = ee - pos;
-                const int wlen = end_rel < WIN ? end_rel : WIN;
-                const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
-                const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
-                const bool all_ascii = stage_window(S, P, pos, lb, nload, lane);
-                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
-                if (send <= 0) { redo = true; break; }
-                const int n_out = compact_window(S, send, lane);
-                if (p1 - p0 == 1 && pos == eb && send == end_rel) {      // one window covered the whole row: its ids leave from shared memory
-                    direct = true;
-                    emitted = n_out;
-                } else {
-                    if (emitted + n_out > O.stage_cap) { redo = true; break; }      // longer than the staging area: the generic path takes the row
-                    for (int t = lane; t < n_out; t += 32) stage[emitted + t] = S.ids[t];
-                    emitted += n_out;
-                    __syncwarp();
+    IdT* const ring = reinterpret_cast<IdT*>(O.stage) + (size_t)(blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * (size_t)O.stage_cap;
+    int n_pend = 0, head = 0, ring_used = 0;
+    int lb_idx = -1;             // look-back progress of the oldest waiting row (-1: not started)
+    long long lb_acc = 0;
+
+    // Write out the oldest waiting row if its offset can be resolved (blocking: wait until it can).  Warp-uniform.
+    auto retire = [&](bool blocking) -> bool {
+        const int prow = S.pend_row[head];
+        const int row = prow & 0x7FFFFFFF;
+        const bool redo = prow < 0;
+        const int count = S.pend_cnt[head], off = S.pend_off[head];
+        long long excl = 0;
+        if (row > 0) {
+            if (lb_idx < 0) { lb_idx = row - 1; lb_acc = 0; }
+            for (int r; (r = lookback_poll(O.desc, O.epoch, 0, lb_idx, lb_acc, lane)) != 1;) {
+                if (r < 0) {                 // a predecessor is still being tokenised
+                    if (!blocking) return false;
+                    __nanosleep(256);
                 }
-                pos += send;
             }
+            excl = lb_acc;
+            if (lane == 0) desc_store(O.desc + row, ((unsigned long long)O.epoch << 34) | kDescPrefix | (uint32_t)(excl + count));
         }
-        uint32_t count = (uint32_t)emitted;
-        if (redo) {               // reserve the row's worst case: one id per byte
-            long long c = 0;
-            for (int p = p0 + lane; p < p1; p += 32) { const int l = P.ends[p] - P.begins[p]; c += l > 0 ? l : 0; }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-            count = (uint32_t)(c > 0x7FFFFFFF ? 0x7FFFFFFF : c);
-        }
-        const long long excl = lookback_exclusive(O.desc, O.epoch, 0, row, count, 0, lane);
+        lb_idx = -1;
         const bool fits = excl + (long long)count <= O.cap;
         if (!fits && lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
         if (redo) {
@@ -511,13 +495,13 @@ __device__ __forceinline__ void ordered_rows(FastSmem<IdT>& S, const RowParams& 
         } else {
             if (fits) {
                 int32_t* const outp = O.ids + excl;
-                const IdT* const src = direct ? S.ids : stage;
-                for (int t = lane; t < emitted; t += 128) {
+                const IdT* const src = ring + off;
+                for (int t = lane; t < count; t += 128) {
                     IdT v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < emitted) ? src[t + 32 * u] : (IdT)0;
+                    for (int u = 0; u < 4; ++u) v[u] = (t + 32 * u < count) ? __ldcg(src + t + 32 * u) : (IdT)0;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (t + 32 * u < emitted) __stcs(outp + t + 32 * u, (int32_t)v[u]);
+                    for (int u = 0; u < 4; ++u) if (t + 32 * u < count) __stcs(outp + t + 32 * u, (int32_t)v[u]);
                 }
             }
             if (lane == 0) { O.begins[row] = (int32_t)excl; O.ends[row] = (int32_t)(excl + count); P.row_flag[row] = 0; }
@@ -526,7 +510,61 @@ __device__ __forceinline__ void ordered_rows(FastSmem<IdT>& S, const RowParams& 
             P.status[ST_TOTAL] = (int32_t)(excl + count);
             if (O.total) *O.total = excl + count;
         }
+        head = (head + 1) & (kPend - 1);
+        if (--n_pend == 0) ring_used = 0;
+        return true;
+    };
+
+    bool exhausted = false;
+    for (;;) {
+        // the one place rows are written out.  Forced (blocking) when the queue is full, the ring is more than half full, or no rows
+        // are left — a warp never blocks while it holds a ticket, or the rows behind it would wait for a row nobody works on;
+        // otherwise a row is tried once it has a successor in the queue: by then its predecessors have usually published.
+        while (n_pend > 0) {
+            const bool must = exhausted || n_pend == kPend || ring_used > (O.stage_cap >> 1);
+            if (!must && n_pend < 2) break;
+            if (!retire(must)) break;
+        }
+        if (exhausted) break;
+        int row = 0;
+        if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+        row = __shfl_sync(FULL, row, 0);
+        if (row >= P.n_rows) { exhausted = true; continue; }
+        const int p0 = P.rb[row], p1 = P.re[row];
+        long long need = 0;          // upper bound of the row's ids: one per byte (src/bpe_tokenizer.cpp:135)
+        for (int p = p0 + lane; p < p1; p += 32) { const int l = P.ends[p] - P.begins[p]; need += l > 0 ? l : 0; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) need += __shfl_xor_sync(FULL, need, o);
+        int emitted = 0;
+        bool redo = ring_used + need > O.stage_cap;  // does not fit the ring (rows longer than half of it may not): the generic path takes the row
+        for (int p = p0; p < p1 && !redo; ++p) {
+            const int eb = P.begins[p], ee = P.ends[p];
+            if (P.skips && P.skips[p]) { redo = true; break; }
+            int pos = eb;
+            while (pos < ee) {
+                const int end_rel = ee - pos;
+                const int wlen = end_rel < WIN ? end_rel : WIN;
+                const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
+                const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
+                const bool all_ascii = stage_window(S, P, pos, lb, nload, lane);
+                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                if (send <= 0) { redo = true; break; }
+                emitted += compact_window(S, send, lane, ring + ring_used + emitted);
+                __syncwarp();
+                pos += send;
+            }
+        }
+        const uint32_t count = redo ? (uint32_t)(need > 0x7FFFFFFF ? 0x7FFFFFFF : need) : (uint32_t)emitted;   // handed back: reserve the worst case
+        if (lane == 0) {
+            lookback_publish_count(O.desc, O.epoch, 0, row, count, 0);
+            const int slot = (head + n_pend) & (kPend - 1);
+            S.pend_row[slot] = row | (redo ? (int)0x80000000 : 0);
+            S.pend_cnt[slot] = (int32_t)count;
+            S.pend_off[slot] = ring_used;
+        }
         __syncwarp();
+        ++n_pend;
+        if (!redo) ring_used += emitted;
     }
 }
 
@@ -554,7 +592,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
             if (row >= P.n_rows) break;
             const int p0 = P.rb[row], p1 = P.re[row];
             int64_t base;
-            if (P.direct_base) {
+            int alloc_b0 = 0;
+            if (P.alloc_base) {          // take the row's worst-case slot range (one id per byte, src/bpe_tokenizer.cpp:135) from the bump allocator
+                int c = 0;
+                for (int p = p0 + lane; p < p1; p += 32) { const int l = P.ends[p] - P.begins[p]; c += l > 0 ? l : 0; }
+                c = (int)__reduce_add_sync(FULL, (unsigned)c);
+                if (lane == 0) alloc_b0 = atomicAdd(&P.status[ST_ALLOC], c);       // (the result is first looked at when the row emits: no wait here)
+                base = -1;
+            } else if (P.direct_base) {
                 base = p1 > p0 ? (int64_t)(P.begins[p0] - P.direct_byte0) + (int64_t)(p0 - P.direct_elem0) * P.direct_extra : 0;
                 if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
             } else base = P.row_base[row];
@@ -595,6 +640,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                     __syncwarp();
                     const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
                     if (send <= 0) { redo = true; break; }
+                    if (base < 0) {                       // bump-allocated slot: pick the allocator's answer up now
+                        base = __shfl_sync(FULL, alloc_b0, 0);
+                        if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
+                    }
                     if (base + emitted + send > P.tmp_cap) {
                         if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
                     } else {
@@ -610,9 +659,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
     #pragma unroll
                             for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
                             if (!nP) {
+                                // 16-bit ids stay 16 bits wide in the row slot (the first half of its i32 range): half the bytes written
+                                // here and read by the compaction pass, which widens them
     #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
-                                    if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
+                                    if (tok[u] >= 0) {
+                                        if constexpr (sizeof(IdT) == 2) reinterpret_cast<uint16_t*>(P.tmp_a + base)[emitted + n_out + __popc(m[u] & ltm)] = (uint16_t)tok[u];
+                                        else outp[n_out + __popc(m[u] & ltm)] = tok[u];
+                                    }
                                     n_out += __popc(m[u]);
                                 }
                             } else {
@@ -662,9 +716,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                     pos += send;
                 }
             }
+            if (base < 0) {                               // nothing was emitted (handed back, or empty): the row still owns its slot range
+                base = __shfl_sync(FULL, alloc_b0, 0);
+                if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;
+            }
             if (lane == 0) {
                 if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
-                else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = 0; }
+                else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = (sizeof(IdT) == 2 && !P.peer.world) ? 4 : 0; }      // bit 2: 16-bit slot
             }
             if (P.peer.world && !redo) {                       // sharded: publish the row's extent to every rank
                 const int64_t o0 = (int64_t)P.peer.rank * P.peer.slot_capacity + base;
