@@ -12,6 +12,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/b200tok.h"
@@ -227,7 +228,7 @@ int init_object(b200tok_object* o, int kind, int device) {
 int ensure_ws(b200tok_object* o) {
     RowWorkspace& w = o->ws;
     if (!w.stream) CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-    if (!w.h_status) CU(cudaMallocHost(&w.h_status, 64));
+    if (!w.h_status) CU(cudaMallocHost(&w.h_status, ST_WORDS * 4 + 64));
     CU(w.status.ensure(ST_WORDS));
     CU(w.pool_used.ensure(1));
     CU(w.total.ensure(1));
@@ -327,7 +328,16 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
     // and of reading its ids back from the staging ring)
     static const bool ordered_env = [] { const char* e = getenv("B200TOK_ORDERED_EMIT"); return e && atoi(e); }();
     const bool fast_ordered = ordered_env && fast && !c.peers && !c.zero_copy && c.out_cap >= c.P.tmp_cap - 1;
-    const bool fast_alloc = fast && !fast_ordered && !c.peers && !c.P.direct_base;      // slots from the bump allocator: no capacity pass, no scan
+    // Row-loop variants of the fast kernel, all bit-identical in their results (tests/test_gpu_parity.py runs each):
+    //   default            plain loop: 16-byte __ldg staging, slot bases from the capacity scan          C1 kernel 0.299 ms
+    //   B200TOK_SLOT_ALLOC=1  plain loop, slots from a bump allocator (no capacity kernel / scan)       0.315 ms (-2 launches, net slower)
+    //   B200TOK_TMA=1|2    TMA loop: windows staged by cp.async.bulk + mbarrier (2), next window prefetched while the
+    //                      current one is tokenised (1); slots from the bump allocator                   0.335 ms
+    // (same box, same run: gpurun_out/bench_c1_r02o_*.json; the kernel is issue-bound, not latency-bound, so the extra
+    // bookkeeping of either variant costs more than the latency it hides — DESIGN.md 3.1)
+    static const int tma_env = [] { const char* e = getenv("B200TOK_TMA"); return e ? atoi(e) : 0; }();
+    static const bool slot_alloc_env = [] { const char* e = getenv("B200TOK_SLOT_ALLOC"); return e && atoi(e); }();
+    const bool fast_alloc = fast && !fast_ordered && !c.peers && (tma_env != 0 || slot_alloc_env);
     if (!c.P.direct_base && !fast_ordered && !fast_alloc) {
         row_capacity_kernel<<<(unsigned)((B + nthreads - 1) / nthreads), nthreads, 0, st>>>(c.P.rb, c.P.re, c.P.begins, c.P.ends, (int32_t)B, c.per_elem_extra, c.row_cap);
         cub::DeviceScan::ExclusiveSum(c.cub_tmp, c.cub_bytes, c.row_cap, const_cast<int32_t*>(c.P.row_base), (int)B, st);
@@ -344,22 +354,27 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         const bool peer_fast = c.peers != nullptr;        // sharded: the fast kernel stores into every rank's slot, no compaction follows
         // everything else: in-order single-pass emit — the kernel writes the compact (begins, ends, ids) itself
         const bool ordered = fast_ordered;
-        static bool fast_attr[8][64] = {};
+        static bool fast_attr[12][64] = {};
         const size_t fsm = narrow ? fast_smem_bytes<uint16_t>() : fast_smem_bytes<int32_t>();
-        const void* fn;
-        if (ordered) fn = narrow ? (l3 ? (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, true, true> : (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, false, true>)
-                                 : (l3 ? (const void*)gpt2_bpe_fast_kernel<int32_t, 4, true, true> : (const void*)gpt2_bpe_fast_kernel<int32_t, 4, false, true>);
-        else fn = narrow ? (l3 ? (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, true, false> : (const void*)gpt2_bpe_fast_kernel<uint16_t, 5, false, false>)
-                         : (l3 ? (const void*)gpt2_bpe_fast_kernel<int32_t, 4, true, false> : (const void*)gpt2_bpe_fast_kernel<int32_t, 4, false, false>);
-        if (!fast_attr[ordered * 4 + narrow * 2 + l3][owner->device]) {
+        const int mode = ordered ? 1 : ((peer_fast || tma_env == 0) ? 2 : 0);
+        auto pick = [&](auto narrow_c, auto l3_c) -> const void* {
+            using IdT = std::conditional_t<decltype(narrow_c)::value, uint16_t, int32_t>;
+            constexpr int CT = decltype(narrow_c)::value ? 5 : 4;
+            constexpr bool L3 = decltype(l3_c)::value;
+            return mode == 1 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 1> : mode == 2 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 2> : (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 0>;
+        };
+        const void* fn = narrow ? (l3 ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{}))
+                                : (l3 ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{}));
+        if (!fast_attr[mode * 4 + narrow * 2 + l3][owner->device]) {
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-            fast_attr[ordered * 4 + narrow * 2 + l3][owner->device] = true;
+            fast_attr[mode * 4 + narrow * 2 + l3][owner->device] = true;
         }
         static const int fast_ctas_env = [] { const char* e = getenv("B200TOK_FAST_CTAS"); return e ? atoi(e) : 0; }();
         const int fast_per_sm = fast_ctas_env > 0 ? fast_ctas_env : (int)std::max<size_t>(1, std::min<size_t>(narrow ? 5 : 4, (227 * 1024) / (fsm + 1024)));
         const int fast_blocks = (int)std::min<int64_t>((B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (int64_t)owner->sm_count * fast_per_sm);
         RowParams Pk = c.P;
         Pk.alloc_base = fast_alloc ? 1 : 0;
+        Pk.prefetch = tma_env;
         if (ordered) {
             uint32_t epoch = 0;
             if (int rc = ensure_ordered(w, B, (int64_t)owner->sm_count * 5 * WARPS_PER_BLOCK, narrow ? 2 : 4, st, epoch)) return rc;
@@ -378,6 +393,7 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         CU(cudaLaunchKernel(fn, dim3((unsigned)fast_blocks), dim3(BLOCK_THREADS), args, fsm, st));
         if (timing) { CU(cudaEventRecord(w.ev1, st)); w.timed = true; }
         RowParams P2 = ordered ? Pk : c.P;
+        if (mode != 1 && !peer_fast) P2.direct_base = 0;       // handed-back rows keep the slot range the fast kernel allocated for them (row_base)
         P2.row_list = c.row_cap;
         rows_kernel<OP_BPE><<<rows_blocks, BLOCK_THREADS, kRowsSmem, st>>>(P2);
         owner->launches += 2;

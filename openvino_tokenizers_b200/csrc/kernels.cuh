@@ -31,8 +31,9 @@ constexpr uint16_t F_MATCH = 0x0400, F_DROP = 0x0800, F_UNC = 0x8000, POS_MASK =
 enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2, OP_SPECIAL = 3 };
 
 // status words (device int32 array)
-enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_MINREDO = 8, ST_TICKET3 = 9, ST_ALLOC = 10,
-             ST_WORDS = 12 };
+enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_MINREDO = 8, ST_TICKET3 = 9,
+             ST_ALLOC = 32,        // the slot allocator: in its own 128-byte line — it and the ticket counter are both hit once per row
+             ST_WORDS = 64 };      // (a multiple of 32 words: consecutive status blocks keep the two counters in separate lines)
 enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
 
 struct GiantItem { int32_t row, begin, end, slot; };
@@ -158,6 +159,8 @@ struct RowParams {
     int32_t direct_base; int32_t direct_byte0; int32_t direct_elem0; int32_t direct_extra;
     // fast kernel: a row takes its slot range from a bump allocator (status[ST_ALLOC]) when it starts — no capacity pass, no scan
     int32_t alloc_base;
+    // slot path: 1 = software-pipelined input (the next window's bulk copy is issued while the current one is tokenised)
+    int32_t prefetch;
     // list mode: process rows row_list[0 .. status[ST_NREDO]) (rows the fast kernel handed back) instead of [0, n_rows)
     const int32_t* row_list;
     // sharded fast path: the emit step stores ids (and row extents) straight into every rank's buffers, rows stay at their
@@ -1124,7 +1127,7 @@ __global__ void giant_bpe_kernel(const GiantParams G) {
 
 // Copies a chunk's status words into mapped host memory (the pipelined host path polls them after an event).
 __global__ void publish_status_kernel(const int32_t* status, int32_t* host_mapped) {
-    if (threadIdx.x < ST_WORDS) host_mapped[threadIdx.x] = status[threadIdx.x];
+    if (threadIdx.x < 16) host_mapped[threadIdx.x] = status[threadIdx.x];
     __threadfence_system();
 }
 

@@ -22,15 +22,19 @@ namespace b200tok {
 
 constexpr int kMStride = NWORDS + 4;   // pass 1 writes four words per iteration
 
+constexpr int kRawBytes = 16 + LBK + WBYTES + 16;      // one staged window incl. up to 15 bytes of source misalignment on either side
 template <class IdT>
 struct __align__(16) FastSmem {
-    uint8_t raw_bytes[LBK + WBYTES];
+    alignas(16) uint8_t raw_pf[2][kRawBytes];        // staged window bytes; two buffers: the slot path prefetches the next window with a TMA bulk copy
+    alignas(8) unsigned long long mbar[2];           // one mbarrier per buffer: the bulk copy completes its transaction bytes on it
+    int32_t pf_row, pf_rb, pf_re, pf_eb, pf_ee;      // prefetch state: next row and its metadata (filled asynchronously by cp.async)
+    int32_t pf_pos, pf_off, pf_n;                    // window the in-flight buffer holds: start byte (-1: none), offset of position 0 in the buffer, bytes copied
     uint32_t segbits[NWORDS], actbits[NWORDS];
     uint32_t m[11][kMStride];                // class masks per word, index = word + 1 (word -1 = look-back): L N S SP A2 A3 CONT MB F NL PG
     IdT ids[WIN];                            // symbol per position; kDead = merged away
     alignas(16) uint32_t key[WIN + 4];       // merge keys; after the merges: staging of the window's compacted ids for wide peer stores
     int32_t pend_row[4], pend_cnt[4], pend_off[4];   // in-order emit: rows tokenised but not yet written out (row | redo << 31, count, ring offset)
-    __device__ __forceinline__ uint8_t* B() { return raw_bytes + LBK; }
+    __device__ __forceinline__ uint8_t* B0() { return raw_pf[0] + 16 + LBK; }      // position 0 of a synchronously staged window
     __device__ __forceinline__ uint16_t* act() { return reinterpret_cast<uint16_t*>(&m[0][0]); }   // merge queue; the masks are consumed by then
     static constexpr IdT kDead = (IdT)-1;
 };
@@ -42,11 +46,14 @@ template <class IdT> constexpr size_t fast_smem_bytes() { return kFastSmemFixed 
 
 // One window.  Returns `send` (how far the window advances; 0 => the first piece does not fit) or -1 when the window
 // needs the generic path.  On success S.ids[0 .. send) holds the window's tokens (-1 = merged away).
-template <class IdT, bool L3>
+struct NoHook {       // fast_window calls hook.after_pass1() / after_pass3(): places where a caller can slip in latency-bound work
+    __device__ __forceinline__ void after_pass1() {}
+    __device__ __forceinline__ void after_pass3() {}
+};
+template <class IdT, bool L3, class Hook>
 __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32,
                                            const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
-                                           bool ascii) {
-    const uint8_t* B = S.B();
+                                           bool ascii, const uint8_t* B, Hook& hook) {
     const uint32_t lt = (1u << lane) - 1u;
     const int lb = off < LBK ? off : LBK;           // look-back bytes staged before the window (off = window start - element start)
     ClassTables T = P.cls;
@@ -194,6 +201,7 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                 if ((uint32_t)(w0 + 32 * u) < (uint32_t)wlen) S.ids[w0 + 32 * u] = (IdT)(g[u] >> V7_ID_SHIFT);
         }
     }
+    hook.after_pass1();
     if (__any_sync(FULL, complex)) return -1;
     __syncwarp();
     // ---- pass 2: piece starts, lane = word ----
@@ -334,6 +342,7 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
         for (uint32_t a = a3; a; a &= a - 1u) act[off++] = (uint16_t)(base + __ffs(a) - 1);
     }
     __syncwarp();
+    hook.after_pass3();
     // ---- pass 4: merge queue, one segment per lane, one merge per iteration ----
     const MergeTable MT = P.bpe.merges;
     int head = 0, s = 0, merges = 0;
@@ -398,12 +407,12 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
 
 // Stage the bytes of one window (+ look-back / look-ahead) into shared memory; returns true if every byte is ASCII.
 template <class IdT>
-__device__ __forceinline__ bool stage_window(FastSmem<IdT>& S, const RowParams& P, int pos, int lb, int nload, int lane) {
+__device__ __forceinline__ bool stage_window(FastSmem<IdT>& S, const RowParams& P, int pos, int lb, int nload, int lane, uint8_t* Bw) {
     uint32_t hibits = 0;
     const uint8_t* src = P.chars + pos - lb;
     if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
         // 16-byte vector loads; the last quad may read up to 15 bytes past the element (padded chars allocation)
-        uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
+        uint4* dst = reinterpret_cast<uint4*>(Bw - lb);
         const int nq = (lb + nload + 15) >> 4;
         for (int q = lane; q < nq; q += 32) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
@@ -417,7 +426,7 @@ __device__ __forceinline__ bool stage_window(FastSmem<IdT>& S, const RowParams& 
     } else {
         for (int w = lane - lb; w < nload; w += 32) {
             const uint8_t bb = __ldg(P.chars + pos + w);
-            S.B()[w] = bb;
+            Bw[w] = bb;
             hibits |= bb;
         }
     }
@@ -546,8 +555,9 @@ __device__ __forceinline__ void ordered_rows(FastSmem<IdT>& S, const RowParams& 
                 const int wlen = end_rel < WIN ? end_rel : WIN;
                 const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
                 const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
-                const bool all_ascii = stage_window(S, P, pos, lb, nload, lane);
-                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                const bool all_ascii = stage_window(S, P, pos, lb, nload, lane, S.B0());
+                NoHook nh;
+                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii, S.B0(), nh);
                 if (send <= 0) { redo = true; break; }
                 emitted += compact_window(S, send, lane, ring + ring_used + emitted);
                 __syncwarp();
@@ -568,7 +578,251 @@ __device__ __forceinline__ void ordered_rows(FastSmem<IdT>& S, const RowParams& 
     }
 }
 
-template <class IdT, int CTAS, bool L3, bool ORDERED>
+
+// ---- TMA bulk copy / mbarrier / cp.async wrappers (PTX ISA: cp.async.bulk, mbarrier, cp.async) ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy by the TMA engine; completes `bytes` transaction bytes on the mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Metadata of the warp's NEXT row, fetched while the current window is being tokenised: fast_window calls the two hooks between its
+// passes; each issues the loads whose addresses the previous step delivered (ticket -> rb/re -> begins/ends), as cp.async copies into
+// shared memory, so no register is held across a pass and no pass waits for them.
+template <class IdT>
+struct RowPrefetch {
+    FastSmem<IdT>& S;
+    const RowParams& P;
+    int lane;
+    int t_next;          // lane 0: the next row's ticket (result of the atomicAdd issued when this row started)
+    int stage;           // 0: nothing issued, 1: rb/re in flight, 2: begins/ends in flight (or not applicable)
+    __device__ __forceinline__ void after_pass1() {
+        if (stage != 0) return;
+        const int nrow = __shfl_sync(FULL, t_next, 0);
+        if (lane == 0) S.pf_row = nrow;
+        if (nrow < P.n_rows) {
+            if (lane == 0) cp_async4(&S.pf_rb, P.rb + nrow);
+            if (lane == 1) cp_async4(&S.pf_re, P.re + nrow);
+            cp_async_commit();
+        }
+        __syncwarp();
+        stage = 1;
+    }
+    __device__ __forceinline__ void after_pass3() {
+        if (stage != 1) return;
+        cp_async_wait_all();
+        __syncwarp();
+        if (S.pf_row < P.n_rows && S.pf_re == S.pf_rb + 1) {      // one string per row (what the converter's add_ragged_dimension produces)
+            if (lane == 0) cp_async4(&S.pf_eb, P.begins + S.pf_rb);
+            if (lane == 1) cp_async4(&S.pf_ee, P.ends + S.pf_rb);
+            cp_async_commit();
+        }
+        stage = 2;
+    }
+};
+
+// Row loop of the slot path (one GPU): bump-allocated worst-case slot per row, ids stored 16 bits wide when they fit, and
+// software-pipelined input: while a window is tokenised, the warp's next window — the next 512 bytes of the same string, or the
+// first window of the row it will take next — is fetched into the second staging buffer by ONE cp.async.bulk (TMA) issued by
+// lane 0 and signalled through an mbarrier, so a window never starts with the ticket -> offsets -> bytes chain of dependent loads.
+template <class IdT, bool L3>
+__device__ __forceinline__ void slot_rows(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32_smem, const uint8_t* ascii_smem,
+                                          int lane, int32_t* __restrict__ redo_rows) {
+    const uint32_t ltm = (1u << lane) - 1u;
+    if (lane == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.pf_pos = -1;
+    }
+    __syncwarp();
+    int buf = 0;                 // staging buffer of the current window
+    uint32_t par = 0;            // phase parity of the two mbarriers (bit b = next phase to wait for on mbar[b])
+    bool inflight = false;       // a bulk copy into raw_pf[buf ^ 1] has been issued and not yet waited for
+    bool meta_ok = false;        // S.pf_rb / pf_re / pf_eb / pf_ee describe `row`
+    const bool can_prefetch = P.prefetch == 1 && P.skips == nullptr;
+    int row = 0;
+    if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+    row = __shfl_sync(FULL, row, 0);
+    while (row < P.n_rows) {
+        RowPrefetch<IdT> hook{S, P, lane, 0, can_prefetch ? 0 : 3};           // (stage 3: hooks off — the next ticket is taken when this row is done)
+        if (can_prefetch && lane == 0) hook.t_next = atomicAdd(&P.status[ST_TICKET], 1);      // looked at after pass 1 of the first window
+        int p0, p1, eb0 = 0, ee0 = 0;
+        if (meta_ok) { p0 = S.pf_rb; p1 = S.pf_re; eb0 = S.pf_eb; ee0 = S.pf_ee; }
+        else { p0 = P.rb[row]; p1 = P.re[row]; }
+        __syncwarp();            // (the hooks overwrite pf_* with the next row's metadata from here on)
+        // the row's worst-case slot range (one id per byte, src/bpe_tokenizer.cpp:135) from the bump allocator; answer picked up at emit time
+        int cap = 0;
+        if (meta_ok) cap = ee0 > eb0 ? ee0 - eb0 : 0;
+        else {
+            for (int p = p0 + lane; p < p1; p += 32) { const int l = P.ends[p] - P.begins[p]; cap += l > 0 ? l : 0; }
+            cap = (int)__reduce_add_sync(FULL, (unsigned)cap);
+        }
+        int alloc_b0 = 0;
+        if (lane == 0) alloc_b0 = atomicAdd(&P.status[ST_ALLOC], cap);
+        int64_t base = -1;
+        int emitted = 0;
+        bool redo = false;
+        for (int p = p0; p < p1 && !redo; ++p) {
+            const int eb = (meta_ok && p == p0) ? eb0 : P.begins[p], ee = (meta_ok && p == p0) ? ee0 : P.ends[p];
+            if (P.skips && P.skips[p]) { redo = true; break; }
+            int pos = eb;
+            while (pos < ee) {
+                const int end_rel = ee - pos;
+                const int wlen = end_rel < WIN ? end_rel : WIN;
+                const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
+                const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
+                // ---- the window's bytes: already on their way (TMA prefetch), or staged now ----
+                if (inflight) {
+                    mbar_wait(&S.mbar[buf ^ 1], (par >> (buf ^ 1)) & 1u);
+                    par ^= 1u << (buf ^ 1);
+                    inflight = false;
+                }
+                bool all_ascii;
+                uint8_t* Bw;
+                {
+                if (S.pf_pos != pos) {
+                    // not prefetched (first window of the warp, multi-string rows): the same TMA bulk copy, waited for now
+                    __syncwarp();
+                    const uint8_t* src = P.chars + pos - lb;
+                    const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+                    const uint32_t bytes = (uint32_t)((head + lb + nload + 15) & ~15);
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect_tx(&S.mbar[buf ^ 1], bytes);
+                        bulk_g2s(S.raw_pf[buf ^ 1], src - head, bytes, &S.mbar[buf ^ 1]);
+                        S.pf_off = head + lb;
+                        S.pf_n = (int32_t)bytes;
+                    }
+                    __syncwarp();
+                    mbar_wait(&S.mbar[buf ^ 1], (par >> (buf ^ 1)) & 1u);
+                    par ^= 1u << (buf ^ 1);
+                }
+                buf ^= 1;
+                Bw = S.raw_pf[buf] + S.pf_off;
+                {
+                    // ASCII test over every 16-byte quad the copy brought in — up to 15 neighbouring bytes on either side included: a
+                    // non-ASCII neighbour only sends an ASCII window down the general (equally exact) path
+                    uint32_t hibits = 0;
+                    const uint4* q4 = reinterpret_cast<const uint4*>(S.raw_pf[buf]);
+                    const int nq = S.pf_n >> 4;
+                    for (int q = lane; q < nq; q += 32) { const uint4 v = q4[q]; hibits |= v.x | v.y | v.z | v.w; }
+                    all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
+                }
+                __syncwarp();
+                }
+                if (lane == 0) S.pf_pos = -1;
+                const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii, Bw, hook);
+                hook.after_pass1();            // (windows that left early: the metadata steps still have to happen, in order)
+                hook.after_pass3();
+                if (send <= 0) redo = true;
+                // ---- issue the prefetch of the warp's next window ----
+                if (can_prefetch) {
+                    int tpos = -1, teb = 0, tee = 0;
+                    if (!redo && pos + send < ee) { tpos = pos + send; teb = eb; tee = ee; }
+                    else if (p == p1 - 1) {                                   // the row ends here: first window of the next row
+                        cp_async_wait_all();
+                        __syncwarp();
+                        if (S.pf_row < P.n_rows && S.pf_re == S.pf_rb + 1 && S.pf_ee > S.pf_eb) { tpos = teb = S.pf_eb; tee = S.pf_ee; }
+                    }
+                    if (tpos >= 0) {
+                        const int lbt = (tpos - teb) < LBK ? (tpos - teb) : LBK;
+                        const int relt = tee - tpos;
+                        const int wl = relt < WIN ? relt : WIN;
+                        const int nl = relt < wl + LA ? relt : wl + LA;
+                        const uint8_t* src = P.chars + tpos - lbt;
+                        const int head = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+                        const uint32_t bytes = (uint32_t)((head + lbt + nl + 15) & ~15);
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            mbar_expect_tx(&S.mbar[buf ^ 1], bytes);
+                            bulk_g2s(S.raw_pf[buf ^ 1], src - head, bytes, &S.mbar[buf ^ 1]);
+                            S.pf_pos = tpos;
+                            S.pf_off = head + lbt;
+                            S.pf_n = (int32_t)bytes;
+                        }
+                        inflight = true;
+                    }
+                    __syncwarp();
+                }
+                if (redo) break;
+                // ---- emit: ballot compaction of the surviving ids into the row's slot ----
+                if (base < 0) {                       // bump-allocated slot: pick the allocator's answer up now
+                    base = __shfl_sync(FULL, alloc_b0, 0);
+                    if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;     // the compaction pass reads it
+                }
+                if (base + emitted + send > P.tmp_cap) {
+                    if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
+                } else {
+                    int n_out = 0;
+                    for (int w = lane; w - lane < send; w += 128) {
+                        int32_t tok[4];
+                        uint32_t m[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) tok[u] = ((w + 32 * u) < send && S.ids[w + 32 * u] != S.kDead) ? (int32_t)S.ids[w + 32 * u] : -1;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(FULL, tok[u] >= 0);
+                        // 16-bit ids stay 16 bits wide in the row slot (the first half of its i32 range): half the bytes written here and
+                        // read by the compaction pass, which widens them
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (tok[u] >= 0) {
+                                if constexpr (sizeof(IdT) == 2) reinterpret_cast<uint16_t*>(P.tmp_a + base)[emitted + n_out + __popc(m[u] & ltm)] = (uint16_t)tok[u];
+                                else P.tmp_a[base + emitted + n_out + __popc(m[u] & ltm)] = tok[u];
+                            }
+                            n_out += __popc(m[u]);
+                        }
+                    }
+                    emitted += n_out;
+                }
+                __syncwarp();
+                pos += send;
+            }
+        }
+        hook.after_pass1();       // rows without a window (empty): the next row's ticket and metadata are still due
+        hook.after_pass3();
+        cp_async_wait_all();
+        __syncwarp();
+        if (base < 0) {                               // nothing was emitted (handed back, or empty): the row still owns its slot range
+            base = __shfl_sync(FULL, alloc_b0, 0);
+            if (lane == 0) const_cast<int32_t*>(P.row_base)[row] = (int32_t)base;
+        }
+        if (lane == 0) {
+            if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
+            else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = sizeof(IdT) == 2 ? 4 : 0; }      // bit 2: 16-bit slot
+        }
+        if (can_prefetch) {
+            row = S.pf_row;
+            meta_ok = row < P.n_rows && S.pf_re == S.pf_rb + 1;
+        } else {
+            if (lane == 0) row = atomicAdd(&P.status[ST_TICKET], 1);
+            row = __shfl_sync(FULL, row, 0);
+        }
+    }
+    if (inflight) mbar_wait(&S.mbar[buf ^ 1], (par >> (buf ^ 1)) & 1u);      // no copy may be in flight when the CTA retires
+}
+
+// MODE 0: row slots + TMA-prefetched input (one GPU); 1: in-order single-pass emit (opt-in); 2: sharded, ids stored into every rank's buffers
+template <class IdT, int CTAS, bool L3, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* ascii_smem = smem_raw;                                            // [128]
@@ -581,8 +835,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
     __syncthreads();
     const uint32_t ltm = (1u << lane) - 1u;
 
-    if constexpr (ORDERED) {
+    if constexpr (MODE == 1) {
         ordered_rows<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, redo_rows);
+        return;
+    } else if constexpr (MODE == 0) {
+        slot_rows<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, redo_rows);
         return;
     } else {
         for (;;) {
@@ -614,31 +871,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                     const int wlen = end_rel < WIN ? end_rel : WIN;
                     const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
                     const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element
-                    uint32_t hibits = 0;
-                    const uint8_t* src = P.chars + pos - lb;
-                    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)lb) & 15) == 0) {
-                        // 16-byte vector loads; the last quad may read up to 15 bytes past the element (padded chars allocation)
-                        uint4* dst = reinterpret_cast<uint4*>(S.B() - lb);
-                        const int nq = (lb + nload + 15) >> 4;
-                        for (int q = lane; q < nq; q += 32) {
-                            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
-                            dst[q] = v;
-                            if ((q << 4) + 16 <= lb + nload) hibits |= v.x | v.y | v.z | v.w;
-                            else {
-                                const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
-                                for (int t = 0; t < 16; ++t) if ((q << 4) + t < lb + nload) hibits |= (ww[t >> 2] >> ((t & 3) * 8)) & 0xFFu;
-                            }
-                        }
-                    } else {
-                        for (int w = lane - lb; w < nload; w += 32) {
-                            const uint8_t bb = __ldg(P.chars + pos + w);
-                            S.B()[w] = bb;
-                            hibits |= bb;
-                        }
-                    }
-                    const bool all_ascii = !__any_sync(FULL, hibits & 0x80808080u);
-                    __syncwarp();
-                    const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii);
+                    const bool all_ascii = stage_window(S, P, pos, lb, nload, lane, S.B0());
+                    NoHook nh;
+                    const int send = fast_window<IdT, L3>(S, P, lut32_smem, ascii_smem, lane, wlen, end_rel, nload, pos - eb, all_ascii, S.B0(), nh);
                     if (send <= 0) { redo = true; break; }
                     if (base < 0) {                       // bump-allocated slot: pick the allocator's answer up now
                         base = __shfl_sync(FULL, alloc_b0, 0);

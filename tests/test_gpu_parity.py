@@ -756,3 +756,17 @@ def test_sharded_exchange_two_ranks():
                             "--master-port", "29577", str(root / "tools" / "peer_gather_check.py"), "8192"], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         assert "on every rank: True" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("env", [{"B200TOK_TMA": "1"}, {"B200TOK_TMA": "2"}, {"B200TOK_SLOT_ALLOC": "1"}, {"B200TOK_ORDERED_EMIT": "1"}, {"B200TOK_GRAPHS": "0"}],
+                         ids=["tma-prefetch", "tma-sync", "slot-alloc", "ordered-emit", "no-graphs"])
+def test_fast_kernel_variants(env):
+    """The opt-in row loops of the fast kernel (TMA bulk-copy staging with / without prefetch, bump-allocated slots, in-order
+    single-pass emit) and the path without CUDA-graph replay give the same tensors as the default: tools/variant_check.py in a
+    process of its own (the library reads the switches once)."""
+    import os
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "variant_check.py")], capture_output=True, text=True, env=dict(os.environ, **env), timeout=900)
+    assert r.returncode == 0 and "variant ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
