@@ -412,6 +412,7 @@ def main():
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true", help="profiling runs: only the device-resident step (no host-buffer calls, no JSON contract)")
+    ap.add_argument("--no-unfused", action="store_true", help="skip the separate-ops (unfused) host-to-host measurement")
     ap.add_argument("--no-verify", action="store_true", help="skip the full-batch CPU-oracle comparison after the timed regions")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -562,6 +563,49 @@ def main():
     h2d = n_bytes + 8 * db.n_rows + 8 * db.n_elems
     d2h = 4 * n_ids + 8 * db.n_rows
 
+    # ---- the same host-to-host job through the SEPARATE ops (what an IR costs when the load-time fusion of the ov::Op shim is off, or
+    # for split patterns it cannot fuse): RegexSplit host -> host, then BPETokenizer / WordpieceTokenizer host -> host; the piece
+    # offsets (8 bytes per ~1.8-byte piece) cross PCIe twice
+    unfused = None
+    if world == 1 and not args.no_unfused:
+        import ctypes as C
+        from openvino_tokenizers_b200 import _capi as K
+        Lb = K.lib()
+        cap_p = db.n_chars + db.n_elems
+        pin = lambda n, dt=torch.int32: torch.empty(max(n, 1), dtype=dt).pin_memory()
+        s_rb, s_re, s_b, s_e = pin(db.n_rows), pin(db.n_rows), pin(cap_p), pin(cap_p)
+        s2_rb, s2_re, s2_b, s2_e = pin(db.n_rows), pin(db.n_rows), pin(cap_p), pin(cap_p)
+
+        def split_host(handle, rb_t, re_t, b_t, e_t, n_el, orb, ore, ob, oe):
+            rin = K.RaggedStrings(rb_t.data_ptr(), re_t.data_ptr(), db.n_rows, b_t.data_ptr(), e_t.data_ptr(), n_el, hb[4].data_ptr(), hb[4].numel(), None, K.MEM_HOST)
+            out = K.RaggedStringsOut(orb.data_ptr(), ore.data_ptr(), ob.data_ptr(), oe.data_ptr(), None, cap_p, 0, 0, K.MEM_HOST)
+            K.check(Lb.b200tok_regexsplit_run(handle, C.byref(rin), C.byref(out), None))
+            return int(out.n_elems)
+
+        def unfused_step():
+            n1 = split_host(pipe.split1.handle, hb[0], hb[1], hb[2], hb[3], hb[2].numel(), s_rb, s_re, s_b, s_e)
+            rb_t, re_t, b_t, e_t = s_rb, s_re, s_b, s_e
+            if pipe.split2 is not None:
+                n1 = split_host(pipe.split2.handle, s_rb, s_re, s_b, s_e, n1, s2_rb, s2_re, s2_b, s2_e)
+                rb_t, re_t, b_t, e_t = s2_rb, s2_re, s2_b, s2_e
+            rin = K.RaggedStrings(rb_t.data_ptr(), re_t.data_ptr(), db.n_rows, b_t.data_ptr(), e_t.data_ptr(), n1, hb[4].data_ptr(), hb[4].numel(), None, K.MEM_HOST)
+            out = K.RaggedIds(ho["begins"].data_ptr(), ho["ends"].data_ptr(), ho["ids"].data_ptr(), ho["cap"], 0, None, K.MEM_HOST)
+            if pipe.kind == "bpe":
+                K.check(Lb.b200tok_bpe_run(pipe.tok.handle, C.byref(rin), C.byref(out), None))
+            else:
+                K.check(Lb.b200tok_wordpiece_run(pipe.tok.handle, C.byref(rin), C.c_int32(pipe.unk), C.byref(out), None))
+            return n1, int(out.n_ids)
+        unfused_step()
+        k_un = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_un):
+            n_pieces, n_un = unfused_step()
+        un_s = (time.perf_counter() - t0) / k_un
+        assert n_un == n_host, "separate ops and fused call disagree on the id count"
+        unfused = {"value": n_bytes / 1e6 / un_s, "unit": "MB/s", "ms_per_step": un_s * 1e3, "pieces": n_pieces,
+                   "path": "b200tok_regexsplit_run -> b200tok_bpe_run / b200tok_wordpiece_run, each host -> host (pinned buffers)"}
+        n_host = pipe.run_host(hb, ho)       # (restore the fused result in the host buffers for the check below)
+
     # ---- verification of the timed configuration (outside every timed region) ----
     # N = 1: the whole batch, device-resident result and host-buffer result, against the CPU oracle.
     # N > 1: every rank re-tokenises the shard of rank (rank + 1) % N on its own GPU and compares it with that rank's slot of the
@@ -638,6 +682,7 @@ def main():
                        "multi_gpu": exchange},
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "path": "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"},
+            "e2e_unfused": unfused,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "verified": verified,
         }))
     if world > 1:

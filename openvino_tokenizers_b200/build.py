@@ -8,7 +8,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libb200tok.so"
-SOURCES = ["api.cu", "tables.cpp"]
+SOURCES = ["api.cu", "tables.cpp", "regex_compile.cpp"]
 
 
 def deps() -> list[Path]:

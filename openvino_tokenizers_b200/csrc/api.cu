@@ -165,7 +165,16 @@ struct b200tok_object {
 
 namespace {
 
-struct SplitObj : b200tok_object { HostSplit h; };
+struct SplitObj : b200tok_object {
+    HostSplit h;
+    // PAT_VM: the compiled program and the general-category tables on the device
+    DBuf<VmInst> vm_code; DBuf<VmSet> vm_sets; DBuf<uint32_t> vm_ranges; DBuf<uint16_t> gc1; DBuf<uint8_t> gc2;
+    SplitSpec dev_spec() const {
+        SplitSpec sp = h.spec;
+        if (sp.pat == PAT_VM) sp.vm = VmProgram{vm_code.p, vm_sets.p, vm_ranges.p, gc1.p, gc2.p, (int32_t)h.vm.code.size()};
+        return sp;
+    }
+};
 struct SpecialObj : b200tok_object {
     HostSpecial h;
     DevTrie trie[kSpecialGroups];
@@ -686,7 +695,7 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     P.spec = SplitSpec{}; P.spec.pat = PAT_NONE; P.mode = SPLIT_ISOLATED; P.invert = 0; P.max_splits = -1; P.repeat = 0;
     if (call.split) {
         const HostSplit& hs = call.split->h;
-        P.spec = hs.spec; P.mode = hs.mode; P.invert = hs.invert; P.max_splits = hs.max_splits; P.repeat = hs.repeat;
+        P.spec = call.split->dev_spec(); P.mode = hs.mode; P.invert = hs.invert; P.max_splits = hs.max_splits; P.repeat = hs.repeat;
         if (call.split2) {
             const HostSplit& h2 = call.split2->h;
             const bool bert = hs.spec.pat == PAT_WS && hs.mode == SPLIT_REMOVED && !hs.invert && hs.max_splits == -1 &&
@@ -920,6 +929,10 @@ B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* d, b200
     if ((rc = init_object(o.get(), K_SPLIT, d->device))) return rc;
     DeviceGuard g(d->device);
     CU(o->cls.upload());
+    if (o->h.spec.pat == PAT_VM) {
+        CU(o->vm_code.upload(o->h.vm.code)); CU(o->vm_sets.upload(o->h.vm.sets)); CU(o->vm_ranges.upload(o->h.vm.ranges));
+        CU(o->gc1.upload(host_gc_tables().stage1)); CU(o->gc2.upload(host_gc_tables().stage2));
+    }
     CU(cudaDeviceSynchronize());
     *out = o.release();
     return B200TOK_OK;
@@ -1654,7 +1667,10 @@ B200TOK_API int b200tok_bytes_to_chars_run(int device, const b200tok_ragged_stri
     gpt2_build_byte_codepoints(cp);
     CU(bt.alloc(512, st));
     CU(cudaMemcpyAsync(bt.p, cp, 512, cudaMemcpyHostToDevice, st));
-    CU(blen.alloc((size_t)E * 4, st)); CU(btot.alloc(8, st));
+    CU(blen.alloc((size_t)E * 4, st)); CU(btot.alloc(16, st));
+    CU(cudaMemsetAsync(btot.p, 0, 16, st));
+    if (!host && in->n_rows > 0)      // device buffers: the partition property is checked on the device (flag read back with the total)
+        rows_partition_check_kernel<<<(unsigned)((in->n_rows + 255) / 256), 256, 0, st>>>(in->ragged_begins, in->ragged_ends, in->n_rows, E, btot.as<int32_t>() + 2);
     int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
     if (host) { CU(bob.alloc((size_t)E * 4, st)); CU(boe.alloc((size_t)E * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
     // the scan "one byte in, one or two bytes out" on the warp-per-string kernel of the normalisers (kernels_norm.cuh)
@@ -1665,9 +1681,11 @@ B200TOK_API int b200tok_bytes_to_chars_run(int device, const b200tok_ragged_stri
     if ((rc = scan_i32(bscan, blen.as<int32_t>(), d_ob, E, st))) return rc;
     launch_norm<true>(R, device, N, d_b, d_e, d_c, d_s, E, blen.as<int32_t>(), d_ob, 0, nullptr, d_oe, d_oc, chars_capacity, btot.as<int64_t>(), st);
     CU(cudaGetLastError());
-    int64_t total = 0;
-    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+    int64_t tot2[2] = {0, 0};
+    CU(cudaMemcpyAsync(tot2, btot.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    const int64_t total = tot2[0];
+    if (tot2[1]) return fail(B200TOK_E_UNSUPPORTED, "BytesToChars: rows must cover the elements contiguously and in order");
     *n_chars_out = total;
     if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
     if (host) {
@@ -1705,8 +1723,10 @@ B200TOK_API int b200tok_chars_to_bytes_run(int device, const b200tok_ragged_stri
         if (cp[b] >= 0x80) pair_map[((0xC0 | (cp[b] >> 6)) - 194) * 64 + ((0x80 | (cp[b] & 0x3F)) - 128)] = (uint8_t)b;
     CU(bt.alloc(256, st));
     CU(cudaMemcpyAsync(bt.p, pair_map, 256, cudaMemcpyHostToDevice, st));
-    CU(blen.alloc((size_t)std::max<int64_t>(E, 1) * 4, st)); CU(boff.alloc((size_t)std::max<int64_t>(E, 1) * 4, st)); CU(btot.alloc(8, st));
-    CU(cudaMemsetAsync(btot.p, 0, 8, st));
+    CU(blen.alloc((size_t)std::max<int64_t>(E, 1) * 4, st)); CU(boff.alloc((size_t)std::max<int64_t>(E, 1) * 4, st)); CU(btot.alloc(16, st));
+    CU(cudaMemsetAsync(btot.p, 0, 16, st));
+    if (!host)      // device buffers: the partition property is checked on the device (flag read back with the total)
+        rows_partition_check_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_rb, d_re, B, E, btot.as<int32_t>() + 2);
     int32_t *d_ob = out_begins, *d_oe = out_ends; uint8_t* d_oc = out_chars;
     if (host) { CU(bob.alloc((size_t)B * 4, st)); CU(boe.alloc((size_t)B * 4, st)); CU(boc.alloc((size_t)chars_capacity + 16, st)); d_ob = bob.as<int32_t>(); d_oe = boe.as<int32_t>(); d_oc = boc.as<uint8_t>(); }
     AsyncBuf bee;
@@ -1722,9 +1742,11 @@ B200TOK_API int b200tok_chars_to_bytes_run(int device, const b200tok_ragged_stri
     }
     c2b_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d_rb, d_re, B, boff.as<int32_t>(), blen.as<int32_t>(), E, d_ob, d_oe);
     CU(cudaGetLastError());
-    int64_t total = 0;
-    CU(cudaMemcpyAsync(&total, btot.p, 8, cudaMemcpyDeviceToHost, st));
+    int64_t tot2[2] = {0, 0};
+    CU(cudaMemcpyAsync(tot2, btot.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    const int64_t total = tot2[0];
+    if (tot2[1]) return fail(B200TOK_E_UNSUPPORTED, "CharsToBytes: rows must cover the elements contiguously and in order");
     *n_chars_out = total;
     if (total > chars_capacity) return fail(B200TOK_E_CAPACITY, "chars capacity %lld is smaller than the result (%lld bytes)", (long long)chars_capacity, (long long)total);
     if (host) {

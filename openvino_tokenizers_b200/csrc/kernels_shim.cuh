@@ -50,4 +50,14 @@ __global__ void fuze_ragged_kernel(const int32_t* rb, const int32_t* re, int64_t
 
 // ---- UTF8Validate runs on the same scan (rule NORM_UTF8): the reference's byte automaton restated per start byte ----
 
+// Device-side form of the host check "rows cover the elements contiguously and in order" (BytesToChars / CharsToBytes take their
+// row extents from an element-order scan, which is the reference's row-order walk only under that condition): flag != 0 = violated.
+__global__ void rows_partition_check_kernel(const int32_t* rb, const int32_t* re, int64_t n_rows, int64_t n_elems, int32_t* flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int32_t b = rb[r], e = re[r];
+    const int32_t prev_end = r == 0 ? 0 : re[r - 1];
+    if (b != prev_end || e < b || (r == n_rows - 1 && e != n_elems)) atomicOr(flag, 1);
+}
+
 }  // namespace b200tok

@@ -2,29 +2,51 @@
 // input/output signatures as the reference extension (src/ov_extension.cpp:72-109) so a converted tokenizer IR loads
 // unchanged, and forwards each evaluate() to the C ABI of libb200tok.so (include/b200tok.h).
 //
-// Built only when OpenVINO is available:  g++ -shared -fPIC -DIMPLEMENT_OPENVINO_EXTENSION_API ov_extension_b200.cpp
-//   -I<openvino>/include -I../../../include -L.. -lb200tok -lopenvino  (see INTEGRATION.md).
-// OpenVINO headers/libraries do not exist in the build container, so this file is NOT compiled or
-// tested there; every behaviour it relies on is exercised through the C ABI by tests/test_gpu_parity.py, and the Python
-// mirror openvino_tokenizers_b200/ops.py follows the same marshalling line by line.
+// Build:  g++ -shared -fPIC -DIMPLEMENT_OPENVINO_EXTENSION_API ov_extension_b200.cpp -I<openvino>/include -I../../../include
+//   [-I<reference>/src for precompiled_charsmap.hpp] -L.. -lb200tok -lopenvino   (INTEGRATION.md).
+// OpenVINO is not installed in the build container; there the file is compiled against the stand-in API of
+// tests/ov_stub by tests/shimlib.py (CPU tier: it must compile and export the entry points) and its evaluate() bodies and the
+// load-time fusion below are driven by tests/test_ov_shim.py on the GPU box, against the reference's own op classes.
+//
+// Load-time fusion: a converted IR has RegexSplit -> BPETokenizer (and RegexSplit -> RegexSplit -> WordpieceTokenizer) as separate
+// layers (python/openvino_tokenizers/tokenizer_pipeline.py:1600-1646); evaluated one by one, the piece offsets between them
+// (8 bytes per ~1.8-byte piece) would cross PCIe twice.  The IR frontend creates every layer through its OpExtension::create
+// (inputs = the producers already built, visitor = the layer's attributes) and wires the consumers to whatever outputs it
+// returns — so the extensions registered for "BPETokenizer" / "WordpieceTokenizer" look at their producers and, when those are
+// this library's RegexSplit layers in a supported configuration whose only consumer is the tokenizer, return the outputs of ONE
+// fused op (B200SplitBPE / B200SplitWordpiece) fed by the splitters' own inputs.  The by-passed RegexSplit layers have no
+// consumer left and drop out of the model; the IR file itself is unchanged.
 #if __has_include(<openvino/op/op.hpp>)
 #include <openvino/core/extension.hpp>
 #include <openvino/core/op_extension.hpp>
 #include <openvino/op/constant.hpp>
 #include <openvino/op/op.hpp>
 
+#include <algorithm>
+#include <cstdlib>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "b200tok.h"
-// CharsMapNormalization's attribute form needs the charsmaps the reference generates at build time; the shim is built inside
-// the reference tree, where this header exists (src/precompiled_charsmap.hpp: get_precompiled_charsmap(form, case_fold)).
+// CharsMapNormalization's attribute form needs the charsmaps the reference generates at build time (src/precompiled_charsmap.hpp:
+// get_precompiled_charsmap(form, case_fold)); present when the shim is built inside the reference tree.
+#if __has_include("precompiled_charsmap.hpp")
 #include "precompiled_charsmap.hpp"
+#else
+inline std::string get_precompiled_charsmap(const std::string&, bool) { return std::string(); }   // attribute form unavailable: pass the charsmap as an input
+#endif
 
 namespace b200 {
 
 inline void check(int rc) { OPENVINO_ASSERT(rc == B200TOK_OK, "b200tok: ", b200tok_last_error()); }
+
+// CUDA device the ops of this process run on: B200TOK_DEVICE (default 0) — one process per GPU, like the rest of the stack.
+inline int device() {
+    static const int d = [] { const char* e = std::getenv("B200TOK_DEVICE"); return e ? std::atoi(e) : 0; }();
+    return d;
+}
 
 inline b200tok_strings strings_of(const ov::TensorVector& in, size_t i) {
     return b200tok_strings{in[i].data<const int32_t>(), in[i + 1].data<const int32_t>(), in[i + 2].data<const uint8_t>(),
@@ -71,20 +93,18 @@ public:
         c->m_state = m_state;
         return c;
     }
-    bool visit_attributes(ov::AttributeVisitor& v) override {
-        v.on_attribute("behaviour", m_behaviour);
-        v.on_attribute("invert", m_invert);
-        v.on_attribute("max_splits", m_max_splits);
+    bool visit_attributes(ov::AttributeVisitor& v) override { return visit_prefixed(v, ""); }
+    bool visit_prefixed(ov::AttributeVisitor& v, const std::string& prefix) {      // (the fused layers store two splitters' attributes)
+        v.on_attribute(prefix + "behaviour", m_behaviour);
+        v.on_attribute(prefix + "invert", m_invert);
+        v.on_attribute(prefix + "max_splits", m_max_splits);
         return true;
     }
     bool has_evaluate() const override { return true; }
     bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
         const bool has_skips = in.size() == 7;
-        std::call_once(m_state->once, [&] {
-            const auto& p = in[5 + has_skips];
-            b200tok_regexsplit_desc d{p.data<const char>(), (int64_t)p.get_size(), m_behaviour.c_str(), m_invert, m_max_splits, 0};
-            check(b200tok_regexsplit_create(&d, &m_state->h));
-        });
+        const auto& pt = in[5 + has_skips];
+        ensure(pt.data<const char>(), pt.get_size());
         const size_t cap = in[4].get_size() + in[2].get_size();          // src/regex_split.cpp:182
         out[0].set_shape(in[0].get_shape());
         out[1].set_shape(in[1].get_shape());
@@ -102,6 +122,16 @@ public:
         if (has_skips) out[5].set_shape({(size_t)r.n_elems});
         return true;
     }
+    // lazily compiled splitter (src/regex_split.cpp:147-151), shared with clones and with the fused layers
+    void ensure(const char* pattern, size_t len) const {
+        std::call_once(m_state->once, [&] {
+            b200tok_regexsplit_desc d{pattern, (int64_t)len, m_behaviour.c_str(), m_invert, m_max_splits, device()};
+            check(b200tok_regexsplit_create(&d, &m_state->h));
+        });
+    }
+    b200tok_handle handle() const { return m_state->h; }
+    const std::string& behaviour() const { return m_behaviour; }
+    int max_splits() const { return m_max_splits; }
 private:
     std::string m_behaviour = "remove";
     bool m_invert = false;
@@ -143,8 +173,16 @@ public:
     }
     bool has_evaluate() const override { return true; }
     bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        ensure(in);
+        auto rin = ragged_of(in);
+        ragged_ids_out(out, in, capacity(in),
+                       [&](b200tok_ragged_ids* r) { return b200tok_bpe_run(m_state->h, &rin, r, nullptr); });
+        return true;
+    }
+    // device tables built once from the Constant inputs [5..] of the 11 / 14 / 15 / 18-input forms (src/bpe_tokenizer.cpp:50-120)
+    void ensure(const ov::TensorVector& in) const {
         const auto n = in.size();
-        std::call_once(m_state->once, [&] {                              // src/bpe_tokenizer.cpp:50-120
+        std::call_once(m_state->once, [&] {
             b200tok_bpe_desc d{};
             d.vocab = strings_of(in, 5);
             d.merges_left = strings_of(in, 8);
@@ -153,17 +191,17 @@ public:
             d.unk_token = m_unk_token.data(); d.unk_token_len = (int64_t)m_unk_token.size();
             d.suffix_indicator = m_suffix_indicator.data(); d.suffix_indicator_len = (int64_t)m_suffix_indicator.size();
             d.end_suffix = m_end_suffix.data(); d.end_suffix_len = (int64_t)m_end_suffix.size();
-            d.fuse_unk = m_fuse_unk; d.byte_fallback = m_byte_fallback; d.cache_capacity = (int64_t)m_cache_capacity; d.device = 0;
+            d.fuse_unk = m_fuse_unk; d.byte_fallback = m_byte_fallback; d.cache_capacity = (int64_t)m_cache_capacity; d.device = device();
             check(b200tok_bpe_create(&d, &m_state->h));
         });
-        auto rin = ragged_of(in);
-        ragged_ids_out(out, in, (int64_t)(in[4].get_size() + in[2].get_size() * m_end_suffix.size()),
-                       [&](b200tok_ragged_ids* r) { return b200tok_bpe_run(m_state->h, &rin, r, nullptr); });
-        return true;
     }
+    int64_t capacity(const ov::TensorVector& in) const { return (int64_t)(in[4].get_size() + in[2].get_size() * m_end_suffix.size()); }
+    b200tok_handle handle() const { return m_state->h; }
 private:
-    std::string m_unk_token, m_suffix_indicator, m_end_suffix;
-    bool m_fuse_unk = false, m_byte_fallback = false;
+    std::string m_unk_token;
+    bool m_fuse_unk = false;
+    std::string m_suffix_indicator, m_end_suffix;
+    bool m_byte_fallback = false;
     size_t m_cache_capacity = 20000;
     mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
 };
@@ -192,16 +230,20 @@ public:
     }
     bool has_evaluate() const override { return true; }
     bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
-        std::call_once(m_state->once, [&] {
-            b200tok_wordpiece_desc d{strings_of(in, 5), m_suffix_indicator.data(), (int64_t)m_suffix_indicator.size(), m_max_bytes_per_word, 0};
-            check(b200tok_wordpiece_create(&d, &m_state->h));
-        });
+        ensure(in);
         const int32_t unk = *in[8].data<const int32_t>();
         auto rin = ragged_of(in);
         ragged_ids_out(out, in, (int64_t)(in[4].get_size() + in[2].get_size()),
                        [&](b200tok_ragged_ids* r) { return b200tok_wordpiece_run(m_state->h, &rin, unk, r, nullptr); });
         return true;
     }
+    void ensure(const ov::TensorVector& in) const {
+        std::call_once(m_state->once, [&] {
+            b200tok_wordpiece_desc d{strings_of(in, 5), m_suffix_indicator.data(), (int64_t)m_suffix_indicator.size(), m_max_bytes_per_word, device()};
+            check(b200tok_wordpiece_create(&d, &m_state->h));
+        });
+    }
+    b200tok_handle handle() const { return m_state->h; }
 private:
     std::string m_suffix_indicator = "##";
     int m_max_bytes_per_word = 100;
@@ -225,7 +267,7 @@ public:
         const bool i64 = in[6].get_element_type() == ov::element::i64;
         OPENVINO_ASSERT(i64 || in[6].get_element_type() == ov::element::i32, "VocabEncoder: unsupported element type: ", in[6].get_element_type());
         std::call_once(m_state->once, [&] {
-            b200tok_vocabenc_desc d{strings_of(in, 3), in[6].data(), i64, 0};
+            b200tok_vocabenc_desc d{strings_of(in, 3), in[6].data(), i64, device()};
             check(b200tok_vocabenc_create(&d, &m_state->h));
         });
         out[0].set_shape({in[0].get_size()});
@@ -261,7 +303,7 @@ public:
     bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
         OPENVINO_ASSERT(in.size() == 4 || in.size() == 5, "Too few inputs passed to VocabDecoder, it means it is not converted properly or it is not used in the supported pattern");
         std::call_once(m_state->once, [&] {
-            b200tok_vocabdec_desc d{strings_of(in, 1), 0};
+            b200tok_vocabdec_desc d{strings_of(in, 1), device()};
             check(b200tok_vocabdec_create(&d, &m_state->h));
         });
         const int64_t B = (int64_t)in[0].get_shape()[0], S = (int64_t)in[0].get_shape()[1], W = S > 0 ? S : 1;
@@ -297,7 +339,7 @@ public:
     bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
         out[0].set_shape(in[0].get_shape()); out[1].set_shape(in[1].get_shape()); out[2].set_shape({in[2].get_size()});
         int64_t n_chars = 0;
-        check(b200tok_bytefallback_run(0, in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(),
+        check(b200tok_bytefallback_run(device(), in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(),
                                        in[2].data<const uint8_t>(), (int64_t)in[2].get_size(), out[0].data<int32_t>(), out[1].data<int32_t>(),
                                        out[2].data<uint8_t>(), &n_chars, B200TOK_MEM_HOST, nullptr));
         out[2].set_shape({(size_t)n_chars});
@@ -329,7 +371,7 @@ public:
         const bool has_skips = in.size() == 7;
         std::call_once(m_state->once, [&] {                                // src/special_tokens_split.cpp:65-69
             const auto& p = in[5 + has_skips];
-            check(b200tok_specialsplit_create(p.data<const char>(), (int64_t)p.get_size(), 0, &m_state->h));
+            check(b200tok_specialsplit_create(p.data<const char>(), (int64_t)p.get_size(), device(), &m_state->h));
         });
         const size_t cap = in[4].get_size() + in[2].get_size();
         out[0].set_shape(in[0].get_shape());
@@ -367,7 +409,7 @@ public:
         for (int i = 0; i < 3 * m_num_inputs; ++i) out[i] = in[i];                                   // :52-56
         int32_t* b1 = m_num_inputs == 2 ? out[3].data<int32_t>() : nullptr;
         int32_t* e1 = m_num_inputs == 2 ? out[4].data<int32_t>() : nullptr;
-        check(b200tok_truncate_run(0, m_num_inputs, out[0].data<int32_t>(), out[1].data<int32_t>(), b1, e1, (int64_t)out[0].get_size(), max_length,
+        check(b200tok_truncate_run(device(), m_num_inputs, out[0].data<int32_t>(), out[1].data<int32_t>(), b1, e1, (int64_t)out[0].get_size(), max_length,
                                    side.c_str(), mode.c_str(), B200TOK_MEM_HOST, nullptr));
         return true;
     }
@@ -402,7 +444,7 @@ public:
         for (size_t j = 0; j < num; ++j) flat += (segs[j].n == 1 ? rows : 1) * (size_t)segs[j].n_elems;      // :65-71
         for (int t = 0; t < 2; ++t) { out[3 * t].set_shape(ps); out[3 * t + 1].set_shape(ps); out[3 * t + 2].set_shape({flat}); }
         int64_t n_out = 0;
-        check(b200tok_combine_segments_run(0, segs.data(), (int)num, in.back().data<const int32_t>(), out[0].data<int32_t>(), out[1].data<int32_t>(),
+        check(b200tok_combine_segments_run(device(), segs.data(), (int)num, in.back().data<const int32_t>(), out[0].data<int32_t>(), out[1].data<int32_t>(),
                                            out[2].data<int32_t>(), out[5].data<int32_t>(), (int64_t)flat, &n_out, B200TOK_MEM_HOST, nullptr));
         std::copy_n(out[0].data<int32_t>(), rows, out[3].data<int32_t>());                                   // both ragged outputs share the offsets (:30-32)
         std::copy_n(out[1].data<int32_t>(), rows, out[4].data<int32_t>());
@@ -434,7 +476,7 @@ public:
         shape.push_back((size_t)target);
         out[0].set_shape(shape); out[1].set_shape(shape);
         const bool pad_right = in.size() == 6 ? in[5].data<bool>()[0] : m_pad_right;                          // :113-116
-        check(b200tok_ragged_to_dense_run(0, in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(), in[2].data<const int32_t>(),
+        check(b200tok_ragged_to_dense_run(device(), in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(), in[2].data<const int32_t>(),
                                           (int64_t)in[2].get_size(), target, in[4].data<const int32_t>()[0], pad_right, m_pad_max_length,
                                           out[0].data<int32_t>(), out[1] ? reinterpret_cast<uint8_t*>(out[1].data<bool>()) : nullptr, B200TOK_MEM_HOST, nullptr));
         return true;
@@ -493,7 +535,7 @@ public:
         const auto& rp = in[4 + has_skips];
         std::call_once(m_state->once, [&] {                                // src/regex_normalization.cpp:133-142 (lazy PCRE2 compile)
             check(b200tok_regexnorm_create(sp.data<const char>(), (int64_t)sp.get_size(), rp.data<const char>(), (int64_t)rp.get_size(),
-                                           m_global_replace, 0, &m_state->h));   // patterns outside the single-character set throw here
+                                           m_global_replace, device(), &m_state->h));   // patterns outside the single-character set throw here
         });
         return run_normalizer(m_state->h, out, in, has_skips, 2 + rp.get_size());
     }
@@ -542,18 +584,269 @@ public:
                 blob.assign(in[3 + has_skips].data<const char>(), in[3 + has_skips].get_size());
             }
             check(b200tok_charsmap_create(reinterpret_cast<const uint8_t*>(blob.data()), (int64_t)blob.size(), m_add_dummy_prefix,
-                                          m_remove_extra_whitespaces, m_escape_whitespaces, 0, &m_state->h));
+                                          m_remove_extra_whitespaces, m_escape_whitespaces, device(), &m_state->h));
         });
         return run_normalizer(m_state->h, out, in, has_skips, 3);
     }
 private:
-    bool m_add_dummy_prefix = false, m_remove_extra_whitespaces = true, m_escape_whitespaces = false, m_case_fold = false, m_nmt = false;
+    bool m_add_dummy_prefix = false, m_remove_extra_whitespaces = true, m_escape_whitespaces = false, m_case_fold = false;
     std::string m_normalization_form;
+    bool m_nmt = false;
     mutable std::shared_ptr<Handle> m_state = std::make_shared<Handle>();
 };
 
-// The byte-level shims (BytesToChars, CharsToBytes, FuzeRagged, UTF8Validate) bind the same way to b200tok_bytes_to_chars_run,
-// b200tok_chars_to_bytes_run, b200tok_fuze_ragged_run and b200tok_utf8_validate_run (worst-case chars 2x / 1x / - / 3x, then shrunk).
+// ---- byte-level shims and detokenizer tail: BytesToChars (src/bytes_to_chars.cpp:272-339), CharsToBytes (src/chars_to_bytes.cpp:10-68),
+// ---- FuzeRagged (src/fuze.cpp:10-40), UTF8Validate (src/utf8_validate.cpp:13-137) ------------------------------------------------
+class BytesToChars : public ov::op::Op {
+public:
+    OPENVINO_OP("BytesToChars");
+    BytesToChars() = default;
+    explicit BytesToChars(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        const auto n = get_input_size();
+        OPENVINO_ASSERT(n == 5 || n == 6, "supported input sizes are 5 or 6");
+        for (size_t i = 0; i < 4; ++i) set_output_type(i, ov::element::i32, i < 2 ? get_input_partial_shape(0) : ov::PartialShape{ov::Dimension()});
+        set_output_type(4, ov::element::u8, ov::PartialShape{ov::Dimension()});
+        if (n == 6) set_output_type(5, get_input_element_type(5), get_input_partial_shape(5));
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<BytesToChars>(in); }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        const bool has_skips = in.size() == 6;
+        out[0] = in[0]; out[1] = in[1];                                      // :296-297
+        out[2].set_shape(in[2].get_shape()); out[3].set_shape(in[3].get_shape());
+        const size_t cap = in[4].get_size() * 2;                             // :300
+        out[4].set_shape({cap});
+        if (has_skips) out[5] = in[5];
+        auto rin = ragged_of(in, has_skips ? reinterpret_cast<const uint8_t*>(in[5].data<bool>()) : nullptr);
+        int64_t n_chars = 0;
+        check(b200tok_bytes_to_chars_run(device(), &rin, out[2].data<int32_t>(), out[3].data<int32_t>(), out[4].data<uint8_t>(), (int64_t)cap, &n_chars, nullptr));
+        out[4].set_shape({(size_t)n_chars});
+        return true;
+    }
+};
+
+class CharsToBytes : public ov::op::Op {
+public:
+    OPENVINO_OP("CharsToBytes");
+    CharsToBytes() = default;
+    explicit CharsToBytes(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::u8, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<CharsToBytes>(in); }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        out[0].set_shape(in[0].get_shape()); out[1].set_shape(in[1].get_shape());
+        const size_t cap = in[4].get_size();                                 // :41
+        out[2].set_shape({cap});
+        auto rin = ragged_of(in);
+        int64_t n_chars = 0;
+        check(b200tok_chars_to_bytes_run(device(), &rin, out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<uint8_t>(), (int64_t)cap, &n_chars, nullptr));
+        out[2].set_shape({(size_t)n_chars});
+        return true;
+    }
+};
+
+class FuzeRagged : public ov::op::Op {
+public:
+    OPENVINO_OP("FuzeRagged");
+    FuzeRagged() = default;
+    explicit FuzeRagged(const ov::OutputVector& args) : ov::op::Op(args) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        for (size_t i = 0; i < 4; ++i) OPENVINO_ASSERT(get_input_element_type(i) == ov::element::i32, "Expected i32 tensors as the decomposed ragged string representation");
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<FuzeRagged>(in); }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        out[0].set_shape(in[0].get_shape()); out[1].set_shape(in[1].get_shape());
+        check(b200tok_fuze_ragged_run(device(), in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(), in[2].data<const int32_t>(),
+                                      in[3].data<const int32_t>(), (int64_t)in[2].get_size(), out[0].data<int32_t>(), out[1].data<int32_t>(), B200TOK_MEM_HOST, nullptr));
+        return true;
+    }
+};
+
+class UTF8Validate : public ov::op::Op {
+public:
+    OPENVINO_OP("UTF8Validate");
+    UTF8Validate() = default;
+    UTF8Validate(const ov::OutputVector& args, bool replace_mode = false) : ov::op::Op(args), m_replace_mode(replace_mode) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::u8, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<UTF8Validate>(in, m_replace_mode); }
+    bool visit_attributes(ov::AttributeVisitor& v) override { v.on_attribute("replace_mode", m_replace_mode); return true; }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override {
+        out[0].set_shape(in[0].get_shape()); out[1].set_shape(in[0].get_shape());
+        const size_t cap = in[2].get_size() * 3;                             // :29-35 — the reference leaves the chars tensor at this size
+        out[2].set_shape({cap});
+        int64_t n_chars = 0;
+        check(b200tok_utf8_validate_run(device(), in[0].data<const int32_t>(), in[1].data<const int32_t>(), (int64_t)in[0].get_size(), in[2].data<const uint8_t>(),
+                                        (int64_t)in[2].get_size(), m_replace_mode, out[0].data<int32_t>(), out[1].data<int32_t>(), out[2].data<uint8_t>(), (int64_t)cap,
+                                        &n_chars, B200TOK_MEM_HOST, nullptr));
+        return true;
+    }
+private:
+    bool m_replace_mode = false;
+};
+
+// ---- fused layers created at IR-load time (see the header comment) -------------------------------------------------------------------
+// B200SplitBPE: inputs = RegexSplit's ragged strings [0..4] (+ skips [5]) followed by BPETokenizer's constants (its inputs [5..]);
+// outputs = BPETokenizer's.  The two wrapped ops keep their own lazily built device state, shared with clones like everywhere else.
+class B200SplitBPE : public ov::op::Op {
+public:
+    OPENVINO_OP("B200SplitBPE");
+    B200SplitBPE() = default;
+    B200SplitBPE(const ov::OutputVector& args, bool has_skips, std::shared_ptr<RegexSplit> split, std::shared_ptr<BPETokenizer> bpe, std::string pattern)
+        : ov::op::Op(args), m_has_skips(has_skips), m_split(std::move(split)), m_bpe(std::move(bpe)), m_pattern(std::move(pattern)) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::i32, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<B200SplitBPE>(in, m_has_skips, m_split, m_bpe, m_pattern); }
+    // a model that was fused at load time can be serialised and read back: the layer carries both wrapped ops' attributes
+    bool visit_attributes(ov::AttributeVisitor& v) override {
+        if (!m_split) m_split = std::make_shared<RegexSplit>();
+        if (!m_bpe) m_bpe = std::make_shared<BPETokenizer>();
+        v.on_attribute("has_skips", m_has_skips);
+        v.on_attribute("split_pattern", m_pattern);
+        return m_split->visit_prefixed(v, "split_") && m_bpe->visit_attributes(v);
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override;
+private:
+    bool m_has_skips = false;
+    std::shared_ptr<RegexSplit> m_split;
+    std::shared_ptr<BPETokenizer> m_bpe;
+    std::string m_pattern;
+};
+// B200SplitWordpiece: inputs = the first RegexSplit's ragged strings [0..4] followed by WordpieceTokenizer's vocab [5..7] and unk id [8].
+class B200SplitWordpiece : public ov::op::Op {
+public:
+    OPENVINO_OP("B200SplitWordpiece");
+    B200SplitWordpiece() = default;
+    B200SplitWordpiece(const ov::OutputVector& args, std::shared_ptr<RegexSplit> s1, std::shared_ptr<RegexSplit> s2, std::shared_ptr<WordpieceTokenizer> wp, std::string p1, std::string p2)
+        : ov::op::Op(args), m_s1(std::move(s1)), m_s2(std::move(s2)), m_wp(std::move(wp)), m_p1(std::move(p1)), m_p2(std::move(p2)) { constructor_validate_and_infer_types(); }
+    void validate_and_infer_types() override {
+        set_output_type(0, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(1, ov::element::i32, get_input_partial_shape(0));
+        set_output_type(2, ov::element::i32, ov::PartialShape{ov::Dimension()});
+    }
+    std::shared_ptr<ov::Node> clone_with_new_inputs(const ov::OutputVector& in) const override { return std::make_shared<B200SplitWordpiece>(in, m_s1, m_s2, m_wp, m_p1, m_p2); }
+    bool visit_attributes(ov::AttributeVisitor& v) override {
+        bool two = (bool)m_s2;
+        v.on_attribute("two_splitters", two);
+        if (!m_s1) m_s1 = std::make_shared<RegexSplit>();
+        if (two && !m_s2) m_s2 = std::make_shared<RegexSplit>();
+        if (!m_wp) m_wp = std::make_shared<WordpieceTokenizer>();
+        v.on_attribute("split_pattern", m_p1);
+        bool ok = m_s1->visit_prefixed(v, "split_");
+        if (two) { v.on_attribute("split2_pattern", m_p2); ok = ok && m_s2->visit_prefixed(v, "split2_"); }
+        return ok && m_wp->visit_attributes(v);
+    }
+    bool has_evaluate() const override { return true; }
+    bool evaluate(ov::TensorVector& out, const ov::TensorVector& in) const override;
+private:
+    std::shared_ptr<RegexSplit> m_s1, m_s2;
+    std::shared_ptr<WordpieceTokenizer> m_wp;
+    std::string m_p1, m_p2;
+};
+
+bool B200SplitBPE::evaluate(ov::TensorVector& out, const ov::TensorVector& in) const {
+    const size_t k = 5 + (m_has_skips ? 1 : 0);
+    m_split->ensure(m_pattern.data(), m_pattern.size());
+    ov::TensorVector bin(in.begin(), in.begin() + 5);                     // the tokenizer's own input list: strings + its constants
+    bin.insert(bin.end(), in.begin() + k, in.end());
+    m_bpe->ensure(bin);
+    auto rin = ragged_of(in, m_has_skips ? reinterpret_cast<const uint8_t*>(in[5].data<bool>()) : nullptr);
+    ragged_ids_out(out, in, m_bpe->capacity(bin),
+                   [&](b200tok_ragged_ids* r) { return b200tok_split_bpe_run(m_split->handle(), m_bpe->handle(), &rin, r, nullptr); });
+    return true;
+}
+bool B200SplitWordpiece::evaluate(ov::TensorVector& out, const ov::TensorVector& in) const {
+    const bool has_skips = in.size() == 10;                               // strings [0..4] (+ skips) + vocab [3] + unk id
+    const size_t k = 5 + (has_skips ? 1 : 0);
+    m_s1->ensure(m_p1.data(), m_p1.size());
+    if (m_s2) m_s2->ensure(m_p2.data(), m_p2.size());
+    ov::TensorVector win(in.begin(), in.begin() + 5);
+    win.insert(win.end(), in.begin() + k, in.end());
+    m_wp->ensure(win);
+    const int32_t unk = *win[8].data<const int32_t>();
+    auto rin = ragged_of(in, has_skips ? reinterpret_cast<const uint8_t*>(in[5].data<bool>()) : nullptr);
+    ragged_ids_out(out, in, (int64_t)(in[4].get_size() + in[2].get_size()),
+                   [&](b200tok_ragged_ids* r) { return b200tok_split_wordpiece_run(m_s1->handle(), m_s2 ? m_s2->handle() : nullptr, m_wp->handle(), &rin, unk, r, nullptr); });
+    return true;
+}
+
+// ---- the load-time fusion --------------------------------------------------------------------------------------------------------------
+// `outs[0..4]` are outputs 0..4 of one of this library's RegexSplit layers whose pattern is a Constant: returns it (and the pattern).
+inline std::shared_ptr<RegexSplit> producing_split(const ov::OutputVector& outs, std::string& pattern) {
+    if (outs.size() < 5) return nullptr;
+    auto rs = std::dynamic_pointer_cast<RegexSplit>(outs[0].get_node_shared_ptr());
+    if (!rs) return nullptr;
+    for (size_t i = 0; i < 5; ++i)
+        if (outs[i].get_node() != rs.get() || outs[i].get_index() != i) return nullptr;
+    const size_t n = rs->get_input_size();
+    auto pc = std::dynamic_pointer_cast<ov::op::v0::Constant>(rs->input_value(n - 1).get_node_shared_ptr());
+    if (!pc || (rs->behaviour() != "isolate" && rs->behaviour() != "remove") || rs->max_splits() != -1) return nullptr;
+    pattern.assign(static_cast<const char*>(pc->get_data_ptr()), pc->get_byte_size());
+    return rs;
+}
+inline bool fusion_enabled() {
+    static const bool on = [] { const char* e = std::getenv("B200TOK_FUSE"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
+
+class FusingBPEExtension : public ov::OpExtension<BPETokenizer> {
+public:
+    ov::OutputVector create(const ov::OutputVector& inputs, ov::AttributeVisitor& visitor) const override {
+        ov::OutputVector plain = ov::OpExtension<BPETokenizer>::create(inputs, visitor);      // attributes read, inputs validated
+        auto bpe = std::dynamic_pointer_cast<BPETokenizer>(plain.at(0).get_node_shared_ptr());
+        std::string pattern;
+        auto rs = fusion_enabled() && bpe ? producing_split(inputs, pattern) : nullptr;
+        if (!rs) return plain;
+        const bool has_skips = rs->get_input_size() == 7;
+        ov::OutputVector args;
+        for (size_t i = 0; i < 5u + (has_skips ? 1u : 0u); ++i) args.push_back(rs->input_value(i));
+        args.insert(args.end(), inputs.begin() + 5, inputs.end());
+        return std::make_shared<B200SplitBPE>(args, has_skips, rs, bpe, pattern)->outputs();
+    }
+};
+class FusingWordpieceExtension : public ov::OpExtension<WordpieceTokenizer> {
+public:
+    ov::OutputVector create(const ov::OutputVector& inputs, ov::AttributeVisitor& visitor) const override {
+        ov::OutputVector plain = ov::OpExtension<WordpieceTokenizer>::create(inputs, visitor);
+        auto wp = std::dynamic_pointer_cast<WordpieceTokenizer>(plain.at(0).get_node_shared_ptr());
+        std::string p2, p1;
+        auto s2 = fusion_enabled() && wp ? producing_split(inputs, p2) : nullptr;
+        if (!s2) return plain;
+        // a second splitter in front (the BERT chain: whitespace removed, then punctuation isolated)?  Its skip flags must be the ones
+        // the first splitter hands on, so that one skips tensor describes the chain.
+        std::shared_ptr<RegexSplit> s1;
+        {
+            ov::OutputVector up;
+            for (size_t i = 0; i < 5; ++i) up.push_back(s2->input_value(i));
+            s1 = producing_split(up, p1);
+            if (s1 && (s1->get_input_size() == 7) != (s2->get_input_size() == 7)) s1 = nullptr;
+            if (s1 && s2->get_input_size() == 7 && (s2->input_value(5).get_node() != s1.get() || s2->input_value(5).get_index() != 5)) s1 = nullptr;
+            if (s1 && !(s1->behaviour() == "remove" && s2->behaviour() == "isolate")) s1 = nullptr;      // the pair the fused kernel implements
+        }
+        const auto& first = s1 ? s1 : s2;
+        const bool has_skips = first->get_input_size() == 7;
+        ov::OutputVector args;
+        for (size_t i = 0; i < 5u + (has_skips ? 1u : 0u); ++i) args.push_back(first->input_value(i));
+        args.insert(args.end(), inputs.begin() + 5, inputs.end());
+        return std::make_shared<B200SplitWordpiece>(args, s1 ? s1 : s2, s1 ? s2 : nullptr, wp, s1 ? p1 : p2, s1 ? p2 : std::string())->outputs();
+    }
+};
 
 }  // namespace b200
 
@@ -561,8 +854,8 @@ private:
 // load the reference extension as well for the remaining ops, ours registered last so that these names resolve here.
 OPENVINO_CREATE_EXTENSIONS(std::vector<ov::Extension::Ptr>({
     std::make_shared<ov::OpExtension<b200::RegexSplit>>(),
-    std::make_shared<ov::OpExtension<b200::BPETokenizer>>(),
-    std::make_shared<ov::OpExtension<b200::WordpieceTokenizer>>(),
+    std::make_shared<b200::FusingBPEExtension>(),
+    std::make_shared<b200::FusingWordpieceExtension>(),
     std::make_shared<ov::OpExtension<b200::VocabEncoder>>(),
     std::make_shared<ov::OpExtension<b200::VocabDecoder>>(),
     std::make_shared<ov::OpExtension<b200::ByteFallback>>(),
@@ -572,13 +865,19 @@ OPENVINO_CREATE_EXTENSIONS(std::vector<ov::Extension::Ptr>({
     std::make_shared<ov::OpExtension<b200::RaggedToDense>>(),
     std::make_shared<ov::OpExtension<b200::RegexNormalization>>(),
     std::make_shared<ov::OpExtension<b200::CharsMapNormalization>>(),
+    std::make_shared<ov::OpExtension<b200::BytesToChars>>(),
+    std::make_shared<ov::OpExtension<b200::CharsToBytes>>(),
+    std::make_shared<ov::OpExtension<b200::FuzeRagged>>(),
+    std::make_shared<ov::OpExtension<b200::UTF8Validate>>(),
+    std::make_shared<ov::OpExtension<b200::B200SplitBPE>>(),
+    std::make_shared<ov::OpExtension<b200::B200SplitWordpiece>>(),
 }));
 
 // GenAI's GGUF path dlsym()s this factory (src/tokenizers_factory.hpp:32-33); the signature is frozen.
 namespace ov { namespace tokenizers {
 OPENVINO_API_C(ov::OutputVector)
 create_tokenizer_node(const std::string& op_type, const ov::OutputVector& inputs, const ov::AnyMap& attributes) {
-    auto get = [&](const char* k, auto def) { auto it = attributes.find(k); return it == attributes.end() ? def : it->second.as<decltype(def)>(); };
+    auto get = [&](const char* k, auto def) { auto it = attributes.find(k); return it == attributes.end() ? def : it->second.template as<decltype(def)>(); };
     if (op_type == "RegexSplit") return std::make_shared<b200::RegexSplit>(inputs, get("behaviour", std::string("remove")), get("invert", false), get("max_splits", -1))->outputs();
     if (op_type == "BPETokenizer") return std::make_shared<b200::BPETokenizer>(inputs, get("unk_token", std::string()), get("fuse_unk", false), get("suffix_indicator", std::string()), get("end_suffix", std::string()), get("byte_fallback", false))->outputs();
     if (op_type == "WordpieceTokenizer") return std::make_shared<b200::WordpieceTokenizer>(inputs, get("suffix_indicator", std::string("##")), get("max_bytes_per_word", 100))->outputs();
@@ -590,6 +889,10 @@ create_tokenizer_node(const std::string& op_type, const ov::OutputVector& inputs
     if (op_type == "CombineSegments") return std::make_shared<b200::CombineSegments>(inputs)->outputs();
     if (op_type == "RaggedToDense") return std::make_shared<b200::RaggedToDense>(inputs, get("pad_right", true), get("m_pad_max_length", false))->outputs();
     if (op_type == "RegexNormalization") return std::make_shared<b200::RegexNormalization>(inputs, get("global_replace", true))->outputs();
+    if (op_type == "BytesToChars") return std::make_shared<b200::BytesToChars>(inputs)->outputs();
+    if (op_type == "CharsToBytes") return std::make_shared<b200::CharsToBytes>(inputs)->outputs();
+    if (op_type == "FuzeRagged") return std::make_shared<b200::FuzeRagged>(inputs)->outputs();
+    if (op_type == "UTF8Validate") return std::make_shared<b200::UTF8Validate>(inputs, get("replace_mode", false))->outputs();
     if (op_type == "CharsMapNormalization") return std::make_shared<b200::CharsMapNormalization>(inputs, get("add_dummy_prefix", false), get("remove_extra_whitespaces", true), get("escape_whitespaces", false), get("case_fold", false), get("normalization_form", std::string()), get("nmt", false))->outputs();
     OPENVINO_THROW("Unsupported operation type in the B200 hot-path extension: ", op_type);
 }

@@ -574,8 +574,10 @@ int parse_split(const b200tok_regexsplit_desc& d, HostSplit& out, std::string& e
         std::memcpy(out.spec.lit, pat.data(), pat.size());
         return B200TOK_OK;
     }
-    err = "RegexSplit: pattern is not one of the tokenizer patterns the GPU splitter implements: " + pat;
-    return B200TOK_E_UNSUPPORTED;
+    // anything else: compile it for the regex machine (regex_vm.cuh); patterns outside its syntax are refused, never approximated
+    const int rc = compile_regex(pat, out.vm, err);
+    if (rc == B200TOK_OK) out.spec.pat = PAT_VM;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------

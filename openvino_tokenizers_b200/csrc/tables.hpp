@@ -80,9 +80,26 @@ struct HostVocabEnc {
 };
 int build_vocabenc(const b200tok_vocabenc_desc& d, HostVocabEnc& out, std::string& err);
 
+// General split patterns: program of the regex machine (regex_vm.cuh), compiled by regex_compile.cpp.
+struct HostVm {
+    std::vector<VmInst> code;
+    std::vector<VmSet> sets;
+    std::vector<uint32_t> ranges;
+};
+struct HostGcTables { std::vector<uint16_t> stage1; std::vector<uint8_t> stage2; };     // Unicode general category per code point
+const HostGcTables& host_gc_tables();
+int compile_regex(const std::string& pattern, HostVm& out, std::string& err);
+
 enum SplitMode : int { MODE_REMOVED = 0, MODE_ISOLATED = 1, MODE_MERGED_PREV = 2, MODE_MERGED_NEXT = 3 };
 struct HostSplit {
     SplitSpec spec{};
+    HostVm vm;             // spec.pat == PAT_VM
+    // spec with vm pointing at this object's host vectors (host harness / tests)
+    SplitSpec host_spec() const {
+        SplitSpec s = spec;
+        if (s.pat == PAT_VM) s.vm = VmProgram{vm.code.data(), vm.sets.data(), vm.ranges.data(), host_gc_tables().stage1.data(), host_gc_tables().stage2.data(), (int32_t)vm.code.size()};
+        return s;
+    }
     int mode = MODE_REMOVED;
     bool invert = false;
     int max_splits = -1;

@@ -13,6 +13,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "regex_vm.cuh"
+
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__ __forceinline__
 #else
@@ -77,7 +79,8 @@ enum PatternId : int {
     PAT_LITERAL = 7,       // one literal string (metaspace etc.)
     PAT_ANYCHAR = 8,       // .
     PAT_CLASS_CHAR = 9,    // one character of a class: \p{N} == \p{Nd}|\p{Nl}|\p{No}, or \p{P}
-    PAT_BERT_FUSED = 10    // internal: \s+ (remove) followed by PAT_BERT_PUNCT (isolate), one pass
+    PAT_BERT_FUSED = 10,   // internal: \s+ (remove) followed by PAT_BERT_PUNCT (isolate), one pass
+    PAT_VM = 11            // any other pattern inside the supported syntax: compiled to the regex machine of regex_vm.cuh
 };
 
 // Partition of characters into "kinds" such that every quantified class of the pattern is a
@@ -100,6 +103,7 @@ struct SplitSpec {
     uint8_t class_mask;       // PAT_CLASS_CHAR
     uint8_t lit_len;          // PAT_LITERAL
     uint8_t lit[22];
+    VmProgram vm;             // PAT_VM (pointers into host memory in the host harness, device memory in the kernels)
 };
 
 struct Match {
@@ -304,6 +308,11 @@ B2_HD Match match_at(const C& c, const SplitSpec& spec, int p, int end) {
             if (!ctx_has(c, p + k, peek) || p + k >= end || c.byte(p + k) != spec.lit[k]) return Match{0, peek, 0};
         }
         return Match{(int)spec.lit_len, peek, 0};
+    }
+    case PAT_VM: {
+        int len, peek;
+        vm_match(c, spec.vm, p, end, len, peek);
+        return Match{len, peek, 0};
     }
     default: return Match{0, p + 1, 0};
     }

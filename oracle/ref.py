@@ -67,6 +67,15 @@ def lib(path: Path | None = None, prefix: str = "ovref"):
     getattr(L, f"{prefix}_node_share").restype = C.c_void_p
     getattr(L, f"{prefix}_node_destroy").argtypes = [C.c_void_p]
     getattr(L, f"{prefix}_last_error").restype = C.c_char_p
+    getattr(L, f"{prefix}_graph_create").restype = C.c_void_p
+    getattr(L, f"{prefix}_graph_destroy").argtypes = [C.c_void_p]
+    getattr(L, f"{prefix}_graph_add_input").argtypes = [C.c_void_p, C.POINTER(_Tensor)]
+    getattr(L, f"{prefix}_graph_add_layer").argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.POINTER(C.c_int), C.c_int]
+    getattr(L, f"{prefix}_graph_value_type").argtypes = [C.c_void_p, C.c_int]
+    getattr(L, f"{prefix}_graph_value_type").restype = C.c_char_p
+    getattr(L, f"{prefix}_graph_evaluate").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_Tensor)]
+    getattr(L, f"{prefix}_graph_evaluated_nodes").argtypes = [C.c_void_p]
+    getattr(L, f"{prefix}_graph_result").argtypes = [C.c_void_p, C.c_int, C.POINTER(_Tensor)]
     if path is None:
         _lib = L
     return L
@@ -187,3 +196,99 @@ class StubOp:
 
 class RefOp(StubOp):
     """A reference op class (src/*.cpp of openvino_tokenizers) — evaluate() is the reference's own code."""
+
+
+def _tensor_to_numpy(d: _Tensor):
+    shape = tuple(d.shape[k] for k in range(d.ndim))
+    n = int(np.prod(shape)) if shape else 1
+    dt = _DTYPES.get(d.dtype)
+    if dt is None:
+        return None
+    if n == 0 or not d.data:
+        return np.zeros(shape, dt)
+    buf = (C.c_uint8 * (n * dt.itemsize)).from_address(d.data)
+    return np.frombuffer(buf, dtype=dt).reshape(shape).copy()
+
+
+class StubGraph:
+    """A chain of layers "read" one after the other through the registered extensions — what loading an IR does — with a minimal
+    executor.  ``parameter(example)`` / ``constant(array)`` return value ids; ``layer(op, inputs, **attrs)`` returns the ids of the
+    layer's outputs; ``run(wanted_ids, parameter_arrays)`` evaluates the producing nodes in dependency order."""
+
+    _prefix = "ovref"
+
+    def _lib(self):
+        return lib()
+
+    def _fn(self, name):
+        return getattr(self._lib(), f"{self._prefix}_{name}")
+
+    def __init__(self):
+        self._g = self._fn("graph_create")()
+        self._keep = []
+
+    def _err(self, what):
+        return RuntimeError(f"{what}: " + self._fn("last_error")().decode(errors="replace"))
+
+    def parameter(self, example):
+        t = _desc(as_tensor(example), False)
+        i = self._fn("graph_add_input")(self._g, C.byref(t))
+        if i < 0:
+            raise self._err("parameter")
+        return i
+
+    def constant(self, value):
+        a = as_tensor(value)
+        self._keep.append(a)
+        t = _desc(a, True)
+        if a.size == 0:
+            dummy = np.zeros(1, np.uint8)
+            self._keep.append(dummy)
+            t.data = dummy.ctypes.data
+        if a.ndim == 0:
+            t.data = a.ctypes.data
+        i = self._fn("graph_add_input")(self._g, C.byref(t))
+        if i < 0:
+            raise self._err("constant")
+        return i
+
+    def layer(self, op, inputs, **attrs):
+        ids = (C.c_int * len(inputs))(*inputs)
+        out = (C.c_int * 16)()
+        text = "\x1e".join(f"{k}={StubOp._fmt(v)}" for k, v in attrs.items()).encode("utf-8", "surrogateescape")
+        n = self._fn("graph_add_layer")(self._g, op.encode(), len(inputs), ids, text, out, 16)
+        if n < 0:
+            raise self._err(op)
+        return [out[i] for i in range(n)]
+
+    def producer_type(self, value_id):
+        return self._fn("graph_value_type")(self._g, value_id).decode()
+
+    def run(self, wanted, parameter_arrays):
+        arrs = [as_tensor(a) for a in parameter_arrays]
+        tin = (_Tensor * max(len(arrs), 1))()
+        for i, a in enumerate(arrs):
+            tin[i] = _desc(a, True)
+            if a.ndim == 0:
+                tin[i].data = a.ctypes.data
+        want = (C.c_int * len(wanted))(*wanted)
+        if self._fn("graph_evaluate")(self._g, len(wanted), want, len(arrs), tin):
+            raise self._err("evaluate")
+        res = []
+        for i in range(len(wanted)):
+            d = _Tensor()
+            self._fn("graph_result")(self._g, i, C.byref(d))
+            res.append(_tensor_to_numpy(d))
+        return res
+
+    @property
+    def evaluated_nodes(self):
+        return self._fn("graph_evaluated_nodes")(self._g)
+
+    def __del__(self):
+        g, self._g = getattr(self, "_g", None), None
+        if g:
+            try:
+                self._fn("graph_destroy")(g)
+            except Exception:
+                pass

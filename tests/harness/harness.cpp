@@ -26,10 +26,11 @@ HZ int64_t hz_split(const char* pattern, int64_t plen, const char* behaviour, in
     int rc = parse_split(d, hs, err);
     if (rc) return rc;
     ScanCtx c{chars, (int)n, host_class_tables().view(), hs.spec.pat, hs.spec.class_mask};
+    const SplitSpec spec = hs.host_spec();          // (PAT_VM: the compiled program, host pointers)
     SplitEmitter em;
     em.reset(hs.mode, hs.invert, hs.max_splits, (int)n);
     int64_t k = 0;
-    split_element_scan(c, hs.spec, hs.repeat, 0, (int)n, em, [&](int b, int e) {
+    split_element_scan(c, spec, hs.repeat, 0, (int)n, em, [&](int b, int e) {
         if (k < cap) { out_b[k] = b; out_e[k] = e; }
         ++k;
     });

@@ -17,10 +17,10 @@ def lib():
     global _lib
     if _lib is None:
         so = HERE / "libharness.so"
-        srcs = [HERE / "harness.cpp", CSRC / "tables.cpp", CSRC / "tables.hpp", CSRC / "tok_core.cuh"]
+        srcs = [HERE / "harness.cpp", CSRC / "tables.cpp", CSRC / "regex_compile.cpp", CSRC / "regex_vm.cuh", CSRC / "tables.hpp", CSRC / "tok_core.cuh"]
         if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-o", str(so),
-                                   str(HERE / "harness.cpp"), str(CSRC / "tables.cpp")])
+                                   str(HERE / "harness.cpp"), str(CSRC / "tables.cpp"), str(CSRC / "regex_compile.cpp")])
         _lib = C.CDLL(str(so))
         _lib.hz_split.restype = C.c_int64
         _lib.hz_bpe_create.restype = C.c_void_p

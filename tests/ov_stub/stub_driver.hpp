@@ -138,6 +138,75 @@ inline int node_output(NodeHandle* h, int i, ovs_tensor* d) {
     return 0;
 }
 
+
+// ---- a whole chain of layers, "read" one after the other like an IR, and a minimal executor for it ---------------------------------
+struct GraphHandle {
+    std::vector<ov::Output<ov::Node>> values;              // value id -> producing output
+    std::vector<std::shared_ptr<ov::Node>> params;         // Parameters in creation order
+    std::vector<std::shared_ptr<ov::Node>> keep;
+    ov::TensorVector results;                              // of the last graph_evaluate
+    int evaluated_nodes = 0;
+};
+inline int graph_add_input(GraphHandle* g, const ovs_tensor* proto) {
+    try {
+        std::vector<std::shared_ptr<ov::Node>> made;
+        ov::OutputVector o = make_producers(1, proto, made);
+        g->keep.push_back(made[0]);
+        if (!proto->data) g->params.push_back(made[0]);
+        g->values.push_back(o[0]);
+        return (int)g->values.size() - 1;
+    } catch (const std::exception& e) { g_error = e.what(); return -1; }
+}
+inline int graph_add_layer(const Registry& reg, GraphHandle* g, const char* op, int n_in, const int* ids, const char* attrs, int* out_ids, int max_out) {
+    try {
+        auto it = reg.find(op);
+        OPENVINO_ASSERT(it != reg.end(), "stub driver: no extension registered for op type ", op);
+        ov::OutputVector in;
+        for (int i = 0; i < n_in; ++i) in.push_back(g->values.at((size_t)ids[i]));
+        ov::AttributeVisitor visitor(parse_attrs(attrs));
+        ov::OutputVector out = it->second->create(in, visitor);
+        OPENVINO_ASSERT(!out.empty() && (int)out.size() <= max_out, "stub driver: unexpected number of outputs");
+        g->keep.push_back(out[0].get_node_shared_ptr());
+        for (size_t i = 0; i < out.size(); ++i) { g->values.push_back(out[i]); out_ids[i] = (int)g->values.size() - 1; }
+        return (int)out.size();
+    } catch (const std::exception& e) { g_error = e.what(); return -1; }
+}
+inline void graph_eval_node(GraphHandle* g, ov::Node* n, std::map<ov::Node*, ov::TensorVector>& done, const ov::TensorVector& param_values) {
+    if (done.count(n)) return;
+    for (size_t p = 0; p < g->params.size(); ++p)
+        if (g->params[p].get() == n) { done[n] = {param_values.at(p)}; return; }
+    ov::TensorVector in;
+    for (size_t i = 0; i < n->get_input_size(); ++i) {
+        ov::Node* src = n->input_value(i).get_node();
+        graph_eval_node(g, src, done, param_values);
+        in.push_back(done[src].at(n->input_value(i).get_index()));
+    }
+    ov::TensorVector out;
+    for (size_t i = 0; i < n->get_output_size(); ++i) out.emplace_back(n->get_output_element_type(i), ov::Shape{0});
+    OPENVINO_ASSERT(n->evaluate(out, in), n->get_type_name(), ": evaluate() returned false");
+    if (std::strcmp(n->get_type_name(), "Constant") != 0) ++g->evaluated_nodes;          // layers with an evaluate() of their own
+    done[n] = out;
+}
+inline int graph_evaluate(GraphHandle* g, int n_want, const int* want, int n_params, const ovs_tensor* params) {
+    try {
+        OPENVINO_ASSERT((size_t)n_params == g->params.size(), "stub driver: expected ", g->params.size(), " parameter tensors");
+        ov::TensorVector pv;
+        for (int i = 0; i < n_params; ++i) {
+            if (params[i].data || params[i].ndim == 0) pv.emplace_back(dtype_of(params[i].dtype), shape_of(params[i]), params[i].data ? params[i].data : (void*)&params[i].shape[3]);
+            else pv.emplace_back(dtype_of(params[i].dtype), shape_of(params[i]));
+        }
+        std::map<ov::Node*, ov::TensorVector> done;
+        g->results.clear();
+        g->evaluated_nodes = 0;
+        for (int i = 0; i < n_want; ++i) {
+            const auto& v = g->values.at((size_t)want[i]);
+            graph_eval_node(g, v.get_node(), done, pv);
+            g->results.push_back(done[v.get_node()].at(v.get_index()));
+        }
+        return 0;
+    } catch (const std::exception& e) { g_error = e.what(); return -1; }
+}
+
 }  // namespace ovs
 
 // The extern "C" surface; REGISTRY is an expression yielding `const ovs::Registry&`.
@@ -164,4 +233,25 @@ inline int node_output(NodeHandle* h, int i, ovs_tensor* d) {
     extern "C" __attribute__((visibility("default"))) double PREFIX##_node_last_ms(void* h) { return static_cast<ovs::NodeHandle*>(h)->last_ms; } \
     extern "C" __attribute__((visibility("default"))) const char* PREFIX##_node_type(void* h) { return static_cast<ovs::NodeHandle*>(h)->node->get_type_name(); } \
     extern "C" __attribute__((visibility("default"))) void PREFIX##_node_destroy(void* h) { delete static_cast<ovs::NodeHandle*>(h); } \
+    extern "C" __attribute__((visibility("default"))) void* PREFIX##_graph_create(void) { return new ovs::GraphHandle(); }                \
+    extern "C" __attribute__((visibility("default"))) void PREFIX##_graph_destroy(void* g) { delete static_cast<ovs::GraphHandle*>(g); }    \
+    extern "C" __attribute__((visibility("default"))) int PREFIX##_graph_add_input(void* g, const ovs_tensor* proto) {                       \
+        return ovs::graph_add_input(static_cast<ovs::GraphHandle*>(g), proto);                                                              \
+    }                                                                                                                                        \
+    extern "C" __attribute__((visibility("default"))) int PREFIX##_graph_add_layer(void* g, const char* op, int n, const int* ids, const char* attrs, int* out_ids, int max_out) { \
+        return ovs::graph_add_layer(REGISTRY, static_cast<ovs::GraphHandle*>(g), op, n, ids, attrs, out_ids, max_out);                       \
+    }                                                                                                                                        \
+    extern "C" __attribute__((visibility("default"))) const char* PREFIX##_graph_value_type(void* g, int id) {                               \
+        return static_cast<ovs::GraphHandle*>(g)->values.at((size_t)id).get_node()->get_type_name();                                         \
+    }                                                                                                                                        \
+    extern "C" __attribute__((visibility("default"))) int PREFIX##_graph_evaluate(void* g, int n_want, const int* want, int n_params, const ovs_tensor* params) { \
+        return ovs::graph_evaluate(static_cast<ovs::GraphHandle*>(g), n_want, want, n_params, params);                                       \
+    }                                                                                                                                        \
+    extern "C" __attribute__((visibility("default"))) int PREFIX##_graph_evaluated_nodes(void* g) { return static_cast<ovs::GraphHandle*>(g)->evaluated_nodes; } \
+    extern "C" __attribute__((visibility("default"))) int PREFIX##_graph_result(void* g, int i, ovs_tensor* d) {                             \
+        auto* G = static_cast<ovs::GraphHandle*>(g);                                                                                         \
+        if (i < 0 || (size_t)i >= G->results.size()) return -1;                                                                              \
+        ovs::NodeHandle tmp; tmp.outputs = {G->results[(size_t)i]};                                                                          \
+        return ovs::node_output(&tmp, 0, d);                                                                                                 \
+    }                                                                                                                                        \
     extern "C" __attribute__((visibility("default"))) const char* PREFIX##_last_error(void) { return ovs::g_error.c_str(); }

@@ -175,20 +175,28 @@ def test_regex_split_golden_vectors(ops):
         op = ops.RegexSplit(case["behaviour"], case["invert"], case["max_splits"])
         rb, re_, b, e, c = cases.batch_from_strings([case["text"]])
         pat = np.frombuffer(case["pattern"].encode(), np.uint8)
-        try:
-            out = op.evaluate([rb, re_, b, e, c, pat])
-        except ops.B200TokError as err:
-            assert err.code == -4 and not case["gpu_supported"], case
-            continue
-        assert case["gpu_supported"], case
+        out = op.evaluate([rb, re_, b, e, c, pat])          # every pattern of the reference's vectors runs on the GPU (CLIP through the regex machine)
         pieces = [p.decode() for p in unpack_strings(out[2], out[3], c)]
         if case["text"] == "":
             assert out[0].tolist() == [0] and out[1].tolist() == [0]   # shape-[1] shortcut
         else:
             assert pieces == case["expected"], case
         n_run += 1
-    assert n_run >= 23
+    assert n_run == 33
 
+
+VM_PATTERNS = {
+    "clip": r"<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+",
+    "o200k": (r"[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+(?i:'s|'t|'re|'ve|'m|'ll|'d)?|"
+              r"[^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*(?i:'s|'t|'re|'ve|'m|'ll|'d)?|\p{N}{1,3}|"
+              r" ?[^\s\p{L}\p{N}]+[\r\n/]*|\s*[\r\n]+|\s+(?!\S)|\s+"),
+    "qwen2": r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+",
+    "cl100k_possessive": r"'(?i:[sdmt]|ll|ve|re)|[^\r\n\p{L}\p{N}]?+\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]++[\r\n]*|\s*[\r\n]|\s+(?!\S)|\s+",
+    "deepseek_digits": r"\p{N}{1,3}",
+    "deepseek_cjk": "[一-龥\u3040-ゟ゠-ヿ]+",
+    "deepseek_main": (r"[!\"#$%&'()*+,\-./:;<=>?@\[\\\]^_`{|}~][A-Za-z]+|[^\r\n\p{L}\p{P}\p{S}]?[\p{L}\p{M}]+| ?[\p{P}\p{S}]+[\r\n]*|"
+                      r"\s*[\r\n]+|\s+(?!\S)|\s+"),
+}
 
 SPLIT_CASES = [
     (A.GPT2_PATTERN, "isolate", False), (A.GPT2_DIGITS_PATTERN, "isolate", False), (A.LLAMA3_PATTERN, "isolate", False),
@@ -197,6 +205,13 @@ SPLIT_CASES = [
     ("▁", "mergedwithprevious", False), (r"\p{N}", "isolate", False), (r"\p{P}", "contiguous", False),
     (r"\s+", "mergedwithprevious", True), (r"\s+", "mergedwithnext", True), (r"\p{Nd}|\p{Nl}|\p{No}", "remove", False),
     (r"\s+", "isolate", True),
+    # general patterns, compiled for the regex machine (csrc/regex_vm.cuh): CLIP, gpt-4o (o200k), Qwen2, cl100k with possessive
+    # quantifiers, the three DeepSeek-V3 splitters, and a few that exercise groups / anchors / counted repeats
+    (VM_PATTERNS["clip"], "isolate", True), (VM_PATTERNS["o200k"], "isolate", False), (VM_PATTERNS["qwen2"], "isolate", False),
+    (VM_PATTERNS["cl100k_possessive"], "isolate", False), (VM_PATTERNS["deepseek_digits"], "isolate", False),
+    (VM_PATTERNS["deepseek_cjk"], "isolate", False), (VM_PATTERNS["deepseek_main"], "isolate", False),
+    (VM_PATTERNS["o200k"], "contiguous", False), (VM_PATTERNS["qwen2"], "remove", True), (r"(ab|a)(c|bcd)?", "mergedwithnext", False),
+    (r"a.c|^x|y$", "mergedwithprevious", False), (r"\s?\w{2,4}", "isolate", False), (r"(?i)straße|[a-f]+", "remove", False),
 ]
 
 
@@ -230,9 +245,10 @@ def test_regex_split_max_splits(ops, oracle_mod):
 
 
 def test_regex_split_unknown_pattern_is_an_error(ops):
-    with pytest.raises(ops.B200TokError) as ei:
-        ops.RegexSplit("isolate").with_pattern(r"(foo|bar)+baz")
-    assert ei.value.code == -4
+    for pat in (r"(foo|bar)+baz", r"\bword\b", r"a*?b", r"(?<=x)y", r"\p{Han}+", r"(?=ab)a", r"[[:alpha:]]+", r"(a)\1"):
+        with pytest.raises(ops.B200TokError) as ei:         # outside the compiled syntax: refused, never approximated
+            ops.RegexSplit("isolate").with_pattern(pat)
+        assert ei.value.code == -4, pat
     with pytest.raises(ops.B200TokError):
         ops.RegexSplit("nonsense").with_pattern(r"\s+")
     with pytest.raises(ops.B200TokError):
@@ -770,3 +786,19 @@ def test_fast_kernel_variants(env):
     root = Path(__file__).resolve().parent.parent
     r = subprocess.run([sys.executable, str(root / "tools" / "variant_check.py")], capture_output=True, text=True, env=dict(os.environ, **env), timeout=900)
     assert r.returncode == 0 and "variant ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_fused_split_bpe_with_a_general_pattern(ops, llama3, oracle_mod):
+    """RegexSplit with a pattern only the regex machine knows (Qwen2's, gpt-4o's), fused with BPETokenizer and as separate ops."""
+    batch = cases.batch_from_strings(cases.EDGE_STRINGS + cases.long_prompts())
+    rnd = cases.mixed_utf8_batch(512, 1024, seed=12)
+    for name in ("qwen2", "o200k", "clip"):
+        pat = VM_PATTERNS[name]
+        split = ops.RegexSplit("isolate").with_pattern(pat)
+        o_split = oracle_mod.SplitOracle(pat, "isolate")
+        for bt in (batch, rnd):
+            s = o_split(*bt)
+            exp = llama3["o_bpe"](s[0], s[1], s[2], s[3], bt[4])
+            assert cases.ragged_rows_equal(ops.split_bpe(split, llama3["bpe"], list(bt)), exp), name
+            g = split.evaluate([*bt, np.frombuffer(pat.encode(), np.uint8)])
+            assert cases.ragged_rows_equal(llama3["bpe"].evaluate([*g[:5], *llama3["consts"]]), exp), name

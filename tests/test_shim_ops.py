@@ -149,3 +149,29 @@ def test_gpu_utf8_validate(ops, oracle_mod, norm_path):
     got = ops.UTF8Validate(True).evaluate([b[5:], e[5:], ch])
     assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1])
     assert np.array_equal(got[2][int(b[5]):], exp[2][int(b[5]):])
+
+
+@pytest.mark.gpu
+def test_chars_to_bytes_device_buffers_validate_row_partition():
+    """Device-resident inputs get the same contract check as host inputs: rows that do not cover the elements contiguously and
+    in order are refused (E_UNSUPPORTED) instead of yielding extents taken from the wrong elements."""
+    import ctypes as C
+    import torch
+    from openvino_tokenizers_b200 import _capi as K
+    dev = torch.device("cuda", 0)
+    b, e, c = pack_strings([b"ab", b"c", b"def", b"g"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    db, de, dc = t(b), t(e), t(np.concatenate([c, np.zeros(64, np.uint8)]))
+    ob, oe, oc = torch.empty(4, dtype=torch.int32, device=dev), torch.empty(4, dtype=torch.int32, device=dev), torch.empty(64, dtype=torch.uint8, device=dev)
+
+    def run(rb, re_):
+        drb, dre = t(np.asarray(rb, np.int32)), t(np.asarray(re_, np.int32))
+        rin = K.RaggedStrings(drb.data_ptr(), dre.data_ptr(), len(rb), db.data_ptr(), de.data_ptr(), 4, dc.data_ptr(), len(c), None, K.MEM_DEVICE)
+        n = C.c_int64(0)
+        rcs = []
+        for fn in (K.lib().b200tok_chars_to_bytes_run, K.lib().b200tok_bytes_to_chars_run):
+            rcs.append(fn(0, C.byref(rin), C.c_void_p(ob.data_ptr()), C.c_void_p(oe.data_ptr()), C.c_void_p(oc.data_ptr()), C.c_int64(64), C.byref(n), None))
+        return rcs
+    assert run([0, 2], [2, 4]) == [0, 0]
+    for rb, re_ in (([0, 3], [2, 4]), ([2, 0], [4, 2]), ([0, 2], [2, 3]), ([1, 2], [2, 4])):      # gap / reordered / short / late start
+        assert run(rb, re_) == [K.E_UNSUPPORTED, K.E_UNSUPPORTED], (rb, re_)

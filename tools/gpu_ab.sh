@@ -9,10 +9,10 @@ for kv in "$@"; do
   i=$((i+1))
   name="v$i"
   echo "== $name: $kv"
-  env $kv timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > "gpurun_out/bench_c1_${TAG}_$name.json" 2> "gpurun_out/bench_c1_${TAG}_$name.err"
+  env $kv timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-unfused > "gpurun_out/bench_c1_${TAG}_$name.json" 2> "gpurun_out/bench_c1_${TAG}_$name.err"
   python tools/bench_brief.py "gpurun_out/bench_c1_${TAG}_$name.json" | cut -c1-260
   if [ -z "$SKIP_C3" ]; then
-  env $kv timeout 600 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline > "gpurun_out/bench_c3_${TAG}_$name.json" 2>> "gpurun_out/bench_c1_${TAG}_$name.err"
+  env $kv timeout 600 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline --no-unfused > "gpurun_out/bench_c3_${TAG}_$name.json" 2>> "gpurun_out/bench_c1_${TAG}_$name.err"
   python tools/bench_brief.py "gpurun_out/bench_c3_${TAG}_$name.json" | cut -c1-260
   fi
 done
