@@ -38,7 +38,7 @@ def test_no_oracle_in_product():
 def test_pattern_and_vocab_errors_do_not_need_a_gpu(K):
     lib = K.lib()
     h = C.c_void_p()
-    d = K.RegexSplitDesc(b"(a|b)+c", 7, b"isolate", 0, -1, 0)
+    d = K.RegexSplitDesc(b"(foo|bar)+baz", 13, b"isolate", 0, -1, 0)      # a group repeated without bound: outside the compiled syntax
     assert lib.b200tok_regexsplit_create(C.byref(d), C.byref(h)) == K.E_UNSUPPORTED
     assert b"pattern" in lib.b200tok_last_error()
     d = K.RegexSplitDesc(rb"\s+", 3, b"sideways", 0, -1, 0)
