@@ -408,7 +408,7 @@ int compile_regex(const std::string& pattern, HostVm& out, std::string& err) {
         err = "RegexSplit: the pattern is outside the syntax the GPU splitter compiles (" + (P.err.empty() ? std::string("unbalanced parenthesis") : P.err) + "): " + pattern;
         return B200TOK_E_UNSUPPORTED;
     }
-    if (!P.gen(*root)) { err = "RegexSplit: " + P.err + ": " + pattern; return B200TOK_E_UNSUPPORTED; }
+    if (!P.gen(*root)) { err = "RegexSplit: the pattern is outside the syntax the GPU splitter compiles (" + P.err + "): " + pattern; return B200TOK_E_UNSUPPORTED; }
     P.emit(VM_MATCH, 0);
     for (const SetSpec& S : P.specs) {
         VmSet v{};
