@@ -120,6 +120,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def profiled(workload, key):
+    """A figure of profiles/roofline_traffic.json (ncu pass over `bench.py --device-only`, tools/step_metrics.py) or None."""
+    try:
+        return (json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(workload) or {}).get(key)
+    except Exception:
+        return None
+
+
 def cpu_sample(w, batch, rows):
     rb, re_, b, e, c = batch
     n = min(rows, len(rb))
@@ -262,6 +270,9 @@ def main_detok(args, w, rank, world, local_rank):
         torch.cuda.synchronize()
     launches = dec.launches - launches0
     clocks = sampler.stop()
+    if args.device_only:
+        print(json.dumps({"device_only": True, "steps": args.steps}))
+        return
     assert n_dev == n_out and bytes(d_c[:n_out].cpu().numpy()) == bytes(ref[4])
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     # end to end: pinned host buffers through the same C-ABI call (H2D of the ids, D2H of offsets + bytes inside the call)
@@ -296,7 +307,7 @@ def main_detok(args, w, rank, world, local_rank):
         "e2e": {"value": n_out / 1e6 / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": 4 * Bn * Sn, "d2h_bytes_per_step": 8 * Bn * Sn + n_out + 8 * Bn,
                 "ms_per_step": e2e_s * 1e3, "path": "b200tok_vocabdec_run with B200TOK_MEM_HOST on pinned buffers"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": algo / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s", "frac": algo / 1e9 / (ms / 1e3) / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": algo / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s", "frac": algo / 1e9 / (ms / 1e3) / peak, "traffic": profiled("c4", "step_dram_bytes"),
                      "kernel": "decode_len_kernel + cub scan + decode_copy_kernel (whole step)", "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},
         "cpu_baseline": {"value": n_out / 1e6 / cpu_s, "unit": "MB/s", "cores": 1, "kind": "port", "sample": "the full 1 Mi ids, mean of 3"},
     }))
@@ -374,6 +385,10 @@ def main_norm(args, w, rank, world, local_rank):
         torch.cuda.synchronize()
     launches = sum(o.launches for o in chain) - launches0
     assert got.value == n_out and bytes(oc[:n_out].cpu().numpy()) == bytes(ref[2])
+    if args.device_only:
+        sampler.stop()
+        print(json.dumps({"device_only": True, "steps": args.steps}))
+        return
     ms = sum(a.elapsed_time(b_) for a, b_ in ev) / args.steps
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -395,7 +410,7 @@ def main_norm(args, w, rank, world, local_rank):
         "e2e": {"value": N / 1e6 / e2e_s, "unit": "MB/s", "h2d_bytes_per_step": N + 8 * Bn, "d2h_bytes_per_step": n_out + 8 * Bn,
                 "ms_per_step": e2e_s * 1e3, "path": "b200tok_normalize_chain_run with B200TOK_MEM_HOST on pinned buffers"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": algo / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s", "frac": algo / 1e9 / (ms / 1e3) / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": algo / 1e9 / (ms / 1e3), "peak": peak, "unit": "GB/s", "frac": algo / 1e9 / (ms / 1e3) / peak, "traffic": profiled("norm", "step_dram_bytes"),
                      "kernel": "compose_kernel<lengths> + cub scan + compose_kernel<write> (whole step, host round trips included)",
                      "algorithmic_bytes_per_launch": algo, "peak_source": peak_src},
         "cpu_baseline": {"value": rows * Ln / 1e6 / cpu_s, "unit": "MB/s", "cores": 1, "kind": "port",
@@ -650,17 +665,28 @@ def main():
         algo_bytes = (n_bytes + 16 * db.n_rows + 4 * n_ids) // n_blocks     # per launch: N > 1 launches the kernel once per row block
         k_ms = statistics.mean(kernel_ms) if kernel_ms else None
         achieved = algo_bytes / 1e9 / (k_ms / 1e3) if k_ms else None
-        traffic = None
+        # ncu-measured DRAM traffic and warp-instruction counts of this workload's step (profiles/roofline_traffic.json, written by
+        # tools/step_metrics.py from an `ncu --metrics dram__bytes_*,smsp__inst_executed.sum` pass over `bench.py --device-only`)
+        traffic, prof = None, {}
         tp = ROOT / "profiles" / "roofline_traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get(args.workload)
+                prof = json.loads(tp.read_text()).get(args.workload) or {}
+                traffic = prof.get("kernel_dram_bytes")
             except Exception:
-                traffic = None
+                prof = {}
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                     "traffic": traffic, "kernel": pipe.dominant_kernel, "kernel_ms": k_ms,
                     "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                    "kernel_share_of_step": (k_ms * n_blocks / ms_per_step) if k_ms else None, "launches_per_step": n_blocks}
+                    "kernel_share_of_step": (k_ms * n_blocks / ms_per_step) if k_ms else None, "launches_per_step": n_blocks,
+                    "step_traffic": prof.get("step_dram_bytes"), "traffic_source": prof.get("source")}
+        if prof.get("kernel_warp_inst") and k_ms:
+            # the bound this integer kernel really runs against: one warp instruction per SM sub-partition per cycle
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            floor_ms = prof["kernel_warp_inst"] / (148 * 4) / sm_hz * 1e3
+            roofline["issue"] = {"warp_inst_per_launch": prof["kernel_warp_inst"], "warp_inst_per_input_byte": prof["kernel_warp_inst"] / n_bytes,
+                                 "issue_floor_ms": floor_ms, "frac_of_issue_peak": floor_ms / k_ms,
+                                 "note": "warp instructions (ncu smsp__inst_executed.sum) / (148 SMs x 4 schedulers x SM clock) over the kernel's event-timed duration"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             run, kind = cpu_runner(w)
