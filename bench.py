@@ -37,6 +37,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
+PULL_FROM_WORLD = 8      # N > 1 exchange: all-gatherv by pull from this many ranks on (16-bit wire), emit fused with peer stores below (measured)
+
 WORKLOADS = {
     "c1": dict(kind="bpe", vocab="gpt2_synth", rows=65536, row_bytes=512, gen="ascii",
                name="C1: gpt2-shaped byte-level BPE (50 257 vocab / 50 000 merges, synthetic stand-in gpt2_synth), "
@@ -475,8 +477,21 @@ def main():
     n_blocks = 1
     exchange = "single GPU"
     if world > 1:
-        mode = os.environ.get("B200TOK_BENCH_EXCHANGE", "peer")
+        mode = os.environ.get("B200TOK_BENCH_EXCHANGE", "auto")
+        if mode == "auto":      # measured (profiles/r02_bench_*_n8_*.json): pull wins from 8 ranks on when the ids fit the 16-bit wire
+            mode = "pull" if (world >= PULL_FROM_WORLD and len(pipe.assets.vocab) < 0xFFFF) else "peer"
         pg = None
+        if mode == "pull":
+            try:
+                from openvino_tokenizers_b200.sharded import PullGather
+                wire16 = len(pipe.assets.vocab) < 0xFFFF and os.environ.get("B200TOK_WIRE16", "auto") != "0"
+                pg = PullGather(db.n_rows, db.n_chars + (db.n_elems if pipe.kind != "bpe" else 0), dev, wire16=wire16)
+                exchange = ("row shards; all-gatherv by pull over NVLink peer memory: one-GPU tokenisation into peer-mapped source buffers, one "
+                            "symmetric-memory barrier, then every rank reads all peers with 16-byte loads and widens into its own i32 result"
+                            + (" (16-bit ids on the wire)" if wire16 else " (32-bit ids on the wire)"))
+            except Exception as ex:
+                print(f"[bench] pull exchange unavailable ({type(ex).__name__}: {ex}); trying the peer-store emit", file=sys.stderr)
+                mode = "peer"
         if mode == "peer":
             try:
                 from openvino_tokenizers_b200.sharded import PeerGather
@@ -577,6 +592,42 @@ def main():
     e2e_s = float(e2e_s.item()) / args.steps
     h2d = n_bytes + 8 * db.n_rows + 8 * db.n_elems
     d2h = 4 * n_ids + 8 * db.n_rows
+    e2e_path = "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"
+    e2e_local = None
+    if world > 1 and pg is not None:
+        # N > 1: the SAME job as `value` (tokenise the shard + all-gatherv on the devices), fed from and drained to pinned host buffers:
+        # H2D of the shard, the sharded step, then D2H of this rank's slot of the gathered ids and of the row extents of ALL ranks' rows
+        # (the host ends up with the whole gathered result across the ranks' buffers, every id crossing PCIe once)
+        e2e_local = {"value": n_bytes * world / 1e6 / e2e_s, "unit": "MB/s", "ms_per_step": e2e_s * 1e3,
+                     "path": "every rank's own b200tok_split_*_run host -> host, no exchange (the N = 1 path per rank)"}
+        g_rows = world * db.n_rows
+        h_gb, h_ge = torch.empty(g_rows, dtype=torch.int32).pin_memory(), torch.empty(g_rows, dtype=torch.int32).pin_memory()
+        slot0 = rank * pg.cap
+
+        def gathered_host_step():
+            for dst, src in zip((db.rb, db.re, db.begins, db.ends), hb[:4]):
+                dst.copy_(src, non_blocking=True)
+            db.chars[:n_bytes].copy_(hb[4], non_blocking=True)
+            pg.run(pipe, db)
+            n_mine = int(pg.n.item())                                   # (one synchronisation: the size of the id copy)
+            ho["ids"][:n_mine].copy_(pg.ids[slot0:slot0 + n_mine], non_blocking=True)
+            h_gb.copy_(pg.begins, non_blocking=True)
+            h_ge.copy_(pg.ends, non_blocking=True)
+            torch.cuda.synchronize()
+            return n_mine
+        for _ in range(2):
+            gathered_host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n_mine = gathered_host_step()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_s.item()) / args.steps
+        d2h = 4 * n_mine + 8 * g_rows
+        e2e_path = ("pinned host shard -> H2D -> tokenise + all-gatherv on the devices (the step `value` times) -> D2H of this rank's id slot "
+                    "and of all row extents; per-rank bytes")
+        n_host = pipe.run_host(hb, ho)       # (restore the plain host-path result for the checks below)
 
     # ---- the same host-to-host job through the SEPARATE ops (what an IR costs when the load-time fusion of the ov::Op shim is off, or
     # for split patterns it cannot fuse): RegexSplit host -> host, then BPETokenizer / WordpieceTokenizer host -> host; the piece
@@ -707,8 +758,8 @@ def main():
                        "l2": "256 MiB buffer zeroed between timed steps (L2 flush), outside the per-step event pair",
                        "multi_gpu": exchange},
             "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3, "path": "b200tok_split_*_run with B200TOK_MEM_HOST on pinned buffers"},
-            "e2e_unfused": unfused,
+                    "ms_per_step": e2e_s * 1e3, "path": e2e_path},
+            "e2e_no_exchange": e2e_local, "e2e_unfused": unfused,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "verified": verified,
         }))
     if world > 1:

@@ -212,6 +212,32 @@ B200TOK_API int b200tok_split_wordpiece_run_sharded(b200tok_handle split1, b200t
 /* wire16 only: after the barrier, widen this rank's staging copy (all world * rows_per_rank rows) into peers->ids[rank]. */
 B200TOK_API int b200tok_peer_expand_run(int device, const b200tok_peer_out* peers, void* cuda_stream);
 
+/* ---- The same all-gatherv by PULL (replaces the NCCL all-gatherv SURVEY 8e describes, like the calls above) ----------
+ * Every rank runs the ordinary b200tok_split_bpe_run / b200tok_split_wordpiece_run on its shard with `out` pointing into
+ * peer-mapped buffers (begins / ends / n_ids_device; ids too for the 32-bit wire), optionally packs the ids to 16 bits with
+ * b200tok_peer_pack_run, orders ONE cross-rank barrier on the stream, and then gathers with b200tok_peer_pull_run: 16-byte loads
+ * from every peer over NVLink, widened straight into the local i32 result.  Layout of the result = the calls above: rank p's rows
+ * in slot p (ids[p * slot_capacity ...], begins/ends[p * rows_per_rank + row], offsets shifted by p * slot_capacity).
+ * slot_capacity must be a multiple of 8; every source id buffer holds slot_capacity + 8 elements.                          */
+typedef struct {
+    int world, rank;
+    int wire16;                                       /* sources are src_ids16 (every id < 65 536), else src_ids */
+    int skip_self_ids;                                /* this rank's ids are already in place in ids[rank * slot_capacity ...] */
+    const uint16_t* src_ids16[B200TOK_MAX_PEERS];     /* peer-mapped, each [slot_capacity + 8] */
+    const int32_t* src_ids[B200TOK_MAX_PEERS];
+    const int32_t* src_begins[B200TOK_MAX_PEERS];     /* peer-mapped, each [rows_per_rank]; offsets relative to that rank's ids */
+    const int32_t* src_ends[B200TOK_MAX_PEERS];
+    const int64_t* src_total[B200TOK_MAX_PEERS];      /* peer-mapped: that rank's id count */
+    int32_t* ids;                                     /* local result [world * slot_capacity] */
+    int32_t* begins;                                  /* local result [world * rows_per_rank] */
+    int32_t* ends;
+    int64_t slot_capacity, rows_per_rank;
+} b200tok_peer_pull;
+/* ids[0 .. *n_ids_device) (device, i32; readable up to the next multiple of 8) -> ids16 (device, capacity + 8 elements). */
+B200TOK_API int b200tok_peer_pack_run(int device, const int32_t* ids, const int64_t* n_ids_device, int64_t capacity, uint16_t* ids16,
+                                      void* cuda_stream);
+B200TOK_API int b200tok_peer_pull_run(int device, const b200tok_peer_pull* pull, void* cuda_stream);
+
 /* ---- WordpieceTokenizer --------------------------------------------------------------------
  * inputs [5..7] vocab, [8] unk_token_id; attributes suffix_indicator / max_bytes_per_word
  * (src/wordpiece_tokenizer.hpp:41-45). */

@@ -90,6 +90,13 @@ class PeerOut(C.Structure):
                 ("ids_mc", C.c_void_p), ("begins_mc", C.c_void_p), ("ends_mc", C.c_void_p)]
 
 
+class PeerPull(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("wire16", C.c_int), ("skip_self_ids", C.c_int),
+                ("src_ids16", C.c_void_p * 8), ("src_ids", C.c_void_p * 8), ("src_begins", C.c_void_p * 8), ("src_ends", C.c_void_p * 8),
+                ("src_total", C.c_void_p * 8), ("ids", C.c_void_p), ("begins", C.c_void_p), ("ends", C.c_void_p),
+                ("slot_capacity", C.c_int64), ("rows_per_rank", C.c_int64)]
+
+
 def make_strings(triple, keep: list) -> Strings:
     """(begins, ends, chars) numpy triple -> Strings struct; arrays are appended to `keep` to stay alive."""
     if triple is None:
@@ -134,6 +141,8 @@ def lib():
         L.b200tok_last_kernel_ms.argtypes = [C.c_void_p]
         L.b200tok_last_kernel_ms.restype = C.c_float
         L.b200tok_vocabdec_max_chars.restype = C.c_int64
+        L.b200tok_peer_pack_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.b200tok_peer_pull_run.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.b200tok_vocabdec_max_chars.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
         _lib = L
     return _lib
@@ -149,6 +158,7 @@ EXPORTED_SYMBOLS = [
     "b200tok_set_timing", "b200tok_last_kernel_ms",
     "b200tok_regexsplit_create", "b200tok_regexsplit_run", "b200tok_specialsplit_create", "b200tok_specialsplit_run",
     "b200tok_bpe_create", "b200tok_bpe_run", "b200tok_split_bpe_run", "b200tok_split_bpe_run_sharded", "b200tok_peer_expand_run",
+    "b200tok_peer_pack_run", "b200tok_peer_pull_run",
     "b200tok_wordpiece_create", "b200tok_wordpiece_run", "b200tok_split_wordpiece_run", "b200tok_split_wordpiece_run_sharded",
     "b200tok_vocabenc_create", "b200tok_vocabenc_run",
     "b200tok_vocabdec_create", "b200tok_vocabdec_run", "b200tok_vocabdec_max_chars",

@@ -1121,6 +1121,42 @@ B200TOK_API int b200tok_split_wordpiece_run(b200tok_handle split1, b200tok_handl
     return run_rows(wp, call, in, out, nullptr, stream);
 }
 
+B200TOK_API int b200tok_peer_pack_run(int device, const int32_t* ids, const int64_t* n_ids_device, int64_t capacity, uint16_t* ids16, void* stream) {
+    if (!ids || !n_ids_device || !ids16 || capacity < 0) return fail(B200TOK_E_INVALID, "expected ids, their device count and a 16-bit staging buffer");
+    if ((reinterpret_cast<uintptr_t>(ids) | reinterpret_cast<uintptr_t>(ids16)) & 15) return fail(B200TOK_E_INVALID, "ids and ids16 must be 16-byte aligned");
+    DeviceGuard guard(device);
+    int sm = 0;
+    CU(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    peer_pack_kernel<<<sm * 8, 256, 0, (cudaStream_t)stream>>>(ids, n_ids_device, capacity, ids16);
+    CU(cudaGetLastError());
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_peer_pull_run(int device, const b200tok_peer_pull* q, void* stream) {
+    if (!q || q->world < 1 || q->world > B200TOK_MAX_PEERS || q->rank < 0 || q->rank >= q->world || !q->ids || !q->begins || !q->ends)
+        return fail(B200TOK_E_INVALID, "expected a peer layout (world 1..8) and local result buffers");
+    if (q->slot_capacity <= 0 || (q->slot_capacity & 7) || q->rows_per_rank <= 0 || (int64_t)q->world * q->slot_capacity >= (1ll << 31))
+        return fail(B200TOK_E_INVALID, "slot_capacity must be a positive multiple of 8 and world * slot_capacity must fit int32 offsets");
+    if (reinterpret_cast<uintptr_t>(q->ids) & 15) return fail(B200TOK_E_INVALID, "ids must be 16-byte aligned");
+    PeerPull Q{};
+    Q.world = q->world; Q.rank = q->rank; Q.wire16 = q->wire16 ? 1 : 0; Q.skip_self_ids = q->skip_self_ids ? 1 : 0;
+    for (int p = 0; p < q->world; ++p) {
+        const bool need_ids = !(Q.skip_self_ids && p == q->rank);
+        const void* src = Q.wire16 ? (const void*)q->src_ids16[p] : (const void*)q->src_ids[p];
+        if ((need_ids && !src) || !q->src_begins[p] || !q->src_ends[p] || !q->src_total[p]) return fail(B200TOK_E_INVALID, "missing source buffer of rank %d", p);
+        if (reinterpret_cast<uintptr_t>(src) & 15) return fail(B200TOK_E_INVALID, "source ids of rank %d must be 16-byte aligned", p);
+        Q.src16[p] = q->src_ids16[p]; Q.src32[p] = q->src_ids[p]; Q.src_begins[p] = q->src_begins[p]; Q.src_ends[p] = q->src_ends[p]; Q.src_total[p] = q->src_total[p];
+    }
+    Q.ids = q->ids; Q.begins = q->begins; Q.ends = q->ends; Q.slot_capacity = q->slot_capacity; Q.rows_per_rank = q->rows_per_rank;
+    DeviceGuard guard(device);
+    int sm = 0;
+    CU(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    static const int per_sm = [] { const char* e = getenv("B200TOK_PULL_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    peer_pull_kernel<<<sm * per_sm, 256, 0, (cudaStream_t)stream>>>(Q);
+    CU(cudaGetLastError());
+    return B200TOK_OK;
+}
+
 B200TOK_API int b200tok_split_wordpiece_run_sharded(b200tok_handle split1, b200tok_handle split2, b200tok_handle wordpiece,
                                                     const b200tok_ragged_strings* in, int32_t unk_token_id, const b200tok_peer_out* peers,
                                                     int64_t* n_ids_device, void* stream) {

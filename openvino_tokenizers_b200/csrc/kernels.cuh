@@ -1309,4 +1309,114 @@ __global__ void peer_expand_kernel(const uint16_t* staging, const int32_t* begin
 }
 __global__ void publish_total_kernel(const int32_t* status, int64_t* total_out) { if (total_out) *total_out = status[ST_TOTAL]; }
 
+// ---- all-gatherv by PULL over NVLink peer memory ------------------------------------------------------------
+// Every rank tokenises its shard with the ordinary one-GPU launch sequence into compact (begins, ends, ids); the ids are then
+// packed to 16 bits (when the vocabulary allows) into a peer-mapped staging buffer.  After ONE cross-rank barrier each rank reads the
+// staging buffers of all the others with 16-byte loads over NVLink and widens them straight into its own i32 result — the
+// transfer and the widening are one pass, the tokenizer kernel runs at its one-GPU speed, and nothing is ever stored remotely.
+struct PeerPull {
+    int world, rank, wire16, skip_self_ids;
+    const uint16_t* src16[8];
+    const int32_t* src32[8];
+    const int32_t* src_begins[8];
+    const int32_t* src_ends[8];
+    const int64_t* src_total[8];
+    int32_t *ids, *begins, *ends;          // this rank's gathered result: [world * slot_capacity], [world * rows_per_rank]
+    int64_t slot_capacity, rows_per_rank;
+};
+constexpr int kPullTile = 8192;            // ids per tile: 256 threads x 4 x 16-byte loads in flight (16-bit wire)
+
+__device__ __forceinline__ uint4 ld_peer16(const void* p) {      // L2-coherent 16-byte load (peer memory is never cached in L1)
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// i32 compact ids -> u16 staging (local pass right after the tokenizer: most of the ids are still in L2)
+__global__ void peer_pack_kernel(const int32_t* __restrict__ ids, const int64_t* __restrict__ n_dev, int64_t capacity, uint16_t* __restrict__ out) {
+    int64_t n = *n_dev;
+    if (n > capacity) n = capacity;
+    const int64_t n8 = (n + 7) >> 3;       // groups of 8 ids: two 16-byte loads, one 16-byte store (buffers are padded to a multiple of 8)
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n8; g += (int64_t)gridDim.x * blockDim.x) {
+        const int4 a = __ldcs(reinterpret_cast<const int4*>(ids) + 2 * g), b = __ldcs(reinterpret_cast<const int4*>(ids) + 2 * g + 1);
+        uint4 o;
+        o.x = (uint32_t)(a.x & 0xFFFF) | ((uint32_t)a.y << 16); o.y = (uint32_t)(a.z & 0xFFFF) | ((uint32_t)a.w << 16);
+        o.z = (uint32_t)(b.x & 0xFFFF) | ((uint32_t)b.y << 16); o.w = (uint32_t)(b.z & 0xFFFF) | ((uint32_t)b.w << 16);
+        reinterpret_cast<uint4*>(out)[g] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_pull_kernel(const PeerPull Q) {
+    __shared__ int64_t tot[8];
+    if (threadIdx.x < Q.world) {
+        int64_t t = *reinterpret_cast<const volatile int64_t*>(Q.src_total[threadIdx.x]);
+        tot[threadIdx.x] = t < 0 ? 0 : (t > Q.slot_capacity ? Q.slot_capacity : t);
+    }
+    __syncthreads();
+    // row extents of every slot (offsets shifted into the slot): B x 8 bytes per rank, spread over the grid
+    {
+        const int64_t R = Q.rows_per_rank, total_rows = R * Q.world;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_rows; i += (int64_t)gridDim.x * blockDim.x) {
+            const int p = (int)(i / R);
+            const int64_t r = i - (int64_t)p * R;
+            const int32_t shift = (int32_t)((int64_t)p * Q.slot_capacity);
+            Q.begins[i] = __ldcg(Q.src_begins[p] + r) + shift;
+            Q.ends[i] = __ldcg(Q.src_ends[p] + r) + shift;
+        }
+    }
+    // ids: tiles interleaved over the peers (consecutive CTAs read from different GPUs), starting with the next rank
+    const int npeer = Q.skip_self_ids ? Q.world - 1 : Q.world;
+    if (npeer <= 0) return;
+    int64_t maxt = 0;
+    for (int p = 0; p < Q.world; ++p) { const int64_t t = (tot[p] + kPullTile - 1) / kPullTile; maxt = t > maxt ? t : maxt; }
+    for (int64_t w = blockIdx.x; w < maxt * npeer; w += gridDim.x) {
+        const int j = (int)(w % npeer);
+        const int64_t tile = w / npeer;
+        const int p = (Q.rank + 1 + j) % Q.world;          // j = world - 1 is this rank itself (only without skip_self_ids)
+        const int64_t lo = tile * kPullTile;
+        if (lo >= tot[p]) continue;
+        int32_t* const dst = Q.ids + (int64_t)p * Q.slot_capacity + lo;
+        const int64_t left = tot[p] - lo;                  // ids of this tile (> 0); groups beyond it are not touched
+        if (Q.wire16) {
+            const uint16_t* const src = Q.src16[p] + lo;
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int g = threadIdx.x + 256 * u; if ((int64_t)g * 8 < left) v[u] = ld_peer16(src + 8 * g); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int g = threadIdx.x + 256 * u;
+                if ((int64_t)g * 8 < left) {
+                    int4 a, b;
+                    a.x = (int32_t)(v[u].x & 0xFFFFu); a.y = (int32_t)(v[u].x >> 16); a.z = (int32_t)(v[u].y & 0xFFFFu); a.w = (int32_t)(v[u].y >> 16);
+                    b.x = (int32_t)(v[u].z & 0xFFFFu); b.y = (int32_t)(v[u].z >> 16); b.z = (int32_t)(v[u].w & 0xFFFFu); b.w = (int32_t)(v[u].w >> 16);
+                    if ((int64_t)g * 8 + 8 <= left) {
+                        __stcs(reinterpret_cast<int4*>(dst + 8 * g), a);
+                        __stcs(reinterpret_cast<int4*>(dst + 8 * g) + 1, b);
+                    } else {                                // the slot's last, partial group: never write past the row data (the next slot starts there)
+                        const int32_t e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        for (int t = 0; t < 8; ++t) if ((int64_t)g * 8 + t < left) dst[8 * g + t] = e[t];
+                    }
+                }
+            }
+        } else {
+            const int32_t* const src = Q.src32[p] + lo;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                   // 8192 ids = 2 x (256 threads x 4 x 4 ids)
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int g = threadIdx.x + 256 * (u + 4 * h); if ((int64_t)g * 4 < left) v[u] = ld_peer16(src + 4 * g); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int g = threadIdx.x + 256 * (u + 4 * h);
+                    if ((int64_t)g * 4 + 4 <= left) __stcs(reinterpret_cast<uint4*>(dst + 4 * g), v[u]);
+                    else if ((int64_t)g * 4 < left) {
+                        const uint32_t e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                        for (int t = 0; t < 4; ++t) if ((int64_t)g * 4 + t < left) dst[4 * g + t] = (int32_t)e[t];
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace b200tok

@@ -126,11 +126,15 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
             }
             const uint32_t gor = g[0] | g[1] | g[2] | g[3];
             if (ballot_bits(gor, V7_AP)) {
+                // apostrophes are sparse: only the words that hold one evaluate the contraction forms (one ballot decides per word)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    int cl = 0;
-                    if (g[u] & V7_AP) cl = L3 ? llama3_contraction_len(B, w0 + 32 * u, nload) : gpt2_contraction_len(B, w0 + 32 * u, nload);
-                    const uint32_t bA2 = __ballot_sync(FULL, cl == 2), bA3 = __ballot_sync(FULL, cl == 3);
+                    uint32_t bA2 = 0u, bA3 = 0u;
+                    if (ballot_bits(g[u], V7_AP)) {
+                        int cl = 0;
+                        if (g[u] & V7_AP) cl = L3 ? llama3_contraction_len(B, w0 + 32 * u, nload) : gpt2_contraction_len(B, w0 + 32 * u, nload);
+                        bA2 = __ballot_sync(FULL, cl == 2); bA3 = __ballot_sync(FULL, cl == 3);
+                    }
                     if (lane == 0) { mm[M_A2 * kMStride + u] = bA2; mm[M_A3 * kMStride + u] = bA3; }
                 }
             } else if (lane < 4) { mm[M_A2 * kMStride + lane] = 0u; mm[M_A3 * kMStride + lane] = 0u; }
@@ -165,6 +169,7 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
             if (ballot_bits(gor, V7_WALK | V7_BAD)) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    if (!ballot_bits(g[u], V7_WALK | V7_BAD)) continue;      // (sparse, like the apostrophes)
                     const int w = w0 + 32 * u;
                     if (g[u] & V7_BAD) complex = true;
                     else if ((g[u] & V7_WALK) && w + 1 < nload) {        // could a longer token start here?  second-byte filter, then the walk
@@ -190,7 +195,7 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
                         if (r >= 0xFFFEu) r = r == 0xFFFFu ? kNoKey : __ldg(pair_rank + ((p << 8) | c[u]));
                     } else r = __ldg(pair_rank + ((p << 8) | c[u]));
                     fb = r != kNoKey;
-                    if (fb) S.key[w] = (r << kPackedBirthBits) | (uint32_t)w;
+                    S.key[w] = (r << kPackedBirthBits) | (uint32_t)w;      // (read only where fb: no branch around the store)
                 }
                 const uint32_t bF = __ballot_sync(FULL, fb);
                 if (lane == 0) mm[M_F * kMStride + u] = bF;

@@ -152,3 +152,86 @@ class PeerGather:
             dev_index = self.device.index if isinstance(self.device, torch.device) else int(self.device)
             K.check(K.lib().b200tok_peer_expand_run(int(dev_index or 0), C.byref(self._po), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return self.begins, self.ends, self.ids
+
+
+class PullGather:
+    """All-gatherv by PULL over NVLink peer memory.  Every rank tokenises its shard with the ordinary one-GPU call —
+    at its one-GPU speed, no remote stores inside the tokenizer kernel — into peer-mapped (torch symmetric memory) source buffers:
+    compact begins / ends / id count, and the ids packed to 16 bits when every id fits (`b200tok_peer_pack_run`), else the i32 ids
+    themselves.  After ONE symmetric-memory barrier on the stream, `b200tok_peer_pull_run` reads every peer's source buffers with
+    16-byte loads over NVLink and widens them straight into this rank's i32 result (transfer and widening are one pass).  The source
+    buffers are double-buffered, so the next step may overwrite them without a second barrier: a peer that still reads step k's
+    buffers has not yet arrived at the barrier of step k + 1, which this rank must pass before step k + 2 writes them again.
+    Result layout = allgather_ragged_slots / PeerGather: rank r's rows in slot r, offsets shifted by r * cap.  Equal shards per rank."""
+
+    def __init__(self, rows_per_rank: int, slot_capacity: int, device, group=None, wire16: bool = False):
+        import torch.distributed._symmetric_memory as symm
+        from . import _capi as K
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PullGather supports up to 8 ranks (one NVSwitch domain)")
+        self.rows, self.cap, self.wire16, self.device = int(rows_per_rank), (int(slot_capacity) + 7) & ~7, bool(wire16), device
+        self.dev_index = int((device.index if isinstance(device, torch.device) else device) or 0)
+        W, R, cap = self.world, self.rows, self.cap
+        self._stride = cap + 8                                     # ids per parity of the source buffer (padded: sources are read in groups of 8)
+        self._src_be = symm.empty(4 * R, dtype=torch.int32, device=device)          # [parity][begins | ends][rows]
+        self._src_tot = symm.empty(2, dtype=torch.int64, device=device)             # [parity]
+        self._src_ids = symm.empty(2 * self._stride, dtype=torch.int16 if self.wire16 else torch.int32, device=device)
+        self._src_tot.zero_()
+        self._h = [symm.rendezvous(t, self.group) for t in (self._src_be, self._src_tot, self._src_ids)]
+        self.ids = torch.empty(W * cap + 8, dtype=torch.int32, device=device)       # the gathered result (local memory only)
+        self.begins = torch.empty(W * R, dtype=torch.int32, device=device)
+        self.ends = torch.empty(W * R, dtype=torch.int32, device=device)
+        self.step = 0
+        self.multicast = False
+        self._pull = []
+        esz = 2 if self.wire16 else 4
+        for par in (0, 1):
+            q = K.PeerPull()
+            q.world, q.rank, q.wire16, q.skip_self_ids = W, self.rank, int(self.wire16), int(self.wire16)
+            q.slot_capacity, q.rows_per_rank = cap, R
+            q.ids, q.begins, q.ends = self.ids.data_ptr(), self.begins.data_ptr(), self.ends.data_ptr()
+            for p in range(W):
+                be, tot, ids = (int(h.buffer_ptrs[p]) for h in self._h)
+                q.src_begins[p] = be + 4 * (2 * par) * R
+                q.src_ends[p] = be + 4 * (2 * par + 1) * R
+                q.src_total[p] = tot + 8 * par
+                if self.wire16:
+                    q.src_ids16[p] = ids + esz * par * self._stride
+                else:
+                    q.src_ids[p] = ids + esz * par * self._stride
+            self._pull.append(q)
+
+    @property
+    def n(self):
+        """This rank's id count of the last step (device int64[1])."""
+        return self._src_tot[(self.step - 1) & 1:((self.step - 1) & 1) + 1]
+
+    def run(self, pipe, db):
+        """pipe: runtime.TokenizerPipeline; db: runtime.DeviceBatch of this rank's shard (db.n_rows == rows_per_rank).  Asynchronous on the
+        current torch stream; returns (begins, ends, ids) of the gathered result held by this rank."""
+        import ctypes as C
+        from . import _capi as K
+        if db.n_rows != self.rows:
+            raise ValueError("PullGather: every rank passes rows_per_rank rows")
+        par = self.step & 1
+        self.step += 1
+        R, cap = self.rows, self.cap
+        L = K.lib()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rin = K.RaggedStrings(db.rb.data_ptr(), db.re.data_ptr(), db.n_rows, db.begins.data_ptr(), db.ends.data_ptr(), db.n_elems,
+                              db.chars.data_ptr(), db.n_chars, None, K.MEM_DEVICE)
+        be, tot = self._src_be.data_ptr(), self._src_tot.data_ptr() + 8 * par
+        if self.wire16:      # the i32 ids go straight to their final place (this rank's slot of its own result); peers read the packed copy
+            ids_ptr = self.ids.data_ptr() + 4 * self.rank * cap
+        else:
+            ids_ptr = self._src_ids.data_ptr() + 4 * par * self._stride
+        out = K.RaggedIds(be + 4 * (2 * par) * R, be + 4 * (2 * par + 1) * R, ids_ptr, cap, 0, tot, K.MEM_DEVICE)
+        pipe._call(rin, out, st)
+        if self.wire16:
+            K.check(L.b200tok_peer_pack_run(self.dev_index, C.c_void_p(ids_ptr), C.c_void_p(tot), C.c_int64(cap),
+                                            C.c_void_p(self._src_ids.data_ptr() + 2 * par * self._stride), st))
+        self._h[0].barrier(channel=0)       # every rank's source buffers of this step are complete and visible after this
+        K.check(L.b200tok_peer_pull_run(self.dev_index, C.byref(self._pull[par]), st))
+        return self.begins, self.ends, self.ids

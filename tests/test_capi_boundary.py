@@ -67,7 +67,8 @@ def test_ctypes_mirrors_match_the_header_layout(K, tmp_path):
     pairs = [("b200tok_strings", K.Strings), ("b200tok_ragged_strings", K.RaggedStrings), ("b200tok_ragged_strings_out", K.RaggedStringsOut),
              ("b200tok_ragged_ids", K.RaggedIds), ("b200tok_regexsplit_desc", K.RegexSplitDesc), ("b200tok_bpe_desc", K.BpeDesc),
              ("b200tok_wordpiece_desc", K.WordpieceDesc), ("b200tok_vocabenc_desc", K.VocabEncDesc), ("b200tok_vocabdec_desc", K.VocabDecDesc),
-             ("b200tok_decoded", K.Decoded), ("b200tok_ragged_i32", K.RaggedI32), ("b200tok_post_desc", K.PostDesc), ("b200tok_peer_out", K.PeerOut)]
+             ("b200tok_decoded", K.Decoded), ("b200tok_ragged_i32", K.RaggedI32), ("b200tok_post_desc", K.PostDesc), ("b200tok_peer_out", K.PeerOut),
+             ("b200tok_peer_pull", K.PeerPull)]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "b200tok.h"\nint main(void) {\n' +
                    "".join(f'  printf("%zu\\n", sizeof({c}));\n' for c, _ in pairs) + "  return 0;\n}\n")

@@ -589,6 +589,49 @@ def test_sharded_peer_store_emit_world1(ops, gpt2):
             dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("wire16", [True, False], ids=["wire16", "wire32"])
+def test_sharded_pull_gather_world1(ops, gpt2, wire16):
+    """sharded.PullGather (all-gatherv by pull: b200tok_peer_pack_run + b200tok_peer_pull_run) on a one-rank group, several steps
+    (both parities of the double-buffered source buffers): compact rows, equal to the ordinary path, inside the rank's slot."""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from openvino_tokenizers_b200 import runtime as R
+    from openvino_tokenizers_b200.sharded import PullGather
+    own = not dist.is_initialized()
+    if own:
+        with socket.socket() as s_:
+            s_.bind(("127.0.0.1", 0))
+            port = s_.getsockname()[1]
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        dev = torch.device("cuda", 0)
+        pipe = R.TokenizerPipeline("bpe", "gpt2_synth")
+        rng = np.random.default_rng(18)
+        pgs = {}
+        for step, n_rows in enumerate((3000, 3000, 3000, 41)):
+            strings = [bytes(rng.integers(0x20, 0x7F, size=int(n), dtype=np.uint8)) for n in rng.integers(0, 900, size=n_rows)]
+            if n_rows > 100:
+                strings[17 + step] = b"x" * 2000                          # a piece longer than a window: giant path
+            batch = cases.batch_from_strings(strings)
+            exp = ops.split_bpe(gpt2["split"], gpt2["bpe"], list(batch))
+            db = R.to_device(batch, dev)
+            cap = 3000 * 900 + 4096
+            pg = pgs.setdefault(n_rows, PullGather(db.n_rows, cap, dev, wire16=wire16))
+            b, e, ids = pg.run(pipe, db)
+            torch.cuda.synchronize()
+            assert int(pg.n.item()) == len(exp[2])
+            gb, ge, gi = b.cpu().numpy(), e.cpu().numpy(), ids.cpu().numpy()
+            assert np.array_equal(gb, exp[0]) and np.array_equal(ge, exp[1])       # rank 0's slot starts at 0: the compact offsets themselves
+            assert np.array_equal(gi[: len(exp[2])], exp[2])
+    finally:
+        if own:
+            dist.destroy_process_group()
+
+
 @pytest.mark.parametrize("vocab,pattern", [("gpt2", "llama3"), ("llama3", "gpt2"), ("gpt2", "gpt2_digits")])
 def test_fast_kernel_every_instantiation(ops, oracle_mod, gpt2, llama3, vocab, pattern):
     """The dedicated kernel is instantiated per (id width, split pattern): cross the vocabularies and patterns so that
@@ -771,7 +814,7 @@ def test_sharded_exchange_two_ranks():
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                             "--master-port", "29577", str(root / "tools" / "peer_gather_check.py"), "8192"], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        assert "on every rank: True" in r.stdout, r.stdout[-2000:]
+        assert "on every rank: True" in r.stdout, r.stdout[-2000:]       # (covers the peer-store emit and the pull gather, both wire widths)
 
 
 @pytest.mark.parametrize("env", [{"B200TOK_TMA": "1"}, {"B200TOK_TMA": "2"}, {"B200TOK_SLOT_ALLOC": "1"}, {"B200TOK_ORDERED_EMIT": "1"}, {"B200TOK_GRAPHS": "0"}],
