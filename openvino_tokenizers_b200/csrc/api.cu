@@ -200,8 +200,12 @@ struct BpeObj : b200tok_object {
 struct WordpieceObj : b200tok_object {
     HostWordpiece h;
     DBuf<RankNode> root_nodes, sub_nodes;
-    DBuf<int32_t> root_first, sub_first;
-    WordpieceTables view() const { return WordpieceTables{RankTrie{root_nodes.p, root_first.p}, RankTrie{sub_nodes.p, sub_first.p}, h.max_bytes}; }
+    DBuf<int32_t> root_first, sub_first, root_val1, sub_val1;
+    DBuf<RankJump> root_jump, sub_jump;
+    WordpieceTables view() const {
+        return WordpieceTables{RankTrie{root_nodes.p, root_first.p, h.root.rank_jump.empty() ? nullptr : root_jump.p, root_val1.p},
+                               RankTrie{sub_nodes.p, sub_first.p, h.sub.rank_jump.empty() ? nullptr : sub_jump.p, sub_val1.p}, h.max_bytes};
+    }
 };
 struct VocabEncObj : b200tok_object {
     HostVocabEnc h;
@@ -1089,6 +1093,9 @@ B200TOK_API int b200tok_wordpiece_create(const b200tok_wordpiece_desc* d, b200to
     CU(o->cls.upload());
     CU(o->root_nodes.upload(o->h.root.rank_nodes)); CU(o->root_first.upload(o->h.root.rank_root));
     CU(o->sub_nodes.upload(o->h.sub.rank_nodes)); CU(o->sub_first.upload(o->h.sub.rank_root));
+    CU(o->root_val1.upload(o->h.root.rank_val1)); CU(o->sub_val1.upload(o->h.sub.rank_val1));
+    if (!o->h.root.rank_jump.empty()) CU(o->root_jump.upload(o->h.root.rank_jump));
+    if (!o->h.sub.rank_jump.empty()) CU(o->sub_jump.upload(o->h.sub.rank_jump));
     CU(cudaDeviceSynchronize());
     *out = o.release();
     return B200TOK_OK;

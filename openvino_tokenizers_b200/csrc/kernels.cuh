@@ -776,12 +776,32 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
     const uint32_t lt = (1u << lane) - 1u;
     int head = 0, s = 0, e = 0, i = 0, n = 0, best = 0;
     int32_t node = -1, found = -1;
-    bool have = false, sub = false;
+    bool have = false, sub = false, jumped = false;
     {   // every slot starts dead (position-parallel); the lanes then write tokens only
         const int send = S.seg[ns] & POS_MASK;
         for (int w = lane; w < send; w += 32) bp.ids[w] = -1;
         __syncwarp();
     }
+    // Start of a longest-match walk at position q of the lane's word (tok_core.cuh rank_trie_longest): words of one byte take their
+    // token from val1, ASCII starts read the two-byte jump table (the first two trie steps in ONE load), anything else starts at the root.
+    auto start_walk = [&](const RankTrie& t, int q) {
+        found = -1; best = q; jumped = false;
+        const uint32_t b0 = B[q];
+        if (e - q == 1 && t.val1) {
+            found = __ldg(t.val1 + b0);
+            best = q + 1; i = q + 1; node = -1;
+        } else if (e - q >= 2 && t.jump2 && ((b0 | B[q + 1]) & 0x80u) == 0u) {
+            const uint2 j = __ldg(reinterpret_cast<const uint2*>(t.jump2) + ((b0 << 7) | B[q + 1]));
+            if (!(j.y & kJumpHas1)) { node = -1; i = q; }
+            else {
+                found = (int32_t)(j.y & 0xFFFFFFu) - 1;
+                best = q + (int)((j.y >> 24) & 3u);
+                i = q + 2;
+                node = i < e ? (int32_t)j.x : -1;
+                jumped = true;
+            }
+        } else { i = q; node = t.root_child[b0]; }
+    };
     while (head < ns || __any_sync(0xFFFFFFFFu, have)) {
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
         if (!have) {
@@ -794,18 +814,21 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
                 } else if (e - s > T.max_bytes || e <= s) {                  // :100-103 (and the zero-length word, see tok_core.cuh)
                     bp.ids[s] = P.unk_id;
                 } else {
-                    have = true; sub = false; n = 0; i = s; best = s; found = -1;
-                    node = T.root.root_child[B[s]];
+                    have = true; sub = false; n = 0;
+                    start_walk(T.root, s);
                 }
             }
         }
         head += __popc(need);
         if (have) {
             if (node >= 0) {                                              // one step of the longest-match walk
-                ++i;
                 const RankNode& nd = (sub ? T.sub.nodes : T.root.nodes)[node];
-                const int32_t v = nd.value;
-                if (v != -1) { found = v; best = i; }
+                if (!jumped) {
+                    ++i;
+                    const int32_t v = nd.value;
+                    if (v != -1) { found = v; best = i; }
+                }
+                jumped = false;
                 if (i >= e) node = -1;
                 else {
                     const uint32_t ch = B[i], wd = ch >> 5, bit = ch & 31u;
@@ -822,7 +845,7 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
                 else {
                     bp.ids[s + n++] = found;
                     if (best >= e) done = true;
-                    else { sub = true; i = best; found = -1; node = T.sub.root_child[B[best]]; }
+                    else { sub = true; start_walk(T.sub, best); }
                 }
                 if (done) have = false;
             }

@@ -316,6 +316,26 @@ void HostTrie::build_rank() {
     }
     rank_root.assign(256, -1);
     for (int b = 0; b < 256; ++b) if (root_child[(size_t)b] >= 0) rank_root[(size_t)b] = newid[(size_t)root_child[(size_t)b]];
+    // one-byte values and the two-byte jump table (tok_core.cuh RankJump): the first two steps of every walk, precomputed
+    rank_val1.assign(256, -1);
+    rank_jump.assign(128 * 128, RankJump{-1, 0u});
+    for (int b0 = 0; b0 < 256; ++b0) {
+        const int32_t n1 = rank_root[(size_t)b0];
+        if (n1 < 0) continue;
+        const int32_t v1 = rank_nodes[(size_t)n1].value;
+        rank_val1[(size_t)b0] = v1;
+        if (b0 >= 128) continue;
+        for (int b1 = 0; b1 < 128; ++b1) {
+            RankJump& j = rank_jump[(size_t)(b0 * 128 + b1)];
+            const int32_t n2 = rank_child(rank_nodes[(size_t)n1], (uint32_t)b1);
+            int32_t found = v1;
+            uint32_t len = v1 != -1 ? 1u : 0u;
+            if (n2 >= 0 && rank_nodes[(size_t)n2].value != -1) { found = rank_nodes[(size_t)n2].value; len = 2u; }
+            j.node2 = n2;
+            j.info = kJumpHas1 | (len << 24) | (uint32_t)((found + 1) & 0xFFFFFF);
+        }
+    }
+    if (value.size() >= (1u << 24) - 2) rank_jump.clear();      // (values must fit 24 bits; never the case for a tokenizer vocabulary)
 }
 
 static std::string str_at(const b200tok_strings& s, int64_t i) {

@@ -36,9 +36,10 @@ struct HostTrie {
     size_t n_nodes() const { return value.size(); }
     // the same trie in rank-indexed form (breadth-first numbering: a node's children are consecutive)
     std::vector<RankNode> rank_nodes;
-    std::vector<int32_t> rank_root;
+    std::vector<int32_t> rank_root, rank_val1;
+    std::vector<RankJump> rank_jump;
     void build_rank();
-    RankTrie rank_view() const { return RankTrie{rank_nodes.data(), rank_root.data()}; }
+    RankTrie rank_view() const { return RankTrie{rank_nodes.data(), rank_root.data(), rank_jump.empty() ? nullptr : rank_jump.data(), rank_val1.data()}; }
 };
 
 struct HostBpe {

@@ -904,9 +904,17 @@ B2_HD int bpe_merge_heap(const MergeTable& M, int n, int32_t* sym_id, int32_t* s
 // index of its first child (children are numbered consecutively, in byte order), so one step is one round of independent
 // loads — bitmap word, prefix count, base, value — instead of a binary search over an edge list.
 struct RankNode { uint32_t bits[8]; int32_t base; int32_t value; uint8_t cum[8]; };      // 48 bytes
+// Two-byte jump table of a RankTrie (ASCII pairs only, 128 x 128 entries): what the first TWO steps of a walk starting with the
+// bytes (b0, b1) find — node2 = the node after both bytes (-1 if none), and the longest valued node on the way (0, 1 or 2 bytes
+// long) — so a walk starts with ONE table read instead of the root lookup and two dependent node loads, and a word of up to two
+// bytes needs no node at all.  val1[b] = value of the root's child for byte b (one-byte words).
+struct RankJump { int32_t node2; uint32_t info; };      // info: bit 31 root child exists | bits 24-25 length of the best value | bits 0-23 value + 1
+constexpr uint32_t kJumpHas1 = 0x80000000u;
 struct RankTrie {
     const RankNode* nodes;
     const int32_t* root_child;   // [256] child of the root per byte, -1 if none
+    const RankJump* jump2;       // [128 * 128] or nullptr
+    const int32_t* val1;         // [256] or nullptr
 };
 B2_HD int32_t rank_popc(uint32_t x) {
 #if defined(__CUDA_ARCH__)
@@ -915,20 +923,39 @@ B2_HD int32_t rank_popc(uint32_t x) {
     return __builtin_popcount(x);
 #endif
 }
+B2_HD int32_t rank_child(const RankNode& nd, uint32_t ch) {
+    const uint32_t w = ch >> 5, bit = ch & 31u;
+    const uint32_t bw = nd.bits[w];
+    return ((bw >> bit) & 1u) ? nd.base + (int32_t)nd.cum[w] + rank_popc(bw & ((1u << bit) - 1u)) : -1;
+}
 // Longest match starting at s[idx] (same contract as trie_longest).
 B2_HD int32_t rank_trie_longest(const RankTrie& t, const uint8_t* s, int& idx, int end) {
-    int32_t node = t.root_child[s[idx]];
-    int32_t found = -1;
+    int32_t node, found = -1;
     int best = idx, i = idx;
+    bool jumped = false;
+    if (t.jump2 && end - idx >= 2 && ((s[idx] | s[idx + 1]) & 0x80) == 0) {
+        const RankJump j = t.jump2[((uint32_t)s[idx] << 7) | s[idx + 1]];
+        if (!(j.info & kJumpHas1)) return -1;
+        found = (int32_t)(j.info & 0xFFFFFFu) - 1;
+        best = idx + (int)((j.info >> 24) & 3u);
+        i = idx + 2;
+        node = i < end ? j.node2 : -1;            // (the value of node2 is already in `found`)
+        jumped = true;
+    } else if (t.val1 && end - idx == 1) {
+        found = t.val1[s[idx]];
+        if (found >= 0) ++idx;
+        return found;
+    } else node = t.root_child[s[idx]];
     while (node >= 0) {
-        ++i;
         const RankNode& nd = t.nodes[node];
-        const int32_t v = nd.value;
-        if (v != -1) { found = v; best = i; }
+        if (!jumped) {
+            ++i;
+            const int32_t v = nd.value;
+            if (v != -1) { found = v; best = i; }
+        }
+        jumped = false;
         if (i >= end) break;
-        const uint32_t ch = s[i], w = ch >> 5, bit = ch & 31u;
-        const uint32_t bw = nd.bits[w];
-        node = ((bw >> bit) & 1u) ? nd.base + (int32_t)nd.cum[w] + rank_popc(bw & ((1u << bit) - 1u)) : -1;
+        node = rank_child(nd, s[i]);
     }
     idx = best;
     return found;

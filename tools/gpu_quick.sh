@@ -11,3 +11,10 @@ for wl in $WLS; do
   timeout 600 ncu --metrics $M --clock-control none -c 400 --csv --log-file gpurun_out/stepmetrics_${wl}_$TAG.csv python bench.py --workload $wl --steps 2 --warmup 3 --device-only > gpurun_out/b_ncu3_$TAG.log 2>&1
   python tools/step_metrics.py gpurun_out/stepmetrics_${wl}_$TAG.csv | tail -12
 done
+if [ -n "$EXTRA" ]; then
+  for wl in c4 norm; do
+    timeout 600 ncu --metrics $M --clock-control none -c 400 --csv --log-file gpurun_out/stepmetrics_${wl}_$TAG.csv python bench.py --workload $wl --steps 2 --warmup 3 --device-only > gpurun_out/b_ncu3_$TAG.log 2>&1
+    python tools/step_metrics.py gpurun_out/stepmetrics_${wl}_$TAG.csv | tail -8
+  done
+  echo "== pcie duplex probe"; timeout 120 python tools/pcie_duplex_probe.py 2>&1 | tail -4 | tee gpurun_out/pcie_duplex_$TAG.txt
+fi
