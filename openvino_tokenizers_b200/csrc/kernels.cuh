@@ -765,25 +765,60 @@ __device__ __forceinline__ uint32_t v7_below(int limit, int base) {
     return r >= 32 ? FULL : r > 0 ? ((1u << r) - 1u) : 0u;
 }
 
-// WordPiece for all kept segments (words) of a window: one lane per word, longest-match trie walks.
+// WordPiece for all kept segments (words) of a window (src/wordpiece_tokenizer.cpp:96-130, tok_core.cuh wordpiece_word).
+//   pass A, one lane per word, no loop per word: dropped segments stay dead, over-long / empty words become [unk], ONE-byte words
+//           take their token from val1, TWO-byte ASCII words are settled by the two-byte jump table (+ val1 of the ## trie when only
+//           the first byte matched) — on split text most words end here (every punctuation mark is a word of its own);
+//   pass B, the remaining words: a per-lane state machine driven by a warp work queue — every iteration performs ONE trie step for
+//           whatever word a lane holds, and a lane that finishes its word takes the next one, so words of different lengths do not
+//           idle the rest of the warp; every walk starts from the jump table (its first two steps in one load).
 __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowParams& P, int lane, int ns, bool whole) {
-    // The word loop of src/wordpiece_tokenizer.cpp:96-130 (tok_core.cuh wordpiece_word) flattened into a per-lane state machine
-    // driven by a warp work queue: every iteration performs ONE trie step for whatever word a lane holds, and a lane that
-    // finishes its word takes the next one — words of different lengths no longer idle the rest of the warp.
     auto& bp = S.u.bp;
     const uint8_t* B = S.B();
     const WordpieceTables& T = P.wp;
     const uint32_t lt = (1u << lane) - 1u;
-    int head = 0, s = 0, e = 0, i = 0, n = 0, best = 0;
-    int32_t node = -1, found = -1;
-    bool have = false, sub = false, jumped = false;
+    uint16_t* const queue = reinterpret_cast<uint16_t*>(bp.key);           // word indices of pass B (WordPiece has no merge keys)
     {   // every slot starts dead (position-parallel); the lanes then write tokens only
         const int send = S.seg[ns] & POS_MASK;
         for (int w = lane; w < send; w += 32) bp.ids[w] = -1;
         __syncwarp();
     }
-    // Start of a longest-match walk at position q of the lane's word (tok_core.cuh rank_trie_longest): words of one byte take their
-    // token from val1, ASCII starts read the two-byte jump table (the first two trie steps in ONE load), anything else starts at the root.
+    const bool tables = T.root.val1 && T.sub.val1 && T.root.jump2;
+    int nq = 0;
+    for (int j0 = 0; j0 < ns; j0 += 32) {
+        const int j = j0 + lane;
+        bool later = false;
+        if (j < ns) {
+            const uint16_t sg = S.seg[j];
+            const int s = sg & POS_MASK, e = S.seg[j + 1] & POS_MASK;
+            if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
+                // dropped segment: its slots stay dead
+            } else if (e - s > T.max_bytes || e <= s) {                      // :100-103 (and the zero-length word, see tok_core.cuh)
+                bp.ids[s] = P.unk_id;
+            } else if (tables && e - s == 1) {
+                const int32_t v = __ldg(T.root.val1 + B[s]);
+                bp.ids[s] = v >= 0 ? v : P.unk_id;
+            } else if (tables && e - s == 2 && ((B[s] | B[s + 1]) & 0x80u) == 0u) {
+                const uint2 jp = __ldg(reinterpret_cast<const uint2*>(T.root.jump2) + (((uint32_t)B[s] << 7) | B[s + 1]));
+                const int len = (int)((jp.y >> 24) & 3u);
+                const int32_t v = (int32_t)(jp.y & 0xFFFFFFu) - 1;
+                if (len == 2) bp.ids[s] = v;
+                else {
+                    const int32_t v2 = len == 1 ? __ldg(T.sub.val1 + B[s + 1]) : -1;      // first byte a token: the second must be a ## token
+                    if (v2 >= 0) { bp.ids[s] = v; bp.ids[s + 1] = v2; } else bp.ids[s] = P.unk_id;
+                }
+            } else later = true;
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, later);
+        if (later) queue[nq + __popc(m & lt)] = (uint16_t)j;
+        nq += __popc(m);
+    }
+    __syncwarp();
+    if (nq == 0) return;
+    int head = 0, s = 0, e = 0, i = 0, n = 0, best = 0;
+    int32_t node = -1, found = -1;
+    bool have = false, sub = false, jumped = false;
+    // Start of a longest-match walk at position q of the lane's word (tok_core.cuh rank_trie_longest)
     auto start_walk = [&](const RankTrie& t, int q) {
         found = -1; best = q; jumped = false;
         const uint32_t b0 = B[q];
@@ -802,21 +837,15 @@ __device__ __forceinline__ void wordpiece_window_pieces(WarpSmem& S, const RowPa
             }
         } else { i = q; node = t.root_child[b0]; }
     };
-    while (head < ns || __any_sync(0xFFFFFFFFu, have)) {
+    while (head < nq || __any_sync(0xFFFFFFFFu, have)) {
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
         if (!have) {
-            const int j = head + __popc(need & lt);
-            if (j < ns) {
-                const uint16_t sg = S.seg[j];
-                s = sg & POS_MASK; e = S.seg[j + 1] & POS_MASK;
-                if (!(whole || seg_kept(sg, P.spec.pat, P.mode, P.invert))) {
-                    // dropped segment: its slots stay dead
-                } else if (e - s > T.max_bytes || e <= s) {                  // :100-103 (and the zero-length word, see tok_core.cuh)
-                    bp.ids[s] = P.unk_id;
-                } else {
-                    have = true; sub = false; n = 0;
-                    start_walk(T.root, s);
-                }
+            const int qi = head + __popc(need & lt);
+            if (qi < nq) {
+                const int j = queue[qi];
+                s = S.seg[j] & POS_MASK; e = S.seg[j + 1] & POS_MASK;
+                have = true; sub = false; n = 0;
+                start_walk(T.root, s);
             }
         }
         head += __popc(need);
@@ -1070,11 +1099,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
                         int32_t* outp = P.tmp_a + base + emitted;
                         const uint32_t ltm = (1u << lane) - 1u;
                         int n_out = 0;
-                        for (int w = lane; w - lane < send; w += 32) {
-                            const int32_t tok = w < send ? S.u.bp.ids[w] : -1;
-                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, tok >= 0);
-                            if (tok >= 0) outp[n_out + __popc(m & ltm)] = tok;
-                            n_out += __popc(m);
+                        for (int w = lane; w - lane < send; w += 128) {       // four words in flight
+                            int32_t tok[4];
+                            uint32_t m[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) tok[u] = (w + 32 * u) < send ? S.u.bp.ids[w + 32 * u] : -1;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(0xFFFFFFFFu, tok[u] >= 0);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (tok[u] >= 0) outp[n_out + __popc(m[u] & ltm)] = tok[u];
+                                n_out += __popc(m[u]);
+                            }
                         }
                         emitted += n_out;
                     }
