@@ -367,14 +367,15 @@ int launch_chunk(b200tok_object* owner, const RowCall& call, ChunkLaunch& c, cud
         const bool peer_fast = c.peers != nullptr;        // sharded: the fast kernel stores into every rank's slot, no compaction follows
         // everything else: in-order single-pass emit — the kernel writes the compact (begins, ends, ids) itself
         const bool ordered = fast_ordered;
-        static bool fast_attr[12][64] = {};
+        static bool fast_attr[16][64] = {};
         const size_t fsm = narrow ? fast_smem_bytes<uint16_t>() : fast_smem_bytes<int32_t>();
-        const int mode = ordered ? 1 : ((peer_fast || tma_env == 0) ? 2 : 0);
+        const int mode = ordered ? 1 : peer_fast ? 3 : (tma_env == 0 ? 2 : 0);
         auto pick = [&](auto narrow_c, auto l3_c) -> const void* {
             using IdT = std::conditional_t<decltype(narrow_c)::value, uint16_t, int32_t>;
             constexpr int CT = decltype(narrow_c)::value ? 5 : 4;
             constexpr bool L3 = decltype(l3_c)::value;
-            return mode == 1 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 1> : mode == 2 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 2> : (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 0>;
+            return mode == 1 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 1> : mode == 2 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 2>
+                 : mode == 3 ? (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 3> : (const void*)gpt2_bpe_fast_kernel<IdT, CT, L3, 0>;
         };
         const void* fn = narrow ? (l3 ? pick(std::true_type{}, std::true_type{}) : pick(std::true_type{}, std::false_type{}))
                                 : (l3 ? pick(std::false_type{}, std::true_type{}) : pick(std::false_type{}, std::false_type{}));

@@ -50,10 +50,14 @@ struct NoHook {       // fast_window calls hook.after_pass1() / after_pass3(): p
     __device__ __forceinline__ void after_pass1() {}
     __device__ __forceinline__ void after_pass3() {}
 };
-template <class IdT, bool L3, class Hook>
-__device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32,
-                                           const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
-                                           bool ascii, const uint8_t* B, Hook& hook) {
+// ASCII is a template parameter, not a flag: the all-ASCII and the general form of a window are two straight-line instruction streams
+// (fast_window below picks one per window), so a workload runs in the instruction-cache footprint of the one it needs — the kernel is
+// ~80 KB of code and `no_instruction` was its top stall on mixed UTF-8 (profiles/r02_fast_kernel_c3_ncu_full.txt).
+template <class IdT, bool L3, bool ASCII, class Hook>
+__device__ __forceinline__ int fast_window_t(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32,
+                                             const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
+                                             const uint8_t* B, Hook& hook) {
+    constexpr bool ascii = ASCII;
     const uint32_t lt = (1u << lane) - 1u;
     const int lb = off < LBK ? off : LBK;           // look-back bytes staged before the window (off = window start - element start)
     ClassTables T = P.cls;
@@ -409,6 +413,14 @@ __device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P,
     return send;
 }
 
+
+template <class IdT, bool L3, class Hook>
+__device__ __forceinline__ int fast_window(FastSmem<IdT>& S, const RowParams& P, const uint32_t* lut32,
+                                           const uint8_t* ascii_smem, int lane, int wlen, int end_rel, int nload, int off,
+                                           bool ascii, const uint8_t* B, Hook& hook) {
+    return ascii ? fast_window_t<IdT, L3, true, Hook>(S, P, lut32, ascii_smem, lane, wlen, end_rel, nload, off, B, hook)
+                 : fast_window_t<IdT, L3, false, Hook>(S, P, lut32, ascii_smem, lane, wlen, end_rel, nload, off, B, hook);
+}
 
 // Stage the bytes of one window (+ look-back / look-ahead) into shared memory; returns true if every byte is ASCII.
 template <class IdT>
@@ -826,7 +838,8 @@ __device__ __forceinline__ void slot_rows(FastSmem<IdT>& S, const RowParams& P, 
     if (inflight) mbar_wait(&S.mbar[buf ^ 1], (par >> (buf ^ 1)) & 1u);      // no copy may be in flight when the CTA retires
 }
 
-// MODE 0: row slots + TMA-prefetched input (one GPU); 1: in-order single-pass emit (opt-in); 2: sharded, ids stored into every rank's buffers
+// MODE 0: row slots + TMA-prefetched input (opt-in); 1: in-order single-pass emit (opt-in); 2: row slots, plain loop (the default);
+// 3: the loop of 2 with the sharded emit — ids stored into every rank's buffers (kept out of the one-GPU kernel's instruction stream)
 template <class IdT, int CTAS, bool L3, int MODE>
 __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(const __grid_constant__ RowParams P, int32_t* __restrict__ redo_rows) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -887,7 +900,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
                     if (base + emitted + send > P.tmp_cap) {
                         if (lane == 0) atomicOr(&P.status[ST_ERROR], ERR_TMP_OVERFLOW);
                     } else {
-                        const int nP = P.peer.world;                  // > 0: sharded output, store into every rank's slot
+                        const int nP = MODE == 3 ? P.peer.world : 0;  // > 0: sharded output, store into every rank's slot
                         const int64_t o0 = (nP ? (int64_t)P.peer.rank * P.peer.slot_capacity : 0) + base + emitted;
                         int32_t* outp = P.tmp_a + o0;
                         int n_out = 0;
@@ -962,9 +975,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, CTAS) gpt2_bpe_fast_kernel(cons
             }
             if (lane == 0) {
                 if (redo) redo_rows[atomicAdd(&P.status[ST_NREDO], 1)] = row;
-                else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = (sizeof(IdT) == 2 && !P.peer.world) ? 4 : 0; }      // bit 2: 16-bit slot
+                else { P.row_ext[row] = emitted; P.row_cnt[row] = emitted; P.row_flag[row] = (sizeof(IdT) == 2 && MODE != 3) ? 4 : 0; }      // bit 2: 16-bit slot
             }
-            if (P.peer.world && !redo) {                       // sharded: publish the row's extent to every rank
+            if (MODE == 3 && P.peer.world && !redo) {          // sharded: publish the row's extent to every rank
                 const int64_t o0 = (int64_t)P.peer.rank * P.peer.slot_capacity + base;
                 if (P.peer.begins_mc) {
                     if (lane == 0) {
