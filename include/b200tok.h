@@ -139,6 +139,10 @@ typedef struct {
 B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* desc, b200tok_handle* out);
 B200TOK_API int b200tok_regexsplit_run(b200tok_handle h, const b200tok_ragged_strings* in,
                                        b200tok_ragged_strings_out* out, void* cuda_stream);
+/* Legacy 9-input form (src/regex_split.cpp:102-113, 164-178, 231-238: inputs [6..8] = skip-token strings): elements equal to one of
+ * `tokens` pass through unsplit (no skip flag is produced; the form has 5 outputs).  Call once after create, like the reference builds
+ * its set on the first evaluate(); an empty list leaves the set unset.  Excludes the `skips` tensor of the 7-input form. */
+B200TOK_API int b200tok_regexsplit_set_skip_tokens(b200tok_handle h, const b200tok_strings* tokens);
 
 /* ---- SpecialTokensSplit ---------------------------------------------------------------------
  * replaces SpecialTokensSplit::evaluate (src/special_tokens_split.cpp:61-162); pattern = input [5|6], the alternation of

@@ -156,7 +156,7 @@ def check(rc: int):
 EXPORTED_SYMBOLS = [
     "b200tok_version", "b200tok_last_error", "b200tok_device_count", "b200tok_destroy", "b200tok_launch_count",
     "b200tok_set_timing", "b200tok_last_kernel_ms",
-    "b200tok_regexsplit_create", "b200tok_regexsplit_run", "b200tok_specialsplit_create", "b200tok_specialsplit_run",
+    "b200tok_regexsplit_create", "b200tok_regexsplit_run", "b200tok_regexsplit_set_skip_tokens", "b200tok_specialsplit_create", "b200tok_specialsplit_run",
     "b200tok_bpe_create", "b200tok_bpe_run", "b200tok_split_bpe_run", "b200tok_split_bpe_run_sharded", "b200tok_peer_expand_run",
     "b200tok_peer_pack_run", "b200tok_peer_pull_run",
     "b200tok_wordpiece_create", "b200tok_wordpiece_run", "b200tok_split_wordpiece_run", "b200tok_split_wordpiece_run_sharded",

@@ -167,6 +167,12 @@ namespace {
 
 struct SplitObj : b200tok_object {
     HostSplit h;
+    // legacy 9-input form (src/regex_split.cpp:164-178, 231-238): elements equal to one of these strings pass through unsplit.
+    // The set is an exact-match string table (the VocabEncoder one: FNV-1a + full key compare), value 1, default 0.
+    bool has_skip_tokens = false;
+    HostVocabEnc skip_h;
+    DBuf<VocabEncSlot> skip_slots;
+    DBuf<uint8_t> skip_keys;
     // PAT_VM: the compiled program and the general-category tables on the device
     DBuf<VmInst> vm_code; DBuf<VmSet> vm_sets; DBuf<uint32_t> vm_ranges; DBuf<uint16_t> gc1; DBuf<uint8_t> gc2;
     SplitSpec dev_spec() const {
@@ -195,7 +201,7 @@ struct BpeObj : b200tok_object {
     DBuf<int32_t> rank_newid;
     DBuf<uint32_t> pair_rank, pair_bits;
     DBuf<uint8_t> suffix;
-    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p}, pair_bits.p, h.newid_base}; }
+    BpeTables view() const { return BpeTables{byte_sym.p, byte_miss.p, pair_rank.p, trie.view(), MergeTable{slots.p, h.mask, rank_newid.p, h.n_duplicate_products > 0 ? 1 : 0}, pair_bits.p, h.newid_base}; }
 };
 struct WordpieceObj : b200tok_object {
     HostWordpiece h;
@@ -492,7 +498,7 @@ int run_rows_host_pipelined(b200tok_object* owner, const RowCall& call, const b2
                             RowParams P, int per_elem_extra, int64_t tmp_cap) {
     RowWorkspace& w = owner->ws;
     const int64_t B = in->n_rows, E = in->n_elems, N = in->n_chars;
-    if (N < (8 << 20) || B < 1024 || E > 4 * B + 1024 || in->skips) return 1;
+    if (N < (8 << 20) || B < 1024 || E > 4 * B + 1024 || in->skips || (call.split && call.split->has_skip_tokens)) return 1;
     // qualify: rows contiguous, elements increasing and non-overlapping (what StringTensorUnpack / RegexSplit produce)
     const int32_t *rb = in->ragged_begins, *re = in->ragged_ends, *eb = in->begins, *ee = in->ends;
     if (rb[0] != 0 || re[B - 1] != E) return 1;
@@ -585,7 +591,7 @@ int run_rows_host_pipelined(b200tok_object* owner, const RowCall& call, const b2
             ++next_out;
             const int32_t* hs = w.h_pipe + 16 * k;
             if (result == B200TOK_OK) {
-                if (hs[ST_ERROR] & (ERR_GIANT_LIST | ERR_GIANT_POOL)) result = 1;          // rare: let the single-shot path size the resources
+                if (hs[ST_ERROR] & (ERR_GIANT_LIST | ERR_GIANT_POOL | ERR_HEAP_TIE)) result = 1;      // rare: let the single-shot path size the resources / report
                 else if (hs[ST_ERROR]) result = fail(B200TOK_E_INVALID, "row slots overflowed: overlapping or unordered input elements are not supported");
                 else if (off + hs[ST_TOTAL] > out->capacity) result = fail(B200TOK_E_CAPACITY, "output capacity %lld is smaller than the result", (long long)out->capacity);
             }
@@ -746,6 +752,15 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
     } else {
         d_rb = in->ragged_begins; d_re = in->ragged_ends; d_b = in->begins; d_e = in->ends; d_c = in->chars; d_sk = in->skips;
     }
+    if (call.split && call.split->has_skip_tokens && E) {
+        // legacy skip tokens: flag the elements that equal one (they pass through like skip-flagged ones, src/regex_split.cpp:235-238)
+        if (d_sk) return fail(B200TOK_E_INVALID, "RegexSplit: skip tokens (9-input form) and a skips tensor (7-input form) exclude each other");
+        CU(w.skips.ensure(E));
+        vocab_lookup_kernel<uint8_t><<<(unsigned)((E + 255) / 256), 256, 0, st>>>(d_b, d_e, d_c, E, call.split->skip_slots.p, call.split->skip_h.mask,
+                                                                                   call.split->skip_keys.p, 0, w.skips.p);
+        ++owner->launches;
+        d_sk = w.skips.p;
+    }
     P.rb = d_rb; P.re = d_re; P.n_rows = (int32_t)B; P.begins = d_b; P.ends = d_e; P.chars = d_c; P.skips = d_sk;
 
     CU(w.row_cap.ensure(B)); CU(w.row_base.ensure(B)); CU(w.row_ext.ensure(B)); CU(w.row_cnt.ensure(B)); CU(w.row_flag.ensure(B));
@@ -852,6 +867,9 @@ int run_rows(b200tok_object* owner, const RowCall& call, const b200tok_ragged_st
             if (err & ERR_GIANT_LIST) w.pool_bytes = std::max<size_t>(w.pool_bytes, 80ull * (size_t)tmp_cap + (1u << 20));
             continue;
         }
+        if (err & ERR_HEAP_TIE)
+            return fail(B200TOK_E_UNSUPPORTED, "BPE: a merge met its own product on both sides (tokens produced by more than one merge): the reference's result "
+                        "depends on std::priority_queue's heap layout there, which only the fused GPT-2 / Llama-3 split + BPE path reproduces");
         if (err & ERR_TMP_OVERFLOW) {
             if (total > out_cap) return fail(B200TOK_E_CAPACITY, "output capacity %lld is smaller than the result (%lld elements)", (long long)out_cap, (long long)total);
             return fail(B200TOK_E_INVALID, "row slots overflowed: overlapping or unordered input elements are not supported");
@@ -940,6 +958,26 @@ B200TOK_API int b200tok_regexsplit_create(const b200tok_regexsplit_desc* d, b200
     }
     CU(cudaDeviceSynchronize());
     *out = o.release();
+    return B200TOK_OK;
+}
+
+B200TOK_API int b200tok_regexsplit_set_skip_tokens(b200tok_handle h, const b200tok_strings* tokens) {
+    SplitObj* s = as<SplitObj>(h, K_SPLIT);
+    if (!s || !tokens) return fail(B200TOK_E_INVALID, "expected a RegexSplit handle and the skip-token strings");
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (tokens->n == 0) { s->has_skip_tokens = false; return B200TOK_OK; }      // src/regex_split.cpp:166: an empty list leaves the set unset
+    std::vector<int32_t> ones((size_t)tokens->n, 1);
+    b200tok_vocabenc_desc d{};
+    d.keys = *tokens; d.values = ones.data(); d.values_are_i64 = 0; d.device = s->device;
+    std::string err;
+    HostVocabEnc hv;
+    if (int rc = build_vocabenc(d, hv, err)) return fail(rc, "%s", err.c_str());
+    DeviceGuard g(s->device);
+    s->skip_h = std::move(hv);
+    CU(s->skip_slots.upload(s->skip_h.slots));
+    CU(s->skip_keys.upload(s->skip_h.key_bytes));
+    CU(cudaDeviceSynchronize());
+    s->has_skip_tokens = true;
     return B200TOK_OK;
 }
 

@@ -34,7 +34,7 @@ enum : int { OP_BPE = 0, OP_WORDPIECE = 1, OP_SPLIT = 2, OP_SPECIAL = 3 };
 enum : int { ST_ERROR = 0, ST_NGIANT = 1, ST_TICKET = 2, ST_TOTAL = 3, ST_BASE = 4, ST_POOL_NEED_HI = 5, ST_NREDO = 6, ST_TICKET2 = 7, ST_MINREDO = 8, ST_TICKET3 = 9,
              ST_ALLOC = 32,        // the slot allocator: in its own 128-byte line — it and the ticket counter are both hit once per row
              ST_WORDS = 64 };      // (a multiple of 32 words: consecutive status blocks keep the two counters in separate lines)
-enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4 };
+enum : int { ERR_TMP_OVERFLOW = 1, ERR_GIANT_LIST = 2, ERR_GIANT_POOL = 4, ERR_HEAP_TIE = 8 };
 
 struct GiantItem { int32_t row, begin, end, slot; };
 
@@ -578,7 +578,9 @@ __device__ __noinline__ void bpe_window_serial(WarpSmem& S, const BpeTables& BT,
         int c = 0;
         if (whole || seg_kept(sg, P.spec.pat, P.mode, P.invert)) {
             const int n = bpe_symbolize(BT, S.B(), s, e, bp.ids + s);
-            c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, n);
+            bool tie = false;
+            c = bpe_merge_packed(BT.merges, bp.ids + s, bp.key + s, n, BT.merges.tie_check ? &tie : nullptr);
+            if (tie) atomicOr(&P.status[ST_ERROR], ERR_HEAP_TIE);      // (see bpe_merge_queue)
         }
         for (int t = s + c; t < e; ++t) bp.ids[t] = -1;
     }
@@ -647,18 +649,27 @@ __device__ __forceinline__ void bpe_merge_queue(WarpSmem& S, const BpeTables& BT
             while (pp >= 0 && bp.ids[s + pp] < 0) --pp;
             int nr = bk + 1;
             while (nr < n0 && bp.ids[s + nr] < 0) ++nr;
+            bool fl = false;
             if (pl > 0) {
                 live -= (bp.key[s + pl] != kNoKey);
                 uint32_t kk = kNoKey;
                 int32_t r, v;
-                if (pp >= 0 && merge_find(BT.merges, bp.ids[s + pp], nid, r, v)) { kk = ((uint32_t)r << kPackedBirthBits) | birth; ++live; }
+                fl = pp >= 0 && merge_find(BT.merges, bp.ids[s + pp], nid, r, v);
+                if (fl) { kk = ((uint32_t)r << kPackedBirthBits) | birth; ++live; }
                 bp.key[s + pl] = kk;
             }
             if (nr < n0) {
                 live -= (bp.key[s + nr] != kNoKey);
                 uint32_t kk = kNoKey;
                 int32_t r, v;
-                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) { kk = ((uint32_t)r << kPackedBirthBits) | birth; ++live; }
+                if (merge_find(BT.merges, nid, bp.ids[s + nr], r, v)) {
+                    kk = ((uint32_t)r << kPackedBirthBits) | birth; ++live;
+                    // The merge found its own product on both sides (only with tokens that several merges produce): the two new pairs tie
+                    // on (rank, seq) and the reference pops them in std::priority_queue's heap order.  This loop takes the left pair; the
+                    // call reports the tie (B200TOK_E_UNSUPPORTED) instead of returning a result that may differ.  (Rows of the fused
+                    // GPT-2 / Llama-3 path never get here with such a tie: they are redone exactly, rows_kernel `fits`.)
+                    if (BT.merges.tie_check && fl && bp.ids[s + pp] == nid && bp.ids[s + nr] == nid) atomicOr(&P.status[ST_ERROR], ERR_HEAP_TIE);
+                }
                 bp.key[s + nr] = kk;
             }
             if (live == 0) have = false;                      // nothing left to merge in this segment
@@ -963,7 +974,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 4) rows_kernel(const __grid_con
                 const int wlen = end_rel < WIN ? end_rel : WIN;
                 int ns = 0, advance = 0;
                 bool keys_ready = false, complex_win = false;
-                const bool fits = !(whole && end_rel > WIN) && !(OP == OP_BPE && P.suffix_len > 0);
+                // BPE with an end_suffix, and the rows the fast kernel handed back under a vocabulary whose merges can tie in the
+                // reference's queue (MergeTable::tie_check — the row may have met such a tie): every piece takes the exact heap form
+                // (giant_bpe_kernel: std::priority_queue's pop order restated).
+                const bool fits = !(whole && end_rel > WIN) && !(OP == OP_BPE && (P.suffix_len > 0 || (listed && P.bpe.merges.tie_check)));
                 if (fits) {
                     const int nload = end_rel < wlen + LA ? end_rel : wlen + LA;
                     const int lb = (pos - eb) < LBK ? (pos - eb) : LBK;   // look-back bytes available inside the element

@@ -365,7 +365,7 @@ __device__ __forceinline__ int fast_window_t(FastSmem<IdT>& S, const RowParams& 
                 s = S.act()[qi];
                 const int e = next_bit(S.segbits, s, send), n = e - s;
                 if (n > 32) {                                           // a run longer than the 32-bit masks: serial loop over the whole segment
-                    const int c = bpe_merge_packed(MT, S.ids + s, S.key + s, n);
+                    const int c = bpe_merge_packed(MT, S.ids + s, S.key + s, n, MT.tie_check ? &complex : nullptr);
                     for (int t = s + c; t < e; ++t) S.ids[t] = S.kDead;
                 } else {
                     const uint32_t mask = n == 32 ? FULL : ((1u << n) - 1u);
@@ -394,16 +394,23 @@ __device__ __forceinline__ int fast_window_t(FastSmem<IdT>& S, const RowParams& 
             ++merges;
             const uint32_t birth = (uint32_t)(WIN + merges);
             const uint32_t below = alive & ((1u << pl) - 1u);
+            bool fl = false;
             if (below) {
                 int32_t r, v;
-                if (merge_find(MT, (int32_t)S.ids[s + 31 - __clz(below)], nid, r, v)) { S.key[s + pl] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << pl; }
+                fl = merge_find(MT, (int32_t)S.ids[s + 31 - __clz(below)], nid, r, v);
+                if (fl) { S.key[s + pl] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << pl; }
             }
             const uint32_t above = alive & ~((2u << bk) - 1u);
             if (above) {
                 const int nr = __ffs(above) - 1;
                 km &= ~(1u << nr);
                 int32_t r, v;
-                if (merge_find(MT, nid, (int32_t)S.ids[s + nr], r, v)) { S.key[s + nr] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << nr; }
+                if (merge_find(MT, nid, (int32_t)S.ids[s + nr], r, v)) {
+                    S.key[s + nr] = ((uint32_t)r << kPackedBirthBits) | birth; km |= 1u << nr;
+                    // the merge found its own product on both sides: the two new pairs tie on (rank, seq) and the reference pops them in
+                    // heap order — the row goes to the exact path (only vocabularies with doubly produced tokens get here)
+                    if (MT.tie_check && fl && (int32_t)S.ids[s + 31 - __clz(below)] == nid && (int32_t)S.ids[s + nr] == nid) complex = true;
+                }
             }
             if (!km) have = false;
         }

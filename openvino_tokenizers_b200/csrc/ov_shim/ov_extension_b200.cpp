@@ -69,7 +69,7 @@ inline void ragged_ids_out(ov::TensorVector& out, const ov::TensorVector& in, in
 
 struct Handle {   // shared by clones, like the reference's shared_ptr<BPETokenizerImpl> (src/bpe_tokenizer.hpp:215-218)
     b200tok_handle h = nullptr;
-    std::once_flag once;
+    std::once_flag once, once2;
     ~Handle() { b200tok_destroy(h); }
 };
 
@@ -82,8 +82,8 @@ public:
         : ov::op::Op(args), m_behaviour(behaviour), m_invert(invert), m_max_splits(max_splits) { constructor_validate_and_infer_types(); }
     void validate_and_infer_types() override {
         const auto n = get_input_size();
-        OPENVINO_ASSERT(n == 6 || n == 7, "Incorrect number of inputs passed to RegexSplit: ", n,
-                        " (the legacy 9-input skip-token form is not supported by the B200 path)");
+        OPENVINO_ASSERT(n == 6 || n == 7 || n == 9, "Incorrect number of inputs passed to RegexSplit: ", n,
+                        "; try to reconvert tokenizer with newer version of OpenVINO Tokenizers");      // src/regex_split.cpp:102
         for (size_t i = 0; i < 4; ++i) set_output_type(i, ov::element::i32, i < 2 ? get_input_partial_shape(0) : ov::PartialShape{ov::Dimension()});
         set_output_type(4, ov::element::u8, ov::PartialShape{ov::Dimension()});
         if (n == 7) set_output_type(5, get_input_element_type(5), get_input_partial_shape(5));
@@ -105,6 +105,11 @@ public:
         const bool has_skips = in.size() == 7;
         const auto& pt = in[5 + has_skips];
         ensure(pt.data<const char>(), pt.get_size());
+        if (in.size() == 9 && in[6].get_size() > 0)                       // legacy skip tokens, set once (src/regex_split.cpp:164-178)
+            std::call_once(m_state->once2, [&] {
+                const b200tok_strings toks = strings_of(in, 6);
+                check(b200tok_regexsplit_set_skip_tokens(m_state->h, &toks));
+            });
         const size_t cap = in[4].get_size() + in[2].get_size();          // src/regex_split.cpp:182
         out[0].set_shape(in[0].get_shape());
         out[1].set_shape(in[1].get_shape());
@@ -795,6 +800,7 @@ inline std::shared_ptr<RegexSplit> producing_split(const ov::OutputVector& outs,
     for (size_t i = 0; i < 5; ++i)
         if (outs[i].get_node() != rs.get() || outs[i].get_index() != i) return nullptr;
     const size_t n = rs->get_input_size();
+    if (n == 9) return nullptr;      // the legacy skip-token form stays a layer of its own
     auto pc = std::dynamic_pointer_cast<ov::op::v0::Constant>(rs->input_value(n - 1).get_node_shared_ptr());
     if (!pc || (rs->behaviour() != "isolate" && rs->behaviour() != "remove") || rs->max_splits() != -1) return nullptr;
     pattern.assign(static_cast<const char*>(pc->get_data_ptr()), pc->get_byte_size());

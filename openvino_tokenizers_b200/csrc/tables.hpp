@@ -58,7 +58,7 @@ struct HostBpe {
     int64_t n_duplicate_products = 0;   // merges whose product token another merge also produces (tie hazard)
     bool bytes_only = false;            // every byte symbolises without a trie walk
     BpeTables view() const {
-        return BpeTables{byte_sym.data(), byte_miss.data(), pair_rank.data(), trie.view(), MergeTable{slots.data(), mask, rank_newid.data()}, pair_bits.data(), newid_base};
+        return BpeTables{byte_sym.data(), byte_miss.data(), pair_rank.data(), trie.view(), MergeTable{slots.data(), mask, rank_newid.data(), n_duplicate_products > 0 ? 1 : 0}, pair_bits.data(), newid_base};
     }
 };
 // returns B200TOK_OK or an error code (message in err)

@@ -638,6 +638,10 @@ struct MergeTable {
     const MergeSlot* slots;
     uint32_t mask;
     const int32_t* rank_newid;   // [n_merges] token produced by the merge of that rank
+    // != 0: some token is the product of more than one merge, so two queue entries can tie on (rank, seq) — when a merge finds its
+    // own product on BOTH sides.  The mask-based and packed merge loops report that (they break such a tie left pair first); the row
+    // is then redone by bpe_merge_heap, which pops ties exactly like the reference's std::priority_queue.
+    int32_t tie_check;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -789,7 +793,7 @@ constexpr uint32_t kNoKey = 0xFFFFFFFFu;
 constexpr int kPackedBirthBits = 12;
 constexpr int kPackedMaxSymbols = 2048;
 template <class IdT>
-B2_HD int bpe_merge_packed(const MergeTable& M, IdT* ids, uint32_t* key, int n) {
+B2_HD int bpe_merge_packed(const MergeTable& M, IdT* ids, uint32_t* key, int n, bool* tie = nullptr) {
     if (n < 2) return n;
     bool any = false;
     for (int k = 0; k + 1 < n; ++k) {
@@ -813,54 +817,68 @@ B2_HD int bpe_merge_packed(const MergeTable& M, IdT* ids, uint32_t* key, int n) 
         for (int k = bk + 1; k + 2 < n; ++k) key[k] = key[k + 1];
         --n;
         ++seq;
+        bool fl = false, fr = false;
         if (bk > 0) {
             int32_t r, v;
-            const bool f = merge_find(M, (int32_t)ids[bk - 1], (int32_t)ids[bk], r, v);
-            key[bk - 1] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
+            fl = merge_find(M, (int32_t)ids[bk - 1], (int32_t)ids[bk], r, v);
+            key[bk - 1] = fl ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
         }
         if (bk + 1 < n) {
             int32_t r, v;
-            const bool f = merge_find(M, (int32_t)ids[bk], (int32_t)ids[bk + 1], r, v);
-            key[bk] = f ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
+            fr = merge_find(M, (int32_t)ids[bk], (int32_t)ids[bk + 1], r, v);
+            key[bk] = fr ? (((uint32_t)r << kPackedBirthBits) | (uint32_t)seq) : kNoKey;
         }
+        if (tie && fl && fr && ids[bk - 1] == ids[bk] && ids[bk + 1] == ids[bk]) *tie = true;      // both new pairs are (x, x): equal (rank, seq)
     }
     return n;
 }
 
-// Heap form of the same loop for very long pieces: O(n log n), state in caller-provided scratch.
+// Heap form of the same loop: O(n log n), state in caller-provided scratch.
 //   sym_id/prev/next : [2n]   (dead symbols have id == -1 after being merged)
 //   heap             : [3n] entries (at most n-1 initial pushes + 2 per merge)
-// Ties on (rank, birth) are broken left pair first (only reachable with duplicate vocab strings,
-// SURVEY App. B item 1).  Returns the token count; tokens are written to out[0..count).
+// This is the EXACT form of the reference's loop (src/bpe_tokenizer.cpp:262-327), heap included: entries with equal (rank, seq) —
+// reachable only when two merges produce the same token, SURVEY App. B item 1 — are popped in the order libstdc++'s
+// std::priority_queue would pop them, because heap_push / heap_pop below are std::push_heap / std::pop_heap operation for operation
+// (bits/stl_heap.h __push_heap / __adjust_heap) under the reference's CompareRank (:166-172).  Vocabularies with such merges run every
+// row that meets the tie through this function (MergeTable::tie_check); checked against std::priority_queue itself in the CPU tier.
+// Returns the token count; tokens are written to out[0..count).
 struct HeapEntry { int32_t rank, birth, a, b; };
-B2_HD bool heap_less(const HeapEntry& x, const HeapEntry& y) {
-    if (x.rank != y.rank) return x.rank < y.rank;
-    if (x.birth != y.birth) return x.birth < y.birth;
-    return x.a < y.a;
+B2_HD bool heap_comp(const HeapEntry& x, const HeapEntry& y) {      // CompareRank: "x sits below y"
+    return x.rank != y.rank ? x.rank > y.rank : x.birth > y.birth;
 }
-B2_HD void heap_push(HeapEntry* h, int& n, HeapEntry e) {
-    int i = n++;
-    while (i > 0) {
-        const int p = (i - 1) >> 1;
-        if (!heap_less(e, h[p])) break;
-        h[i] = h[p];
-        i = p;
+B2_HD void heap_sift_up(HeapEntry* h, int hole, int top, const HeapEntry& v) {      // std::__push_heap
+    int parent = (hole - 1) / 2;
+    while (hole > top && heap_comp(h[parent], v)) {
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
     }
-    h[i] = e;
+    h[hole] = v;
 }
-B2_HD HeapEntry heap_pop(HeapEntry* h, int& n) {
+B2_HD void heap_push(HeapEntry* h, int& n, HeapEntry e) {      // c.push_back(e); std::push_heap(c.begin(), c.end(), comp)
+    heap_sift_up(h, n, 0, e);
+    ++n;
+}
+B2_HD HeapEntry heap_pop(HeapEntry* h, int& n) {               // top(); std::pop_heap(c.begin(), c.end(), comp); c.pop_back()
     const HeapEntry top = h[0];
-    const HeapEntry last = h[--n];
-    int i = 0;
-    for (;;) {
-        int c = 2 * i + 1;
-        if (c >= n) break;
-        if (c + 1 < n && heap_less(h[c + 1], h[c])) ++c;
-        if (!heap_less(h[c], last)) break;
-        h[i] = h[c];
-        i = c;
+    if (n > 1) {
+        const HeapEntry v = h[n - 1];
+        const int len = n - 1;                                  // std::__adjust_heap(first, 0, len, v)
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (heap_comp(h[child], h[child - 1])) --child;
+            h[hole] = h[child];
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            h[hole] = h[child - 1];
+            hole = child - 1;
+        }
+        heap_sift_up(h, hole, 0, v);
     }
-    if (n > 0) h[i] = last;
+    --n;
     return top;
 }
 B2_HD int bpe_merge_heap(const MergeTable& M, int n, int32_t* sym_id, int32_t* sym_prev, int32_t* sym_next,

@@ -98,7 +98,8 @@ def _ids_out(n_rows, capacity):
 
 
 class RegexSplit(_Handle):
-    """RegexSplit(behaviour, invert, max_splits); inputs: ragged strings [0..4], optional skips [5], pattern."""
+    """RegexSplit(behaviour, invert, max_splits); inputs: ragged strings [0..4], optional skips [5], pattern; legacy form:
+    ragged strings [0..4], pattern [5], skip-token strings [6..8] (src/regex_split.cpp:98-113)."""
 
     def __init__(self, behaviour="remove", invert=False, max_splits=-1, device=0):
         super().__init__()
@@ -117,11 +118,22 @@ class RegexSplit(_Handle):
         self._ensure(pattern.encode() if isinstance(pattern, str) else pattern)
         return self
 
+    def with_skip_tokens(self, tokens):
+        """Legacy 9-input form: `tokens` = (begins, ends, chars) of the skip-token strings (inputs [6..8])."""
+        keep = []
+        st = K.make_strings(tokens, keep)
+        K.check(K.lib().b200tok_regexsplit_set_skip_tokens(self._h, C.byref(st)))
+        self._skip_tokens_set = True
+        return self
+
     def evaluate(self, inputs):
-        if len(inputs) not in (6, 7):
-            raise ValueError("Incorrect number of inputs passed to RegexSplit: %d" % len(inputs))
+        if len(inputs) not in (6, 7, 9):
+            raise ValueError("Incorrect number of inputs passed to RegexSplit: %d; try to reconvert tokenizer with newer version of "
+                             "OpenVINO Tokenizers" % len(inputs))
         has_skips = len(inputs) == 7
         self._ensure(_u8(inputs[5 + has_skips]).tobytes())
+        if len(inputs) == 9 and not getattr(self, "_skip_tokens_set", False) and len(inputs[6]) > 0:      # src/regex_split.cpp:166
+            self.with_skip_tokens((inputs[6], inputs[7], inputs[8]))
         keep = []
         rin = _ragged_in(*inputs[:5], skips=inputs[5] if has_skips else None, keep=keep)
         n_rows, cap = rin.n_rows, rin.n_chars + rin.n_elems

@@ -81,6 +81,24 @@ HZ int64_t hz_bpe_piece(void* h, const uint8_t* bytes, int64_t n, int mode, int3
     return cnt;
 }
 
+// The packed-key loop with its tie report (MergeTable::tie_check): returns the count, *tie = 1 if a merge found its own product on both sides.
+HZ int64_t hz_bpe_piece_tie(void* h, const uint8_t* bytes, int64_t n, int32_t* out, int32_t* tie) {
+    auto* b = (HzBpe*)h;
+    std::string s((const char*)bytes, (size_t)n);
+    s += b->t.end_suffix;
+    const BpeTables T = b->t.view();
+    const int L = (int)s.size();
+    std::vector<int32_t> ids(2 * L + 2);
+    std::vector<uint32_t> key(L + 2);
+    const int m = bpe_symbolize(T, (const uint8_t*)s.data(), 0, L, ids.data());
+    if (m > kPackedMaxSymbols) return -1;
+    bool t = false;
+    const int cnt = bpe_merge_packed(T.merges, ids.data(), key.data(), m, T.merges.tie_check ? &t : nullptr);
+    std::memcpy(out, ids.data(), (size_t)cnt * 4);
+    *tie = t ? 1 : 0;
+    return cnt;
+}
+
 struct HzWp { HostWordpiece t; };
 HZ void* hz_wp_create(const b200tok_wordpiece_desc* d) {
     auto h = std::make_unique<HzWp>();

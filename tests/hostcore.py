@@ -75,6 +75,17 @@ class HostBpe:
         return out[:n].tolist()
 
 
+    def piece_packed_with_tie(self, data: bytes):
+        """The packed-key merge loop (left pair first on ties) and its tie report."""
+        arr = np.frombuffer(data, np.uint8) if len(data) else np.zeros(1, np.uint8)
+        out = np.empty(len(data) + 64, np.int32)
+        tie = C.c_int32(0)
+        L = lib()
+        L.hz_bpe_piece_tie.restype = C.c_int64
+        n = L.hz_bpe_piece_tie(self.h, arr.ctypes.data_as(K.u8p), C.c_int64(len(data)), out.ctypes.data_as(K.i32p), C.byref(tie))
+        return out[:n].tolist(), bool(tie.value)
+
+
 class HostWordpiece:
     def __init__(self, vocab, suffix=b"##", max_bytes=100):
         self._keep = []

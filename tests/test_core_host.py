@@ -87,6 +87,58 @@ def test_bpe_suffix_unk_fallback_tables(oracle_mod):
                     assert h.piece(w, mode) == ids[ob[i]:oe[i]].tolist(), (w, bf, unk, mode)
 
 
+def _tie_vocab(seed):
+    """A vocabulary over {a, b} in which many tokens are the product of several merges: every string up to six
+    characters is a token, the merges are a random selection of (left, right) splits in random order."""
+    import itertools
+    rng = np.random.default_rng(seed)
+    toks = ["".join(t) for n in range(1, 7) for t in itertools.product("ab", repeat=n)]
+    splits = [(t[:k], t[k:]) for t in toks for k in range(1, len(t))]
+    order = rng.permutation(len(splits))[: int(len(splits) * 0.7)]
+    return toks, [splits[i][0] + " " + splits[i][1] for i in order]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_heap_ties_pop_like_std_priority_queue(oracle_mod, seed):
+    """Two merges producing one token let queue entries tie on (rank, seq); the reference then follows libstdc++'s heap layout
+    (src/bpe_tokenizer.cpp:166-183).  bpe_merge_heap restates std::push_heap / std::pop_heap operation for operation and must give the
+    oracle's result (the oracle runs std::priority_queue itself; tests/test_reference_pin.py ties it to the reference's compiled code);
+    the packed loop breaks ties left pair first and must REPORT the tie wherever its result differs."""
+    toks, merges = _tie_vocab(seed)
+    v, mg = pack_strings(toks), pack_strings(merges)
+    o = oracle_mod.BpeOracle(v, mg, None, use_cache=False)
+    h = H.HostBpe(v, mg, None)
+    assert h.info(0) > 0                       # tokens with more than one producing merge: tie_check is on for this vocabulary
+    rng = np.random.default_rng(100 + seed)
+    words = [bytes(rng.choice([97, 98], size=int(rng.integers(2, 48))).astype(np.uint8)) for _ in range(4000)]
+    words += [b"a" * n for n in range(2, 40)] + [b"ab" * n for n in range(1, 24)] + [b"aab" * n for n in range(1, 16)]
+    b, e, c = pack_strings(words)
+    rb = np.arange(len(words), dtype=np.int32)
+    ob, oe, ids = o(rb, rb + 1, b, e, c)
+    differ = 0
+    for i, w in enumerate(words):
+        exp = ids[ob[i]:oe[i]].tolist()
+        assert h.piece(w, 1) == exp, w         # exact, ties included
+        packed, tie = h.piece_packed_with_tie(w)
+        if packed != exp:
+            differ += 1
+            assert tie, w                      # a left-first result that differs from the reference's is always flagged
+    if refops_available():
+        import refops
+        r = refops.bpe(v, mg)                  # the reference's own compiled BPETokenizer on the same pieces
+        rb_, re_, rids = r(rb, rb + 1, b, e, c)
+        assert np.array_equal(rids, ids) and np.array_equal(rb_, ob) and np.array_equal(re_, oe)
+    print(f"seed {seed}: left-first differs from the reference on {differ} of {len(words)} pieces")
+
+
+def refops_available():
+    try:
+        import refops
+        return refops.available()
+    except Exception:
+        return False
+
+
 def test_birth_order_differs_from_position_order(oracle_mod):
     """equal ranks are ordered by push sequence, not by position."""
     vocab = ["u", "v", "q", "p", "X", "XX", "pq"]

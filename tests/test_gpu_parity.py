@@ -244,6 +244,87 @@ def test_regex_split_max_splits(ops, oracle_mod):
             assert np.array_equal(got[k], exp[k])
 
 
+def test_regex_split_legacy_skip_tokens(ops, oracle_mod):
+    """The legacy 9-input form (reference src/regex_split.cpp:98-113, 164-178, 231-238): elements equal to a skip token pass through
+    unsplit.  Checked against the reference's own compiled RegexSplit (one element per row: its stand-in skips tensor has one entry
+    per ROW, :196-197) and, for rows of several elements, against the 7-input oracle with the equal elements flagged."""
+    import refops
+    from oracle import ref
+    from openvino_tokenizers_b200.strings import pack_strings
+    tokens = ["<|endoftext|>", "<s>", "hello world", "a", "...", "  "]
+    tb, te, tc = pack_strings(tokens)
+    rng = np.random.default_rng(5)
+    alpha = ["a", "b", " ", "  ", ".", "<s>", "<|endoftext|>", "hello world", "...", "é", "1"]
+    strings = [t for t in tokens] + ["".join(rng.choice(alpha, size=int(rng.integers(0, 12)))) for _ in range(600)] + ["hello world!", "<s> ", ""]
+    pat = A.GPT2_PATTERN
+    pat_u8 = np.frombuffer(pat.encode(), np.uint8)
+    for behaviour in ("isolate", "remove", "mergedwithprevious"):
+        op = ops.RegexSplit(behaviour)
+        # (i) one element per row, against the reference
+        batch = cases.batch_from_strings(strings)
+        got = op.evaluate([*batch, pat_u8, tb, te, tc])
+        assert len(got) == 5
+        if refops.available():
+            protos = [np.zeros(1, np.int32)] * 4 + [np.zeros(1, np.uint8), pat_u8, np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.uint8)]
+            rop = ref.RefOp("RegexSplit", protos, constants={5: pat_u8, 6: tb, 7: te, 8: tc}, behaviour=behaviour, invert=False, max_splits=-1)
+            exp = rop(*batch, pat_u8, tb, te, tc)
+            for k in range(4):
+                assert np.array_equal(got[k], exp[k]), (behaviour, k)
+        # (ii) several elements per row, against the oracle with the equal elements flagged as skips
+        rb, re_, b, e, c = batch
+        n = len(b)
+        rb2 = np.arange(0, n, 3, dtype=np.int32)
+        re2 = np.minimum(rb2 + 3, n).astype(np.int32)
+        flags = np.array([bytes(c[b[i]:e[i]]).decode() in tokens for i in range(n)], np.uint8)
+        exp2 = oracle_mod.SplitOracle(pat, behaviour)(rb2, re2, b, e, c, flags)
+        got2 = op.evaluate([rb2, re2, b, e, c, pat_u8, tb, te, tc])
+        for k in range(4):
+            assert np.array_equal(got2[k], exp2[k]), (behaviour, "rows of three", k)
+    with pytest.raises(ValueError):
+        ops.RegexSplit("isolate").evaluate([*batch, pat_u8, tb, te])          # 8 inputs
+
+
+def test_bpe_with_doubly_produced_tokens(ops, oracle_mod, gpt2):
+    """A vocabulary in which tokens are the product of more than one merge (tiktoken-derived merge lists are like that; SURVEY App. B
+    item 1): MergeTable::tie_check is on — the fast kernel watches for merges that meet their own product on both sides, and every row
+    it hands back (here: rows with an added token inside the text) is redone through the exact heap form of the loop
+    (std::priority_queue's pop order restated).  Results must equal the oracle's, fused and as separate ops."""
+    a = gpt2["assets"]
+    vocab = list(a.vocab)
+    index = {t: i for i, t in enumerate(vocab)}
+    merges = list(a.merges)
+    have = set(merges)
+    extra = []
+    for l, r in merges[:4000]:
+        t = l + r
+        for k in range(1, len(t)):
+            l2, r2 = t[:k], t[k:]
+            if (l2, r2) not in have and l2 in index and r2 in index:
+                extra.append((l2, r2)); have.add((l2, r2))
+                break
+        if len(extra) >= 300:
+            break
+    assert extra
+    allm = merges + extra
+    v = pack_strings(vocab)
+    ml, mr = pack_strings([m[0] for m in allm]), pack_strings([m[1] for m in allm])
+    _, _, _, ad, aid = a.tensors()
+    consts = [*v, *ml, *mr] + ([*ad, aid] if ad is not None else [])
+    bpe = ops.BPETokenizer().with_constants(consts)
+    o_bpe = oracle_mod.BpeOracle(v, ml, mr, ad, aid, use_cache=False)
+    rng = np.random.default_rng(77)
+    strings = [s.encode() for s in cases.EDGE_STRINGS] + [p.encode() for p in cases.long_prompts()]
+    strings += [bytes(rng.integers(0x20, 0x7F, size=int(n), dtype=np.uint8)) for n in rng.integers(0, 700, size=1500)]
+    strings += [b"aaaa" * 100, b"abab" * 150, b"the the the the " * 40, b"x<|endoftext|>y" * 10]
+    batch = cases.batch_from_strings(strings)
+    sp = gpt2["o_split"](*batch)
+    exp = o_bpe(sp[0], sp[1], sp[2], sp[3], batch[4])
+    got = ops.split_bpe(gpt2["split"], bpe, list(batch))
+    assert cases.ragged_rows_equal(got, exp)
+    got2 = bpe.evaluate([sp[0], sp[1], sp[2], sp[3], batch[4], *consts])       # separate ops: the generic kernel (exact, or an explicit error)
+    assert cases.ragged_rows_equal(got2, exp)
+
+
 def test_regex_split_unknown_pattern_is_an_error(ops):
     for pat in (r"(foo|bar)+baz", r"\bword\b", r"a*?b", r"(?<=x)y", r"\p{Han}+", r"(?=ab)a", r"[[:alpha:]]+", r"(a)\1"):
         with pytest.raises(ops.B200TokError) as ei:         # outside the compiled syntax: refused, never approximated
