@@ -610,7 +610,9 @@ def main():
             db.chars[:n_bytes].copy_(hb[4], non_blocking=True)
             pg.run(pipe, db)
             n_mine = int(pg.n.item())                                   # (one synchronisation: the size of the id copy)
-            ho["ids"][:n_mine].copy_(pg.ids[slot0:slot0 + n_mine], non_blocking=True)
+            # the pull gathers compact rows; the fused emit leaves the rows at their worst-case positions inside the slot: copy its whole extent
+            span = n_mine if getattr(pg, "compact_slots", False) else min(pg.cap, ho["ids"].numel())
+            ho["ids"][:span].copy_(pg.ids[slot0:slot0 + span], non_blocking=True)
             h_gb.copy_(pg.begins, non_blocking=True)
             h_ge.copy_(pg.ends, non_blocking=True)
             torch.cuda.synchronize()
@@ -624,7 +626,7 @@ def main():
         e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_s = float(e2e_s.item()) / args.steps
-        d2h = 4 * n_mine + 8 * g_rows
+        d2h = 4 * (n_mine if getattr(pg, "compact_slots", False) else min(pg.cap, ho["ids"].numel())) + 8 * g_rows
         e2e_path = ("pinned host shard -> H2D -> tokenise + all-gatherv on the devices (the step `value` times) -> D2H of this rank's id slot "
                     "and of all row extents; per-rank bytes")
         n_host = pipe.run_host(hb, ho)       # (restore the plain host-path result for the checks below)

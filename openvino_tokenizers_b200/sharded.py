@@ -88,9 +88,14 @@ class PeerGather:
     """Emit fused with the all-gatherv over NVLink peer memory: the result buffers of every rank live in torch
     symmetric memory; `b200tok_split_bpe_run_sharded` stores this rank's compacted id rows into all of them from inside its
     compaction kernel, and one symmetric-memory barrier on the stream orders the ranks.  Equal shards (rows, capacity) per rank.
-    Result layout = allgather_ragged_slots: rank r's rows in slot r, offsets shifted by r * cap."""
+    Result layout = allgather_ragged_slots: rank r's rows in slot r, offsets shifted by r * cap.
 
-    def __init__(self, rows_per_rank: int, slot_capacity: int, device, group=None, wire16: bool = False, multicast: bool = False):
+    The result buffers are double-buffered (step k uses set k & 1), so ONE barrier per step is enough: a rank overwrites set k & 1
+    again in step k + 2, after it has passed the barrier of step k + 1 — which every peer reaches only when everything it enqueued
+    before it, readers of its step-k result included, has finished.  `begins / ends / ids` are the set of the latest step."""
+
+    def __init__(self, rows_per_rank: int, slot_capacity: int, device, group=None, wire16: bool = False, multicast: bool = False,
+                 double_buffer: bool = True):
         """wire16: ship ids over NVLink as u16 (every id < 65 535) into symmetric staging buffers and widen them locally after the
         barrier — halves the NVLink bytes, worth a few percent from about four ranks on.  multicast: use NVLS multimem.st through the
         switch instead of one store per peer (measured slower than wide unicast stores for this access pattern on B200: off by default)."""
@@ -101,57 +106,69 @@ class PeerGather:
         if self.world > 8:
             raise ValueError("PeerGather supports up to 8 ranks (one NVSwitch domain)")
         self.rows, self.cap, self.wire16, self.device = int(rows_per_rank), int(slot_capacity), bool(wire16), device
-        mk = lambda n, dt=torch.int32: symm.empty(n, dtype=dt, device=device)
-        self.begins, self.ends = mk(self.world * self.rows), mk(self.world * self.rows)
-        if self.wire16:
-            self.ids = torch.empty(self.world * self.cap, dtype=torch.int32, device=device)       # local, filled by the widening pass
-            self.ids16 = mk(self.world * self.cap, torch.int16)
-            syms = (self.ids16, self.begins, self.ends)
-        else:
-            self.ids = mk(self.world * self.cap)
-            syms = (self.ids, self.begins, self.ends)
-        self._h = [symm.rendezvous(t, self.group) for t in syms]
         self.n = torch.zeros(1, dtype=torch.int64, device=device)
-        po = K.PeerOut()
-        po.world, po.rank, po.slot_capacity, po.rows_per_rank, po.wire16 = self.world, self.rank, self.cap, self.rows, int(self.wire16)
-        for p in range(self.world):
-            if self.wire16:
-                po.ids16[p] = int(self._h[0].buffer_ptrs[p])
-                po.ids[p] = self.ids.data_ptr() if p == self.rank else None
-            else:
-                po.ids[p] = int(self._h[0].buffer_ptrs[p])
-            po.begins[p], po.ends[p] = int(self._h[1].buffer_ptrs[p]), int(self._h[2].buffer_ptrs[p])
         self.multicast = False
-        if multicast and not self.wire16 and self.world > 1:      # NVLS: one store through the switch reaches every rank's copy
-            try:
-                mc = [int(h.multicast_ptr) for h in self._h]
-                if all(mc):
-                    po.ids_mc, po.begins_mc, po.ends_mc = mc
-                    self.multicast = True
-            except Exception:
-                pass
-        self._po = po
+        self.step = 0
+        self._sets = []
+        mk = lambda n, dt=torch.int32: symm.empty(n, dtype=dt, device=device)
+        for _ in range(2 if (double_buffer and self.world > 1) else 1):
+            begins, ends = mk(self.world * self.rows), mk(self.world * self.rows)
+            if self.wire16:
+                ids = torch.empty(self.world * self.cap, dtype=torch.int32, device=device)       # local, filled by the widening pass
+                ids16 = mk(self.world * self.cap, torch.int16)
+                syms = (ids16, begins, ends)
+            else:
+                ids = mk(self.world * self.cap)
+                ids16 = None
+                syms = (ids, begins, ends)
+            h = [symm.rendezvous(t, self.group) for t in syms]
+            po = K.PeerOut()
+            po.world, po.rank, po.slot_capacity, po.rows_per_rank, po.wire16 = self.world, self.rank, self.cap, self.rows, int(self.wire16)
+            for p in range(self.world):
+                if self.wire16:
+                    po.ids16[p] = int(h[0].buffer_ptrs[p])
+                    po.ids[p] = ids.data_ptr() if p == self.rank else None
+                else:
+                    po.ids[p] = int(h[0].buffer_ptrs[p])
+                po.begins[p], po.ends[p] = int(h[1].buffer_ptrs[p]), int(h[2].buffer_ptrs[p])
+            if multicast and not self.wire16 and self.world > 1:      # NVLS: one store through the switch reaches every rank's copy
+                try:
+                    mc = [int(x.multicast_ptr) for x in h]
+                    if all(mc):
+                        po.ids_mc, po.begins_mc, po.ends_mc = mc
+                        self.multicast = True
+                except Exception:
+                    pass
+            self._sets.append(dict(begins=begins, ends=ends, ids=ids, ids16=ids16, h=h, po=po))
+        self._cur = self._sets[0]
+
+    begins = property(lambda self: self._cur["begins"])
+    ends = property(lambda self: self._cur["ends"])
+    ids = property(lambda self: self._cur["ids"])
 
     def run(self, pipe, db):
         """pipe: runtime.TokenizerPipeline (BPE or WordPiece); db: runtime.DeviceBatch of this rank's shard.  Asynchronous on the current
         torch stream up to the barrier; returns (begins, ends, ids) views of this rank's copy of the gathered result."""
         import ctypes as C
         from . import _capi as K
+        cur = self._cur = self._sets[self.step % len(self._sets)]
+        self.step += 1
         rin = K.RaggedStrings(db.rb.data_ptr(), db.re.data_ptr(), db.n_rows, db.begins.data_ptr(), db.ends.data_ptr(), db.n_elems,
                               db.chars.data_ptr(), db.n_chars, None, K.MEM_DEVICE)
-        self._h[0].barrier(channel=1)   # nobody still reads the previous result (readers are ordered before this on their streams)
+        if len(self._sets) == 1:
+            cur["h"][0].barrier(channel=1)   # nobody still reads the previous result (readers are ordered before this on their streams)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if pipe.kind == "bpe":
-            K.check(K.lib().b200tok_split_bpe_run_sharded(pipe.split1.handle, pipe.tok.handle, C.byref(rin), C.byref(self._po),
+            K.check(K.lib().b200tok_split_bpe_run_sharded(pipe.split1.handle, pipe.tok.handle, C.byref(rin), C.byref(cur["po"]),
                                                           C.c_void_p(self.n.data_ptr()), st))
         else:
             K.check(K.lib().b200tok_split_wordpiece_run_sharded(pipe.split1.handle, pipe.split2.handle, pipe.tok.handle, C.byref(rin),
-                                                                C.c_int32(pipe.unk), C.byref(self._po), C.c_void_p(self.n.data_ptr()), st))
-        self._h[0].barrier(channel=0)   # every rank's stores into my buffers are complete and visible after this
+                                                                C.c_int32(pipe.unk), C.byref(cur["po"]), C.c_void_p(self.n.data_ptr()), st))
+        cur["h"][0].barrier(channel=0)   # every rank's stores into my buffers are complete and visible after this
         if self.wire16:
             dev_index = self.device.index if isinstance(self.device, torch.device) else int(self.device)
-            K.check(K.lib().b200tok_peer_expand_run(int(dev_index or 0), C.byref(self._po), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return self.begins, self.ends, self.ids
+            K.check(K.lib().b200tok_peer_expand_run(int(dev_index or 0), C.byref(cur["po"]), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return cur["begins"], cur["ends"], cur["ids"]
 
 
 class PullGather:
@@ -185,6 +202,7 @@ class PullGather:
         self.ends = torch.empty(W * R, dtype=torch.int32, device=device)
         self.step = 0
         self.multicast = False
+        self.compact_slots = True          # every slot holds its rank's rows back to back
         self._pull = []
         esz = 2 if self.wire16 else 4
         for par in (0, 1):
