@@ -501,10 +501,7 @@ int run_rows_host_pipelined(b200tok_object* owner, const RowCall& call, const b2
     if (N < (8 << 20) || B < 1024 || E > 4 * B + 1024 || in->skips || (call.split && call.split->has_skip_tokens)) return 1;
     // qualify: rows contiguous, elements increasing and non-overlapping (what StringTensorUnpack / RegexSplit produce)
     const int32_t *rb = in->ragged_begins, *re = in->ragged_ends, *eb = in->begins, *ee = in->ends;
-    if (rb[0] != 0 || re[B - 1] != E) return 1;
-    for (int64_t r = 0; r + 1 < B; ++r) if (rb[r + 1] != re[r] || re[r] < rb[r]) return 1;
-    if (re[B - 1] < rb[B - 1]) return 1;
-    for (int64_t p = 0; p < E; ++p) if (eb[p] < 0 || ee[p] < eb[p] || ee[p] > N || (p + 1 < E && eb[p + 1] < ee[p])) return 1;
+    if (!contiguous_batch(rb, re, eb, ee, B, E, N)) return 1;
     // chunk plan (MiB of text per chunk; the last entry repeats): small first chunks so the D2H stream starts early,
     // then sizes that keep the kernels efficient while compute stays ahead of the copy engine
     static const std::vector<double> plan = [] {

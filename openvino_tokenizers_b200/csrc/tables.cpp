@@ -338,6 +338,29 @@ void HostTrie::build_rank() {
     if (value.size() >= (1u << 24) - 2) rank_jump.clear();      // (values must fit 24 bits; never the case for a tokenizer vocabulary)
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2")))
+#endif
+static bool contiguous_batch_impl(const int32_t* __restrict rb, const int32_t* __restrict re, const int32_t* __restrict eb,
+                                  const int32_t* __restrict ee, int64_t B, int64_t E, int32_t n) {
+    int acc = 0;
+    for (int64_t r = 0; r + 1 < B; ++r) acc |= (rb[r + 1] != re[r]) | (re[r] < rb[r]);
+    for (int64_t p = 0; p < E; ++p) acc |= (eb[p] < 0) | (ee[p] < eb[p]) | (ee[p] > n);
+    for (int64_t p = 0; p + 1 < E; ++p) acc |= (eb[p + 1] < ee[p]);
+    return acc == 0;
+}
+bool contiguous_batch(const int32_t* rb, const int32_t* re, const int32_t* eb, const int32_t* ee, int64_t B, int64_t E, int64_t N) {
+    if (B <= 0 || N >= (1ll << 31) || rb[0] != 0 || re[B - 1] != E || re[B - 1] < rb[B - 1]) return false;
+#if defined(__x86_64__) && defined(__GNUC__)
+    if (!__builtin_cpu_supports("avx2")) {           // same predicate, baseline instruction set
+        for (int64_t r = 0; r + 1 < B; ++r) if (rb[r + 1] != re[r] || re[r] < rb[r]) return false;
+        for (int64_t p = 0; p < E; ++p) if (eb[p] < 0 || ee[p] < eb[p] || ee[p] > N || (p + 1 < E && eb[p + 1] < ee[p])) return false;
+        return true;
+    }
+#endif
+    return contiguous_batch_impl(rb, re, eb, ee, B, E, (int32_t)N);
+}
+
 static std::string str_at(const b200tok_strings& s, int64_t i) {
     return std::string((const char*)s.chars + s.begins[i], (const char*)s.chars + s.ends[i]);
 }

@@ -81,6 +81,11 @@ struct HostVocabEnc {
 };
 int build_vocabenc(const b200tok_vocabenc_desc& d, HostVocabEnc& out, std::string& err);
 
+// Host-buffer fast path qualification: rows contiguous (rb[0] == 0, rb[r + 1] == re[r], re[B - 1] == E), elements inside [0, N],
+// increasing and non-overlapping — what StringTensorUnpack / RegexSplit produce.  Branch-free so that the compiler vectorises it
+// (the early-exit form cost 0.19 ms per 65 536-row call, 7 % of the whole host-to-host C1 call).
+bool contiguous_batch(const int32_t* rb, const int32_t* re, const int32_t* eb, const int32_t* ee, int64_t B, int64_t E, int64_t N);
+
 // General split patterns: program of the regex machine (regex_vm.cuh), compiled by regex_compile.cpp.
 struct HostVm {
     std::vector<VmInst> code;

@@ -37,6 +37,10 @@ HZ int64_t hz_split(const char* pattern, int64_t plen, const char* behaviour, in
     return k;
 }
 
+HZ int hz_contiguous_batch(const int32_t* rb, const int32_t* re, const int32_t* eb, const int32_t* ee, int64_t B, int64_t E, int64_t N) {
+    return contiguous_batch(rb, re, eb, ee, B, E, N) ? 1 : 0;
+}
+
 struct HzBpe { HostBpe t; };
 HZ void* hz_bpe_create(const b200tok_bpe_desc* d) {
     auto h = std::make_unique<HzBpe>();

@@ -272,3 +272,44 @@ def test_llama3_word_form_equals_pcre2(oracle_mod):
             got = H.llama3_word_form(s.encode())
             if got is not None:      # (None: a non-ASCII digit — such rows go to the generic kernel)
                 assert got == _oracle_split(o, s.encode()), s[:40]
+
+
+def test_contiguous_batch_predicate():
+    """tables.cpp contiguous_batch (the qualification of the pipelined host-buffer path, vectorised) against the plain predicate."""
+    import ctypes as C
+    L = H.lib()
+    i32p = C.POINTER(C.c_int32)
+
+    def plain(rb, re_, eb, ee, N):
+        B, E = len(rb), len(eb)
+        if rb[0] != 0 or re_[B - 1] != E or re_[B - 1] < rb[B - 1]:
+            return False
+        if np.any(rb[1:] != re_[:-1]) or np.any(re_[:-1] < rb[:-1]):
+            return False
+        return not (np.any(eb < 0) or np.any(ee < eb) or np.any(ee > N) or np.any(eb[1:] < ee[:-1]))
+
+    def got(rb, re_, eb, ee, N):
+        a = [np.ascontiguousarray(x, np.int32) for x in (rb, re_, eb, ee)]
+        return bool(L.hz_contiguous_batch(*(x.ctypes.data_as(i32p) for x in a), C.c_int64(len(rb)), C.c_int64(len(eb)), C.c_int64(N)))
+
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        B = int(rng.integers(1, 70))
+        per = rng.integers(0, 4, size=B)                       # elements per row (rows may be empty)
+        E = int(per.sum())
+        re_ = np.cumsum(per).astype(np.int32)
+        rb = (re_ - per).astype(np.int32)
+        lens = rng.integers(0, 9, size=E)
+        gaps = rng.integers(0, 3, size=E)                      # gaps between elements are fine
+        eb = (np.cumsum(lens + gaps) - lens).astype(np.int32)
+        ee = (eb + lens).astype(np.int32)
+        N = int(ee[-1]) + int(rng.integers(0, 5)) if E else int(rng.integers(0, 5))
+        assert got(rb, re_, eb, ee, N) == plain(rb, re_, eb, ee, N) == True
+        if E == 0:
+            continue
+        for _ in range(6):                                     # one perturbation at a time: both must agree (mostly: reject)
+            arrs = [rb.copy(), re_.copy(), eb.copy(), ee.copy()]
+            k = int(rng.integers(0, 4))
+            i = int(rng.integers(0, len(arrs[k])))
+            arrs[k][i] += int(rng.choice([-9, -1, 1, 9, 1000]))
+            assert got(*arrs, N) == plain(*arrs, N), (trial, k, i)
