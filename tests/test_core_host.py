@@ -169,6 +169,38 @@ def test_wordpiece_word_equals_oracle(oracle_mod):
         assert h.word(w, a.unk_token_id) == ids[ob[i]:oe[i]].tolist(), w
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_wordpiece_jump_tables_on_random_vocabularies(oracle_mod, seed):
+    """The walks start from val1 / the two-byte jump table (tok_core.cuh rank_trie_longest): random vocabularies over a small alphabet
+    that includes non-ASCII bytes (which must fall back to the root lookup), with and without one-, two- and three-byte tokens, every
+    word up to four bytes exhaustively plus random longer ones, against the oracle and the reference's compiled WordpieceTokenizer."""
+    import itertools
+    rng = np.random.default_rng(seed)
+    alpha = [b"a", b"b", b"c", b"\xc3", b"\xa9", b"1"]
+    pool = [b"".join(t) for n in range(1, 5) for t in itertools.product(alpha, repeat=n)]
+    keep = rng.random(len(pool)) < [0.9, 0.5, 0.25, 0.1][seed]
+    root = [t for t, k in zip(pool, keep) if k]
+    keep2 = rng.random(len(pool)) < 0.35
+    sub = [b"##" + t for t, k in zip(pool, keep2) if k]
+    vocab = [b"[UNK]"] + root + sub
+    rng.shuffle(vocab)
+    unk = vocab.index(b"[UNK]")
+    v = pack_strings(vocab)
+    o = oracle_mod.WordpieceOracle(v, b"##", 100)
+    h = H.HostWordpiece(v, b"##", 100)
+    words = pool + [b"".join(rng.choice(alpha, size=int(rng.integers(5, 14)))) for _ in range(1500)]
+    b, e, c = pack_strings(words)
+    rb = np.arange(len(words), dtype=np.int32)
+    ob, oe, ids = o(rb, rb + 1, b, e, c, unk)
+    for i, w in enumerate(words):
+        assert h.word(w, unk) == ids[ob[i]:oe[i]].tolist(), w
+    if refops_available():
+        import refops
+        r = refops.wordpiece(v, unk, b"##", 100)
+        rb_, re_, rids = r(rb, rb + 1, b, e, c)
+        assert np.array_equal(rids, ids) and np.array_equal(rb_, ob) and np.array_equal(re_, oe)
+
+
 def test_class_table_spot_checks():
     L, N, S, P, W, BP, NL = 1, 2, 4, 8, 16, 32, 64
     assert H.lib().hz_char_class(ord("a")) & L
