@@ -82,6 +82,23 @@ def test_loading_a_chain_fuses_split_and_tokenizer():
     assert G.producer_type(G.layer("BPETokenizer", params + [G.constant(x) for x in consts])[0]) == "BPETokenizer"
 
 
+def test_legacy_nine_input_regex_split_loads_and_stays_a_layer_of_its_own():
+    """The legacy RegexSplit form (reference src/regex_split.cpp:98-113: pattern at input 5, skip-token strings at 6..8, five outputs)
+    is accepted by the shim's validate_and_infer_types, 8 inputs are not, and the load-time fusion leaves such a splitter alone."""
+    a = A.load_bpe("gpt2_synth")
+    G = shimlib.ShimGraph()
+    params = [G.parameter(x) for x in [I32, I32, I32, I32, U8]]
+    toks = pack_strings(["<|endoftext|>", "<s>"])
+    rs = G.layer("RegexSplit", params + [G.constant(a.split_pattern.encode())] + [G.constant(x) for x in toks], behaviour="isolate", invert=False, max_splits=-1)
+    assert len(rs) == 5 and G.producer_type(rs[0]) == "RegexSplit"
+    v, ml, mr, ad, aid = a.tensors()
+    consts = [*v, *ml, *mr] + ([*ad, np.asarray(aid, np.int32)] if ad is not None else [])
+    out = G.layer("BPETokenizer", rs[:5] + [G.constant(x) for x in consts])
+    assert G.producer_type(out[0]) == "BPETokenizer"
+    with pytest.raises(RuntimeError):
+        G.layer("RegexSplit", params + [G.constant(a.split_pattern.encode())] + [G.constant(x) for x in toks[:2]], behaviour="isolate", invert=False, max_splits=-1)
+
+
 def test_fusion_can_be_switched_off():
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "import shimlib, test_ov_shim as T\nfrom openvino_tokenizers_b200 import assets as A\n"
