@@ -77,3 +77,25 @@ def test_ctypes_mirrors_match_the_header_layout(K, tmp_path):
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     for (cname, ct), n in zip(pairs, sizes):
         assert C.sizeof(ct) == n, (cname, C.sizeof(ct), n)
+
+
+def test_peer_pull_and_pack_reject_bad_layouts_before_touching_a_device(K):
+    """Argument errors of the all-gatherv-by-pull entry points come back as B200TOK_E_INVALID with a message, GPU or not."""
+    lib = K.lib()
+    buf = np.zeros(64, np.int32)
+    q = K.PeerPull()
+    q.world, q.rank, q.wire16, q.skip_self_ids, q.slot_capacity, q.rows_per_rank = 2, 0, 1, 1, 16, 4
+    q.ids = q.begins = q.ends = buf.ctypes.data
+    assert lib.b200tok_peer_pull_run(0, C.byref(q), None) == K.E_INVALID and b"missing source buffer" in lib.b200tok_last_error()
+    q.slot_capacity = 12                                        # not a multiple of 8
+    assert lib.b200tok_peer_pull_run(0, C.byref(q), None) == K.E_INVALID and b"multiple of 8" in lib.b200tok_last_error()
+    q.slot_capacity, q.world = 16, 9
+    assert lib.b200tok_peer_pull_run(0, C.byref(q), None) == K.E_INVALID
+    q.world, q.rank = 2, 2
+    assert lib.b200tok_peer_pull_run(0, C.byref(q), None) == K.E_INVALID
+    assert lib.b200tok_peer_pull_run(0, None, None) == K.E_INVALID
+    assert lib.b200tok_peer_pack_run(0, None, None, C.c_int64(16), None, None) == K.E_INVALID
+    assert lib.b200tok_peer_pack_run(0, C.c_void_p(buf.ctypes.data + 4), C.c_void_p(buf.ctypes.data), C.c_int64(16), C.c_void_p(buf.ctypes.data), None) == K.E_INVALID
+    assert b"16-byte aligned" in lib.b200tok_last_error()
+    st = K.make_strings((np.zeros(1, np.int32), np.ones(1, np.int32), b"x"), [])
+    assert lib.b200tok_regexsplit_set_skip_tokens(None, C.byref(st)) == K.E_INVALID
